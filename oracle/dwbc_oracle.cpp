@@ -1,0 +1,940 @@
+// TEST INFRASTRUCTURE -- CPU oracle for the batched whole-body-control hot path.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` leg may
+// load the library built from this file (oracle/build/liboracle.so).  The product
+// (libdwbc_b200/csrc) never links, includes or calls anything in oracle/.
+//
+// This is a plain, single-state, FP64 restatement of the reference's per-control-cycle path,
+// following the reference AS WRITTEN (same products, LU inverses, COD pseudo-inverse):
+//   UpdateKinematics             reference src/dwbc.cpp:279-371   (+ RBDL FK / CRBA / RNEA restated
+//                                from Featherstone, "Rigid Body Dynamics Algorithms", ch. 5-6;
+//                                RBDL = saga0619/rbdl-orb fork, unpinned, not available offline)
+//   SetContact / UpdateContactConstraint   include/dwbc.h:432-474, src/dwbc.cpp:433-454,
+//                                src/contact_constraint.cpp:51-77
+//   CalcContactConstraint        src/dwbc.cpp:456-478 -> src/wbd.cpp:108-143, 32-53
+//   CalcGravCompensation         src/dwbc.cpp:875-889 -> src/wbd.cpp:186-192
+//   SetTaskSpace/UpdateTaskSpace/CalcTaskSpace   src/dwbc.cpp:662-816, src/task.cpp:90-93,202-211,
+//                                src/wbd.cpp:207-213,257-261
+//   CalcTaskControlTorque / CalcSingleTaskTorqueWithQP   src/dwbc.cpp:818-873, 941-1127
+//   CalcContactRedistribute      src/dwbc.cpp:1372-1568
+// Parity is pinned by the reference's golden vectors tests/cases/{1,2} (tests/test_oracle_golden.py).
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+
+#include "linalg.hpp"
+#include "qp.hpp"
+
+#include <atomic>
+#include <thread>
+
+namespace orc {
+
+struct V3 {
+    double x = 0, y = 0, z = 0;
+};
+static inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+static inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+static inline V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+static inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+struct M3 {
+    double m[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+};
+static inline M3 eye3() {
+    M3 r;
+    r.m[0][0] = r.m[1][1] = r.m[2][2] = 1;
+    return r;
+}
+static inline M3 mul(const M3 &a, const M3 &b) {
+    M3 r;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) r.m[i][j] = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j] + a.m[i][2] * b.m[2][j];
+    return r;
+}
+static inline M3 tr(const M3 &a) {
+    M3 r;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) r.m[i][j] = a.m[j][i];
+    return r;
+}
+static inline V3 mul(const M3 &a, V3 v) {
+    return {a.m[0][0] * v.x + a.m[0][1] * v.y + a.m[0][2] * v.z, a.m[1][0] * v.x + a.m[1][1] * v.y + a.m[1][2] * v.z,
+            a.m[2][0] * v.x + a.m[2][1] * v.y + a.m[2][2] * v.z};
+}
+static inline M3 skew3(V3 v) {
+    M3 r;
+    r.m[0][1] = -v.z; r.m[0][2] = v.y;
+    r.m[1][0] = v.z;  r.m[1][2] = -v.x;
+    r.m[2][0] = -v.y; r.m[2][1] = v.x;
+    return r;
+}
+static inline M3 axis_rot(V3 a, double th) {
+    double n = std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z);
+    a = (1.0 / n) * a;
+    M3 K = skew3(a), K2 = mul(K, K), R = eye3();
+    double s = std::sin(th), c = 1 - std::cos(th);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) R.m[i][j] += s * K.m[i][j] + c * K2.m[i][j];
+    return R;
+}
+static inline M3 quat_rot(double x, double y, double z, double w) {
+    M3 R;
+    R.m[0][0] = 1 - 2 * (y * y + z * z); R.m[0][1] = 2 * (x * y - z * w);     R.m[0][2] = 2 * (x * z + y * w);
+    R.m[1][0] = 2 * (x * y + z * w);     R.m[1][1] = 1 - 2 * (x * x + z * z); R.m[1][2] = 2 * (y * z - x * w);
+    R.m[2][0] = 2 * (x * z - y * w);     R.m[2][1] = 2 * (y * z + x * w);     R.m[2][2] = 1 - 2 * (x * x + y * y);
+    return R;
+}
+
+// 6x6 helpers on spatial quantities ordered [angular; linear] (Featherstone).
+struct M6 {
+    double m[6][6];
+    M6() { std::memset(m, 0, sizeof(m)); }
+};
+struct V6 {
+    double v[6] = {0, 0, 0, 0, 0, 0};
+};
+static inline V6 mul(const M6 &a, const V6 &x) {
+    V6 r;
+    for (int i = 0; i < 6; i++) {
+        double s = 0;
+        for (int j = 0; j < 6; j++) s += a.m[i][j] * x.v[j];
+        r.v[i] = s;
+    }
+    return r;
+}
+static inline V6 mulT(const M6 &a, const V6 &x) {
+    V6 r;
+    for (int i = 0; i < 6; i++) {
+        double s = 0;
+        for (int j = 0; j < 6; j++) s += a.m[j][i] * x.v[j];
+        r.v[i] = s;
+    }
+    return r;
+}
+static inline M6 mul(const M6 &a, const M6 &b) {
+    M6 r;
+    for (int i = 0; i < 6; i++)
+        for (int k = 0; k < 6; k++) {
+            double aik = a.m[i][k];
+            if (aik == 0) continue;
+            for (int j = 0; j < 6; j++) r.m[i][j] += aik * b.m[k][j];
+        }
+    return r;
+}
+static inline M6 tr(const M6 &a) {
+    M6 r;
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) r.m[i][j] = a.m[j][i];
+    return r;
+}
+// motion transform parent -> child; R = rotation child->parent, r = child origin in parent coords
+static inline M6 xform(const M3 &R, V3 r) {
+    M6 X;
+    M3 Rt = tr(R), Rr = mul(Rt, skew3(r));
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            X.m[i][j] = Rt.m[i][j];
+            X.m[3 + i][3 + j] = Rt.m[i][j];
+            X.m[3 + i][j] = -Rr.m[i][j];
+        }
+    return X;
+}
+static inline M6 spatial_inertia(double mass, V3 c, const M3 &Ic) {
+    M6 I;
+    M3 cx = skew3(c), cxcx = mul(cx, cx);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            I.m[i][j] = Ic.m[i][j] - mass * cxcx.m[i][j];
+            I.m[i][3 + j] = mass * cx.m[i][j];
+            I.m[3 + i][j] = -mass * cx.m[i][j];
+        }
+    for (int i = 0; i < 3; i++) I.m[3 + i][3 + i] = mass;
+    return I;
+}
+static inline V6 crm(const V6 &v, const V6 &u) {  // v x u (motion)
+    V3 w{v.v[0], v.v[1], v.v[2]}, vl{v.v[3], v.v[4], v.v[5]}, uw{u.v[0], u.v[1], u.v[2]}, ul{u.v[3], u.v[4], u.v[5]};
+    V3 a = cross(w, uw), b = cross(w, ul) + cross(vl, uw);
+    V6 r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = b.x; r.v[4] = b.y; r.v[5] = b.z;
+    return r;
+}
+static inline V6 crf(const V6 &v, const V6 &f) {  // v x* f (force)
+    V3 w{v.v[0], v.v[1], v.v[2]}, vl{v.v[3], v.v[4], v.v[5]}, n{f.v[0], f.v[1], f.v[2]}, fl{f.v[3], f.v[4], f.v[5]};
+    V3 a = cross(w, n) + cross(vl, fl), b = cross(w, fl);
+    V6 r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = b.x; r.v[4] = b.y; r.v[5] = b.z;
+    return r;
+}
+
+enum { TASK_LINK_6D = 0, TASK_LINK_6D_COM_FRAME, TASK_LINK_6D_CUSTOM_FRAME, TASK_LINK_POSITION, TASK_LINK_POSITION_COM_FRAME,
+       TASK_LINK_POSITION_CUSTOM_FRAME, TASK_LINK_ROTATION, TASK_LINK_ROTATION_CUSTOM_FRAME };
+static const double INFTY = 1.0e20;  // qpOASES INFTY, confirmed by the golden lbA*mat
+static const double COD_THRESHOLD = 1.0e-6;  // reference include/dwbc_wbd.h:10
+
+struct Contact {
+    int link = 0;
+    V3 point, normal;
+    double lx = 0, ly = 0, mu = 0.2, muz = 0.2;  // reference src/contact_constraint.cpp:42
+    bool on = false;
+    Mat J;    // 6 x n, rows [linear; angular]
+    M3 rotm;  // world <- link
+    V3 xc;
+};
+struct TaskLink {
+    int mode = 0, link = 0, dof = 0;
+    V3 point;
+};
+struct Task {
+    bool custom = false;
+    int dof = 0;
+    std::vector<TaskLink> links;
+    Mat J, Lambda, Jkt, Null, fstar, fstar_qp, contact_qp, torque_h;
+    Mat qpA, qpub;  // last assembled QP (parity with the golden A*mat / ubA*mat)
+    std::vector<int> active;
+    int qp_status = 0, prox_iters = 0;
+};
+
+struct Robot {
+    // model
+    int nb = 0, n = 0, m = 0;
+    std::vector<int> parent;
+    std::vector<M3> E_T, inertia;
+    std::vector<V3> r_T, axis, com;
+    std::vector<double> mass;
+    double total_mass = 0;
+    // configuration
+    std::vector<Contact> cc;
+    std::vector<Task> ts;
+    bool tlim_set = false;
+    Mat tlim;
+    // state
+    std::vector<double> q, qd;
+    std::vector<M3> Rw;      // world <- body
+    std::vector<V3> pw;      // body origin, world
+    std::vector<M6> Xl;      // parent -> body motion transform
+    std::vector<V6> vel;     // spatial velocity, body coords
+    Mat A, A_inv, B, G, CMM, J_com, J_C, Lambda_c, J_C_INV_T, N_C, A_inv_N_C, W, W_inv, V2, NwJw, P_C;
+    Mat torque_grav, torque_task, torque_contact, cf_redis_qp, redisA, redisub;
+    V3 com_pos;
+    int contact_dof = 0, contact_links = 0, contact_ok = 0, redis_status = 0;
+    std::vector<int> redis_active;
+
+    void update_kinematics(const double *q_, const double *qd_);
+    Mat point_jac(int body, V3 pl) const;
+    void set_contact(const unsigned char *flags);
+    int calc_contact_constraint();
+    void calc_grav();
+    void update_task_space();
+    void calc_task_space();
+    int calc_task_torque(bool hqp);
+    int single_task_qp(Task &t, const Mat &null_prev, const Mat &torque_prev);
+    int calc_redistribute(bool hqp);
+    void contact_const(Mat &A_const, Mat &A_rot, int &csize) const;
+};
+
+void Robot::update_kinematics(const double *q_, const double *qd_) {
+    q.assign(q_, q_ + n + 1);
+    qd.assign(qd_, qd_ + n);
+    Rw.assign(nb, M3());
+    pw.assign(nb, V3());
+    Xl.assign(nb, M6());
+    vel.assign(nb, V6());
+    std::vector<M6> Ic(nb);
+    // --- FK (RBDL UpdateKinematicsCustom), reference src/dwbc.cpp:304 ---
+    Rw[0] = quat_rot(q[3], q[4], q[5], q[n]);
+    pw[0] = {q[0], q[1], q[2]};
+    Xl[0] = xform(Rw[0], V3());
+    {
+        V3 vb = mul(tr(Rw[0]), V3{qd[0], qd[1], qd[2]});
+        vel[0].v[0] = qd[3]; vel[0].v[1] = qd[4]; vel[0].v[2] = qd[5];
+        vel[0].v[3] = vb.x; vel[0].v[4] = vb.y; vel[0].v[5] = vb.z;
+    }
+    for (int i = 1; i < nb; i++) {
+        int l = parent[i];
+        M3 Rj = mul(E_T[i], axis_rot(axis[i], q[5 + i]));
+        Rw[i] = mul(Rw[l], Rj);
+        pw[i] = pw[l] + mul(Rw[l], r_T[i]);
+        Xl[i] = xform(Rj, r_T[i]);
+        V6 vp = mul(Xl[i], vel[l]);
+        vp.v[0] += axis[i].x * qd[5 + i]; vp.v[1] += axis[i].y * qd[5 + i]; vp.v[2] += axis[i].z * qd[5 + i];
+        vel[i] = vp;
+    }
+    // --- CRBA (RBDL CompositeRigidBodyAlgorithm), reference src/dwbc.cpp:305 ---
+    for (int i = 0; i < nb; i++) Ic[i] = spatial_inertia(mass[i], com[i], inertia[i]);
+    for (int i = nb - 1; i >= 1; i--) {
+        M6 t = mul(tr(Xl[i]), mul(Ic[i], Xl[i]));
+        M6 &P = Ic[parent[i]];
+        for (int a = 0; a < 6; a++)
+            for (int b = 0; b < 6; b++) P.m[a][b] += t.m[a][b];
+    }
+    A.set_zero(n, n);
+    M6 S0;  // base motion subspace in body-0 coordinates; columns: v_world (3), omega_body (3)
+    {
+        M3 Rt = tr(Rw[0]);
+        for (int i = 0; i < 3; i++)
+            for (int k = 0; k < 3; k++) S0.m[3 + i][k] = Rt.m[i][k];
+        for (int k = 0; k < 3; k++) S0.m[k][3 + k] = 1.0;
+    }
+    for (int i = nb - 1; i >= 1; i--) {
+        V6 S;
+        S.v[0] = axis[i].x; S.v[1] = axis[i].y; S.v[2] = axis[i].z;
+        V6 F = mul(Ic[i], S);
+        A(5 + i, 5 + i) = S.v[0] * F.v[0] + S.v[1] * F.v[1] + S.v[2] * F.v[2];
+        int j = i;
+        while (j > 0) {
+            F = mulT(Xl[j], F);
+            j = parent[j];
+            if (j > 0) {
+                double v = axis[j].x * F.v[0] + axis[j].y * F.v[1] + axis[j].z * F.v[2];
+                A(5 + i, 5 + j) = v;
+                A(5 + j, 5 + i) = v;
+            } else {
+                V6 b = mulT(S0, F);
+                for (int k = 0; k < 6; k++) A(5 + i, k) = A(k, 5 + i) = b.v[k];
+            }
+        }
+    }
+    {
+        M6 t = mul(tr(S0), mul(Ic[0], S0));
+        for (int a = 0; a < 6; a++)
+            for (int b = 0; b < 6; b++) A(a, b) = t.m[a][b];
+    }
+    // A_inv_ = A_.llt().solve(I), reference src/dwbc.cpp:307
+    llt_solve_identity(A, A_inv);
+
+    // COM position from A_, reference src/dwbc.cpp:320-324
+    M3 A30;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) A30.m[i][j] = A(3 + i, j) / total_mass;
+    M3 skm = mul(Rw[0], A30);
+    V3 cfp{skm.m[2][1], skm.m[0][2], skm.m[1][0]};
+    com_pos = cfp + pw[0];
+    // CMM_ = cm_rot6 * A_.topRows(6), reference src/dwbc.cpp:331-340
+    Mat cm = Mat::identity(6);
+    M3 skt = tr(skew3(cfp));
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            cm(3 + i, 3 + j) = Rw[0].m[i][j];
+            cm(3 + i, j) = skt.m[i][j];
+        }
+    CMM = cm * A.top_rows(6);
+    // B_ = NonlinearEffects (RNEA with qddot = 0, gravity (0,0,-9.81)), reference src/dwbc.cpp:343-344
+    {
+        std::vector<V6> acc(nb), f(nb);
+        V6 aT;
+        aT.v[5] = 9.81;
+        V6 vJ0;
+        vJ0.v[0] = qd[3]; vJ0.v[1] = qd[4]; vJ0.v[2] = qd[5];
+        V6 a0 = mul(Xl[0], aT), c0 = crm(vel[0], vJ0);
+        for (int k = 0; k < 6; k++) a0.v[k] += c0.v[k];
+        acc[0] = a0;
+        for (int i = 1; i < nb; i++) {
+            V6 vJ;
+            vJ.v[0] = axis[i].x * qd[5 + i]; vJ.v[1] = axis[i].y * qd[5 + i]; vJ.v[2] = axis[i].z * qd[5 + i];
+            V6 a = mul(Xl[i], acc[parent[i]]), c = crm(vel[i], vJ);
+            for (int k = 0; k < 6; k++) a.v[k] += c.v[k];
+            acc[i] = a;
+        }
+        for (int i = 0; i < nb; i++) {
+            M6 I = spatial_inertia(mass[i], com[i], inertia[i]);
+            V6 Ia = mul(I, acc[i]), Iv = mul(I, vel[i]), c = crf(vel[i], Iv);
+            for (int k = 0; k < 6; k++) f[i].v[k] = Ia.v[k] + c.v[k];
+        }
+        B.set_zero(n, 1);
+        for (int i = nb - 1; i >= 1; i--) {
+            B[5 + i] = axis[i].x * f[i].v[0] + axis[i].y * f[i].v[1] + axis[i].z * f[i].v[2];
+            V6 fp = mulT(Xl[i], f[i]);
+            for (int k = 0; k < 6; k++) f[parent[i]].v[k] += fp.v[k];
+        }
+        V6 fb = mulT(S0, f[0]);
+        for (int k = 0; k < 6; k++) B[k] = fb.v[k];
+    }
+    // COM inertia, SI_body_, COM Jacobian, G_, reference src/dwbc.cpp:346-358
+    M3 A33;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) A33.m[i][j] = A(3 + i, 3 + j);
+    M3 RAR = mul(Rw[0], mul(A33, tr(Rw[0])));
+    M3 sc = skew3(cfp), scsct = mul(sc, tr(sc));
+    Mat SI(6, 6);
+    for (int i = 0; i < 3; i++) {
+        SI(i, i) = total_mass;
+        for (int j = 0; j < 3; j++) SI(3 + i, 3 + j) = RAR.m[i][j] - total_mass * scsct.m[i][j];
+    }
+    J_com = lu_inverse(SI) * CMM;
+    G.set_zero(n, 1);
+    for (int j = 0; j < n; j++) G[j] = -(J_com(2, j) * total_mass * (-9.81));
+}
+
+// RBDL CalcPointJacobian6D followed by the reference's row swap (linear rows on top),
+// reference src/contact_constraint.cpp:56-62, src/link.cpp:98-107.
+Mat Robot::point_jac(int body, V3 pl) const {
+    Mat J(6, n);
+    V3 p = pw[body] + mul(Rw[body], pl);
+    M3 sk = mul(skew3(p - pw[0]), Rw[0]);
+    for (int i = 0; i < 3; i++) {
+        J(i, i) = 1.0;
+        for (int j = 0; j < 3; j++) {
+            J(i, 3 + j) = -sk.m[i][j];
+            J(3 + i, 3 + j) = Rw[0].m[i][j];
+        }
+    }
+    int i = body;
+    while (i > 0) {
+        V3 a = mul(Rw[i], axis[i]);
+        V3 l = cross(a, p - pw[i]);
+        J(0, 5 + i) = l.x; J(1, 5 + i) = l.y; J(2, 5 + i) = l.z;
+        J(3, 5 + i) = a.x; J(4, 5 + i) = a.y; J(5, 5 + i) = a.z;
+        i = parent[i];
+    }
+    return J;
+}
+
+// SetContact (reference include/dwbc.h:432-474) + UpdateContactConstraint (src/dwbc.cpp:433-454)
+void Robot::set_contact(const unsigned char *flags) {
+    contact_dof = 0;
+    contact_links = 0;
+    for (size_t i = 0; i < cc.size(); i++) {
+        cc[i].on = flags[i] != 0;
+        if (cc[i].on) contact_dof += 6, contact_links++;
+        cc[i].xc = pw[cc[i].link] + mul(Rw[cc[i].link], cc[i].point);
+        cc[i].rotm = Rw[cc[i].link];
+        cc[i].J = point_jac(cc[i].link, cc[i].point);
+    }
+    J_C.set_zero(contact_dof, n);
+    int row = 0;
+    for (auto &c : cc)
+        if (c.on) {
+            J_C.set_block(row, 0, c.J);
+            row += 6;
+        }
+}
+
+// reference src/wbd.cpp:108-143
+int Robot::calc_contact_constraint() {
+    int c = contact_dof;
+    Lambda_c = lu_inverse(J_C * A_inv * J_C.t());
+    J_C_INV_T = Lambda_c * J_C * A_inv;
+    N_C = Mat::identity(n) - J_C.t() * J_C_INV_T;
+    A_inv_N_C = A_inv * N_C;
+    W = A_inv_N_C.block(6, 6, m, m);
+    V2.set_zero(std::max(c - 6, 0), m);
+    NwJw.set_zero(m, m);  // reference src/dwbc.cpp:471 (33x33 zeros until overwritten)
+    P_C.set_zero(c, 1);
+    contact_ok = 1;
+    Cod f = cod_compute(W, COD_THRESHOLD);
+    W_inv = f.pinv;
+    if (c > 6) {
+        int rank = f.rank;
+        V2 = f.Q.t().block(rank, 0, m - rank, m);
+        Mat tmp = lu_inverse(J_C_INV_T.block(0, 6, c - 6, m) * V2.t());  // topRightCorner(rows-6, cols-6)
+        NwJw = V2.t() * tmp;
+        if (c - 6 != V2.r) contact_ok = 0;
+    }
+    return contact_ok;
+}
+
+// reference src/wbd.cpp:186-192
+void Robot::calc_grav() {
+    torque_task.set_zero(m, 1);
+    torque_contact.set_zero(m, 1);
+    torque_grav = W_inv * (A_inv.bottom_rows(m) * (N_C * G));
+    P_C = J_C_INV_T * G;
+}
+
+// reference src/dwbc.cpp:685-793 (Jacobian assembly only; the f* PD hooks are outside this path)
+void Robot::update_task_space() {
+    for (auto &t : ts) {
+        if (t.custom || t.links.empty()) continue;
+        t.J.set_zero(t.dof, n);
+        int row = 0;
+        for (auto &tl : t.links) {
+            Mat Jl;
+            bool is_com = tl.link == nb;
+            switch (tl.mode) {
+            case TASK_LINK_6D:
+            case TASK_LINK_POSITION:
+            case TASK_LINK_ROTATION:
+            case TASK_LINK_ROTATION_CUSTOM_FRAME:
+                Jl = is_com ? J_com : point_jac(tl.link, V3());
+                break;
+            case TASK_LINK_6D_COM_FRAME:
+            case TASK_LINK_POSITION_COM_FRAME:
+                Jl = is_com ? J_com : point_jac(tl.link, com[tl.link]);
+                break;
+            default:  // *_CUSTOM_FRAME
+                Jl = is_com ? J_com : point_jac(tl.link, tl.point);
+                break;
+            }
+            switch (tl.mode) {
+            case TASK_LINK_6D: case TASK_LINK_6D_COM_FRAME: case TASK_LINK_6D_CUSTOM_FRAME:
+                t.J.set_block(row, 0, Jl);
+                break;
+            case TASK_LINK_POSITION: case TASK_LINK_POSITION_COM_FRAME: case TASK_LINK_POSITION_CUSTOM_FRAME:
+                t.J.set_block(row, 0, Jl.top_rows(3));
+                break;
+            default:
+                t.J.set_block(row, 0, Jl.bottom_rows(3));
+                break;
+            }
+            row += tl.dof;
+        }
+    }
+}
+
+// reference src/dwbc.cpp:795-816, src/wbd.cpp:207-213, 257-261
+void Robot::calc_task_space() {
+    update_task_space();
+    for (size_t i = 0; i < ts.size(); i++) {
+        Task &t = ts[i];
+        t.Lambda = lu_inverse(t.J * A_inv * N_C * t.J.t());
+        Mat Q = (t.Lambda * t.J * A_inv * N_C).right_cols(m);
+        Mat QWQ = Q * W_inv * Q.t();
+        t.Jkt = W_inv * Q.t() * cod_compute(QWQ, COD_THRESHOLD).pinv;
+        if (i + 1 != ts.size()) {
+            Mat prev = (i == 0) ? Mat::identity(m) : ts[i - 1].Null;
+            t.Null = prev * (Mat::identity(m) - t.Jkt * t.Lambda * t.J * A_inv_N_C.right_cols(m));
+        }
+    }
+}
+
+// A_const_a and A_rot of the active contacts, reference src/dwbc.cpp:1055-1075 / src/wbd.cpp:59-97
+void Robot::contact_const(Mat &A_const, Mat &A_rot, int &csize) const {
+    csize = 10 * contact_links;
+    A_const.set_zero(csize, contact_dof);
+    A_rot.set_zero(contact_dof, contact_dof);
+    int ci = 0, ki = 0;
+    for (auto &c : cc) {
+        if (!c.on) continue;
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) {
+                A_rot(ki + a, ki + b) = c.rotm.m[b][a];
+                A_rot(ki + 3 + a, ki + 3 + b) = c.rotm.m[b][a];
+            }
+        // GetZMPConstMatrix
+        A_const(ci + 0, ki + 2) = -c.lx; A_const(ci + 0, ki + 4) = -1;
+        A_const(ci + 1, ki + 2) = -c.lx; A_const(ci + 1, ki + 4) = 1;
+        A_const(ci + 2, ki + 2) = -c.ly; A_const(ci + 2, ki + 3) = -1;
+        A_const(ci + 3, ki + 2) = -c.ly; A_const(ci + 3, ki + 3) = 1;
+        // GetForceConstMatrix
+        int f = ci + 4;
+        A_const(f + 0, ki + 0) = 1.0;  A_const(f + 0, ki + 2) = -c.mu;
+        A_const(f + 1, ki + 0) = -1.0; A_const(f + 1, ki + 2) = -c.mu;
+        A_const(f + 2, ki + 1) = 1.0;  A_const(f + 2, ki + 2) = -c.mu;
+        A_const(f + 3, ki + 1) = -1.0; A_const(f + 3, ki + 2) = -c.mu;
+        A_const(f + 4, ki + 5) = 1.0;  A_const(f + 4, ki + 2) = -c.muz;
+        A_const(f + 5, ki + 5) = -1.0; A_const(f + 5, ki + 2) = -c.muz;
+        ci += 10;
+        ki += 6;
+    }
+}
+
+// reference src/dwbc.cpp:941-1127
+int Robot::single_task_qp(Task &t, const Mat &null_prev, const Mat &torque_prev) {
+    int td = t.dof, r = std::max(contact_dof - 6, 0);
+    int nv = td + r;
+    int tl_rows = tlim_set ? 2 * m : 0;
+    Mat A_const, A_rot;
+    int csize;
+    contact_const(A_const, A_rot, csize);
+    int rows = csize + tl_rows;
+    Mat Aq(rows, nv), ub(rows, 1);
+    Mat Nt = null_prev * t.Jkt * t.Lambda;
+    Mat base = torque_prev + Nt * t.fstar;
+    if (tlim_set) {
+        Aq.set_block(0, 0, Nt);
+        Aq.set_block(m, 0, -Nt);
+        if (r > 0) {
+            Aq.set_block(0, td, NwJw);
+            Aq.set_block(m, td, -NwJw);
+        }
+        for (int i = 0; i < m; i++) {
+            ub[i] = tlim[i] - base[i];
+            ub[m + i] = tlim[i] + base[i];
+        }
+    }
+    if (csize > 0) {
+        Mat Atemp = A_const * A_rot * J_C_INV_T.right_cols(m);
+        Aq.set_block(tl_rows, 0, -(Atemp * Nt));
+        if (r > 0) Aq.set_block(tl_rows, td, -(Atemp * NwJw));
+        Mat bA = A_const * (A_rot * P_C) - Atemp * base;
+        for (int i = 0; i < csize; i++) ub[tl_rows + i] = -bA[i];
+    }
+    t.qpA = Aq;
+    t.qpub = ub;
+    QpResult res = lexqp(Aq, ub.d, td);
+    t.qp_status = res.status;
+    t.prox_iters = res.prox_iters;
+    t.active = res.active;
+    t.fstar_qp.set_zero(td, 1);
+    t.contact_qp.set_zero(r, 1);
+    if (!res.status) return 0;
+    for (int i = 0; i < td; i++) t.fstar_qp[i] = res.x[i];
+    for (int i = 0; i < r; i++) t.contact_qp[i] = res.x[td + i];
+    return 1;
+}
+
+// reference src/dwbc.cpp:818-873
+int Robot::calc_task_torque(bool hqp) {
+    calc_task_space();
+    torque_task.set_zero(m, 1);
+    torque_contact.set_zero(m, 1);
+    for (auto &t : ts) t.qp_status = 0, t.active.clear(), t.fstar_qp.set_zero(t.dof, 1), t.contact_qp.set_zero(std::max(contact_dof - 6, 0), 1);
+    for (size_t i = 0; i < ts.size(); i++) {
+        Task &t = ts[i];
+        if (hqp) {
+            Mat prev_null = (i == 0) ? Mat::identity(m) : ts[i - 1].Null;
+            Mat tprev = (i == 0) ? torque_grav : torque_grav + torque_task;
+            if (!single_task_qp(t, prev_null, tprev)) return 0;
+            t.torque_h = t.Jkt * t.Lambda * (t.fstar + t.fstar_qp);
+            torque_task = (i == 0) ? t.torque_h : torque_task + ts[i - 1].Null * t.torque_h;
+            // quirk 1: with no internal-force space the reference multiplies a
+            // 33x33 zero matrix by an empty vector; defined here as zero.
+            if (contact_dof > 6) torque_contact = NwJw * t.contact_qp;
+            else torque_contact.set_zero(m, 1);
+        } else {
+            t.torque_h = t.Jkt * t.Lambda * t.fstar;
+            torque_task = (i == 0) ? t.torque_h : torque_task + ts[i - 1].Null * t.torque_h;
+        }
+    }
+    return 1;
+}
+
+// reference src/dwbc.cpp:1377-1568 (QP branch).  The reference sizes the QP with
+// contact_link_num_*contact_constraint_size rows (quirk 5): the extra rows are 0*x in [0,0]
+// and are dropped here.
+int Robot::calc_redistribute(bool hqp) {
+    redis_status = 0;
+    redis_active.clear();
+    Mat tin = torque_grav + torque_task + torque_contact;
+    int r = contact_dof - 6;
+    if (!hqp) {  // analytic two-foot branch is outside this file's scope for now
+        torque_contact.set_zero(m, 1);
+        return 0;
+    }
+    if (r <= 0) {
+        torque_contact.set_zero(m, 1);
+        redis_status = 1;
+        return 1;
+    }
+    Mat A_const, A_rot;
+    int csize;
+    contact_const(A_const, A_rot, csize);
+    int tl_rows = tlim_set ? 2 * m : 0;
+    Mat Aq(tl_rows + csize, r), ub(tl_rows + csize, 1);
+    if (tlim_set) {
+        Aq.set_block(0, 0, NwJw);
+        Aq.set_block(m, 0, -NwJw);
+        for (int i = 0; i < m; i++) {
+            ub[i] = tlim[i] - tin[i];
+            ub[m + i] = tlim[i] + tin[i];
+        }
+    }
+    Mat CM = -(A_const * A_rot);
+    Mat CJ = CM * J_C_INV_T.right_cols(m);
+    Aq.set_block(tl_rows, 0, CJ * NwJw);
+    Mat rhs = CM * P_C - CJ * tin;
+    for (int i = 0; i < csize; i++) ub[tl_rows + i] = rhs[i];
+    redisA = Aq;
+    redisub = ub;
+    QpResult res = qp_min_norm(Aq, ub.d);
+    if (!res.status) {
+        torque_contact.set_zero(m, 1);
+        return 0;
+    }
+    fill_active(Aq, ub.d, res);
+    redis_active = res.active;
+    cf_redis_qp.set_zero(r, 1);
+    for (int i = 0; i < r; i++) cf_redis_qp[i] = res.x[i];
+    torque_contact = torque_contact + NwJw * cf_redis_qp;
+    redis_status = 1;
+    return 1;
+}
+
+}  // namespace orc
+
+// ------------------------------------------------------------------------------------------
+// C API (ctypes) -- test/bench harness only.
+// ------------------------------------------------------------------------------------------
+using namespace orc;
+
+extern "C" {
+
+void *orc_create(int nb, const int *parent, const double *E_T, const double *r_T, const double *axis, const double *mass,
+                 const double *com, const double *inertia) {
+    Robot *R = new Robot();
+    R->nb = nb; R->n = nb + 5; R->m = nb - 1;
+    for (int i = 0; i < nb; i++) {
+        R->parent.push_back(parent[i]);
+        M3 E, I;
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) E.m[a][b] = E_T[i * 9 + a * 3 + b], I.m[a][b] = inertia[i * 9 + a * 3 + b];
+        R->E_T.push_back(E);
+        R->inertia.push_back(I);
+        R->r_T.push_back({r_T[i * 3], r_T[i * 3 + 1], r_T[i * 3 + 2]});
+        R->axis.push_back({axis[i * 3], axis[i * 3 + 1], axis[i * 3 + 2]});
+        R->com.push_back({com[i * 3], com[i * 3 + 1], com[i * 3 + 2]});
+        R->mass.push_back(mass[i]);
+        R->total_mass += mass[i];
+    }
+    return R;
+}
+void orc_destroy(void *h) { delete (Robot *)h; }
+
+int orc_add_contact(void *h, int link, const double *point, const double *normal, double lx, double ly) {
+    Robot *R = (Robot *)h;
+    for (auto &c : R->cc)
+        if (c.link == link) return -1;  // "Contact Constraint Already Exist", reference src/dwbc.cpp:379-386
+    Contact c;
+    c.link = link;
+    c.point = {point[0], point[1], point[2]};
+    c.normal = {normal[0], normal[1], normal[2]};
+    c.lx = lx; c.ly = ly;
+    R->cc.push_back(c);
+    return (int)R->cc.size() - 1;
+}
+// AddTaskSpace(heirarchy, mode, link, point): new level if heirarchy == size, else AddTaskLink
+// (reference src/dwbc.cpp:553-600)
+int orc_add_task(void *h, int level, int mode, int link, const double *point) {
+    Robot *R = (Robot *)h;
+    TaskLink tl;
+    tl.mode = mode; tl.link = link;
+    tl.point = {point[0], point[1], point[2]};
+    tl.dof = (mode <= TASK_LINK_6D_CUSTOM_FRAME) ? 6 : 3;
+    if ((int)R->ts.size() == level) {
+        Task t;
+        t.dof = tl.dof;
+        t.links.push_back(tl);
+        R->ts.push_back(t);
+    } else if ((int)R->ts.size() > level) {
+        R->ts[level].links.push_back(tl);
+        R->ts[level].dof += tl.dof;
+    } else
+        return -1;
+    R->ts[level].fstar.set_zero(R->ts[level].dof, 1);
+    return 0;
+}
+int orc_add_custom_task(void *h, int level, int dof) {
+    Robot *R = (Robot *)h;
+    if ((int)R->ts.size() != level) return -1;
+    Task t;
+    t.custom = true;
+    t.dof = dof;
+    t.fstar.set_zero(dof, 1);
+    R->ts.push_back(t);
+    return 0;
+}
+void orc_set_torque_limit(void *h, const double *tlim) {
+    Robot *R = (Robot *)h;
+    R->tlim_set = true;
+    R->tlim.set_zero(R->m, 1);
+    for (int i = 0; i < R->m; i++) R->tlim[i] = tlim[i];
+}
+void orc_set_friction(void *h, int contact, double mu, double muz) {
+    Robot *R = (Robot *)h;
+    R->cc[contact].mu = mu; R->cc[contact].muz = muz;
+}
+void orc_update_kinematics(void *h, const double *q, const double *qd) { ((Robot *)h)->update_kinematics(q, qd); }
+void orc_set_contact(void *h, const unsigned char *flags) { ((Robot *)h)->set_contact(flags); }
+int orc_calc_contact_constraint(void *h) { return ((Robot *)h)->calc_contact_constraint(); }
+void orc_set_task(void *h, int level, const double *fstar, const double *J) {
+    Robot *R = (Robot *)h;
+    Task &t = R->ts[level];
+    t.fstar.set_zero(t.dof, 1);
+    for (int i = 0; i < t.dof; i++) t.fstar[i] = fstar[i];
+    if (J) {  // column-major t x n
+        t.J.set_zero(t.dof, R->n);
+        for (int i = 0; i < t.dof * R->n; i++) t.J[i] = J[i];
+    }
+}
+void orc_calc_grav(void *h) { ((Robot *)h)->calc_grav(); }
+int orc_calc_task_torque(void *h, int hqp) { return ((Robot *)h)->calc_task_torque(hqp != 0); }
+int orc_calc_redistribute(void *h, int hqp) { return ((Robot *)h)->calc_redistribute(hqp != 0); }
+
+static const Mat *find_mat(Robot *R, const std::string &name, Mat &tmp) {
+    auto lvl = [&](const char *prefix) -> int {
+        size_t L = std::strlen(prefix);
+        if (name.compare(0, L, prefix) == 0 && name.size() > L) return std::atoi(name.c_str() + L);
+        return -1;
+    };
+    if (name == "A") return &R->A;
+    if (name == "A_inv") return &R->A_inv;
+    if (name == "B") return &R->B;
+    if (name == "G") return &R->G;
+    if (name == "CMM") return &R->CMM;
+    if (name == "J_com") return &R->J_com;
+    if (name == "J_C") return &R->J_C;
+    if (name == "Lambda_contact") return &R->Lambda_c;
+    if (name == "J_C_INV_T") return &R->J_C_INV_T;
+    if (name == "N_C") return &R->N_C;
+    if (name == "A_inv_N_C") return &R->A_inv_N_C;
+    if (name == "W") return &R->W;
+    if (name == "W_inv") return &R->W_inv;
+    if (name == "V2") return &R->V2;
+    if (name == "NwJw") return &R->NwJw;
+    if (name == "P_C") return &R->P_C;
+    if (name == "torque_grav") return &R->torque_grav;
+    if (name == "torque_task") return &R->torque_task;
+    if (name == "torque_contact") return &R->torque_contact;
+    if (name == "cf_redis_qp") return &R->cf_redis_qp;
+    if (name == "redisA") return &R->redisA;
+    if (name == "redisub") return &R->redisub;
+    if (name == "com_pos") {
+        tmp.set_zero(3, 1);
+        tmp[0] = R->com_pos.x; tmp[1] = R->com_pos.y; tmp[2] = R->com_pos.z;
+        return &tmp;
+    }
+    if (name == "link_pos") {  // 3 x nb
+        tmp.set_zero(3, R->nb);
+        for (int i = 0; i < R->nb; i++) tmp(0, i) = R->pw[i].x, tmp(1, i) = R->pw[i].y, tmp(2, i) = R->pw[i].z;
+        return &tmp;
+    }
+    if (name == "link_rot") {  // 9 x nb, each column a column-major 3x3 (world <- link)
+        tmp.set_zero(9, R->nb);
+        for (int i = 0; i < R->nb; i++)
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) tmp(b * 3 + a, i) = R->Rw[i].m[a][b];
+        return &tmp;
+    }
+    if (name == "link_vel") {  // 6 x nb: [v_world; w_world] of each link origin (reference src/link.cpp:85-88)
+        tmp.set_zero(6, R->nb);
+        for (int i = 0; i < R->nb; i++) {
+            V3 w = mul(R->Rw[i], V3{R->vel[i].v[0], R->vel[i].v[1], R->vel[i].v[2]});
+            V3 v = mul(R->Rw[i], V3{R->vel[i].v[3], R->vel[i].v[4], R->vel[i].v[5]});
+            tmp(0, i) = v.x; tmp(1, i) = v.y; tmp(2, i) = v.z; tmp(3, i) = w.x; tmp(4, i) = w.y; tmp(5, i) = w.z;
+        }
+        return &tmp;
+    }
+    int l;
+    if ((l = lvl("J_task")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].J;
+    if ((l = lvl("Lambda_task")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].Lambda;
+    if ((l = lvl("J_kt")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].Jkt;
+    if ((l = lvl("Null_task")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].Null;
+    if ((l = lvl("f_star_qp")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].fstar_qp;
+    if ((l = lvl("contact_qp")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].contact_qp;
+    if ((l = lvl("torque_h")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].torque_h;
+    if ((l = lvl("qpA")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].qpA;
+    if ((l = lvl("qpub")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].qpub;
+    return nullptr;
+}
+
+// Copies the named matrix (column-major) into out (may be NULL to query the shape). Returns
+// rows*cols, or -1 for an unknown name.
+int orc_get(void *h, const char *name, double *out, int *rows, int *cols) {
+    Robot *R = (Robot *)h;
+    Mat tmp;
+    const Mat *M = find_mat(R, name, tmp);
+    if (!M) return -1;
+    if (rows) *rows = M->r;
+    if (cols) *cols = M->c;
+    if (out)
+        for (int i = 0; i < M->r * M->c; i++) out[i] = M->d[i];
+    return M->r * M->c;
+}
+// active rows of the level's task QP (level >= 0) or of the redistribution QP (level = -1)
+int orc_get_active(void *h, int level, int *out, int cap) {
+    Robot *R = (Robot *)h;
+    const std::vector<int> &a = level < 0 ? R->redis_active : R->ts[level].active;
+    for (int i = 0; i < (int)a.size() && i < cap; i++) out[i] = a[i];
+    return (int)a.size();
+}
+int orc_get_qp_info(void *h, int level, int *status, int *prox_iters) {
+    Robot *R = (Robot *)h;
+    if (level < 0) {
+        *status = R->redis_status;
+        *prox_iters = 0;
+    } else {
+        *status = R->ts[level].qp_status;
+        *prox_iters = R->ts[level].prox_iters;
+    }
+    return 0;
+}
+
+// Stand-alone access to the QP layer (tests): lexicographic QP on user data, column-major A.
+int orc_lexqp(int rows, int nv, int t, const double *A, const double *ub, double *x, int *prox_iters) {
+    Mat Am(rows, nv);
+    for (int i = 0; i < rows * nv; i++) Am[i] = A[i];
+    std::vector<double> u(ub, ub + rows);
+    QpResult r = lexqp(Am, u, t);
+    if (prox_iters) *prox_iters = r.prox_iters;
+    if (r.status)
+        for (int i = 0; i < nv; i++) x[i] = r.x[i];
+    return r.status;
+}
+
+// Dense helpers exposed for unit tests of the linear algebra restatement.
+void orc_cod_pinv(int rows, int cols, const double *A, double thr, double *pinv, int *rank) {
+    Mat Am(rows, cols);
+    for (int i = 0; i < rows * cols; i++) Am[i] = A[i];
+    Cod f = cod_compute(Am, thr);
+    *rank = f.rank;
+    for (int i = 0; i < rows * cols; i++) pinv[i] = f.pinv[i];
+}
+
+// Whole cycle over a batch (CPU baseline + bulk parity): one state per call in reference call
+// order, cold-start QP per state.  `stages`: bit0 grav, bit1 task torque, bit2 HQP, bit3 redistribute.
+// fstar: concatenation over levels of [B x t_l] row-major blocks; flags: [B x ncontact].
+// Outputs [B x m] row-major torques, status [B] (bit0 contact ok, bit1 task ok, bit2 redistribute ok).
+int orc_run_batch(void *h, int B, const double *q, const double *qd, const double *fstar, const unsigned char *flags,
+                  int stages, double *tau_grav, double *tau_task, double *tau_contact, int *status, int nthreads) {
+    Robot *R0 = (Robot *)h;
+    int n = R0->n, m = R0->m, nc = (int)R0->cc.size();
+    std::vector<size_t> foff;
+    size_t off = 0;
+    for (auto &t : R0->ts) {
+        foff.push_back(off);
+        off += (size_t)B * t.dof;
+    }
+    if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads <= 0) nthreads = 1;
+    std::atomic<int> next(0);
+    const int chunk = 16;
+    auto worker = [&]() {
+        Robot R = *R0;
+        while (true) {
+            int b0 = next.fetch_add(chunk);
+            if (b0 >= B) break;
+            int b1 = std::min(B, b0 + chunk);
+            for (int b = b0; b < b1; b++) {
+                R.update_kinematics(q + (size_t)b * (n + 1), qd + (size_t)b * n);
+                R.set_contact(flags + (size_t)b * nc);
+                int st = R.calc_contact_constraint() ? 1 : 0;
+                for (size_t l = 0; l < R.ts.size(); l++) {
+                    Task &t = R.ts[l];
+                    for (int i = 0; i < t.dof; i++) t.fstar[i] = fstar[foff[l] + (size_t)b * t.dof + i];
+                }
+                R.calc_grav();
+                if (stages & 2) st |= R.calc_task_torque((stages & 4) != 0) ? 2 : 0;
+                if (stages & 8) st |= R.calc_redistribute(true) ? 4 : 0;
+                for (int i = 0; i < m; i++) {
+                    tau_grav[(size_t)b * m + i] = R.torque_grav[i];
+                    tau_task[(size_t)b * m + i] = R.torque_task[i];
+                    tau_contact[(size_t)b * m + i] = R.torque_contact[i];
+                }
+                status[b] = st;
+            }
+        }
+    };
+    if (nthreads == 1) {
+        worker();
+    } else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nthreads; i++) th.emplace_back(worker);
+        for (auto &t : th) t.join();
+    }
+    return 0;
+}
+
+int orc_num_threads() {
+    int n = (int)std::thread::hardware_concurrency();
+    return n > 0 ? n : 1;
+}
+}
+
+extern "C" void orc_nnls(int m, int n, const double *E, const double *f, double *x) {
+    orc::Mat Em(m, n);
+    for (int i = 0; i < m * n; i++) Em[i] = E[i];
+    std::vector<double> fv(f, f + m), xv;
+    orc::nnls(Em, fv, xv);
+    for (int i = 0; i < n; i++) x[i] = xv[i];
+}

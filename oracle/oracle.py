@@ -1,0 +1,219 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` leg may import
+this.  It mirrors the reference call order on one `RobotData` (reference include/dwbc.h:59-430):
+UpdateKinematics -> SetContact -> CalcContactConstraint -> SetTaskSpace -> CalcGravCompensation
+-> CalcTaskControlTorque -> CalcContactRedistribute.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .urdf_model import Model, load_urdf
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "build", "liboracle.so")
+
+# LINK_MODE values, reference include/dwbc_task.h:23-33
+TASK_LINK_6D, TASK_LINK_6D_COM_FRAME, TASK_LINK_6D_CUSTOM_FRAME = 0, 1, 2
+TASK_LINK_POSITION, TASK_LINK_POSITION_COM_FRAME, TASK_LINK_POSITION_CUSTOM_FRAME = 3, 4, 5
+TASK_LINK_ROTATION, TASK_LINK_ROTATION_CUSTOM_FRAME = 6, 7
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in ("dwbc_oracle.cpp", "linalg.hpp", "qp.hpp")]
+    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        subprocess.check_call(["make", "-s", "-C", _HERE])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_add_contact.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_double, C.c_double]
+        L.orc_add_task.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp]
+        L.orc_add_custom_task.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_set_torque_limit.argtypes = [C.c_void_p, _dp]
+        L.orc_set_friction.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+        L.orc_update_kinematics.argtypes = [C.c_void_p, _dp, _dp]
+        L.orc_set_contact.argtypes = [C.c_void_p, C.c_char_p]
+        L.orc_calc_contact_constraint.argtypes = [C.c_void_p]
+        L.orc_set_task.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        L.orc_calc_grav.argtypes = [C.c_void_p]
+        L.orc_calc_task_torque.argtypes = [C.c_void_p, C.c_int]
+        L.orc_calc_redistribute.argtypes = [C.c_void_p, C.c_int]
+        L.orc_get.argtypes = [C.c_void_p, C.c_char_p, _dp, _ip, _ip]
+        L.orc_get_active.argtypes = [C.c_void_p, C.c_int, _ip, C.c_int]
+        L.orc_get_qp_info.argtypes = [C.c_void_p, C.c_int, _ip, _ip]
+        L.orc_lexqp.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _ip]
+        L.orc_cod_pinv.argtypes = [C.c_int, C.c_int, _dp, C.c_double, _dp, _ip]
+        L.orc_run_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_char_p, C.c_int, _dp, _dp, _dp, _ip, C.c_int]
+        L.orc_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+class OracleRobot:
+    """One reference-shaped RobotData evaluated by the CPU oracle."""
+
+    def __init__(self, model: Model | str):
+        if isinstance(model, str):
+            model = load_urdf(model)
+        self.model = model
+        f = model.flat()
+        self._keep = f
+        L = lib()
+        self.h = L.orc_create(int(f["nb"]), f["parent"].ctypes.data_as(_ip), *[f[k].ctypes.data_as(_dp) for k in
+                                                                                ("E_T", "r_T", "axis", "mass", "com", "inertia")])
+        self.n = model.system_dof
+        self.m = model.model_dof
+        self.task_dofs = []
+        self.ncontact = 0
+
+    def __del__(self):
+        try:
+            lib().orc_destroy(self.h)
+        except Exception:
+            pass
+
+    # ---- setup ----
+    def add_contact(self, link, point, normal=(0, 0, 1), lx=0.0, ly=0.0):
+        if isinstance(link, str):
+            link = self.model.link_id(link)
+        _, p = _d(point)
+        _, nrm = _d(normal)
+        r = lib().orc_add_contact(self.h, int(link), p, nrm, float(lx), float(ly))
+        if r >= 0:
+            self.ncontact += 1
+        return r
+
+    def add_task(self, level, mode, link, point=(0, 0, 0)):
+        if isinstance(link, str):
+            link = self.model.link_id(link)
+        _, p = _d(point)
+        r = lib().orc_add_task(self.h, int(level), int(mode), int(link), p)
+        if r == 0:
+            dof = 6 if mode <= 2 else 3
+            if level == len(self.task_dofs):
+                self.task_dofs.append(dof)
+            else:
+                self.task_dofs[level] += dof
+        return r
+
+    def add_custom_task(self, level, dof):
+        r = lib().orc_add_custom_task(self.h, int(level), int(dof))
+        if r == 0:
+            self.task_dofs.append(int(dof))
+        return r
+
+    def set_torque_limit(self, tlim):
+        a, p = _d(np.broadcast_to(np.asarray(tlim, dtype=np.float64), (self.m,)))
+        lib().orc_set_torque_limit(self.h, p)
+
+    # ---- cycle ----
+    def update_kinematics(self, q, qd=None):
+        qa, qp = _d(q)
+        qda, qdp = _d(np.zeros(self.n) if qd is None else qd)
+        assert qa.size == self.n + 1 and qda.size == self.n
+        lib().orc_update_kinematics(self.h, qp, qdp)
+
+    def set_contact(self, *flags):
+        fl = bytes(bytearray([1 if f else 0 for f in flags] + [0] * (self.ncontact - len(flags))))
+        lib().orc_set_contact(self.h, fl)
+
+    def calc_contact_constraint(self):
+        return lib().orc_calc_contact_constraint(self.h)
+
+    def set_task(self, level, fstar, J=None):
+        _, fp = _d(fstar)
+        if J is None:
+            lib().orc_set_task(self.h, int(level), fp, None)
+        else:
+            Ja = np.asfortranarray(np.asarray(J, dtype=np.float64))
+            lib().orc_set_task(self.h, int(level), fp, Ja.ctypes.data_as(_dp))
+
+    def calc_grav(self):
+        lib().orc_calc_grav(self.h)
+        return self.get("torque_grav")[:, 0]
+
+    def calc_task_torque(self, hqp=True):
+        return lib().orc_calc_task_torque(self.h, 1 if hqp else 0)
+
+    def calc_redistribute(self, hqp=True):
+        return lib().orc_calc_redistribute(self.h, 1 if hqp else 0)
+
+    # ---- results ----
+    def get(self, name):
+        r, c = C.c_int(), C.c_int()
+        nb = lib().orc_get(self.h, name.encode(), None, C.byref(r), C.byref(c))
+        if nb < 0:
+            raise KeyError(name)
+        out = np.zeros((c.value, r.value), dtype=np.float64)
+        lib().orc_get(self.h, name.encode(), out.ctypes.data_as(_dp), None, None)
+        return out.T.copy()
+
+    def active_set(self, level):
+        buf = (C.c_int * 256)()
+        k = lib().orc_get_active(self.h, int(level), buf, 256)
+        return list(buf[:k])
+
+    def qp_info(self, level):
+        s, p = C.c_int(), C.c_int()
+        lib().orc_get_qp_info(self.h, int(level), C.byref(s), C.byref(p))
+        return s.value, p.value
+
+    def run_batch(self, q, qd, fstars, flags, stages=0xF, nthreads=0):
+        """Whole cycle over B states. fstars: list over levels of [B, t_l]. Returns dict."""
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        qd = np.ascontiguousarray(qd, dtype=np.float64)
+        B = q.shape[0]
+        fs = np.concatenate([np.ascontiguousarray(f, dtype=np.float64).reshape(-1) for f in fstars]) if fstars else np.zeros(1)
+        fl = np.ascontiguousarray(flags, dtype=np.uint8)
+        assert fl.shape == (B, self.ncontact)
+        tg = np.zeros((B, self.m)); tt = np.zeros((B, self.m)); tc = np.zeros((B, self.m))
+        st = np.zeros(B, dtype=np.int32)
+        lib().orc_run_batch(self.h, B, q.ctypes.data_as(_dp), qd.ctypes.data_as(_dp), fs.ctypes.data_as(_dp),
+                            fl.ctypes.data_as(C.c_char_p), int(stages), tg.ctypes.data_as(_dp), tt.ctypes.data_as(_dp),
+                            tc.ctypes.data_as(_dp), st.ctypes.data_as(_ip), int(nthreads))
+        return dict(torque_grav=tg, torque_task=tt, torque_contact=tc, status=st)
+
+
+def lexqp(A, ub, t):
+    A = np.asfortranarray(np.asarray(A, dtype=np.float64))
+    ub = np.ascontiguousarray(ub, dtype=np.float64)
+    x = np.zeros(A.shape[1])
+    it = C.c_int()
+    st = lib().orc_lexqp(A.shape[0], A.shape[1], int(t), A.ctypes.data_as(_dp), ub.ctypes.data_as(_dp), x.ctypes.data_as(_dp), C.byref(it))
+    return st, x, it.value
+
+
+def cod_pinv(A, thr=1e-6):
+    A = np.asfortranarray(np.asarray(A, dtype=np.float64))
+    out = np.zeros((A.shape[0], A.shape[1]), dtype=np.float64)  # holds (cols x rows) column-major
+    rk = C.c_int()
+    lib().orc_cod_pinv(A.shape[0], A.shape[1], A.ctypes.data_as(_dp), float(thr), out.ctypes.data_as(_dp), C.byref(rk))
+    return out.reshape(-1).reshape((A.shape[0], A.shape[1]), order="C").reshape(-1).reshape((A.shape[1], A.shape[0]), order="F"), rk.value
+
+
+def num_threads():
+    return lib().orc_num_threads()

@@ -1,0 +1,65 @@
+"""Shared test inputs: the reference's own test configurations (tests/dwbc_test.cpp:48-77,152-179)
+and the synthetic state generator of SURVEY.md section 8(d)."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+URDF = os.path.join(GOLDEN, "tocabi_model.urdf")
+
+# reference tests/dwbc_test.cpp:48-54 and :152-158
+Q_CASE = {
+    1: [0, 0, 0.92983, 0, 0, 0, 0.0, 0.0, -0.24, 0.6, -0.36, 0.0, 0.0, 0.0, -0.24, 0.6, -0.36, 0.0, 0, 0, 0,
+        0.3, 0.3, 1.5, -1.27, -1, 0, -1, 0, 0, 0, -0.3, -0.3, -1.5, 1.27, 1, 0, 1, 0, 1.0],
+    2: [0, 0, 0.92983, 0, 0, 0, 0.1, 0.0, -0.24, 0.5, -0.6, 0.0, 0.05, 0.0, -0.21, 0.7, -0.31, 0.0, 0, 0, 0,
+        0.2, 0.5, 1.5, -1.27, -1.2, 0, -1, 0, 0, 0, -0.3, -0.3, -1.5, 1.27, 1.3, 0.1, 1.3, 0, 1.0],
+}
+# reference tests/dwbc_test.cpp:56-57 and :160-161
+FSTAR_CASE = {1: ([0.1, 4.0, 0.1, 0.1, -0.1, 0.1], [0.1, -0.1, 0.1]), 2: ([0.4, 2.0, 0.1, 0.3, -0.1, 0.1], [0.1, 0.1, 0.1])}
+FOOT_POINT = (0.03, 0.0, -0.1585)  # reference tests/dwbc_test.cpp:66-67
+LEFT_FOOT, RIGHT_FOOT, PELVIS, UPPERBODY = 6, 12, 0, 15
+
+# golden file -> oracle/product matrix name
+GOLDEN_NAMES = [
+    ("A", "Acontact_mat"), ("A_inv", "A_inv_"), ("J_C", "J_C"), ("Lambda_contact", "Lambda_contact"),
+    ("J_C_INV_T", "J_C_INV_T"), ("N_C", "N_C"), ("W", "W"), ("W_inv", "W_inv"), ("NwJw", "NwJw"),
+    ("torque_grav", "torque_grav_"),
+]
+
+
+def synth_states(B, seed, q0=None):
+    """SURVEY.md section 8(d) 'Synthetic inputs': PCG64(seed); joints q0+0.05U, base xyz +0.01U, base rpy 0.1U,
+    qdot 0.1U."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    q0 = np.asarray(Q_CASE[1] if q0 is None else q0, dtype=np.float64)
+    q = np.tile(q0, (B, 1))
+    q[:, 6:39] += 0.05 * rng.uniform(-1, 1, (B, 33))
+    q[:, 0:3] = np.array([0, 0, 0.92983]) + 0.01 * rng.uniform(-1, 1, (B, 3))
+    rpy = 0.1 * rng.uniform(-1, 1, (B, 3))
+    cr, sr = np.cos(rpy[:, 0] / 2), np.sin(rpy[:, 0] / 2)
+    cp, sp = np.cos(rpy[:, 1] / 2), np.sin(rpy[:, 1] / 2)
+    cy, sy = np.cos(rpy[:, 2] / 2), np.sin(rpy[:, 2] / 2)
+    q[:, 39] = cr * cp * cy + sr * sp * sy
+    q[:, 3] = sr * cp * cy - cr * sp * sy
+    q[:, 4] = cr * sp * cy + sr * cp * sy
+    q[:, 5] = cr * cp * sy - sr * sp * cy
+    qd = 0.1 * rng.uniform(-1, 1, (B, 39))
+    return q, qd, rng
+
+
+def synth_fstar(rng, B, dofs=(3, 6, 21), scales=(0.5, 1.0, 2.0), hard_frac=0.05):
+    fs = [s * rng.standard_normal((B, d)) for d, s in zip(dofs, scales)]
+    k = int(round(hard_frac * B))
+    if k > 0:
+        idx = rng.choice(B, size=k, replace=False)
+        fs[0][idx, 1] = 4.0  # infeasible lateral acceleration, reference tests/dwbc_test.cpp:56
+    return fs
+
+
+def posture_selector(n=39, first_joint=12, count=21):
+    """TASK_CUSTOM Jacobian [0 | S] selecting the non-leg joints."""
+    J = np.zeros((count, n))
+    for i in range(count):
+        J[i, 6 + first_joint + i] = 1.0
+    return J
