@@ -1,0 +1,183 @@
+/*
+ * dwbc_b200 -- C ABI of the batched whole-body-control hot path (B200 / sm_100a).
+ *
+ * This header is the drop-in boundary.  Each entry point names the reference interface it replaces
+ * (paths relative to the saga0619/libdwbc checkout).  One `dwbc_batch_t` plays the role of B
+ * independent `DWBC::RobotData` objects (reference include/dwbc.h:59-430) that share a model, a contact
+ * list, a task hierarchy and a torque limit, and differ only in their per-cycle state.
+ *
+ * Conventions
+ *   - Everything is FP64.  Per-state vectors are stored state-major: x[b*len + i].
+ *   - Per-state matrices are column-major (Eigen::MatrixXd layout, reference tests/dwbc_test_util.h:23-26)
+ *     and state-major: M[b*rows*cols + i + j*rows].
+ *   - q has n+1 entries: [p(3) | quat xyz(3) | joints(m) | quat w]; qdot has n entries
+ *     [v_world(3) | omega_body(3) | joint rates(m)]   (reference src/pybind/rl_wbc_bridge.cpp:88-98).
+ *   - Pointers named *_dev must be device pointers on the batch's GPU, valid until the stream work that
+ *     uses them has completed; the library never copies host<->device behind the caller's back except
+ *     in the explicitly named *_host entry points.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls on one handle are
+ *     stream-ordered; different handles are independent.  A handle is not thread-safe (like RobotData).
+ *   - Return value: 0 on success, a negative DWBC_ERR_* code otherwise; dwbc_last_error() gives text.
+ *     Per-state outcomes (the reference's 1/0 ints) are reported in status[b], see DWBC_ST_*.
+ *   - There is no CPU fallback: every compute entry point launches CUDA kernels.
+ */
+#ifndef DWBC_B200_H
+#define DWBC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dwbc_model dwbc_model_t;
+typedef struct dwbc_batch dwbc_batch_t;
+
+enum {
+    DWBC_OK = 0,
+    DWBC_ERR_ARG = -1,      /* bad argument (null pointer, size, unknown link, level out of order ...) */
+    DWBC_ERR_MODEL = -2,    /* URDF could not be read / unsupported model */
+    DWBC_ERR_CUDA = -3,     /* CUDA runtime error (no device, out of memory, launch failure) */
+    DWBC_ERR_ORDER = -4,    /* call-order contract violated (e.g. solve before update_kinematics) */
+    DWBC_ERR_LIMIT = -5     /* exceeds a compiled-in limit (contacts, levels, task dof) */
+};
+
+/* reference include/dwbc_contact_constraint.h:19-25 */
+enum { DWBC_CONTACT_6D = 0, DWBC_CONTACT_POINT = 1, DWBC_CONTACT_LINK = 2, DWBC_CONTACT_LINE = 3 };
+
+/* reference include/dwbc_task.h:23-33 (LINK_MODE) */
+enum {
+    DWBC_TASK_LINK_6D = 0,
+    DWBC_TASK_LINK_6D_COM_FRAME = 1,
+    DWBC_TASK_LINK_6D_CUSTOM_FRAME = 2,
+    DWBC_TASK_LINK_POSITION = 3,
+    DWBC_TASK_LINK_POSITION_COM_FRAME = 4,
+    DWBC_TASK_LINK_POSITION_CUSTOM_FRAME = 5,
+    DWBC_TASK_LINK_ROTATION = 6,
+    DWBC_TASK_LINK_ROTATION_CUSTOM_FRAME = 7
+};
+
+/* stage selection for dwbc_batch_solve */
+enum {
+    DWBC_SOLVE_GRAV = 1,      /* CalcGravCompensation            reference src/dwbc.cpp:875-889 */
+    DWBC_SOLVE_TASK = 2,      /* CalcTaskSpace + CalcTaskControlTorque(hqp=false)  :795-873 */
+    DWBC_SOLVE_HQP = 4,       /* ... with hqp=true: per-level QP  :941-1127 (implies DWBC_SOLVE_TASK) */
+    DWBC_SOLVE_REDIST = 8     /* CalcContactRedistribute(hqp=true) :1372-1568 */
+};
+
+/* per-state status bits (1 = the corresponding reference call would have returned 1) */
+enum {
+    DWBC_ST_CONTACT_OK = 1,   /* CalcContactConstraint */
+    DWBC_ST_TASK_OK = 2,      /* CalcTaskControlTorque */
+    DWBC_ST_REDIST_OK = 4     /* CalcContactRedistribute */
+};
+
+/* matrices retrievable with dwbc_batch_get_matrix (public RobotData fields of the reference) */
+enum {
+    DWBC_MAT_A = 0,           /* A_            n x n */
+    DWBC_MAT_A_INV,           /* A_inv_        n x n */
+    DWBC_MAT_G,               /* G_            n x 1 */
+    DWBC_MAT_B,               /* B_            n x 1 */
+    DWBC_MAT_J_C,             /* J_C           cmax x n   (rows >= contact_dof are zero) */
+    DWBC_MAT_LAMBDA_C,        /* Lambda_contact cmax x cmax */
+    DWBC_MAT_J_C_INV_T,       /* J_C_INV_T     cmax x n */
+    DWBC_MAT_N_C,             /* N_C           n x n      (materialised on request) */
+    DWBC_MAT_A_INV_N_C,       /* A_inv_N_C     n x n */
+    DWBC_MAT_W,               /* W             m x m */
+    DWBC_MAT_W_INV,           /* W_inv         m x m */
+    DWBC_MAT_V2,              /* V2            rmax x m   (orthonormal rows; basis is not unique) */
+    DWBC_MAT_NWJW,            /* NwJw          m x rmax */
+    DWBC_MAT_P_C,             /* P_C           cmax x 1 */
+    DWBC_MAT_TORQUE_GRAV,     /* torque_grav_  m x 1 */
+    DWBC_MAT_TORQUE_TASK,     /* torque_task_  m x 1 */
+    DWBC_MAT_TORQUE_CONTACT,  /* torque_contact_ m x 1 */
+    DWBC_MAT_COM,             /* com_pos       3 x 1 */
+    DWBC_MAT_LINK_POS,        /* link_[i].xpos 3 x nb */
+    DWBC_MAT_LINK_ROT,        /* link_[i].rotm 9 x nb (each column a column-major 3x3) */
+    DWBC_MAT_LINK_VEL,        /* link_[i].v, .w 6 x nb */
+    DWBC_MAT_CF_REDIS,        /* cf_redis_qp_  rmax x 1 */
+    /* per hierarchy level (argument `level`) */
+    DWBC_MAT_J_TASK = 64,     /* ts_[l].J_task_      t x n */
+    DWBC_MAT_LAMBDA_TASK,     /* ts_[l].Lambda_task_ t x t */
+    DWBC_MAT_J_KT,            /* ts_[l].J_kt_        m x t */
+    DWBC_MAT_NULL_TASK,       /* ts_[l].Null_task_   m x m */
+    DWBC_MAT_FSTAR_QP,        /* ts_[l].f_star_qp_   t x 1 */
+    DWBC_MAT_CONTACT_QP,      /* ts_[l].contact_qp_  rmax x 1 */
+    DWBC_MAT_TORQUE_H         /* ts_[l].torque_h_    m x 1 */
+};
+
+const char *dwbc_last_error(void);
+/* number of CUDA kernels launched by this library since process start (bench.py's gpu_launches) */
+long long dwbc_launch_count(void);
+
+/* ---- model: RobotData::LoadModelData(urdf_path, floating)  reference src/dwbc.cpp:102-123 ---- */
+dwbc_model_t *dwbc_model_load_urdf(const char *urdf_path, int floating);
+void dwbc_model_destroy(dwbc_model_t *m);
+/* system_dof_, model_dof_, number of links (without the COM pseudo link), total_mass_ */
+int dwbc_model_info(const dwbc_model_t *m, int *system_dof, int *model_dof, int *n_links, double *total_mass);
+/* case-insensitive link lookup (reference src/dwbc.cpp:393-404); "COM" gives n_links; -1 if unknown */
+int dwbc_model_link_id(const dwbc_model_t *m, const char *name);
+const char *dwbc_model_link_name(const dwbc_model_t *m, int link);
+
+/* ---- batch handle ---- */
+dwbc_batch_t *dwbc_batch_create(const dwbc_model_t *m, int batch, int device);
+void dwbc_batch_destroy(dwbc_batch_t *b);
+int dwbc_batch_size(const dwbc_batch_t *b);
+/* compile-time capacities: cmax = 6*max active contacts, rmax = cmax-6 */
+int dwbc_batch_limits(const dwbc_batch_t *b, int *cmax, int *rmax, int *max_levels, int *max_task_dof);
+
+/* ---- setup (once): same meaning as the RobotData calls they replace ---- */
+/* AddContactConstraint(link, type, point, normal, lx, ly)   reference src/dwbc.cpp:377-391.
+ * Returns the contact index (>= 0). Only DWBC_CONTACT_6D is supported on this path. */
+int dwbc_batch_add_contact(dwbc_batch_t *b, int link, int contact_type, const double point[3], const double normal[3], double lx, double ly);
+/* ContactConstraint::SetFrictionRatio   reference src/contact_constraint.cpp:93-97 (default 0.2, 0.2) */
+int dwbc_batch_set_friction(dwbc_batch_t *b, int contact, double friction_ratio, double friction_ratio_z);
+/* AddTaskSpace(heirarchy, task_mode, link, point): a new level if heirarchy == number of levels, otherwise
+ * the link is appended to that level (AddTaskLink)   reference src/dwbc.cpp:531-600 */
+int dwbc_batch_add_task(dwbc_batch_t *b, int level, int task_mode, int link, const double point[3]);
+/* AddTaskSpace(heirarchy, TASK_CUSTOM, task_dof)   reference src/dwbc.cpp:522-530 */
+int dwbc_batch_add_custom_task(dwbc_batch_t *b, int level, int task_dof);
+int dwbc_batch_clear_tasks(dwbc_batch_t *b);
+/* SetTorqueLimit(tlim)   reference src/dwbc.cpp:254-258; tlim is a HOST array of model_dof entries */
+int dwbc_batch_set_torque_limit(dwbc_batch_t *b, const double *tlim_host);
+
+/* ---- per control cycle, device buffers, in the reference's call order ---- */
+/* UpdateKinematics(q, qdot, qddot)   reference src/dwbc.cpp:279-371.  q_dev [B x (n+1)], qdot_dev [B x n]. */
+int dwbc_batch_update_kinematics(dwbc_batch_t *b, const double *q_dev, const double *qdot_dev, void *stream);
+/* SetContact(flags...)   reference include/dwbc.h:432-474. flags_dev [B x ncontact], 0/1 per registered contact. */
+int dwbc_batch_set_contact(dwbc_batch_t *b, const uint8_t *flags_dev, void *stream);
+/* CalcContactConstraint()   reference src/dwbc.cpp:456-478 */
+int dwbc_batch_calc_contact_constraint(dwbc_batch_t *b, void *stream);
+/* SetTaskSpace(heirarchy, f_star, J_task)   reference src/dwbc.cpp:662-678.  fstar_dev [B x t].
+ * jtask_dev: NULL for link tasks; for a custom task either [t x n] shared by all states (jtask_per_state = 0)
+ * or [B x t x n] (jtask_per_state = 1), column-major. */
+int dwbc_batch_set_task(dwbc_batch_t *b, int level, const double *fstar_dev, const double *jtask_dev, int jtask_per_state, void *stream);
+/* CalcGravCompensation / CalcTaskControlTorque / CalcContactRedistribute as selected by `stages`.
+ * Any output pointer may be NULL.  torques are [B x m]; status [B] (DWBC_ST_* bits). */
+int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *tau_task_dev, double *tau_contact_dev,
+                     int32_t *status_dev, void *stream);
+/* Copies a per-state matrix into out_dev ([B x rows x cols], column-major per state). rows/cols may be NULL. */
+int dwbc_batch_get_matrix(dwbc_batch_t *b, int which, int level, double *out_dev, int *rows, int *cols, void *stream);
+/* Active rows of the level's task QP (level >= 0) or of the redistribution QP (level = -1) as a bit mask
+ * per state: out_dev [B x 4] uint32 words, bit i of word i/32 = row i (rows ordered as in the reference:
+ * +torque (m), -torque (m), contact (10 per active contact)). */
+int dwbc_batch_get_active_set(dwbc_batch_t *b, int level, uint32_t *out_dev, void *stream);
+
+/* ---- whole cycle with HOST buffers (pinned or pageable): H2D, all stages, D2H, synchronised on return.
+ * This is what the RobotData shim, the pybind bridge and bench.py's end-to-end timing call.
+ * fstar_host: concatenation over levels of [B x t_l] blocks. flags_host [B x ncontact]. */
+int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, const double *qdot_host, const double *fstar_host,
+                          const uint8_t *flags_host, double *tau_grav_host, double *tau_task_host, double *tau_contact_host,
+                          int32_t *status_host, void *stream);
+
+/* ---- diagnostics ---- */
+/* Best DFMA-chain throughput (TFLOP/s, 2 flop per FMA) observed over ~`seconds` of back-to-back launches on
+ * `device`: the FP64-pipe roofline denominator used by bench.py. */
+int dwbc_probe_fp64(int device, double seconds, double *tflops);
+/* Total active-set iterations of the last dwbc_batch_solve per state: out_dev [B] int32. */
+int dwbc_batch_get_qp_iterations(dwbc_batch_t *b, int32_t *out_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DWBC_B200_H */

@@ -1,0 +1,82 @@
+"""Loader of the CUDA library.  Fails loudly: no fallback of any kind."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBNAME = "libdwbc_b200.so"
+
+
+class DwbcError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, _LIBNAME)
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def declare(L):
+    """ctypes prototypes of every symbol include/dwbc_b200.h declares."""
+    vp = C.c_void_p
+    L.dwbc_last_error.restype = C.c_char_p
+    L.dwbc_launch_count.restype = C.c_longlong
+    L.dwbc_model_load_urdf.restype = vp
+    L.dwbc_model_load_urdf.argtypes = [C.c_char_p, C.c_int]
+    L.dwbc_model_destroy.argtypes = [vp]
+    L.dwbc_model_info.argtypes = [vp, _ip, _ip, _ip, _dp]
+    L.dwbc_model_link_id.argtypes = [vp, C.c_char_p]
+    L.dwbc_model_link_name.restype = C.c_char_p
+    L.dwbc_model_link_name.argtypes = [vp, C.c_int]
+    L.dwbc_batch_create.restype = vp
+    L.dwbc_batch_create.argtypes = [vp, C.c_int, C.c_int]
+    L.dwbc_batch_destroy.argtypes = [vp]
+    L.dwbc_batch_size.argtypes = [vp]
+    L.dwbc_batch_limits.argtypes = [vp, _ip, _ip, _ip, _ip]
+    L.dwbc_batch_add_contact.argtypes = [vp, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_double]
+    L.dwbc_batch_set_friction.argtypes = [vp, C.c_int, C.c_double, C.c_double]
+    L.dwbc_batch_add_task.argtypes = [vp, C.c_int, C.c_int, C.c_int, _dp]
+    L.dwbc_batch_add_custom_task.argtypes = [vp, C.c_int, C.c_int]
+    L.dwbc_batch_clear_tasks.argtypes = [vp]
+    L.dwbc_batch_set_torque_limit.argtypes = [vp, _dp]
+    L.dwbc_batch_update_kinematics.argtypes = [vp, vp, vp, vp]
+    L.dwbc_batch_set_contact.argtypes = [vp, vp, vp]
+    L.dwbc_batch_calc_contact_constraint.argtypes = [vp, vp]
+    L.dwbc_batch_set_task.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp]
+    L.dwbc_batch_solve.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
+    L.dwbc_batch_get_matrix.argtypes = [vp, C.c_int, C.c_int, vp, _ip, _ip, vp]
+    L.dwbc_batch_get_active_set.argtypes = [vp, C.c_int, vp, vp]
+    L.dwbc_batch_cycle_host.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.dwbc_probe_fp64.argtypes = [C.c_int, C.c_double, _dp]
+    L.dwbc_batch_get_qp_iterations.argtypes = [vp, vp, vp]
+    return L
+
+
+EXPORTS = [
+    "dwbc_last_error", "dwbc_launch_count", "dwbc_model_load_urdf", "dwbc_model_destroy", "dwbc_model_info", "dwbc_model_link_id",
+    "dwbc_model_link_name", "dwbc_batch_create", "dwbc_batch_destroy", "dwbc_batch_size", "dwbc_batch_limits", "dwbc_batch_add_contact",
+    "dwbc_batch_set_friction", "dwbc_batch_add_task", "dwbc_batch_add_custom_task", "dwbc_batch_clear_tasks", "dwbc_batch_set_torque_limit",
+    "dwbc_batch_update_kinematics", "dwbc_batch_set_contact", "dwbc_batch_calc_contact_constraint", "dwbc_batch_set_task", "dwbc_batch_solve",
+    "dwbc_batch_get_matrix", "dwbc_batch_get_active_set", "dwbc_batch_cycle_host", "dwbc_probe_fp64", "dwbc_batch_get_qp_iterations",
+]
+
+_lib = None
+
+
+def load_library():
+    """Loads libdwbc_b200.so (built in-tree by __graft_entry__.build()).  Raises DwbcError if it is missing."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise DwbcError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(nvcc, sm_100a). There is no CPU fallback.")
+        try:
+            _lib = declare(C.CDLL(path))
+        except OSError as e:
+            raise DwbcError(f"cannot load {path}: {e}") from e
+    return _lib

@@ -1,0 +1,262 @@
+"""RobotDataBatch: Python host over the C ABI, mirroring the reference's RobotData call sequence for B states.
+
+reference include/dwbc.h:59-430 (RobotData) -- same method names in snake_case, same argument meaning:
+    UpdateKinematics -> update_kinematics(q, qdot)        SetContact -> set_contact(flags)
+    CalcContactConstraint -> calc_contact_constraint()    SetTaskSpace -> set_task_space(level, fstar, J=None)
+    CalcGravCompensation / CalcTaskControlTorque / CalcContactRedistribute -> solve(stages)
+Public RobotData fields (A_, A_inv_, J_C, Lambda_contact, ... torque_task_) are read with get(name).
+
+Device memory and streams come from PyTorch (plumbing only): every tensor argument must be a CUDA tensor on the
+batch's device, float64 (uint8 for contact flags) and contiguous.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import DwbcError, load_library
+
+CONTACT_6D = 0
+(TASK_LINK_6D, TASK_LINK_6D_COM_FRAME, TASK_LINK_6D_CUSTOM_FRAME, TASK_LINK_POSITION, TASK_LINK_POSITION_COM_FRAME,
+ TASK_LINK_POSITION_CUSTOM_FRAME, TASK_LINK_ROTATION, TASK_LINK_ROTATION_CUSTOM_FRAME) = range(8)
+SOLVE_GRAV, SOLVE_TASK, SOLVE_HQP, SOLVE_REDIST = 1, 2, 4, 8
+ST_CONTACT_OK, ST_TASK_OK, ST_REDIST_OK = 1, 2, 4
+
+# name -> (matrix id, per-level?)
+_MATS = {
+    "A": (0, False), "A_inv": (1, False), "G": (2, False), "B": (3, False), "J_C": (4, False), "Lambda_contact": (5, False),
+    "J_C_INV_T": (6, False), "N_C": (7, False), "A_inv_N_C": (8, False), "W": (9, False), "W_inv": (10, False), "V2": (11, False),
+    "NwJw": (12, False), "P_C": (13, False), "torque_grav": (14, False), "torque_task": (15, False), "torque_contact": (16, False),
+    "com_pos": (17, False), "link_pos": (18, False), "link_rot": (19, False), "link_vel": (20, False), "cf_redis_qp": (21, False),
+    "J_task": (64, True), "Lambda_task": (65, True), "J_kt": (66, True), "Null_task": (67, True), "f_star_qp": (68, True),
+    "contact_qp": (69, True), "torque_h": (70, True),
+}
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class _CudaBackend:
+    """Device buffers = torch CUDA tensors."""
+
+    name = "cuda"
+
+    def __init__(self, device):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise DwbcError("libdwbc_b200 needs a CUDA device (no CPU fallback)")
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.index = device
+
+    def lib(self):
+        return load_library()
+
+    def empty(self, shape, dtype="f8"):
+        t = self.torch
+        dt = {"f8": t.float64, "u1": t.uint8, "i4": t.int32, "u4": t.int32}[dtype]
+        return t.empty(shape, dtype=dt, device=self.device)
+
+    def check(self, x, dtype="f8"):
+        t = self.torch
+        dt = {"f8": t.float64, "u1": t.uint8, "i4": t.int32}[dtype]
+        if not isinstance(x, t.Tensor) or not x.is_cuda or x.device != self.device or x.dtype != dt or not x.is_contiguous():
+            raise DwbcError(f"expected a contiguous {dt} CUDA tensor on {self.device}")
+        return x
+
+    def ptr(self, x):
+        return C.c_void_p(x.data_ptr())
+
+    def stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def to_numpy(self, x):
+        return x.cpu().numpy()
+
+    def from_numpy(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
+
+class RobotDataBatch:
+    def __init__(self, urdf_path: str, batch: int, device: int = 0, floating: bool = True, _backend=None):
+        self.be = _backend if _backend is not None else _CudaBackend(device)
+        self.L = self.be.lib()
+        self._model = self.L.dwbc_model_load_urdf(urdf_path.encode(), 1 if floating else 0)
+        if not self._model:
+            raise DwbcError(self._err())
+        n, m, nb, mass = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        self.L.dwbc_model_info(self._model, C.byref(n), C.byref(m), C.byref(nb), C.byref(mass))
+        self.system_dof_, self.model_dof_, self.n_links, self.total_mass_ = n.value, m.value, nb.value, mass.value
+        self.batch = int(batch)
+        self._h = self.L.dwbc_batch_create(self._model, self.batch, getattr(self.be, "index", 0))
+        if not self._h:
+            raise DwbcError(self._err())
+        cm, rm, ml, mt = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self.L.dwbc_batch_limits(self._h, C.byref(cm), C.byref(rm), C.byref(ml), C.byref(mt))
+        self.cmax, self.rmax = cm.value, rm.value
+        self.task_dofs = []
+        self.ncontact = 0
+        self._keep = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.L.dwbc_batch_destroy(self._h)
+            if getattr(self, "_model", None):
+                self.L.dwbc_model_destroy(self._model)
+        except Exception:
+            pass
+
+    def _err(self):
+        return self.L.dwbc_last_error().decode()
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise DwbcError(f"dwbc error {rc}: {self._err()}")
+        return rc
+
+    # ---- model queries ----
+    def link_id(self, name: str) -> int:
+        return self.L.dwbc_model_link_id(self._model, name.encode())
+
+    def link_name(self, link: int) -> str:
+        s = self.L.dwbc_model_link_name(self._model, link)
+        return s.decode() if s else ""
+
+    # ---- setup ----
+    def _link(self, link):
+        if isinstance(link, str):
+            i = self.link_id(link)
+            if i < 0:
+                raise DwbcError("Link Name is Wrong : " + link)
+            return i
+        return int(link)
+
+    def add_contact_constraint(self, link, contact_type, point, normal=(0, 0, 1), lx=0.0, ly=0.0):
+        p = (C.c_double * 3)(*point)
+        nrm = (C.c_double * 3)(*normal)
+        idx = self._ck(self.L.dwbc_batch_add_contact(self._h, self._link(link), int(contact_type), p, nrm, float(lx), float(ly)))
+        self.ncontact += 1
+        return idx
+
+    def set_friction_ratio(self, contact, mu, muz):
+        self._ck(self.L.dwbc_batch_set_friction(self._h, int(contact), float(mu), float(muz)))
+
+    def add_task_space(self, level, task_mode, link, point=(0, 0, 0)):
+        p = (C.c_double * 3)(*point)
+        self._ck(self.L.dwbc_batch_add_task(self._h, int(level), int(task_mode), self._link(link), p))
+        dof = 6 if task_mode <= TASK_LINK_6D_CUSTOM_FRAME else 3
+        if level == len(self.task_dofs):
+            self.task_dofs.append(dof)
+        else:
+            self.task_dofs[level] += dof
+
+    def add_custom_task_space(self, level, task_dof):
+        self._ck(self.L.dwbc_batch_add_custom_task(self._h, int(level), int(task_dof)))
+        self.task_dofs.append(int(task_dof))
+
+    def clear_task_space(self):
+        self._ck(self.L.dwbc_batch_clear_tasks(self._h))
+        self.task_dofs = []
+
+    def set_torque_limit(self, tlim):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(tlim, dtype=np.float64), (self.model_dof_,)))
+        self._ck(self.L.dwbc_batch_set_torque_limit(self._h, a.ctypes.data_as(_dp)))
+
+    # ---- per cycle (device tensors) ----
+    def update_kinematics(self, q, qdot):
+        be = self.be
+        q, qdot = be.check(q), be.check(qdot)
+        if tuple(q.shape) != (self.batch, self.system_dof_ + 1) or tuple(qdot.shape) != (self.batch, self.system_dof_):
+            raise DwbcError("q size is not matched")
+        self._keep["q"], self._keep["qd"] = q, qdot
+        self._ck(self.L.dwbc_batch_update_kinematics(self._h, be.ptr(q), be.ptr(qdot), be.stream()))
+
+    def set_contact(self, flags):
+        be = self.be
+        flags = be.check(flags, "u1")
+        if tuple(flags.shape) != (self.batch, self.ncontact):
+            raise DwbcError("contact flags must be [batch, number of registered contacts]")
+        self._keep["flags"] = flags
+        self._ck(self.L.dwbc_batch_set_contact(self._h, be.ptr(flags), be.stream()))
+
+    def calc_contact_constraint(self):
+        self._ck(self.L.dwbc_batch_calc_contact_constraint(self._h, self.be.stream()))
+
+    def set_task_space(self, level, fstar, J=None):
+        be = self.be
+        fstar = be.check(fstar)
+        t = self.task_dofs[level]
+        if tuple(fstar.shape) != (self.batch, t):
+            raise DwbcError("ERROR : task dof not matching!")
+        self._keep[("f", level)] = fstar
+        jp, per_state = None, 0
+        if J is not None:
+            J = be.check(J)
+            # J is given in the natural (rows = task dof, cols = system dof) orientation; the ABI wants column-major
+            if J.ndim == 2:
+                Jc = J.t().contiguous()
+            else:
+                Jc = J.transpose(1, 2).contiguous()
+                per_state = 1
+            self._keep[("J", level)] = Jc
+            jp = be.ptr(Jc)
+        self._ck(self.L.dwbc_batch_set_task(self._h, int(level), be.ptr(fstar), jp, per_state, be.stream()))
+
+    def solve(self, stages=SOLVE_GRAV | SOLVE_TASK | SOLVE_HQP | SOLVE_REDIST, out=None):
+        """Runs the selected stages; returns (torque_grav, torque_task, torque_contact, status) device tensors."""
+        be = self.be
+        B, m = self.batch, self.model_dof_
+        if out is None:
+            out = (be.empty((B, m)), be.empty((B, m)), be.empty((B, m)), be.empty((B,), "i4"))
+        tg, tt, tc, st = out
+        self._ck(self.L.dwbc_batch_solve(self._h, int(stages), be.ptr(tg), be.ptr(tt), be.ptr(tc), be.ptr(st), be.stream()))
+        return tg, tt, tc, st
+
+    def get(self, name, level=0):
+        """Public RobotData field `name` for all states: tensor [B, rows, cols] (vectors: [B, rows])."""
+        be = self.be
+        mid, per_level = _MATS[name]
+        r, c = C.c_int(), C.c_int()
+        self._ck(self.L.dwbc_batch_get_matrix(self._h, mid, int(level), None, C.byref(r), C.byref(c), be.stream()))
+        buf = be.empty((self.batch, c.value, r.value))  # column-major per state
+        self._ck(self.L.dwbc_batch_get_matrix(self._h, mid, int(level), be.ptr(buf), None, None, be.stream()))
+        out = buf.transpose(1, 2) if hasattr(buf, "transpose") and not isinstance(buf, np.ndarray) else np.swapaxes(buf, 1, 2)
+        if c.value == 1:
+            out = out[:, :, 0]
+        return out
+
+    def active_set(self, level):
+        """Active rows of the level's QP (level = -1: redistribution QP) as a list of row-index lists."""
+        be = self.be
+        buf = be.empty((self.batch, 4), "u4")
+        self._ck(self.L.dwbc_batch_get_active_set(self._h, int(level), be.ptr(buf), be.stream()))
+        words = be.to_numpy(buf).astype(np.uint32)
+        res = []
+        for b in range(self.batch):
+            rows = [i for i in range(128) if (int(words[b, i >> 5]) >> (i & 31)) & 1]
+            res.append(rows)
+        return res
+
+    def qp_iterations(self):
+        buf = self.be.empty((self.batch,), "i4")
+        self._ck(self.L.dwbc_batch_get_qp_iterations(self._h, self.be.ptr(buf), self.be.stream()))
+        return buf
+
+    # ---- whole cycle from host buffers (pinned numpy / torch CPU tensors) ----
+    def cycle_host(self, stages, q, qdot, fstars, flags, out=None):
+        """H2D + all stages + D2H through dwbc_batch_cycle_host.  All arguments are host arrays (numpy)."""
+        B, m = self.batch, self.model_dof_
+
+        def hp(a):
+            return C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
+
+        if out is None:
+            out = (np.empty((B, m)), np.empty((B, m)), np.empty((B, m)), np.empty((B,), dtype=np.int32))
+        tg, tt, tc, st = out
+        fcat = fstars if not isinstance(fstars, (list, tuple)) else (np.concatenate([np.ascontiguousarray(f).reshape(-1) for f in fstars]) if fstars else None)
+        self._ck(self.L.dwbc_batch_cycle_host(self._h, int(stages), hp(q), hp(qdot), hp(fcat) if fcat is not None else None, hp(flags),
+                                             hp(tg), hp(tt), hp(tc), hp(st), self.be.stream()))
+        return tg, tt, tc, st

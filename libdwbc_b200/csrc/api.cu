@@ -1,0 +1,545 @@
+// C ABI of the batched whole-body-control hot path (include/dwbc_b200.h).  Host logic only: argument
+// checking, workspace ownership, kernel launches.  There is deliberately no CPU code path for the math.
+#include "../../include/dwbc_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "batch.h"
+#include "cuda_compat.h"
+#include "kernels_contact.cuh"
+#include "kernels_hqp.cuh"
+#include "kernels_task.cuh"
+#include "model.h"
+
+using namespace dwbc;
+
+struct dwbc_model {
+    HostModel hm;
+};
+
+struct dwbc_batch {
+    HostModel hm;
+    int B = 0, device = 0;
+    BatchCfg cfg;
+    DevModel *d_model = nullptr;
+    BatchCfg *d_cfg = nullptr;
+    bool cfg_dirty = true;
+    Work w;
+    std::vector<void *> allocs;
+    std::vector<void *> task_allocs;
+    bool tasks_allocated = false;
+    double *d_scratch = nullptr;  // B*n*n doubles (N_C on request, staging)
+    // staging for the *_host entry point
+    double *d_q = nullptr, *d_qd = nullptr, *d_fstar = nullptr, *d_tg = nullptr, *d_tt = nullptr, *d_tc = nullptr;
+    uint8_t *d_flags = nullptr;
+    int32_t *d_status = nullptr;
+    size_t d_fstar_cap = 0;
+    int sm_count = 148;
+    // call-order tracking
+    bool have_kin = false, have_contact = false, have_cc = false;
+};
+
+namespace {
+thread_local std::string g_err;
+long long g_launches = 0;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+bool cuda_ok(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+#define CK(call)                                               \
+    do {                                                       \
+        if (!cuda_ok((call), #call)) return DWBC_ERR_CUDA;     \
+    } while (0)
+
+template <class T>
+bool dev_alloc(dwbc_batch *b, T **p, size_t count, std::vector<void *> *list = nullptr) {
+    void *raw = nullptr;
+    if (!cuda_ok(cudaMalloc(&raw, count * sizeof(T) + 16), "cudaMalloc")) return false;
+    cudaMemset(raw, 0, count * sizeof(T) + 16);
+    (list ? *list : b->allocs).push_back(raw);
+    *p = (T *)raw;
+    return true;
+}
+
+constexpr int WARPS_PER_BLOCK = 4;
+inline int grid_for(int B, int wpb) { return (B + wpb - 1) / wpb; }
+
+int upload_cfg(dwbc_batch *b, cudaStream_t st) {
+    if (!b->cfg_dirty) return DWBC_OK;
+    CK(cudaMemcpyAsync(b->d_cfg, &b->cfg, sizeof(BatchCfg), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // cfg lives on the host stack of the handle: keep it simple and safe
+    b->cfg_dirty = false;
+    return DWBC_OK;
+}
+
+int alloc_tasks(dwbc_batch *b) {
+    if (b->tasks_allocated) return DWBC_OK;
+    const size_t B = b->B, n = b->w.n, m = b->w.m;
+    for (int l = 0; l < b->cfg.nlevels; l++) {
+        const size_t t = b->cfg.tasks[l].dof;
+        if (!dev_alloc(b, &b->w.Jt[l], B * t * n, &b->task_allocs) || !dev_alloc(b, &b->w.Lamt[l], B * t * t, &b->task_allocs) ||
+            !dev_alloc(b, &b->w.Jkt[l], B * m * t, &b->task_allocs) || !dev_alloc(b, &b->w.Null[l], B * m * m, &b->task_allocs) ||
+            !dev_alloc(b, &b->w.Ntq[l], B * m * t, &b->task_allocs) || !dev_alloc(b, &b->w.fstar_qp[l], B * t, &b->task_allocs) ||
+            !dev_alloc(b, &b->w.contact_qp[l], B * RMAX, &b->task_allocs) || !dev_alloc(b, &b->w.torque_h[l], B * m, &b->task_allocs) ||
+            !dev_alloc(b, &b->w.active[l], B * ACTIVE_WORDS, &b->task_allocs))
+            return DWBC_ERR_CUDA;
+    }
+    b->tasks_allocated = true;
+    return DWBC_OK;
+}
+void free_tasks(dwbc_batch *b) {
+    for (void *p : b->task_allocs) cudaFree(p);
+    b->task_allocs.clear();
+    b->tasks_allocated = false;
+    for (int l = 0; l < MAX_LEVELS; l++) {
+        b->w.Jt[l] = b->w.Lamt[l] = b->w.Jkt[l] = b->w.Null[l] = b->w.Ntq[l] = nullptr;
+        b->w.fstar_qp[l] = b->w.contact_qp[l] = b->w.torque_h[l] = nullptr;
+        b->w.active[l] = nullptr;
+        b->w.fstar[l] = b->w.jcustom[l] = nullptr;
+        b->w.jcustom_per_state[l] = 0;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+const char *dwbc_last_error(void) { return g_err.c_str(); }
+long long dwbc_launch_count(void) { return g_launches; }
+
+dwbc_model_t *dwbc_model_load_urdf(const char *urdf_path, int floating) {
+    if (!urdf_path) {
+        g_err = "urdf_path is null";
+        return nullptr;
+    }
+    try {
+        dwbc_model *m = new dwbc_model();
+        m->hm = load_urdf_model(urdf_path, floating != 0);
+        return m;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void dwbc_model_destroy(dwbc_model_t *m) { delete m; }
+int dwbc_model_info(const dwbc_model_t *m, int *system_dof, int *model_dof, int *n_links, double *total_mass) {
+    if (!m) return fail(DWBC_ERR_ARG, "model is null");
+    if (system_dof) *system_dof = m->hm.dev.n;
+    if (model_dof) *model_dof = m->hm.dev.m;
+    if (n_links) *n_links = m->hm.dev.nb;
+    if (total_mass) *total_mass = m->hm.dev.total_mass;
+    return DWBC_OK;
+}
+int dwbc_model_link_id(const dwbc_model_t *m, const char *name) { return m ? m->hm.link_id(name) : -1; }
+const char *dwbc_model_link_name(const dwbc_model_t *m, int link) {
+    if (!m || link < 0 || link > m->hm.dev.nb) return nullptr;
+    return link == m->hm.dev.nb ? "COM" : m->hm.names[link].c_str();
+}
+
+dwbc_batch_t *dwbc_batch_create(const dwbc_model_t *m, int batch, int device) {
+    if (!m || batch <= 0) {
+        g_err = "dwbc_batch_create: bad arguments";
+        return nullptr;
+    }
+    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return nullptr;
+    dwbc_batch *b = new (std::nothrow) dwbc_batch();
+    if (!b) return nullptr;
+    b->hm = m->hm;
+    b->B = batch;
+    b->device = device;
+    std::memset(&b->cfg, 0, sizeof(b->cfg));
+    std::memset(&b->w, 0, sizeof(b->w));
+    cudaDeviceProp prop;
+    if (cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) b->sm_count = prop.multiProcessorCount;
+    Work &w = b->w;
+    w.B = batch;
+    w.n = b->hm.dev.n;
+    w.m = b->hm.dev.m;
+    w.nb = b->hm.dev.nb;
+    const size_t B = batch, n = w.n, mm = w.m, nb = w.nb;
+    bool ok = dev_alloc(b, &b->d_model, 1) && dev_alloc(b, &b->d_cfg, 1) && dev_alloc(b, &w.A, B * n * n) && dev_alloc(b, &w.Ainv, B * n * n) &&
+              dev_alloc(b, &w.G, B * n) && dev_alloc(b, &w.Bnl, B * n) && dev_alloc(b, &w.pose, B * nb * POSE_STRIDE) &&
+              dev_alloc(b, &w.com, B * 16) && dev_alloc(b, &w.linkvel, B * nb * 6) && dev_alloc(b, &w.Jc, B * CMAX * n) &&
+              dev_alloc(b, &w.cdof, B) && dev_alloc(b, &w.cidx, B * MAX_ACTIVE_CONTACTS) && dev_alloc(b, &w.Lam, B * CMAX * CMAX) &&
+              dev_alloc(b, &w.Jbar, B * CMAX * n) && dev_alloc(b, &w.AinvNc, B * n * n) && dev_alloc(b, &w.W, B * mm * mm) &&
+              dev_alloc(b, &w.Winv, B * mm * mm) && dev_alloc(b, &w.V2, B * RMAX * mm) && dev_alloc(b, &w.NwJw, B * mm * RMAX) &&
+              dev_alloc(b, &w.PC, B * CMAX) && dev_alloc(b, &w.tau_grav, B * mm) && dev_alloc(b, &w.status, B) &&
+              dev_alloc(b, &w.tau_task, B * mm) && dev_alloc(b, &w.tau_contact, B * mm) && dev_alloc(b, &w.cf_redis, B * RMAX) &&
+              dev_alloc(b, &w.active[MAX_LEVELS], B * ACTIVE_WORDS) && dev_alloc(b, &w.qp_iters, B) && dev_alloc(b, &b->d_scratch, B * n * n) &&
+              dev_alloc(b, &b->d_q, B * (n + 1)) && dev_alloc(b, &b->d_qd, B * n) && dev_alloc(b, &b->d_flags, B * MAX_CONTACTS) &&
+              dev_alloc(b, &b->d_tg, B * mm) && dev_alloc(b, &b->d_tt, B * mm) && dev_alloc(b, &b->d_tc, B * mm) && dev_alloc(b, &b->d_status, B);
+    if (ok) ok = cuda_ok(cudaMemcpy(b->d_model, &b->hm.dev, sizeof(DevModel), cudaMemcpyHostToDevice), "cudaMemcpy(model)");
+    if (!ok) {
+        dwbc_batch_destroy(b);
+        return nullptr;
+    }
+    return b;
+}
+void dwbc_batch_destroy(dwbc_batch_t *b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    for (void *p : b->allocs) cudaFree(p);
+    for (void *p : b->task_allocs) cudaFree(p);
+    if (b->d_fstar) cudaFree(b->d_fstar);
+    delete b;
+}
+int dwbc_batch_size(const dwbc_batch_t *b) { return b ? b->B : 0; }
+int dwbc_batch_limits(const dwbc_batch_t *, int *cmax, int *rmax, int *max_levels, int *max_task_dof) {
+    if (cmax) *cmax = CMAX;
+    if (rmax) *rmax = RMAX;
+    if (max_levels) *max_levels = MAX_LEVELS;
+    if (max_task_dof) *max_task_dof = MAX_TASK_DOF;
+    return DWBC_OK;
+}
+
+int dwbc_batch_add_contact(dwbc_batch_t *b, int link, int contact_type, const double point[3], const double normal[3], double lx, double ly) {
+    if (!b || !point) return fail(DWBC_ERR_ARG, "add_contact: null argument");
+    (void)normal;  // kept for signature parity; the reference stores it but the path never reads it
+    if (contact_type != DWBC_CONTACT_6D) return fail(DWBC_ERR_ARG, "add_contact: only CONTACT_6D is supported on this path");
+    if (link < 0 || link >= b->hm.dev.nb) return fail(DWBC_ERR_ARG, "add_contact: link out of range");
+    for (int i = 0; i < b->cfg.ncontact; i++)
+        if (b->cfg.contacts[i].link == link) return fail(DWBC_ERR_ARG, "Contact Constraint Already Exist for Link");
+    if (b->cfg.ncontact >= MAX_CONTACTS) return fail(DWBC_ERR_LIMIT, "add_contact: too many contacts");
+    ContactCfg &c = b->cfg.contacts[b->cfg.ncontact];
+    c.link = link;
+    for (int k = 0; k < 3; k++) c.point[k] = point[k];
+    c.lx = lx;
+    c.ly = ly;
+    c.mu = 0.2;  // reference src/contact_constraint.cpp:42
+    c.muz = 0.2;
+    b->cfg_dirty = true;
+    return b->cfg.ncontact++;
+}
+int dwbc_batch_set_friction(dwbc_batch_t *b, int contact, double mu, double muz) {
+    if (!b || contact < 0 || contact >= b->cfg.ncontact) return fail(DWBC_ERR_ARG, "set_friction: bad contact index");
+    b->cfg.contacts[contact].mu = mu;
+    b->cfg.contacts[contact].muz = muz;
+    b->cfg_dirty = true;
+    return DWBC_OK;
+}
+int dwbc_batch_add_task(dwbc_batch_t *b, int level, int task_mode, int link, const double point[3]) {
+    if (!b || !point) return fail(DWBC_ERR_ARG, "add_task: null argument");
+    if (task_mode < DWBC_TASK_LINK_6D || task_mode > DWBC_TASK_LINK_ROTATION_CUSTOM_FRAME) return fail(DWBC_ERR_ARG, "add_task: unknown task mode");
+    if (link < 0 || link > b->hm.dev.nb) return fail(DWBC_ERR_ARG, "Link Name is not Correct");
+    BatchCfg &c = b->cfg;
+    if (level < 0 || level > c.nlevels) return fail(DWBC_ERR_ARG, "add_task: hierarchy levels must be added in order");
+    int ntl = 0;
+    for (int l = 0; l < c.nlevels; l++) {
+        for (int k = 0; k < c.tasks[l].link_count; k++)
+            if (c.tlinks[c.tasks[l].link_start + k].link == link) return fail(DWBC_ERR_ARG, "Task Space Already Exist for Link");
+        ntl += c.tasks[l].link_count;
+    }
+    if (ntl >= MAX_TASK_LINKS) return fail(DWBC_ERR_LIMIT, "add_task: too many task links");
+    const int dof = task_mode <= DWBC_TASK_LINK_6D_CUSTOM_FRAME ? 6 : 3;
+    if (level == c.nlevels) {
+        if (c.nlevels >= MAX_LEVELS) return fail(DWBC_ERR_LIMIT, "add_task: too many hierarchy levels");
+        TaskCfg &t = c.tasks[c.nlevels++];
+        t.custom = 0;
+        t.dof = 0;
+        t.link_start = ntl;
+        t.link_count = 0;
+    } else if (level != c.nlevels - 1) {
+        // links of a level are stored contiguously: only the newest level can still grow
+        return fail(DWBC_ERR_ARG, "add_task: links can only be appended to the most recently added level");
+    }
+    TaskCfg &t = c.tasks[level];
+    if (t.custom) return fail(DWBC_ERR_ARG, "add_task: level holds a custom task");
+    if (t.dof + dof > MAX_TASK_DOF) return fail(DWBC_ERR_LIMIT, "add_task: task dof exceeds MAX_TASK_DOF");
+    TaskLinkCfg &tl = c.tlinks[t.link_start + t.link_count++];
+    tl.mode = task_mode;
+    tl.link = link;
+    tl.dof = dof;
+    for (int k = 0; k < 3; k++) tl.point[k] = point[k];
+    t.dof += dof;
+    b->cfg_dirty = true;
+    free_tasks(b);
+    return DWBC_OK;
+}
+int dwbc_batch_add_custom_task(dwbc_batch_t *b, int level, int task_dof) {
+    if (!b) return fail(DWBC_ERR_ARG, "add_custom_task: null handle");
+    BatchCfg &c = b->cfg;
+    if (level != c.nlevels) return fail(DWBC_ERR_ARG, "add_custom_task: hierarchy levels must be added in order");
+    if (c.nlevels >= MAX_LEVELS) return fail(DWBC_ERR_LIMIT, "add_custom_task: too many hierarchy levels");
+    if (task_dof <= 0 || task_dof > MAX_TASK_DOF) return fail(DWBC_ERR_LIMIT, "add_custom_task: task dof out of range");
+    int ntl = 0;
+    for (int l = 0; l < c.nlevels; l++) ntl += c.tasks[l].link_count;
+    TaskCfg &t = c.tasks[c.nlevels++];
+    t.custom = 1;
+    t.dof = task_dof;
+    t.link_start = ntl;
+    t.link_count = 0;
+    b->cfg_dirty = true;
+    free_tasks(b);
+    return DWBC_OK;
+}
+int dwbc_batch_clear_tasks(dwbc_batch_t *b) {
+    if (!b) return fail(DWBC_ERR_ARG, "clear_tasks: null handle");
+    b->cfg.nlevels = 0;
+    b->cfg_dirty = true;
+    free_tasks(b);
+    return DWBC_OK;
+}
+int dwbc_batch_set_torque_limit(dwbc_batch_t *b, const double *tlim_host) {
+    if (!b || !tlim_host) return fail(DWBC_ERR_ARG, "set_torque_limit: null argument");
+    b->cfg.tlim_set = 1;
+    for (int i = 0; i < b->w.m; i++) b->cfg.tlim[i] = tlim_host[i];
+    b->cfg_dirty = true;
+    return DWBC_OK;
+}
+
+int dwbc_batch_update_kinematics(dwbc_batch_t *b, const double *q_dev, const double *qdot_dev, void *stream) {
+    if (!b || !q_dev || !qdot_dev) return fail(DWBC_ERR_ARG, "update_kinematics: null argument");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wpb = WARPS_PER_BLOCK, grid = grid_for(b->B, wpb);
+    const int n = b->w.n;
+    CK(cudaMemsetAsync(b->w.status, 0xff, sizeof(int) * b->B, st));  // "valid so far"; stages clear it on failure
+    {
+        size_t smem = sizeof(double) * wpb * rbd_smem_doubles(b->w.nb);
+        DWBC_LAUNCH(rbd_kernel, grid, wpb * 32, smem, st, b->d_model, q_dev, qdot_dev, b->w);
+        g_launches++;
+    }
+    {
+        size_t smem = sizeof(double) * wpb * ainv_smem_doubles(n);
+        CK(cudaFuncSetAttribute(ainv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DWBC_LAUNCH(ainv_kernel, grid, wpb * 32, smem, st, b->w);
+        g_launches++;
+    }
+    CK(cudaGetLastError());
+    b->have_kin = true;
+    b->have_contact = b->have_cc = false;
+    return DWBC_OK;
+}
+
+int dwbc_batch_set_contact(dwbc_batch_t *b, const uint8_t *flags_dev, void *stream) {
+    if (!b || !flags_dev) return fail(DWBC_ERR_ARG, "set_contact: null argument");
+    if (!b->have_kin) return fail(DWBC_ERR_ORDER, "set_contact: call update_kinematics first");
+    if (b->cfg.ncontact == 0) return fail(DWBC_ERR_ORDER, "set_contact: no contact registered");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = upload_cfg(b, st);
+    if (rc) return rc;
+    const int wpb = WARPS_PER_BLOCK, grid = grid_for(b->B, wpb);
+    DWBC_LAUNCH(contact_jacobian_kernel, grid, wpb * 32, 0, st, b->d_model, b->d_cfg, flags_dev, b->w);
+    g_launches++;
+    CK(cudaGetLastError());
+    b->have_contact = true;
+    b->have_cc = false;
+    return DWBC_OK;
+}
+
+int dwbc_batch_calc_contact_constraint(dwbc_batch_t *b, void *stream) {
+    if (!b) return fail(DWBC_ERR_ARG, "calc_contact_constraint: null handle");
+    if (!b->have_contact) return fail(DWBC_ERR_ORDER, "calc_contact_constraint: call set_contact first");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wpb = 2, grid = grid_for(b->B, wpb);
+    ContactSmem L(b->w.n, b->w.m);
+    size_t smem = sizeof(double) * wpb * L.total;
+    CK(cudaFuncSetAttribute(contact_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DWBC_LAUNCH(contact_dynamics_kernel, grid, wpb * 32, smem, st, b->d_model, b->w);
+    g_launches++;
+    CK(cudaGetLastError());
+    b->have_cc = true;
+    return DWBC_OK;
+}
+
+int dwbc_batch_set_task(dwbc_batch_t *b, int level, const double *fstar_dev, const double *jtask_dev, int jtask_per_state, void *) {
+    if (!b || !fstar_dev) return fail(DWBC_ERR_ARG, "set_task: null argument");
+    if (level < 0 || level >= b->cfg.nlevels) return fail(DWBC_ERR_ARG, "ERROR : task space size overflow");
+    if (b->cfg.tasks[level].custom && !jtask_dev && !b->w.jcustom[level]) return fail(DWBC_ERR_ARG, "set_task: a custom task needs its Jacobian");
+    b->w.fstar[level] = fstar_dev;
+    if (jtask_dev) {
+        b->w.jcustom[level] = jtask_dev;
+        b->w.jcustom_per_state[level] = jtask_per_state ? 1 : 0;
+    }
+    return DWBC_OK;
+}
+
+int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *tau_task_dev, double *tau_contact_dev, int32_t *status_dev,
+                     void *stream) {
+    if (!b) return fail(DWBC_ERR_ARG, "solve: null handle");
+    if (!b->have_cc) return fail(DWBC_ERR_ORDER, "solve: call calc_contact_constraint first");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = upload_cfg(b, st);
+    if (rc) return rc;
+    const size_t B = b->B, m = b->w.m;
+    if (stages & DWBC_SOLVE_HQP) stages |= DWBC_SOLVE_TASK;
+    if (stages & (DWBC_SOLVE_TASK | DWBC_SOLVE_REDIST)) {
+        if (stages & DWBC_SOLVE_TASK) {
+            if (b->cfg.nlevels == 0) return fail(DWBC_ERR_ORDER, "solve: no task registered");
+            for (int l = 0; l < b->cfg.nlevels; l++)
+                if (!b->w.fstar[l]) return fail(DWBC_ERR_ORDER, "solve: set_task has not been called for every level");
+        }
+        rc = alloc_tasks(b);
+        if (rc) return rc;
+    }
+    if (stages & DWBC_SOLVE_TASK) {
+        const int wpb = 2, grid = grid_for(b->B, wpb);
+        TaskSmem L(b->w.n, b->w.m);
+        size_t smem = sizeof(double) * wpb * L.total;
+        CK(cudaFuncSetAttribute(task_space_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DWBC_LAUNCH(task_space_kernel, grid, wpb * 32, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0);
+        g_launches++;
+    } else {
+        CK(cudaMemsetAsync(b->w.tau_task, 0, sizeof(double) * B * m, st));
+        CK(cudaMemsetAsync(b->w.tau_contact, 0, sizeof(double) * B * m, st));
+    }
+    if (stages & (DWBC_SOLVE_HQP | DWBC_SOLVE_REDIST)) {
+        const int wpb = 2, grid = grid_for(b->B, wpb);
+        HqpSmem L(b->w.n, b->w.m);
+        size_t smem = sizeof(double) * wpb * L.total;
+        CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DWBC_LAUNCH(hqp_kernel, grid, wpb * 32, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0,
+                    (stages & DWBC_SOLVE_REDIST) ? 1 : 0);
+        g_launches++;
+    }
+    CK(cudaGetLastError());
+    if (tau_grav_dev) CK(cudaMemcpyAsync(tau_grav_dev, b->w.tau_grav, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));
+    if (tau_task_dev) CK(cudaMemcpyAsync(tau_task_dev, b->w.tau_task, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));
+    if (tau_contact_dev) CK(cudaMemcpyAsync(tau_contact_dev, b->w.tau_contact, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));
+    if (status_dev) CK(cudaMemcpyAsync(status_dev, b->w.status, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+    return DWBC_OK;
+}
+
+int dwbc_batch_get_matrix(dwbc_batch_t *b, int which, int level, double *out_dev, int *rows, int *cols, void *stream) {
+    if (!b) return fail(DWBC_ERR_ARG, "get_matrix: null handle");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Work &w = b->w;
+    const int n = w.n, m = w.m, nb = w.nb;
+    const double *src = nullptr;
+    int r = 0, c = 0;
+    int t = 0;
+    if (which >= DWBC_MAT_J_TASK) {
+        if (level < 0 || level >= b->cfg.nlevels) return fail(DWBC_ERR_ARG, "get_matrix: level out of range");
+        if (!b->tasks_allocated) return fail(DWBC_ERR_ORDER, "get_matrix: task quantities have not been computed yet");
+        t = b->cfg.tasks[level].dof;
+    }
+    switch (which) {
+    case DWBC_MAT_A: src = w.A; r = n; c = n; break;
+    case DWBC_MAT_A_INV: src = w.Ainv; r = n; c = n; break;
+    case DWBC_MAT_G: src = w.G; r = n; c = 1; break;
+    case DWBC_MAT_B: src = w.Bnl; r = n; c = 1; break;
+    case DWBC_MAT_J_C: src = w.Jc; r = CMAX; c = n; break;
+    case DWBC_MAT_LAMBDA_C: src = w.Lam; r = CMAX; c = CMAX; break;
+    case DWBC_MAT_J_C_INV_T: src = w.Jbar; r = CMAX; c = n; break;
+    case DWBC_MAT_A_INV_N_C: src = w.AinvNc; r = n; c = n; break;
+    case DWBC_MAT_W: src = w.W; r = m; c = m; break;
+    case DWBC_MAT_W_INV: src = w.Winv; r = m; c = m; break;
+    case DWBC_MAT_V2: src = w.V2; r = RMAX; c = m; break;
+    case DWBC_MAT_NWJW: src = w.NwJw; r = m; c = RMAX; break;
+    case DWBC_MAT_P_C: src = w.PC; r = CMAX; c = 1; break;
+    case DWBC_MAT_TORQUE_GRAV: src = w.tau_grav; r = m; c = 1; break;
+    case DWBC_MAT_TORQUE_TASK: src = w.tau_task; r = m; c = 1; break;
+    case DWBC_MAT_TORQUE_CONTACT: src = w.tau_contact; r = m; c = 1; break;
+    case DWBC_MAT_CF_REDIS: src = w.cf_redis; r = RMAX; c = 1; break;
+    case DWBC_MAT_J_TASK: src = w.Jt[level]; r = t; c = n; break;
+    case DWBC_MAT_LAMBDA_TASK: src = w.Lamt[level]; r = t; c = t; break;
+    case DWBC_MAT_J_KT: src = w.Jkt[level]; r = m; c = t; break;
+    case DWBC_MAT_NULL_TASK: src = w.Null[level]; r = m; c = m; break;
+    case DWBC_MAT_FSTAR_QP: src = w.fstar_qp[level]; r = t; c = 1; break;
+    case DWBC_MAT_CONTACT_QP: src = w.contact_qp[level]; r = RMAX; c = 1; break;
+    case DWBC_MAT_TORQUE_H: src = w.torque_h[level]; r = m; c = 1; break;
+    case DWBC_MAT_N_C: r = n; c = n; break;
+    case DWBC_MAT_COM: r = 3; c = 1; break;
+    case DWBC_MAT_LINK_POS: r = 3; c = nb; break;
+    case DWBC_MAT_LINK_ROT: r = 9; c = nb; break;
+    case DWBC_MAT_LINK_VEL: src = w.linkvel; r = 6; c = nb; break;
+    default: return fail(DWBC_ERR_ARG, "get_matrix: unknown matrix id");
+    }
+    if (rows) *rows = r;
+    if (cols) *cols = c;
+    if (!out_dev) return DWBC_OK;
+    const size_t bytes = sizeof(double) * (size_t)b->B * r * c;
+    if (src) {
+        CK(cudaMemcpyAsync(out_dev, src, bytes, cudaMemcpyDeviceToDevice, st));
+        return DWBC_OK;
+    }
+    const int wpb = WARPS_PER_BLOCK, grid = grid_for(b->B, wpb);
+    if (which == DWBC_MAT_N_C) {
+        if (!b->have_cc) return fail(DWBC_ERR_ORDER, "get_matrix(N_C): call calc_contact_constraint first");
+        DWBC_LAUNCH(nc_kernel, grid, wpb * 32, 0, st, b->w, out_dev);
+    } else {
+        DWBC_LAUNCH(pose_export_kernel, grid, wpb * 32, 0, st, b->w, which == DWBC_MAT_COM ? 0 : (which == DWBC_MAT_LINK_POS ? 1 : 2), out_dev);
+    }
+    g_launches++;
+    CK(cudaGetLastError());
+    return DWBC_OK;
+}
+
+int dwbc_batch_get_active_set(dwbc_batch_t *b, int level, uint32_t *out_dev, void *stream) {
+    if (!b || !out_dev) return fail(DWBC_ERR_ARG, "get_active_set: null argument");
+    if (level >= b->cfg.nlevels || level < -1) return fail(DWBC_ERR_ARG, "get_active_set: level out of range");
+    if (level >= 0 && !b->tasks_allocated) return fail(DWBC_ERR_ORDER, "get_active_set: no QP has been solved yet");
+    const uint32_t *src = level < 0 ? b->w.active[MAX_LEVELS] : b->w.active[level];
+    CK(cudaMemcpyAsync(out_dev, src, sizeof(uint32_t) * (size_t)b->B * ACTIVE_WORDS, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return DWBC_OK;
+}
+
+int dwbc_batch_get_qp_iterations(dwbc_batch_t *b, int32_t *out_dev, void *stream) {
+    if (!b || !out_dev) return fail(DWBC_ERR_ARG, "get_qp_iterations: null argument");
+    CK(cudaMemcpyAsync(out_dev, b->w.qp_iters, sizeof(int32_t) * (size_t)b->B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return DWBC_OK;
+}
+
+int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, const double *qdot_host, const double *fstar_host,
+                          const uint8_t *flags_host, double *tau_grav_host, double *tau_task_host, double *tau_contact_host,
+                          int32_t *status_host, void *stream) {
+    if (!b || !q_host || !qdot_host || !flags_host) return fail(DWBC_ERR_ARG, "cycle_host: null argument");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = b->B, n = b->w.n, m = b->w.m;
+    const bool need_tasks = (stages & (DWBC_SOLVE_TASK | DWBC_SOLVE_HQP)) != 0;
+    size_t ftot = 0;
+    for (int l = 0; l < b->cfg.nlevels; l++) ftot += (size_t)b->cfg.tasks[l].dof * B;
+    if (need_tasks) {
+        if (!fstar_host) return fail(DWBC_ERR_ARG, "cycle_host: fstar_host is null");
+        if (ftot > b->d_fstar_cap) {
+            if (b->d_fstar) cudaFree(b->d_fstar);
+            void *raw = nullptr;
+            CK(cudaMalloc(&raw, ftot * sizeof(double)));
+            b->d_fstar = (double *)raw;
+            b->d_fstar_cap = ftot;
+        }
+        CK(cudaMemcpyAsync(b->d_fstar, fstar_host, ftot * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(b->d_q, q_host, sizeof(double) * B * (n + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b->d_qd, qdot_host, sizeof(double) * B * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b->d_flags, flags_host, B * b->cfg.ncontact, cudaMemcpyHostToDevice, st));
+    int rc = dwbc_batch_update_kinematics(b, b->d_q, b->d_qd, stream);
+    if (rc) return rc;
+    rc = dwbc_batch_set_contact(b, b->d_flags, stream);
+    if (rc) return rc;
+    rc = dwbc_batch_calc_contact_constraint(b, stream);
+    if (rc) return rc;
+    if (need_tasks) {
+        size_t off = 0;
+        for (int l = 0; l < b->cfg.nlevels; l++) {
+            rc = dwbc_batch_set_task(b, l, b->d_fstar + off, nullptr, 0, stream);
+            if (rc) return rc;
+            off += (size_t)b->cfg.tasks[l].dof * B;
+        }
+    }
+    rc = dwbc_batch_solve(b, stages, b->d_tg, b->d_tt, b->d_tc, b->d_status, stream);
+    if (rc) return rc;
+    if (tau_grav_host) CK(cudaMemcpyAsync(tau_grav_host, b->d_tg, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st));
+    if (tau_task_host) CK(cudaMemcpyAsync(tau_task_host, b->d_tt, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st));
+    if (tau_contact_host) CK(cudaMemcpyAsync(tau_contact_host, b->d_tc, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st));
+    if (status_host) CK(cudaMemcpyAsync(status_host, b->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return DWBC_OK;
+}
+
+}  // extern "C"

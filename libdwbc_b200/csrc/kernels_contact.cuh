@@ -1,0 +1,279 @@
+// Stages a1 (A^{-1}), a2 (contact Jacobian stack), a3 (contact-consistent dynamics) and a4 (gravity
+// compensation).  One warp per robot state, operands staged in shared memory.
+//
+// Reference: RobotData::UpdateKinematics `A_inv_ = A_.llt().solve(I)` (src/dwbc.cpp:307),
+// SetContact/UpdateContactConstraint (include/dwbc.h:432-474, src/dwbc.cpp:433-454),
+// CalculateContactConstraint + PinvCODWB (src/wbd.cpp:108-143, 32-53),
+// CalculateGravityCompensation (src/wbd.cpp:186-192).
+//
+// The arithmetic is restructured (results identical up to rounding):
+//   X = A^{-1} Jc^T,  Lambda_c = (Jc X)^{-1} by Cholesky (the matrix is SPD),  Jbar^T = Lambda_c X^T,
+//   A^{-1} N_c = A^{-1} - X Jbar^T                      (rank-c update instead of a 39^3 product),
+//   null(W) is known in closed form: {S Jc^T f : (Jc^T f)[0:6] = 0}; with an orthonormal basis V of it
+//   W^+ = (W + V V^T)^{-1} - V V^T                      (one SPD inverse instead of a COD),
+//   NwJw = V (Jbar^T[0:r, 6:] V)^{-1},  tau_g = W^+ ((A^{-1}N_c)[6:, :] G),  P_C = Jbar^T G.
+#pragma once
+#include "batch.h"
+#include "kernels_rbd.cuh"
+#include "warp_linalg.cuh"
+
+namespace dwbc {
+
+// ---------------------------------------------------------------- a1: rigid-body dynamics
+__global__ void rbd_kernel(const DevModel *__restrict__ md, const double *__restrict__ q, const double *__restrict__ qd, Work w) {
+    DWBC_DYN_SMEM(smem);
+    const int wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;
+    const long long s = (long long)blockIdx.x * wpb + wid;
+    if (s >= w.B) return;
+    double *rb = (double *)smem + (size_t)wid * rbd_smem_doubles(md->nb);
+    RbdOut out{w.A, w.G, w.Bnl, w.pose, w.com, w.linkvel};
+    rbd_state(md, q + s * (md->n + 1), qd + s * md->n, rb, out, s);
+}
+
+// ---------------------------------------------------------------- a1: A^{-1} by Cholesky
+__host__ __device__ inline int ainv_smem_doubles(int n) { return 2 * (n | 1) * n + n; }
+
+__global__ void ainv_kernel(Work w) {
+    DWBC_DYN_SMEM(smem);
+    const int wpb = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = lane_id();
+    const long long s = (long long)blockIdx.x * wpb + wid;
+    if (s >= w.B) return;
+    const int n = w.n, ld = n | 1;
+    double *L = (double *)smem + (size_t)wid * ainv_smem_doubles(n);
+    double *X = L + ld * n, *rd = X + ld * n;
+    wcopy(n, n, w.A + s * n * n, n, L, ld);
+    __syncwarp();
+    const double minpiv = wchol_lower(n, L, ld, rd);
+    wchol_inverse(n, L, ld, rd, X, ld);
+    wcopy(n, n, X, ld, w.Ainv + s * n * n, n);
+    if (lane == 0 && !(minpiv > 0.0)) w.status[s] = 0;  // mass matrix not SPD: everything downstream is invalid
+}
+
+// ---------------------------------------------------------------- a2: contact Jacobian stack
+__global__ void contact_jacobian_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, const uint8_t *__restrict__ flags,
+                                        Work w) {
+    const int wpb = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = lane_id();
+    const long long s = (long long)blockIdx.x * wpb + wid;
+    if (s >= w.B) return;
+    const int n = w.n;
+    double *Jc = w.Jc + s * CMAX * n;
+    for (int e = lane; e < CMAX * n; e += 32) Jc[e] = 0.0;
+    __syncwarp();
+    int k = 0, over = 0;
+    for (int i = 0; i < cfg->ncontact; i++) {
+        if (!flags[s * cfg->ncontact + i]) continue;
+        if (k >= MAX_ACTIVE_CONTACTS) {
+            over = 1;
+            break;
+        }
+        const ContactCfg &c = cfg->contacts[i];
+        point_jacobian(md, w.pose + s * md->nb * POSE_STRIDE, c.link, v3(c.point[0], c.point[1], c.point[2]), Jc, CMAX, 6 * k, 0, 6);
+        if (lane == 0) w.cidx[s * MAX_ACTIVE_CONTACTS + k] = i;
+        k++;
+    }
+    if (lane == 0) {
+        for (int j = k; j < MAX_ACTIVE_CONTACTS; j++) w.cidx[s * MAX_ACTIVE_CONTACTS + j] = -1;
+        w.cdof[s] = over ? -1 : 6 * k;
+    }
+}
+
+// ---------------------------------------------------------------- a3 + a4
+// shared-memory arena (doubles) per warp
+struct ContactSmem {
+    int ldn, ldc, ldm;
+    int P, Q, Jc, X, Jbar, Lam, Lw, V, Aug, vec, total;
+    __host__ __device__ ContactSmem(int n, int m) {
+        ldn = n | 1; ldc = CMAX | 1; ldm = m | 1;
+        int o = 0;
+        P = o; o += ldn * n;        // A^{-1} -> A^{-1}N_c ; its [6:,6:] block later holds chol(W + V V^T)
+        Q = o; o += ldm * m;        // (W + V V^T)^{-1} -> W^+
+        Jc = o; o += ldc * n;
+        X = o; o += ldn * CMAX;
+        Jbar = o; o += ldc * n;
+        Lam = o; o += ldc * CMAX;   // Jc X -> its Cholesky factor
+        Lw = o; o += ldc * CMAX;    // Lambda_c
+        V = o; o += ldm * (RMAX > 0 ? RMAX : 1);
+        Aug = o; o += 13 * 32;      // Gauss-Jordan scratch, up to 12 rows x 32 columns, ld 13
+        vec = o; o += 4 * (n + 1);  // rdiag / G / u / tau
+        total = o;
+    }
+};
+
+__global__ void contact_dynamics_kernel(const DevModel *__restrict__ md, Work w) {
+    DWBC_DYN_SMEM(smem);
+    const int wpb = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = lane_id();
+    const long long s = (long long)blockIdx.x * wpb + wid;
+    if (s >= w.B) return;
+    const int n = w.n, m = w.m;
+    const ContactSmem L(n, m);
+    double *sm = (double *)smem + (size_t)wid * L.total;
+    double *P = sm + L.P, *Q = sm + L.Q, *Jc = sm + L.Jc, *X = sm + L.X, *Jbar = sm + L.Jbar, *Lam = sm + L.Lam, *Lw = sm + L.Lw;
+    double *V = sm + L.V, *Aug = sm + L.Aug, *rd = sm + L.vec, *Gs = rd + n + 1, *u = Gs + n + 1, *tg = u + n + 1;
+    const int ldn = L.ldn, ldc = L.ldc, ldm = L.ldm;
+    const int c = w.cdof[s];
+    const int r = c > 6 ? c - 6 : 0;
+    int ok = (c > 0 && c <= CMAX) ? 1 : 0;
+    if (w.status[s] == 0) ok = 0;  // A not SPD
+    if (!ok) {
+        if (lane == 0) w.status[s] = 0;
+        return;
+    }
+    wcopy(n, n, w.Ainv + s * n * n, n, P, ldn);
+    wcopy(c, n, w.Jc + s * CMAX * n, CMAX, Jc, ldc);
+    for (int e = lane; e < n; e += 32) Gs[e] = w.G[s * n + e];
+    __syncwarp();
+    // X = A^{-1} Jc^T  (n x c)
+    wgemm<4, 3, false, true>(n, c, n, P, ldn, Jc, ldc, [&](int i, int j, double v) { X[i + j * ldn] = v; });
+    __syncwarp();
+    // Jc X (c x c, SPD) -> Cholesky -> Lambda_c
+    wgemm<2, 2, false, false>(c, c, n, Jc, ldc, X, ldn, [&](int i, int j, double v) { Lam[i + j * ldc] = v; });
+    __syncwarp();
+    const double piv_c = wchol_lower(c, Lam, ldc, rd);
+    wchol_inverse(c, Lam, ldc, rd, Lw, ldc);
+    if (!(piv_c > 0.0)) ok = 0;
+    // Jbar^T = Lambda_c X^T  (c x n)
+    wgemm<3, 4, false, true>(c, n, c, Lw, ldc, X, ldn, [&](int i, int j, double v) { Jbar[i + j * ldc] = v; });
+    __syncwarp();
+    // A^{-1} N_c = A^{-1} - X Jbar^T
+    wgemm<4, 4, false, false>(n, n, c, X, ldn, Jbar, ldc, [&](int i, int j, double v) { P[i + j * ldn] -= v; });
+    __syncwarp();
+    // outputs of a3 that do not depend on the pseudo-inverse
+    {
+        double *g = w.Lam + s * CMAX * CMAX;
+        for (int e = lane; e < CMAX * CMAX; e += 32) {
+            int j = e / CMAX, i = e - j * CMAX;
+            g[e] = (i < c && j < c) ? Lw[i + j * ldc] : 0.0;
+        }
+        g = w.Jbar + s * CMAX * n;
+        for (int e = lane; e < CMAX * n; e += 32) {
+            int j = e / CMAX, i = e - j * CMAX;
+            g[e] = (i < c) ? Jbar[i + j * ldc] : 0.0;
+        }
+        wcopy(n, n, P, ldn, w.AinvNc + s * n * n, n);
+        wcopy(m, m, P + 6 + 6 * ldn, ldn, w.W + s * m * m, m);
+    }
+    // u = (A^{-1}N_c)[6:, :] G   and   P_C = Jbar^T G
+    wgemv<false>(m, n, P + 6, ldn, Gs, [&](int i, double v) { u[i] = v; });
+    wgemv<false>(c, n, Jbar, ldc, Gs, [&](int i, double v) { w.PC[s * CMAX + i] = v; });
+    for (int i = c + lane; i < CMAX; i += 32) w.PC[s * CMAX + i] = 0.0;
+    __syncwarp();
+    double *Wblk = P + 6 + 6 * ldn;  // view of W inside P, leading dimension ldn
+    if (r > 0) {
+        // ---- orthonormal basis V (m x r) of null(W) ----
+        // T = B_1^{-T} [B_2^T ...]  with  B_i = Jc[6i:6i+6, 0:6] : Gauss-Jordan on [B_1^T | B_2^T ...]
+        const int lda = 13;
+        for (int e = lane; e < 6 * (6 + r); e += 32) {
+            int col = e / 6, row = e - col * 6;
+            // column `col` < 6: B_1^T(row, col) = Jc[col][row]; col >= 6: B_k^T(row, col-6) = Jc[col][row] (col indexes Jc rows)
+            Aug[row + col * lda] = Jc[col + row * ldc];
+        }
+        __syncwarp();
+        const double cond1 = wgauss_jordan(6, r, Aug, lda);
+        if (!(cond1 > 1e-14)) ok = 0;
+        // V_raw(a, b) = Jc[6+b][6+a] - sum_e Jc[e][6+a] * T(e, b)
+        for (int e = lane; e < m * r; e += 32) {
+            int b = e / m, a = e - b * m;
+            double v = Jc[(6 + b) + (6 + a) * ldc];
+            for (int k = 0; k < 6; k++) v = fma(-Jc[k + (6 + a) * ldc], Aug[k + (6 + b) * lda], v);
+            V[a + b * ldm] = v;
+        }
+        __syncwarp();
+        // modified Gram-Schmidt, two passes (rows of V across lanes, m may exceed 32)
+        for (int b = 0; b < r; b++) {
+            for (int pass = 0; pass < 2; pass++) {
+                for (int k = 0; k < b; k++) {
+                    double d = 0.0;
+                    for (int a = lane; a < m; a += 32) d = fma(V[a + k * ldm], V[a + b * ldm], d);
+                    d = warp_sum(d);
+                    for (int a = lane; a < m; a += 32) V[a + b * ldm] = fma(-d, V[a + k * ldm], V[a + b * ldm]);
+                }
+            }
+            double nn = 0.0;
+            for (int a = lane; a < m; a += 32) nn = fma(V[a + b * ldm], V[a + b * ldm], nn);
+            nn = warp_sum(nn);
+            if (!(nn > 1e-280)) ok = 0, nn = 1.0;
+            const double rn = 1.0 / sqrt(nn);
+            for (int a = lane; a < m; a += 32) V[a + b * ldm] *= rn;
+            __syncwarp();
+        }
+        // V2 (rows = basis vectors), reference layout r x m
+        {
+            double *g = w.V2 + s * RMAX * m;
+            for (int e = lane; e < RMAX * m; e += 32) {
+                int a = e / RMAX, b = e - a * RMAX;
+                g[e] = b < r ? V[a + b * ldm] : 0.0;
+            }
+        }
+        // W + V V^T in place
+        wgemm<4, 4, false, true>(m, m, r, V, ldm, V, ldm, [&](int i, int j, double v) { Wblk[i + j * ldn] += v; });
+        __syncwarp();
+    } else {
+        double *g = w.V2 + s * RMAX * m;
+        for (int e = lane; e < RMAX * m; e += 32) g[e] = 0.0;
+    }
+    // (W + V V^T)^{-1}
+    const double piv_w = wchol_lower(m, Wblk, ldn, rd);
+    wchol_inverse(m, Wblk, ldn, rd, Q, ldm);
+    if (!(piv_w > 0.0)) ok = 0;
+    if (r > 0) {
+        wgemm<4, 4, false, true>(m, m, r, V, ldm, V, ldm, [&](int i, int j, double v) { Q[i + j * ldm] -= v; });
+        __syncwarp();
+        // Mx = Jbar^T[0:r, 6:6+m] V  (r x r);  NwJw = V Mx^{-1}
+        const int lda = 13;
+        wgemm<1, 1, false, false>(r, r, m, Jbar + 6 * ldc, ldc, V, ldm, [&](int i, int j, double v) { Aug[i + j * lda] = v; });
+        for (int e = lane; e < r * r; e += 32) {
+            int j = e / r, i = e - j * r;
+            Aug[i + (r + j) * lda] = (i == j) ? 1.0 : 0.0;
+        }
+        __syncwarp();
+        const double cond2 = wgauss_jordan(r, r, Aug, lda);
+        if (!(cond2 > 1e-14)) ok = 0;
+        double *g = w.NwJw + s * m * RMAX;
+        wgemm<2, 1, false, false>(m, r, r, V, ldm, Aug + r * lda, lda, [&](int i, int j, double v) { g[i + j * m] = v; });
+        for (int e = m * r + lane; e < m * RMAX; e += 32) g[e] = 0.0;
+    } else {
+        double *g = w.NwJw + s * m * RMAX;
+        for (int e = lane; e < m * RMAX; e += 32) g[e] = 0.0;
+    }
+    __syncwarp();
+    wcopy(m, m, Q, ldm, w.Winv + s * m * m, m);
+    // tau_g = W^+ u
+    wgemv<false>(m, m, Q, ldm, u, [&](int i, double v) { w.tau_grav[s * m + i] = v; });
+    if (lane == 0) w.status[s] = ok ? 1 : 0;
+}
+
+// N_C = I - Jc^T Jbar^T, materialised only when a caller asks for the public field (dwbc_batch_get_matrix)
+__global__ void nc_kernel(Work w, double *out) {
+    const int wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;
+    const long long s = (long long)blockIdx.x * wpb + wid;
+    if (s >= w.B) return;
+    const int n = w.n;
+    const int c = w.cdof[s] > 0 ? w.cdof[s] : 0;
+    const double *Jc = w.Jc + s * CMAX * n, *Jb = w.Jbar + s * CMAX * n;
+    double *o = out + s * n * n;
+    wgemm<4, 4, true, false>(n, n, c, Jc, CMAX, Jb, CMAX, [&](int i, int j, double v) { o[i + j * n] = (i == j ? 1.0 : 0.0) - v; });
+}
+
+}  // namespace dwbc
+
+namespace dwbc {
+// Export of kinematic public fields: mode 0 com_pos (3), 1 link_[i].xpos (3 x nb), 2 link_[i].rotm
+// (9 x nb, column-major 3x3 per link; reference src/link.cpp:78-79).
+__global__ void pose_export_kernel(Work w, int mode, double *out) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nb = w.nb;
+    if (mode == 0) {
+        if (tid < (long long)w.B * 3) out[tid] = w.com[(tid / 3) * 16 + tid % 3];
+        return;
+    }
+    for (long long e = tid; e < (long long)w.B * nb; e += (long long)gridDim.x * blockDim.x) {
+        const double *po = w.pose + e * POSE_STRIDE;
+        if (mode == 1) {
+            for (int k = 0; k < 3; k++) out[e * 3 + k] = po[9 + k];
+        } else {
+            for (int a = 0; a < 3; a++)
+                for (int c = 0; c < 3; c++) out[e * 9 + c * 3 + a] = po[a * 3 + c];
+        }
+    }
+}
+}  // namespace dwbc

@@ -63,3 +63,63 @@ def posture_selector(n=39, first_joint=12, count=21):
     for i in range(count):
         J[i, 6 + first_joint + i] = 1.0
     return J
+
+
+# ---------------------------------------------------------------------------------------------
+# Configurations of BASELINE.json / SURVEY.md section 8(d), applied identically to the product
+# (libdwbc_b200.RobotDataBatch) and to the oracle (oracle.oracle.OracleRobot).
+# ---------------------------------------------------------------------------------------------
+def configure_product(rd, config, ncontacts=2):
+    from libdwbc_b200 import CONTACT_6D, TASK_LINK_6D, TASK_LINK_POSITION, TASK_LINK_ROTATION
+    rd.add_contact_constraint(LEFT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+    rd.add_contact_constraint(RIGHT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+    if ncontacts == 4:
+        rd.add_contact_constraint(23, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.04, 0.04)
+        rd.add_contact_constraint(31, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.04, 0.04)
+    if config == "golden":  # reference tests/dwbc_test.cpp:71-77
+        rd.add_task_space(0, TASK_LINK_6D, PELVIS)
+        rd.add_task_space(1, TASK_LINK_ROTATION, UPPERBODY)
+        rd.set_torque_limit(300.0)
+    elif config == 1:  # COM position + pelvis rotation, closed form
+        rd.add_task_space(0, TASK_LINK_POSITION, "COM")
+        rd.add_task_space(1, TASK_LINK_ROTATION, "pelvis_link")
+    elif config == 2:  # 3-level HQP: COM / pelvis+upper-body rotation / posture
+        rd.add_task_space(0, TASK_LINK_POSITION, "COM")
+        rd.add_task_space(1, TASK_LINK_ROTATION, "pelvis_link")
+        rd.add_task_space(1, TASK_LINK_ROTATION, "upperbody_link")
+        rd.add_custom_task_space(2, 21)
+        rd.set_torque_limit(300.0)
+    return rd
+
+
+def configure_oracle(ref, config, ncontacts=2):
+    from oracle import oracle as orc
+    ref.add_contact(LEFT_FOOT, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+    ref.add_contact(RIGHT_FOOT, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+    if ncontacts == 4:
+        ref.add_contact(23, FOOT_POINT, (0, 0, 1), 0.04, 0.04)
+        ref.add_contact(31, FOOT_POINT, (0, 0, 1), 0.04, 0.04)
+    if config == "golden":
+        ref.add_task(0, orc.TASK_LINK_6D, PELVIS)
+        ref.add_task(1, orc.TASK_LINK_ROTATION, UPPERBODY)
+        ref.set_torque_limit(300.0)
+    elif config == 1:
+        ref.add_task(0, orc.TASK_LINK_POSITION, "COM")
+        ref.add_task(1, orc.TASK_LINK_ROTATION, "pelvis_link")
+    elif config == 2:
+        ref.add_task(0, orc.TASK_LINK_POSITION, "COM")
+        ref.add_task(1, orc.TASK_LINK_ROTATION, "pelvis_link")
+        ref.add_task(1, orc.TASK_LINK_ROTATION, "upperbody_link")
+        ref.add_custom_task(2, 21)
+        ref.set_torque_limit(300.0)
+        ref.set_task(2, np.zeros(21), posture_selector())
+    return ref
+
+
+def config_dofs(config):
+    return {"golden": (6, 3), 1: (3, 3), 2: (3, 6, 21)}[config]
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))

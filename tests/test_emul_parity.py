@@ -1,0 +1,94 @@
+"""Kernel logic vs oracle WITHOUT a GPU: the product's kernel sources compiled for the host through
+tests/emul/cuda_emul.h (test infrastructure) and driven through the same C ABI.  These tests catch algorithmic
+regressions in the container; the authoritative parity tests are the `-m gpu` ones (tests/test_gpu_parity.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from libdwbc_b200 import SOLVE_GRAV, SOLVE_HQP, SOLVE_REDIST, SOLVE_TASK, RobotDataBatch
+from oracle import oracle as orc
+from oracle.urdf_model import read_golden
+from tests.common import *
+from tests.emul.emul_backend import EmulBackend
+
+
+def run_product(config, q, qd, fstars, flags, stages, ncontacts=2):
+    B = q.shape[0]
+    rd = configure_product(RobotDataBatch(URDF, B, _backend=EmulBackend()), config, ncontacts)
+    rd.update_kinematics(np.ascontiguousarray(q), np.ascontiguousarray(qd))
+    rd.set_contact(np.ascontiguousarray(flags, dtype=np.uint8))
+    rd.calc_contact_constraint()
+    for l, f in enumerate(fstars):
+        rd.set_task_space(l, np.ascontiguousarray(f), np.ascontiguousarray(posture_selector()) if (config == 2 and l == 2) else None)
+    out = rd.solve(stages)
+    return rd, out
+
+
+@pytest.mark.parametrize("case", [1, 2])
+def test_emul_golden(case):
+    q = np.array([Q_CASE[case]], dtype=np.float64)
+    flags = np.array([[1, 1, 0, 0]], dtype=np.uint8)
+    fs = [np.array([FSTAR_CASE[case][0]]), np.array([FSTAR_CASE[case][1]])]
+    rd, (tg, tt, tc, st) = run_product("golden", q, np.zeros((1, 39)), fs, flags, SOLVE_GRAV | SOLVE_HQP | SOLVE_REDIST, 4)
+    assert st[0] == 7
+    g = lambda n: read_golden(os.path.join(GOLDEN, "cases", str(case), n))
+    for name, gname in GOLDEN_NAMES:
+        a = rd.get(name)[0]
+        gg = g(gname)
+        if a.ndim == 1:
+            gg = gg[:, 0]
+        a = a[:gg.shape[0]] if a.ndim == 2 else a
+        a = a[:, :gg.shape[1]] if a.ndim == 2 else a
+        assert relerr(a, gg) < 1e-9, name
+    assert relerr(tt[0], g("torque_task_")[:, 0]) < 1e-9
+    assert relerr(tc[0], g("torque_contact_")[:, 0]) < (1e-9 if case == 1 else 1e-4)
+    if case == 1:
+        assert rd.active_set(0)[0] == [66, 67, 68, 69, 70, 71, 72, 73, 74, 75, 78]
+        assert rd.active_set(1)[0] == [67, 68, 71, 72, 75, 78]
+    else:
+        assert rd.active_set(1)[0] == [68, 70]
+
+
+def test_emul_config2_vs_oracle():
+    """3-level HQP, double and single support, including the forced-active state."""
+    B = 6
+    q, qd, rng = synth_states(B, 20242)
+    fs = synth_fstar(rng, B)
+    fs[0][0, 1] = 4.0
+    flags = np.ones((B, 2), dtype=np.uint8)
+    flags[4] = [1, 0]
+    flags[5] = [0, 1]
+    rd, (tg, tt, tc, st) = run_product(2, q, qd, fs, flags, SOLVE_GRAV | SOLVE_HQP | SOLVE_REDIST)
+    ref = configure_oracle(orc.OracleRobot(URDF), 2)
+    o = ref.run_batch(q, qd, fs, flags)
+    assert np.array_equal(st & 7, o["status"] & 7)
+    for b in range(B):
+        if (o["status"][b] & 7) != 7:
+            continue
+        assert relerr(tg[b], o["torque_grav"][b]) < 1e-9
+        assert relerr(tt[b], o["torque_task"][b]) < 1e-6
+        assert np.abs(tc[b] - o["torque_contact"][b]).max() < 1e-6 * max(1.0, np.abs(o["torque_contact"][b]).max())
+
+
+def test_emul_config1_closed_form():
+    B = 3
+    q, qd, rng = synth_states(B, 20241)
+    fs = synth_fstar(rng, B, dofs=(3, 3), scales=(0.5, 1.0), hard_frac=0)
+    flags = np.ones((B, 2), dtype=np.uint8)
+    rd, (tg, tt, tc, st) = run_product(1, q, qd, fs, flags, SOLVE_GRAV | SOLVE_TASK)
+    ref = configure_oracle(orc.OracleRobot(URDF), 1)
+    for b in range(B):
+        ref.update_kinematics(q[b], qd[b]); ref.set_contact(1, 1); ref.calc_contact_constraint()
+        ref.set_task(0, fs[0][b]); ref.set_task(1, fs[1][b]); ref.calc_grav(); ref.calc_task_torque(False)
+        assert relerr(tt[b], ref.get("torque_task")[:, 0]) < 1e-9
+        for l in (0, 1):
+            assert relerr(rd.get("Lambda_task", l)[b], ref.get(f"Lambda_task{l}")) < 1e-9
+            assert relerr(rd.get("J_kt", l)[b], ref.get(f"J_kt{l}")) < 1e-9
+            assert relerr(rd.get("J_task", l)[b], ref.get(f"J_task{l}")) < 1e-12
+        assert relerr(rd.get("Null_task", 0)[b], ref.get("Null_task0")) < 1e-9
+        assert relerr(rd.get("B")[b], ref.get("B")[:, 0]) < 1e-10
+        assert relerr(rd.get("com_pos")[b], ref.get("com_pos")[:, 0]) < 1e-12
+        assert relerr(rd.get("link_pos")[b], ref.get("link_pos")) < 1e-12
+        assert relerr(rd.get("link_rot")[b], ref.get("link_rot")) < 1e-12
+        assert relerr(rd.get("link_vel")[b], ref.get("link_vel")) < 1e-11
