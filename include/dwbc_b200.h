@@ -174,6 +174,14 @@ int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, con
 /* Best DFMA-chain throughput (TFLOP/s, 2 flop per FMA) observed over ~`seconds` of back-to-back launches on
  * `device`: the FP64-pipe roofline denominator used by bench.py. */
 int dwbc_probe_fp64(int device, double seconds, double *tflops);
+/* Per-kernel device time: with profiling enabled every kernel launch of this handle is bracketed by CUDA events
+ * recorded on the launch stream (no host synchronisation is added to the hot path).  dwbc_batch_get_kernel_times
+ * synchronises the pending events and returns, per DWBC_K_* kernel, the summed duration in ms (only launches made while
+ * profiling was on) and the launch count since the last reset.  bench.py's roofline numbers come from here. */
+enum { DWBC_K_RBD = 0, DWBC_K_AINV, DWBC_K_CONTACT_JAC, DWBC_K_CONTACT_DYN, DWBC_K_TASK, DWBC_K_HQP, DWBC_K_EXPORT, DWBC_K_COUNT };
+int dwbc_batch_set_profiling(dwbc_batch_t *b, int enable);
+int dwbc_batch_get_kernel_times(dwbc_batch_t *b, double *ms_sum, long long *launches, int reset);
+const char *dwbc_kernel_name(int k);
 /* Total active-set iterations of the last dwbc_batch_solve per state: out_dev [B] int32. */
 int dwbc_batch_get_qp_iterations(dwbc_batch_t *b, int32_t *out_dev, void *stream);
 

@@ -245,6 +245,18 @@ class RobotDataBatch:
         self._ck(self.L.dwbc_batch_get_qp_iterations(self._h, self.be.ptr(buf), self.be.stream()))
         return buf
 
+    # ---- per-kernel device timing (CUDA events recorded by the library around each of its launches) ----
+    def set_profiling(self, enable=True):
+        self._ck(self.L.dwbc_batch_set_profiling(self._h, 1 if enable else 0))
+
+    def kernel_times(self, reset=True):
+        """{kernel name: (summed ms while profiling was on, launches since the last reset)}"""
+        K = 7
+        ms = (C.c_double * K)()
+        cnt = (C.c_longlong * K)()
+        self._ck(self.L.dwbc_batch_get_kernel_times(self._h, ms, cnt, 1 if reset else 0))
+        return {self.L.dwbc_kernel_name(k).decode(): (ms[k], cnt[k]) for k in range(K)}
+
     # ---- whole cycle from host buffers (pinned numpy / torch CPU tensors) ----
     def cycle_host(self, stages, q, qdot, fstars, flags, out=None):
         """H2D + all stages + D2H through dwbc_batch_cycle_host.  All arguments are host arrays (numpy)."""

@@ -42,6 +42,16 @@ struct dwbc_batch {
     int sm_count = 148;
     // call-order tracking
     bool have_kin = false, have_contact = false, have_cc = false;
+    // optional per-kernel timing (dwbc_batch_set_profiling): event pairs recorded on the launch stream
+    bool profiling = false;
+    struct Pending {
+        int k;
+        cudaEvent_t e0, e1;
+    };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> free_events;
+    double k_ms[DWBC_K_COUNT] = {0};
+    long long k_launches[DWBC_K_COUNT] = {0};
 };
 
 namespace {
@@ -71,6 +81,39 @@ bool dev_alloc(dwbc_batch *b, T **p, size_t count, std::vector<void *> *list = n
     *p = (T *)raw;
     return true;
 }
+
+cudaEvent_t prof_event(dwbc_batch *b) {
+    cudaEvent_t e;
+    if (!b->free_events.empty()) {
+        e = b->free_events.back();
+        b->free_events.pop_back();
+        return e;
+    }
+    cudaEventCreate(&e);
+    return e;
+}
+// Brackets one kernel launch with events when profiling is on (no host synchronisation here).
+struct KernelScope {
+    dwbc_batch *b;
+    cudaStream_t st;
+    int k;
+    cudaEvent_t e0{}, e1{};
+    KernelScope(dwbc_batch *b_, int k_, cudaStream_t st_) : b(b_), st(st_), k(k_) {
+        if (b->profiling) {
+            e0 = prof_event(b);
+            e1 = prof_event(b);
+            cudaEventRecord(e0, st);
+        }
+    }
+    ~KernelScope() {
+        g_launches++;
+        b->k_launches[k]++;
+        if (b->profiling) {
+            cudaEventRecord(e1, st);
+            b->pending.push_back({k, e0, e1});
+        }
+    }
+};
 
 constexpr int WARPS_PER_BLOCK = 4;
 inline int grid_for(int B, int wpb) { return (B + wpb - 1) / wpb; }
@@ -191,6 +234,11 @@ void dwbc_batch_destroy(dwbc_batch_t *b) {
     for (void *p : b->allocs) cudaFree(p);
     for (void *p : b->task_allocs) cudaFree(p);
     if (b->d_fstar) cudaFree(b->d_fstar);
+    for (auto &p : b->pending) {
+        cudaEventDestroy(p.e0);
+        cudaEventDestroy(p.e1);
+    }
+    for (cudaEvent_t e : b->free_events) cudaEventDestroy(e);
     delete b;
 }
 int dwbc_batch_size(const dwbc_batch_t *b) { return b ? b->B : 0; }
@@ -306,14 +354,14 @@ int dwbc_batch_update_kinematics(dwbc_batch_t *b, const double *q_dev, const dou
     CK(cudaMemsetAsync(b->w.status, 0xff, sizeof(int) * b->B, st));  // "valid so far"; stages clear it on failure
     {
         size_t smem = sizeof(double) * wpb * rbd_smem_doubles(b->w.nb);
+        KernelScope ks(b, DWBC_K_RBD, st);
         DWBC_LAUNCH(rbd_kernel, grid, wpb * 32, smem, st, b->d_model, q_dev, qdot_dev, b->w);
-        g_launches++;
     }
     {
         size_t smem = sizeof(double) * wpb * ainv_smem_doubles(n);
         CK(cudaFuncSetAttribute(ainv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KernelScope ks(b, DWBC_K_AINV, st);
         DWBC_LAUNCH(ainv_kernel, grid, wpb * 32, smem, st, b->w);
-        g_launches++;
     }
     CK(cudaGetLastError());
     b->have_kin = true;
@@ -330,8 +378,10 @@ int dwbc_batch_set_contact(dwbc_batch_t *b, const uint8_t *flags_dev, void *stre
     int rc = upload_cfg(b, st);
     if (rc) return rc;
     const int wpb = WARPS_PER_BLOCK, grid = grid_for(b->B, wpb);
-    DWBC_LAUNCH(contact_jacobian_kernel, grid, wpb * 32, 0, st, b->d_model, b->d_cfg, flags_dev, b->w);
-    g_launches++;
+    {
+        KernelScope ks(b, DWBC_K_CONTACT_JAC, st);
+        DWBC_LAUNCH(contact_jacobian_kernel, grid, wpb * 32, 0, st, b->d_model, b->d_cfg, flags_dev, b->w);
+    }
     CK(cudaGetLastError());
     b->have_contact = true;
     b->have_cc = false;
@@ -347,8 +397,10 @@ int dwbc_batch_calc_contact_constraint(dwbc_batch_t *b, void *stream) {
     ContactSmem L(b->w.n, b->w.m);
     size_t smem = sizeof(double) * wpb * L.total;
     CK(cudaFuncSetAttribute(contact_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DWBC_LAUNCH(contact_dynamics_kernel, grid, wpb * 32, smem, st, b->d_model, b->w);
-    g_launches++;
+    {
+        KernelScope ks(b, DWBC_K_CONTACT_DYN, st);
+        DWBC_LAUNCH(contact_dynamics_kernel, grid, wpb * 32, smem, st, b->d_model, b->w);
+    }
     CK(cudaGetLastError());
     b->have_cc = true;
     return DWBC_OK;
@@ -390,8 +442,8 @@ int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *
         TaskSmem L(b->w.n, b->w.m);
         size_t smem = sizeof(double) * wpb * L.total;
         CK(cudaFuncSetAttribute(task_space_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KernelScope ks(b, DWBC_K_TASK, st);
         DWBC_LAUNCH(task_space_kernel, grid, wpb * 32, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0);
-        g_launches++;
     } else {
         CK(cudaMemsetAsync(b->w.tau_task, 0, sizeof(double) * B * m, st));
         CK(cudaMemsetAsync(b->w.tau_contact, 0, sizeof(double) * B * m, st));
@@ -401,9 +453,9 @@ int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *
         HqpSmem L(b->w.n, b->w.m);
         size_t smem = sizeof(double) * wpb * L.total;
         CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KernelScope ks(b, DWBC_K_HQP, st);
         DWBC_LAUNCH(hqp_kernel, grid, wpb * 32, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0,
                     (stages & DWBC_SOLVE_REDIST) ? 1 : 0);
-        g_launches++;
     }
     CK(cudaGetLastError());
     if (tau_grav_dev) CK(cudaMemcpyAsync(tau_grav_dev, b->w.tau_grav, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));
@@ -470,11 +522,12 @@ int dwbc_batch_get_matrix(dwbc_batch_t *b, int which, int level, double *out_dev
     const int wpb = WARPS_PER_BLOCK, grid = grid_for(b->B, wpb);
     if (which == DWBC_MAT_N_C) {
         if (!b->have_cc) return fail(DWBC_ERR_ORDER, "get_matrix(N_C): call calc_contact_constraint first");
+        KernelScope ks(b, DWBC_K_EXPORT, st);
         DWBC_LAUNCH(nc_kernel, grid, wpb * 32, 0, st, b->w, out_dev);
     } else {
+        KernelScope ks(b, DWBC_K_EXPORT, st);
         DWBC_LAUNCH(pose_export_kernel, grid, wpb * 32, 0, st, b->w, which == DWBC_MAT_COM ? 0 : (which == DWBC_MAT_LINK_POS ? 1 : 2), out_dev);
     }
-    g_launches++;
     CK(cudaGetLastError());
     return DWBC_OK;
 }
@@ -492,6 +545,38 @@ int dwbc_batch_get_qp_iterations(dwbc_batch_t *b, int32_t *out_dev, void *stream
     if (!b || !out_dev) return fail(DWBC_ERR_ARG, "get_qp_iterations: null argument");
     CK(cudaMemcpyAsync(out_dev, b->w.qp_iters, sizeof(int32_t) * (size_t)b->B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return DWBC_OK;
+}
+
+int dwbc_batch_set_profiling(dwbc_batch_t *b, int enable) {
+    if (!b) return fail(DWBC_ERR_ARG, "set_profiling: null handle");
+    b->profiling = enable != 0;
+    return DWBC_OK;
+}
+
+int dwbc_batch_get_kernel_times(dwbc_batch_t *b, double *ms_sum, long long *launches, int reset) {
+    if (!b) return fail(DWBC_ERR_ARG, "get_kernel_times: null handle");
+    CK(cudaSetDevice(b->device));
+    for (auto &p : b->pending) {
+        CK(cudaEventSynchronize(p.e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, p.e0, p.e1));
+        b->k_ms[p.k] += ms;
+        b->free_events.push_back(p.e0);
+        b->free_events.push_back(p.e1);
+    }
+    b->pending.clear();
+    for (int k = 0; k < DWBC_K_COUNT; k++) {
+        if (ms_sum) ms_sum[k] = b->k_ms[k];
+        if (launches) launches[k] = b->k_launches[k];
+        if (reset) b->k_ms[k] = 0.0, b->k_launches[k] = 0;
+    }
+    return DWBC_OK;
+}
+
+const char *dwbc_kernel_name(int k) {
+    static const char *names[DWBC_K_COUNT] = {"rbd_kernel", "ainv_kernel", "contact_jacobian_kernel", "contact_dynamics_kernel",
+                                              "task_space_kernel", "hqp_kernel", "export_kernels"};
+    return (k >= 0 && k < DWBC_K_COUNT) ? names[k] : nullptr;
 }
 
 int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, const double *qdot_host, const double *fstar_host,
