@@ -358,10 +358,10 @@ int dwbc_batch_update_kinematics(dwbc_batch_t *b, const double *q_dev, const dou
         DWBC_LAUNCH(rbd_kernel, grid, wpb * 32, smem, st, b->d_model, q_dev, qdot_dev, b->w);
     }
     {
-        size_t smem = sizeof(double) * wpb * ainv_smem_doubles(n);
+        size_t smem = sizeof(double) * ainv_smem_doubles(n);
         CK(cudaFuncSetAttribute(ainv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelScope ks(b, DWBC_K_AINV, st);
-        DWBC_LAUNCH(ainv_kernel, grid, wpb * 32, smem, st, b->w);
+        DWBC_LAUNCH(ainv_kernel, b->B, TEAM, smem, st, b->w);
     }
     CK(cudaGetLastError());
     b->have_kin = true;
@@ -393,13 +393,12 @@ int dwbc_batch_calc_contact_constraint(dwbc_batch_t *b, void *stream) {
     if (!b->have_contact) return fail(DWBC_ERR_ORDER, "calc_contact_constraint: call set_contact first");
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int wpb = 2, grid = grid_for(b->B, wpb);
     ContactSmem L(b->w.n, b->w.m);
-    size_t smem = sizeof(double) * wpb * L.total;
+    size_t smem = sizeof(double) * L.total;
     CK(cudaFuncSetAttribute(contact_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         KernelScope ks(b, DWBC_K_CONTACT_DYN, st);
-        DWBC_LAUNCH(contact_dynamics_kernel, grid, wpb * 32, smem, st, b->d_model, b->w);
+        DWBC_LAUNCH(contact_dynamics_kernel, b->B, TEAM, smem, st, b->d_model, b->w);
     }
     CK(cudaGetLastError());
     b->have_cc = true;
@@ -438,23 +437,23 @@ int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *
         if (rc) return rc;
     }
     if (stages & DWBC_SOLVE_TASK) {
-        const int wpb = 2, grid = grid_for(b->B, wpb);
-        TaskSmem L(b->w.n, b->w.m);
-        size_t smem = sizeof(double) * wpb * L.total;
+        int tmax = 1;
+        for (int l = 0; l < b->cfg.nlevels; l++) tmax = b->cfg.tasks[l].dof > tmax ? b->cfg.tasks[l].dof : tmax;
+        TaskSmem L(b->w.n, b->w.m, tmax);
+        size_t smem = sizeof(double) * L.total;
         CK(cudaFuncSetAttribute(task_space_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelScope ks(b, DWBC_K_TASK, st);
-        DWBC_LAUNCH(task_space_kernel, grid, wpb * 32, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0);
+        DWBC_LAUNCH(task_space_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0, tmax);
     } else {
         CK(cudaMemsetAsync(b->w.tau_task, 0, sizeof(double) * B * m, st));
         CK(cudaMemsetAsync(b->w.tau_contact, 0, sizeof(double) * B * m, st));
     }
     if (stages & (DWBC_SOLVE_HQP | DWBC_SOLVE_REDIST)) {
-        const int wpb = 2, grid = grid_for(b->B, wpb);
         HqpSmem L(b->w.n, b->w.m);
-        size_t smem = sizeof(double) * wpb * L.total;
+        size_t smem = sizeof(double) * L.total;
         CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelScope ks(b, DWBC_K_HQP, st);
-        DWBC_LAUNCH(hqp_kernel, grid, wpb * 32, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0,
+        DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0,
                     (stages & DWBC_SOLVE_REDIST) ? 1 : 0);
     }
     CK(cudaGetLastError());

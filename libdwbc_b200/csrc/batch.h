@@ -20,6 +20,11 @@ constexpr int MAX_LEVELS = 4;
 constexpr int MAX_TASK_LINKS = 8;      // over all levels
 constexpr int MAX_TASK_DOF = 24;       // per level
 constexpr int QP_ROWS_MAX = 2 * (MAXB - 1) + 10 * MAX_ACTIVE_CONTACTS;
+#ifdef DWBC_TEAM
+constexpr int TEAM = DWBC_TEAM;        // build-time override (the emulation build of the tests uses a smaller team)
+#else
+constexpr int TEAM = 128;              // threads cooperating on one state in the dense stages (one CTA per state)
+#endif
 constexpr int ACTIVE_WORDS = 4;        // bit mask words per QP (>= QP_ROWS_MAX/32)
 
 struct ContactCfg {

@@ -15,6 +15,7 @@
 #pragma once
 #include "batch.h"
 #include "kernels_rbd.cuh"
+#include "team_linalg.cuh"
 #include "warp_linalg.cuh"
 
 namespace dwbc {
@@ -31,22 +32,44 @@ __global__ void rbd_kernel(const DevModel *__restrict__ md, const double *__rest
 }
 
 // ---------------------------------------------------------------- a1: A^{-1} by Cholesky
-__host__ __device__ inline int ainv_smem_doubles(int n) { return 2 * (n | 1) * n + n; }
+// One CTA (team) per state.  A = L L^T with register-resident ownership (team_linalg.cuh), Xi = L^{-1} by forward
+// substitution (one column per thread), A^{-1} = Xi^T Xi on the lower triangle, mirrored.
+__host__ __device__ inline int ainv_smem_doubles(int n) { return 2 * (n | 1) * n + n + 1; }
 
-__global__ void ainv_kernel(Work w) {
+template <int MAXOWN>
+__device__ __forceinline__ double team_spd_inverse_t(int n, double *L, int ld, double *Xi, int ldx, double *rd) {
+    const double minpiv = tchol_lower<MAXOWN>(n, L, ld, rd);
+    ttri_inverse(n, L, ld, rd, Xi, ldx);
+    tsync();
+    tsyrk_inverse(n, Xi, ldx, [&](int i, int j, double v) { L[i + j * ld] = v; });
+    tsync();
+    return minpiv;
+}
+// SPD inverse in place: on return the full symmetric inverse is in L (n x n, ld); Xi is scratch of the same size.
+// Synchronises on entry and exit.  Returns the smallest Cholesky pivot.
+__device__ __forceinline__ double team_spd_inverse(int n, double *L, int ld, double *Xi, int ldx, double *rd) {
+    const int total = n * (n + 1) / 2, nt = t_n();
+    if (total <= 2 * nt) return team_spd_inverse_t<2>(n, L, ld, Xi, ldx, rd);
+    if (total <= 5 * nt) return team_spd_inverse_t<5>(n, L, ld, Xi, ldx, rd);
+    if (total <= 7 * nt) return team_spd_inverse_t<7>(n, L, ld, Xi, ldx, rd);
+    if constexpr (TEAM >= 128) {
+        return team_spd_inverse_t<12>(n, L, ld, Xi, ldx, rd);  // n <= 54
+    } else {
+        if (total <= 12 * nt) return team_spd_inverse_t<12>(n, L, ld, Xi, ldx, rd);
+        return team_spd_inverse_t<45>(n, L, ld, Xi, ldx, rd);  // small teams (emulation builds of the tests)
+    }
+}
+
+__global__ void __launch_bounds__(TEAM, 6) ainv_kernel(Work w) {
     DWBC_DYN_SMEM(smem);
-    const int wpb = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = lane_id();
-    const long long s = (long long)blockIdx.x * wpb + wid;
-    if (s >= w.B) return;
+    const long long s = blockIdx.x;
     const int n = w.n, ld = n | 1;
-    double *L = (double *)smem + (size_t)wid * ainv_smem_doubles(n);
+    double *L = (double *)smem;
     double *X = L + ld * n, *rd = X + ld * n;
-    wcopy(n, n, w.A + s * n * n, n, L, ld);
-    __syncwarp();
-    const double minpiv = wchol_lower(n, L, ld, rd);
-    wchol_inverse(n, L, ld, rd, X, ld);
-    wcopy(n, n, X, ld, w.Ainv + s * n * n, n);
-    if (lane == 0 && !(minpiv > 0.0)) w.status[s] = 0;  // mass matrix not SPD: everything downstream is invalid
+    tcopy(n, n, w.A + s * n * n, n, L, ld);
+    const double minpiv = team_spd_inverse(n, L, ld, X, ld, rd);
+    tcopy(n, n, L, ld, w.Ainv + s * n * n, n);
+    if (t_id() == 0 && !(minpiv > 0.0)) w.status[s] = 0;  // mass matrix not SPD: everything downstream is invalid
 }
 
 // ---------------------------------------------------------------- a2: contact Jacobian stack
@@ -78,168 +101,173 @@ __global__ void contact_jacobian_kernel(const DevModel *__restrict__ md, const B
 }
 
 // ---------------------------------------------------------------- a3 + a4
-// shared-memory arena (doubles) per warp
+// shared-memory arena (doubles) of one state
 struct ContactSmem {
     int ldn, ldc, ldm;
     int P, Q, Jc, X, Jbar, Lam, Lw, V, Aug, vec, total;
     __host__ __device__ ContactSmem(int n, int m) {
         ldn = n | 1; ldc = CMAX | 1; ldm = m | 1;
         int o = 0;
-        P = o; o += ldn * n;        // A^{-1} -> A^{-1}N_c ; its [6:,6:] block later holds chol(W + V V^T)
-        Q = o; o += ldm * m;        // (W + V V^T)^{-1} -> W^+
+        P = o; o += ldn * n;        // A^{-1} -> A^{-1}N_c ; its [6:,6:] block later holds W + V V^T, then W^+
+        Q = o; o += ldm * m;        // scratch: inverse Cholesky factor of W + V V^T
         Jc = o; o += ldc * n;
         X = o; o += ldn * CMAX;
         Jbar = o; o += ldc * n;
-        Lam = o; o += ldc * CMAX;   // Jc X -> its Cholesky factor
-        Lw = o; o += ldc * CMAX;    // Lambda_c
+        Lam = o; o += ldc * CMAX;   // Jc X -> Lambda_c
+        Lw = o; o += ldc * CMAX;    // scratch of the c x c inverse
         V = o; o += ldm * (RMAX > 0 ? RMAX : 1);
         Aug = o; o += 13 * 32;      // Gauss-Jordan scratch, up to 12 rows x 32 columns, ld 13
-        vec = o; o += 4 * (n + 1);  // rdiag / G / u / tau
+        vec = o; o += 4 * (n + 1);  // rdiag / G / u / flag word
         total = o;
     }
 };
 
-__global__ void contact_dynamics_kernel(const DevModel *__restrict__ md, Work w) {
+__global__ void __launch_bounds__(TEAM, 5) contact_dynamics_kernel(const DevModel *__restrict__ md, Work w) {
     DWBC_DYN_SMEM(smem);
-    const int wpb = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = lane_id();
-    const long long s = (long long)blockIdx.x * wpb + wid;
-    if (s >= w.B) return;
+    const int tid = t_id(), nt = t_n(), warp = tid >> 5, lane = lane_id();
+    const long long s = blockIdx.x;
     const int n = w.n, m = w.m;
     const ContactSmem L(n, m);
-    double *sm = (double *)smem + (size_t)wid * L.total;
+    double *sm = (double *)smem;
     double *P = sm + L.P, *Q = sm + L.Q, *Jc = sm + L.Jc, *X = sm + L.X, *Jbar = sm + L.Jbar, *Lam = sm + L.Lam, *Lw = sm + L.Lw;
-    double *V = sm + L.V, *Aug = sm + L.Aug, *rd = sm + L.vec, *Gs = rd + n + 1, *u = Gs + n + 1, *tg = u + n + 1;
+    double *V = sm + L.V, *Aug = sm + L.Aug, *rd = sm + L.vec, *Gs = rd + n + 1, *u = Gs + n + 1;
+    int &s_ok = *(int *)(u + n + 1);  // CTA-wide validity flag (lives in the arena: no static shared memory)
     const int ldn = L.ldn, ldc = L.ldc, ldm = L.ldm;
     const int c = w.cdof[s];
     const int r = c > 6 ? c - 6 : 0;
-    int ok = (c > 0 && c <= CMAX) ? 1 : 0;
-    if (w.status[s] == 0) ok = 0;  // A not SPD
-    if (!ok) {
-        if (lane == 0) w.status[s] = 0;
+    if (!(c > 0 && c <= CMAX) || w.status[s] == 0) {  // no contact / too many contacts / A not SPD (uniform over the CTA)
+        if (tid == 0) w.status[s] = 0;
         return;
     }
-    wcopy(n, n, w.Ainv + s * n * n, n, P, ldn);
-    wcopy(c, n, w.Jc + s * CMAX * n, CMAX, Jc, ldc);
-    for (int e = lane; e < n; e += 32) Gs[e] = w.G[s * n + e];
-    __syncwarp();
+    if (tid == 0) s_ok = 1;
+    tcopy(n, n, w.Ainv + s * n * n, n, P, ldn);
+    tcopy(c, n, w.Jc + s * CMAX * n, CMAX, Jc, ldc);
+    for (int e = tid; e < n; e += nt) Gs[e] = w.G[s * n + e];
+    tsync();
     // X = A^{-1} Jc^T  (n x c)
-    wgemm<4, 3, false, true>(n, c, n, P, ldn, Jc, ldc, [&](int i, int j, double v) { X[i + j * ldn] = v; });
-    __syncwarp();
-    // Jc X (c x c, SPD) -> Cholesky -> Lambda_c
-    wgemm<2, 2, false, false>(c, c, n, Jc, ldc, X, ldn, [&](int i, int j, double v) { Lam[i + j * ldc] = v; });
-    __syncwarp();
-    const double piv_c = wchol_lower(c, Lam, ldc, rd);
-    wchol_inverse(c, Lam, ldc, rd, Lw, ldc);
-    if (!(piv_c > 0.0)) ok = 0;
+    tgemm<2, 2, false, true>(n, c, n, P, ldn, Jc, ldc, [&](int i, int j, double v) { X[i + j * ldn] = v; });
+    tsync();
+    // Jc X (c x c, SPD) -> Lambda_c (in Lam)
+    tgemm<1, 2, false, false>(c, c, n, Jc, ldc, X, ldn, [&](int i, int j, double v) { Lam[i + j * ldc] = v; });
+    const double piv_c = team_spd_inverse(c, Lam, ldc, Lw, ldc, rd);
+    if (!(piv_c > 0.0) && tid == 0) s_ok = 0;
     // Jbar^T = Lambda_c X^T  (c x n)
-    wgemm<3, 4, false, true>(c, n, c, Lw, ldc, X, ldn, [&](int i, int j, double v) { Jbar[i + j * ldc] = v; });
-    __syncwarp();
+    tgemm<2, 2, false, true>(c, n, c, Lam, ldc, X, ldn, [&](int i, int j, double v) { Jbar[i + j * ldc] = v; });
+    tsync();
     // A^{-1} N_c = A^{-1} - X Jbar^T
-    wgemm<4, 4, false, false>(n, n, c, X, ldn, Jbar, ldc, [&](int i, int j, double v) { P[i + j * ldn] -= v; });
-    __syncwarp();
+    tgemm<4, 4, false, false>(n, n, c, X, ldn, Jbar, ldc, [&](int i, int j, double v) { P[i + j * ldn] -= v; });
+    tsync();
     // outputs of a3 that do not depend on the pseudo-inverse
     {
         double *g = w.Lam + s * CMAX * CMAX;
-        for (int e = lane; e < CMAX * CMAX; e += 32) {
+        for (int e = tid; e < CMAX * CMAX; e += nt) {
             int j = e / CMAX, i = e - j * CMAX;
-            g[e] = (i < c && j < c) ? Lw[i + j * ldc] : 0.0;
+            g[e] = (i < c && j < c) ? Lam[i + j * ldc] : 0.0;
         }
         g = w.Jbar + s * CMAX * n;
-        for (int e = lane; e < CMAX * n; e += 32) {
+        for (int e = tid; e < CMAX * n; e += nt) {
             int j = e / CMAX, i = e - j * CMAX;
             g[e] = (i < c) ? Jbar[i + j * ldc] : 0.0;
         }
-        wcopy(n, n, P, ldn, w.AinvNc + s * n * n, n);
-        wcopy(m, m, P + 6 + 6 * ldn, ldn, w.W + s * m * m, m);
+        tcopy(n, n, P, ldn, w.AinvNc + s * n * n, n);
+        tcopy(m, m, P + 6 + 6 * ldn, ldn, w.W + s * m * m, m);
     }
     // u = (A^{-1}N_c)[6:, :] G   and   P_C = Jbar^T G
-    wgemv<false>(m, n, P + 6, ldn, Gs, [&](int i, double v) { u[i] = v; });
-    wgemv<false>(c, n, Jbar, ldc, Gs, [&](int i, double v) { w.PC[s * CMAX + i] = v; });
-    for (int i = c + lane; i < CMAX; i += 32) w.PC[s * CMAX + i] = 0.0;
-    __syncwarp();
+    tgemv<false>(m, n, P + 6, ldn, Gs, [&](int i, double v) { u[i] = v; });
+    tgemv<false>(c, n, Jbar, ldc, Gs, [&](int i, double v) { w.PC[s * CMAX + i] = v; });
+    for (int i = c + tid; i < CMAX; i += nt) w.PC[s * CMAX + i] = 0.0;
     double *Wblk = P + 6 + 6 * ldn;  // view of W inside P, leading dimension ldn
+    const int lda = 13;
     if (r > 0) {
         // ---- orthonormal basis V (m x r) of null(W) ----
-        // T = B_1^{-T} [B_2^T ...]  with  B_i = Jc[6i:6i+6, 0:6] : Gauss-Jordan on [B_1^T | B_2^T ...]
-        const int lda = 13;
-        for (int e = lane; e < 6 * (6 + r); e += 32) {
-            int col = e / 6, row = e - col * 6;
-            // column `col` < 6: B_1^T(row, col) = Jc[col][row]; col >= 6: B_k^T(row, col-6) = Jc[col][row] (col indexes Jc rows)
-            Aug[row + col * lda] = Jc[col + row * ldc];
+        // T = B_1^{-T} [B_2^T ...]  with  B_i = Jc[6i:6i+6, 0:6] : Gauss-Jordan on [B_1^T | B_2^T ...]  (warp 0)
+        if (warp == 0) {
+            for (int e = lane; e < 6 * (6 + r); e += 32) {
+                int col = e / 6, row = e - col * 6;
+                Aug[row + col * lda] = Jc[col + row * ldc];
+            }
+            __syncwarp();
+            const double cond1 = wgauss_jordan(6, r, Aug, lda);
+            if (!(cond1 > 1e-14) && lane == 0) s_ok = 0;
         }
-        __syncwarp();
-        const double cond1 = wgauss_jordan(6, r, Aug, lda);
-        if (!(cond1 > 1e-14)) ok = 0;
+        tsync();
         // V_raw(a, b) = Jc[6+b][6+a] - sum_e Jc[e][6+a] * T(e, b)
-        for (int e = lane; e < m * r; e += 32) {
+        for (int e = tid; e < m * r; e += nt) {
             int b = e / m, a = e - b * m;
             double v = Jc[(6 + b) + (6 + a) * ldc];
             for (int k = 0; k < 6; k++) v = fma(-Jc[k + (6 + a) * ldc], Aug[k + (6 + b) * lda], v);
             V[a + b * ldm] = v;
         }
-        __syncwarp();
-        // modified Gram-Schmidt, two passes (rows of V across lanes, m may exceed 32)
-        for (int b = 0; b < r; b++) {
-            for (int pass = 0; pass < 2; pass++) {
-                for (int k = 0; k < b; k++) {
-                    double d = 0.0;
-                    for (int a = lane; a < m; a += 32) d = fma(V[a + k * ldm], V[a + b * ldm], d);
-                    d = warp_sum(d);
-                    for (int a = lane; a < m; a += 32) V[a + b * ldm] = fma(-d, V[a + k * ldm], V[a + b * ldm]);
+        tsync();
+        // modified Gram-Schmidt, two passes (warp 0; rows of V across lanes, m may exceed 32)
+        if (warp == 0) {
+            for (int b = 0; b < r; b++) {
+                for (int pass = 0; pass < 2; pass++) {
+                    for (int k = 0; k < b; k++) {
+                        double d = 0.0;
+                        for (int a = lane; a < m; a += 32) d = fma(V[a + k * ldm], V[a + b * ldm], d);
+                        d = warp_sum(d);
+                        for (int a = lane; a < m; a += 32) V[a + b * ldm] = fma(-d, V[a + k * ldm], V[a + b * ldm]);
+                        __syncwarp();
+                    }
                 }
+                double nn = 0.0;
+                for (int a = lane; a < m; a += 32) nn = fma(V[a + b * ldm], V[a + b * ldm], nn);
+                nn = warp_sum(nn);
+                if (!(nn > 1e-280)) {
+                    nn = 1.0;
+                    if (lane == 0) s_ok = 0;
+                }
+                const double rn = 1.0 / sqrt(nn);
+                for (int a = lane; a < m; a += 32) V[a + b * ldm] *= rn;
+                __syncwarp();
             }
-            double nn = 0.0;
-            for (int a = lane; a < m; a += 32) nn = fma(V[a + b * ldm], V[a + b * ldm], nn);
-            nn = warp_sum(nn);
-            if (!(nn > 1e-280)) ok = 0, nn = 1.0;
-            const double rn = 1.0 / sqrt(nn);
-            for (int a = lane; a < m; a += 32) V[a + b * ldm] *= rn;
-            __syncwarp();
         }
+        tsync();
         // V2 (rows = basis vectors), reference layout r x m
         {
             double *g = w.V2 + s * RMAX * m;
-            for (int e = lane; e < RMAX * m; e += 32) {
+            for (int e = tid; e < RMAX * m; e += nt) {
                 int a = e / RMAX, b = e - a * RMAX;
                 g[e] = b < r ? V[a + b * ldm] : 0.0;
             }
         }
         // W + V V^T in place
-        wgemm<4, 4, false, true>(m, m, r, V, ldm, V, ldm, [&](int i, int j, double v) { Wblk[i + j * ldn] += v; });
-        __syncwarp();
+        tgemm<3, 3, false, true>(m, m, r, V, ldm, V, ldm, [&](int i, int j, double v) { Wblk[i + j * ldn] += v; });
     } else {
         double *g = w.V2 + s * RMAX * m;
-        for (int e = lane; e < RMAX * m; e += 32) g[e] = 0.0;
+        for (int e = tid; e < RMAX * m; e += nt) g[e] = 0.0;
     }
-    // (W + V V^T)^{-1}
-    const double piv_w = wchol_lower(m, Wblk, ldn, rd);
-    wchol_inverse(m, Wblk, ldn, rd, Q, ldm);
-    if (!(piv_w > 0.0)) ok = 0;
+    // (W + V V^T)^{-1}, in place
+    const double piv_w = team_spd_inverse(m, Wblk, ldn, Q, ldm, rd);
+    if (!(piv_w > 0.0) && tid == 0) s_ok = 0;
     if (r > 0) {
-        wgemm<4, 4, false, true>(m, m, r, V, ldm, V, ldm, [&](int i, int j, double v) { Q[i + j * ldm] -= v; });
-        __syncwarp();
+        tgemm<3, 3, false, true>(m, m, r, V, ldm, V, ldm, [&](int i, int j, double v) { Wblk[i + j * ldn] -= v; });
         // Mx = Jbar^T[0:r, 6:6+m] V  (r x r);  NwJw = V Mx^{-1}
-        const int lda = 13;
-        wgemm<1, 1, false, false>(r, r, m, Jbar + 6 * ldc, ldc, V, ldm, [&](int i, int j, double v) { Aug[i + j * lda] = v; });
-        for (int e = lane; e < r * r; e += 32) {
+        tgemm<1, 1, false, false>(r, r, m, Jbar + 6 * ldc, ldc, V, ldm, [&](int i, int j, double v) { Aug[i + j * lda] = v; });
+        for (int e = tid; e < r * r; e += nt) {
             int j = e / r, i = e - j * r;
             Aug[i + (r + j) * lda] = (i == j) ? 1.0 : 0.0;
         }
-        __syncwarp();
-        const double cond2 = wgauss_jordan(r, r, Aug, lda);
-        if (!(cond2 > 1e-14)) ok = 0;
+        tsync();
+        if (warp == 0) {
+            const double cond2 = wgauss_jordan(r, r, Aug, lda);
+            if (!(cond2 > 1e-14) && lane == 0) s_ok = 0;
+        }
+        tsync();
         double *g = w.NwJw + s * m * RMAX;
-        wgemm<2, 1, false, false>(m, r, r, V, ldm, Aug + r * lda, lda, [&](int i, int j, double v) { g[i + j * m] = v; });
-        for (int e = m * r + lane; e < m * RMAX; e += 32) g[e] = 0.0;
+        tgemm<1, 2, false, false>(m, r, r, V, ldm, Aug + r * lda, lda, [&](int i, int j, double v) { g[i + j * m] = v; });
+        for (int e = m * r + tid; e < m * RMAX; e += nt) g[e] = 0.0;
     } else {
         double *g = w.NwJw + s * m * RMAX;
-        for (int e = lane; e < m * RMAX; e += 32) g[e] = 0.0;
+        for (int e = tid; e < m * RMAX; e += nt) g[e] = 0.0;
+        tsync();
     }
-    __syncwarp();
-    wcopy(m, m, Q, ldm, w.Winv + s * m * m, m);
+    tcopy(m, m, Wblk, ldn, w.Winv + s * m * m, m);
     // tau_g = W^+ u
-    wgemv<false>(m, m, Q, ldm, u, [&](int i, double v) { w.tau_grav[s * m + i] = v; });
-    if (lane == 0) w.status[s] = ok ? 1 : 0;
+    tgemv<false>(m, m, Wblk, ldn, u, [&](int i, double v) { w.tau_grav[s * m + i] = v; });
+    tsync();
+    if (tid == 0) w.status[s] = s_ok ? 1 : 0;
 }
 
 // N_C = I - Jc^T Jbar^T, materialised only when a caller asks for the public field (dwbc_batch_get_matrix)

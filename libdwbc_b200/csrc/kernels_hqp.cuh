@@ -26,6 +26,7 @@
 #pragma once
 #include "batch.h"
 #include "kernels_rbd.cuh"
+#include "team_linalg.cuh"
 #include "warp_linalg.cuh"
 
 namespace dwbc {
@@ -51,7 +52,7 @@ struct HqpSmem {
         rin = o; o += mc + 2;   // 1 / scaled row norm
         bt = o; o += mc + 2;    // right-hand side of the current sub-problem
         gi = o; o += 6 * QP_NV_MAX + 8;  // GiScratch
-        vec = o; o += 6 * (n + 2);
+        vec = o; o += 6 * (n + 2) + 2;  // + status / iteration words of the QP just solved
         total = o;
     }
 };
@@ -118,14 +119,23 @@ __device__ __forceinline__ GiResult gi_solve(const QpView &V, const double *bt, 
     for (int e = lane; e < ldq * nv; e += 32) Q[e] = 0.0;
     __syncwarp();
     if (lane < nv) Q[lane + lane * ldq] = 1.0;
-    // 1 / (scaled row norm): violations are compared as distances in y-space
+    // 1 / (scaled row norm): violations are compared as distances in y-space.  Rows whose norm is below 1e-10 of the
+    // largest row norm are numerically zero (what rounding leaves of a constraint already active at a higher level) and
+    // never enter the active set (rin = 0); the oracle applies the same rule.
+    double smax = 0.0;
     for (int i = lane; i < mc; i += 32) {
         double s = 0.0;
         for (int j = 0; j < nv; j++) {
             const double v = V.a(i, j) * isds[j];
             s = fma(v, v, s);
         }
-        rin[i] = s > 0.0 ? 1.0 / sqrt(s) : 0.0;
+        rin[i] = s;
+        smax = s > smax ? s : smax;
+    }
+    smax = warp_max(smax);
+    for (int i = lane; i < mc; i += 32) {
+        const double s = rin[i];
+        rin[i] = (s > 0.0 && s > 1e-20 * smax) ? 1.0 / sqrt(s) : 0.0;
     }
     __syncwarp();
     double y = 0.0;           // lane j: scaled variable j
@@ -337,24 +347,42 @@ __device__ __forceinline__ LevelOut solve_level(int t, int r, int m, int mt, int
     const int nv = t + r, mc = mt + nc;
     LevelOut out{1, 0};
     QpView V{U, AU, ldm, ldc, m, mt, nc, 0, nv};
-    // row tolerances in the units of the rows, the quick exit, and the active rows of the quick exit
+    // row tolerances in the units of the rows, the quick exit, and the active rows of the quick exit.  Numerically zero
+    // rows (norm <= 1e-10 of the largest) cannot be influenced by x: they only decide feasibility (b >= -1e-9).
+    double smax = 0.0;
+    for (int i = lane; i < mc; i += 32) {
+        double s = 0.0;
+        for (int j = 0; j < nv; j++) {
+            const double v = V.a(i, j);
+            s = fma(v, v, s);
+        }
+        rin[i] = s;
+        smax = s > smax ? s : smax;
+    }
+    smax = warp_max(smax);
     double bmin = 1e300;
+    bool infeasible = false;
     for (int i0 = 0; i0 < mc; i0 += 32) {
         const int i = i0 + lane;
         bool on = false;
         if (i < mc) {
-            double s = 0.0;
-            for (int j = 0; j < nv; j++) {
-                const double v = V.a(i, j);
-                s = fma(v, v, s);
-            }
+            const double s = rin[i];
             const double sc = fmax(sqrt(s), fabs(b[i]));
             tolv[i] = 1e-10 * sc;
-            bmin = fmin(bmin, b[i] + 1e-10 * sc);
+            if (s > 1e-20 * smax && s >= 1e-28)
+                bmin = fmin(bmin, b[i] + 1e-10 * sc);
+            else if (b[i] < -1e-9)
+                infeasible = true;
             on = s > 0.0 && b[i] < 1e-9 * (1.0 + fabs(b[i]));
         }
         const unsigned bal = __ballot_sync(DWBC_FULL, on);
         if (lane == 0) S.pinw[i0 >> 5] = bal;
+    }
+    if (__any_sync(DWBC_FULL, infeasible)) {
+        out.status = 0;
+        x_out = 0.0;
+        __syncwarp();
+        return out;
     }
     bmin = warp_min(bmin);
     __syncwarp();
@@ -492,19 +520,22 @@ __device__ __forceinline__ LevelOut solve_level(int t, int r, int m, int mt, int
     return out;
 }
 
-__global__ void hqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int redist) {
+// One CTA (team) per state: QP assembly (U, Atemp U, right-hand sides) and the torque updates use every thread; the
+// active-set iterations of one QP are inherently narrow (one lane per variable) and run on warp 0 while the CTA's other
+// warps wait at the barrier -- the SM's other resident CTAs fill the issue slots meanwhile.
+__global__ void __launch_bounds__(TEAM, 5) hqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int redist) {
     DWBC_DYN_SMEM(smem);
-    const int wpb = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = lane_id();
-    const long long s = (long long)blockIdx.x * wpb + wid;
-    if (s >= w.B) return;
+    const int tid = t_id(), nt = t_n(), warp = tid >> 5, lane = lane_id();
+    const long long s = blockIdx.x;
     const int n = w.n, m = w.m, nb = w.nb;
     const HqpSmem L(n, m);
-    double *sm = (double *)smem + (size_t)wid * L.total;
+    double *sm = (double *)smem;
     double *U = sm + L.U, *AU = sm + L.AU, *At = sm + L.At, *Q = sm + L.Q, *R = sm + L.R, *b = sm + L.b, *tolv = sm + L.tol, *rin = sm + L.rin;
     const GiScratch S(sm + L.gi, sm + L.bt);
     double *vec = sm + L.vec;
     const int vs = n + 2;
     double *tprev = vec, *base = vec + vs, *fs = vec + 2 * vs, *bA0 = vec + 3 * vs, *xs = vec + 4 * vs, *lf = vec + 5 * vs;
+    int *s_lo = (int *)(vec + 6 * vs);  // status, iterations of the QP just solved by warp 0
     const int ldm = L.ldm, ldc = L.ldc, ldq = L.ldq;
     int st = w.status[s];
     const bool contact_ok = st & 1;
@@ -517,82 +548,87 @@ __global__ void hqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__re
     const int mt = cfg->tlim_set ? 2 * m : 0;
     int total_iters = 0;
     double *tau_task = w.tau_task + s * m, *tau_contact = w.tau_contact + s * m;
-    if (!contact_ok) {
-        if (lane == 0) w.status[s] = st, w.qp_iters[s] = 0;
+    if (!contact_ok) {  // uniform over the CTA
+        if (tid == 0) w.status[s] = st, w.qp_iters[s] = 0;
         return;
     }
     // ---- Atemp = A_const A_rot Jbar^T[:, 6:]  (nc x m)  and  bA0 = A_const A_rot P_C ----
     {
         const double *Jb = w.Jbar + s * (long long)CMAX * n;
         const double *pose = w.pose + s * (long long)nb * POSE_STRIDE;
-        for (int k = 0; k < kc; k++) {
+        for (int e = tid; e < kc * (m + 1); e += nt) {
+            const int k = e / (m + 1), j = e - k * (m + 1);
             const ContactCfg &cc = cfg->contacts[w.cidx[s * MAX_ACTIVE_CONTACTS + k]];
             const double *Rl = pose + cc.link * POSE_STRIDE;
-            for (int j = lane; j < m; j += 32) {
+            double o[10];
+            if (j < m) {
                 const double *col = Jb + 6 * k + (long long)(6 + j) * CMAX;
-                double o[10];
                 contact_rows(cc, Rl, ld3(col), ld3(col + 3), o);
                 for (int a = 0; a < 10; a++) At[10 * k + a + j * ldc] = o[a];
-            }
-            if (lane == 0) {
+            } else {
                 const double *pc = w.PC + s * CMAX + 6 * k;
-                double o[10];
                 contact_rows(cc, Rl, ld3(pc), ld3(pc + 3), o);
                 for (int a = 0; a < 10; a++) bA0[10 * k + a] = o[a];
             }
         }
     }
-    for (int i = lane; i < m; i += 32) tprev[i] = w.tau_grav[s * m + i];
-    __syncwarp();
+    for (int i = tid; i < m; i += nt) tprev[i] = w.tau_grav[s * m + i];
+    tsync();
     const double *NwJw = w.NwJw + s * (long long)m * RMAX;
     if (hqp) {
         const int nl = cfg->nlevels;
-        for (int i = lane; i < m; i += 32) tau_task[i] = 0.0, tau_contact[i] = 0.0;
+        for (int i = tid; i < m; i += nt) tau_task[i] = 0.0, tau_contact[i] = 0.0;
         for (int l = 0; l < nl; l++) {
             const int t = cfg->tasks[l].dof;
-            for (int i = lane; i < t; i += 32) w.fstar_qp[l][s * t + i] = 0.0;
-            for (int i = lane; i < RMAX; i += 32) w.contact_qp[l][s * RMAX + i] = 0.0;
-            if (lane < ACTIVE_WORDS) w.active[l][s * ACTIVE_WORDS + lane] = 0u;
+            for (int i = tid; i < t; i += nt) w.fstar_qp[l][s * t + i] = 0.0;
+            for (int i = tid; i < RMAX; i += nt) w.contact_qp[l][s * RMAX + i] = 0.0;
+            if (tid < ACTIVE_WORDS) w.active[l][s * ACTIVE_WORDS + tid] = 0u;
         }
         bool all_ok = task_ok;
         for (int l = 0; l < nl && all_ok; l++) {
             const int t = cfg->tasks[l].dof;
             const int nv = t + r;
+            tsync();  // the previous level is done with U / AU / b / fs
             // U = [Ntorque | NwJw]
-            wcopy(m, t, w.Ntq[l] + s * (long long)m * t, m, U, ldm);
-            wcopy(m, r, NwJw, m, U + t * ldm, ldm);
-            for (int i = lane; i < t; i += 32) fs[i] = w.fstar[l][s * t + i];
-            __syncwarp();
+            tcopy(m, t, w.Ntq[l] + s * (long long)m * t, m, U, ldm);
+            tcopy(m, r, NwJw, m, U + t * ldm, ldm);
+            for (int i = tid; i < t; i += nt) fs[i] = w.fstar[l][s * t + i];
+            tsync();
             // base = tau_prev + Ntorque f*
-            wgemv<false>(m, t, U, ldm, fs, [&](int i, double v) { base[i] = tprev[i] + v; });
+            tgemv<false>(m, t, U, ldm, fs, [&](int i, double v) { base[i] = tprev[i] + v; });
             // AU = Atemp U
-            wgemm<2, 2, false, false>(nc, nv, m, At, ldc, U, ldm, [&](int i, int j, double v) { AU[i + j * ldc] = v; });
-            __syncwarp();
+            tgemm<2, 2, false, false>(nc, nv, m, At, ldc, U, ldm, [&](int i, int j, double v) { AU[i + j * ldc] = v; });
+            tsync();
             if (mt)
-                for (int i = lane; i < m; i += 32) {
+                for (int i = tid; i < m; i += nt) {
                     b[i] = cfg->tlim[i] - base[i];
                     b[m + i] = cfg->tlim[i] + base[i];
                 }
-            wgemv<false>(nc, m, At, ldc, base, [&](int i, double v) { b[mt + i] = -(bA0[i] - v); });
-            __syncwarp();
-            double xj;
-            LevelOut lo = solve_level(t, r, m, mt, nc, U, AU, ldm, ldc, b, tolv, rin, Q, R, ldq, S, xj, w.active[l] + s * ACTIVE_WORDS);
-            total_iters += lo.iters;
-            if (!lo.status) {
+            tgemv<false>(nc, m, At, ldc, base, [&](int i, double v) { b[mt + i] = -(bA0[i] - v); });
+            tsync();
+            if (warp == 0) {
+                double xj;
+                LevelOut lo = solve_level(t, r, m, mt, nc, U, AU, ldm, ldc, b, tolv, rin, Q, R, ldq, S, xj, w.active[l] + s * ACTIVE_WORDS);
+                if (lane == 0) s_lo[0] = lo.status, s_lo[1] = lo.iters;
+                if (lo.status) {
+                    if (lane < t) {
+                        w.fstar_qp[l][s * t + lane] = xj;
+                        fs[lane] += xj;
+                    }
+                    if (lane >= t && lane < nv) {
+                        w.contact_qp[l][s * RMAX + lane - t] = xj;
+                        xs[lane - t] = xj;
+                    }
+                }
+            }
+            tsync();
+            total_iters += s_lo[1];
+            if (!s_lo[0]) {
                 all_ok = false;  // reference: f_star_qp_ = contact_qp_ = 0 and return 0 (src/dwbc.cpp:1117-1125, 836-837)
                 break;
             }
-            if (lane < t) {
-                w.fstar_qp[l][s * t + lane] = xj;
-                fs[lane] += xj;
-            }
-            if (lane >= t && lane < nv) {
-                w.contact_qp[l][s * RMAX + lane - t] = xj;
-                xs[lane - t] = xj;
-            }
-            __syncwarp();
             // torque_task += Null_{l-1} J_kt Lambda (f* + f*_qp) = Ntorque (f* + x_t);  tau_prev = tau_grav + torque_task
-            wgemv<false>(m, t, U, ldm, fs, [&](int i, double v) {
+            tgemv<false>(m, t, U, ldm, fs, [&](int i, double v) {
                 const double tt = tau_task[i] + v;
                 tau_task[i] = tt;
                 tprev[i] = w.tau_grav[s * m + i] + tt;
@@ -600,53 +636,54 @@ __global__ void hqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__re
             // torque_h = J_kt Lambda_t (f* + f*_qp)
             {
                 const double *Lt = w.Lamt[l] + s * (long long)t * t, *Jk = w.Jkt[l] + s * (long long)m * t;
-                wgemv<false>(t, t, Lt, t, fs, [&](int i, double v) { lf[i] = v; });
-                __syncwarp();
-                wgemv<false>(m, t, Jk, m, lf, [&](int i, double v) { w.torque_h[l][s * m + i] = v; });
+                tgemv<false>(t, t, Lt, t, fs, [&](int i, double v) { lf[i] = v; });
+                tsync();
+                tgemv<false>(m, t, Jk, m, lf, [&](int i, double v) { w.torque_h[l][s * m + i] = v; });
             }
             // torque_contact = NwJw contact_qp  (zero without an internal-force space: quirk 1 of SURVEY Appendix A)
-            if (r > 0) wgemv<false>(m, r, NwJw, m, xs, [&](int i, double v) { tau_contact[i] = v; });
-            __syncwarp();
+            if (r > 0) tgemv<false>(m, r, NwJw, m, xs, [&](int i, double v) { tau_contact[i] = v; });
         }
         if (all_ok) st |= 2;
     }
     if (redist) {
-        if (lane < ACTIVE_WORDS) w.active[MAX_LEVELS][s * ACTIVE_WORDS + lane] = 0u;
-        for (int i = lane; i < RMAX; i += 32) w.cf_redis[s * RMAX + i] = 0.0;
+        if (tid < ACTIVE_WORDS) w.active[MAX_LEVELS][s * ACTIVE_WORDS + tid] = 0u;
+        for (int i = tid; i < RMAX; i += nt) w.cf_redis[s * RMAX + i] = 0.0;
+        tsync();  // tau_task / tau_contact of the level loop are visible to every thread
         if (r <= 0) {
-            for (int i = lane; i < m; i += 32) tau_contact[i] = 0.0;  // reference src/dwbc.cpp:1562-1566
+            for (int i = tid; i < m; i += nt) tau_contact[i] = 0.0;  // reference src/dwbc.cpp:1562-1566
             st |= 4;
         } else {
-            __syncwarp();
-            for (int i = lane; i < m; i += 32) base[i] = w.tau_grav[s * m + i] + tau_task[i] + tau_contact[i];  // tau_in
-            wcopy(m, r, NwJw, m, U, ldm);
-            __syncwarp();
-            wgemm<2, 2, false, false>(nc, r, m, At, ldc, U, ldm, [&](int i, int j, double v) { AU[i + j * ldc] = v; });
+            for (int i = tid; i < m; i += nt) base[i] = w.tau_grav[s * m + i] + tau_task[i] + tau_contact[i];  // tau_in
+            tcopy(m, r, NwJw, m, U, ldm);
+            tsync();
+            tgemm<2, 1, false, false>(nc, r, m, At, ldc, U, ldm, [&](int i, int j, double v) { AU[i + j * ldc] = v; });
             if (mt)
-                for (int i = lane; i < m; i += 32) {
+                for (int i = tid; i < m; i += nt) {
                     b[i] = cfg->tlim[i] - base[i];
                     b[m + i] = cfg->tlim[i] + base[i];
                 }
-            wgemv<false>(nc, m, At, ldc, base, [&](int i, double v) { b[mt + i] = -(bA0[i] - v); });
-            __syncwarp();
-            double xj;
-            LevelOut lo = solve_level(0, r, m, mt, nc, U, AU, ldm, ldc, b, tolv, rin, Q, R, ldq, S, xj, w.active[MAX_LEVELS] + s * ACTIVE_WORDS);
-            total_iters += lo.iters;
-            if (lo.status) {
-                if (lane < r) {
+            tgemv<false>(nc, m, At, ldc, base, [&](int i, double v) { b[mt + i] = -(bA0[i] - v); });
+            tsync();
+            if (warp == 0) {
+                double xj;
+                LevelOut lo = solve_level(0, r, m, mt, nc, U, AU, ldm, ldc, b, tolv, rin, Q, R, ldq, S, xj, w.active[MAX_LEVELS] + s * ACTIVE_WORDS);
+                if (lane == 0) s_lo[0] = lo.status, s_lo[1] = lo.iters;
+                if (lo.status && lane < r) {
                     w.cf_redis[s * RMAX + lane] = xj;
                     xs[lane] = xj;
                 }
-                __syncwarp();
-                wgemv<false>(m, r, NwJw, m, xs, [&](int i, double v) { tau_contact[i] += v; });
+            }
+            tsync();
+            total_iters += s_lo[1];
+            if (s_lo[0]) {
+                tgemv<false>(m, r, NwJw, m, xs, [&](int i, double v) { tau_contact[i] += v; });
                 st |= 4;
             } else {
-                for (int i = lane; i < m; i += 32) tau_contact[i] = 0.0;  // reference src/dwbc.cpp:1553-1559
+                for (int i = tid; i < m; i += nt) tau_contact[i] = 0.0;  // reference src/dwbc.cpp:1553-1559
             }
         }
     }
-    __syncwarp();
-    if (lane == 0) {
+    if (tid == 0) {
         w.status[s] = st;
         w.qp_iters[s] = total_iters;
     }

@@ -272,17 +272,17 @@ __device__ __forceinline__ void rbd_state(const DevModel *__restrict__ md, const
 }
 
 // 6 x n point Jacobian (rows [linear; angular], reference src/contact_constraint.cpp:56-62) of a
-// point fixed in body `body` at local offset `pl`, one column per lane, written to dst with leading
-// dimension ldd starting at row `row0`.  `pose` = this state's pose records.
-__device__ __forceinline__ void point_jacobian(const DevModel *__restrict__ md, const double *__restrict__ pose, int body, Vec3 pl,
-                                               double *dst, int ldd, int row0, int rows_first, int rows_count) {
+// point fixed in body `body` at local offset `pl`, one column per thread (`tid` of `nt` cooperating threads),
+// written to dst with leading dimension ldd starting at row `row0`.  `pose` = this state's pose records.
+__device__ __forceinline__ void point_jacobian_t(const DevModel *__restrict__ md, const double *__restrict__ pose, int body, Vec3 pl,
+                                                 double *dst, int ldd, int row0, int rows_first, int rows_count, int tid, int nt) {
     const int n = md->n;
     const double *pb = pose + body * POSE_STRIDE;
     const Vec3 pw = ld3(pb + 9) + mv(pb, pl);
     const double *R0 = pose;
     const Vec3 p0 = ld3(pose + 9);
     const uint64_t anc = md->anc_mask[body];
-    for (int j = lane_id(); j < n; j += 32) {
+    for (int j = tid; j < n; j += nt) {
         Vec3 lin = v3(0, 0, 0), ang = v3(0, 0, 0);
         if (j < 3) {
             lin = v3(j == 0, j == 1, j == 2);
@@ -299,6 +299,10 @@ __device__ __forceinline__ void point_jacobian(const DevModel *__restrict__ md, 
         const double v[6] = {lin.x, lin.y, lin.z, ang.x, ang.y, ang.z};
         for (int r = 0; r < rows_count; r++) dst[row0 + r + j * ldd] = v[rows_first + r];
     }
+}
+__device__ __forceinline__ void point_jacobian(const DevModel *__restrict__ md, const double *__restrict__ pose, int body, Vec3 pl,
+                                               double *dst, int ldd, int row0, int rows_first, int rows_count) {
+    point_jacobian_t(md, pose, body, pl, dst, ldd, row0, rows_first, rows_count, lane_id(), 32);
 }
 
 }  // namespace dwbc

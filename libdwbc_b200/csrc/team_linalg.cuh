@@ -1,0 +1,246 @@
+// Team-cooperative dense FP64 linear algebra: one CTA (the "team", 64-256 threads) owns one robot state
+// and works on small column-major matrices (n <= ~50) held in shared memory.
+//
+// Why a CTA and not a warp per state: a state's working set is 30-45 KB of shared memory, so only 5-7
+// states fit on an SM.  With one warp each the SM would run 5-7 warps (measured: 4-6 % warp occupancy, FP64
+// pipe 2-7 % busy); with 4 warps each it runs 20-28 warps and the matrix products are spread over 128 threads.
+//
+// Conventions
+//   * every routine is called by ALL threads of the CTA with identical arguments;
+//   * routines do NOT synchronise on entry or exit unless their comment says so: the caller places
+//     tsync() between a producer and its consumers;
+//   * leading dimensions are odd (conflict-free column sweeps for 64-bit words).
+#pragma once
+#include "cuda_compat.h"
+#include "warp_linalg.cuh"
+
+namespace dwbc {
+
+__device__ __forceinline__ int t_id() { return (int)threadIdx.x; }
+__device__ __forceinline__ int t_n() { return (int)blockDim.x; }
+__device__ __forceinline__ void tsync() { __syncthreads(); }
+
+// Cooperative copy of a column-major rows x cols block (global or shared on either side).
+__device__ __forceinline__ void tcopy(int rows, int cols, const double *__restrict__ src, int lds, double *__restrict__ dst, int ldd) {
+    const int tid = t_id(), nt = t_n();
+    if (lds == rows && ldd == rows) {
+        for (int e = tid; e < rows * cols; e += nt) dst[e] = src[e];
+    } else {
+        for (int e = tid; e < rows * cols; e += nt) {
+            int j = e / rows, i = e - j * rows;
+            dst[i + j * ldd] = src[i + j * lds];
+        }
+    }
+}
+// Copy into a zero-padded destination block: dst is drows x dcols (leading dimension drows), src is rows x cols (lds).
+__device__ __forceinline__ void tcopy_pad(int rows, int cols, const double *__restrict__ src, int lds, int drows, int dcols, double *__restrict__ dst) {
+    for (int e = t_id(); e < drows * dcols; e += t_n()) {
+        int j = e / drows, i = e - j * drows;
+        dst[e] = (i < rows && j < cols) ? src[i + j * lds] : 0.0;
+    }
+}
+__device__ __forceinline__ void tfill(int count, double *dst, double v) {
+    for (int e = t_id(); e < count; e += t_n()) dst[e] = v;
+}
+
+// C(i,j) <- epi(i, j, sum_k opA(i,k) * opB(k,j)) for an M x N result; same operand conventions as wgemm.
+// Tiles are cyclic (rows ti + r*tr, columns tj + c*tc); the tile index runs over the whole team.
+template <int TR, int TC, bool TA, bool TB, class Epi>
+__device__ __forceinline__ void tgemm(int M, int N, int K, const double *__restrict__ A, int lda, const double *__restrict__ B, int ldb, Epi epi) {
+    const int tr = (M + TR - 1) / TR, tc = (N + TC - 1) / TC;
+    for (int tile = t_id(); tile < tr * tc; tile += t_n()) {
+        const int tj = tile / tr, ti = tile - tj * tr;
+        int ia[TR], jb[TC];
+        DWBC_UNROLL(TR)
+        for (int r = 0; r < TR; r++) {
+            int i = ti + r * tr;
+            ia[r] = (i < M ? i : ti) * (TA ? lda : 1);
+        }
+        DWBC_UNROLL(TC)
+        for (int c = 0; c < TC; c++) {
+            int j = tj + c * tc;
+            jb[c] = (j < N ? j : tj) * (TB ? 1 : ldb);
+        }
+        double acc[TR][TC];
+        DWBC_UNROLL(TR)
+        for (int r = 0; r < TR; r++) {
+            DWBC_UNROLL(TC)
+            for (int c = 0; c < TC; c++) acc[r][c] = 0.0;
+        }
+        const int sa = TA ? 1 : lda, sb = TB ? ldb : 1;
+        DWBC_UNROLL(2)
+        for (int k = 0; k < K; k++) {
+            double a[TR], b[TC];
+            DWBC_UNROLL(TR)
+            for (int r = 0; r < TR; r++) a[r] = A[ia[r] + k * sa];
+            DWBC_UNROLL(TC)
+            for (int c = 0; c < TC; c++) b[c] = B[jb[c] + k * sb];
+            DWBC_UNROLL(TR)
+            for (int r = 0; r < TR; r++) {
+                DWBC_UNROLL(TC)
+                for (int c = 0; c < TC; c++) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+            }
+        }
+        DWBC_UNROLL(TR)
+        for (int r = 0; r < TR; r++) {
+            DWBC_UNROLL(TC)
+            for (int c = 0; c < TC; c++) {
+                int i = ti + r * tr, j = tj + c * tc;
+                if (i < M && j < N) epi(i, j, acc[r][c]);
+            }
+        }
+    }
+}
+
+// y(i) <- epi(i, sum_k opA(i,k) x(k)).  Four adjacent lanes share one row (each takes every 4th k) and combine with
+// two shuffles, so a 33..39-row product keeps the whole team busy.  Requires blockDim.x to be a multiple of 32.
+template <bool TA, class Epi>
+__device__ __forceinline__ void tgemv(int M, int K, const double *__restrict__ A, int lda, const double *__restrict__ x, Epi epi) {
+    const int tid = t_id(), rows_per_pass = t_n() >> 2, part = tid & 3;
+    for (int r0 = 0; r0 < M; r0 += rows_per_pass) {
+        const int i = r0 + (tid >> 2);
+        const bool act = i < M;
+        const int ii = act ? i : 0;
+        double a0 = 0.0;
+        for (int k = part; k < K; k += 4) a0 = fma(TA ? A[k + ii * lda] : A[ii + k * lda], x[k], a0);
+        a0 += __shfl_xor_sync(DWBC_FULL, a0, 1);
+        a0 += __shfl_xor_sync(DWBC_FULL, a0, 2);
+        if (act && part == 0) epi(i, a0);
+    }
+}
+
+// ---- Cholesky with register-resident ownership ------------------------------------------------------------
+// The lower triangle (n(n+1)/2 entries, packed column by column) is dealt cyclically to the threads; every thread keeps
+// its entries in registers for the whole factorisation.  Step k: the owners of column k publish their (fully updated,
+// still unscaled) values to shared memory, ONE barrier, then every thread applies  a_ij -= a_ik a_jk / a_kk  to its
+// entries with j > k.  A final pass scales column k by 1/sqrt(a_kk).  One barrier per column instead of two, no
+// shared-memory read-modify-write, and the trailing update is spread over the whole team.
+constexpr int CHOL_MAX_OWN = 8;  // ceil(40*41/2 / 128) = 7 for n <= 40 with >= 128 threads (13 for 64 threads -> see static checks at call sites)
+
+// In-place lower Cholesky of the SPD matrix in the lower triangle of A (n x n, leading dimension ld).  On return the
+// lower triangle holds L, rdiag[i] = 1/L(i,i).  Returns the smallest pivot (<= 0: not SPD; the factorisation continues
+// with a clamped pivot so no NaN appears).  Synchronises on entry and on exit.  n(n+1)/2 <= MAXOWN * blockDim.x.
+template <int MAXOWN>
+__device__ __forceinline__ double tchol_lower(int n, double *A, int ld, double *rdiag) {
+    const int tid = t_id(), nt = t_n();
+    const int total = n * (n + 1) / 2;
+    int ei[MAXOWN], ej[MAXOWN];
+    double v[MAXOWN];
+    tsync();
+    DWBC_UNROLL(MAXOWN)
+    for (int s = 0; s < MAXOWN; s++) {
+        const int e = tid + s * nt;
+        int i = 0, j = n;  // j = n marks "no entry"
+        if (e < total) {
+            // packed column-major lower triangle: column j starts at j*n - j(j-1)/2
+            int jj = (int)((2.0 * n + 1.0 - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * e)) * 0.5);
+            if (jj < 0) jj = 0;
+            if (jj > n - 1) jj = n - 1;
+            while (jj > 0 && jj * n - jj * (jj - 1) / 2 > e) jj--;
+            while (jj + 1 < n && (jj + 1) * n - (jj + 1) * jj / 2 <= e) jj++;
+            j = jj;
+            i = j + (e - (j * n - j * (j - 1) / 2));
+        }
+        ei[s] = i;
+        ej[s] = j;
+        v[s] = (j < n) ? A[i + j * ld] : 0.0;
+    }
+    double minpiv = 1e300;
+    for (int k = 0; k < n; k++) {
+        DWBC_UNROLL(MAXOWN)
+        for (int s = 0; s < MAXOWN; s++)
+            if (ej[s] == k) A[ei[s] + k * ld] = v[s];
+        tsync();
+        double akk = A[k + k * ld];
+        minpiv = akk < minpiv ? akk : minpiv;
+        if (!(akk > 1e-300)) akk = 1e-300;
+        const double inv = 1.0 / akk;
+        DWBC_UNROLL(MAXOWN)
+        for (int s = 0; s < MAXOWN; s++)
+            if (ej[s] > k && ej[s] < n) v[s] = fma(-A[ei[s] + k * ld] * inv, A[ej[s] + k * ld], v[s]);
+    }
+    tsync();
+    // rdiag, then scale: L(i,k) = a_ik / sqrt(a_kk)
+    for (int k = tid; k < n; k += nt) {
+        double akk = A[k + k * ld];
+        if (!(akk > 1e-300)) akk = 1e-300;
+        rdiag[k] = 1.0 / sqrt(akk);
+    }
+    tsync();
+    DWBC_UNROLL(MAXOWN)
+    for (int s = 0; s < MAXOWN; s++)
+        if (ej[s] < n) {
+            const double r = rdiag[ej[s]];
+            A[ei[s] + ej[s] * ld] = (ei[s] == ej[s]) ? 1.0 / r : A[ei[s] + ej[s] * ld] * r;
+        }
+    tsync();
+    return minpiv;
+}
+
+// Xi <- L^{-1} (lower triangular, full n x n storage with zeros above the diagonal), one column per thread, forward
+// substitution on a unit vector.  L and Xi must not overlap.  No synchronisation.
+__device__ __forceinline__ void ttri_inverse(int n, const double *L, int ld, const double *rdiag, double *Xi, int ldx) {
+    for (int j = t_id(); j < n; j += t_n()) {
+        double *xj = Xi + j * ldx;
+        for (int i = 0; i < j; i++) xj[i] = 0.0;
+        xj[j] = rdiag[j];
+        for (int i = j + 1; i < n; i++) {
+            double a0 = 0.0, a1 = 0.0;
+            int k = j;
+            for (; k + 1 < i; k += 2) {
+                a0 = fma(-L[i + k * ld], xj[k], a0);
+                a1 = fma(-L[i + (k + 1) * ld], xj[k + 1], a1);
+            }
+            if (k < i) a0 = fma(-L[i + k * ld], xj[k], a0);
+            xj[i] = (a0 + a1) * rdiag[i];
+        }
+    }
+}
+
+// Out(i,j) <- epi(i, j, (A^{-1})(i,j)) with A^{-1} = Xi^T Xi for the lower-triangular Xi = L^{-1}: only k >= max(i,j)
+// contributes.  Each thread computes a TR x TC tile of the LOWER triangle and mirrors it.  No synchronisation.
+template <class Epi>
+__device__ __forceinline__ void tsyrk_inverse(int n, const double *Xi, int ldx, Epi epi) {
+    constexpr int T = 4;
+    const int tb = (n + T - 1) / T;  // tiles per dimension (blocked, not cyclic: the k-range depends on the tile position)
+    const int ntiles = tb * (tb + 1) / 2;
+    for (int tile = t_id(); tile < ntiles; tile += t_n()) {
+        // tile -> (bi >= bj)
+        int bj = 0, rem = tile;
+        while (rem >= tb - bj) rem -= tb - bj, bj++;
+        const int bi = bj + rem;
+        const int i0 = bi * T, j0 = bj * T;
+        double acc[T][T];
+        DWBC_UNROLL(T)
+        for (int r = 0; r < T; r++) {
+            DWBC_UNROLL(T)
+            for (int c = 0; c < T; c++) acc[r][c] = 0.0;
+        }
+        int io[T], jo[T];
+        DWBC_UNROLL(T)
+        for (int r = 0; r < T; r++) io[r] = (i0 + r < n ? i0 + r : i0) * ldx, jo[r] = (j0 + r < n ? j0 + r : j0) * ldx;
+        for (int k = i0; k < n; k++) {  // Xi(k, i) = 0 for k < i, and i >= i0
+            double a[T], b[T];
+            DWBC_UNROLL(T)
+            for (int r = 0; r < T; r++) a[r] = Xi[k + io[r]], b[r] = Xi[k + jo[r]];
+            DWBC_UNROLL(T)
+            for (int r = 0; r < T; r++) {
+                DWBC_UNROLL(T)
+                for (int c = 0; c < T; c++) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+            }
+        }
+        DWBC_UNROLL(T)
+        for (int r = 0; r < T; r++) {
+            DWBC_UNROLL(T)
+            for (int c = 0; c < T; c++) {
+                const int i = i0 + r, j = j0 + c;
+                if (i < n && j < n && i >= j) {
+                    epi(i, j, acc[r][c]);
+                    if (i != j) epi(j, i, acc[r][c]);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace dwbc

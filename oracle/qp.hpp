@@ -174,13 +174,23 @@ inline bool ldp(const Mat &G, const std::vector<double> &h, std::vector<double> 
     x.assign(n, 0.0);
     lambda.assign(m, 0.0);
     // row scaling (does not change the feasible set); all-zero rows are decided directly
+    // A row whose norm is below 1e-10 of the largest row norm is numerically zero: in the hierarchy such rows are what is
+    // left of a constraint that is already active at a higher level (its normal lies in the range the null-space projector
+    // removed, so only rounding noise remains).  Normalising it would turn noise into a constraint; qpOASES discards such
+    // rows through its epsNum/epsDen ratio tests.
     std::vector<int> rows;
     std::vector<double> scale, vtol;
+    double smax = 0;
+    for (int i = 0; i < m; i++) {
+        double s = 0;
+        for (int j = 0; j < n; j++) s += G(i, j) * G(i, j);
+        smax = std::max(smax, std::sqrt(s));
+    }
     for (int i = 0; i < m; i++) {
         double s = 0;
         for (int j = 0; j < n; j++) s += G(i, j) * G(i, j);
         s = std::sqrt(s);
-        if (s < 1e-14) {
+        if (s < 1e-14 || s <= 1e-10 * smax) {
             if (h[i] > 1e-9) return false;
             continue;
         }

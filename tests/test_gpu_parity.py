@@ -178,14 +178,39 @@ def test_config2_hqp_vs_oracle(mixed):
     idx = [b for b in range(B) if good[b]][:96]
     # include every state of the subset that actually has an active QP
     hard = [b for b in range(B) if good[b] and any(len(act[l][b]) for l in range(4))][:64]
+    nact = 0
     for b in sorted(set(idx + hard)):
         ref.update_kinematics(q[b], qd[b]); ref.set_contact(*flags[b]); ref.calc_contact_constraint()
         for l in range(3):
             ref.set_task(l, fs[l][b], posture_selector() if l == 2 else None)
         ref.calc_grav(); ref.calc_task_torque(True); ref.calc_redistribute(True)
-        for l in range(3):
-            assert act[l][b] == ref.active_set(l), (b, l)
-        assert act[3][b] == ref.active_set(-1), (b, "redist")
+        for l in (0, 1, 2, -1):
+            a_ref = ref.active_set(l)
+            nact += len(a_ref)
+            assert same_active_set(act[l if l >= 0 else 3][b], a_ref, gray_rows(ref, l)), (b, l)
+    assert nact > 50  # the sample does exercise the active-set logic
+
+
+def gray_rows(ref, level):
+    """Rows whose slack at the oracle's solution lies within a decade of the reporting threshold 1e-9 (1 + |b|) (the rule
+    both sides use to call a row active).  Such weakly active rows -- zero multiplier, slack inherited from the round-off
+    of the level above -- are the only ones allowed to differ."""
+    if level < 0:
+        A = ref.get("redisA")
+        if A.size == 0 or ref.get("cf_redis_qp").size == 0:  # single support: no internal-force space, no QP
+            return set()
+        ub, x = ref.get("redisub")[:, 0], ref.get("cf_redis_qp")[:, 0]
+    else:
+        A, ub = ref.get(f"qpA{level}"), ref.get(f"qpub{level}")[:, 0]
+        x = np.concatenate([ref.get(f"f_star_qp{level}")[:, 0], ref.get(f"contact_qp{level}")[:, 0]])[:A.shape[1]]
+    if A.size == 0:
+        return set()
+    s = (A @ x - ub) / (1.0 + np.abs(ub))
+    return set(np.where((s > -1e-8) & (s < -1e-10))[0].tolist())
+
+
+def same_active_set(a, b, gray):
+    return set(a) - gray == set(b) - gray
 
 
 def test_full_size_properties():
