@@ -48,14 +48,14 @@ __device__ __forceinline__ double team_spd_inverse_t(int n, double *L, int ld, d
 // SPD inverse in place: on return the full symmetric inverse is in L (n x n, ld); Xi is scratch of the same size.
 // Synchronises on entry and exit.  Returns the smallest Cholesky pivot.
 __device__ __forceinline__ double team_spd_inverse(int n, double *L, int ld, double *Xi, int ldx, double *rd) {
-    const int total = n * (n + 1) / 2, nt = t_n();
-    if (total <= 2 * nt) return team_spd_inverse_t<2>(n, L, ld, Xi, ldx, rd);
-    if (total <= 5 * nt) return team_spd_inverse_t<5>(n, L, ld, Xi, ldx, rd);
-    if (total <= 7 * nt) return team_spd_inverse_t<7>(n, L, ld, Xi, ldx, rd);
+    const int nt = t_n();
+    const int slots = ((n + 1) >> 1) * (n + 1);  // ownership slots of tchol_lower
+    if (slots <= 2 * nt) return team_spd_inverse_t<2>(n, L, ld, Xi, ldx, rd);
+    if (slots <= 7 * nt) return team_spd_inverse_t<7>(n, L, ld, Xi, ldx, rd);
     if constexpr (TEAM >= 128) {
         return team_spd_inverse_t<12>(n, L, ld, Xi, ldx, rd);  // n <= 54
     } else {
-        if (total <= 12 * nt) return team_spd_inverse_t<12>(n, L, ld, Xi, ldx, rd);
+        if (slots <= 12 * nt) return team_spd_inverse_t<12>(n, L, ld, Xi, ldx, rd);
         return team_spd_inverse_t<45>(n, L, ld, Xi, ldx, rd);  // small teams (emulation builds of the tests)
     }
 }

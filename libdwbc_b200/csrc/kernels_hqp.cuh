@@ -109,7 +109,10 @@ __device__ __forceinline__ bool bit_test(const uint32_t *w, int i) { return (w[i
 // Goldfarb-Idnani on  min 1/2|y|^2  s.t.  sum_j a(i,j) dx_j <= bt_i,  dx_j = isd_j y_j  (dx = x - x0).
 // Lane j returns dx_j.  `pin` (may be null): rows to be pinned as equalities, added first and never dropped.
 // On return act_out / u_out hold, for logical position = lane, the active row (-1 if none) and its multiplier.
-__device__ __forceinline__ GiResult gi_solve(const QpView &V, const double *bt, const double *tolv, double *rin, double isd, double *Q,
+// Deliberately NOT inlined: the solver is called from several places of solve_level, itself called per level and for the
+// redistribution QP; inlined, the kernel grew to 54k SASS instructions and the working warps spent 59 % of their
+// non-barrier stall samples waiting for instruction fetch (ncu, profiles/r01_*).
+__device__ __noinline__ GiResult gi_solve(const QpView &V, const double *bt, const double *tolv, double *rin, double isd, double *Q,
                                              double *R, int ldq, const GiScratch &S, const uint32_t *pin, double &dx_out, int &act_out,
                                              double &u_out, int max_iter) {
     const int lane = lane_id();
@@ -340,7 +343,7 @@ struct LevelOut {
 
 // Solves one QP (t task variables first, then r contact variables).  U (m x nv), AU (nc x nv) and b (rows) are in
 // shared memory; lane j returns x_j.  active_out (global, ACTIVE_WORDS words): rows with zero slack at the solution.
-__device__ __forceinline__ LevelOut solve_level(int t, int r, int m, int mt, int nc, const double *U, const double *AU, int ldm, int ldc,
+__device__ __noinline__ LevelOut solve_level(int t, int r, int m, int mt, int nc, const double *U, const double *AU, int ldm, int ldc,
                                                 const double *b, double *tolv, double *rin, double *Q, double *R, int ldq,
                                                 const GiScratch &S, double &x_out, uint32_t *active_out) {
     const int lane = lane_id();

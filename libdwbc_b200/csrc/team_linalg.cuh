@@ -121,9 +121,11 @@ constexpr int CHOL_MAX_OWN = 8;  // ceil(40*41/2 / 128) = 7 for n <= 40 with >= 
 // lower triangle holds L, rdiag[i] = 1/L(i,i).  Returns the smallest pivot (<= 0: not SPD; the factorisation continues
 // with a clamped pivot so no NaN appears).  Synchronises on entry and on exit.  n(n+1)/2 <= MAXOWN * blockDim.x.
 template <int MAXOWN>
-__device__ __forceinline__ double tchol_lower(int n, double *A, int ld, double *rdiag) {
+__device__ __noinline__ double tchol_lower(int n, double *A, int ld, double *rdiag) {
     const int tid = t_id(), nt = t_n();
-    const int total = n * (n + 1) / 2;
+    // Ownership without a square root: fold the triangle into a ((n+1)/2) x (n+1) rectangle -- fold row a holds column a
+    // (n - a entries) followed by column n-1-a (a + 1 entries).
+    const int w = n + 1, slots = ((n + 1) >> 1) * w;
     int ei[MAXOWN], ej[MAXOWN];
     double v[MAXOWN];
     tsync();
@@ -131,15 +133,15 @@ __device__ __forceinline__ double tchol_lower(int n, double *A, int ld, double *
     for (int s = 0; s < MAXOWN; s++) {
         const int e = tid + s * nt;
         int i = 0, j = n;  // j = n marks "no entry"
-        if (e < total) {
-            // packed column-major lower triangle: column j starts at j*n - j(j-1)/2
-            int jj = (int)((2.0 * n + 1.0 - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * e)) * 0.5);
-            if (jj < 0) jj = 0;
-            if (jj > n - 1) jj = n - 1;
-            while (jj > 0 && jj * n - jj * (jj - 1) / 2 > e) jj--;
-            while (jj + 1 < n && (jj + 1) * n - (jj + 1) * jj / 2 <= e) jj++;
-            j = jj;
-            i = j + (e - (j * n - j * (j - 1) / 2));
+        if (e < slots) {
+            const int a = e / w, b = e - a * w;
+            if (b < n - a) {
+                j = a;
+                i = a + b;
+            } else if (n - 1 - a != a) {
+                j = n - 1 - a;
+                i = j + (b - (n - a));
+            }
         }
         ei[s] = i;
         ej[s] = j;
@@ -160,26 +162,25 @@ __device__ __forceinline__ double tchol_lower(int n, double *A, int ld, double *
             if (ej[s] > k && ej[s] < n) v[s] = fma(-A[ei[s] + k * ld] * inv, A[ej[s] + k * ld], v[s]);
     }
     tsync();
-    // rdiag, then scale: L(i,k) = a_ik / sqrt(a_kk)
+    // rdiag[k] = 1/sqrt(a_kk); the diagonal itself becomes sqrt(a_kk) = a_kk * rdiag[k]
     for (int k = tid; k < n; k += nt) {
         double akk = A[k + k * ld];
         if (!(akk > 1e-300)) akk = 1e-300;
-        rdiag[k] = 1.0 / sqrt(akk);
+        const double r = rsqrt(akk);
+        rdiag[k] = r;
+        A[k + k * ld] = akk * r;
     }
     tsync();
     DWBC_UNROLL(MAXOWN)
     for (int s = 0; s < MAXOWN; s++)
-        if (ej[s] < n) {
-            const double r = rdiag[ej[s]];
-            A[ei[s] + ej[s] * ld] = (ei[s] == ej[s]) ? 1.0 / r : A[ei[s] + ej[s] * ld] * r;
-        }
+        if (ej[s] < n && ei[s] != ej[s]) A[ei[s] + ej[s] * ld] *= rdiag[ej[s]];
     tsync();
     return minpiv;
 }
 
 // Xi <- L^{-1} (lower triangular, full n x n storage with zeros above the diagonal), one column per thread, forward
 // substitution on a unit vector.  L and Xi must not overlap.  No synchronisation.
-__device__ __forceinline__ void ttri_inverse(int n, const double *L, int ld, const double *rdiag, double *Xi, int ldx) {
+__device__ __noinline__ void ttri_inverse(int n, const double *L, int ld, const double *rdiag, double *Xi, int ldx) {
     for (int j = t_id(); j < n; j += t_n()) {
         double *xj = Xi + j * ldx;
         for (int i = 0; i < j; i++) xj[i] = 0.0;

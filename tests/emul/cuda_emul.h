@@ -27,6 +27,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ thread_local /* only `extern __shared__` is used; mapped through emul_smem() */
