@@ -1,5 +1,5 @@
 // Stages a6-a8: the prioritised torque QPs (one per hierarchy level) and the contact-force
-// redistribution QP, solved by a batched dense FP64 active-set method -- one warp per robot state.
+// redistribution QP, solved by a batched dense FP64 active-set method -- one CTA (team) per robot state.
 //
 // Reference: RobotData::CalcTaskControlTorque hqp=true branch and CalcSingleTaskTorqueWithQP
 // (src/dwbc.cpp:818-853, 941-1127), CalcContactRedistribute QP branch (src/dwbc.cpp:1377-1568),
@@ -22,7 +22,8 @@
 // y = sqrt(d) (x - x0) and is solved by the Goldfarb-Idnani dual active-set method (Math. Prog. 27, 1983) with an
 // identity Hessian: Q (orthogonal, nv x nv) and R (upper triangular) of the active normals are updated by one
 // Householder reflection per added constraint and Givens rotations per dropped constraint.
-// Warp mapping: lane j owns variable j (row j of Q) and logical active-set position j (act, multiplier, R column slot).
+// Team mapping (gi_solve): solver state (y, multipliers, active rows, Q, R) lives in shared memory; one thread per constraint
+// row in the scan, four threads per entry in the products with Q, the whole team in the rank-one update of Q.
 #pragma once
 #include "batch.h"
 #include "kernels_rbd.cuh"
@@ -33,6 +34,7 @@ namespace dwbc {
 
 constexpr int QP_NV_MAX = 32;  // one lane per variable
 constexpr int QP_NC_MAX = 10 * MAX_ACTIVE_CONTACTS;
+constexpr int GI_SCRATCH_DOUBLES = 448;  // >= GiScratch::DOUBLES (static_assert below)
 
 struct HqpSmem {
     int ldm, ldq, ldc, U, AU, At, Q, R, b, tol, rin, bt, gi, vec, total;
@@ -51,7 +53,7 @@ struct HqpSmem {
         tol = o; o += mc + 2;
         rin = o; o += mc + 2;   // 1 / scaled row norm
         bt = o; o += mc + 2;    // right-hand side of the current sub-problem
-        gi = o; o += 6 * QP_NV_MAX + 8;  // GiScratch
+        gi = o; o += GI_SCRATCH_DOUBLES;  // GiScratch
         vec = o; o += 6 * (n + 2) + 2;  // + status / iteration words of the QP just solved
         total = o;
     }
@@ -84,49 +86,123 @@ struct QpView {
         if (i < mt) return i < m ? U[i + (col0 + j) * ldm] : -U[i - m + (col0 + j) * ldm];
         return -AU[i - mt + (col0 + j) * ldc];
     }
+    // row i as (pointer to its first window entry, column stride, sign)
+    __device__ __forceinline__ void row(int i, const double *&p, int &ld, double &sgn) const {
+        if (i < mt) {
+            p = U + (i < m ? i : i - m) + col0 * ldm;
+            ld = ldm;
+            sgn = i < m ? 1.0 : -1.0;
+        } else {
+            p = AU + (i - mt) + col0 * ldc;
+            ld = ldc;
+            sgn = -1.0;
+        }
+    }
+    // sum_j a(i, j) x[j], four independent partial sums
+    __device__ __forceinline__ double dot(int i, const double *x) const {
+        const double *p;
+        int ld;
+        double sgn;
+        row(i, p, ld, sgn);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int j = 0;
+        for (; j + 3 < nv; j += 4) {
+            s0 = fma(p[j * ld], x[j], s0);
+            s1 = fma(p[(j + 1) * ld], x[j + 1], s1);
+            s2 = fma(p[(j + 2) * ld], x[j + 2], s2);
+            s3 = fma(p[(j + 3) * ld], x[j + 3], s3);
+        }
+        for (; j < nv; j++) s0 = fma(p[j * ld], x[j], s0);
+        return sgn * ((s0 + s1) + (s2 + s3));
+    }
 };
 
-// per-warp scratch of the active-set solver (shared memory)
+constexpr int GI_WARPS_MAX = 8;  // TEAM <= 256
+
+// per-state scratch of the active-set solver (shared memory); every array has QP_NV_MAX entries unless noted
 struct GiScratch {
-    double *np, *dv, *hv, *dxs, *isds, *xs;  // QP_NV_MAX doubles each
-    uint32_t *pinw;                           // ACTIVE_WORDS words
-    double *bt;                               // rows doubles
+    double *y, *u, *dxs, *dv, *zv, *rkv, *isds, *xs, *xp, *xj;
+    double *gcs;   // 2 * QP_NV_MAX: Givens (cos, sin) of a drop step
+    double *scal;  // 8
+    double *red;   // GI_WARPS_MAX
+    int *act, *slot;  // QP_NV_MAX each
+    int *ired;        // 2 * GI_WARPS_MAX
+    uint32_t *pinw, *amask;  // ACTIVE_WORDS each
+    double *bt;              // rows doubles
+    static constexpr int DOUBLES = 10 * QP_NV_MAX + 2 * QP_NV_MAX + 8 + GI_WARPS_MAX + (2 * QP_NV_MAX + 2 * GI_WARPS_MAX + 2 * ACTIVE_WORDS + 1) / 2;
     __device__ __forceinline__ GiScratch(double *base, double *bt_) {
-        np = base; dv = base + QP_NV_MAX; hv = base + 2 * QP_NV_MAX; dxs = base + 3 * QP_NV_MAX; isds = base + 4 * QP_NV_MAX;
-        xs = base + 5 * QP_NV_MAX;
-        pinw = (uint32_t *)(base + 6 * QP_NV_MAX);
+        y = base; u = y + QP_NV_MAX; dxs = u + QP_NV_MAX; dv = dxs + QP_NV_MAX; zv = dv + QP_NV_MAX; rkv = zv + QP_NV_MAX;
+        isds = rkv + QP_NV_MAX; xs = isds + QP_NV_MAX; xp = xs + QP_NV_MAX; xj = xp + QP_NV_MAX;
+        gcs = xj + QP_NV_MAX; scal = gcs + 2 * QP_NV_MAX; red = scal + 8;
+        act = (int *)(red + GI_WARPS_MAX); slot = act + QP_NV_MAX; ired = slot + QP_NV_MAX;
+        pinw = (uint32_t *)(ired + 2 * GI_WARPS_MAX); amask = pinw + ACTIVE_WORDS;
         bt = bt_;
     }
 };
 
+static_assert(GiScratch::DOUBLES <= GI_SCRATCH_DOUBLES, "GiScratch arena");
+static_assert(TEAM / 32 <= GI_WARPS_MAX && TEAM % 32 == 0, "team size");
+
 struct GiResult {
     int status;  // 1 solved, 0 infeasible / iteration limit
     int iters;
+    int q;       // size of the final active set (S.act / S.u hold its rows and multipliers)
 };
 
 __device__ __forceinline__ bool bit_test(const uint32_t *w, int i) { return (w[i >> 5] >> (i & 31)) & 1u; }
 
-// Goldfarb-Idnani on  min 1/2|y|^2  s.t.  sum_j a(i,j) dx_j <= bt_i,  dx_j = isd_j y_j  (dx = x - x0).
-// Lane j returns dx_j.  `pin` (may be null): rows to be pinned as equalities, added first and never dropped.
-// On return act_out / u_out hold, for logical position = lane, the active row (-1 if none) and its multiplier.
-// Deliberately NOT inlined: the solver is called from several places of solve_level, itself called per level and for the
-// redistribution QP; inlined, the kernel grew to 54k SASS instructions and the working warps spent 59 % of their
-// non-barrier stall samples waiting for instruction fetch (ncu, profiles/r01_*).
-__device__ __noinline__ GiResult gi_solve(const QpView &V, const double *bt, const double *tolv, double *rin, double isd, double *Q,
-                                             double *R, int ldq, const GiScratch &S, const uint32_t *pin, double &dx_out, int &act_out,
-                                             double &u_out, int max_iter) {
-    const int lane = lane_id();
+// ---- team reductions through shared memory (every thread gets the result; two barriers each) ----
+__device__ __forceinline__ double team_max(double v, const GiScratch &S) {
+    v = warp_max(v);
+    if (lane_id() == 0) S.red[t_id() >> 5] = v;
+    tsync();
+    double r = S.red[0];
+    for (int w = 1; w < (t_n() >> 5); w++) r = S.red[w] > r ? S.red[w] : r;
+    tsync();
+    return r;
+}
+__device__ __forceinline__ double team_sum(double v, const GiScratch &S) {
+    v = warp_sum(v);
+    if (lane_id() == 0) S.red[t_id() >> 5] = v;
+    tsync();
+    double r = 0.0;
+    for (int w = 0; w < (t_n() >> 5); w++) r += S.red[w];
+    tsync();
+    return r;
+}
+
+// Goldfarb-Idnani on  min 1/2|y|^2  s.t.  sum_j a(i,j) dx_j <= bt_i,  dx_j = isd_j y_j  (dx = x - x0), executed by the WHOLE
+// team: the row scan takes one row per thread, the products with Q four threads per output, the rank-one update of Q the
+// whole team; only the back substitution with R (a dependent chain of q steps) runs on warp 0.  All control decisions are
+// taken from values in shared memory after a barrier, so every thread follows the same path.
+// isd_j = isd_t for j < tsplit, isd_c otherwise.  `pin` (may be null): rows to be pinned as equalities, added first and never
+// dropped.  On return S.dxs holds dx, S.act / S.u the active rows and their multipliers (logical positions < q).
+// Deliberately NOT inlined (instruction-cache footprint, profiles/r01_ncu_summary.md).  Synchronises on entry and exit.
+__device__ __noinline__ GiResult gi_solve(const QpView &V, const double *bt, const double *tolv, double *rin, double isd_t, double isd_c,
+                                          int tsplit, double *Q, double *R, int ldq, const GiScratch &S, const uint32_t *pin, int max_iter) {
+    const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
     const int nv = V.nv, mc = V.rows();
-    double *np = S.np, *dv = S.dv, *hv = S.hv, *dxs = S.dxs, *isds = S.isds;
-    if (lane < nv) isds[lane] = isd;
-    for (int e = lane; e < ldq * nv; e += 32) Q[e] = 0.0;
-    __syncwarp();
-    if (lane < nv) Q[lane + lane * ldq] = 1.0;
+    double *y = S.y, *u = S.u, *dxs = S.dxs, *dv = S.dv, *zv = S.zv, *rkv = S.rkv, *isds = S.isds, *gcs = S.gcs, *scal = S.scal;
+    int *act = S.act, *slot = S.slot, *ired = S.ired;
+    uint32_t *amask = S.amask;
+    tsync();
+    for (int e = tid; e < ldq * nv; e += nt) Q[e] = 0.0;
+    if (tid < nv) {
+        isds[tid] = tid < tsplit ? isd_t : isd_c;
+        y[tid] = 0.0;
+        dxs[tid] = 0.0;
+        u[tid] = 0.0;
+        act[tid] = -1;
+        slot[tid] = -1;
+    }
+    if (tid < ACTIVE_WORDS) amask[tid] = 0u;
+    tsync();
+    if (tid < nv) Q[tid + tid * ldq] = 1.0;
     // 1 / (scaled row norm): violations are compared as distances in y-space.  Rows whose norm is below 1e-10 of the
     // largest row norm are numerically zero (what rounding leaves of a constraint already active at a higher level) and
     // never enter the active set (rin = 0); the oracle applies the same rule.
     double smax = 0.0;
-    for (int i = lane; i < mc; i += 32) {
+    for (int i = tid; i < mc; i += nt) {
         double s = 0.0;
         for (int j = 0; j < nv; j++) {
             const double v = V.a(i, j) * isds[j];
@@ -135,19 +211,15 @@ __device__ __noinline__ GiResult gi_solve(const QpView &V, const double *bt, con
         rin[i] = s;
         smax = s > smax ? s : smax;
     }
-    smax = warp_max(smax);
-    for (int i = lane; i < mc; i += 32) {
+    smax = team_max(smax, S);
+    for (int i = tid; i < mc; i += nt) {
         const double s = rin[i];
         rin[i] = (s > 0.0 && s > 1e-20 * smax) ? 1.0 / sqrt(s) : 0.0;
     }
-    __syncwarp();
-    double y = 0.0;           // lane j: scaled variable j
-    int act = -1, slot = -1;  // lane k: row and physical R column of logical active position k
-    double u = 0.0;           // lane k: multiplier of logical position k
+    tsync();
     int q = 0, neq = 0;
-    uint32_t used = 0;                            // physical R columns in use (warp-uniform)
-    uint32_t amask[ACTIVE_WORDS] = {0, 0, 0, 0};  // active rows (warp-uniform)
-    GiResult res{0, 0};
+    uint32_t used = 0;  // physical R columns in use
+    GiResult res{0, 0, 0};
     int p = -1;  // row being added
     double sp = 0.0, sigma = 1.0, up = 0.0;
     int pin_scan = 0;
@@ -165,11 +237,9 @@ __device__ __noinline__ GiResult gi_solve(const QpView &V, const double *bt, con
                     }
                 }
             }
-            if (lane < nv) dxs[lane] = y * isd;
-            __syncwarp();
             if (found >= 0) {
                 double part = lane < nv ? V.a(found, lane) * dxs[lane] : 0.0;
-                part = warp_sum(part);
+                part = warp_sum(part);  // identical in every warp
                 const double sl = bt[found] - part;
                 p = found;
                 sigma = sl <= 0.0 ? 1.0 : -1.0;  // reach the equality from whichever side we are on
@@ -177,26 +247,21 @@ __device__ __noinline__ GiResult gi_solve(const QpView &V, const double *bt, con
             } else {
                 double best = 0.0;
                 int bi = -1;
-                if (V.mt > 0) {
-                    for (int i = lane; i < V.m; i += 32) {
-                        double s = 0.0;
-                        for (int j = 0; j < nv; j++) s = fma(V.U[i + (V.col0 + j) * V.ldm], dxs[j], s);
-                        const int i2 = i + V.m;
-                        const double s1 = bt[i] - s, s2 = bt[i2] + s;
-                        if (!bit_test(amask, i) && s1 < -tolv[i] && s1 * rin[i] < best) best = s1 * rin[i], bi = i;
-                        if (!bit_test(amask, i2) && s2 < -tolv[i2] && s2 * rin[i2] < best) best = s2 * rin[i2], bi = i2;
-                    }
-                }
-                for (int i = lane; i < V.nc; i += 32) {
-                    double s = 0.0;
-                    for (int j = 0; j < nv; j++) s = fma(V.AU[i + (V.col0 + j) * V.ldc], dxs[j], s);
-                    const int row = V.mt + i;
-                    const double s1 = bt[row] + s;
-                    if (!bit_test(amask, row) && s1 < -tolv[row] && s1 * rin[row] < best) best = s1 * rin[row], bi = row;
+                for (int i = tid; i < mc; i += nt) {
+                    const double s1 = bt[i] - V.dot(i, dxs);
+                    if (!bit_test(amask, i) && s1 < -tolv[i] && s1 * rin[i] < best) best = s1 * rin[i], bi = i;
                 }
                 for (int o = 16; o > 0; o >>= 1) {
                     const double ob = __shfl_xor_sync(DWBC_FULL, best, o);
                     const int oi = __shfl_xor_sync(DWBC_FULL, bi, o);
+                    if (oi >= 0 && (bi < 0 || ob < best || (ob == best && oi < bi))) best = ob, bi = oi;
+                }
+                if (lane == 0) S.red[warp] = best, ired[warp] = bi;
+                tsync();
+                best = S.red[0], bi = ired[0];
+                for (int w = 1; w < nw; w++) {
+                    const double ob = S.red[w];
+                    const int oi = ired[w];
                     if (oi >= 0 && (bi < 0 || ob < best || (ob == best && oi < bi))) best = ob, bi = oi;
                 }
                 if (bi < 0) {
@@ -209,38 +274,67 @@ __device__ __noinline__ GiResult gi_solve(const QpView &V, const double *bt, con
             }
             up = 0.0;
         }
-        // ---- step direction: n+ = -sigma a~_p, d = Q^T n+, z = Q_2 d_2, r = R^{-1} d_1 ----
-        __syncwarp();
-        if (lane < nv) np[lane] = -sigma * V.a(p, lane) * isd;
-        __syncwarp();
-        double dk = 0.0;
-        if (lane < nv) {
-            for (int j = 0; j < nv; j++) dk = fma(Q[j + lane * ldq], np[j], dk);
-            dv[lane] = dk;
+        // ---- step direction: n+ = -sigma a~_p, d = Q^T n+ (four threads per entry) ----
+        {
+            const double *rp;
+            int rld;
+            double rs;
+            V.row(p, rp, rld, rs);
+            rs *= -sigma;
+            const int part = tid & 3;
+            for (int k0 = 0; k0 < nv; k0 += nt >> 2) {
+                const int k = k0 + (tid >> 2);
+                double a0 = 0.0;
+                if (k < nv)
+                    for (int j = part; j < nv; j += 4) a0 = fma(Q[j + k * ldq], rp[j * rld] * isds[j], a0);
+                a0 += __shfl_xor_sync(DWBC_FULL, a0, 1);
+                a0 += __shfl_xor_sync(DWBC_FULL, a0, 2);
+                if (k < nv && part == 0) dv[k] = rs * a0;
+            }
         }
-        __syncwarp();
-        double z = 0.0;
-        if (lane < nv)
-            for (int k = q; k < nv; k++) z = fma(Q[lane + k * ldq], dv[k], z);
-        const double zz = warp_sum((lane >= q && lane < nv) ? dk * dk : 0.0);
-        const double nn = warp_sum(lane < nv ? dk * dk : 0.0);
-        double rk = (lane < q) ? dk : 0.0;
-        for (int k = q - 1; k >= 0; k--) {
-            const int sk = __shfl_sync(DWBC_FULL, slot, k);
-            const double val = __shfl_sync(DWBC_FULL, rk, k) / R[k + sk * ldq];
-            if (lane == k) rk = val;
-            if (lane < k) rk = fma(-R[lane + sk * ldq], val, rk);
+        tsync();
+        // ---- z = Q_2 d_2 (four threads per entry); r = R^{-1} d_1 and the dual step bound on warp 0 ----
+        const double dk = lane < nv ? dv[lane] : 0.0;
+        const double zz = warp_sum((lane >= q && lane < nv) ? dk * dk : 0.0);  // identical in every warp
+        const double nn = warp_sum(dk * dk);
+        {
+            const int part = tid & 3;
+            for (int j0 = 0; j0 < nv; j0 += nt >> 2) {
+                const int j = j0 + (tid >> 2);
+                double a0 = 0.0;
+                if (j < nv)
+                    for (int k = q + part; k < nv; k += 4) a0 = fma(Q[j + k * ldq], dv[k], a0);
+                a0 += __shfl_xor_sync(DWBC_FULL, a0, 1);
+                a0 += __shfl_xor_sync(DWBC_FULL, a0, 2);
+                if (j < nv && part == 0) zv[j] = a0;
+            }
         }
+        if (warp == 0) {
+            const int myslot = lane < q ? slot[lane] : 0;
+            const double invd = lane < q ? 1.0 / R[lane + myslot * ldq] : 0.0;
+            double rk = (lane < q) ? dk : 0.0;
+            for (int k = q - 1; k >= 0; k--) {
+                const int sk = __shfl_sync(DWBC_FULL, myslot, k);
+                const double val = __shfl_sync(DWBC_FULL, rk, k) * __shfl_sync(DWBC_FULL, invd, k);
+                if (lane == k) rk = val;
+                if (lane < k) rk = fma(-R[lane + sk * ldq], val, rk);
+            }
+            // largest dual step that keeps the multipliers of the droppable active rows non-negative
+            double t1 = 1e300;
+            int l1 = -1;
+            if (lane >= neq && lane < q && rk > 0.0) t1 = u[lane] / rk, l1 = lane;
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ot = __shfl_xor_sync(DWBC_FULL, t1, o);
+                const int ol = __shfl_xor_sync(DWBC_FULL, l1, o);
+                if (ol >= 0 && (l1 < 0 || ot < t1 || (ot == t1 && ol < l1))) t1 = ot, l1 = ol;
+            }
+            if (lane < q) rkv[lane] = rk;
+            if (lane == 0) scal[0] = t1, ired[GI_WARPS_MAX] = l1;
+        }
+        tsync();
+        const double t1 = scal[0];
+        const int l1 = ired[GI_WARPS_MAX];
         const bool dependent = (q >= nv) || !(zz > 1e-22 * nn);
-        // largest dual step that keeps the multipliers of the droppable active rows non-negative
-        double t1 = 1e300;
-        int l1 = -1;
-        if (lane >= neq && lane < q && rk > 0.0) t1 = u / rk, l1 = lane;
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ot = __shfl_xor_sync(DWBC_FULL, t1, o);
-            const int ol = __shfl_xor_sync(DWBC_FULL, l1, o);
-            if (ol >= 0 && (l1 < 0 || ot < t1 || (ot == t1 && ol < l1))) t1 = ot, l1 = ol;
-        }
         if (dependent && l1 < 0) {
             // no primal and no dual step possible
             const bool is_pin = pin && bit_test(pin, p);
@@ -248,6 +342,7 @@ __device__ __noinline__ GiResult gi_solve(const QpView &V, const double *bt, con
                 // a pinned row that depends on the rows pinned so far (consistent by construction), or a row
                 // that is violated by less than its tolerance: nothing to do for it
                 p = -1;
+                tsync();
                 continue;
             }
             res.status = 0;  // infeasible
@@ -255,84 +350,99 @@ __device__ __noinline__ GiResult gi_solve(const QpView &V, const double *bt, con
         }
         const double t2 = dependent ? 1e300 : -sp / zz;
         const double t = t1 < t2 ? t1 : t2;
-        if (lane < q) u = fma(-t, rk, u);
+        if (tid < q) u[tid] = fma(-t, rkv[tid], u[tid]);
         up += t;
-        if (!dependent) y = fma(t, z, y);
+        if (!dependent && tid < nv) {
+            const double yn = fma(t, zv[tid], y[tid]);
+            y[tid] = yn;
+            dxs[tid] = yn * isds[tid];
+        }
         if (!dependent && t2 <= t1) {
-            // ---- full step: row p becomes active.  One Householder reflection on Q_2 maps d_2 to alpha e_q ----
+            // ---- full step: row p becomes active.  One Householder reflection on Q_2 maps d_2 to alpha e_q:
+            // h = d_2 - alpha e_q,  Q_2 <- Q_2 - w h^T,  w = tau Q_2 h = tau (z - alpha Q[:, q]) ----
             const double dq = dv[q];
             const double alpha = dq > 0.0 ? -sqrt(zz) : sqrt(zz);
-            if (lane >= q && lane < nv) hv[lane] = (lane == q) ? dk - alpha : dk;
-            __syncwarp();
             const double tau = 1.0 / (zz - alpha * dq);
-            if (lane < nv) {
-                double wj = 0.0;
-                for (int k = q; k < nv; k++) wj = fma(Q[lane + k * ldq], hv[k], wj);
-                wj *= tau;
-                for (int k = q; k < nv; k++) Q[lane + k * ldq] = fma(-wj, hv[k], Q[lane + k * ldq]);
+            const int part = tid & 3;
+            for (int j0 = 0; j0 < nv; j0 += nt >> 2) {
+                const int j = j0 + (tid >> 2);
+                const double wj = j < nv ? tau * (zv[j] - alpha * Q[j + q * ldq]) : 0.0;
+                __syncwarp();  // the four threads of row j have read Q[j, q] before it is overwritten
+                if (j < nv)
+                    for (int k = q + part; k < nv; k += 4) {
+                        const double hk = k == q ? dq - alpha : dv[k];
+                        Q[j + k * ldq] = fma(-wj, hk, Q[j + k * ldq]);
+                    }
             }
             const int ns = __ffs((int)~used) - 1;
             used |= 1u << ns;
-            if (lane < q) R[lane + ns * ldq] = dk;
-            if (lane == q) {
+            if (tid < q) R[tid + ns * ldq] = dv[tid];
+            if (tid == q) {
                 R[q + ns * ldq] = alpha;
-                act = p;
-                u = up;
-                slot = ns;
+                act[q] = p;
+                u[q] = up;
+                slot[q] = ns;
             }
-            amask[p >> 5] |= 1u << (p & 31);
+            if (tid == 0) amask[p >> 5] |= 1u << (p & 31);
             if (pin && bit_test(pin, p)) neq = q + 1;
             q++;
             p = -1;
-            __syncwarp();
+            tsync();
         } else {
             // ---- partial (or purely dual) step: the blocking row at logical position l1 leaves the active set ----
             const int l = l1;
-            const int dropped = __shfl_sync(DWBC_FULL, act, l);
-            const int dslot = __shfl_sync(DWBC_FULL, slot, l);
-            for (int k = l; k + 1 < q; k++) {
-                // Givens rotation of rows k, k+1 of R: the column moving into position k becomes upper triangular
-                const int sk1 = __shfl_sync(DWBC_FULL, slot, k + 1);
-                const double a = R[k + sk1 * ldq], bb = R[k + 1 + sk1 * ldq];
-                const double h = sqrt(a * a + bb * bb);
-                const double cs = h > 0.0 ? a / h : 1.0, sn = h > 0.0 ? bb / h : 0.0;
-                __syncwarp();
-                if (lane > k && lane < q) {
-                    double *col = R + slot * ldq;
-                    const double r0 = col[k], r1 = col[k + 1];
-                    col[k] = cs * r0 + sn * r1;
-                    col[k + 1] = -sn * r0 + cs * r1;
+            const int dropped = act[l];
+            const int dslot = slot[l];
+            if (warp == 0) {
+                // Givens rotations of rows k, k+1 of R: lane j owns logical column j (only it touches that column)
+                double *col = R + (lane < q ? slot[lane] : 0) * ldq;
+                for (int k = l; k + 1 < q; k++) {
+                    double a = 0.0, bb = 0.0;
+                    if (lane == k + 1) a = col[k], bb = col[k + 1];
+                    a = __shfl_sync(DWBC_FULL, a, k + 1);
+                    bb = __shfl_sync(DWBC_FULL, bb, k + 1);
+                    const double h = sqrt(a * a + bb * bb);
+                    const double cs = h > 0.0 ? a / h : 1.0, sn = h > 0.0 ? bb / h : 0.0;
+                    if (lane > k && lane < q) {
+                        const double r0 = col[k], r1 = col[k + 1];
+                        col[k] = cs * r0 + sn * r1;
+                        col[k + 1] = -sn * r0 + cs * r1;
+                    }
+                    if (lane == 0) gcs[2 * k] = cs, gcs[2 * k + 1] = sn;
                 }
-                if (lane < nv) {
-                    const double q0 = Q[lane + k * ldq], q1 = Q[lane + (k + 1) * ldq];
-                    Q[lane + k * ldq] = cs * q0 + sn * q1;
-                    Q[lane + (k + 1) * ldq] = -sn * q0 + cs * q1;
-                }
-                __syncwarp();
             }
-            {
-                const int a2 = __shfl_down_sync(DWBC_FULL, act, 1);
-                const int s2 = __shfl_down_sync(DWBC_FULL, slot, 1);
-                const double u2 = __shfl_down_sync(DWBC_FULL, u, 1);
-                if (lane >= l && lane < q - 1) act = a2, slot = s2, u = u2;
-                if (lane == q - 1) act = -1, slot = -1, u = 0.0;
+            tsync();  // every thread has read act[l] / slot[l]; the rotations are published
+            if (tid < nv) {
+                double q0 = Q[tid + l * ldq];
+                for (int k = l; k + 1 < q; k++) {
+                    const double cs = gcs[2 * k], sn = gcs[2 * k + 1];
+                    const double q1 = Q[tid + (k + 1) * ldq];
+                    Q[tid + k * ldq] = cs * q0 + sn * q1;
+                    q0 = -sn * q0 + cs * q1;
+                }
+                if (l + 1 < q) Q[tid + (q - 1) * ldq] = q0;
+            }
+            if (warp == 0) {
+                const int a2 = lane + 1 < QP_NV_MAX ? act[lane + 1] : -1;
+                const int s2 = lane + 1 < QP_NV_MAX ? slot[lane + 1] : -1;
+                const double u2 = lane + 1 < QP_NV_MAX ? u[lane + 1] : 0.0;
+                __syncwarp();
+                if (lane >= l && lane < q - 1) act[lane] = a2, slot[lane] = s2, u[lane] = u2;
+                if (lane == q - 1) act[lane] = -1, slot[lane] = -1, u[lane] = 0.0;
             }
             used &= ~(1u << dslot);
-            amask[dropped >> 5] &= ~(1u << (dropped & 31));
+            if (tid == 0) amask[dropped >> 5] &= ~(1u << (dropped & 31));
             q--;
             // slack of row p at the new point
-            if (lane < nv) dxs[lane] = y * isd;
-            __syncwarp();
             double part = lane < nv ? V.a(p, lane) * dxs[lane] : 0.0;
             part = warp_sum(part);
             sp = sigma * (bt[p] - part);
             if (sp > 0.0) sp = 0.0;
+            tsync();
         }
     }
-    dx_out = lane < nv ? y * isd : 0.0;
-    act_out = lane < q ? act : -1;
-    u_out = lane < q ? u : 0.0;
-    __syncwarp();
+    res.q = q;
+    tsync();
     return res;
 }
 
@@ -341,19 +451,23 @@ struct LevelOut {
     int iters;
 };
 
-// Solves one QP (t task variables first, then r contact variables).  U (m x nv), AU (nc x nv) and b (rows) are in
-// shared memory; lane j returns x_j.  active_out (global, ACTIVE_WORDS words): rows with zero slack at the solution.
+// Solves one QP (t task variables first, then r contact variables) with the whole team.  U (m x nv), AU (nc x nv) and b (rows)
+// are in shared memory; the solution is left in S.xj.  active_out (global, ACTIVE_WORDS words): rows with zero slack at the
+// solution.  Synchronises on entry and exit.
 __device__ __noinline__ LevelOut solve_level(int t, int r, int m, int mt, int nc, const double *U, const double *AU, int ldm, int ldc,
-                                                const double *b, double *tolv, double *rin, double *Q, double *R, int ldq,
-                                                const GiScratch &S, double &x_out, uint32_t *active_out) {
-    const int lane = lane_id();
+                                             const double *b, double *tolv, double *rin, double *Q, double *R, int ldq, const GiScratch &S,
+                                             uint32_t *active_out) {
+    const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
     const int nv = t + r, mc = mt + nc;
     LevelOut out{1, 0};
     QpView V{U, AU, ldm, ldc, m, mt, nc, 0, nv};
+    double *xj = S.xj, *xs = S.xs, *xp = S.xp;
+    tsync();
+    if (tid < QP_NV_MAX) xj[tid] = 0.0;
     // row tolerances in the units of the rows, the quick exit, and the active rows of the quick exit.  Numerically zero
     // rows (norm <= 1e-10 of the largest) cannot be influenced by x: they only decide feasibility (b >= -1e-9).
     double smax = 0.0;
-    for (int i = lane; i < mc; i += 32) {
+    for (int i = tid; i < mc; i += nt) {
         double s = 0.0;
         for (int j = 0; j < nv; j++) {
             const double v = V.a(i, j);
@@ -362,11 +476,11 @@ __device__ __noinline__ LevelOut solve_level(int t, int r, int m, int mt, int nc
         rin[i] = s;
         smax = s > smax ? s : smax;
     }
-    smax = warp_max(smax);
+    smax = team_max(smax, S);
     double bmin = 1e300;
     bool infeasible = false;
-    for (int i0 = 0; i0 < mc; i0 += 32) {
-        const int i = i0 + lane;
+    for (int i0 = 0; i0 < mc; i0 += nt) {
+        const int i = i0 + tid;
         bool on = false;
         if (i < mc) {
             const double s = rin[i];
@@ -379,89 +493,94 @@ __device__ __noinline__ LevelOut solve_level(int t, int r, int m, int mt, int nc
             on = s > 0.0 && b[i] < 1e-9 * (1.0 + fabs(b[i]));
         }
         const unsigned bal = __ballot_sync(DWBC_FULL, on);
-        if (lane == 0) S.pinw[i0 >> 5] = bal;
-    }
-    if (__any_sync(DWBC_FULL, infeasible)) {
-        out.status = 0;
-        x_out = 0.0;
-        __syncwarp();
-        return out;
+        const int word = (i0 >> 5) + warp;
+        if (lane == 0 && word < ACTIVE_WORDS) S.pinw[word] = bal;
     }
     bmin = warp_min(bmin);
-    __syncwarp();
-    double xj = 0.0;
+    const bool winf = __any_sync(DWBC_FULL, infeasible);
+    if (lane == 0) S.red[warp] = bmin, S.ired[warp] = winf ? 1 : 0;
+    tsync();
+    bool any_inf = false;
+    bmin = 1e300;
+    for (int w = 0; w < nw; w++) {
+        bmin = fmin(bmin, S.red[w]);
+        any_inf = any_inf || S.ired[w];
+    }
+    tsync();
+    if (any_inf) {
+        out.status = 0;
+        return out;
+    }
     if (bmin >= 0.0) {
         // x = 0 satisfies every row: optimal for both stages, no factorisation needed
-        if (active_out && lane < ACTIVE_WORDS) active_out[lane] = lane < (mc + 31) / 32 ? S.pinw[lane] : 0u;
-        x_out = 0.0;
-        __syncwarp();
+        if (active_out && tid < ACTIVE_WORDS) active_out[tid] = tid < (mc + 31) / 32 ? S.pinw[tid] : 0u;
         return out;
     }
     const int max_iter = 20 * (nv + 8);
-    int act = -1;
-    double u = 0.0, dx = 0.0;
     bool done = false;
     if (t == 0 || r == 0) {
-        GiResult g = gi_solve(V, b, tolv, rin, 1.0, Q, R, ldq, S, nullptr, dx, act, u, max_iter);
+        GiResult g = gi_solve(V, b, tolv, rin, 1.0, 1.0, nv, Q, R, ldq, S, nullptr, max_iter);
         out.iters += g.iters;
         out.status = g.status;
-        xj = dx;
+        if (tid < nv) xj[tid] = S.dxs[tid];
         done = true;
     }
     if (!done) {
         // ---- A: is x_t = 0 attainable?  (looser tolerances: the set may be a thin face inherited from the levels above)
-        for (int i = lane; i < mc; i += 32) tolv[i] *= 100.0;
-        __syncwarp();
+        for (int i = tid; i < mc; i += nt) tolv[i] *= 100.0;
         QpView Vc = V;
         Vc.col0 = t;
         Vc.nv = r;
-        GiResult g = gi_solve(Vc, b, tolv, rin, 1.0, Q, R, ldq, S, nullptr, dx, act, u, max_iter);
+        GiResult g = gi_solve(Vc, b, tolv, rin, 1.0, 1.0, r, Q, R, ldq, S, nullptr, max_iter);
         out.iters += g.iters;
         if (g.status) {
-            const double v = __shfl_sync(DWBC_FULL, dx, lane >= t ? lane - t : 0);
-            xj = (lane >= t && lane < nv) ? v : 0.0;
+            if (tid < r) xj[t + tid] = S.dxs[tid];
             done = true;
         }
-        for (int i = lane; i < mc; i += 32) tolv[i] *= 0.01;
-        __syncwarp();
+        for (int i = tid; i < mc; i += nt) tolv[i] *= 0.01;
+        tsync();
     }
     if (!done) {
         // ---- B: proximal point on 1/2|x_t|^2 + delta/2 |x_c - c|^2 ----
-        double nt = 0.0, ncn = 0.0;
-        for (int i = lane; i < mc; i += 32)
+        double ntn = 0.0, ncn = 0.0;
+        for (int i = tid; i < mc; i += nt)
             for (int j = 0; j < nv; j++) {
                 const double v = V.a(i, j);
-                if (j < t) nt = fma(v, v, nt);
+                if (j < t) ntn = fma(v, v, ntn);
                 else ncn = fma(v, v, ncn);
             }
-        nt = warp_sum(nt);
-        ncn = warp_sum(ncn);
-        const double delta = 1e-5 * (ncn / r) / fmax(nt / t, 1e-300);
-        const double isd = lane < t ? 1.0 : rsqrt(delta);
-        double *bt = S.bt, *xs = S.xs;
-        double x0 = 0.0, xprev = 0.0;
+        ntn = team_sum(ntn, S);
+        ncn = team_sum(ncn, S);
+        const double delta = 1e-5 * (ncn / r) / fmax(ntn / t, 1e-300);
+        const double isd_c = rsqrt(delta);
+        double *bt = S.bt;
+        if (tid < nv) xs[tid] = 0.0, xp[tid] = 0.0;  // xs: prox centre (zero on the task columns), xp: previous iterate
+        tsync();
         bool conv = false;
+        GiResult g{0, 0, 0};
         for (int k = 0; k < 30; k++) {
-            if (lane < nv) xs[lane] = x0;
-            __syncwarp();
-            for (int i = lane; i < mc; i += 32) {  // bt = b - A x0 (x0 is zero on the task columns)
+            for (int i = tid; i < mc; i += nt) {  // bt = b - A x0 (x0 is zero on the task columns)
                 double s = b[i];
                 for (int j = t; j < nv; j++) s = fma(-V.a(i, j), xs[j], s);
                 bt[i] = s;
             }
-            __syncwarp();
-            GiResult g = gi_solve(V, bt, tolv, rin, isd, Q, R, ldq, S, nullptr, dx, act, u, max_iter);
+            g = gi_solve(V, bt, tolv, rin, 1.0, isd_c, t, Q, R, ldq, S, nullptr, max_iter);
             out.iters += g.iters;
             if (!g.status) {
                 out.status = 0;
                 break;
             }
-            const double xn = x0 + dx;
-            const double dd = warp_sum(lane < t ? (xn - xprev) * (xn - xprev) : 0.0);
+            const double xn = lane < nv ? xs[lane] + S.dxs[lane] : 0.0;
+            const double xo = lane < nv ? xp[lane] : 0.0;
+            const double dd = warp_sum(lane < t ? (xn - xo) * (xn - xo) : 0.0);  // identical in every warp
             const double xx = warp_sum(lane < t ? xn * xn : 0.0);
-            xprev = xn;
-            xj = xn;
-            x0 = (lane >= t && lane < nv) ? xn : 0.0;
+            tsync();
+            if (tid < nv) {
+                xp[tid] = xn;
+                xj[tid] = xn;
+                xs[tid] = tid >= t ? xn : 0.0;
+            }
+            tsync();
             if (k > 0 && sqrt(dd) <= 1e-12 * (1.0 + sqrt(xx))) {
                 conv = true;
                 break;
@@ -470,62 +589,57 @@ __device__ __noinline__ LevelOut solve_level(int t, int r, int m, int mt, int nc
         if (out.status && !conv) out.status = 0;
         if (out.status) {
             // ---- C: min |x_c|^2 on the optimal face; rows with a positive multiplier are pinned ----
-            const double umax = warp_max(u);
-            if (lane < ACTIVE_WORDS) S.pinw[lane] = 0u;
-            __syncwarp();
-            const int mine = (act >= 0 && u > 1e-9 * umax) ? act : -1;
-            for (int k = 0; k < nv; k++) {
-                const int ak = __shfl_sync(DWBC_FULL, mine, k);
-                if (ak >= 0 && lane == 0) S.pinw[ak >> 5] |= 1u << (ak & 31);
-            }
-            if (lane < nv) xs[lane] = xj;
-            __syncwarp();
-            for (int i = lane; i < mc; i += 32) {
+            const double umax = warp_max(lane < g.q ? S.u[lane] : 0.0);  // identical in every warp
+            if (tid < ACTIVE_WORDS) S.pinw[tid] = 0u;
+            tsync();
+            if (tid == 0)
+                for (int k = 0; k < g.q; k++) {
+                    const int ak = S.act[k];
+                    if (ak >= 0 && S.u[k] > 1e-9 * umax) S.pinw[ak >> 5] |= 1u << (ak & 31);
+                }
+            for (int i = tid; i < mc; i += nt) {
                 double s = b[i];
-                for (int j = 0; j < t; j++) s = fma(-V.a(i, j), xs[j], s);
+                for (int j = 0; j < t; j++) s = fma(-V.a(i, j), xj[j], s);
                 bt[i] = s;
                 tolv[i] *= 100.0;
             }
-            __syncwarp();
             QpView Vc = V;
             Vc.col0 = t;
             Vc.nv = r;
-            GiResult g = gi_solve(Vc, bt, tolv, rin, 1.0, Q, R, ldq, S, S.pinw, dx, act, u, max_iter);
-            out.iters += g.iters;
-            if (!g.status) out.status = 0;
-            const double v = __shfl_sync(DWBC_FULL, dx, lane >= t ? lane - t : 0);
-            if (lane >= t && lane < nv) xj = v;
+            GiResult gc = gi_solve(Vc, bt, tolv, rin, 1.0, 1.0, r, Q, R, ldq, S, S.pinw, max_iter);
+            out.iters += gc.iters;
+            if (!gc.status) out.status = 0;
+            if (tid < r) xj[t + tid] = S.dxs[tid];
         }
     }
-    if (!out.status) xj = 0.0;
+    tsync();
+    if (!out.status && tid < QP_NV_MAX) xj[tid] = 0.0;
+    tsync();
     // active rows at the solution: slack within 1e-9 (1 + |b|), rows with a zero normal excluded (the oracle's rule)
-    if (lane < nv) S.xs[lane] = xj;
-    __syncwarp();
-    for (int i0 = 0; i0 < mc; i0 += 32) {
-        const int i = i0 + lane;
+    for (int i0 = 0; i0 < mc; i0 += nt) {
+        const int i = i0 + tid;
         bool on = false;
         if (i < mc && out.status) {
             double s = -b[i], nn2 = 0.0;
             for (int j = 0; j < nv; j++) {
                 const double a = V.a(i, j);
-                s = fma(a, S.xs[j], s);
+                s = fma(a, xj[j], s);
                 nn2 = fma(a, a, nn2);
             }
             on = nn2 > 0.0 && s > -1e-9 * (1.0 + fabs(b[i]));
         }
         const unsigned bal = __ballot_sync(DWBC_FULL, on);
-        if (lane == 0) S.pinw[i0 >> 5] = bal;
+        const int word = (i0 >> 5) + warp;
+        if (lane == 0 && word < ACTIVE_WORDS) S.pinw[word] = bal;
     }
-    __syncwarp();
-    if (active_out && lane < ACTIVE_WORDS) active_out[lane] = lane < (mc + 31) / 32 ? S.pinw[lane] : 0u;
-    x_out = xj;
-    __syncwarp();
+    tsync();
+    if (active_out && tid < ACTIVE_WORDS) active_out[tid] = tid < (mc + 31) / 32 ? S.pinw[tid] : 0u;
+    tsync();
     return out;
 }
 
-// One CTA (team) per state: QP assembly (U, Atemp U, right-hand sides) and the torque updates use every thread; the
-// active-set iterations of one QP are inherently narrow (one lane per variable) and run on warp 0 while the CTA's other
-// warps wait at the barrier -- the SM's other resident CTAs fill the issue slots meanwhile.
+// One CTA (team) per state: QP assembly (U, Atemp U, right-hand sides), the active-set iterations (gi_solve) and the torque
+// updates all use every thread of the team.
 __global__ void __launch_bounds__(TEAM, 5) hqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int redist) {
     DWBC_DYN_SMEM(smem);
     const int tid = t_id(), nt = t_n(), warp = tid >> 5, lane = lane_id();
@@ -538,7 +652,6 @@ __global__ void __launch_bounds__(TEAM, 5) hqp_kernel(const DevModel *__restrict
     double *vec = sm + L.vec;
     const int vs = n + 2;
     double *tprev = vec, *base = vec + vs, *fs = vec + 2 * vs, *bA0 = vec + 3 * vs, *xs = vec + 4 * vs, *lf = vec + 5 * vs;
-    int *s_lo = (int *)(vec + 6 * vs);  // status, iterations of the QP just solved by warp 0
     const int ldm = L.ldm, ldc = L.ldc, ldq = L.ldq;
     int st = w.status[s];
     const bool contact_ok = st & 1;
@@ -609,27 +722,22 @@ __global__ void __launch_bounds__(TEAM, 5) hqp_kernel(const DevModel *__restrict
                 }
             tgemv<false>(nc, m, At, ldc, base, [&](int i, double v) { b[mt + i] = -(bA0[i] - v); });
             tsync();
-            if (warp == 0) {
-                double xj;
-                LevelOut lo = solve_level(t, r, m, mt, nc, U, AU, ldm, ldc, b, tolv, rin, Q, R, ldq, S, xj, w.active[l] + s * ACTIVE_WORDS);
-                if (lane == 0) s_lo[0] = lo.status, s_lo[1] = lo.iters;
-                if (lo.status) {
-                    if (lane < t) {
-                        w.fstar_qp[l][s * t + lane] = xj;
-                        fs[lane] += xj;
-                    }
-                    if (lane >= t && lane < nv) {
-                        w.contact_qp[l][s * RMAX + lane - t] = xj;
-                        xs[lane - t] = xj;
-                    }
-                }
-            }
-            tsync();
-            total_iters += s_lo[1];
-            if (!s_lo[0]) {
+            const LevelOut lo = solve_level(t, r, m, mt, nc, U, AU, ldm, ldc, b, tolv, rin, Q, R, ldq, S, w.active[l] + s * ACTIVE_WORDS);
+            total_iters += lo.iters;
+            if (!lo.status) {
                 all_ok = false;  // reference: f_star_qp_ = contact_qp_ = 0 and return 0 (src/dwbc.cpp:1117-1125, 836-837)
                 break;
             }
+            if (tid < t) {
+                const double xj = S.xj[tid];
+                w.fstar_qp[l][s * t + tid] = xj;
+                fs[tid] += xj;
+            } else if (tid < nv) {
+                const double xj = S.xj[tid];
+                w.contact_qp[l][s * RMAX + tid - t] = xj;
+                xs[tid - t] = xj;
+            }
+            tsync();
             // torque_task += Null_{l-1} J_kt Lambda (f* + f*_qp) = Ntorque (f* + x_t);  tau_prev = tau_grav + torque_task
             tgemv<false>(m, t, U, ldm, fs, [&](int i, double v) {
                 const double tt = tau_task[i] + v;
@@ -667,18 +775,15 @@ __global__ void __launch_bounds__(TEAM, 5) hqp_kernel(const DevModel *__restrict
                 }
             tgemv<false>(nc, m, At, ldc, base, [&](int i, double v) { b[mt + i] = -(bA0[i] - v); });
             tsync();
-            if (warp == 0) {
-                double xj;
-                LevelOut lo = solve_level(0, r, m, mt, nc, U, AU, ldm, ldc, b, tolv, rin, Q, R, ldq, S, xj, w.active[MAX_LEVELS] + s * ACTIVE_WORDS);
-                if (lane == 0) s_lo[0] = lo.status, s_lo[1] = lo.iters;
-                if (lo.status && lane < r) {
-                    w.cf_redis[s * RMAX + lane] = xj;
-                    xs[lane] = xj;
+            const LevelOut lo = solve_level(0, r, m, mt, nc, U, AU, ldm, ldc, b, tolv, rin, Q, R, ldq, S, w.active[MAX_LEVELS] + s * ACTIVE_WORDS);
+            total_iters += lo.iters;
+            if (lo.status) {
+                if (tid < r) {
+                    const double xj = S.xj[tid];
+                    w.cf_redis[s * RMAX + tid] = xj;
+                    xs[tid] = xj;
                 }
-            }
-            tsync();
-            total_iters += s_lo[1];
-            if (s_lo[0]) {
+                tsync();
                 tgemv<false>(m, r, NwJw, m, xs, [&](int i, double v) { tau_contact[i] += v; });
                 st |= 4;
             } else {
