@@ -449,12 +449,15 @@ int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *
         CK(cudaMemsetAsync(b->w.tau_contact, 0, sizeof(double) * B * m, st));
     }
     if (stages & (DWBC_SOLVE_HQP | DWBC_SOLVE_REDIST)) {
-        HqpSmem L(b->w.n, b->w.m);
+        int nvmax = RMAX > 0 ? RMAX : 1;
+        if (stages & DWBC_SOLVE_HQP)
+            for (int l = 0; l < b->cfg.nlevels; l++) nvmax = b->cfg.tasks[l].dof + RMAX > nvmax ? b->cfg.tasks[l].dof + RMAX : nvmax;
+        HqpSmem L(b->w.n, b->w.m, nvmax);
         size_t smem = sizeof(double) * L.total;
         CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelScope ks(b, DWBC_K_HQP, st);
         DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0,
-                    (stages & DWBC_SOLVE_REDIST) ? 1 : 0);
+                    (stages & DWBC_SOLVE_REDIST) ? 1 : 0, nvmax);
     }
     CK(cudaGetLastError());
     if (tau_grav_dev) CK(cudaMemcpyAsync(tau_grav_dev, b->w.tau_grav, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));

@@ -38,23 +38,24 @@ constexpr int GI_SCRATCH_DOUBLES = 448;  // >= GiScratch::DOUBLES (static_assert
 
 struct HqpSmem {
     int ldm, ldq, ldc, U, AU, At, Q, R, b, tol, rin, bt, gi, vec, total;
-    __host__ __device__ HqpSmem(int n, int m) {
+    // nvmax: largest number of QP variables of the configured hierarchy (max task dof + RMAX); the arena is sized for it
+    __host__ __device__ HqpSmem(int n, int m, int nvmax) {
         ldm = m | 1;
-        ldq = QP_NV_MAX - 1;  // 31, odd
+        ldq = nvmax | 1;
         ldc = QP_NC_MAX | 1;  // 21
         int o = 0;
-        U = o; o += ldm * QP_NV_MAX;
-        AU = o; o += ldc * QP_NV_MAX;
-        At = o; o += ldc * m;
-        Q = o; o += ldq * QP_NV_MAX;
-        R = o; o += ldq * QP_NV_MAX;
+        U = o; o += ldm * nvmax;
+        AU = o; o += ldc * nvmax;
+        // Atemp (nc x m) is only needed while a level's QP is assembled; it shares its storage with the solver's Q and R
+        const int qr = 2 * ldq * nvmax, at = ldc * m;
+        At = o; Q = o; R = o + ldq * nvmax; o += qr > at ? qr : at;
         const int mc = 2 * m + QP_NC_MAX;
         b = o; o += mc + 2;
         tol = o; o += mc + 2;
         rin = o; o += mc + 2;   // 1 / scaled row norm
         bt = o; o += mc + 2;    // right-hand side of the current sub-problem
         gi = o; o += GI_SCRATCH_DOUBLES;  // GiScratch
-        vec = o; o += 6 * (n + 2) + 2;  // + status / iteration words of the QP just solved
+        vec = o; o += 6 * (n + 2) + 2;
         total = o;
     }
 };
@@ -178,10 +179,20 @@ __device__ __forceinline__ double team_sum(double v, const GiScratch &S) {
 // isd_j = isd_t for j < tsplit, isd_c otherwise.  `pin` (may be null): rows to be pinned as equalities, added first and never
 // dropped.  On return S.dxs holds dx, S.act / S.u the active rows and their multipliers (logical positions < q).
 // Deliberately NOT inlined (instruction-cache footprint, profiles/r01_ncu_summary.md).  Synchronises on entry and exit.
-__device__ __noinline__ GiResult gi_solve(const QpView &V, const double *bt, const double *tolv, double *rin, double isd_t, double isd_c,
-                                          int tsplit, double *Q, double *R, int ldq, const GiScratch &S, const uint32_t *pin, int max_iter) {
+__device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, int mt, int nc, int col0, int nv, int use_bt, double isd_t,
+                                          double isd_c, int tsplit, int use_pin, int max_iter) {
+    // Everything is re-derived from the arena base and a few integers: structs passed by reference to a non-inlined function
+    // live in local memory, and with most of L1 carved out as shared memory those loads went to L2 (ncu: 20 % L1 hit rate,
+    // long-scoreboard the second largest stall of the first team version).
+    const HqpSmem L(n, m, nvmax);
+    const GiScratch S(sm + L.gi, sm + L.bt);
+    const QpView V{sm + L.U, sm + L.AU, L.ldm, L.ldc, m, mt, nc, col0, nv};
+    const double *bt = use_bt ? sm + L.bt : sm + L.b, *tolv = sm + L.tol;
+    double *rin = sm + L.rin, *Q = sm + L.Q, *R = sm + L.R;
+    const int ldq = L.ldq;
+    const uint32_t *pin = use_pin ? S.pinw : nullptr;
     const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
-    const int nv = V.nv, mc = V.rows();
+    const int mc = V.rows();
     double *y = S.y, *u = S.u, *dxs = S.dxs, *dv = S.dv, *zv = S.zv, *rkv = S.rkv, *isds = S.isds, *gcs = S.gcs, *scal = S.scal;
     int *act = S.act, *slot = S.slot, *ired = S.ired;
     uint32_t *amask = S.amask;
@@ -446,6 +457,82 @@ __device__ __noinline__ GiResult gi_solve(const QpView &V, const double *bt, con
     return res;
 }
 
+// Re-solve after a change of the right-hand side only (the next proximal-point iterate): with the factorisation Q, R and the
+// active set left by the previous gi_solve, the candidate  y = Q_1 w,  R^T w = -bt_W  is the least-norm point on the active
+// rows and  lambda = R^{-1} w  its multipliers.  If lambda >= 0 and every other row is satisfied this is the (unique) optimum
+// of the new sub-problem -- at the cost of about one active-set iteration; otherwise nothing is modified and the caller falls
+// back to a cold gi_solve.  Same team conventions as gi_solve; synchronises on entry and exit.
+__device__ __noinline__ bool gi_warm(double *sm, int n, int m, int nvmax, int mt, int nc, int col0, int nv, int q) {
+    const HqpSmem L(n, m, nvmax);
+    const GiScratch S(sm + L.gi, sm + L.bt);
+    const QpView V{sm + L.U, sm + L.AU, L.ldm, L.ldc, m, mt, nc, col0, nv};
+    const double *bt = sm + L.bt, *tolv = sm + L.tol, *rin = sm + L.rin, *Q = sm + L.Q, *R = sm + L.R;
+    const int ldq = L.ldq;
+    const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
+    const int mc = V.rows();
+    double *wv = S.dv, *lam = S.rkv, *yn = S.zv;  // scratch vectors of gi_solve, free between calls
+    tsync();
+    if (warp == 0) {
+        const int myslot = lane < q ? S.slot[lane] : 0;
+        const double *col = R + myslot * ldq;
+        const double invd = lane < q ? 1.0 / col[lane] : 0.0;
+        double rhs = lane < q ? -bt[S.act[lane]] : 0.0;
+        for (int k = 0; k < q; k++) {  // forward substitution with R^T (column j of R is owned by lane j)
+            const double val = __shfl_sync(DWBC_FULL, rhs, k) * __shfl_sync(DWBC_FULL, invd, k);
+            if (lane == k) rhs = val;
+            if (lane > k && lane < q) rhs = fma(-col[k], val, rhs);
+        }
+        const double w = rhs;
+        double rk = w;
+        for (int k = q - 1; k >= 0; k--) {  // back substitution with R
+            const int sk = __shfl_sync(DWBC_FULL, myslot, k);
+            const double val = __shfl_sync(DWBC_FULL, rk, k) * __shfl_sync(DWBC_FULL, invd, k);
+            if (lane == k) rk = val;
+            if (lane < k) rk = fma(-R[lane + sk * ldq], val, rk);
+        }
+        const double lmax = warp_max(lane < q ? fabs(rk) : 0.0);
+        const bool neg = lane < q && rk < -1e-12 * lmax;
+        const bool anyneg = __any_sync(DWBC_FULL, neg);
+        if (lane < q) wv[lane] = w, lam[lane] = rk;
+        if (lane == 0) S.ired[GI_WARPS_MAX] = anyneg ? 1 : 0;
+    }
+    tsync();
+    if (S.ired[GI_WARPS_MAX]) {
+        tsync();
+        return false;
+    }
+    {
+        const int part = tid & 3;
+        for (int j0 = 0; j0 < nv; j0 += nt >> 2) {
+            const int j = j0 + (tid >> 2);
+            double a0 = 0.0;
+            if (j < nv)
+                for (int k = part; k < q; k += 4) a0 = fma(Q[j + k * ldq], wv[k], a0);
+            a0 += __shfl_xor_sync(DWBC_FULL, a0, 1);
+            a0 += __shfl_xor_sync(DWBC_FULL, a0, 2);
+            if (j < nv && part == 0) yn[j] = a0 * S.isds[j];  // dx = y o isd
+        }
+    }
+    tsync();
+    bool viol = false;
+    for (int i = tid; i < mc; i += nt) {
+        const double s1 = bt[i] - V.dot(i, yn);
+        if (!bit_test(S.amask, i) && s1 < -tolv[i] && rin[i] > 0.0) viol = true;
+    }
+    const bool wviol = __any_sync(DWBC_FULL, viol);
+    if (lane == 0) S.ired[warp] = wviol ? 1 : 0;
+    tsync();
+    bool bad = false;
+    for (int w = 0; w < nw; w++) bad = bad || S.ired[w];
+    if (!bad && tid < nv) {
+        S.dxs[tid] = yn[tid];
+        S.y[tid] = yn[tid] / S.isds[tid];
+        if (tid < q) S.u[tid] = lam[tid] > 0.0 ? lam[tid] : 0.0;
+    }
+    tsync();
+    return !bad;
+}
+
 struct LevelOut {
     int status;
     int iters;
@@ -454,13 +541,15 @@ struct LevelOut {
 // Solves one QP (t task variables first, then r contact variables) with the whole team.  U (m x nv), AU (nc x nv) and b (rows)
 // are in shared memory; the solution is left in S.xj.  active_out (global, ACTIVE_WORDS words): rows with zero slack at the
 // solution.  Synchronises on entry and exit.
-__device__ __noinline__ LevelOut solve_level(int t, int r, int m, int mt, int nc, const double *U, const double *AU, int ldm, int ldc,
-                                             const double *b, double *tolv, double *rin, double *Q, double *R, int ldq, const GiScratch &S,
-                                             uint32_t *active_out) {
+__device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax, int t, int r, int mt, int nc, uint32_t *active_out) {
+    const HqpSmem L(n, m, nvmax);
+    const GiScratch S(sm + L.gi, sm + L.bt);
+    const double *b = sm + L.b;
+    double *tolv = sm + L.tol, *rin = sm + L.rin;
     const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
     const int nv = t + r, mc = mt + nc;
     LevelOut out{1, 0};
-    QpView V{U, AU, ldm, ldc, m, mt, nc, 0, nv};
+    const QpView V{sm + L.U, sm + L.AU, L.ldm, L.ldc, m, mt, nc, 0, nv};
     double *xj = S.xj, *xs = S.xs, *xp = S.xp;
     tsync();
     if (tid < QP_NV_MAX) xj[tid] = 0.0;
@@ -519,7 +608,7 @@ __device__ __noinline__ LevelOut solve_level(int t, int r, int m, int mt, int nc
     const int max_iter = 20 * (nv + 8);
     bool done = false;
     if (t == 0 || r == 0) {
-        GiResult g = gi_solve(V, b, tolv, rin, 1.0, 1.0, nv, Q, R, ldq, S, nullptr, max_iter);
+        GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, 0, nv, 0, 1.0, 1.0, nv, 0, max_iter);
         out.iters += g.iters;
         out.status = g.status;
         if (tid < nv) xj[tid] = S.dxs[tid];
@@ -528,10 +617,7 @@ __device__ __noinline__ LevelOut solve_level(int t, int r, int m, int mt, int nc
     if (!done) {
         // ---- A: is x_t = 0 attainable?  (looser tolerances: the set may be a thin face inherited from the levels above)
         for (int i = tid; i < mc; i += nt) tolv[i] *= 100.0;
-        QpView Vc = V;
-        Vc.col0 = t;
-        Vc.nv = r;
-        GiResult g = gi_solve(Vc, b, tolv, rin, 1.0, 1.0, r, Q, R, ldq, S, nullptr, max_iter);
+        GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, t, r, 0, 1.0, 1.0, r, 0, max_iter);
         out.iters += g.iters;
         if (g.status) {
             if (tid < r) xj[t + tid] = S.dxs[tid];
@@ -564,8 +650,12 @@ __device__ __noinline__ LevelOut solve_level(int t, int r, int m, int mt, int nc
                 for (int j = t; j < nv; j++) s = fma(-V.a(i, j), xs[j], s);
                 bt[i] = s;
             }
-            g = gi_solve(V, bt, tolv, rin, 1.0, isd_c, t, Q, R, ldq, S, nullptr, max_iter);
-            out.iters += g.iters;
+            if (k > 0 && gi_warm(sm, n, m, nvmax, mt, nc, 0, nv, g.q)) {
+                out.iters += 1;
+            } else {
+                g = gi_solve(sm, n, m, nvmax, mt, nc, 0, nv, 1, 1.0, isd_c, t, 0, max_iter);
+                out.iters += g.iters;
+            }
             if (!g.status) {
                 out.status = 0;
                 break;
@@ -603,10 +693,7 @@ __device__ __noinline__ LevelOut solve_level(int t, int r, int m, int mt, int nc
                 bt[i] = s;
                 tolv[i] *= 100.0;
             }
-            QpView Vc = V;
-            Vc.col0 = t;
-            Vc.nv = r;
-            GiResult gc = gi_solve(Vc, bt, tolv, rin, 1.0, 1.0, r, Q, R, ldq, S, S.pinw, max_iter);
+            GiResult gc = gi_solve(sm, n, m, nvmax, mt, nc, t, r, 1, 1.0, 1.0, r, 1, max_iter);
             out.iters += gc.iters;
             if (!gc.status) out.status = 0;
             if (tid < r) xj[t + tid] = S.dxs[tid];
@@ -640,12 +727,13 @@ __device__ __noinline__ LevelOut solve_level(int t, int r, int m, int mt, int nc
 
 // One CTA (team) per state: QP assembly (U, Atemp U, right-hand sides), the active-set iterations (gi_solve) and the torque
 // updates all use every thread of the team.
-__global__ void __launch_bounds__(TEAM, 5) hqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int redist) {
+__global__ void __launch_bounds__(TEAM, 6) hqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int redist,
+                                                      int nvmax) {
     DWBC_DYN_SMEM(smem);
     const int tid = t_id(), nt = t_n(), warp = tid >> 5, lane = lane_id();
     const long long s = blockIdx.x;
     const int n = w.n, m = w.m, nb = w.nb;
-    const HqpSmem L(n, m);
+    const HqpSmem L(n, m, nvmax);
     double *sm = (double *)smem;
     double *U = sm + L.U, *AU = sm + L.AU, *At = sm + L.At, *Q = sm + L.Q, *R = sm + L.R, *b = sm + L.b, *tolv = sm + L.tol, *rin = sm + L.rin;
     const GiScratch S(sm + L.gi, sm + L.bt);
@@ -668,8 +756,9 @@ __global__ void __launch_bounds__(TEAM, 5) hqp_kernel(const DevModel *__restrict
         if (tid == 0) w.status[s] = st, w.qp_iters[s] = 0;
         return;
     }
-    // ---- Atemp = A_const A_rot Jbar^T[:, 6:]  (nc x m)  and  bA0 = A_const A_rot P_C ----
-    {
+    // ---- Atemp = A_const A_rot Jbar^T[:, 6:]  (nc x m)  and  bA0 = A_const A_rot P_C.  Rebuilt for every QP: the solver's Q / R
+    // overwrite its storage (a few hundred flops from L2-resident operands against 4-5 KB of shared memory per state) ----
+    auto build_At = [&]() {
         const double *Jb = w.Jbar + s * (long long)CMAX * n;
         const double *pose = w.pose + s * (long long)nb * POSE_STRIDE;
         for (int e = tid; e < kc * (m + 1); e += nt) {
@@ -687,7 +776,7 @@ __global__ void __launch_bounds__(TEAM, 5) hqp_kernel(const DevModel *__restrict
                 for (int a = 0; a < 10; a++) bA0[10 * k + a] = o[a];
             }
         }
-    }
+    };
     for (int i = tid; i < m; i += nt) tprev[i] = w.tau_grav[s * m + i];
     tsync();
     const double *NwJw = w.NwJw + s * (long long)m * RMAX;
@@ -709,6 +798,7 @@ __global__ void __launch_bounds__(TEAM, 5) hqp_kernel(const DevModel *__restrict
             tcopy(m, t, w.Ntq[l] + s * (long long)m * t, m, U, ldm);
             tcopy(m, r, NwJw, m, U + t * ldm, ldm);
             for (int i = tid; i < t; i += nt) fs[i] = w.fstar[l][s * t + i];
+            build_At();
             tsync();
             // base = tau_prev + Ntorque f*
             tgemv<false>(m, t, U, ldm, fs, [&](int i, double v) { base[i] = tprev[i] + v; });
@@ -722,7 +812,7 @@ __global__ void __launch_bounds__(TEAM, 5) hqp_kernel(const DevModel *__restrict
                 }
             tgemv<false>(nc, m, At, ldc, base, [&](int i, double v) { b[mt + i] = -(bA0[i] - v); });
             tsync();
-            const LevelOut lo = solve_level(t, r, m, mt, nc, U, AU, ldm, ldc, b, tolv, rin, Q, R, ldq, S, w.active[l] + s * ACTIVE_WORDS);
+            const LevelOut lo = solve_level(sm, n, m, nvmax, t, r, mt, nc, w.active[l] + s * ACTIVE_WORDS);
             total_iters += lo.iters;
             if (!lo.status) {
                 all_ok = false;  // reference: f_star_qp_ = contact_qp_ = 0 and return 0 (src/dwbc.cpp:1117-1125, 836-837)
@@ -766,6 +856,7 @@ __global__ void __launch_bounds__(TEAM, 5) hqp_kernel(const DevModel *__restrict
         } else {
             for (int i = tid; i < m; i += nt) base[i] = w.tau_grav[s * m + i] + tau_task[i] + tau_contact[i];  // tau_in
             tcopy(m, r, NwJw, m, U, ldm);
+            build_At();
             tsync();
             tgemm<2, 1, false, false>(nc, r, m, At, ldc, U, ldm, [&](int i, int j, double v) { AU[i + j * ldc] = v; });
             if (mt)
@@ -775,7 +866,7 @@ __global__ void __launch_bounds__(TEAM, 5) hqp_kernel(const DevModel *__restrict
                 }
             tgemv<false>(nc, m, At, ldc, base, [&](int i, double v) { b[mt + i] = -(bA0[i] - v); });
             tsync();
-            const LevelOut lo = solve_level(0, r, m, mt, nc, U, AU, ldm, ldc, b, tolv, rin, Q, R, ldq, S, w.active[MAX_LEVELS] + s * ACTIVE_WORDS);
+            const LevelOut lo = solve_level(sm, n, m, nvmax, 0, r, mt, nc, w.active[MAX_LEVELS] + s * ACTIVE_WORDS);
             total_iters += lo.iters;
             if (lo.status) {
                 if (tid < r) {
