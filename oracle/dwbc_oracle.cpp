@@ -18,6 +18,8 @@
 //   CalcTaskControlTorque / CalcSingleTaskTorqueWithQP   src/dwbc.cpp:818-873, 941-1127
 //   CalcContactRedistribute      src/dwbc.cpp:1372-1568
 // Parity is pinned by the reference's golden vectors tests/cases/{1,2} (tests/test_oracle_golden.py).
+#include <array>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -218,6 +220,7 @@ struct Robot {
     Mat torque_grav, torque_task, torque_contact, cf_redis_qp, redisA, redisub;
     V3 com_pos;
     int contact_dof = 0, contact_links = 0, contact_ok = 0, redis_status = 0;
+    double redis_eta = 0;
     std::vector<int> redis_active;
 
     void update_kinematics(const double *q_, const double *qd_);
@@ -230,6 +233,8 @@ struct Robot {
     int calc_task_torque(bool hqp);
     int single_task_qp(Task &t, const Mat &null_prev, const Mat &torque_prev);
     int calc_redistribute(bool hqp);
+    Mat get_contact_force(const Mat &command_torque) const;
+    V3 get_zmp(const Mat &contact_force, std::vector<V3> *per_contact = nullptr) const;
     void contact_const(Mat &A_const, Mat &A_rot, int &csize) const;
 };
 
@@ -600,6 +605,90 @@ int Robot::calc_task_torque(bool hqp) {
     return 1;
 }
 
+// Eigen MatrixBase::eulerAngles(2, 1, 0) as documented (Eigen 3.3 / 3.4 Geometry/EulerAngles.h; Eigen is an unpinned
+// third-party dependency, CMakeLists.txt:32): returns (angle about z, about y, about x) with the first angle in [0, pi].
+// The reference stores it as Link::rpy (src/link.cpp:81), so rpy(2) is the angle about x of that decomposition.
+static inline std::array<double, 3> eigen_euler_zyx(const M3 &R) {
+    const int i = 2, j = 1, k = 0;  // a0 = 2, a1 = 1: odd permutation
+    std::array<double, 3> res;
+    res[0] = std::atan2(R.m[j][k], R.m[k][k]);
+    const double c2 = std::sqrt(R.m[i][i] * R.m[i][i] + R.m[i][j] * R.m[i][j]);
+    if (res[0] < 0.0) {
+        res[0] += M_PI;
+        res[1] = std::atan2(-R.m[i][k], -c2);
+    } else {
+        res[1] = std::atan2(-R.m[i][k], c2);
+    }
+    const double s1 = std::sin(res[0]), c1 = std::cos(res[0]);
+    res[2] = std::atan2(s1 * R.m[k][i] - c1 * R.m[j][i], c1 * R.m[j][j] - s1 * R.m[k][j]);
+    return res;
+}
+
+// ContactRedistributetwomod, reference src/wbd.cpp:273-404 (closed-form split of the resultant wrench between two feet)
+static void contact_redistribute_two(double eta_cust, double footlength, double footwidth, double staticFrictionCoeff, double ratio_x,
+                                     double ratio_y, V3 P1, V3 P2, const double *F12, double *RF, double *FR, double &eta) {
+    // ResultantForce = [I 0 I 0; skew(P1) I skew(P2) I] F12
+    V3 f1{F12[0], F12[1], F12[2]}, m1{F12[3], F12[4], F12[5]}, f2{F12[6], F12[7], F12[8]}, m2{F12[9], F12[10], F12[11]};
+    V3 fs = f1 + f2, ms = cross(P1, f1) + m1 + cross(P2, f2) + m2;
+    RF[0] = fs.x; RF[1] = fs.y; RF[2] = fs.z; RF[3] = ms.x; RF[4] = ms.y; RF[5] = ms.z;
+    double eta_lb = 1.0 - eta_cust, eta_ub = eta_cust;
+    auto clip = [&](double A, double B, double C) {
+        double a = A * A, b = 2.0 * A * B, c = B * B - C * C;
+        double s1 = (-b + std::sqrt(b * b - 4.0 * a * c)) / 2.0 / a;
+        double s2 = (-b - std::sqrt(b * b - 4.0 * a * c)) / 2.0 / a;
+        if (s1 > s2) {
+            if (s1 < eta_ub) eta_ub = s1;
+            if (s2 > eta_lb) eta_lb = s2;
+        } else {
+            if (s2 < eta_ub) eta_ub = s2;
+            if (s1 > eta_lb) eta_lb = s1;
+        }
+    };
+    const double Ax = (P1.z - P2.z) * RF[1] - (P1.y - P2.y) * RF[2], Bx = RF[3] + P2.z * RF[1] - P2.y * RF[2];
+    const double Ay = -(P1.z - P2.z) * RF[0] + (P1.x - P2.x) * RF[2], By = RF[4] - P2.z * RF[0] + P2.x * RF[2];
+    const double Az = -(P1.x - P2.x) * RF[1] + (P1.y - P2.y) * RF[0], Bz = RF[5] + P2.y * RF[0] - P2.x * RF[1];
+    clip(Ax, Bx, ratio_y * footwidth / 2.0 * std::fabs(RF[2]));
+    clip(Ay, By, ratio_x * footlength / 2.0 * std::fabs(RF[2]));
+    clip(Az, Bz, staticFrictionCoeff * std::fabs(RF[2]));
+    const double eta_s = (-RF[3] - P2.z * RF[1] + P2.y * RF[2]) / ((P1.z - P2.z) * RF[1] - (P1.y - P2.y) * RF[2]);
+    eta = eta_s;
+    if (eta_s > eta_ub) eta = eta_ub;
+    else if (eta_s < eta_lb) eta = eta_lb;
+    if ((eta > eta_cust) || (eta < 1.0 - eta_cust)) eta = 0.5;
+    FR[0] = eta * RF[0]; FR[1] = eta * RF[1]; FR[2] = eta * RF[2];
+    FR[3] = Ax * eta * eta + Bx * eta;
+    FR[4] = Ay * eta * eta + By * eta;
+    FR[5] = Az * eta * eta + Bz * eta;
+    FR[6] = (1.0 - eta) * RF[0]; FR[7] = (1.0 - eta) * RF[1]; FR[8] = (1.0 - eta) * RF[2];
+    FR[9] = (1.0 - eta) * (Ax * eta + Bx);
+    FR[10] = (1.0 - eta) * (Ay * eta + By);
+    FR[11] = (1.0 - eta) * (Az * eta + Bz);
+}
+
+// getContactForce -> CalculateContactForce, reference src/dwbc.cpp:891-896, src/wbd.cpp:268-271
+Mat Robot::get_contact_force(const Mat &command_torque) const { return J_C_INV_T.right_cols(m) * command_torque - P_C; }
+
+// getZMP, reference src/dwbc.cpp:898-939 (as written: registered contact i reads contact_force(6 i + ...), i.e. the active
+// contacts are assumed to be a prefix of the registered ones)
+V3 Robot::get_zmp(const Mat &cf, std::vector<V3> *per_contact) const {
+    V3 zmp{0, 0, 0};
+    double total_fz = 0;
+    for (size_t i = 0; i < cc.size(); i++)
+        if (cc[i].on) total_fz += cf[2 + i * 6];
+    if (per_contact) per_contact->assign(cc.size(), V3{0, 0, 0});
+    for (size_t i = 0; i < cc.size(); i++) {
+        if (!cc[i].on) continue;
+        V3 z = cc[i].xc;
+        if (!(cf[i * 6 + 2] > -1.0e-3)) {
+            z.x = cc[i].xc.x + (-cf[i * 6 + 4] / cf[i * 6 + 2]);
+            z.y = cc[i].xc.y + (cf[i * 6 + 3] / cf[i * 6 + 2]);
+        }
+        if (per_contact) (*per_contact)[i] = z;
+        zmp = zmp + (cf[i * 6 + 2] / total_fz) * z;
+    }
+    return zmp;
+}
+
 // reference src/dwbc.cpp:1377-1568 (QP branch).  The reference sizes the QP with
 // contact_link_num_*contact_constraint_size rows (quirk 5): the extra rows are 0*x in [0,0]
 // and are dropped here.
@@ -608,9 +697,36 @@ int Robot::calc_redistribute(bool hqp) {
     redis_active.clear();
     Mat tin = torque_grav + torque_task + torque_contact;
     int r = contact_dof - 6;
-    if (!hqp) {  // analytic two-foot branch is outside this file's scope for now
-        torque_contact.set_zero(m, 1);
-        return 0;
+    if (!hqp) {
+        // analytic two-foot branch, reference src/dwbc.cpp:1570-1619: the first two REGISTERED contacts (cc_[0], cc_[1])
+        if (contact_dof != 12) {
+            torque_contact.set_zero(m, 1);
+            return 0;
+        }
+        Mat cf = J_C_INV_T.right_cols(m) * tin - P_C;  // ContactForce_
+        const double ang = -eigen_euler_zyx(Rw[0])[2];  // -link_[0].rpy(2), rpy = rotm.eulerAngles(2, 1, 0) (src/link.cpp:81)
+        M3 Rz = eye3();  // rotateWithZ, reference src/math.cpp:55-74
+        Rz.m[0][0] = std::cos(ang); Rz.m[0][1] = -std::sin(ang);
+        Rz.m[1][0] = std::sin(ang); Rz.m[1][1] = std::cos(ang);
+        V3 P1 = mul(Rz, cc[0].xc - com_pos), P2 = mul(Rz, cc[1].xc - com_pos);
+        double F12[12], FR[12], res6[6], eta = 0.95;
+        for (int k = 0; k < 4; k++) {
+            V3 f = mul(Rz, V3{cf[3 * k], cf[3 * k + 1], cf[3 * k + 2]});
+            F12[3 * k] = f.x; F12[3 * k + 1] = f.y; F12[3 * k + 2] = f.z;
+        }
+        contact_redistribute_two(0.99, 0.26, 0.1, 1.0, 0.9, 0.9, P1, P2, F12, res6, FR, eta);
+        Mat des(6, 1);
+        M3 Rzt = tr(Rz);
+        for (int k = 2; k < 4; k++) {
+            V3 f = mul(Rzt, V3{FR[3 * k], FR[3 * k + 1], FR[3 * k + 2]});
+            des[3 * (k - 2)] = -cf[3 * k] + f.x;
+            des[3 * (k - 2) + 1] = -cf[3 * k + 1] + f.y;
+            des[3 * (k - 2) + 2] = -cf[3 * k + 2] + f.z;
+        }
+        redis_eta = eta;
+        torque_contact = V2.t() * lu_inverse(J_C_INV_T.right_cols(m).bottom_rows(6) * V2.t()) * des;
+        redis_status = 1;
+        return 1;
     }
     if (r <= 0) {
         torque_contact.set_zero(m, 1);
@@ -750,6 +866,24 @@ void orc_set_task(void *h, int level, const double *fstar, const double *J) {
 void orc_calc_grav(void *h) { ((Robot *)h)->calc_grav(); }
 int orc_calc_task_torque(void *h, int hqp) { return ((Robot *)h)->calc_task_torque(hqp != 0); }
 int orc_calc_redistribute(void *h, int hqp) { return ((Robot *)h)->calc_redistribute(hqp != 0); }
+// getContactForce(command_torque) -> out [contact_dof]; returns contact_dof
+int orc_contact_force(void *h, const double *torque, double *out) {
+    Robot *R = (Robot *)h;
+    Mat t(R->m, 1);
+    for (int i = 0; i < R->m; i++) t[i] = torque[i];
+    Mat cf = R->get_contact_force(t);
+    for (int i = 0; i < cf.r; i++) out[i] = cf[i];
+    return cf.r;
+}
+// getZMP(contact_force [6 * ncontact, zero padded]) -> out [3]
+void orc_zmp(void *h, const double *cf, double *out) {
+    Robot *R = (Robot *)h;
+    Mat c((int)(6 * R->cc.size()), 1);
+    for (int i = 0; i < c.r; i++) c[i] = cf[i];
+    V3 z = R->get_zmp(c);
+    out[0] = z.x, out[1] = z.y, out[2] = z.z;
+}
+double orc_redis_eta(void *h) { return ((Robot *)h)->redis_eta; }
 
 static const Mat *find_mat(Robot *R, const std::string &name, Mat &tmp) {
     auto lvl = [&](const char *prefix) -> int {
@@ -875,8 +1009,11 @@ void orc_cod_pinv(int rows, int cols, const double *A, double thr, double *pinv,
 // order, cold-start QP per state.  `stages`: bit0 grav, bit1 task torque, bit2 HQP, bit3 redistribute.
 // fstar: concatenation over levels of [B x t_l] row-major blocks; flags: [B x ncontact].
 // Outputs [B x m] row-major torques, status [B] (bit0 contact ok, bit1 task ok, bit2 redistribute ok).
+// bit4: CalcContactRedistribute(hqp=false) (analytic two-foot branch) instead of the QP.  Optional outputs: contact_force
+// [B x 6*ncontact] = getContactForce(tau_grav + tau_task + tau_contact) (zero padded), zmp [B x 3] = getZMP(contact_force).
 int orc_run_batch(void *h, int B, const double *q, const double *qd, const double *fstar, const unsigned char *flags,
-                  int stages, double *tau_grav, double *tau_task, double *tau_contact, int *status, int nthreads) {
+                  int stages, double *tau_grav, double *tau_task, double *tau_contact, int *status, int nthreads,
+                  double *contact_force, double *zmp) {
     Robot *R0 = (Robot *)h;
     int n = R0->n, m = R0->m, nc = (int)R0->cc.size();
     std::vector<size_t> foff;
@@ -906,6 +1043,18 @@ int orc_run_batch(void *h, int B, const double *q, const double *qd, const doubl
                 R.calc_grav();
                 if (stages & 2) st |= R.calc_task_torque((stages & 4) != 0) ? 2 : 0;
                 if (stages & 8) st |= R.calc_redistribute(true) ? 4 : 0;
+                else if (stages & 16) st |= R.calc_redistribute(false) ? 4 : 0;
+                if (contact_force || zmp) {
+                    Mat cf = R.get_contact_force(R.torque_grav + R.torque_task + R.torque_contact);
+                    if (contact_force)
+                        for (int i = 0; i < 6 * nc; i++) contact_force[(size_t)b * 6 * nc + i] = i < cf.r ? cf[i] : 0.0;
+                    if (zmp) {
+                        Mat cfp(6 * nc, 1);
+                        for (int i = 0; i < cf.r && i < 6 * nc; i++) cfp[i] = cf[i];
+                        V3 z = R.get_zmp(cfp);
+                        zmp[(size_t)b * 3] = z.x, zmp[(size_t)b * 3 + 1] = z.y, zmp[(size_t)b * 3 + 2] = z.z;
+                    }
+                }
                 for (int i = 0; i < m; i++) {
                     tau_grav[(size_t)b * m + i] = R.torque_grav[i];
                     tau_task[(size_t)b * m + i] = R.torque_task[i];

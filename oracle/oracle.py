@@ -62,7 +62,11 @@ def lib():
         L.orc_get_qp_info.argtypes = [C.c_void_p, C.c_int, _ip, _ip]
         L.orc_lexqp.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _ip]
         L.orc_cod_pinv.argtypes = [C.c_int, C.c_int, _dp, C.c_double, _dp, _ip]
-        L.orc_run_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_char_p, C.c_int, _dp, _dp, _dp, _ip, C.c_int]
+        L.orc_run_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_char_p, C.c_int, _dp, _dp, _dp, _ip, C.c_int, _dp, _dp]
+        L.orc_contact_force.argtypes = [C.c_void_p, _dp, _dp]
+        L.orc_zmp.argtypes = [C.c_void_p, _dp, _dp]
+        L.orc_redis_eta.argtypes = [C.c_void_p]
+        L.orc_redis_eta.restype = C.c_double
         L.orc_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -162,6 +166,21 @@ class OracleRobot:
     def calc_redistribute(self, hqp=True):
         return lib().orc_calc_redistribute(self.h, 1 if hqp else 0)
 
+    def contact_force(self, torque):
+        """getContactForce(command_torque), reference src/dwbc.cpp:891-896"""
+        _, tp = _d(torque)
+        out = np.zeros(6 * self.ncontact)
+        k = lib().orc_contact_force(self.h, tp, out.ctypes.data_as(_dp))
+        return out[:k]
+
+    def zmp(self, contact_force):
+        """getZMP(contact_force), reference src/dwbc.cpp:898-939"""
+        cf = np.zeros(6 * self.ncontact)
+        cf[:len(contact_force)] = contact_force
+        out = np.zeros(3)
+        lib().orc_zmp(self.h, cf.ctypes.data_as(_dp), out.ctypes.data_as(_dp))
+        return out
+
     # ---- results ----
     def get(self, name):
         r, c = C.c_int(), C.c_int()
@@ -192,10 +211,11 @@ class OracleRobot:
         assert fl.shape == (B, self.ncontact)
         tg = np.zeros((B, self.m)); tt = np.zeros((B, self.m)); tc = np.zeros((B, self.m))
         st = np.zeros(B, dtype=np.int32)
+        cf = np.zeros((B, 6 * self.ncontact)); zmp = np.zeros((B, 3))
         lib().orc_run_batch(self.h, B, q.ctypes.data_as(_dp), qd.ctypes.data_as(_dp), fs.ctypes.data_as(_dp),
                             fl.ctypes.data_as(C.c_char_p), int(stages), tg.ctypes.data_as(_dp), tt.ctypes.data_as(_dp),
-                            tc.ctypes.data_as(_dp), st.ctypes.data_as(_ip), int(nthreads))
-        return dict(torque_grav=tg, torque_task=tt, torque_contact=tc, status=st)
+                            tc.ctypes.data_as(_dp), st.ctypes.data_as(_ip), int(nthreads), cf.ctypes.data_as(_dp), zmp.ctypes.data_as(_dp))
+        return dict(torque_grav=tg, torque_task=tt, torque_contact=tc, status=st, contact_force=cf, zmp=zmp)
 
 
 def lexqp(A, ub, t):
