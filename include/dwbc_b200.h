@@ -62,7 +62,9 @@ enum {
     DWBC_SOLVE_GRAV = 1,      /* CalcGravCompensation            reference src/dwbc.cpp:875-889 */
     DWBC_SOLVE_TASK = 2,      /* CalcTaskSpace + CalcTaskControlTorque(hqp=false)  :795-873 */
     DWBC_SOLVE_HQP = 4,       /* ... with hqp=true: per-level QP  :941-1127 (implies DWBC_SOLVE_TASK) */
-    DWBC_SOLVE_REDIST = 8     /* CalcContactRedistribute(hqp=true) :1372-1568 */
+    DWBC_SOLVE_REDIST = 8,    /* CalcContactRedistribute(hqp=true) :1372-1568 */
+    DWBC_SOLVE_REDIST_ANALYTIC = 16 /* CalcContactRedistribute(hqp=false) :1570-1619 + ContactRedistributetwomod src/wbd.cpp:273-404
+                                       (two-foot closed form; ignored when DWBC_SOLVE_REDIST is also set) */
 };
 
 /* per-state status bits (1 = the corresponding reference call would have returned 1) */
@@ -163,6 +165,13 @@ int dwbc_batch_get_matrix(dwbc_batch_t *b, int which, int level, double *out_dev
  * +torque (m), -torque (m), contact (10 per active contact)). */
 int dwbc_batch_get_active_set(dwbc_batch_t *b, int level, uint32_t *out_dev, void *stream);
 
+/* getContactForce(command_torque)   reference src/dwbc.cpp:891-896, src/wbd.cpp:268-271:
+ * cf = J_C_INV_T[:, 6:] tau - P_C.  torque_dev [B x m], or NULL for torque_grav_ + torque_task_ + torque_contact_ of the last
+ * solve.  cf_dev [B x cmax], rows >= contact_dof are zero. */
+int dwbc_batch_get_contact_force(dwbc_batch_t *b, const double *torque_dev, double *cf_dev, void *stream);
+/* getZMP(contact_force)   reference src/dwbc.cpp:898-939.  cf_dev [B x cmax] (stacked active contacts), zmp_dev [B x 3]. */
+int dwbc_batch_get_zmp(dwbc_batch_t *b, const double *cf_dev, double *zmp_dev, void *stream);
+
 /* ---- whole cycle with HOST buffers (pinned or pageable): H2D, all stages, D2H, synchronised on return.
  * This is what the RobotData shim, the pybind bridge and bench.py's end-to-end timing call.
  * fstar_host: concatenation over levels of [B x t_l] blocks. flags_host [B x ncontact]. */
@@ -178,7 +187,7 @@ int dwbc_probe_fp64(int device, double seconds, double *tflops);
  * recorded on the launch stream (no host synchronisation is added to the hot path).  dwbc_batch_get_kernel_times
  * synchronises the pending events and returns, per DWBC_K_* kernel, the summed duration in ms (only launches made while
  * profiling was on) and the launch count since the last reset.  bench.py's roofline numbers come from here. */
-enum { DWBC_K_RBD = 0, DWBC_K_AINV, DWBC_K_CONTACT_JAC, DWBC_K_CONTACT_DYN, DWBC_K_TASK, DWBC_K_HQP, DWBC_K_EXPORT, DWBC_K_COUNT };
+enum { DWBC_K_RBD = 0, DWBC_K_AINV, DWBC_K_CONTACT_JAC, DWBC_K_CONTACT_DYN, DWBC_K_TASK, DWBC_K_HQP, DWBC_K_EXPORT, DWBC_K_POST, DWBC_K_COUNT };
 int dwbc_batch_set_profiling(dwbc_batch_t *b, int enable);
 int dwbc_batch_get_kernel_times(dwbc_batch_t *b, double *ms_sum, long long *launches, int reset);
 const char *dwbc_kernel_name(int k);

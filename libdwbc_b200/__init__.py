@@ -12,6 +12,7 @@ from .batch import (  # noqa: F401
     SOLVE_GRAV,
     SOLVE_HQP,
     SOLVE_REDIST,
+    SOLVE_REDIST_ANALYTIC,
     SOLVE_TASK,
     ST_CONTACT_OK,
     ST_REDIST_OK,

@@ -50,6 +50,8 @@ def declare(L):
     L.dwbc_batch_solve.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
     L.dwbc_batch_get_matrix.argtypes = [vp, C.c_int, C.c_int, vp, _ip, _ip, vp]
     L.dwbc_batch_get_active_set.argtypes = [vp, C.c_int, vp, vp]
+    L.dwbc_batch_get_contact_force.argtypes = [vp, vp, vp, vp]
+    L.dwbc_batch_get_zmp.argtypes = [vp, vp, vp, vp]
     L.dwbc_batch_cycle_host.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.dwbc_probe_fp64.argtypes = [C.c_int, C.c_double, _dp]
     L.dwbc_batch_get_qp_iterations.argtypes = [vp, vp, vp]
@@ -66,7 +68,7 @@ EXPORTS = [
     "dwbc_batch_set_friction", "dwbc_batch_add_task", "dwbc_batch_add_custom_task", "dwbc_batch_clear_tasks", "dwbc_batch_set_torque_limit",
     "dwbc_batch_update_kinematics", "dwbc_batch_set_contact", "dwbc_batch_calc_contact_constraint", "dwbc_batch_set_task", "dwbc_batch_solve",
     "dwbc_batch_get_matrix", "dwbc_batch_get_active_set", "dwbc_batch_cycle_host", "dwbc_probe_fp64", "dwbc_batch_get_qp_iterations",
-    "dwbc_batch_set_profiling", "dwbc_batch_get_kernel_times", "dwbc_kernel_name",
+    "dwbc_batch_set_profiling", "dwbc_batch_get_kernel_times", "dwbc_kernel_name", "dwbc_batch_get_contact_force", "dwbc_batch_get_zmp",
 ]
 
 _lib = None

@@ -20,7 +20,7 @@ from ._lib import DwbcError, load_library
 CONTACT_6D = 0
 (TASK_LINK_6D, TASK_LINK_6D_COM_FRAME, TASK_LINK_6D_CUSTOM_FRAME, TASK_LINK_POSITION, TASK_LINK_POSITION_COM_FRAME,
  TASK_LINK_POSITION_CUSTOM_FRAME, TASK_LINK_ROTATION, TASK_LINK_ROTATION_CUSTOM_FRAME) = range(8)
-SOLVE_GRAV, SOLVE_TASK, SOLVE_HQP, SOLVE_REDIST = 1, 2, 4, 8
+SOLVE_GRAV, SOLVE_TASK, SOLVE_HQP, SOLVE_REDIST, SOLVE_REDIST_ANALYTIC = 1, 2, 4, 8, 16
 ST_CONTACT_OK, ST_TASK_OK, ST_REDIST_OK = 1, 2, 4
 
 # name -> (matrix id, per-level?)
@@ -228,6 +228,30 @@ class RobotDataBatch:
             out = out[:, :, 0]
         return out
 
+    def get_contact_force(self, torque=None):
+        """getContactForce(command_torque) (reference src/dwbc.cpp:891-896): [B, cmax]; torque=None uses
+        torque_grav_ + torque_task_ + torque_contact_ of the last solve."""
+        be = self.be
+        out = be.empty((self.batch, self.cmax))
+        tp = None
+        if torque is not None:
+            torque = be.check(torque)
+            if tuple(torque.shape) != (self.batch, self.model_dof_):
+                raise DwbcError("command torque must be [batch, model_dof]")
+            tp = be.ptr(torque)
+        self._ck(self.L.dwbc_batch_get_contact_force(self._h, tp, be.ptr(out), be.stream()))
+        return out
+
+    def get_zmp(self, contact_force):
+        """getZMP(contact_force) (reference src/dwbc.cpp:898-939): [B, 3]"""
+        be = self.be
+        cf = be.check(contact_force)
+        if tuple(cf.shape) != (self.batch, self.cmax):
+            raise DwbcError("contact force must be [batch, cmax]")
+        out = be.empty((self.batch, 3))
+        self._ck(self.L.dwbc_batch_get_zmp(self._h, be.ptr(cf), be.ptr(out), be.stream()))
+        return out
+
     def active_set(self, level):
         """Active rows of the level's QP (level = -1: redistribution QP) as a list of row-index lists."""
         be = self.be
@@ -251,7 +275,7 @@ class RobotDataBatch:
 
     def kernel_times(self, reset=True):
         """{kernel name: (summed ms while profiling was on, launches since the last reset)}"""
-        K = 7
+        K = 8
         ms = (C.c_double * K)()
         cnt = (C.c_longlong * K)()
         self._ck(self.L.dwbc_batch_get_kernel_times(self._h, ms, cnt, 1 if reset else 0))

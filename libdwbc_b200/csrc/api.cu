@@ -13,6 +13,7 @@
 #include "cuda_compat.h"
 #include "kernels_contact.cuh"
 #include "kernels_hqp.cuh"
+#include "kernels_post.cuh"
 #include "kernels_task.cuh"
 #include "model.h"
 
@@ -427,7 +428,7 @@ int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *
     if (rc) return rc;
     const size_t B = b->B, m = b->w.m;
     if (stages & DWBC_SOLVE_HQP) stages |= DWBC_SOLVE_TASK;
-    if (stages & (DWBC_SOLVE_TASK | DWBC_SOLVE_REDIST)) {
+    if (stages & (DWBC_SOLVE_TASK | DWBC_SOLVE_REDIST | DWBC_SOLVE_REDIST_ANALYTIC)) {
         if (stages & DWBC_SOLVE_TASK) {
             if (b->cfg.nlevels == 0) return fail(DWBC_ERR_ORDER, "solve: no task registered");
             for (int l = 0; l < b->cfg.nlevels; l++)
@@ -458,6 +459,12 @@ int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *
         KernelScope ks(b, DWBC_K_HQP, st);
         DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0,
                     (stages & DWBC_SOLVE_REDIST) ? 1 : 0, nvmax);
+    }
+    if ((stages & DWBC_SOLVE_REDIST_ANALYTIC) && !(stages & DWBC_SOLVE_REDIST)) {
+        const int wpb = WARPS_PER_BLOCK, grid = grid_for(b->B, wpb);
+        const size_t smem = sizeof(double) * wpb * (MAXB + CMAX + 6 * 7 + 8);
+        KernelScope ks(b, DWBC_K_POST, st);
+        DWBC_LAUNCH(redistribute_analytic_kernel, grid, wpb * 32, smem, st, b->d_model, b->d_cfg, b->w);
     }
     CK(cudaGetLastError());
     if (tau_grav_dev) CK(cudaMemcpyAsync(tau_grav_dev, b->w.tau_grav, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));
@@ -534,6 +541,39 @@ int dwbc_batch_get_matrix(dwbc_batch_t *b, int which, int level, double *out_dev
     return DWBC_OK;
 }
 
+int dwbc_batch_get_contact_force(dwbc_batch_t *b, const double *torque_dev, double *cf_dev, void *stream) {
+    if (!b || !cf_dev) return fail(DWBC_ERR_ARG, "get_contact_force: null argument");
+    if (!b->have_cc) return fail(DWBC_ERR_ORDER, "get_contact_force: call calc_contact_constraint first");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = upload_cfg(b, st);
+    if (rc) return rc;
+    const int wpb = WARPS_PER_BLOCK, grid = grid_for(b->B, wpb);
+    {
+        KernelScope ks(b, DWBC_K_POST, st);
+        DWBC_LAUNCH(contact_force_kernel, grid, wpb * 32, sizeof(double) * wpb * (MAXB + CMAX), st, b->d_model, b->d_cfg, b->w, 1, torque_dev,
+                    (const double *)nullptr, cf_dev, (double *)nullptr);
+    }
+    CK(cudaGetLastError());
+    return DWBC_OK;
+}
+int dwbc_batch_get_zmp(dwbc_batch_t *b, const double *cf_dev, double *zmp_dev, void *stream) {
+    if (!b || !cf_dev || !zmp_dev) return fail(DWBC_ERR_ARG, "get_zmp: null argument");
+    if (!b->have_cc) return fail(DWBC_ERR_ORDER, "get_zmp: call calc_contact_constraint first");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = upload_cfg(b, st);
+    if (rc) return rc;
+    const int wpb = WARPS_PER_BLOCK, grid = grid_for(b->B, wpb);
+    {
+        KernelScope ks(b, DWBC_K_POST, st);
+        DWBC_LAUNCH(contact_force_kernel, grid, wpb * 32, sizeof(double) * wpb * (MAXB + CMAX), st, b->d_model, b->d_cfg, b->w, 2,
+                    (const double *)nullptr, cf_dev, (double *)nullptr, zmp_dev);
+    }
+    CK(cudaGetLastError());
+    return DWBC_OK;
+}
+
 int dwbc_batch_get_active_set(dwbc_batch_t *b, int level, uint32_t *out_dev, void *stream) {
     if (!b || !out_dev) return fail(DWBC_ERR_ARG, "get_active_set: null argument");
     if (level >= b->cfg.nlevels || level < -1) return fail(DWBC_ERR_ARG, "get_active_set: level out of range");
@@ -577,7 +617,7 @@ int dwbc_batch_get_kernel_times(dwbc_batch_t *b, double *ms_sum, long long *laun
 
 const char *dwbc_kernel_name(int k) {
     static const char *names[DWBC_K_COUNT] = {"rbd_kernel", "ainv_kernel", "contact_jacobian_kernel", "contact_dynamics_kernel",
-                                              "task_space_kernel", "hqp_kernel", "export_kernels"};
+                                              "task_space_kernel", "hqp_kernel", "export_kernels", "post_kernels"};
     return (k >= 0 && k < DWBC_K_COUNT) ? names[k] : nullptr;
 }
 

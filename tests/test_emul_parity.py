@@ -92,3 +92,33 @@ def test_emul_config1_closed_form():
         assert relerr(rd.get("link_pos")[b], ref.get("link_pos")) < 1e-12
         assert relerr(rd.get("link_rot")[b], ref.get("link_rot")) < 1e-12
         assert relerr(rd.get("link_vel")[b], ref.get("link_vel")) < 1e-11
+
+
+def test_emul_analytic_redistribution_contact_force_zmp():
+    """CalcTaskControlTorque(hqp=false) + CalcContactRedistribute(hqp=false) (the path the reference's Python bridge runs,
+    src/pybind/rl_wbc_bridge.cpp:123-129), getContactForce and getZMP against the oracle."""
+    from libdwbc_b200 import SOLVE_REDIST_ANALYTIC
+    B = 12
+    q, qd, rng = synth_states(B, 20251)
+    q[:, 3:6] *= 3.0  # larger base tilt / yaw of either sign: exercises the Eigen eulerAngles branch
+    q[:, 39] = np.sqrt(1.0 - np.sum(q[:, 3:6] ** 2, axis=1))
+    fs = synth_fstar(rng, B, dofs=config_dofs(1), scales=(0.5, 1.0))
+    flags = np.ones((B, 2), dtype=np.uint8)
+    flags[5] = [1, 0]
+    rd, (tg, tt, tc, st) = run_product(1, q, qd, fs, flags, SOLVE_GRAV | SOLVE_TASK | SOLVE_REDIST_ANALYTIC)
+    ref = configure_oracle(orc.OracleRobot(URDF), 1)
+    o = ref.run_batch(q, qd, fs, flags, stages=1 | 2 | 16)
+    assert np.array_equal(st & 7, o["status"] & 7)
+    assert (o["status"][np.arange(B) != 5] & 4).all() and not (o["status"][5] & 4)
+    assert np.abs(o["torque_contact"]).max() > 1e-3
+    for name, a in (("torque_grav", tg), ("torque_task", tt), ("torque_contact", tc)):
+        assert relerr(a, o[name]) < 1e-9, name
+    cf = rd.get_contact_force()
+    assert relerr(cf, o["contact_force"]) < 1e-9
+    zmp = rd.get_zmp(np.ascontiguousarray(cf))
+    assert relerr(zmp, o["zmp"]) < 1e-9
+    # explicit command torque
+    tau = np.ascontiguousarray(tg + tt)
+    cf2 = rd.get_contact_force(tau)
+    ref.update_kinematics(q[0], qd[0]); ref.set_contact(1, 1); ref.calc_contact_constraint(); ref.calc_grav()
+    assert relerr(cf2[0], ref.contact_force(tau[0])) < 1e-9

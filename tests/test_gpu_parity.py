@@ -286,3 +286,30 @@ def test_no_contact_and_empty_flags():
     assert st[3] & 7 == 0
     assert np.all(tt[3] == 0) and np.all(tc[3] == 0)
     assert np.all((st[[0, 1, 2, 4, 5, 6, 7]] & 1) == 1)
+
+
+def test_analytic_redistribution_contact_force_zmp():
+    """CalcTaskControlTorque(hqp=false) + CalcContactRedistribute(hqp=false) (reference src/dwbc.cpp:1570-1619,
+    src/wbd.cpp:273-404: the path the reference's Python bridge runs), getContactForce and getZMP (src/dwbc.cpp:891-939)
+    against the oracle, 1e-9 relative."""
+    from libdwbc_b200 import SOLVE_GRAV, SOLVE_REDIST_ANALYTIC, SOLVE_TASK
+    from oracle import oracle as orc
+
+    B = 512
+    q, qd, rng = synth_states(B, 20251)
+    q[:, 3:6] *= 3.0  # base yaw of either sign: both branches of Eigen's eulerAngles
+    q[:, 39] = np.sqrt(1.0 - np.sum(q[:, 3:6] ** 2, axis=1))
+    fs = synth_fstar(rng, B, dofs=config_dofs(1), scales=(0.5, 1.0))
+    flags = np.ones((B, 2), dtype=np.uint8)
+    flags[5] = [1, 0]
+    rd, (tg, tt, tc, st) = run_product(1, q, qd, fs, flags, SOLVE_GRAV | SOLVE_TASK | SOLVE_REDIST_ANALYTIC)
+    ref = configure_oracle(orc.OracleRobot(URDF), 1)
+    o = ref.run_batch(q, qd, fs, flags, stages=1 | 2 | 16)
+    assert np.array_equal(st & 7, o["status"] & 7)
+    for name, a in (("torque_grav", tg), ("torque_task", tt), ("torque_contact", tc)):
+        err = np.linalg.norm(a - o[name], axis=1) / np.maximum(np.linalg.norm(o[name], axis=1), 1e-3)
+        assert err.max() < 1e-9, (name, err.max(), int(err.argmax()))
+    cf = rd.get_contact_force()
+    assert relerr(cf.cpu().numpy(), o["contact_force"]) < 1e-9
+    zmp = rd.get_zmp(cf)
+    assert relerr(zmp.cpu().numpy(), o["zmp"]) < 1e-9
