@@ -99,22 +99,23 @@ struct QpView {
             sgn = -1.0;
         }
     }
-    // sum_j a(i, j) x[j], four independent partial sums
+    // sum_j a(i, j) x[j], two independent partial sums.  Deliberately a compact loop: this is inlined at every row scan of the
+    // solver, and the solver's hot loop has to stay within the 32 KB L1.5 instruction cache (profiles/r01_ncu_warm_prox.md:
+    // no_instruction was the top stall of hqp_kernel).
     __device__ __forceinline__ double dot(int i, const double *x) const {
         const double *p;
         int ld;
         double sgn;
         row(i, p, ld, sgn);
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        double s0 = 0.0, s1 = 0.0;
         int j = 0;
-        for (; j + 3 < nv; j += 4) {
+        DWBC_UNROLL(1)
+        for (; j + 1 < nv; j += 2) {
             s0 = fma(p[j * ld], x[j], s0);
             s1 = fma(p[(j + 1) * ld], x[j + 1], s1);
-            s2 = fma(p[(j + 2) * ld], x[j + 2], s2);
-            s3 = fma(p[(j + 3) * ld], x[j + 3], s3);
         }
-        for (; j < nv; j++) s0 = fma(p[j * ld], x[j], s0);
-        return sgn * ((s0 + s1) + (s2 + s3));
+        if (j < nv) s0 = fma(p[j * ld], x[j], s0);
+        return sgn * (s0 + s1);
     }
 };
 
@@ -197,6 +198,7 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
     int *act = S.act, *slot = S.slot, *ired = S.ired;
     uint32_t *amask = S.amask;
     tsync();
+    DWBC_UNROLL(1)
     for (int e = tid; e < ldq * nv; e += nt) Q[e] = 0.0;
     if (tid < nv) {
         isds[tid] = tid < tsplit ? isd_t : isd_c;
@@ -213,8 +215,10 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
     // largest row norm are numerically zero (what rounding leaves of a constraint already active at a higher level) and
     // never enter the active set (rin = 0); the oracle applies the same rule.
     double smax = 0.0;
+    DWBC_UNROLL(1)
     for (int i = tid; i < mc; i += nt) {
         double s = 0.0;
+        DWBC_UNROLL(1)
         for (int j = 0; j < nv; j++) {
             const double v = V.a(i, j) * isds[j];
             s = fma(v, v, s);
@@ -223,6 +227,7 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
         smax = s > smax ? s : smax;
     }
     smax = team_max(smax, S);
+    DWBC_UNROLL(1)
     for (int i = tid; i < mc; i += nt) {
         const double s = rin[i];
         rin[i] = (s > 0.0 && s > 1e-20 * smax) ? 1.0 / sqrt(s) : 0.0;
@@ -234,6 +239,7 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
     int p = -1;  // row being added
     double sp = 0.0, sigma = 1.0, up = 0.0;
     int pin_scan = 0;
+    DWBC_UNROLL(1)
     for (int it = 0; it < max_iter; it++) {
         res.iters = it + 1;
         if (p < 0) {
@@ -258,6 +264,7 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
             } else {
                 double best = 0.0;
                 int bi = -1;
+                DWBC_UNROLL(1)
                 for (int i = tid; i < mc; i += nt) {
                     const double s1 = bt[i] - V.dot(i, dxs);
                     if (!bit_test(amask, i) && s1 < -tolv[i] && s1 * rin[i] < best) best = s1 * rin[i], bi = i;
@@ -270,6 +277,7 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
                 if (lane == 0) S.red[warp] = best, ired[warp] = bi;
                 tsync();
                 best = S.red[0], bi = ired[0];
+                DWBC_UNROLL(1)
                 for (int w = 1; w < nw; w++) {
                     const double ob = S.red[w];
                     const int oi = ired[w];
@@ -293,10 +301,12 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
             V.row(p, rp, rld, rs);
             rs *= -sigma;
             const int part = tid & 3;
+            DWBC_UNROLL(1)
             for (int k0 = 0; k0 < nv; k0 += nt >> 2) {
                 const int k = k0 + (tid >> 2);
                 double a0 = 0.0;
                 if (k < nv)
+                    DWBC_UNROLL(1)
                     for (int j = part; j < nv; j += 4) a0 = fma(Q[j + k * ldq], rp[j * rld] * isds[j], a0);
                 a0 += __shfl_xor_sync(DWBC_FULL, a0, 1);
                 a0 += __shfl_xor_sync(DWBC_FULL, a0, 2);
@@ -310,10 +320,12 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
         const double nn = warp_sum(dk * dk);
         {
             const int part = tid & 3;
+            DWBC_UNROLL(1)
             for (int j0 = 0; j0 < nv; j0 += nt >> 2) {
                 const int j = j0 + (tid >> 2);
                 double a0 = 0.0;
                 if (j < nv)
+                    DWBC_UNROLL(1)
                     for (int k = q + part; k < nv; k += 4) a0 = fma(Q[j + k * ldq], dv[k], a0);
                 a0 += __shfl_xor_sync(DWBC_FULL, a0, 1);
                 a0 += __shfl_xor_sync(DWBC_FULL, a0, 2);
@@ -324,6 +336,7 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
             const int myslot = lane < q ? slot[lane] : 0;
             const double invd = lane < q ? 1.0 / R[lane + myslot * ldq] : 0.0;
             double rk = (lane < q) ? dk : 0.0;
+            DWBC_UNROLL(1)
             for (int k = q - 1; k >= 0; k--) {
                 const int sk = __shfl_sync(DWBC_FULL, myslot, k);
                 const double val = __shfl_sync(DWBC_FULL, rk, k) * __shfl_sync(DWBC_FULL, invd, k);
@@ -375,11 +388,13 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
             const double alpha = dq > 0.0 ? -sqrt(zz) : sqrt(zz);
             const double tau = 1.0 / (zz - alpha * dq);
             const int part = tid & 3;
+            DWBC_UNROLL(1)
             for (int j0 = 0; j0 < nv; j0 += nt >> 2) {
                 const int j = j0 + (tid >> 2);
                 const double wj = j < nv ? tau * (zv[j] - alpha * Q[j + q * ldq]) : 0.0;
                 __syncwarp();  // the four threads of row j have read Q[j, q] before it is overwritten
                 if (j < nv)
+                    DWBC_UNROLL(1)
                     for (int k = q + part; k < nv; k += 4) {
                         const double hk = k == q ? dq - alpha : dv[k];
                         Q[j + k * ldq] = fma(-wj, hk, Q[j + k * ldq]);
@@ -407,6 +422,7 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
             if (warp == 0) {
                 // Givens rotations of rows k, k+1 of R: lane j owns logical column j (only it touches that column)
                 double *col = R + (lane < q ? slot[lane] : 0) * ldq;
+                DWBC_UNROLL(1)
                 for (int k = l; k + 1 < q; k++) {
                     double a = 0.0, bb = 0.0;
                     if (lane == k + 1) a = col[k], bb = col[k + 1];
@@ -425,6 +441,7 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
             tsync();  // every thread has read act[l] / slot[l]; the rotations are published
             if (tid < nv) {
                 double q0 = Q[tid + l * ldq];
+                DWBC_UNROLL(1)
                 for (int k = l; k + 1 < q; k++) {
                     const double cs = gcs[2 * k], sn = gcs[2 * k + 1];
                     const double q1 = Q[tid + (k + 1) * ldq];
@@ -477,6 +494,7 @@ __device__ __noinline__ bool gi_warm(double *sm, int n, int m, int nvmax, int mt
         const double *col = R + myslot * ldq;
         const double invd = lane < q ? 1.0 / col[lane] : 0.0;
         double rhs = lane < q ? -bt[S.act[lane]] : 0.0;
+        DWBC_UNROLL(1)
         for (int k = 0; k < q; k++) {  // forward substitution with R^T (column j of R is owned by lane j)
             const double val = __shfl_sync(DWBC_FULL, rhs, k) * __shfl_sync(DWBC_FULL, invd, k);
             if (lane == k) rhs = val;
@@ -484,6 +502,7 @@ __device__ __noinline__ bool gi_warm(double *sm, int n, int m, int nvmax, int mt
         }
         const double w = rhs;
         double rk = w;
+        DWBC_UNROLL(1)
         for (int k = q - 1; k >= 0; k--) {  // back substitution with R
             const int sk = __shfl_sync(DWBC_FULL, myslot, k);
             const double val = __shfl_sync(DWBC_FULL, rk, k) * __shfl_sync(DWBC_FULL, invd, k);
@@ -503,10 +522,12 @@ __device__ __noinline__ bool gi_warm(double *sm, int n, int m, int nvmax, int mt
     }
     {
         const int part = tid & 3;
+        DWBC_UNROLL(1)
         for (int j0 = 0; j0 < nv; j0 += nt >> 2) {
             const int j = j0 + (tid >> 2);
             double a0 = 0.0;
             if (j < nv)
+                DWBC_UNROLL(1)
                 for (int k = part; k < q; k += 4) a0 = fma(Q[j + k * ldq], wv[k], a0);
             a0 += __shfl_xor_sync(DWBC_FULL, a0, 1);
             a0 += __shfl_xor_sync(DWBC_FULL, a0, 2);
@@ -515,6 +536,7 @@ __device__ __noinline__ bool gi_warm(double *sm, int n, int m, int nvmax, int mt
     }
     tsync();
     bool viol = false;
+    DWBC_UNROLL(1)
     for (int i = tid; i < mc; i += nt) {
         const double s1 = bt[i] - V.dot(i, yn);
         if (!bit_test(S.amask, i) && s1 < -tolv[i] && rin[i] > 0.0) viol = true;
@@ -523,6 +545,7 @@ __device__ __noinline__ bool gi_warm(double *sm, int n, int m, int nvmax, int mt
     if (lane == 0) S.ired[warp] = wviol ? 1 : 0;
     tsync();
     bool bad = false;
+    DWBC_UNROLL(1)
     for (int w = 0; w < nw; w++) bad = bad || S.ired[w];
     if (!bad && tid < nv) {
         S.dxs[tid] = yn[tid];
@@ -556,8 +579,10 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
     // row tolerances in the units of the rows, the quick exit, and the active rows of the quick exit.  Numerically zero
     // rows (norm <= 1e-10 of the largest) cannot be influenced by x: they only decide feasibility (b >= -1e-9).
     double smax = 0.0;
+    DWBC_UNROLL(1)
     for (int i = tid; i < mc; i += nt) {
         double s = 0.0;
+        DWBC_UNROLL(1)
         for (int j = 0; j < nv; j++) {
             const double v = V.a(i, j);
             s = fma(v, v, s);
@@ -568,6 +593,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
     smax = team_max(smax, S);
     double bmin = 1e300;
     bool infeasible = false;
+    DWBC_UNROLL(1)
     for (int i0 = 0; i0 < mc; i0 += nt) {
         const int i = i0 + tid;
         bool on = false;
@@ -591,6 +617,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
     tsync();
     bool any_inf = false;
     bmin = 1e300;
+    DWBC_UNROLL(1)
     for (int w = 0; w < nw; w++) {
         bmin = fmin(bmin, S.red[w]);
         any_inf = any_inf || S.ired[w];
@@ -616,6 +643,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
     }
     if (!done) {
         // ---- A: is x_t = 0 attainable?  (looser tolerances: the set may be a thin face inherited from the levels above)
+        DWBC_UNROLL(1)
         for (int i = tid; i < mc; i += nt) tolv[i] *= 100.0;
         GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, t, r, 0, 1.0, 1.0, r, 0, max_iter);
         out.iters += g.iters;
@@ -623,13 +651,16 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
             if (tid < r) xj[t + tid] = S.dxs[tid];
             done = true;
         }
+        DWBC_UNROLL(1)
         for (int i = tid; i < mc; i += nt) tolv[i] *= 0.01;
         tsync();
     }
     if (!done) {
         // ---- B: proximal point on 1/2|x_t|^2 + delta/2 |x_c - c|^2 ----
         double ntn = 0.0, ncn = 0.0;
+        DWBC_UNROLL(1)
         for (int i = tid; i < mc; i += nt)
+            DWBC_UNROLL(1)
             for (int j = 0; j < nv; j++) {
                 const double v = V.a(i, j);
                 if (j < t) ntn = fma(v, v, ntn);
@@ -644,9 +675,12 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
         tsync();
         bool conv = false;
         GiResult g{0, 0, 0};
+        DWBC_UNROLL(1)
         for (int k = 0; k < 30; k++) {
+            DWBC_UNROLL(1)
             for (int i = tid; i < mc; i += nt) {  // bt = b - A x0 (x0 is zero on the task columns)
                 double s = b[i];
+                DWBC_UNROLL(1)
                 for (int j = t; j < nv; j++) s = fma(-V.a(i, j), xs[j], s);
                 bt[i] = s;
             }
@@ -683,12 +717,15 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
             if (tid < ACTIVE_WORDS) S.pinw[tid] = 0u;
             tsync();
             if (tid == 0)
+                DWBC_UNROLL(1)
                 for (int k = 0; k < g.q; k++) {
                     const int ak = S.act[k];
                     if (ak >= 0 && S.u[k] > 1e-9 * umax) S.pinw[ak >> 5] |= 1u << (ak & 31);
                 }
+            DWBC_UNROLL(1)
             for (int i = tid; i < mc; i += nt) {
                 double s = b[i];
+                DWBC_UNROLL(1)
                 for (int j = 0; j < t; j++) s = fma(-V.a(i, j), xj[j], s);
                 bt[i] = s;
                 tolv[i] *= 100.0;
@@ -703,11 +740,13 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
     if (!out.status && tid < QP_NV_MAX) xj[tid] = 0.0;
     tsync();
     // active rows at the solution: slack within 1e-9 (1 + |b|), rows with a zero normal excluded (the oracle's rule)
+    DWBC_UNROLL(1)
     for (int i0 = 0; i0 < mc; i0 += nt) {
         const int i = i0 + tid;
         bool on = false;
         if (i < mc && out.status) {
             double s = -b[i], nn2 = 0.0;
+            DWBC_UNROLL(1)
             for (int j = 0; j < nv; j++) {
                 const double a = V.a(i, j);
                 s = fma(a, xj[j], s);

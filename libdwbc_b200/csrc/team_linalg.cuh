@@ -102,6 +102,7 @@ __device__ __forceinline__ void tgemv(int M, int K, const double *__restrict__ A
         const bool act = i < M;
         const int ii = act ? i : 0;
         double a0 = 0.0;
+        DWBC_UNROLL(2)
         for (int k = part; k < K; k += 4) a0 = fma(TA ? A[k + ii * lda] : A[ii + k * lda], x[k], a0);
         a0 += __shfl_xor_sync(DWBC_FULL, a0, 1);
         a0 += __shfl_xor_sync(DWBC_FULL, a0, 2);
