@@ -18,6 +18,7 @@
 //   CalcTaskControlTorque / CalcSingleTaskTorqueWithQP   src/dwbc.cpp:818-873, 941-1127
 //   CalcContactRedistribute      src/dwbc.cpp:1372-1568
 // Parity is pinned by the reference's golden vectors tests/cases/{1,2} (tests/test_oracle_golden.py).
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdio>
@@ -195,6 +196,10 @@ struct Task {
     Mat qpA, qpub;  // last assembled QP (parity with the golden A*mat / ubA*mat)
     std::vector<int> active;
     int qp_status = 0, prox_iters = 0;
+    // a9 reduced-dimension variant (reference include/dwbc_task.h: noncont_task, reduced_task_, cmm_task, ..._R_ members)
+    bool noncont = false, reduced = false, cmm = false;
+    int nc_h = 0;
+    Mat J_R, Lambda_R, Jkt_R, Null_R, J_NC, torque_nc, force_on_nc, torque_h_R, torque_null_h_R, torque_null_h_nc;
 };
 
 struct Robot {
@@ -236,6 +241,20 @@ struct Robot {
     Mat get_contact_force(const Mat &command_torque) const;
     V3 get_zmp(const Mat &contact_force, std::vector<V3> *per_contact = nullptr) const;
     void contact_const(Mat &A_const, Mat &A_rot, int &csize) const;
+
+    // ---- a9: reduced-dimension variant (Ahn 2024), reference src/dwbc.cpp:2752-3446 ----
+    std::vector<int> co_link, nc_link, co_joint, nc_joint, vc_joint;
+    int co_dof = 0, nc_dof = 0, vc_dof = 0, rsys = 0, rmod = 0, reduced_ok = 0;
+    double mass_nc = 0;
+    V3 com_pos_nc;
+    Mat A_NC, SI_nc_b, SI_nc_l, cmm_nc, J_I_nc, J_R, A_R_inv, A_R, J_I_nc_inv_T, N_I_nc, G_R, J_CR;
+    Mat Lambda_CR, J_CR_INV_T, N_CR, A_R_inv_N_CR, W_R, W_R_inv, V2_R, NwJw_R, P_CR, torque_grav_R;
+    Mat J_base_R, J_base_R_kt, lambda_base_R, torque_task_R, torque_task_NC;
+    void reduced_dynamics();
+    int reduced_contact_constraint();
+    void reduced_grav();
+    int reduced_task_space();
+    int reduced_task_torque(bool hqp);
 };
 
 void Robot::update_kinematics(const double *q_, const double *qd_) {
@@ -767,6 +786,318 @@ int Robot::calc_redistribute(bool hqp) {
     return 1;
 }
 
+
+// ==========================================================================================
+// a9: reduced-dimension variant (Ahn 2024).  Literal restatement of reference src/dwbc.cpp:2752-3446,
+// src/task.cpp:95-142, src/wbd.cpp:220-226.  No goldens exist for it: parity is pinned by the property
+// "reduced torques == full-model torques" printed by reference tests/sp_test/redu_dyn_test.cpp:323-360
+// and asserted in tests/test_oracle_reduced.py.  hqp=true (CalcSingleTaskTorqueWithQP_R[_NC]) is not restated yet.
+// ==========================================================================================
+static inline bool has(const std::vector<int> &v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); }
+
+// ReducedDynamicsCalculate, reference src/dwbc.cpp:2752-2989
+void Robot::reduced_dynamics() {
+    co_link.clear(); nc_link.clear(); co_joint.clear(); nc_joint.clear(); vc_joint.clear();
+    co_link.push_back(0);
+    for (auto &c : cc)
+        if (c.on) {
+            int l = c.link;
+            while (l != 0) {
+                co_link.push_back(l);
+                co_joint.push_back(5 + l);  // joint_[l].joint_id_ = q index of the joint that moves link l
+                l = parent[l];
+            }
+        }
+    std::sort(co_link.begin(), co_link.end());
+    for (int i = 0; i < nb; i++)
+        if (!has(co_link, i)) nc_link.push_back(i);
+    std::sort(co_joint.begin(), co_joint.end());
+    for (int i = 0; i < 6; i++) vc_joint.push_back(i);
+    vc_joint.insert(vc_joint.end(), co_joint.begin(), co_joint.end());
+    for (int l0 : nc_link) {
+        int l = l0;
+        while (l != 0) {
+            if (!has(nc_joint, 5 + l)) nc_joint.push_back(5 + l);
+            l = parent[l];
+            if (has(nc_link, l)) break;
+        }
+    }
+    std::sort(nc_joint.begin(), nc_joint.end());
+    nc_dof = (int)nc_joint.size();
+    co_dof = (int)co_joint.size();
+    vc_dof = co_dof + 6;
+    rmod = co_dof + 6;
+    rsys = rmod + 6;
+
+    // CRBA restricted to the non-contact bodies, reference :2828-2878
+    std::vector<M6> Ic(nb);
+    for (int i = 0; i < nb; i++)
+        if (has(nc_link, i)) Ic[i] = spatial_inertia(mass[i], com[i], inertia[i]);
+    Mat A_NC_O(n, n);
+    M6 S0;
+    {
+        M3 Rt = tr(Rw[0]);
+        for (int i = 0; i < 3; i++)
+            for (int k = 0; k < 3; k++) S0.m[3 + i][k] = Rt.m[i][k];
+        for (int k = 0; k < 3; k++) S0.m[k][3 + k] = 1.0;
+    }
+    for (int i = nb - 1; i >= 1; i--) {
+        if (!has(nc_link, i)) continue;
+        {   // the RBDL parent of every real body is non-zero (the pelvis hangs off the translation body)
+            M6 t = mul(tr(Xl[i]), mul(Ic[i], Xl[i]));
+            M6 &P = Ic[parent[i]];
+            for (int a = 0; a < 6; a++)
+                for (int b = 0; b < 6; b++) P.m[a][b] += t.m[a][b];
+        }
+        V6 S;
+        S.v[0] = axis[i].x; S.v[1] = axis[i].y; S.v[2] = axis[i].z;
+        V6 F = mul(Ic[i], S);
+        A_NC_O(5 + i, 5 + i) = S.v[0] * F.v[0] + S.v[1] * F.v[1] + S.v[2] * F.v[2];
+        int j = i;
+        while (j > 0) {
+            F = mulT(Xl[j], F);
+            j = parent[j];
+            if (j > 0) {
+                double v = axis[j].x * F.v[0] + axis[j].y * F.v[1] + axis[j].z * F.v[2];
+                A_NC_O(5 + i, 5 + j) = v;
+                A_NC_O(5 + j, 5 + i) = v;
+            } else {
+                V6 b = mulT(S0, F);
+                for (int k = 0; k < 6; k++) A_NC_O(5 + i, k) = A_NC_O(k, 5 + i) = b.v[k];
+            }
+        }
+    }
+    // SI_nc_b_ from model_.Ic[2] (composite of the nc chain at the pelvis, pelvis frame), reference :2880-2885
+    SI_nc_b.set_zero(6, 6);
+    const double M = Ic[0].m[3][3];
+    for (int i = 0; i < 3; i++) {
+        SI_nc_b(i, i) = M;
+        for (int j = 0; j < 3; j++) {
+            SI_nc_b(3 + i, 3 + j) = Ic[0].m[i][j];
+            SI_nc_b(3 + i, j) = Ic[0].m[i][3 + j];
+            SI_nc_b(j, 3 + i) = Ic[0].m[i][3 + j];
+        }
+    }
+    // InertiaMatrixSegment / InertiaMatrix, reference src/math.cpp:304-320
+    mass_nc = SI_nc_b(0, 0);
+    com_pos_nc = {SI_nc_b(5, 1) / mass_nc, SI_nc_b(3, 2) / mass_nc, SI_nc_b(4, 0) / mass_nc};
+    M3 sc = skew3(com_pos_nc), scsct = mul(sc, tr(sc));
+    SI_nc_l.set_zero(6, 6);
+    for (int i = 0; i < 3; i++) {
+        SI_nc_l(i, i) = mass_nc;
+        for (int j = 0; j < 3; j++) SI_nc_l(3 + i, 3 + j) = SI_nc_b(3 + i, 3 + j) - mass_nc * scsct.m[i][j];
+    }
+    // A_NC, reference :2890-2906 (only its top-right 6 x nc block is rotated; the bottom-left is left as is)
+    A_NC.set_zero(nc_dof + 6, nc_dof + 6);
+    A_NC.set_block(0, 0, SI_nc_b);
+    for (int i = 0; i < nc_dof; i++) {
+        for (int j = 0; j < 6; j++) {
+            A_NC(6 + i, j) = A_NC_O(nc_joint[i], j);
+            A_NC(j, 6 + i) = A_NC_O(j, nc_joint[i]);
+        }
+        for (int j = 0; j < nc_dof; j++) A_NC(6 + i, 6 + j) = A_NC_O(nc_joint[i], nc_joint[j]);
+    }
+    {
+        Mat R0t(3, 3);
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) R0t(a, b) = Rw[0].m[b][a];
+        A_NC.set_block(0, 6, R0t * A_NC.block(0, 6, 3, nc_dof));
+    }
+    // cmm_nc_, J_I_nc_, reference :2908-2916
+    Mat cm_rot6 = Mat::identity(6);
+    {
+        M3 skt = tr(sc);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) cm_rot6(3 + i, j) = skt.m[i][j];
+    }
+    cmm_nc = cm_rot6 * A_NC.block(0, 6, 6, nc_dof);
+    J_I_nc = lu_inverse(SI_nc_l) * cmm_nc;
+    // J_R, reference :2918-2929
+    J_R.set_zero(rsys, n);
+    for (int i = 0; i < vc_dof; i++) J_R(i, vc_joint[i]) = 1.0;
+    for (int i = 0; i < nc_dof; i++)
+        for (int k = 0; k < 6; k++) J_R(vc_dof + k, nc_joint[i]) = J_I_nc(k, i);
+    // A_R_inv assembled blockwise, reference :2936-2956
+    A_R_inv.set_zero(rsys, rsys);
+    Mat A_tr_temp(vc_dof, n);
+    for (int i = 0; i < vc_dof; i++) {
+        for (int j = 0; j < vc_dof; j++) A_R_inv(i, j) = A_inv(vc_joint[i], vc_joint[j]);
+        for (int j = 0; j < n; j++) A_tr_temp(i, j) = A_inv(vc_joint[i], j);
+    }
+    Mat tr_blk = A_tr_temp.right_cols(nc_dof) * J_I_nc.t();
+    A_R_inv.set_block(0, vc_dof, tr_blk);
+    A_R_inv.set_block(vc_dof, 0, tr_blk.t());
+    A_R_inv.set_block(vc_dof, vc_dof, J_R.bottom_rows(6) * A_inv * J_R.bottom_rows(6).t());
+    llt_solve_identity(A_R_inv, A_R);  // reference :2958
+    // reference :2971-2989 (block indexing assumes q order [base | contact chain | non-contact chain])
+    J_I_nc_inv_T = A_R.block(vc_dof, 0, 6, vc_dof) * A_inv.block(0, vc_dof, vc_dof, nc_dof) +
+                   A_R.block(vc_dof, vc_dof, 6, 6) * J_I_nc * A_inv.block(vc_dof, vc_dof, nc_dof, nc_dof);
+    N_I_nc = Mat::identity(nc_dof) - J_I_nc.t() * J_I_nc_inv_T;
+    G_R.set_zero(rsys, 1);
+    for (int i = 0; i < vc_dof; i++) G_R[i] = G[i];
+    G_R.set_block(vc_dof, 0, J_I_nc_inv_T * G.block(vc_dof, 0, nc_dof, 1));
+    J_CR.set_zero(contact_dof, rsys);
+    J_CR.set_block(0, 0, J_C.block(0, 0, contact_dof, vc_dof));
+}
+
+// ReducedCalcContactConstraint, reference src/dwbc.cpp:3077-3142
+int Robot::reduced_contact_constraint() {
+    const int c = contact_dof, cols = rsys;
+    J_CR.set_zero(c, rsys);
+    J_CR.set_block(0, 0, J_C.block(0, 0, c, vc_dof));
+    Mat Jl = J_CR.left_cols(c + 6);
+    Lambda_CR = lu_inverse(Jl * A_R_inv.block(0, 0, c + 6, c + 6) * Jl.t());
+    J_C_INV_T = (Lambda_CR * J_C) * A_inv;
+    J_CR_INV_T.set_zero(c, rsys);
+    J_CR_INV_T.set_block(0, 0, J_C_INV_T.block(0, 0, c, vc_dof));
+    J_CR_INV_T.set_block(0, vc_dof, J_C_INV_T.block(0, vc_dof, c, nc_dof) * J_I_nc.t());
+    N_C = Mat::identity(n) - J_C.t() * J_C_INV_T;
+    N_CR = Mat::identity(cols) - J_CR.t() * J_CR_INV_T;
+    A_R_inv_N_CR = A_R_inv * N_CR;
+    W_R = A_R_inv_N_CR.block(6, 6, cols - 6, cols - 6);
+    V2_R.set_zero(std::max(c - 6, 0), rmod);
+    NwJw_R.set_zero(rmod, rmod);
+    Cod f = cod_compute(W_R, COD_THRESHOLD);
+    W_R_inv = f.pinv;
+    reduced_ok = 1;
+    if (c > 6) {
+        const int rank = cols - c;  // force_rank, reference :3119
+        V2_R = f.Q.t().block(rank, 0, rmod - rank, rmod);
+        NwJw_R = V2_R.t() * lu_inverse(J_CR_INV_T.right_cols(cols - 6).top_rows(c - 6) * V2_R.t());
+        if (c - 6 != V2_R.r) reduced_ok = 0;
+    }
+    return reduced_ok;
+}
+
+// ReducedCalcGravCompensation, reference src/dwbc.cpp:3144-3150
+void Robot::reduced_grav() {
+    torque_grav_R = W_R_inv * (A_R_inv.bottom_rows(rmod) * (N_CR * G_R));
+    if (torque_grav.r != m) torque_grav.set_zero(m, 1);
+    for (int i = 0; i < rmod; i++) torque_grav[i] = torque_grav_R[i];
+    for (int i = 0; i < nc_dof; i++) torque_grav[co_dof + i] = G[vc_dof + i];
+    P_CR = J_CR_INV_T * G_R;
+}
+
+// CalculateJKT_R, reference src/wbd.cpp:220-226
+static void calculate_jkt_r(const Mat &J_task_R, const Mat &A_R_inv_N_CR, const Mat &W_R_inv, Mat &J_kt_R, Mat &lambda_R) {
+    lambda_R = lu_inverse(J_task_R * A_R_inv_N_CR * J_task_R.t());
+    Mat Q = (lambda_R * J_task_R * A_R_inv_N_CR).right_cols(J_task_R.c - 6);
+    J_kt_R = W_R_inv * Q.t() * cod_compute(Q * W_R_inv * Q.t(), COD_THRESHOLD).pinv;
+}
+
+// ReducedCalcTaskSpace, reference src/dwbc.cpp:3152-3253 + TaskSpace::CalcJKT_R src/task.cpp:95-142.
+// Returns 0 for the reference's "UNDEFINED TASK TYPE" (a level that mixes contact-chain and non-contact links).
+int Robot::reduced_task_space() {
+    A_inv_N_C = A_inv * N_C;
+    update_task_space();
+    J_base_R = point_jac(0, V3()).left_cols(rsys);
+    calculate_jkt_r(J_base_R, A_R_inv_N_CR, W_R_inv, J_base_R_kt, lambda_base_R);
+    int nch = 0;
+    for (auto &t : ts) {
+        if (t.custom) {
+            t.noncont = t.reduced = t.cmm = false;
+            if (t.J.left_cols(vc_dof).norm() > 1.0e-4) t.reduced = true;
+            if (t.J.right_cols(nc_dof).norm() > 1.0e-4) {
+                t.noncont = true;
+                t.nc_h = nch++;
+            }
+        } else {
+            for (auto &tl : t.links) {
+                if (tl.link == nb) t.cmm = true;
+                else if (has(co_link, tl.link)) t.reduced = true;
+                else {
+                    t.noncont = true;
+                    t.nc_h = nch++;
+                }
+            }
+        }
+    }
+    for (size_t i = 0; i < ts.size(); i++) {
+        Task &t = ts[i];
+        const int td = t.dof;
+        t.J_R.set_zero(td, rsys);
+        t.Lambda_R.set_zero(td, td);
+        t.Jkt_R.set_zero(rsys - 6, td);
+        t.force_on_nc.set_zero(6, 1);
+        if (t.cmm) {
+            t.J_R.set_block(0, 0, t.J.block(0, 0, td, vc_dof));
+            t.J_R.set_block(0, vc_dof, t.J.block(0, vc_dof, td, nc_dof) * J_I_nc_inv_T.t());
+            calculate_jkt_r(t.J_R, A_R_inv_N_CR, W_R_inv, t.Jkt_R, t.Lambda_R);
+            t.Lambda = t.Lambda_R;
+        } else if (t.reduced && !t.noncont) {
+            t.J_R.set_block(0, 0, t.J.block(0, 0, td, vc_dof));
+            calculate_jkt_r(t.J_R, A_R_inv_N_CR, W_R_inv, t.Jkt_R, t.Lambda_R);
+            t.Lambda = t.Lambda_R;
+        } else if (!t.reduced && t.noncont) {
+            t.Lambda = lu_inverse(t.J * A_inv_N_C * t.J.t());
+            t.J_NC = t.J.block(0, vc_dof, td, nc_dof);
+            t.J_R.set_block(0, 0, t.J.block(0, 0, td, vc_dof));
+            t.J_R.set_block(0, vc_dof, t.J.block(0, vc_dof, td, nc_dof) * J_I_nc_inv_T.t());
+        } else {
+            return 0;  // "UNDEFINED TASK TYPE"
+        }
+        if (i + 1 != ts.size()) {
+            if (!t.noncont) {
+                Mat prev = (i == 0) ? Mat::identity(rmod) : ts[i - 1].Null_R;
+                t.Null_R = prev * (Mat::identity(rmod) - t.Jkt_R * t.Lambda_R * t.J_R * A_R_inv_N_CR.right_cols(rmod));
+            } else {
+                if (i == 0) return 0;  // the reference reads ts_[-1]
+                t.Null_R = ts[i - 1].Null_R;
+            }
+        }
+    }
+    return 1;
+}
+
+// ReducedCalcTaskControlTorque(hqp=false), reference src/dwbc.cpp:3255-3446 (else-branch :3374-3417, expansion :3442-3443)
+int Robot::reduced_task_torque(bool hqp) {
+    if (hqp) return 0;  // CalcSingleTaskTorqueWithQP_R / _R_NC: not restated yet
+    torque_task_R.set_zero(rmod, 1);
+    torque_task.set_zero(m, 1);
+    torque_task_NC.set_zero(nc_dof, 1);
+    Mat R0(3, 3);
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) R0(a, b) = Rw[0].m[a][b];
+    for (size_t i = 0; i < ts.size(); i++) {
+        Task &t = ts[i];
+        t.torque_nc.set_zero(nc_dof, 1);
+        t.torque_h_R.set_zero(rmod, 1);
+        t.torque_null_h_nc.set_zero(nc_dof, 1);
+        t.torque_null_h_R.set_zero(rmod, 1);
+        if (t.noncont) {
+            if (i == 0) return 0;
+            Mat temp = t.J.t() * (t.Lambda * t.fstar);
+            t.torque_nc = temp.block(vc_dof, 0, nc_dof, 1);
+            t.force_on_nc.set_block(0, 0, temp.block(0, 0, 3, 1));
+            t.force_on_nc.set_block(3, 0, R0 * temp.block(3, 0, 3, 1));
+            t.torque_h_R.set_block(0, 0, J_base_R_kt.top_rows(co_dof) * t.force_on_nc);
+            t.torque_h_R.set_block(co_dof, 0, J_I_nc_inv_T * t.torque_nc);
+            if (t.nc_h == 0) {
+                t.torque_null_h_R = ts[i - 1].Null_R * t.torque_h_R;
+                t.torque_null_h_nc = t.torque_nc;
+            } else {
+                Task &p = ts[i - 1];
+                Mat null_force = p.Lambda * (p.J * (A_inv_N_C * (t.J.t() * (t.Lambda * t.fstar))));
+                Mat null_torque_h_r(rmod, 1);
+                temp = p.J.t() * null_force;
+                t.torque_null_h_nc = t.torque_nc - temp.block(vc_dof, 0, nc_dof, 1);
+                temp.set_block(3, 0, R0 * temp.block(3, 0, 3, 1));
+                null_torque_h_r.set_block(0, 0, t.torque_h_R.block(0, 0, co_dof, 1) - J_base_R_kt.top_rows(co_dof) * temp.block(0, 0, 6, 1));
+                null_torque_h_r.set_block(co_dof, 0, J_I_nc_inv_T * (t.torque_nc - p.J_NC.t() * null_force));
+                t.torque_null_h_R = p.Null_R * null_torque_h_r;
+            }
+        } else {
+            t.torque_h_R = t.Jkt_R * t.Lambda * t.fstar;
+            t.torque_null_h_R = (i == 0) ? t.torque_h_R : ts[i - 1].Null_R * t.torque_h_R;
+        }
+        torque_task_R = torque_task_R + t.torque_null_h_R;
+        torque_task_NC = torque_task_NC + t.torque_null_h_nc;
+    }
+    torque_task.set_block(0, 0, torque_task_R.block(0, 0, co_dof, 1));
+    torque_task.set_block(co_dof, 0, J_I_nc.t() * torque_task_R.block(co_dof, 0, 6, 1) + N_I_nc * torque_task_NC);
+    return 1;
+}
+
 }  // namespace orc
 
 // ------------------------------------------------------------------------------------------
@@ -866,6 +1197,16 @@ void orc_set_task(void *h, int level, const double *fstar, const double *J) {
 void orc_calc_grav(void *h) { ((Robot *)h)->calc_grav(); }
 int orc_calc_task_torque(void *h, int hqp) { return ((Robot *)h)->calc_task_torque(hqp != 0); }
 int orc_calc_redistribute(void *h, int hqp) { return ((Robot *)h)->calc_redistribute(hqp != 0); }
+// a9 reduced-dimension variant
+void orc_reduced_dynamics(void *h) { ((Robot *)h)->reduced_dynamics(); }
+int orc_reduced_contact_constraint(void *h) { return ((Robot *)h)->reduced_contact_constraint(); }
+void orc_reduced_grav(void *h) { ((Robot *)h)->reduced_grav(); }
+int orc_reduced_task_space(void *h) { return ((Robot *)h)->reduced_task_space(); }
+int orc_reduced_task_torque(void *h, int hqp) { return ((Robot *)h)->reduced_task_torque(hqp != 0); }
+void orc_reduced_dims(void *h, int *out) {
+    Robot *R = (Robot *)h;
+    out[0] = R->co_dof; out[1] = R->nc_dof; out[2] = R->vc_dof; out[3] = R->rsys; out[4] = R->rmod;
+}
 // getContactForce(command_torque) -> out [contact_dof]; returns contact_dof
 int orc_contact_force(void *h, const double *torque, double *out) {
     Robot *R = (Robot *)h;
@@ -913,6 +1254,16 @@ static const Mat *find_mat(Robot *R, const std::string &name, Mat &tmp) {
     if (name == "cf_redis_qp") return &R->cf_redis_qp;
     if (name == "redisA") return &R->redisA;
     if (name == "redisub") return &R->redisub;
+    {
+        const std::pair<const char *, const Mat *> red[] = {
+            {"A_NC", &R->A_NC}, {"SI_nc_b", &R->SI_nc_b}, {"SI_nc_l", &R->SI_nc_l}, {"cmm_nc", &R->cmm_nc}, {"J_I_nc", &R->J_I_nc}, {"J_R", &R->J_R},
+            {"A_R_inv", &R->A_R_inv}, {"A_R", &R->A_R}, {"J_I_nc_inv_T", &R->J_I_nc_inv_T}, {"N_I_nc", &R->N_I_nc}, {"G_R", &R->G_R}, {"J_CR", &R->J_CR},
+            {"Lambda_CR", &R->Lambda_CR}, {"J_CR_INV_T", &R->J_CR_INV_T}, {"N_CR", &R->N_CR}, {"A_R_inv_N_CR", &R->A_R_inv_N_CR}, {"W_R", &R->W_R},
+            {"W_R_inv", &R->W_R_inv}, {"V2_R", &R->V2_R}, {"NwJw_R", &R->NwJw_R}, {"P_CR", &R->P_CR}, {"torque_grav_R", &R->torque_grav_R},
+            {"J_base_R_kt", &R->J_base_R_kt}, {"torque_task_R", &R->torque_task_R}, {"torque_task_NC", &R->torque_task_NC}};
+        for (auto &e : red)
+            if (name == e.first) return e.second;
+    }
     if (name == "com_pos") {
         tmp.set_zero(3, 1);
         tmp[0] = R->com_pos.x; tmp[1] = R->com_pos.y; tmp[2] = R->com_pos.z;
@@ -948,6 +1299,11 @@ static const Mat *find_mat(Robot *R, const std::string &name, Mat &tmp) {
     if ((l = lvl("contact_qp")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].contact_qp;
     if ((l = lvl("torque_h")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].torque_h;
     if ((l = lvl("qpA")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].qpA;
+    if ((l = lvl("R_J_task")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].J_R;
+    if ((l = lvl("R_Lambda_task")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].Lambda_R;
+    if ((l = lvl("R_J_kt")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].Jkt_R;
+    if ((l = lvl("R_Null_task")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].Null_R;
+    if ((l = lvl("R_torque_h")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].torque_h_R;
     if ((l = lvl("qpub")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].qpub;
     return nullptr;
 }

@@ -68,6 +68,10 @@ def lib():
         L.orc_redis_eta.argtypes = [C.c_void_p]
         L.orc_redis_eta.restype = C.c_double
         L.orc_num_threads.restype = C.c_int
+        for f in ("orc_reduced_dynamics", "orc_reduced_contact_constraint", "orc_reduced_grav", "orc_reduced_task_space"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.orc_reduced_task_torque.argtypes = [C.c_void_p, C.c_int]
+        L.orc_reduced_dims.argtypes = [C.c_void_p, _ip]
         _lib = L
     return _lib
 
@@ -165,6 +169,28 @@ class OracleRobot:
 
     def calc_redistribute(self, hqp=True):
         return lib().orc_calc_redistribute(self.h, 1 if hqp else 0)
+
+    # ---- a9: reduced-dimension variant, reference src/dwbc.cpp:2752-3446 (call order of tests/sp_test/redu_dyn_test.cpp:262-267) ----
+    def reduced_dynamics(self):
+        lib().orc_reduced_dynamics(self.h)
+
+    def reduced_contact_constraint(self):
+        return lib().orc_reduced_contact_constraint(self.h)
+
+    def reduced_grav(self):
+        lib().orc_reduced_grav(self.h)
+        return self.get("torque_grav")[:, 0]
+
+    def reduced_task_space(self):
+        return lib().orc_reduced_task_space(self.h)
+
+    def reduced_task_torque(self, hqp=False):
+        return lib().orc_reduced_task_torque(self.h, 1 if hqp else 0)
+
+    def reduced_dims(self):
+        out = (C.c_int * 5)()
+        lib().orc_reduced_dims(self.h, out)
+        return dict(zip(("co_dof", "nc_dof", "vc_dof", "reduced_system_dof", "reduced_model_dof"), out))
 
     def contact_force(self, torque):
         """getContactForce(command_torque), reference src/dwbc.cpp:891-896"""

@@ -1,0 +1,86 @@
+"""a9 reduced-dimension variant of the oracle.  The reference holds no goldens for it; its own check is the printed
+"reduced torques == full-model torques" similarity (reference tests/sp_test/redu_dyn_test.cpp:323-360, threshold 1e-4).
+The oracle restates src/dwbc.cpp:2752-3446 literally and must satisfy that property to 1e-9 on the golden
+configurations and on synthetic states; structural facts from SURVEY.md Appendix B are checked as well."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.common import *
+
+
+def reduced_tasks(ref):
+    """The hierarchy of reference tests/sp_test/redu_dyn_test.cpp:97-101: COM position / pelvis rotation /
+    upper-body rotation / left-hand 6D (COM task, contact-chain task, two non-contact tasks)."""
+    ref.add_task(0, orc.TASK_LINK_POSITION, "COM")
+    ref.add_task(1, orc.TASK_LINK_ROTATION, "pelvis_link")
+    ref.add_task(2, orc.TASK_LINK_ROTATION, "upperbody_link")
+    ref.add_task(3, orc.TASK_LINK_6D, "L_Wrist2_Link")
+
+
+def full_and_reduced(q, qd, flags, fstars):
+    out = []
+    for reduced in (False, True):
+        ref = orc.OracleRobot(URDF)
+        ref.add_contact(LEFT_FOOT, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+        ref.add_contact(RIGHT_FOOT, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+        reduced_tasks(ref)
+        ref.update_kinematics(q, qd)
+        ref.set_contact(*flags)
+        for l, f in enumerate(fstars):
+            ref.set_task(l, f)
+        if not reduced:
+            assert ref.calc_contact_constraint() == 1
+            ref.calc_grav()
+            assert ref.calc_task_torque(hqp=False) == 1
+        else:
+            ref.reduced_dynamics()
+            assert ref.reduced_contact_constraint() == 1
+            ref.reduced_grav()
+            assert ref.reduced_task_space() == 1
+            assert ref.reduced_task_torque(hqp=False) == 1
+        out.append(ref)
+    return out
+
+
+FS = [np.array([0.3, 0.6, -0.3]), np.array([0.1, -0.1, 0.1]), np.array([-0.1, 0.1, -0.1]), np.array([0.05, 0.1, -0.05, 0.05, -0.05, 0.05])]
+
+
+@pytest.mark.parametrize("case", [1, 2])
+def test_reduced_equals_full_on_golden_configurations(case):
+    full, red = full_and_reduced(np.array(Q_CASE[case]), np.zeros(39), (1, 1), FS)
+    d = red.reduced_dims()
+    assert d == dict(co_dof=12, nc_dof=21, vc_dof=18, reduced_system_dof=24, reduced_model_dof=18)  # reference src/dwbc.cpp:2818-2823
+    assert abs(red.get("SI_nc_b")[0, 0] - 42.6195) < 1e-3  # nc-chain mass, reference tests/dwbc_test.cpp:664
+    assert np.linalg.matrix_rank(red.get("W_R"), tol=1e-8) == 12
+    assert relerr(red.get("A_R") @ red.get("A_R_inv"), np.eye(24)) < 1e-10
+    assert relerr(red.get("J_R") @ full.get("A_inv") @ red.get("J_R").T, red.get("A_R_inv")) < 1e-12
+    assert relerr(red.get("Lambda_CR"), full.get("Lambda_contact")) < 1e-9
+    assert relerr(red.get("torque_grav")[:, 0], full.get("torque_grav")[:, 0]) < 1e-9
+    assert relerr(red.get("torque_task")[:, 0], full.get("torque_task")[:, 0]) < 1e-9
+
+
+def test_reduced_equals_full_on_synthetic_states():
+    B = 6
+    q, qd, rng = synth_states(B, 20243)
+    for b in range(B):
+        fs = [0.5 * rng.standard_normal(3), rng.standard_normal(3), rng.standard_normal(3), rng.standard_normal(6)]
+        flags = (1, 1) if b != 3 else (1, 0)  # left-foot single support: co 6..11, nc 12..38 (the layout the reference supports)
+        full, red = full_and_reduced(q[b], qd[b], flags, fs)
+        if b == 3:
+            assert red.reduced_dims()["reduced_system_dof"] == 18
+        assert relerr(red.get("torque_grav")[:, 0], full.get("torque_grav")[:, 0]) < 1e-9
+        assert relerr(red.get("torque_task")[:, 0], full.get("torque_task")[:, 0]) < 1e-8
+
+
+def test_undefined_task_type_is_rejected():
+    """A level mixing a contact-chain link and a non-contact link is the reference's "UNDEFINED TASK TYPE" (src/task.cpp:129-136)."""
+    ref = orc.OracleRobot(URDF)
+    configure_oracle(ref, 2)
+    ref.update_kinematics(np.array(Q_CASE[1]), np.zeros(39))
+    ref.set_contact(1, 1)
+    for l, t in enumerate((3, 6, 21)):
+        ref.set_task(l, np.zeros(t), posture_selector() if l == 2 else None)
+    ref.reduced_dynamics()
+    ref.reduced_contact_constraint()
+    assert ref.reduced_task_space() == 0
