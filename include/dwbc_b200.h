@@ -172,6 +172,53 @@ int dwbc_batch_get_contact_force(dwbc_batch_t *b, const double *torque_dev, doub
 /* getZMP(contact_force)   reference src/dwbc.cpp:898-939.  cf_dev [B x cmax] (stacked active contacts), zmp_dev [B x 3]. */
 int dwbc_batch_get_zmp(dwbc_batch_t *b, const double *cf_dev, double *zmp_dev, void *stream);
 
+/* ---- a9: reduced-dimension variant (Ahn 2024), reference src/dwbc.cpp:2752-3446, in the call order of
+ * reference tests/sp_test/redu_dyn_test.cpp:262-267: update_kinematics -> set_contact -> reduced_dynamics ->
+ * reduced_calc_contact_constraint -> set_task -> reduced_solve.
+ * The non-contact chain is condensed to a 6-dof body: n 39 -> 24 and m 33 -> 18 in double support.  As in the reference
+ * the q order [base | contact chain | non-contact chain] must be contiguous (double support or left-foot single support),
+ * and one call handles ONE contact pattern: `pattern_host` [ncontact] gives the flags every state is expected to show;
+ * states with other flags get status 0.  Levels must be ordered COM / contact-chain tasks first, then non-contact tasks;
+ * a level mixing both is the reference's "UNDEFINED TASK TYPE" and is rejected (DWBC_ERR_ARG). */
+/* ReducedDynamicsCalculate()   reference src/dwbc.cpp:2752-2989 */
+int dwbc_batch_reduced_dynamics(dwbc_batch_t *b, const uint8_t *pattern_host, void *stream);
+/* ReducedCalcContactConstraint()   reference src/dwbc.cpp:3077-3142 */
+int dwbc_batch_reduced_calc_contact_constraint(dwbc_batch_t *b, void *stream);
+/* ReducedCalcGravCompensation (DWBC_SOLVE_GRAV) + ReducedCalcTaskSpace + ReducedCalcTaskControlTorque(hqp=false)
+ * (DWBC_SOLVE_TASK)   reference src/dwbc.cpp:3144-3446.  Outputs as dwbc_batch_solve (full 33-joint torques).
+ * DWBC_SOLVE_HQP / DWBC_SOLVE_REDIST (CalcSingleTaskTorqueWithQP_R[_NC], CalcContactRedistributeR) are not built yet
+ * and return DWBC_ERR_ARG. */
+int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *tau_task_dev, double *tau_contact_dev,
+                             int32_t *status_dev, void *stream);
+/* co_dof, nc_dof, vc_dof, reduced_system_dof_, reduced_model_dof_ of the current pattern (reference src/dwbc.cpp:2818-2823) */
+int dwbc_batch_reduced_dims(const dwbc_batch_t *b, int *co_dof, int *nc_dof, int *vc_dof, int *reduced_system_dof, int *reduced_model_dof);
+/* public RobotData fields of the reduced variant */
+enum {
+    DWBC_RMAT_A_R_INV = 0,    /* A_R_inv        rn x rn */
+    DWBC_RMAT_A_R,            /* A_R            rn x rn */
+    DWBC_RMAT_J_I_NC,         /* J_I_nc_        6 x nc */
+    DWBC_RMAT_J_I_NC_INV_T,   /* J_I_nc_inv_T   6 x nc */
+    DWBC_RMAT_G_R,            /* G_R            rn x 1 */
+    DWBC_RMAT_J_CR,           /* J_CR           cmax x rn */
+    DWBC_RMAT_LAMBDA_CR,      /* Lambda_CR      cmax x cmax */
+    DWBC_RMAT_J_CR_INV_T,     /* J_CR_INV_T     cmax x rn */
+    DWBC_RMAT_A_R_INV_N_CR,   /* A_R_inv_N_CR   rn x rn */
+    DWBC_RMAT_W_R,            /* W_R            rm x rm */
+    DWBC_RMAT_W_R_INV,        /* W_R_inv        rm x rm */
+    DWBC_RMAT_NWJW_R,         /* NwJw_R         rm x rmax */
+    DWBC_RMAT_P_CR,           /* P_CR           cmax x 1 */
+    DWBC_RMAT_TORQUE_GRAV_R,  /* torque_grav_R_ rm x 1 */
+    DWBC_RMAT_TORQUE_TASK_R,  /* torque_task_R_ rm x 1 */
+    DWBC_RMAT_J_BASE_R_KT,    /* J_base_R_kt_   rm x 6 */
+    DWBC_RMAT_SI_NC,          /* [mass_nc_, com_pos_nc_ (3), inertia_nc_ (9, row-major)]  13 x 1 */
+    /* per hierarchy level */
+    DWBC_RMAT_J_TASK_R = 64,  /* ts_[l].J_task_R_      t x rn  (COM / contact-chain levels) */
+    DWBC_RMAT_LAMBDA_TASK,    /* ts_[l].Lambda_task_   t x t */
+    DWBC_RMAT_J_KT_R,         /* ts_[l].J_kt_R_        rm x t  (COM / contact-chain levels) */
+    DWBC_RMAT_NULL_TASK_R     /* ts_[l].Null_task_R_   rm x rm (COM / contact-chain levels) */
+};
+int dwbc_batch_get_reduced_matrix(dwbc_batch_t *b, int which, int level, double *out_dev, int *rows, int *cols, void *stream);
+
 /* ---- whole cycle with HOST buffers (pinned or pageable): H2D, all stages, D2H, synchronised on return.
  * This is what the RobotData shim, the pybind bridge and bench.py's end-to-end timing call.
  * fstar_host: concatenation over levels of [B x t_l] blocks. flags_host [B x ncontact]. */
@@ -187,7 +234,7 @@ int dwbc_probe_fp64(int device, double seconds, double *tflops);
  * recorded on the launch stream (no host synchronisation is added to the hot path).  dwbc_batch_get_kernel_times
  * synchronises the pending events and returns, per DWBC_K_* kernel, the summed duration in ms (only launches made while
  * profiling was on) and the launch count since the last reset.  bench.py's roofline numbers come from here. */
-enum { DWBC_K_RBD = 0, DWBC_K_AINV, DWBC_K_CONTACT_JAC, DWBC_K_CONTACT_DYN, DWBC_K_TASK, DWBC_K_HQP, DWBC_K_EXPORT, DWBC_K_POST, DWBC_K_COUNT };
+enum { DWBC_K_RBD = 0, DWBC_K_AINV, DWBC_K_CONTACT_JAC, DWBC_K_CONTACT_DYN, DWBC_K_TASK, DWBC_K_HQP, DWBC_K_EXPORT, DWBC_K_POST, DWBC_K_REDUCED, DWBC_K_COUNT };
 int dwbc_batch_set_profiling(dwbc_batch_t *b, int enable);
 int dwbc_batch_get_kernel_times(dwbc_batch_t *b, double *ms_sum, long long *launches, int reset);
 const char *dwbc_kernel_name(int k);

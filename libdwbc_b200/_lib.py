@@ -59,6 +59,11 @@ def declare(L):
     L.dwbc_batch_get_kernel_times.argtypes = [vp, _dp, C.POINTER(C.c_longlong), C.c_int]
     L.dwbc_kernel_name.restype = C.c_char_p
     L.dwbc_kernel_name.argtypes = [C.c_int]
+    L.dwbc_batch_reduced_dynamics.argtypes = [vp, vp, vp]
+    L.dwbc_batch_reduced_calc_contact_constraint.argtypes = [vp, vp]
+    L.dwbc_batch_reduced_solve.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
+    L.dwbc_batch_reduced_dims.argtypes = [vp, _ip, _ip, _ip, _ip, _ip]
+    L.dwbc_batch_get_reduced_matrix.argtypes = [vp, C.c_int, C.c_int, vp, _ip, _ip, vp]
     return L
 
 
@@ -69,6 +74,8 @@ EXPORTS = [
     "dwbc_batch_update_kinematics", "dwbc_batch_set_contact", "dwbc_batch_calc_contact_constraint", "dwbc_batch_set_task", "dwbc_batch_solve",
     "dwbc_batch_get_matrix", "dwbc_batch_get_active_set", "dwbc_batch_cycle_host", "dwbc_probe_fp64", "dwbc_batch_get_qp_iterations",
     "dwbc_batch_set_profiling", "dwbc_batch_get_kernel_times", "dwbc_kernel_name", "dwbc_batch_get_contact_force", "dwbc_batch_get_zmp",
+    "dwbc_batch_reduced_dynamics", "dwbc_batch_reduced_calc_contact_constraint", "dwbc_batch_reduced_solve", "dwbc_batch_reduced_dims",
+    "dwbc_batch_get_reduced_matrix",
 ]
 
 _lib = None

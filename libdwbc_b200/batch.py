@@ -33,6 +33,14 @@ _MATS = {
     "contact_qp": (69, True), "torque_h": (70, True),
 }
 
+# reduced-dimension variant: name -> (matrix id, per-level?)   (DWBC_RMAT_* of include/dwbc_b200.h)
+_RMATS = {
+    "A_R_inv": (0, False), "A_R": (1, False), "J_I_nc": (2, False), "J_I_nc_inv_T": (3, False), "G_R": (4, False), "J_CR": (5, False),
+    "Lambda_CR": (6, False), "J_CR_INV_T": (7, False), "A_R_inv_N_CR": (8, False), "W_R": (9, False), "W_R_inv": (10, False),
+    "NwJw_R": (11, False), "P_CR": (12, False), "torque_grav_R": (13, False), "torque_task_R": (14, False), "J_base_R_kt": (15, False),
+    "SI_nc": (16, False), "J_task_R": (64, True), "Lambda_task": (65, True), "J_kt_R": (66, True), "Null_task_R": (67, True),
+}
+
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
@@ -215,14 +223,42 @@ class RobotDataBatch:
         self._ck(self.L.dwbc_batch_solve(self._h, int(stages), be.ptr(tg), be.ptr(tt), be.ptr(tc), be.ptr(st), be.stream()))
         return tg, tt, tc, st
 
+    # ---- a9: reduced-dimension variant (reference src/dwbc.cpp:2752-3446; call order of tests/sp_test/redu_dyn_test.cpp:262-267) ----
+    def reduced_dynamics_calculate(self, pattern):
+        """ReducedDynamicsCalculate for the contact pattern (one 0/1 flag per registered contact) every state shows."""
+        pat = (C.c_uint8 * max(self.ncontact, 1))(*[1 if f else 0 for f in pattern])
+        self._ck(self.L.dwbc_batch_reduced_dynamics(self._h, pat, self.be.stream()))
+        d = [C.c_int() for _ in range(5)]
+        self._ck(self.L.dwbc_batch_reduced_dims(self._h, *[C.byref(x) for x in d]))
+        self.co_dof, self.nc_dof, self.vc_dof, self.reduced_system_dof_, self.reduced_model_dof_ = [x.value for x in d]
+
+    def reduced_calc_contact_constraint(self):
+        self._ck(self.L.dwbc_batch_reduced_calc_contact_constraint(self._h, self.be.stream()))
+
+    def reduced_solve(self, stages=SOLVE_GRAV | SOLVE_TASK, out=None):
+        """ReducedCalcGravCompensation + ReducedCalcTaskSpace + ReducedCalcTaskControlTorque(hqp=false);
+        returns (torque_grav, torque_task, torque_contact, status) like solve()."""
+        be = self.be
+        B, m = self.batch, self.model_dof_
+        if out is None:
+            out = (be.empty((B, m)), be.empty((B, m)), be.empty((B, m)), be.empty((B,), "i4"))
+        tg, tt, tc, st = out
+        self._ck(self.L.dwbc_batch_reduced_solve(self._h, int(stages), be.ptr(tg), be.ptr(tt), be.ptr(tc), be.ptr(st), be.stream()))
+        return tg, tt, tc, st
+
+    def get_reduced(self, name, level=0):
+        return self._get(self.L.dwbc_batch_get_reduced_matrix, _RMATS[name][0], level)
+
     def get(self, name, level=0):
         """Public RobotData field `name` for all states: tensor [B, rows, cols] (vectors: [B, rows])."""
+        return self._get(self.L.dwbc_batch_get_matrix, _MATS[name][0], level)
+
+    def _get(self, fn, mid, level):
         be = self.be
-        mid, per_level = _MATS[name]
         r, c = C.c_int(), C.c_int()
-        self._ck(self.L.dwbc_batch_get_matrix(self._h, mid, int(level), None, C.byref(r), C.byref(c), be.stream()))
+        self._ck(fn(self._h, mid, int(level), None, C.byref(r), C.byref(c), be.stream()))
         buf = be.empty((self.batch, c.value, r.value))  # column-major per state
-        self._ck(self.L.dwbc_batch_get_matrix(self._h, mid, int(level), be.ptr(buf), None, None, be.stream()))
+        self._ck(fn(self._h, mid, int(level), be.ptr(buf), None, None, be.stream()))
         out = buf.transpose(1, 2) if hasattr(buf, "transpose") and not isinstance(buf, np.ndarray) else np.swapaxes(buf, 1, 2)
         if c.value == 1:
             out = out[:, :, 0]
@@ -275,7 +311,7 @@ class RobotDataBatch:
 
     def kernel_times(self, reset=True):
         """{kernel name: (summed ms while profiling was on, launches since the last reset)}"""
-        K = 8
+        K = 9
         ms = (C.c_double * K)()
         cnt = (C.c_longlong * K)()
         self._ck(self.L.dwbc_batch_get_kernel_times(self._h, ms, cnt, 1 if reset else 0))

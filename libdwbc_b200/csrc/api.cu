@@ -2,6 +2,7 @@
 // checking, workspace ownership, kernel launches.  There is deliberately no CPU code path for the math.
 #include "../../include/dwbc_b200.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -14,6 +15,7 @@
 #include "kernels_contact.cuh"
 #include "kernels_hqp.cuh"
 #include "kernels_post.cuh"
+#include "kernels_reduced.cuh"
 #include "kernels_task.cuh"
 #include "model.h"
 
@@ -53,6 +55,16 @@ struct dwbc_batch {
     std::vector<cudaEvent_t> free_events;
     double k_ms[DWBC_K_COUNT] = {0};
     long long k_launches[DWBC_K_COUNT] = {0};
+    // a9 reduced-dimension variant: second workspace (n = rn, m = rm) + extras
+    Work wr;
+    ReducedX rx;
+    ReducedCfg rc;
+    BatchCfg cfgR;
+    BatchCfg *d_cfgR = nullptr;
+    std::vector<void *> red_allocs, red_task_allocs;
+    int red_rn = 0;
+    std::string red_task_sig;
+    bool have_red_dyn = false, have_red_cc = false;
 };
 
 namespace {
@@ -203,6 +215,9 @@ dwbc_batch_t *dwbc_batch_create(const dwbc_model_t *m, int batch, int device) {
     b->device = device;
     std::memset(&b->cfg, 0, sizeof(b->cfg));
     std::memset(&b->w, 0, sizeof(b->w));
+    std::memset(&b->wr, 0, sizeof(b->wr));
+    std::memset(&b->rx, 0, sizeof(b->rx));
+    std::memset(&b->rc, 0, sizeof(b->rc));
     cudaDeviceProp prop;
     if (cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) b->sm_count = prop.multiProcessorCount;
     Work &w = b->w;
@@ -234,6 +249,8 @@ void dwbc_batch_destroy(dwbc_batch_t *b) {
     cudaSetDevice(b->device);
     for (void *p : b->allocs) cudaFree(p);
     for (void *p : b->task_allocs) cudaFree(p);
+    for (void *p : b->red_allocs) cudaFree(p);
+    for (void *p : b->red_task_allocs) cudaFree(p);
     if (b->d_fstar) cudaFree(b->d_fstar);
     for (auto &p : b->pending) {
         cudaEventDestroy(p.e0);
@@ -367,6 +384,7 @@ int dwbc_batch_update_kinematics(dwbc_batch_t *b, const double *q_dev, const dou
     CK(cudaGetLastError());
     b->have_kin = true;
     b->have_contact = b->have_cc = false;
+    b->have_red_dyn = b->have_red_cc = false;
     return DWBC_OK;
 }
 
@@ -386,6 +404,7 @@ int dwbc_batch_set_contact(dwbc_batch_t *b, const uint8_t *flags_dev, void *stre
     CK(cudaGetLastError());
     b->have_contact = true;
     b->have_cc = false;
+    b->have_red_dyn = b->have_red_cc = false;
     return DWBC_OK;
 }
 
@@ -444,7 +463,7 @@ int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *
         size_t smem = sizeof(double) * L.total;
         CK(cudaFuncSetAttribute(task_space_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelScope ks(b, DWBC_K_TASK, st);
-        DWBC_LAUNCH(task_space_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0, tmax);
+        DWBC_LAUNCH(task_space_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0, tmax, 0);
     } else {
         CK(cudaMemsetAsync(b->w.tau_task, 0, sizeof(double) * B * m, st));
         CK(cudaMemsetAsync(b->w.tau_contact, 0, sizeof(double) * B * m, st));
@@ -617,7 +636,7 @@ int dwbc_batch_get_kernel_times(dwbc_batch_t *b, double *ms_sum, long long *laun
 
 const char *dwbc_kernel_name(int k) {
     static const char *names[DWBC_K_COUNT] = {"rbd_kernel", "ainv_kernel", "contact_jacobian_kernel", "contact_dynamics_kernel",
-                                              "task_space_kernel", "hqp_kernel", "export_kernels", "post_kernels"};
+                                              "task_space_kernel", "hqp_kernel", "export_kernels", "post_kernels", "reduced_kernels"};
     return (k >= 0 && k < DWBC_K_COUNT) ? names[k] : nullptr;
 }
 
@@ -666,6 +685,307 @@ int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, con
     if (tau_contact_host) CK(cudaMemcpyAsync(tau_contact_host, b->d_tc, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st));
     if (status_host) CK(cudaMemcpyAsync(status_host, b->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return DWBC_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ a9: reduced-dimension variant
+namespace {
+void free_reduced_tasks(dwbc_batch *b) {
+    for (void *p : b->red_task_allocs) cudaFree(p);
+    b->red_task_allocs.clear();
+    b->red_task_sig.clear();
+    for (int l = 0; l < MAX_LEVELS; l++) {
+        b->wr.Jt[l] = b->wr.Lamt[l] = b->wr.Jkt[l] = b->wr.Null[l] = b->wr.Ntq[l] = b->wr.torque_h[l] = nullptr;
+        b->rx.JtR[l] = b->rx.LamNC[l] = nullptr;
+    }
+}
+void free_reduced(dwbc_batch *b) {
+    free_reduced_tasks(b);
+    for (void *p : b->red_allocs) cudaFree(p);
+    b->red_allocs.clear();
+    b->red_rn = 0;
+    b->d_cfgR = nullptr;
+}
+int alloc_reduced(dwbc_batch *b, int rn, int rm) {
+    if (b->red_rn == rn) return DWBC_OK;
+    free_reduced(b);
+    Work &r = b->wr;
+    const Work &w = b->w;
+    r = Work();
+    std::memset(&r, 0, sizeof(r));
+    r.B = w.B; r.n = rn; r.m = rm; r.nb = w.nb;
+    r.A = w.A; r.Bnl = w.Bnl; r.pose = w.pose; r.com = w.com; r.linkvel = w.linkvel; r.cdof = w.cdof; r.cidx = w.cidx;  // shared with the full model
+    const size_t B = w.B, n = rn, m = rm;
+    std::vector<void *> *L = &b->red_allocs;
+    ReducedX &x = b->rx;
+    bool ok = dev_alloc(b, &r.Ainv, B * n * n, L) && dev_alloc(b, &r.G, B * n, L) && dev_alloc(b, &r.Jc, B * CMAX * n, L) &&
+              dev_alloc(b, &r.Lam, B * CMAX * CMAX, L) && dev_alloc(b, &r.Jbar, B * CMAX * n, L) && dev_alloc(b, &r.AinvNc, B * n * n, L) &&
+              dev_alloc(b, &r.W, B * m * m, L) && dev_alloc(b, &r.Winv, B * m * m, L) && dev_alloc(b, &r.V2, B * RMAX * m, L) &&
+              dev_alloc(b, &r.NwJw, B * m * RMAX, L) && dev_alloc(b, &r.PC, B * CMAX, L) && dev_alloc(b, &r.tau_grav, B * m, L) &&
+              dev_alloc(b, &r.tau_task, B * m, L) && dev_alloc(b, &r.tau_contact, B * m, L) && dev_alloc(b, &r.status, B, L) &&
+              dev_alloc(b, &x.JI, B * 6 * NCMAX, L) && dev_alloc(b, &x.JIinvT, B * 6 * NCMAX, L) && dev_alloc(b, &x.SInc, B * 16, L) &&
+              dev_alloc(b, &x.AR, B * n * n, L) && dev_alloc(b, &x.Jbkt, B * m * 6, L) && dev_alloc(b, &x.tauR, B * m, L) &&
+              dev_alloc(b, &x.tauNC, B * NCMAX, L) && dev_alloc(b, &b->d_cfgR, 1, L);
+    if (!ok) {
+        free_reduced(b);
+        return DWBC_ERR_CUDA;
+    }
+    b->red_rn = rn;
+    return DWBC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int dwbc_batch_reduced_dynamics(dwbc_batch_t *b, const uint8_t *pattern_host, void *stream) {
+    if (!b || !pattern_host) return fail(DWBC_ERR_ARG, "reduced_dynamics: null argument");
+    if (!b->have_contact) return fail(DWBC_ERR_ORDER, "reduced_dynamics: call update_kinematics and set_contact first");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const DevModel &md = b->hm.dev;
+    // index sets of the pattern, reference src/dwbc.cpp:2755-2823
+    ReducedCfg rc;
+    std::memset(&rc, 0, sizeof(rc));
+    std::vector<char> co(md.nb, 0);
+    co[0] = 1;
+    for (int i = 0; i < b->cfg.ncontact; i++) {
+        if (!pattern_host[i]) continue;
+        if (rc.ncontact_active >= MAX_ACTIVE_CONTACTS) return fail(DWBC_ERR_LIMIT, "reduced_dynamics: too many active contacts in the pattern");
+        rc.pattern[rc.ncontact_active++] = i;
+        for (int l = b->cfg.contacts[i].link; l != 0; l = md.parent[l]) co[l] = 1;
+    }
+    if (rc.ncontact_active == 0) return fail(DWBC_ERR_ARG, "reduced_dynamics: the pattern has no active contact");
+    int co_dof = 0;
+    for (int l = 1; l < md.nb; l++) co_dof += co[l];
+    for (int l = 1; l < md.nb; l++)
+        if ((co[l] != 0) != (l <= co_dof))
+            return fail(DWBC_ERR_ARG,
+                        "reduced_dynamics: the contact-chain joints are not a prefix of q (the reference's block indexing needs [base | contact chain | "
+                        "non-contact chain]: double support or left-foot single support)");
+    rc.co_dof = co_dof;
+    rc.vc_dof = co_dof + 6;
+    rc.nc_dof = md.n - rc.vc_dof;
+    rc.rm = co_dof + 6;
+    rc.rn = rc.rm + 6;
+    for (int l = 0; l < md.nb; l++)
+        if (!co[l]) rc.nc_mask |= 1ull << l;
+    if (rc.nc_dof <= 0) return fail(DWBC_ERR_ARG, "reduced_dynamics: empty non-contact chain");
+    int rcode = alloc_reduced(b, rc.rn, rc.rm);
+    if (rcode) return rcode;
+    b->rc = rc;
+    {
+        size_t smem = sizeof(double) * reduced_dyn_smem_doubles(rc.rn, rc.nc_dof);
+        CK(cudaFuncSetAttribute(reduced_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KernelScope ks(b, DWBC_K_REDUCED, st);
+        DWBC_LAUNCH(reduced_dynamics_kernel, b->B, TEAM, smem, st, b->d_model, b->w, b->wr, b->rx, b->rc);
+    }
+    CK(cudaGetLastError());
+    b->have_red_dyn = true;
+    b->have_red_cc = false;
+    return DWBC_OK;
+}
+
+int dwbc_batch_reduced_calc_contact_constraint(dwbc_batch_t *b, void *stream) {
+    if (!b) return fail(DWBC_ERR_ARG, "reduced_calc_contact_constraint: null handle");
+    if (!b->have_red_dyn) return fail(DWBC_ERR_ORDER, "reduced_calc_contact_constraint: call reduced_dynamics first");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ContactSmem L(b->wr.n, b->wr.m);
+    size_t smem = sizeof(double) * L.total;
+    CK(cudaFuncSetAttribute(contact_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        KernelScope ks(b, DWBC_K_CONTACT_DYN, st);
+        DWBC_LAUNCH(contact_dynamics_kernel, b->B, TEAM, smem, st, b->d_model, b->wr);
+    }
+    CK(cudaGetLastError());
+    b->have_red_cc = true;
+    return DWBC_OK;
+}
+
+int dwbc_batch_reduced_dims(const dwbc_batch_t *b, int *co_dof, int *nc_dof, int *vc_dof, int *rsys, int *rmod) {
+    if (!b || !b->have_red_dyn) return fail(DWBC_ERR_ORDER, "reduced_dims: call reduced_dynamics first");
+    if (co_dof) *co_dof = b->rc.co_dof;
+    if (nc_dof) *nc_dof = b->rc.nc_dof;
+    if (vc_dof) *vc_dof = b->rc.vc_dof;
+    if (rsys) *rsys = b->rc.rn;
+    if (rmod) *rmod = b->rc.rm;
+    return DWBC_OK;
+}
+
+int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *tau_task_dev, double *tau_contact_dev, int32_t *status_dev,
+                             void *stream) {
+    if (!b) return fail(DWBC_ERR_ARG, "reduced_solve: null handle");
+    if (!b->have_red_cc) return fail(DWBC_ERR_ORDER, "reduced_solve: call reduced_calc_contact_constraint first");
+    if (stages & (DWBC_SOLVE_HQP | DWBC_SOLVE_REDIST | DWBC_SOLVE_REDIST_ANALYTIC))
+        return fail(DWBC_ERR_ARG, "reduced_solve: the QP branches of the reduced variant (CalcSingleTaskTorqueWithQP_R, CalcContactRedistributeR) are not built yet");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rcode = upload_cfg(b, st);
+    if (rcode) return rcode;
+    const DevModel &md = b->hm.dev;
+    const size_t B = b->B, m = b->w.m;
+    ReducedCfg &rc = b->rc;
+    Work &wr = b->wr;
+    const int rn = rc.rn, rm = rc.rm;
+    rc.nlevels = 0;
+    rc.k_contact = 0;
+    int tmax = 1, tmaxR = 1;
+    CK(cudaMemsetAsync(wr.tau_task, 0, sizeof(double) * B * rm, st));
+    if (stages & DWBC_SOLVE_TASK) {
+        const BatchCfg &c = b->cfg;
+        if (c.nlevels == 0) return fail(DWBC_ERR_ORDER, "reduced_solve: no task registered");
+        for (int l = 0; l < c.nlevels; l++)
+            if (!b->w.fstar[l]) return fail(DWBC_ERR_ORDER, "reduced_solve: set_task has not been called for every level");
+        rcode = alloc_tasks(b);
+        if (rcode) return rcode;
+        // task classification, reference src/dwbc.cpp:3166-3227
+        std::string sig = std::to_string(rn);
+        for (int l = 0; l < c.nlevels; l++) {
+            const TaskCfg &t = c.tasks[l];
+            bool cmm = false, red = false, non = false;
+            if (t.custom) {
+                if (b->w.jcustom_per_state[l])
+                    return fail(DWBC_ERR_ARG, "reduced_solve: a custom task with per-state Jacobians cannot be classified for the whole batch");
+                std::vector<double> J((size_t)t.dof * md.n);
+                CK(cudaMemcpyAsync(J.data(), b->w.jcustom[l], sizeof(double) * J.size(), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                double nl2 = 0.0, nr2 = 0.0;
+                for (int j = 0; j < md.n; j++)
+                    for (int i = 0; i < t.dof; i++) (j < rc.vc_dof ? nl2 : nr2) += J[i + (size_t)j * t.dof] * J[i + (size_t)j * t.dof];
+                red = std::sqrt(nl2) > 1.0e-4;
+                non = std::sqrt(nr2) > 1.0e-4;
+            } else {
+                for (int k = 0; k < t.link_count; k++) {
+                    const int link = c.tlinks[t.link_start + k].link;
+                    if (link == md.nb) cmm = true;
+                    else if (!((rc.nc_mask >> link) & 1ull)) red = true;
+                    else non = true;
+                }
+            }
+            int cls;
+            if (cmm) cls = 0;  // src/task.cpp:105: cmm_task wins
+            else if (red && !non) cls = 1;
+            else if (!red && non) cls = 2;
+            else return fail(DWBC_ERR_ARG, "UNDEFINED TASK TYPE (a level mixes contact-chain and non-contact links, reference src/task.cpp:129-136)");
+            rc.cls[l] = cls;
+            sig += "," + std::to_string(t.dof) + ":" + std::to_string(cls);
+            tmax = t.dof > tmax ? t.dof : tmax;
+        }
+        rc.nlevels = c.nlevels;
+        int k = 0;
+        while (k < c.nlevels && rc.cls[k] != 2) k++;
+        for (int l = k; l < c.nlevels; l++)
+            if (rc.cls[l] != 2) return fail(DWBC_ERR_ARG, "reduced_solve: COM / contact-chain levels must precede the non-contact levels");
+        if (k == 0) return fail(DWBC_ERR_ARG, "reduced_solve: the first level cannot be a non-contact task (the reference reads ts_[-1])");
+        rc.k_contact = k;
+        if (sig != b->red_task_sig) {
+            free_reduced_tasks(b);
+            std::vector<void *> *L = &b->red_task_allocs;
+            for (int l = 0; l < c.nlevels; l++) {
+                const size_t t = c.tasks[l].dof;
+                bool ok;
+                if (l < k)
+                    ok = dev_alloc(b, &wr.Jt[l], B * t * rn, L) && dev_alloc(b, &wr.Lamt[l], B * t * t, L) && dev_alloc(b, &wr.Jkt[l], B * rm * t, L) &&
+                         dev_alloc(b, &wr.Null[l], B * rm * rm, L) && dev_alloc(b, &wr.Ntq[l], B * rm * t, L) && dev_alloc(b, &wr.torque_h[l], B * rm, L) &&
+                         dev_alloc(b, &b->rx.JtR[l], B * t * rn, L);
+                else
+                    ok = dev_alloc(b, &b->rx.LamNC[l], B * t * t, L);
+                if (!ok) return DWBC_ERR_CUDA;
+            }
+            b->red_task_sig = sig;
+        }
+        // reduced hierarchy = the first k levels with per-state custom Jacobians
+        b->cfgR = b->cfg;
+        b->cfgR.nlevels = k;
+        for (int l = 0; l < k; l++) {
+            b->cfgR.tasks[l].custom = 1;
+            b->cfgR.tasks[l].link_count = 0;
+            wr.jcustom[l] = b->rx.JtR[l];
+            wr.jcustom_per_state[l] = 1;
+            wr.fstar[l] = b->w.fstar[l];
+            tmaxR = c.tasks[l].dof > tmaxR ? c.tasks[l].dof : tmaxR;
+        }
+        CK(cudaMemcpyAsync(b->d_cfgR, &b->cfgR, sizeof(BatchCfg), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        {
+            size_t smem = sizeof(double) * (size_t)(tmaxR | 1) * md.n;
+            CK(cudaFuncSetAttribute(reduced_task_jacobian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            KernelScope ks(b, DWBC_K_REDUCED, st);
+            DWBC_LAUNCH(reduced_task_jacobian_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, b->wr, b->rx, b->rc, tmaxR);
+        }
+        {
+            TaskSmem L(rn, rm, tmaxR);
+            size_t smem = sizeof(double) * L.total;
+            CK(cudaFuncSetAttribute(task_space_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            KernelScope ks(b, DWBC_K_TASK, st);
+            DWBC_LAUNCH(task_space_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, b->wr, 0, tmaxR, k < c.nlevels ? 1 : 0);
+        }
+    }
+    {
+        ReducedNcSmem L(md.n, rm, tmax);
+        size_t smem = sizeof(double) * L.total;
+        CK(cudaFuncSetAttribute(reduced_nc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KernelScope ks(b, DWBC_K_REDUCED, st);
+        DWBC_LAUNCH(reduced_nc_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, b->wr, b->rx, b->rc, tmax);
+    }
+    CK(cudaGetLastError());
+    if (tau_grav_dev) CK(cudaMemcpyAsync(tau_grav_dev, b->w.tau_grav, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));
+    if (tau_task_dev) CK(cudaMemcpyAsync(tau_task_dev, b->w.tau_task, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));
+    if (tau_contact_dev) CK(cudaMemcpyAsync(tau_contact_dev, b->w.tau_contact, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));
+    if (status_dev) CK(cudaMemcpyAsync(status_dev, b->w.status, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+    return DWBC_OK;
+}
+
+int dwbc_batch_get_reduced_matrix(dwbc_batch_t *b, int which, int level, double *out_dev, int *rows, int *cols, void *stream) {
+    if (!b) return fail(DWBC_ERR_ARG, "get_reduced_matrix: null handle");
+    if (!b->have_red_dyn) return fail(DWBC_ERR_ORDER, "get_reduced_matrix: call reduced_dynamics first");
+    CK(cudaSetDevice(b->device));
+    const Work &r = b->wr;
+    const ReducedX &x = b->rx;
+    const int rn = b->rc.rn, rm = b->rc.rm, nc = b->rc.nc_dof;
+    const double *src = nullptr;
+    int rr = 0, cc = 0, stride = 0;  // stride != 0: the per-state record is larger than rr*cc
+    int t = 0;
+    if (which >= DWBC_RMAT_J_TASK_R) {
+        if (level < 0 || level >= b->rc.nlevels) return fail(DWBC_ERR_ARG, "get_reduced_matrix: level out of range (or reduced_solve not called)");
+        t = b->cfg.tasks[level].dof;
+    }
+    const bool contact_level = level < b->rc.k_contact;
+    switch (which) {
+    case DWBC_RMAT_A_R_INV: src = r.Ainv; rr = rn; cc = rn; break;
+    case DWBC_RMAT_A_R: src = x.AR; rr = rn; cc = rn; break;
+    case DWBC_RMAT_J_I_NC: src = x.JI; rr = 6; cc = nc; stride = 6 * NCMAX; break;
+    case DWBC_RMAT_J_I_NC_INV_T: src = x.JIinvT; rr = 6; cc = nc; stride = 6 * NCMAX; break;
+    case DWBC_RMAT_G_R: src = r.G; rr = rn; cc = 1; break;
+    case DWBC_RMAT_J_CR: src = r.Jc; rr = CMAX; cc = rn; break;
+    case DWBC_RMAT_LAMBDA_CR: src = r.Lam; rr = CMAX; cc = CMAX; break;
+    case DWBC_RMAT_J_CR_INV_T: src = r.Jbar; rr = CMAX; cc = rn; break;
+    case DWBC_RMAT_A_R_INV_N_CR: src = r.AinvNc; rr = rn; cc = rn; break;
+    case DWBC_RMAT_W_R: src = r.W; rr = rm; cc = rm; break;
+    case DWBC_RMAT_W_R_INV: src = r.Winv; rr = rm; cc = rm; break;
+    case DWBC_RMAT_NWJW_R: src = r.NwJw; rr = rm; cc = RMAX; break;
+    case DWBC_RMAT_P_CR: src = r.PC; rr = CMAX; cc = 1; break;
+    case DWBC_RMAT_TORQUE_GRAV_R: src = r.tau_grav; rr = rm; cc = 1; break;
+    case DWBC_RMAT_TORQUE_TASK_R: src = x.tauR; rr = rm; cc = 1; break;
+    case DWBC_RMAT_J_BASE_R_KT: src = x.Jbkt; rr = rm; cc = 6; break;
+    case DWBC_RMAT_SI_NC: src = x.SInc; rr = 13; cc = 1; stride = 16; break;
+    case DWBC_RMAT_J_TASK_R: src = contact_level ? x.JtR[level] : nullptr; rr = t; cc = rn; break;
+    case DWBC_RMAT_LAMBDA_TASK: src = contact_level ? r.Lamt[level] : x.LamNC[level]; rr = t; cc = t; break;
+    case DWBC_RMAT_J_KT_R: src = contact_level ? r.Jkt[level] : nullptr; rr = rm; cc = t; break;
+    case DWBC_RMAT_NULL_TASK_R: src = contact_level ? r.Null[level] : nullptr; rr = rm; cc = rm; break;
+    default: return fail(DWBC_ERR_ARG, "get_reduced_matrix: unknown matrix id");
+    }
+    if (rows) *rows = rr;
+    if (cols) *cols = cc;
+    if (!out_dev) return DWBC_OK;
+    if (!src) return fail(DWBC_ERR_ARG, "get_reduced_matrix: not defined for this level");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!stride)
+        CK(cudaMemcpyAsync(out_dev, src, sizeof(double) * (size_t)b->B * rr * cc, cudaMemcpyDeviceToDevice, st));
+    else
+        CK(cudaMemcpy2DAsync(out_dev, sizeof(double) * rr * cc, src, sizeof(double) * stride, sizeof(double) * rr * cc, b->B, cudaMemcpyDeviceToDevice, st));
     return DWBC_OK;
 }
 

@@ -104,7 +104,8 @@ __device__ __forceinline__ double spd_inverse_small(int t, double *S, int ld, do
     return dmax > 0.0 ? piv / dmax : 0.0;
 }
 
-__global__ void __launch_bounds__(TEAM, 5) task_space_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int tmax) {
+__global__ void __launch_bounds__(TEAM, 5) task_space_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int tmax,
+                                                             int null_last) {
     DWBC_DYN_SMEM(smem);
     const int tid = t_id(), nt = t_n();
     const long long s = blockIdx.x;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(TEAM, 5) task_space_kernel(const DevModel *__r
         // closed-form torque: torque_task += Null_{l-1} torque_h = Ntorque f*
         tgemv<false>(m, t, Nt, ldm, fs, [&](int i, double v) { tt[i] += v; });
         // Null_l = Null_{l-1} - Ntorque T[:, 6:]     (not needed for the last level)
-        if (l + 1 < nl) {
+        if (l + 1 < nl || null_last) {  // null_last: the reduced variant needs Null of its last contact-chain level
             if (l == 0) {
                 tgemm<3, 3, false, false>(m, m, t, Nt, ldm, T + 6 * ldt, ldt,
                                           [&](int i, int j, double v) { Nul[i + j * ldm] = (i == j ? 1.0 : 0.0) - v; });

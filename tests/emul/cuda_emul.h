@@ -159,6 +159,11 @@ inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyK
     std::memcpy(d, s, n);
     return cudaSuccess;
 }
+inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dpitch, const void *s, size_t spitch, size_t width, size_t height, cudaMemcpyKind,
+                                     cudaStream_t = nullptr) {
+    for (size_t r = 0; r < height; r++) std::memcpy((char *)d + r * dpitch, (const char *)s + r * spitch, width);
+    return cudaSuccess;
+}
 inline cudaError_t cudaMemset(void *d, int v, size_t n) {
     std::memset(d, v, n);
     return cudaSuccess;

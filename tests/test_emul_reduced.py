@@ -1,0 +1,105 @@
+"""a9 reduced-dimension variant: the product's kernels (host emulation build, tests/emul) against the oracle's literal
+restatement of reference src/dwbc.cpp:2752-3446, and against the full-model torques (the reference's own check,
+tests/sp_test/redu_dyn_test.cpp:323-360).  The authoritative run is the `-m gpu` twin in tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from libdwbc_b200 import CONTACT_6D, SOLVE_GRAV, SOLVE_TASK, TASK_LINK_6D, TASK_LINK_POSITION, TASK_LINK_ROTATION, DwbcError, RobotDataBatch
+from tests.common import *
+from tests.emul.emul_backend import EmulBackend
+from tests.test_oracle_reduced import full_and_reduced
+
+
+def reduced_product(backend, q, qd, flags, fstars, B):
+    rd = RobotDataBatch(URDF, B, _backend=backend) if backend is not None else RobotDataBatch(URDF, B, 0)
+    rd.add_contact_constraint(LEFT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+    rd.add_contact_constraint(RIGHT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+    rd.add_task_space(0, TASK_LINK_POSITION, "COM")
+    rd.add_task_space(1, TASK_LINK_ROTATION, "pelvis_link")
+    rd.add_task_space(2, TASK_LINK_ROTATION, "upperbody_link")
+    rd.add_task_space(3, TASK_LINK_6D, "L_Wrist2_Link")
+    return rd
+
+
+REDUCED_NAMES = ["A_R_inv", "A_R", "J_I_nc", "J_I_nc_inv_T", "G_R", "Lambda_CR", "J_CR_INV_T", "A_R_inv_N_CR", "W_R", "W_R_inv", "NwJw_R", "P_CR",
+                 "torque_grav_R", "J_base_R_kt", "torque_task_R"]
+
+
+def check_reduced_against_oracle(rd, to_np, q, qd, flags, fs, tol=1e-9):
+    B = q.shape[0]
+    tg, tt, tc, st = [to_np(x) for x in rd.reduced_solve(SOLVE_GRAV | SOLVE_TASK)]
+    c = 6 * int(sum(flags))
+    for b in range(B):
+        full, red = full_and_reduced(q[b], qd[b], flags, [f[b] for f in fs])
+        assert st[b] == 3
+        for name in REDUCED_NAMES:
+            a = to_np(rd.get_reduced(name))[b]
+            o = red.get(name)
+            if o.shape[1] == 1:
+                o = o[:, 0]
+            if name in ("Lambda_CR", "J_CR_INV_T", "P_CR"):
+                a = a[:c]
+                a = a[:, :c] if name == "Lambda_CR" else a
+            if name == "NwJw_R":
+                a, o = a[:, :c - 6], o[:, :c - 6]
+            assert relerr(a, o) < tol, (b, name, relerr(a, o))
+        for l in range(4):
+            assert relerr(to_np(rd.get_reduced("Lambda_task", l))[b], red.get(f"Lambda_task{l}")) < tol, l
+        for l in range(2):
+            assert relerr(to_np(rd.get_reduced("J_task_R", l))[b], red.get(f"R_J_task{l}")) < tol
+            assert relerr(to_np(rd.get_reduced("J_kt_R", l))[b], red.get(f"R_J_kt{l}")) < tol
+            assert relerr(to_np(rd.get_reduced("Null_task_R", l))[b], red.get(f"R_Null_task{l}")) < tol
+        assert relerr(tg[b], red.get("torque_grav")[:, 0]) < tol
+        assert relerr(tt[b], red.get("torque_task")[:, 0]) < tol
+        # the reference's own check: reduced == full-model torques
+        assert relerr(tg[b], full.get("torque_grav")[:, 0]) < 1e-8
+        assert relerr(tt[b], full.get("torque_task")[:, 0]) < 1e-8
+        assert np.all(tc[b] == 0)
+
+
+@pytest.mark.parametrize("flags", [(1, 1), (1, 0)])
+def test_emul_reduced_vs_oracle(flags):
+    B = 3
+    q, qd, rng = synth_states(B, 20243)
+    fs = [0.5 * rng.standard_normal((B, 3)), rng.standard_normal((B, 3)), rng.standard_normal((B, 3)), rng.standard_normal((B, 6))]
+    rd = reduced_product(EmulBackend(), q, qd, flags, fs, B)
+    rd.update_kinematics(q, qd)
+    fl = np.tile(np.array(flags, dtype=np.uint8), (B, 1))
+    fl[2] = (1, 1) if flags == (1, 0) else (0, 1)  # a state that does not show the pattern
+    rd.set_contact(fl)
+    rd.reduced_dynamics_calculate(flags)
+    assert (rd.co_dof, rd.nc_dof, rd.reduced_system_dof_, rd.reduced_model_dof_) == ((12, 21, 24, 18) if flags == (1, 1) else (6, 27, 18, 12))
+    rd.reduced_calc_contact_constraint()
+    for l, f in enumerate(fs):
+        rd.set_task_space(l, np.ascontiguousarray(f))
+    tg, tt, tc, st = rd.reduced_solve(SOLVE_GRAV | SOLVE_TASK)
+    assert st[2] == 0 and np.all(tt[2] == 0)
+    check_reduced_against_oracle(rd, lambda x: np.asarray(x)[:2], q[:2], qd[:2], flags, [f[:2] for f in fs])
+
+
+def test_emul_reduced_rejections():
+    rd = reduced_product(EmulBackend(), None, None, None, None, 1)
+    q, qd, _ = synth_states(1, 1)
+    with pytest.raises(DwbcError):
+        rd.reduced_dynamics_calculate((1, 1))  # before update_kinematics / set_contact
+    rd.update_kinematics(q, qd)
+    rd.set_contact(np.array([[0, 1]], dtype=np.uint8))
+    with pytest.raises(DwbcError, match="prefix"):
+        rd.reduced_dynamics_calculate((0, 1))  # right-foot single support: the reference's block indexing breaks
+    rd.set_contact(np.array([[1, 1]], dtype=np.uint8))
+    rd.reduced_dynamics_calculate((1, 1))
+    with pytest.raises(DwbcError):
+        rd.reduced_solve(SOLVE_GRAV)  # before reduced_calc_contact_constraint
+    rd.reduced_calc_contact_constraint()
+    tg, _, _, st = rd.reduced_solve(SOLVE_GRAV)
+    assert st[0] == 1 and np.abs(tg[0]).max() > 1
+    # config-2 hierarchy: level 1 mixes pelvis (contact chain) and upper body (non-contact) -> UNDEFINED TASK TYPE
+    rd2 = configure_product(RobotDataBatch(URDF, 1, _backend=EmulBackend()), 2)
+    rd2.update_kinematics(q, qd)
+    rd2.set_contact(np.array([[1, 1]], dtype=np.uint8))
+    rd2.reduced_dynamics_calculate((1, 1))
+    rd2.reduced_calc_contact_constraint()
+    for l, t in enumerate((3, 6, 21)):
+        rd2.set_task_space(l, np.zeros((1, t)), np.ascontiguousarray(posture_selector()) if l == 2 else None)
+    with pytest.raises(DwbcError, match="UNDEFINED TASK TYPE"):
+        rd2.reduced_solve(SOLVE_TASK)

@@ -313,3 +313,56 @@ def test_analytic_redistribution_contact_force_zmp():
     assert relerr(cf.cpu().numpy(), o["contact_force"]) < 1e-9
     zmp = rd.get_zmp(cf)
     assert relerr(zmp.cpu().numpy(), o["zmp"]) < 1e-9
+
+
+@pytest.mark.parametrize("flags", [(1, 1), (1, 0)])
+def test_reduced_dimension_variant_vs_oracle(flags):
+    """a9 (reference src/dwbc.cpp:2752-3446): reduced dynamics, contact constraint, gravity compensation, task space and
+    closed-form task torque against the oracle's literal restatement (1e-9) and against the full-model torques
+    (the reference's own check, tests/sp_test/redu_dyn_test.cpp:323-360)."""
+    from tests.test_emul_reduced import check_reduced_against_oracle, reduced_product
+
+    B = 8
+    q, qd, rng = synth_states(B, 20243)
+    fs = [0.5 * rng.standard_normal((B, 3)), rng.standard_normal((B, 3)), rng.standard_normal((B, 3)), rng.standard_normal((B, 6))]
+    rd = reduced_product(None, q, qd, flags, fs, B)
+    rd.update_kinematics(T(q), T(qd))
+    rd.set_contact(T(np.tile(np.array(flags, dtype=np.uint8), (B, 1)), torch.uint8))
+    rd.reduced_dynamics_calculate(flags)
+    rd.reduced_calc_contact_constraint()
+    keep = [T(f) for f in fs]
+    for l, f in enumerate(keep):
+        rd.set_task_space(l, f)
+    check_reduced_against_oracle(rd, lambda x: x.cpu().numpy(), q, qd, flags, fs)
+
+
+def test_reduced_full_size_equals_full_model():
+    """B = 65536 (config 3(i)): the reduced pipeline reproduces the full-model torque_grav_ / torque_task_ of every state."""
+    from libdwbc_b200 import SOLVE_GRAV, SOLVE_TASK
+    from tests.test_emul_reduced import reduced_product
+
+    B = 65536
+    q, qd, rng = synth_states(B, 20243)
+    fs = [0.5 * rng.standard_normal((B, 3)), rng.standard_normal((B, 3)), rng.standard_normal((B, 3)), rng.standard_normal((B, 6))]
+    flags = T(np.ones((B, 2), dtype=np.uint8), torch.uint8)
+    qt, qdt, fst = T(q), T(qd), [T(f) for f in fs]
+    full = reduced_product(None, q, qd, (1, 1), fs, B)
+    full.update_kinematics(qt, qdt)
+    full.set_contact(flags)
+    full.calc_contact_constraint()
+    for l, f in enumerate(fst):
+        full.set_task_space(l, f)
+    tg, tt, _, st = full.solve(SOLVE_GRAV | SOLVE_TASK)
+    red = reduced_product(None, q, qd, (1, 1), fs, B)
+    red.update_kinematics(qt, qdt)
+    red.set_contact(flags)
+    red.reduced_dynamics_calculate((1, 1))
+    red.reduced_calc_contact_constraint()
+    for l, f in enumerate(fst):
+        red.set_task_space(l, f)
+    rg, rt, _, rs = red.reduced_solve(SOLVE_GRAV | SOLVE_TASK)
+    torch.cuda.synchronize()
+    assert bool((st == 3).all()) and bool((rs == 3).all())
+    eg = ((rg - tg).norm(dim=1) / tg.norm(dim=1)).max().item()
+    et = ((rt - tt).norm(dim=1) / tt.norm(dim=1).clamp_min(1.0)).max().item()
+    assert eg < 1e-8 and et < 1e-7, (eg, et)
