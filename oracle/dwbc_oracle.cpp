@@ -255,6 +255,23 @@ struct Robot {
     void reduced_grav();
     int reduced_task_space();
     int reduced_task_torque(bool hqp);
+
+    // ---- a10: LQP variant (Ahn 2025), reference src/dwbc.cpp:4304-4502, src/dwbc_hqp.cpp ----
+    struct LqpLevel {
+        int nineq = 0, neq = 0, nu = 0;  // own inequality rows, equality rows, null-space size after this level
+        Mat A, a, B, b;                  // A y + a <= v,  B y + b = w   (rows normalised)
+        bool cost = false;
+        Mat Z, y, v, w, u;               // Z_: nvar x nu; y_ans_, v_ans_, w_ans_, u_ans_
+        Mat qpH, qpg, qpA, qpub;         // the level QP exactly as the reference assembles it
+        int status = 0;
+    };
+    std::vector<LqpLevel> lqp;
+    Mat lqp_H, lqp_torque;  // cost Hessian shared by the levels; torque of the final y
+    int lqp_acc = 0, lqp_con = 0;
+    void configure_lqp();
+    void lqp_prepare();
+    int lqp_solve_level(int i);
+    int calc_lqp();
 };
 
 void Robot::update_kinematics(const double *q_, const double *qd_) {
@@ -1105,6 +1122,266 @@ int Robot::reduced_task_torque(bool hqp) {
 // ------------------------------------------------------------------------------------------
 using namespace orc;
 
+
+// ================================================================================================
+// a10: LQP / centroidal simplified-WBD variant.  PARITY UNPINNED: the reference solves every level
+// with OSQP (ADMM, default eps 1e-3, sigma 1e-6) and holds no golden vector for this path; this
+// restatement assembles the level QPs exactly as the reference does and solves them EXACTLY.
+// ================================================================================================
+
+// OSQP regularises its KKT system with sigma = 1e-6 (default setting, not overridden by the reference,
+// src/dwbc_hqp.cpp:596-598).  The level Hessians are singular (internal contact forces carry no cost), so the
+// exact solve needs a rule for those directions: the same sigma on the null-space coordinates u, i.e. among
+// the level's minimisers the one closest to the previous level's y (Z is orthonormal).
+static const double LQP_SIGMA = 1.0e-6;
+
+// getNullSpace (reference src/math.cpp:349-360): orthonormal basis of null(A), A is me x nvar.
+static Mat lqp_null_space(const Mat &A) {
+    Cod f = cod_compute(A.t(), 1e-10);  // A^T P = Q R;  null(A) = last (nvar - rank) columns of Q
+    return f.Q.right_cols(A.c - f.rank);
+}
+
+static void lqp_normalize(Mat &A, Mat &a) {  // HQP_Hierarch::normalizeConstraintMatrix, reference src/dwbc_hqp.cpp:555-581
+    for (int i = 0; i < A.r; i++) {
+        double s = 0;
+        for (int j = 0; j < A.c; j++) s += A(i, j) * A(i, j);
+        s = std::sqrt(s);
+        if (s > 0) {
+            for (int j = 0; j < A.c; j++) A(i, j) /= s;
+            a[i] /= s;
+        }
+    }
+}
+
+// reference src/dwbc.cpp:4304-4430 (ConfigureLQP)
+void Robot::configure_lqp() {
+    const int acc = n, tq = m, con = contact_dof, nvar = acc + con;
+    lqp_acc = acc;
+    lqp_con = con;
+    lqp.clear();
+    lqp_H.set_zero(nvar, nvar);
+    const double an = A.norm();
+    for (int j = 0; j < acc; j++)
+        for (int i = 0; i < acc; i++) lqp_H(i, j) = A(i, j) / an * 5.0;  // :4341
+    Mat JcT = J_C.t();
+    // Priority 1: floating-base Newton-Euler rows (equality), torque limit +-200 (inequality); preset answer  :4343-4381
+    {
+        LqpLevel L;
+        L.nineq = 2 * tq;
+        L.neq = 6;
+        L.A.set_zero(L.nineq, nvar);
+        L.a.set_zero(L.nineq, 1);
+        L.B.set_zero(6, nvar);
+        L.b.set_zero(6, 1);
+        for (int j = 0; j < acc; j++)
+            for (int i = 0; i < 6; i++) L.B(i, j) = A(i, j);
+        for (int j = 0; j < con; j++)
+            for (int i = 0; i < 6; i++) L.B(i, acc + j) = JcT(i, j);
+        for (int i = 0; i < 6; i++) L.b[i] = B[i];
+        for (int i = 0; i < tq; i++) {
+            for (int j = 0; j < acc; j++) L.A(i, j) = A(6 + i, j), L.A(tq + i, j) = -A(6 + i, j);
+            for (int j = 0; j < con; j++) L.A(i, acc + j) = JcT(6 + i, j), L.A(tq + i, acc + j) = -JcT(6 + i, j);
+            L.a[i] = -200.0 + B[6 + i];
+            L.a[tq + i] = -200.0 - B[6 + i];
+        }
+        lqp_normalize(L.A, L.a);
+        lqp_normalize(L.B, L.b);
+        L.v.set_zero(L.nineq, 1);
+        L.w.set_zero(6, 1);
+        L.y.set_zero(nvar, 1);
+        Mat qdd = A_inv * B;
+        for (int i = 0; i < acc; i++) L.y[i] = -qdd[i];
+        L.status = 1;
+        lqp.push_back(L);
+    }
+    // Priority 2: contact rows J_C qdd = 0 (equality); friction/ZMP rows on Fc and |qdd_joint| <= 5 (inequality)  :4383-4407
+    {
+        LqpLevel L;
+        const int cs = contact_links * 10;
+        L.nineq = cs + 2 * tq;
+        L.neq = con;
+        L.A.set_zero(L.nineq, nvar);
+        L.a.set_zero(L.nineq, 1);
+        Mat A_const, A_rot;
+        int csz;
+        contact_const(A_const, A_rot, csz);
+        Mat C = -(A_const * A_rot);  // getContactConstraintMatrix, :480-513
+        for (int j = 0; j < con; j++)
+            for (int i = 0; i < cs; i++) L.A(i, acc + j) = C(i, j);
+        for (int i = 0; i < tq; i++) {
+            L.A(cs + i, 6 + i) = 1.0;
+            L.A(cs + tq + i, 6 + i) = -1.0;
+            L.a[cs + i] = -5.0;
+            L.a[cs + tq + i] = -5.0;
+        }
+        L.B.set_zero(con, nvar);
+        L.b.set_zero(con, 1);
+        for (int j = 0; j < acc; j++)
+            for (int i = 0; i < con; i++) L.B(i, j) = J_C(i, j);
+        L.cost = true;
+        lqp_normalize(L.A, L.a);
+        lqp_normalize(L.B, L.b);
+        lqp.push_back(L);
+    }
+    // Priority 3..: one level per task space, J_task qdd = f*  :4409-4425
+    for (auto &t : ts) {
+        LqpLevel L;
+        L.nineq = 0;
+        L.neq = t.dof;
+        L.B.set_zero(t.dof, nvar);
+        L.b.set_zero(t.dof, 1);
+        for (int j = 0; j < acc; j++)
+            for (int i = 0; i < t.dof; i++) L.B(i, j) = t.J(i, j);
+        for (int i = 0; i < t.dof; i++) L.b[i] = -t.fstar[i];
+        L.cost = true;
+        lqp_normalize(L.B, L.b);
+        lqp.push_back(L);
+    }
+    lqp_prepare();
+}
+
+// HQP::prepare, reference src/dwbc_hqp.cpp:23-85
+void Robot::lqp_prepare() {
+    lqp[0].Z = lqp_null_space(lqp[0].B);
+    lqp[0].nu = lqp[0].Z.c;
+    for (size_t i = 1; i < lqp.size(); i++) {
+        Mat Bn = lqp[i].B * lqp[i - 1].Z;
+        Mat nb_ = lqp_null_space(Bn);
+        lqp[i].Z = lqp[i - 1].Z * nb_;
+        lqp[i].nu = lqp[i].Z.c;
+    }
+}
+
+// HQP::solveSequentialSingle, reference src/dwbc_hqp.cpp:291-395: the QP over [u (null-space coordinates of the
+// previous level); v (slack of this level's inequality rows)] is assembled as written there; HQP_Hierarch::solveOSQP
+// (:583-631) passes H, g, A, ubA only (lbA = -inf, no variable bounds), so that is the problem solved here.
+int Robot::lqp_solve_level(int i) {
+    LqpLevel &L = lqp[i];
+    const LqpLevel &P = lqp[i - 1];
+    const int nu = P.nu, nv = L.nineq, nz = nu + nv;
+    int rows = nv;
+    for (int j = 0; j < i; j++) rows += lqp[j].nineq;
+    L.qpH.set_zero(nz, nz);
+    L.qpg.set_zero(nz, 1);
+    L.qpA.set_zero(rows, nz);
+    L.qpub.set_zero(rows, 1);
+    if (nv > 0) {
+        Mat AZ = L.A * P.Z, Ay = L.A * P.y;
+        for (int r = 0; r < nv; r++) {
+            for (int j = 0; j < nu; j++) L.qpA(r, j) = AZ(r, j);
+            L.qpA(r, nu + r) = -1.0;
+            L.qpub[r] = -Ay[r] - L.a[r];
+            L.qpH(nu + r, nu + r) = 1.0;
+        }
+    }
+    Mat E = L.B * P.Z, e = L.B * P.y + L.b;
+    Mat EtE = E.t() * E, Ete = E.t() * e;
+    for (int c = 0; c < nu; c++) {
+        for (int r = 0; r < nu; r++) L.qpH(r, c) = EtE(r, c);
+        L.qpg[c] = Ete[c];
+    }
+    if (L.cost) {
+        Mat ZtH = P.Z.t() * lqp_H;
+        Mat C = ZtH * P.Z, cg = ZtH * P.y;
+        for (int c = 0; c < nu; c++) {
+            for (int r = 0; r < nu; r++) L.qpH(r, c) += C(r, c);
+            L.qpg[c] += cg[c];
+        }
+    }
+    int ci = nv;
+    for (int j = 0; j < i; j++) {
+        if (lqp[j].nineq == 0) continue;
+        Mat AZ = lqp[j].A * P.Z, Ay = lqp[j].A * P.y;
+        for (int r = 0; r < lqp[j].nineq; r++) {
+            for (int c = 0; c < nu; c++) L.qpA(ci + r, c) = AZ(r, c);
+            L.qpub[ci + r] = -Ay[r] + lqp[j].v[r] - lqp[j].a[r];
+        }
+        ci += lqp[j].nineq;
+    }
+    // exact solve of  min 1/2 z^T (H + sigma I_u) z + g^T z  s.t.  qpA z <= qpub:
+    // Cholesky of the u-block (the v-block is the identity) turns it into a least-distance problem.
+    Mat M(nu, nu);
+    for (int c = 0; c < nu; c++)
+        for (int r = 0; r < nu; r++) M(r, c) = L.qpH(r, c) + (r == c ? LQP_SIGMA : 0.0);
+    // lower Cholesky M = Lc Lc^T
+    Mat Lc(nu, nu);
+    for (int j = 0; j < nu; j++) {
+        double s = M(j, j);
+        for (int k = 0; k < j; k++) s -= Lc(j, k) * Lc(j, k);
+        if (!(s > 0)) return L.status = 0;
+        Lc(j, j) = std::sqrt(s);
+        for (int r = j + 1; r < nu; r++) {
+            double t = M(r, j);
+            for (int k = 0; k < j; k++) t -= Lc(r, k) * Lc(j, k);
+            Lc(r, j) = t / Lc(j, j);
+        }
+    }
+    auto fwd = [&](std::vector<double> &x) {  // x <- Lc^{-1} x
+        for (int r = 0; r < nu; r++) {
+            double s = x[r];
+            for (int k = 0; k < r; k++) s -= Lc(r, k) * x[k];
+            x[r] = s / Lc(r, r);
+        }
+    };
+    auto bwd = [&](std::vector<double> &x) {  // x <- Lc^{-T} x
+        for (int r = nu - 1; r >= 0; r--) {
+            double s = x[r];
+            for (int k = r + 1; k < nu; k++) s -= Lc(k, r) * x[k];
+            x[r] = s / Lc(r, r);
+        }
+    };
+    // xhat = Lc^T u + Lc^{-1} g  =>  objective 1/2 |xhat|^2 + 1/2 |v|^2;  u = Lc^{-T} (xhat - gh)
+    std::vector<double> gh(nu);
+    for (int r = 0; r < nu; r++) gh[r] = L.qpg[r];
+    fwd(gh);
+    Mat Ah(rows, nz);
+    std::vector<double> ubh(rows);
+    for (int r = 0; r < rows; r++) {
+        std::vector<double> row(nu);
+        for (int c = 0; c < nu; c++) row[c] = L.qpA(r, c);
+        fwd(row);  // row^T Lc^{-T} = (Lc^{-1} row)^T
+        double s = 0;
+        for (int c = 0; c < nu; c++) Ah(r, c) = row[c], s += row[c] * gh[c];
+        for (int c = nu; c < nz; c++) Ah(r, c) = L.qpA(r, c);
+        ubh[r] = L.qpub[r] + s;
+    }
+    QpResult res = qp_min_norm(Ah, ubh);
+    if (!res.status) return L.status = 0;
+    std::vector<double> uu(nu);
+    for (int r = 0; r < nu; r++) uu[r] = res.x[r] - gh[r];
+    bwd(uu);
+    L.u.set_zero(nu, 1);
+    for (int r = 0; r < nu; r++) L.u[r] = uu[r];
+    L.y = P.y + P.Z * L.u;
+    L.v.set_zero(nv, 1);
+    for (int r = 0; r < nv; r++) L.v[r] = res.x[nu + r];
+    L.w = L.B * L.y + L.b;
+    return L.status = 1;
+}
+
+// CalcControlTorqueLQP -> HQP::solveSequential, reference src/dwbc.cpp:4432-4454, src/dwbc_hqp.cpp:397-403.
+// The joint torque of the answer is the torque-limit row expression of priority 1 (src/dwbc.cpp:4355-4370):
+// tau = A[6:,:] qdd + J_C^T[6:,:] Fc + B[6:].
+int Robot::calc_lqp() {
+    int ok = 1;
+    for (size_t i = 1; i < lqp.size(); i++) {
+        if (!lqp_solve_level((int)i)) {
+            ok = 0;
+            for (size_t k = i; k < lqp.size(); k++) lqp[k].y = lqp[i - 1].y, lqp[k].status = 0;
+            break;
+        }
+    }
+    const Mat &y = lqp.back().y;
+    lqp_torque.set_zero(m, 1);
+    for (int i = 0; i < m; i++) {
+        double s = B[6 + i];
+        for (int j = 0; j < n; j++) s += A(6 + i, j) * y[j];
+        for (int j = 0; j < lqp_con; j++) s += J_C(j, 6 + i) * y[n + j];
+        lqp_torque[i] = s;
+    }
+    return ok;
+}
+
 extern "C" {
 
 void *orc_create(int nb, const int *parent, const double *E_T, const double *r_T, const double *axis, const double *mass,
@@ -1195,6 +1472,7 @@ void orc_set_task(void *h, int level, const double *fstar, const double *J) {
     }
 }
 void orc_calc_grav(void *h) { ((Robot *)h)->calc_grav(); }
+void orc_update_task_space(void *h) { ((Robot *)h)->update_task_space(); }
 int orc_calc_task_torque(void *h, int hqp) { return ((Robot *)h)->calc_task_torque(hqp != 0); }
 int orc_calc_redistribute(void *h, int hqp) { return ((Robot *)h)->calc_redistribute(hqp != 0); }
 // a9 reduced-dimension variant
@@ -1203,6 +1481,9 @@ int orc_reduced_contact_constraint(void *h) { return ((Robot *)h)->reduced_conta
 void orc_reduced_grav(void *h) { ((Robot *)h)->reduced_grav(); }
 int orc_reduced_task_space(void *h) { return ((Robot *)h)->reduced_task_space(); }
 int orc_reduced_task_torque(void *h, int hqp) { return ((Robot *)h)->reduced_task_torque(hqp != 0); }
+void orc_configure_lqp(void *h) { ((Robot *)h)->configure_lqp(); }
+int orc_calc_lqp(void *h) { return ((Robot *)h)->calc_lqp(); }
+int orc_lqp_levels(void *h) { return (int)((Robot *)h)->lqp.size(); }
 void orc_reduced_dims(void *h, int *out) {
     Robot *R = (Robot *)h;
     out[0] = R->co_dof; out[1] = R->nc_dof; out[2] = R->vc_dof; out[3] = R->rsys; out[4] = R->rmod;
@@ -1291,6 +1572,24 @@ static const Mat *find_mat(Robot *R, const std::string &name, Mat &tmp) {
         return &tmp;
     }
     int l;
+    if (name == "lqp_H") return &R->lqp_H;
+    if (name == "lqp_torque") return &R->lqp_torque;
+    {
+        const int nl = (int)R->lqp.size();
+        if ((l = lvl("lqp_y")) >= 0 && l < nl) return &R->lqp[l].y;
+        if ((l = lvl("lqp_v")) >= 0 && l < nl) return &R->lqp[l].v;
+        if ((l = lvl("lqp_w")) >= 0 && l < nl) return &R->lqp[l].w;
+        if ((l = lvl("lqp_u")) >= 0 && l < nl) return &R->lqp[l].u;
+        if ((l = lvl("lqp_Z")) >= 0 && l < nl) return &R->lqp[l].Z;
+        if ((l = lvl("lqp_A")) >= 0 && l < nl) return &R->lqp[l].A;
+        if ((l = lvl("lqp_a")) >= 0 && l < nl) return &R->lqp[l].a;
+        if ((l = lvl("lqp_B")) >= 0 && l < nl) return &R->lqp[l].B;
+        if ((l = lvl("lqp_b")) >= 0 && l < nl) return &R->lqp[l].b;
+        if ((l = lvl("lqp_qpH")) >= 0 && l < nl) return &R->lqp[l].qpH;
+        if ((l = lvl("lqp_qpg")) >= 0 && l < nl) return &R->lqp[l].qpg;
+        if ((l = lvl("lqp_qpA")) >= 0 && l < nl) return &R->lqp[l].qpA;
+        if ((l = lvl("lqp_qpub")) >= 0 && l < nl) return &R->lqp[l].qpub;
+    }
     if ((l = lvl("J_task")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].J;
     if ((l = lvl("Lambda_task")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].Lambda;
     if ((l = lvl("J_kt")) >= 0 && l < (int)R->ts.size()) return &R->ts[l].Jkt;

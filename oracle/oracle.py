@@ -72,6 +72,8 @@ def lib():
             getattr(L, f).argtypes = [C.c_void_p]
         L.orc_reduced_task_torque.argtypes = [C.c_void_p, C.c_int]
         L.orc_reduced_dims.argtypes = [C.c_void_p, _ip]
+        for f in ("orc_configure_lqp", "orc_calc_lqp", "orc_lqp_levels", "orc_update_task_space"):
+            getattr(L, f).argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -191,6 +193,17 @@ class OracleRobot:
         out = (C.c_int * 5)()
         lib().orc_reduced_dims(self.h, out)
         return dict(zip(("co_dof", "nc_dof", "vc_dof", "reduced_system_dof", "reduced_model_dof"), out))
+
+    # ---- a10: LQP variant, reference src/dwbc.cpp:4304-4454 (call order of tests/sp_test/jacc_compare.cpp:319-384) ----
+    def update_task_space(self):
+        lib().orc_update_task_space(self.h)
+
+    def configure_lqp(self):
+        lib().orc_configure_lqp(self.h)
+        return lib().orc_lqp_levels(self.h)
+
+    def calc_lqp(self):
+        return lib().orc_calc_lqp(self.h)
 
     def contact_force(self, torque):
         """getContactForce(command_torque), reference src/dwbc.cpp:891-896"""
