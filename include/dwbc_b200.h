@@ -219,6 +219,26 @@ enum {
 };
 int dwbc_batch_get_reduced_matrix(dwbc_batch_t *b, int which, int level, double *out_dev, int *rows, int *cols, void *stream);
 
+/* ---- a10: LQP / centroidal simplified-WBD variant (Ahn 2025): ConfigureLQP + CalcControlTorqueLQP in one call,
+ * reference src/dwbc.cpp:4304-4454, src/dwbc_hqp.cpp:23-85, 291-403.  Call order as reference
+ * tests/sp_test/jacc_compare.cpp:367-384: update_kinematics -> set_contact -> calc_contact_constraint -> set_task (every
+ * level) -> calc_control_torque_lqp.  Decision vector y = [qdd (n); Fc (contact_dof)].  Levels: 0 floating-base dynamics
+ * (preset answer), 1 contact rows, 2.. one per task level.  Every level is solved exactly (the reference uses OSQP with
+ * eps 1e-3; parity unpinned).
+ * y_dev [B x (n + cmax)] final answer (entries >= n + contact_dof are zero), tau_dev [B x m] joint torque
+ * A[6:,:] qdd + Jc^T[6:,:] Fc + B[6:], status_dev [B]: number of levels (= 2 + task levels) when every level was solved,
+ * -(levels solved) when a level failed (the answer of the last solved level is returned, as HQP::solveSequential leaves it),
+ * 0 when the contact constraint of the state is invalid.  Any output pointer may be NULL. */
+int dwbc_batch_calc_control_torque_lqp(dwbc_batch_t *b, double *y_dev, double *tau_dev, int32_t *status_dev, void *stream);
+enum {
+    DWBC_LQP_Y = 0,      /* hqp_hs_[level].y_ans_   (n + cmax) x 1, level in [0, 2 + task levels) */
+    DWBC_LQP_V1,         /* hqp_hs_[1].v_ans_       (2m + 10*max_active_contacts) x 1: friction/ZMP rows, then +accel, -accel */
+    DWBC_LQP_TORQUE      /* m x 1 */
+};
+int dwbc_batch_get_lqp(dwbc_batch_t *b, int which, int level, double *out_dev, int *rows, int *cols, void *stream);
+/* active-set iterations of the last LQP call per state: out_dev [B] int32 */
+int dwbc_batch_get_lqp_iterations(dwbc_batch_t *b, int32_t *out_dev, void *stream);
+
 /* ---- whole cycle with HOST buffers (pinned or pageable): H2D, all stages, D2H, synchronised on return.
  * This is what the RobotData shim, the pybind bridge and bench.py's end-to-end timing call.
  * fstar_host: concatenation over levels of [B x t_l] blocks. flags_host [B x ncontact]. */
@@ -234,7 +254,7 @@ int dwbc_probe_fp64(int device, double seconds, double *tflops);
  * recorded on the launch stream (no host synchronisation is added to the hot path).  dwbc_batch_get_kernel_times
  * synchronises the pending events and returns, per DWBC_K_* kernel, the summed duration in ms (only launches made while
  * profiling was on) and the launch count since the last reset.  bench.py's roofline numbers come from here. */
-enum { DWBC_K_RBD = 0, DWBC_K_AINV, DWBC_K_CONTACT_JAC, DWBC_K_CONTACT_DYN, DWBC_K_TASK, DWBC_K_HQP, DWBC_K_EXPORT, DWBC_K_POST, DWBC_K_REDUCED, DWBC_K_COUNT };
+enum { DWBC_K_RBD = 0, DWBC_K_AINV, DWBC_K_CONTACT_JAC, DWBC_K_CONTACT_DYN, DWBC_K_TASK, DWBC_K_HQP, DWBC_K_EXPORT, DWBC_K_POST, DWBC_K_REDUCED, DWBC_K_LQP, DWBC_K_COUNT };
 int dwbc_batch_set_profiling(dwbc_batch_t *b, int enable);
 int dwbc_batch_get_kernel_times(dwbc_batch_t *b, double *ms_sum, long long *launches, int reset);
 const char *dwbc_kernel_name(int k);

@@ -249,6 +249,26 @@ class RobotDataBatch:
     def get_reduced(self, name, level=0):
         return self._get(self.L.dwbc_batch_get_reduced_matrix, _RMATS[name][0], level)
 
+    # ---- a10: LQP variant (reference src/dwbc.cpp:4304-4454, src/dwbc_hqp.cpp; call order of tests/sp_test/jacc_compare.cpp:367-384) ----
+    def calc_control_torque_lqp(self, out=None):
+        """ConfigureLQP + CalcControlTorqueLQP for every state: returns (y = [qdd; Fc] [B, n + cmax], torque [B, m], status [B])."""
+        be = self.be
+        B, m, nv = self.batch, self.model_dof_, self.system_dof_ + self.cmax
+        if out is None:
+            out = (be.empty((B, nv)), be.empty((B, m)), be.empty((B,), "i4"))
+        y, tau, st = out
+        self._ck(self.L.dwbc_batch_calc_control_torque_lqp(self._h, be.ptr(y), be.ptr(tau), be.ptr(st), be.stream()))
+        return y, tau, st
+
+    def get_lqp(self, name, level=0):
+        """"y" (answer after `level`), "v1" (slack of the level-1 inequality rows), "torque"."""
+        return self._get(self.L.dwbc_batch_get_lqp, {"y": 0, "v1": 1, "torque": 2}[name], level)
+
+    def lqp_iterations(self):
+        buf = self.be.empty((self.batch,), "i4")
+        self._ck(self.L.dwbc_batch_get_lqp_iterations(self._h, self.be.ptr(buf), self.be.stream()))
+        return buf
+
     def get(self, name, level=0):
         """Public RobotData field `name` for all states: tensor [B, rows, cols] (vectors: [B, rows])."""
         return self._get(self.L.dwbc_batch_get_matrix, _MATS[name][0], level)
@@ -311,7 +331,7 @@ class RobotDataBatch:
 
     def kernel_times(self, reset=True):
         """{kernel name: (summed ms while profiling was on, launches since the last reset)}"""
-        K = 9
+        K = 10
         ms = (C.c_double * K)()
         cnt = (C.c_longlong * K)()
         self._ck(self.L.dwbc_batch_get_kernel_times(self._h, ms, cnt, 1 if reset else 0))

@@ -14,6 +14,7 @@
 #include "cuda_compat.h"
 #include "kernels_contact.cuh"
 #include "kernels_hqp.cuh"
+#include "kernels_lqp.cuh"
 #include "kernels_post.cuh"
 #include "kernels_reduced.cuh"
 #include "kernels_task.cuh"
@@ -65,6 +66,9 @@ struct dwbc_batch {
     int red_rn = 0;
     std::string red_task_sig;
     bool have_red_dyn = false, have_red_cc = false;
+    // a10 LQP variant
+    LqpOut lq{};
+    bool lqp_allocated = false, have_lqp = false;
 };
 
 namespace {
@@ -636,7 +640,7 @@ int dwbc_batch_get_kernel_times(dwbc_batch_t *b, double *ms_sum, long long *laun
 
 const char *dwbc_kernel_name(int k) {
     static const char *names[DWBC_K_COUNT] = {"rbd_kernel", "ainv_kernel", "contact_jacobian_kernel", "contact_dynamics_kernel",
-                                              "task_space_kernel", "hqp_kernel", "export_kernels", "post_kernels", "reduced_kernels"};
+                                              "task_space_kernel", "hqp_kernel", "export_kernels", "post_kernels", "reduced_kernels", "lqp_kernel"};
     return (k >= 0 && k < DWBC_K_COUNT) ? names[k] : nullptr;
 }
 
@@ -986,6 +990,82 @@ int dwbc_batch_get_reduced_matrix(dwbc_batch_t *b, int which, int level, double 
         CK(cudaMemcpyAsync(out_dev, src, sizeof(double) * (size_t)b->B * rr * cc, cudaMemcpyDeviceToDevice, st));
     else
         CK(cudaMemcpy2DAsync(out_dev, sizeof(double) * rr * cc, src, sizeof(double) * stride, sizeof(double) * rr * cc, b->B, cudaMemcpyDeviceToDevice, st));
+    return DWBC_OK;
+}
+
+
+// ---- a10: LQP variant ----
+int dwbc_batch_calc_control_torque_lqp(dwbc_batch_t *b, double *y_dev, double *tau_dev, int32_t *status_dev, void *stream) {
+    if (!b) return fail(DWBC_ERR_ARG, "calc_control_torque_lqp: null handle");
+    if (!b->have_cc) return fail(DWBC_ERR_ORDER, "calc_control_torque_lqp: call calc_contact_constraint first");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = upload_cfg(b, st);
+    if (rc) return rc;
+    for (int l = 0; l < b->cfg.nlevels; l++)
+        if (!b->w.fstar[l]) return fail(DWBC_ERR_ORDER, "calc_control_torque_lqp: set_task has not been called for every level");
+    const size_t B = b->B, n = b->w.n, m = b->w.m;
+    if (n + CMAX - 6 > LQP_WCAP || (n + CMAX - 6) * (n + CMAX - 5) / 2 > LQP_CHOL_OWN * TEAM)
+        return fail(DWBC_ERR_ARG, "calc_control_torque_lqp: model too large for the LQP kernel (n + cmax - 6 <= 48)");
+    if (!b->lqp_allocated) {
+        if (!dev_alloc(b, &b->lq.y, B * LQP_MAX_LEVELS * (n + CMAX)) || !dev_alloc(b, &b->lq.v1, B * (2 * m + 10 * MAX_ACTIVE_CONTACTS)) ||
+            !dev_alloc(b, &b->lq.tau, B * m) || !dev_alloc(b, &b->lq.status, B) || !dev_alloc(b, &b->lq.iters, B))
+            return DWBC_ERR_CUDA;
+        b->lqp_allocated = true;
+    }
+    int tmax = 1;
+    for (int l = 0; l < b->cfg.nlevels; l++) tmax = b->cfg.tasks[l].dof > tmax ? b->cfg.tasks[l].dof : tmax;
+    const LqpSmem L((int)n, (int)m, tmax);
+    const size_t smem = sizeof(double) * L.total;
+    CK(cudaFuncSetAttribute(lqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        KernelScope ks(b, DWBC_K_LQP, st);
+        DWBC_LAUNCH(lqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, b->lq, tmax);
+    }
+    CK(cudaGetLastError());
+    b->have_lqp = true;
+    const int nlev = 2 + b->cfg.nlevels;
+    if (y_dev)
+        CK(cudaMemcpy2DAsync(y_dev, sizeof(double) * (n + CMAX), b->lq.y + (size_t)(nlev - 1) * (n + CMAX), sizeof(double) * LQP_MAX_LEVELS * (n + CMAX),
+                             sizeof(double) * (n + CMAX), B, cudaMemcpyDeviceToDevice, st));
+    if (tau_dev) CK(cudaMemcpyAsync(tau_dev, b->lq.tau, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));
+    if (status_dev) CK(cudaMemcpyAsync(status_dev, b->lq.status, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+    return DWBC_OK;
+}
+
+int dwbc_batch_get_lqp(dwbc_batch_t *b, int which, int level, double *out_dev, int *rows, int *cols, void *stream) {
+    if (!b) return fail(DWBC_ERR_ARG, "get_lqp: null handle");
+    if (!b->have_lqp) return fail(DWBC_ERR_ORDER, "get_lqp: call calc_control_torque_lqp first");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = b->B, n = b->w.n, m = b->w.m, nvs = n + CMAX;
+    const int nlev = 2 + b->cfg.nlevels;
+    int rr = 0;
+    switch (which) {
+    case DWBC_LQP_Y:
+        if (level < 0 || level >= nlev) return fail(DWBC_ERR_ARG, "get_lqp: level out of range");
+        rr = (int)nvs;
+        break;
+    case DWBC_LQP_V1: rr = (int)(2 * m + 10 * MAX_ACTIVE_CONTACTS); break;
+    case DWBC_LQP_TORQUE: rr = (int)m; break;
+    default: return fail(DWBC_ERR_ARG, "get_lqp: unknown id");
+    }
+    if (rows) *rows = rr;
+    if (cols) *cols = 1;
+    if (!out_dev) return DWBC_OK;
+    if (which == DWBC_LQP_Y)
+        CK(cudaMemcpy2DAsync(out_dev, sizeof(double) * nvs, b->lq.y + (size_t)level * nvs, sizeof(double) * LQP_MAX_LEVELS * nvs, sizeof(double) * nvs, B,
+                             cudaMemcpyDeviceToDevice, st));
+    else
+        CK(cudaMemcpyAsync(out_dev, which == DWBC_LQP_V1 ? b->lq.v1 : b->lq.tau, sizeof(double) * B * rr, cudaMemcpyDeviceToDevice, st));
+    return DWBC_OK;
+}
+
+int dwbc_batch_get_lqp_iterations(dwbc_batch_t *b, int32_t *out_dev, void *stream) {
+    if (!b || !out_dev) return fail(DWBC_ERR_ARG, "get_lqp_iterations: null argument");
+    if (!b->have_lqp) return fail(DWBC_ERR_ORDER, "get_lqp_iterations: call calc_control_torque_lqp first");
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemcpyAsync(out_dev, b->lq.iters, sizeof(int32_t) * b->B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return DWBC_OK;
 }
 

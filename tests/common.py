@@ -89,6 +89,10 @@ def configure_product(rd, config, ncontacts=2):
         rd.add_task_space(1, TASK_LINK_ROTATION, "upperbody_link")
         rd.add_custom_task_space(2, 21)
         rd.set_torque_limit(300.0)
+    elif config == "lqp":  # reference tests/sp_test/jacc_compare.cpp:319-334: COM position + pelvis rotation / left hand 6D
+        rd.add_task_space(0, TASK_LINK_POSITION, "COM")
+        rd.add_task_space(0, TASK_LINK_ROTATION, "pelvis_link")
+        rd.add_task_space(1, TASK_LINK_6D, "L_Wrist2_Link")
     return rd
 
 
@@ -113,11 +117,26 @@ def configure_oracle(ref, config, ncontacts=2):
         ref.add_custom_task(2, 21)
         ref.set_torque_limit(300.0)
         ref.set_task(2, np.zeros(21), posture_selector())
+    elif config == "lqp":
+        ref.add_task(0, orc.TASK_LINK_POSITION, "COM")
+        ref.add_task(0, orc.TASK_LINK_ROTATION, "pelvis_link")
+        ref.add_task(1, orc.TASK_LINK_6D, "L_Wrist2_Link")
     return ref
 
 
 def config_dofs(config):
-    return {"golden": (6, 3), 1: (3, 3), 2: (3, 6, 21)}[config]
+    return {"golden": (6, 3), 1: (3, 3), 2: (3, 6, 21), "lqp": (6, 6)}[config]
+
+
+def lqp_fstars(rng, B, hard=False):
+    """f* of the LQP cases: level 0 = [COM acceleration; pelvis angular acceleration], level 1 = left-hand 6D.  `hard`: a lateral
+    COM acceleration far beyond the friction cone and a large hand acceleration (contact / acceleration rows saturate)."""
+    f0 = np.concatenate([0.5 * rng.standard_normal((B, 3)), 1.0 * rng.standard_normal((B, 3))], axis=1)
+    f1 = 1.0 * rng.standard_normal((B, 6))
+    if hard:
+        f0[:, 1] = 12.0
+        f1[:, :3] *= 30.0
+    return [f0, f1]
 
 
 def relerr(a, b):

@@ -366,3 +366,90 @@ def test_reduced_full_size_equals_full_model():
     eg = ((rg - tg).norm(dim=1) / tg.norm(dim=1)).max().item()
     et = ((rt - tt).norm(dim=1) / tt.norm(dim=1).clamp_min(1.0)).max().item()
     assert eg < 1e-8 and et < 1e-7, (eg, et)
+
+
+def _lqp_product(q, qd, flags, fs):
+    from libdwbc_b200 import RobotDataBatch
+
+    B = q.shape[0]
+    rd = configure_product(RobotDataBatch(URDF, B, 0), "lqp")
+    rd.update_kinematics(T(q), T(qd))
+    rd.set_contact(T(flags, torch.uint8))
+    rd.calc_contact_constraint()
+    for l, f in enumerate(fs):
+        rd.set_task_space(l, T(f))
+    out = rd.calc_control_torque_lqp()
+    torch.cuda.synchronize()
+    return rd, out
+
+
+class _LqpView:
+    """numpy view of the device results with the accessors tests/test_emul_lqp.check_lqp uses"""
+
+    def __init__(self, rd):
+        self.rd = rd
+
+    def get_lqp(self, name, level=0):
+        return self.rd.get_lqp(name, level).cpu().numpy()
+
+
+@pytest.mark.parametrize("hard", [False, True])
+def test_gpu_lqp_vs_oracle(hard):
+    """a10 (config 3(ii) tasks, reference tests/sp_test/jacc_compare.cpp:319-334): every level's y, the level-1 slack and the
+    torque equal the oracle's exact solve to 1e-6, double and single support.  Parity w.r.t. the reference is unpinned (OSQP)."""
+    from tests.test_emul_lqp import check_lqp, lqp_oracle_states
+
+    B = 24
+    q, qd, rng = synth_states(B, 20243)
+    fs = lqp_fstars(rng, B, hard)
+    flags = np.ones((B, 2), dtype=np.uint8)
+    flags[2::4] = [1, 0]
+    flags[3::4] = [0, 1]
+    rd, out = _lqp_product(q, qd, flags, fs)
+    refs = lqp_oracle_states(q, qd, flags, fs)
+    check_lqp(_LqpView(rd), tuple(o.cpu().numpy() for o in out), refs, flags)
+
+
+def test_gpu_lqp_full_size_properties():
+    """B = 65536 (config 3(ii)): size-independent properties of the LQP answer.
+    (1) level 0 (floating-base rows of the equation of motion) holds for the final answer of every solved state;
+    (2) hierarchy: the contact-row residual Jc qdd of the final answer equals the one level 1 left (later levels work in its
+        null space);
+    (3) torque = A[6:,:] qdd + Jc^T[6:,:] Fc + B[6:] and |torque| <= 200 (+1e-6), |qdd_joint| <= 5 + v1 (+1e-6);
+    (4) a seeded sample of 64 states equals the oracle to 1e-6."""
+    from tests.test_emul_lqp import check_lqp, lqp_oracle_states
+
+    B = 65536
+    n = 39
+    q, qd, rng = synth_states(B, 20243)
+    fs = lqp_fstars(rng, B, False)
+    hard = rng.choice(B, B // 20, replace=False)
+    fs[0][hard, 1] = 12.0
+    flags = np.ones((B, 2), dtype=np.uint8)
+    rd, (y, tau, st) = _lqp_product(q, qd, flags, fs)
+    ok = st == 4
+    assert ok.float().mean().item() > 0.98
+    A, Bn, Jc = rd.get("A"), rd.get("B"), rd.get("J_C")
+    qdd, Fc = y[:, :n], y[:, n:]
+    eom = torch.einsum("bij,bj->bi", A, qdd) + torch.einsum("bji,bj->bi", Jc, Fc) + Bn
+    scale = Bn.norm(dim=1).clamp_min(1.0)
+    assert (eom[:, :6].norm(dim=1) / scale)[ok].max().item() < 1e-8
+    assert ((eom[:, 6:] - tau).norm(dim=1) / scale)[ok].max().item() < 1e-10
+    assert tau[ok].abs().max().item() <= 200.0 + 1e-6
+    y1 = rd.get_lqp("y", 1)
+    r1 = torch.einsum("bij,bj->bi", Jc, y1[:, :n])
+    rf = torch.einsum("bij,bj->bi", Jc, qdd)
+    assert ((rf - r1).norm(dim=1))[ok].max().item() < 1e-7
+    v1 = rd.get_lqp("v1")
+    m = 33
+    va = torch.maximum(v1[:, 20:20 + m], v1[:, 20 + m:20 + 2 * m])
+    assert ((qdd[:, 6:].abs() - 5.0 - va)[ok]).max().item() < 1e-6
+    sample = np.random.default_rng(3).choice(B, 64, replace=False)
+    refs = lqp_oracle_states(q[sample], qd[sample], flags[sample], [f[sample] for f in fs])
+
+    class V:
+        def get_lqp(self, name, level=0):
+            return rd.get_lqp(name, level)[torch.as_tensor(sample, device=y.device)].cpu().numpy()
+
+    idx = torch.as_tensor(sample, device=y.device)
+    check_lqp(V(), (y[idx].cpu().numpy(), tau[idx].cpu().numpy(), st[idx].cpu().numpy()), refs, flags[sample])
