@@ -145,17 +145,17 @@ __global__ void __launch_bounds__(TEAM, 5) contact_dynamics_kernel(const DevMode
     for (int e = tid; e < n; e += nt) Gs[e] = w.G[s * n + e];
     tsync();
     // X = A^{-1} Jc^T  (n x c)
-    tgemm<2, 2, false, true>(n, c, n, P, ldn, Jc, ldc, [&](int i, int j, double v) { X[i + j * ldn] = v; });
+    tgemm_mma<2, false, true>(n, c, n, P, ldn, Jc, ldc, [&](int i, int j, double v) { X[i + j * ldn] = v; });
     tsync();
     // Jc X (c x c, SPD) -> Lambda_c (in Lam)
-    tgemm<1, 2, false, false>(c, c, n, Jc, ldc, X, ldn, [&](int i, int j, double v) { Lam[i + j * ldc] = v; });
+    tgemm_mma<1, false, false>(c, c, n, Jc, ldc, X, ldn, [&](int i, int j, double v) { Lam[i + j * ldc] = v; });
     const double piv_c = team_spd_inverse(c, Lam, ldc, Lw, ldc, rd);
     if (!(piv_c > 0.0) && tid == 0) s_ok = 0;
     // Jbar^T = Lambda_c X^T  (c x n)
-    tgemm<2, 2, false, true>(c, n, c, Lam, ldc, X, ldn, [&](int i, int j, double v) { Jbar[i + j * ldc] = v; });
+    tgemm_mma<2, false, true>(c, n, c, Lam, ldc, X, ldn, [&](int i, int j, double v) { Jbar[i + j * ldc] = v; });
     tsync();
     // A^{-1} N_c = A^{-1} - X Jbar^T
-    tgemm<4, 4, false, false>(n, n, c, X, ldn, Jbar, ldc, [&](int i, int j, double v) { P[i + j * ldn] -= v; });
+    tgemm_mma<2, false, false>(n, n, c, X, ldn, Jbar, ldc, [&](int i, int j, double v) { P[i + j * ldn] -= v; });
     tsync();
     // outputs of a3 that do not depend on the pseudo-inverse
     {
@@ -199,31 +199,43 @@ __global__ void __launch_bounds__(TEAM, 5) contact_dynamics_kernel(const DevMode
             V[a + b * ldm] = v;
         }
         tsync();
-        // modified Gram-Schmidt, two passes (warp 0; rows of V across lanes, m may exceed 32)
-        if (warp == 0) {
-            for (int b = 0; b < r; b++) {
-                for (int pass = 0; pass < 2; pass++) {
-                    for (int k = 0; k < b; k++) {
-                        double d = 0.0;
-                        for (int a = lane; a < m; a += 32) d = fma(V[a + k * ldm], V[a + b * ldm], d);
-                        d = warp_sum(d);
-                        for (int a = lane; a < m; a += 32) V[a + b * ldm] = fma(-d, V[a + k * ldm], V[a + b * ldm]);
-                        __syncwarp();
-                    }
+        // orthonormalise V (m x r) by Cholesky-QR, twice: G = V^T V = R^T R, V <- V R^{-1}.  (Two-pass modified Gram-Schmidt
+        // on one warp was a fifth of this kernel's stall samples: three warps waited for r(r-1) dependent warp reductions.)
+        for (int pass = 0; pass < 2; pass++) {
+            for (int e = tid; e < r * r; e += nt) {
+                const int j = e / r, i = e - j * r;
+                if (i <= j) {
+                    double d = 0.0;
+                    for (int a = 0; a < m; a++) d = fma(V[a + i * ldm], V[a + j * ldm], d);
+                    Aug[i + j * lda] = d;
                 }
-                double nn = 0.0;
-                for (int a = lane; a < m; a += 32) nn = fma(V[a + b * ldm], V[a + b * ldm], nn);
-                nn = warp_sum(nn);
-                if (!(nn > 1e-280)) {
-                    nn = 1.0;
-                    if (lane == 0) s_ok = 0;
-                }
-                const double rn = 1.0 / sqrt(nn);
-                for (int a = lane; a < m; a += 32) V[a + b * ldm] *= rn;
-                __syncwarp();
             }
+            tsync();
+            if (tid == 0) {
+                for (int j = 0; j < r; j++)
+                    for (int i = 0; i <= j; i++) {
+                        double sacc = Aug[i + j * lda];
+                        for (int k = 0; k < i; k++) sacc = fma(-Aug[k + i * lda], Aug[k + j * lda], sacc);
+                        if (i == j) {
+                            if (!(sacc > 1e-280)) {
+                                sacc = 1.0;
+                                s_ok = 0;
+                            }
+                            Aug[j + j * lda] = sqrt(sacc);
+                        } else {
+                            Aug[i + j * lda] = sacc / Aug[i + i * lda];
+                        }
+                    }
+            }
+            tsync();
+            for (int a = tid; a < m; a += nt)
+                for (int j = 0; j < r; j++) {
+                    double x = V[a + j * ldm];
+                    for (int k = 0; k < j; k++) x = fma(-V[a + k * ldm], Aug[k + j * lda], x);
+                    V[a + j * ldm] = x / Aug[j + j * lda];
+                }
+            tsync();
         }
-        tsync();
         // V2 (rows = basis vectors), reference layout r x m
         {
             double *g = w.V2 + s * RMAX * m;
@@ -233,7 +245,7 @@ __global__ void __launch_bounds__(TEAM, 5) contact_dynamics_kernel(const DevMode
             }
         }
         // W + V V^T in place
-        tgemm<3, 3, false, true>(m, m, r, V, ldm, V, ldm, [&](int i, int j, double v) { Wblk[i + j * ldn] += v; });
+        tgemm_mma<2, false, true>(m, m, r, V, ldm, V, ldm, [&](int i, int j, double v) { Wblk[i + j * ldn] += v; });
     } else {
         double *g = w.V2 + s * RMAX * m;
         for (int e = tid; e < RMAX * m; e += nt) g[e] = 0.0;
@@ -242,7 +254,7 @@ __global__ void __launch_bounds__(TEAM, 5) contact_dynamics_kernel(const DevMode
     const double piv_w = team_spd_inverse(m, Wblk, ldn, Q, ldm, rd);
     if (!(piv_w > 0.0) && tid == 0) s_ok = 0;
     if (r > 0) {
-        tgemm<3, 3, false, true>(m, m, r, V, ldm, V, ldm, [&](int i, int j, double v) { Wblk[i + j * ldn] -= v; });
+        tgemm_mma<2, false, true>(m, m, r, V, ldm, V, ldm, [&](int i, int j, double v) { Wblk[i + j * ldn] -= v; });
         // Mx = Jbar^T[0:r, 6:6+m] V  (r x r);  NwJw = V Mx^{-1}
         tgemm<1, 1, false, false>(r, r, m, Jbar + 6 * ldc, ldc, V, ldm, [&](int i, int j, double v) { Aug[i + j * lda] = v; });
         for (int e = tid; e < r * r; e += nt) {

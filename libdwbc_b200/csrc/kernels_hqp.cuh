@@ -842,7 +842,7 @@ __global__ void __launch_bounds__(TEAM, 6) hqp_kernel(const DevModel *__restrict
             // base = tau_prev + Ntorque f*
             tgemv<false>(m, t, U, ldm, fs, [&](int i, double v) { base[i] = tprev[i] + v; });
             // AU = Atemp U
-            tgemm<2, 2, false, false>(nc, nv, m, At, ldc, U, ldm, [&](int i, int j, double v) { AU[i + j * ldc] = v; });
+            tgemm_mma<2, false, false>(nc, nv, m, At, ldc, U, ldm, [&](int i, int j, double v) { AU[i + j * ldc] = v; });
             tsync();
             if (mt)
                 for (int i = tid; i < m; i += nt) {
@@ -897,7 +897,7 @@ __global__ void __launch_bounds__(TEAM, 6) hqp_kernel(const DevModel *__restrict
             tcopy(m, r, NwJw, m, U, ldm);
             build_At();
             tsync();
-            tgemm<2, 1, false, false>(nc, r, m, At, ldc, U, ldm, [&](int i, int j, double v) { AU[i + j * ldc] = v; });
+            tgemm_mma<1, false, false>(nc, r, m, At, ldc, U, ldm, [&](int i, int j, double v) { AU[i + j * ldc] = v; });
             if (mt)
                 for (int i = tid; i < m; i += nt) {
                     b[i] = cfg->tlim[i] - base[i];

@@ -136,48 +136,33 @@ __global__ void __launch_bounds__(TEAM, 5) task_space_kernel(const DevModel *__r
         tsync();
         tcopy(t, n, Js, ldt, w.Jt[l] + s * (long long)t * n, t);
         // T = J (A^{-1} N_c)      (t x n)
-        if (t <= 8)
-            tgemm<1, 2, false, false>(t, n, n, Js, ldt, P, n, [&](int i, int j, double v) { T[i + j * ldt] = v; });
-        else
-            tgemm<3, 3, false, false>(t, n, n, Js, ldt, P, n, [&](int i, int j, double v) { T[i + j * ldt] = v; });
+        tgemm_mma<2, false, false>(t, n, n, Js, ldt, P, n, [&](int i, int j, double v) { T[i + j * ldt] = v; });
         tsync();
         // Lambda_t = (T J^T)^{-1}  (t x t)
-        tgemm<1, 2, false, true>(t, t, n, T, ldt, Js, ldt, [&](int i, int j, double v) { S1[i + j * ldt] = v; });
+        tgemm_mma<1, false, true>(t, t, n, T, ldt, Js, ldt, [&](int i, int j, double v) { S1[i + j * ldt] = v; });
         const double cnd1 = spd_inverse_small(t, S1, ldt, S3, rd);  // S1 = Lambda_t
         if (!(cnd1 > 1e-14)) ok = 0;
         tcopy(t, t, S1, ldt, w.Lamt[l] + s * (long long)t * t, t);
         // Q = Lambda_t T[:, 6:]    (t x m) -> X1 (J_task is dead)
         double *Qm = X1;
-        if (t <= 8)
-            tgemm<1, 2, false, false>(t, m, t, S1, ldt, T + 6 * ldt, ldt, [&](int i, int j, double v) { Qm[i + j * ldt] = v; });
-        else
-            tgemm<3, 3, false, false>(t, m, t, S1, ldt, T + 6 * ldt, ldt, [&](int i, int j, double v) { Qm[i + j * ldt] = v; });
+        tgemm_mma<2, false, false>(t, m, t, S1, ldt, T + 6 * ldt, ldt, [&](int i, int j, double v) { Qm[i + j * ldt] = v; });
         tsync();
         // WQ = W^+ Q^T             (m x t)
         double *WQ = X2;
-        if (t <= 8)
-            tgemm<2, 1, false, true>(m, t, m, Winv, m, Qm, ldt, [&](int i, int j, double v) { WQ[i + j * ldm] = v; });
-        else
-            tgemm<2, 3, false, true>(m, t, m, Winv, m, Qm, ldt, [&](int i, int j, double v) { WQ[i + j * ldm] = v; });
+        tgemm_mma<2, false, true>(m, t, m, Winv, m, Qm, ldt, [&](int i, int j, double v) { WQ[i + j * ldm] = v; });
         tsync();
         // (Q W^+ Q^T)^{-1}         (t x t)
-        tgemm<1, 2, false, false>(t, t, m, Qm, ldt, WQ, ldm, [&](int i, int j, double v) { S2[i + j * ldt] = v; });
+        tgemm_mma<1, false, false>(t, t, m, Qm, ldt, WQ, ldm, [&](int i, int j, double v) { S2[i + j * ldt] = v; });
         const double cnd2 = spd_inverse_small(t, S2, ldt, S3, rd);
         if (!(cnd2 > 1e-14)) ok = 0;
         // J_kt = WQ (Q W^+ Q^T)^{-1}   (m x t) -> X1 (Q is dead)
         double *Jkt = X1;
-        if (t <= 8)
-            tgemm<2, 1, false, false>(m, t, t, WQ, ldm, S2, ldt, [&](int i, int j, double v) { Jkt[i + j * ldm] = v; });
-        else
-            tgemm<2, 3, false, false>(m, t, t, WQ, ldm, S2, ldt, [&](int i, int j, double v) { Jkt[i + j * ldm] = v; });
+        tgemm_mma<2, false, false>(m, t, t, WQ, ldm, S2, ldt, [&](int i, int j, double v) { Jkt[i + j * ldm] = v; });
         tsync();
         tcopy(m, t, Jkt, ldm, w.Jkt[l] + s * (long long)m * t, m);
         // JL = J_kt Lambda_t       (m x t) -> X2 (WQ is dead)
         double *JL = X2;
-        if (t <= 8)
-            tgemm<2, 1, false, false>(m, t, t, Jkt, ldm, S1, ldt, [&](int i, int j, double v) { JL[i + j * ldm] = v; });
-        else
-            tgemm<2, 3, false, false>(m, t, t, Jkt, ldm, S1, ldt, [&](int i, int j, double v) { JL[i + j * ldm] = v; });
+        tgemm_mma<2, false, false>(m, t, t, Jkt, ldm, S1, ldt, [&](int i, int j, double v) { JL[i + j * ldm] = v; });
         tsync();
         // torque_h = JL f*  (closed-form branch; the HQP kernel overwrites it with f* + f*_qp)
         tgemv<false>(m, t, JL, ldm, fs, [&](int i, double v) { w.torque_h[l][s * m + i] = v; });
@@ -185,10 +170,7 @@ __global__ void __launch_bounds__(TEAM, 5) task_space_kernel(const DevModel *__r
         double *Nt = JL;
         if (l > 0) {
             Nt = X1;
-            if (t <= 8)
-                tgemm<2, 1, false, false>(m, t, m, Nul, ldm, JL, ldm, [&](int i, int j, double v) { Nt[i + j * ldm] = v; });
-            else
-                tgemm<2, 3, false, false>(m, t, m, Nul, ldm, JL, ldm, [&](int i, int j, double v) { Nt[i + j * ldm] = v; });
+            tgemm_mma<2, false, false>(m, t, m, Nul, ldm, JL, ldm, [&](int i, int j, double v) { Nt[i + j * ldm] = v; });
             tsync();
         }
         tcopy(m, t, Nt, ldm, w.Ntq[l] + s * (long long)m * t, m);
@@ -197,10 +179,10 @@ __global__ void __launch_bounds__(TEAM, 5) task_space_kernel(const DevModel *__r
         // Null_l = Null_{l-1} - Ntorque T[:, 6:]     (not needed for the last level)
         if (l + 1 < nl || null_last) {  // null_last: the reduced variant needs Null of its last contact-chain level
             if (l == 0) {
-                tgemm<3, 3, false, false>(m, m, t, Nt, ldm, T + 6 * ldt, ldt,
+                tgemm_mma<2, false, false>(m, m, t, Nt, ldm, T + 6 * ldt, ldt,
                                           [&](int i, int j, double v) { Nul[i + j * ldm] = (i == j ? 1.0 : 0.0) - v; });
             } else {
-                tgemm<3, 3, false, false>(m, m, t, Nt, ldm, T + 6 * ldt, ldt, [&](int i, int j, double v) { Nul[i + j * ldm] -= v; });
+                tgemm_mma<2, false, false>(m, m, t, Nt, ldm, T + 6 * ldt, ldt, [&](int i, int j, double v) { Nul[i + j * ldm] -= v; });
             }
             tsync();
             tcopy(m, m, Nul, ldm, w.Null[l] + s * (long long)m * m, m);

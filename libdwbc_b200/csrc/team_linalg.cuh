@@ -92,6 +92,85 @@ __device__ __forceinline__ void tgemm(int M, int N, int K, const double *__restr
     }
 }
 
+// ---- FP64 tensor-core products (DMMA) ---------------------------------------------------------------------
+// One mma.sync.m8n8k4.f64 does 256 FMAs for ONE issue slot and two 8-byte operand loads per lane; the register-tiled
+// tgemm above needs 8 issue slots and 8-16 shared-memory wavefronts for the same work, and ncu shows the dense stages
+// limited by exactly those (LSU wavefronts 45-87 %, DFMA 10 % of the issued instructions; profiles/r01_ncu_main_lqpbuild.md).
+// Measured on this pool's B200 (tools/dmma_probe.cu, profiles/r01_dmma_probe.json): DMMA chain 37.2 TFLOP/s vs DFMA chain
+// 34.1; a 40x40x40 product out of shared memory with 128 threads: 21.5 TFLOP/s with DMMA vs 7.9 with 2x2 register tiles.
+// Fragment layout (PTX ISA, m8n8k4 .f64): lane = 4 g + t;  a = A(g, t);  b = B(t, g);  d0, d1 = D(g, 2t), D(g, 2t + 1).
+#ifdef DWBC_CPU_EMUL
+__device__ inline void dmma884(double &d0, double &d1, double a, double b) {
+    const int lane = lane_id(), g = lane >> 2, t = lane & 3;
+    double s0 = d0, s1 = d1;
+    for (int k = 0; k < 4; k++) {
+        const double ak = __shfl_sync(DWBC_FULL, a, g * 4 + k);
+        const double b0 = __shfl_sync(DWBC_FULL, b, (2 * t) * 4 + k);
+        const double b1 = __shfl_sync(DWBC_FULL, b, (2 * t + 1) * 4 + k);
+        s0 = fma(ak, b0, s0);
+        s1 = fma(ak, b1, s1);
+    }
+    d0 = s0;
+    d1 = s1;
+}
+#else
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+#endif
+
+// Same contract as tgemm (C(i,j) <- epi(i, j, sum_k opA(i,k) opB(k,j)), any M, N, K; operands in shared or global memory),
+// computed on the FP64 tensor cores.  A work item is one 8-row band times NT adjacent 8-column tiles (the A fragment is
+// reused NT times); items are dealt round-robin to the warps of the team.  Ragged edges are zero-filled by predicated
+// loads.  Requires blockDim.x to be a multiple of 32; every warp runs the same item count modulo one.
+// KTRI: opA(i,k) = 0 for k < i and opB(k,j) = 0 for k < j (the X^T X product of a lower-triangular X): the k loop of an
+// item starts at its first row / column.
+template <int NT, bool TA, bool TB, bool KTRI = false, class Epi>
+__device__ __forceinline__ void tgemm_mma(int M, int N, int K, const double *__restrict__ A, int lda, const double *__restrict__ B, int ldb,
+                                          Epi epi) {
+    const int lane = lane_id(), warp = t_id() >> 5, nw = t_n() >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int tr = (M + 7) >> 3, tc = (N + 7) >> 3, gc = (tc + NT - 1) / NT;
+    for (int item = warp; item < tr * gc; item += nw) {
+        const int gj = item / tr, bi = item - gj * tr;
+        const int i = bi * 8 + g;
+        const bool iv = i < M;
+        const double *ap = A + (iv ? i : 0) * (TA ? lda : 1);
+        const double *bp[NT];
+        bool jv[NT];
+        double c[NT][2];
+        DWBC_UNROLL(NT)
+        for (int jj = 0; jj < NT; jj++) {
+            const int j = (gj * NT + jj) * 8 + g;
+            jv[jj] = j < N;
+            bp[jj] = B + (jv[jj] ? j : 0) * (TB ? 1 : ldb);
+            c[jj][0] = 0.0;
+            c[jj][1] = 0.0;
+        }
+        const int sa = TA ? 1 : lda, sb = TB ? ldb : 1;
+        const int kbeg = KTRI ? 8 * (bi > gj * NT ? bi : gj * NT) : 0;
+        DWBC_UNROLL(2)
+        for (int k0 = kbeg; k0 < K; k0 += 4) {
+            const int k = k0 + t;
+            const bool kv = k < K;
+            const double a = (iv && kv) ? ap[k * sa] : 0.0;
+            DWBC_UNROLL(NT)
+            for (int jj = 0; jj < NT; jj++) {
+                if ((gj * NT + jj) * 8 < N) {  // warp-uniform: skip tiles beyond the last column
+                    const double b = (jv[jj] && kv) ? bp[jj][k * sb] : 0.0;
+                    dmma884(c[jj][0], c[jj][1], a, b);
+                }
+            }
+        }
+        DWBC_UNROLL(NT)
+        for (int jj = 0; jj < NT; jj++) {
+            const int j = (gj * NT + jj) * 8 + 2 * t;
+            if (iv && j < N) epi(i, j, c[jj][0]);
+            if (iv && j + 1 < N) epi(i, j + 1, c[jj][1]);
+        }
+    }
+}
+
 // y(i) <- epi(i, sum_k opA(i,k) x(k)).  Four adjacent lanes share one row (each takes every 4th k) and combine with
 // two shuffles, so a 33..39-row product keeps the whole team busy.  Requires blockDim.x to be a multiple of 32.
 template <bool TA, class Epi>
@@ -199,50 +278,12 @@ __device__ __noinline__ void ttri_inverse(int n, const double *L, int ld, const 
     }
 }
 
-// Out(i,j) <- epi(i, j, (A^{-1})(i,j)) with A^{-1} = Xi^T Xi for the lower-triangular Xi = L^{-1}: only k >= max(i,j)
-// contributes.  Each thread computes a TR x TC tile of the LOWER triangle and mirrors it.  No synchronisation.
+// Out(i,j) <- epi(i, j, (A^{-1})(i,j)) with A^{-1} = Xi^T Xi for the lower-triangular Xi = L^{-1} (full storage, zeros above
+// the diagonal): only k >= max(i,j) contributes.  Computed for the full square on the tensor cores (the register-tiled
+// triangle version kept 55 of 128 threads busy for n = 39 and was a third of ainv_kernel's stall samples).  No synchronisation.
 template <class Epi>
 __device__ __forceinline__ void tsyrk_inverse(int n, const double *Xi, int ldx, Epi epi) {
-    constexpr int T = 4;
-    const int tb = (n + T - 1) / T;  // tiles per dimension (blocked, not cyclic: the k-range depends on the tile position)
-    const int ntiles = tb * (tb + 1) / 2;
-    for (int tile = t_id(); tile < ntiles; tile += t_n()) {
-        // tile -> (bi >= bj)
-        int bj = 0, rem = tile;
-        while (rem >= tb - bj) rem -= tb - bj, bj++;
-        const int bi = bj + rem;
-        const int i0 = bi * T, j0 = bj * T;
-        double acc[T][T];
-        DWBC_UNROLL(T)
-        for (int r = 0; r < T; r++) {
-            DWBC_UNROLL(T)
-            for (int c = 0; c < T; c++) acc[r][c] = 0.0;
-        }
-        int io[T], jo[T];
-        DWBC_UNROLL(T)
-        for (int r = 0; r < T; r++) io[r] = (i0 + r < n ? i0 + r : i0) * ldx, jo[r] = (j0 + r < n ? j0 + r : j0) * ldx;
-        for (int k = i0; k < n; k++) {  // Xi(k, i) = 0 for k < i, and i >= i0
-            double a[T], b[T];
-            DWBC_UNROLL(T)
-            for (int r = 0; r < T; r++) a[r] = Xi[k + io[r]], b[r] = Xi[k + jo[r]];
-            DWBC_UNROLL(T)
-            for (int r = 0; r < T; r++) {
-                DWBC_UNROLL(T)
-                for (int c = 0; c < T; c++) acc[r][c] = fma(a[r], b[c], acc[r][c]);
-            }
-        }
-        DWBC_UNROLL(T)
-        for (int r = 0; r < T; r++) {
-            DWBC_UNROLL(T)
-            for (int c = 0; c < T; c++) {
-                const int i = i0 + r, j = j0 + c;
-                if (i < n && j < n && i >= j) {
-                    epi(i, j, acc[r][c]);
-                    if (i != j) epi(j, i, acc[r][c]);
-                }
-            }
-        }
-    }
+    tgemm_mma<2, true, false, true>(n, n, n, Xi, ldx, Xi, ldx, epi);
 }
 
 }  // namespace dwbc
