@@ -239,6 +239,29 @@ int dwbc_batch_get_lqp(dwbc_batch_t *b, int which, int level, double *out_dev, i
 /* active-set iterations of the last LQP call per state: out_dev [B] int32 */
 int dwbc_batch_get_lqp_iterations(dwbc_batch_t *b, int32_t *out_dev, void *stream);
 
+/* ---- f* generation (task PD on quintic / slerp trajectories), the step before the path.
+ * TaskLink::SetTaskGain / SetTrajectoryQuintic / SetTrajectoryRotation / GetFstarPosPD / GetFstarRotPD
+ * (reference src/task.cpp:223-334), QuinticSpline and GetPhi (src/math.cpp:127-183, 272-287), per LINK_MODE as in
+ * UpdateTaskSpace (src/dwbc.cpp:714-785).  `link_index` counts the task links of the level in AddTaskSpace order.
+ * gains18_host = [pos_p, pos_d, pos_a, rot_p, rot_d, rot_a] (3 each), shared by all states.  Trajectory parameters are
+ * per state and stay caller-owned device buffers: time_dev [B x 2] = (start, end), positions / velocities [B x 3],
+ * rotations [B x 9] row-major.  (The reference's twist_init / twist_desired are stored but never used by GetFstarRotPD.) */
+int dwbc_batch_set_task_gain(dwbc_batch_t *b, int level, int link_index, const double *gains18_host);
+int dwbc_batch_set_trajectory_quintic(dwbc_batch_t *b, int level, int link_index, const double *time_dev, const double *pos_init_dev,
+                                      const double *vel_init_dev, const double *pos_desired_dev, const double *vel_desired_dev);
+int dwbc_batch_set_trajectory_rotation(dwbc_batch_t *b, int level, int link_index, const double *time_dev, const double *rot_init_dev,
+                                       const double *rot_desired_dev);
+/* f* of `level` at control_time_dev [B] from the link states of the last update_kinematics (whose qdot buffer must still be
+ * valid): writes the rows of every task link whose trajectory is set into fstar_dev [B x t] (other rows are left as they
+ * are, like f_star_ in the reference); pass fstar_dev to dwbc_batch_set_task afterwards. */
+int dwbc_batch_calc_fstar(dwbc_batch_t *b, int level, const double *control_time_dev, double *fstar_dev, void *stream);
+
+/* ---- section 8(f) row 3: the RL caller's wire format (reference src/pybind/rl_wbc_bridge.cpp:88-107, 131-139).
+ * update_kinematics from MuJoCo-ordered qpos [B x (n+1)] = [xyz | qw qx qy qz | joints] and qvel [B x n]. */
+int dwbc_batch_update_kinematics_mujoco(dwbc_batch_t *b, const double *qpos_dev, const double *qvel_dev, void *stream);
+/* getTorqueCommand(): float32 (torque_grav_ + torque_task_ + torque_contact_) of the last solve, out_dev [B x m]. */
+int dwbc_batch_get_torque_command_f32(dwbc_batch_t *b, float *out_dev, void *stream);
+
 /* ---- whole cycle with HOST buffers (pinned or pageable): H2D, all stages, D2H, synchronised on return.
  * This is what the RobotData shim, the pybind bridge and bench.py's end-to-end timing call.
  * fstar_host: concatenation over levels of [B x t_l] blocks. flags_host [B x ncontact]. */

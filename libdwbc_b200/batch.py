@@ -64,7 +64,7 @@ class _CudaBackend:
 
     def empty(self, shape, dtype="f8"):
         t = self.torch
-        dt = {"f8": t.float64, "u1": t.uint8, "i4": t.int32, "u4": t.int32}[dtype]
+        dt = {"f8": t.float64, "f4": t.float32, "u1": t.uint8, "i4": t.int32, "u4": t.int32}[dtype]
         return t.empty(shape, dtype=dt, device=self.device)
 
     def check(self, x, dtype="f8"):
@@ -248,6 +248,52 @@ class RobotDataBatch:
 
     def get_reduced(self, name, level=0):
         return self._get(self.L.dwbc_batch_get_reduced_matrix, _RMATS[name][0], level)
+
+    # ---- f* from trajectories, MuJoCo layout, float32 torque command ----
+    def set_task_gain(self, level, link_index, pos_p, pos_d, pos_a, rot_p, rot_d, rot_a):
+        """TaskLink::SetTaskGain (reference src/task.cpp:253-264)"""
+        g = np.concatenate([np.broadcast_to(np.asarray(x, dtype=np.float64), (3,)) for x in (pos_p, pos_d, pos_a, rot_p, rot_d, rot_a)])
+        g = np.ascontiguousarray(g)
+        self._ck(self.L.dwbc_batch_set_task_gain(self._h, int(level), int(link_index), g.ctypes.data_as(_dp)))
+
+    def set_trajectory_quintic(self, level, link_index, time, pos_init, vel_init, pos_desired, vel_desired):
+        """TaskLink::SetTrajectoryQuintic per state: time [B, 2] = (start, end), the rest [B, 3] (device tensors, kept alive here)."""
+        be = self.be
+        a = [be.check(x) for x in (time, pos_init, vel_init, pos_desired, vel_desired)]
+        self._keep[("trajp", level, link_index)] = a
+        self._ck(self.L.dwbc_batch_set_trajectory_quintic(self._h, int(level), int(link_index), *[be.ptr(x) for x in a]))
+
+    def set_trajectory_rotation(self, level, link_index, time, rot_init, rot_desired):
+        """TaskLink::SetTrajectoryRotation per state: time [B, 2], rotations [B, 3, 3] (row-major)."""
+        be = self.be
+        a = [be.check(x) for x in (time, rot_init, rot_desired)]
+        self._keep[("trajr", level, link_index)] = a
+        self._ck(self.L.dwbc_batch_set_trajectory_rotation(self._h, int(level), int(link_index), *[be.ptr(x) for x in a]))
+
+    def calc_fstar(self, level, control_time, fstar=None):
+        """GetFstarPosPD / GetFstarRotPD of every task link of `level` whose trajectory is set; returns f* [B, t]."""
+        be = self.be
+        ct = be.check(control_time)
+        if fstar is None:
+            fstar = be.empty((self.batch, self.task_dofs[level]))
+        self._ck(self.L.dwbc_batch_calc_fstar(self._h, int(level), be.ptr(ct), be.ptr(be.check(fstar)), be.stream()))
+        return fstar
+
+    def update_kinematics_mujoco(self, qpos, qvel):
+        """RlWBCBridge::UpdateKinematics (reference src/pybind/rl_wbc_bridge.cpp:82-107): MuJoCo-ordered qpos / qvel."""
+        be = self.be
+        qpos, qvel = be.check(qpos), be.check(qvel)
+        if tuple(qpos.shape) != (self.batch, self.system_dof_ + 1) or tuple(qvel.shape) != (self.batch, self.system_dof_):
+            raise DwbcError("q size is not matched")
+        self._keep["q"], self._keep["qd"] = qpos, qvel
+        self._ck(self.L.dwbc_batch_update_kinematics_mujoco(self._h, be.ptr(qpos), be.ptr(qvel), be.stream()))
+
+    def get_torque_command(self):
+        """RlWBCBridge::getTorqueCommand (reference src/pybind/rl_wbc_bridge.cpp:131-139): float32 [B, m]."""
+        be = self.be
+        out = be.empty((self.batch, self.model_dof_), "f4")
+        self._ck(self.L.dwbc_batch_get_torque_command_f32(self._h, be.ptr(out), be.stream()))
+        return out
 
     # ---- a10: LQP variant (reference src/dwbc.cpp:4304-4454, src/dwbc_hqp.cpp; call order of tests/sp_test/jacc_compare.cpp:367-384) ----
     def calc_control_torque_lqp(self, out=None):

@@ -14,6 +14,7 @@
 #include "cuda_compat.h"
 #include "kernels_contact.cuh"
 #include "kernels_hqp.cuh"
+#include "kernels_io.cuh"
 #include "kernels_lqp.cuh"
 #include "kernels_post.cuh"
 #include "kernels_reduced.cuh"
@@ -66,6 +67,14 @@ struct dwbc_batch {
     int red_rn = 0;
     std::string red_task_sig;
     bool have_red_dyn = false, have_red_cc = false;
+    // section 8(f): f* generation and the MuJoCo / float32 wire format
+    struct TrajHost {
+        double gains[18] = {0};
+        const double *pos_time = nullptr, *pos_init = nullptr, *vel_init = nullptr, *pos_des = nullptr, *vel_des = nullptr;
+        const double *rot_time = nullptr, *rot_init = nullptr, *rot_des = nullptr;
+    } traj[MAX_TASK_LINKS];
+    const double *last_qd = nullptr;  // qdot of the last update_kinematics (caller-owned or mj_qd)
+    double *mj_q = nullptr, *mj_qd = nullptr;
     // a10 LQP variant
     LqpOut lq{};
     bool lqp_allocated = false, have_lqp = false;
@@ -387,6 +396,7 @@ int dwbc_batch_update_kinematics(dwbc_batch_t *b, const double *q_dev, const dou
     }
     CK(cudaGetLastError());
     b->have_kin = true;
+    b->last_qd = qdot_dev;
     b->have_contact = b->have_cc = false;
     b->have_red_dyn = b->have_red_cc = false;
     return DWBC_OK;
@@ -1066,6 +1076,106 @@ int dwbc_batch_get_lqp_iterations(dwbc_batch_t *b, int32_t *out_dev, void *strea
     if (!b->have_lqp) return fail(DWBC_ERR_ORDER, "get_lqp_iterations: call calc_control_torque_lqp first");
     CK(cudaSetDevice(b->device));
     CK(cudaMemcpyAsync(out_dev, b->lq.iters, sizeof(int32_t) * b->B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return DWBC_OK;
+}
+
+
+// ---- f* from trajectories, MuJoCo layout, float32 torque command ----
+namespace {
+int traj_slot(dwbc_batch *b, int level, int link_index, const char *who) {
+    if (!b) return fail(DWBC_ERR_ARG, std::string(who) + ": null handle");
+    if (level < 0 || level >= b->cfg.nlevels || b->cfg.tasks[level].custom) return fail(DWBC_ERR_ARG, std::string(who) + ": level out of range or TASK_CUSTOM");
+    if (link_index < 0 || link_index >= b->cfg.tasks[level].link_count) return fail(DWBC_ERR_ARG, std::string(who) + ": task link index out of range");
+    return b->cfg.tasks[level].link_start + link_index;
+}
+}  // namespace
+
+int dwbc_batch_set_task_gain(dwbc_batch_t *b, int level, int link_index, const double *gains18_host) {
+    const int k = traj_slot(b, level, link_index, "set_task_gain");
+    if (k < 0) return k;
+    if (!gains18_host) return fail(DWBC_ERR_ARG, "set_task_gain: null gains");
+    std::memcpy(b->traj[k].gains, gains18_host, sizeof(double) * 18);
+    return DWBC_OK;
+}
+int dwbc_batch_set_trajectory_quintic(dwbc_batch_t *b, int level, int link_index, const double *time_dev, const double *pos_init_dev,
+                                      const double *vel_init_dev, const double *pos_desired_dev, const double *vel_desired_dev) {
+    const int k = traj_slot(b, level, link_index, "set_trajectory_quintic");
+    if (k < 0) return k;
+    if (b->cfg.tlinks[k].mode > DWBC_TASK_LINK_POSITION_CUSTOM_FRAME) return fail(DWBC_ERR_ARG, "set_trajectory_quintic: the task link has no position rows");
+    if (!time_dev || !pos_init_dev || !vel_init_dev || !pos_desired_dev || !vel_desired_dev) return fail(DWBC_ERR_ARG, "set_trajectory_quintic: null argument");
+    auto &t = b->traj[k];
+    t.pos_time = time_dev; t.pos_init = pos_init_dev; t.vel_init = vel_init_dev; t.pos_des = pos_desired_dev; t.vel_des = vel_desired_dev;
+    return DWBC_OK;
+}
+int dwbc_batch_set_trajectory_rotation(dwbc_batch_t *b, int level, int link_index, const double *time_dev, const double *rot_init_dev,
+                                       const double *rot_desired_dev) {
+    const int k = traj_slot(b, level, link_index, "set_trajectory_rotation");
+    if (k < 0) return k;
+    const int mode = b->cfg.tlinks[k].mode;
+    if (mode > DWBC_TASK_LINK_6D_CUSTOM_FRAME && mode < DWBC_TASK_LINK_ROTATION) return fail(DWBC_ERR_ARG, "set_trajectory_rotation: the task link has no rotation rows");
+    if (!time_dev || !rot_init_dev || !rot_desired_dev) return fail(DWBC_ERR_ARG, "set_trajectory_rotation: null argument");
+    auto &t = b->traj[k];
+    t.rot_time = time_dev; t.rot_init = rot_init_dev; t.rot_des = rot_desired_dev;
+    return DWBC_OK;
+}
+int dwbc_batch_calc_fstar(dwbc_batch_t *b, int level, const double *control_time_dev, double *fstar_dev, void *stream) {
+    if (!b || !control_time_dev || !fstar_dev) return fail(DWBC_ERR_ARG, "calc_fstar: null argument");
+    if (!b->have_kin) return fail(DWBC_ERR_ORDER, "calc_fstar: call update_kinematics first");
+    if (level < 0 || level >= b->cfg.nlevels || b->cfg.tasks[level].custom) return fail(DWBC_ERR_ARG, "calc_fstar: level out of range or TASK_CUSTOM");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const TaskCfg &tc = b->cfg.tasks[level];
+    TrajLevel lv{};
+    lv.nlinks = tc.link_count;
+    int row = 0;
+    for (int i = 0; i < tc.link_count; i++) {
+        const TaskLinkCfg &c = b->cfg.tlinks[tc.link_start + i];
+        const auto &h = b->traj[tc.link_start + i];
+        TrajLink &t = lv.links[i];
+        t.mode = c.mode; t.link = c.link; t.row = row; t.dof = c.dof;
+        std::memcpy(t.point, c.point, sizeof(t.point));
+        std::memcpy(t.gains, h.gains, sizeof(t.gains));
+        t.pos_time = h.pos_time; t.pos_init = h.pos_init; t.vel_init = h.vel_init; t.pos_des = h.pos_des; t.vel_des = h.vel_des;
+        t.rot_time = h.rot_time; t.rot_init = h.rot_init; t.rot_des = h.rot_des;
+        row += c.dof;
+    }
+    const long long total = (long long)b->B * lv.nlinks;
+    const int threads = 128, grid = (int)((total + threads - 1) / threads);
+    {
+        KernelScope ks(b, DWBC_K_POST, st);
+        DWBC_LAUNCH(fstar_pd_kernel, grid, threads, 0, st, b->d_model, b->w, b->last_qd, lv, tc.dof, control_time_dev, fstar_dev);
+    }
+    CK(cudaGetLastError());
+    return DWBC_OK;
+}
+
+int dwbc_batch_update_kinematics_mujoco(dwbc_batch_t *b, const double *qpos_dev, const double *qvel_dev, void *stream) {
+    if (!b || !qpos_dev || !qvel_dev) return fail(DWBC_ERR_ARG, "update_kinematics_mujoco: null argument");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = b->w.n;
+    if (!b->mj_q && (!dev_alloc(b, &b->mj_q, (size_t)b->B * (n + 1)) || !dev_alloc(b, &b->mj_qd, (size_t)b->B * n))) return DWBC_ERR_CUDA;
+    const long long total = (long long)b->B * (n + 1);
+    const int threads = 256, grid = (int)((total + threads - 1) / threads);
+    {
+        KernelScope ks(b, DWBC_K_EXPORT, st);
+        DWBC_LAUNCH(mujoco_to_rbdl_kernel, grid, threads, 0, st, b->B, n, qpos_dev, qvel_dev, b->mj_q, b->mj_qd);
+    }
+    return dwbc_batch_update_kinematics(b, b->mj_q, b->mj_qd, stream);
+}
+
+int dwbc_batch_get_torque_command_f32(dwbc_batch_t *b, float *out_dev, void *stream) {
+    if (!b || !out_dev) return fail(DWBC_ERR_ARG, "get_torque_command_f32: null argument");
+    if (!b->have_cc) return fail(DWBC_ERR_ORDER, "get_torque_command_f32: no solve has been run");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)b->B * b->w.m;
+    const int threads = 256, grid = (int)((total + threads - 1) / threads);
+    {
+        KernelScope ks(b, DWBC_K_EXPORT, st);
+        DWBC_LAUNCH(torque_command_f32_kernel, grid, threads, 0, st, total, b->w.tau_grav, b->w.tau_task, b->w.tau_contact, out_dev);
+    }
+    CK(cudaGetLastError());
     return DWBC_OK;
 }
 

@@ -22,7 +22,7 @@ class EmulBackend:
         return _lib
 
     def empty(self, shape, dtype="f8"):
-        return np.zeros(shape, dtype={"f8": np.float64, "u1": np.uint8, "i4": np.int32, "u4": np.uint32}[dtype])
+        return np.zeros(shape, dtype={"f8": np.float64, "f4": np.float32, "u1": np.uint8, "i4": np.int32, "u4": np.uint32}[dtype])
 
     def check(self, x, dtype="f8"):
         dt = {"f8": np.float64, "u1": np.uint8, "i4": np.int32}[dtype]

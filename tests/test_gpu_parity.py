@@ -453,3 +453,16 @@ def test_gpu_lqp_full_size_properties():
 
     idx = torch.as_tensor(sample, device=y.device)
     check_lqp(V(), (y[idx].cpu().numpy(), tau[idx].cpu().numpy(), st[idx].cpu().numpy()), refs, flags[sample])
+
+
+def test_gpu_fstar_and_wire_format():
+    """SURVEY.md section 8(f) rows 1 and 3 on the device: f* from quintic / slerp trajectories for every LINK_MODE family vs the
+    numpy restatement (oracle/fstar.py), MuJoCo qpos/qvel layout, float32 torque command."""
+    from libdwbc_b200 import RobotDataBatch
+    from tests.test_fstar import run_fstar_case
+
+    def D(a):
+        a = np.ascontiguousarray(a)
+        return T(a, torch.uint8 if a.dtype == np.uint8 else torch.float64)
+
+    run_fstar_case(lambda B: RobotDataBatch(URDF, B, 0), D, lambda x: x.cpu().numpy())
