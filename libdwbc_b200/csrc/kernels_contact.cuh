@@ -109,12 +109,15 @@ struct ContactSmem {
         ldn = n | 1; ldc = CMAX | 1; ldm = m | 1;
         int o = 0;
         P = o; o += ldn * n;        // A^{-1} -> A^{-1}N_c ; its [6:,6:] block later holds W + V V^T, then W^+
-        Q = o; o += ldm * m;        // scratch: inverse Cholesky factor of W + V V^T
+        // Q (scratch of the W + V V^T inverse) is only live after Jc, X, Lambda_c and Lw are dead: it shares their storage,
+        // which brings the arena under 36.8 KB = six states per SM instead of five
+        Q = o;
         Jc = o; o += ldc * n;
         X = o; o += ldn * CMAX;
-        Jbar = o; o += ldc * n;
         Lam = o; o += ldc * CMAX;   // Jc X -> Lambda_c
         Lw = o; o += ldc * CMAX;    // scratch of the c x c inverse
+        if (o - Q < ldm * m) o = Q + ldm * m;
+        Jbar = o; o += ldc * n;
         V = o; o += ldm * (RMAX > 0 ? RMAX : 1);
         Aug = o; o += 13 * 32;      // Gauss-Jordan scratch, up to 12 rows x 32 columns, ld 13
         vec = o; o += 4 * (n + 1);  // rdiag / G / u / flag word
@@ -122,7 +125,7 @@ struct ContactSmem {
     }
 };
 
-__global__ void __launch_bounds__(TEAM, 5) contact_dynamics_kernel(const DevModel *__restrict__ md, Work w) {
+__global__ void __launch_bounds__(TEAM, 6) contact_dynamics_kernel(const DevModel *__restrict__ md, Work w) {
     DWBC_DYN_SMEM(smem);
     const int tid = t_id(), nt = t_n(), warp = tid >> 5, lane = lane_id();
     const long long s = blockIdx.x;

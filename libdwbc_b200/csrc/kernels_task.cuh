@@ -33,7 +33,7 @@ struct TaskSmem {
         Nul = o; o += ldm * m;      // Null_{l-1}
         S1 = o; o += ldt * tmax;    // Lambda_t
         S2 = o; o += ldt * tmax;    // (Q W^+ Q^T)^{-1}
-        S3 = o; o += ldt * tmax;    // scratch of the SPD inverses
+        S3 = -1;                    // scratch of the SPD inverses: X2 for Lambda_t (W^+ Q^T not formed yet), X1 for (Q W^+ Q^T)^{-1} (Q dead)
         vec = o; o += 3 * (n + 1);
         total = o;
     }
@@ -104,7 +104,7 @@ __device__ __forceinline__ double spd_inverse_small(int t, double *S, int ld, do
     return dmax > 0.0 ? piv / dmax : 0.0;
 }
 
-__global__ void __launch_bounds__(TEAM, 5) task_space_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int tmax,
+__global__ void __launch_bounds__(TEAM, 6) task_space_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int tmax,
                                                              int null_last) {
     DWBC_DYN_SMEM(smem);
     const int tid = t_id(), nt = t_n();
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(TEAM, 5) task_space_kernel(const DevModel *__r
     const int n = w.n, m = w.m;
     const TaskSmem L(n, m, tmax);
     double *sm = (double *)smem;
-    double *X1 = sm + L.X1, *X2 = sm + L.X2, *T = sm + L.T, *Nul = sm + L.Nul, *S1 = sm + L.S1, *S2 = sm + L.S2, *S3 = sm + L.S3;
+    double *X1 = sm + L.X1, *X2 = sm + L.X2, *T = sm + L.T, *Nul = sm + L.Nul, *S1 = sm + L.S1, *S2 = sm + L.S2;
     double *rd = sm + L.vec, *fs = rd + n + 1, *tt = fs + n + 1;
     const int ldm = L.ldm;
     double *tau_task = w.tau_task + s * m;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(TEAM, 5) task_space_kernel(const DevModel *__r
         tsync();
         // Lambda_t = (T J^T)^{-1}  (t x t)
         tgemm_mma<1, false, true>(t, t, n, T, ldt, Js, ldt, [&](int i, int j, double v) { S1[i + j * ldt] = v; });
-        const double cnd1 = spd_inverse_small(t, S1, ldt, S3, rd);  // S1 = Lambda_t
+        const double cnd1 = spd_inverse_small(t, S1, ldt, X2, rd);  // S1 = Lambda_t
         if (!(cnd1 > 1e-14)) ok = 0;
         tcopy(t, t, S1, ldt, w.Lamt[l] + s * (long long)t * t, t);
         // Q = Lambda_t T[:, 6:]    (t x m) -> X1 (J_task is dead)
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(TEAM, 5) task_space_kernel(const DevModel *__r
         tsync();
         // (Q W^+ Q^T)^{-1}         (t x t)
         tgemm_mma<1, false, false>(t, t, m, Qm, ldt, WQ, ldm, [&](int i, int j, double v) { S2[i + j * ldt] = v; });
-        const double cnd2 = spd_inverse_small(t, S2, ldt, S3, rd);
+        const double cnd2 = spd_inverse_small(t, S2, ldt, X1, rd);
         if (!(cnd2 > 1e-14)) ok = 0;
         // J_kt = WQ (Q W^+ Q^T)^{-1}   (m x t) -> X1 (Q is dead)
         double *Jkt = X1;

@@ -258,22 +258,44 @@ __device__ __noinline__ double tchol_lower(int n, double *A, int ld, double *rdi
     return minpiv;
 }
 
-// Xi <- L^{-1} (lower triangular, full n x n storage with zeros above the diagonal), one column per thread, forward
-// substitution on a unit vector.  L and Xi must not overlap.  No synchronisation.
+// Xi <- L^{-1} (lower triangular, full n x n storage with zeros above the diagonal) by forward substitution on unit vectors.
+// Four adjacent lanes share a column: lane `part` accumulates the terms k = j + part (mod 4) of every row's dot product and
+// two shuffles combine them.  A group owns column g and then column n-1-g, so every group runs exactly n + 1 row steps
+// (uniform trip count: the shuffles are full-warp) and the long columns are not left to a few threads -- with one column per
+// thread 39 of 128 threads worked and a third of ainv_kernel's warp time was spent waiting for them (profiles/r01_ncu_dmma.md).
+// Entry (i, j) is written by the lane with part == (i - j) mod 4, which is also the only lane that reads it back.
+// L and Xi must not overlap.  No synchronisation (Xi is complete after the caller's next barrier).
 __device__ __noinline__ void ttri_inverse(int n, const double *L, int ld, const double *rdiag, double *Xi, int ldx) {
-    for (int j = t_id(); j < n; j += t_n()) {
-        double *xj = Xi + j * ldx;
-        for (int i = 0; i < j; i++) xj[i] = 0.0;
-        xj[j] = rdiag[j];
-        for (int i = j + 1; i < n; i++) {
-            double a0 = 0.0, a1 = 0.0;
-            int k = j;
-            for (; k + 1 < i; k += 2) {
-                a0 = fma(-L[i + k * ld], xj[k], a0);
-                a1 = fma(-L[i + (k + 1) * ld], xj[k + 1], a1);
+    const int tid = t_id(), nt = t_n(), part = tid & 3;
+    for (int e = tid; e < n * n; e += nt) {
+        const int j = e / n, i = e - j * n;
+        if (i < j) Xi[i + j * ldx] = 0.0;
+    }
+    const int ng = (n + 1) >> 1;
+    for (int g0 = 0; g0 < ng; g0 += nt >> 2) {
+        const int g = g0 + (tid >> 2);
+        const bool act = g < ng;
+        DWBC_UNROLL(1)
+        for (int it = 0; it < n + 1; it++) {
+            int j, i;
+            bool valid = act;
+            if (it < n - g) {
+                j = g;
+                i = g + it;
+            } else {
+                j = n - 1 - g;
+                i = j + (it - (n - g));
+                valid = valid && j != g;
             }
-            if (k < i) a0 = fma(-L[i + k * ld], xj[k], a0);
-            xj[i] = (a0 + a1) * rdiag[i];
+            double s0 = 0.0;
+            if (valid) {
+                const double *lr = L + i, *xc = Xi + j * ldx;
+                DWBC_UNROLL(2)
+                for (int k = j + part; k < i; k += 4) s0 = fma(lr[k * ld], xc[k], s0);
+            }
+            s0 += __shfl_xor_sync(DWBC_FULL, s0, 1);
+            s0 += __shfl_xor_sync(DWBC_FULL, s0, 2);
+            if (valid && ((i - j) & 3) == part) Xi[i + j * ldx] = (i == j) ? rdiag[j] : -s0 * rdiag[i];
         }
     }
 }
