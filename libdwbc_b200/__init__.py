@@ -27,3 +27,4 @@ from .batch import (  # noqa: F401
     TASK_LINK_ROTATION_CUSTOM_FRAME,
     RobotDataBatch,
 )
+from .bridge import RlWBCBridge, RlWBCBridgeBatch  # noqa: F401,E402

@@ -63,3 +63,27 @@ def test_no_device_fails_loudly():
 
     with pytest.raises(DwbcError):
         RobotDataBatch(URDF, 4, 0)
+
+
+def test_cpp_shim_runs_reference_cycle():
+    """include/dwbc_b200.hpp (DWBC::RobotDataBatch, the C++ host shim with RobotData's method names) compiles with g++ and, linked
+    against the EMULATION build of the C ABI, reproduces the golden torques of reference tests/cases/1 (tests/dwbc_test.cpp:48-131)."""
+    import subprocess
+
+    import numpy as np
+
+    from oracle.urdf_model import read_golden
+    from tests.common import GOLDEN, relerr
+    from tests.emul.build_emul import build
+
+    lib = build()
+    exe = os.path.join(os.path.dirname(lib), "shim_check")
+    src = os.path.join(ROOT, "tests", "shim_check.cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), src, lib, "-Wl,-rpath," + os.path.dirname(lib), "-lpthread", "-o", exe])
+    out = subprocess.run([exe, URDF], capture_output=True, text=True, check=True).stdout.splitlines()
+    vals = np.array([[float(x) for x in l.split()] for l in out[:33]])
+    g = lambda n: read_golden(os.path.join(GOLDEN, "cases", "1", n))[:, 0]
+    assert relerr(vals[:, 0], g("torque_grav_")) < 1e-9
+    assert relerr(vals[:, 1], g("torque_task_")) < 1e-9
+    assert relerr(vals[:, 2], g("torque_contact_")) < 1e-9
+    assert out[33] == "status 7" and out[34].startswith("error ok: Link Name is Wrong")
