@@ -466,3 +466,16 @@ def test_gpu_fstar_and_wire_format():
         return T(a, torch.uint8 if a.dtype == np.uint8 else torch.float64)
 
     run_fstar_case(lambda B: RobotDataBatch(URDF, B, 0), D, lambda x: x.cpu().numpy())
+
+
+@pytest.mark.parametrize("dof", [18, 25, 45])
+def test_gpu_generic_dof(dof):
+    """the reference's DoF-study models (18 / 25 / 45 joints) on the device vs the oracle."""
+    from libdwbc_b200 import RobotDataBatch
+    from tests.test_generic_dof import run_generic
+
+    def D(a):
+        a = np.ascontiguousarray(a)
+        return T(a, torch.uint8 if a.dtype == np.uint8 else torch.float64)
+
+    run_generic(dof, lambda urdf, B: RobotDataBatch(urdf, B, 0), D, lambda x: x.cpu().numpy(), B=8)
