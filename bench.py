@@ -181,7 +181,7 @@ def run_reference(args):
             "config": {"workload": workload_name(args), "states_per_step": S},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -356,13 +356,31 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         q, qd, fs, fl = sets[0]
         line["cpu_baseline"] = cpu_baseline(args, q, qd, fs, fl)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything libraries print meanwhile (e.g. NCCL's version banner) was sent
+    to stderr by main()."""
+    out = json.dumps(line) + "\n"
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, out.encode())
+    else:
+        sys.stdout.write(out)
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the duration of the run
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
