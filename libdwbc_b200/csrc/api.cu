@@ -385,8 +385,10 @@ int dwbc_batch_update_kinematics(dwbc_batch_t *b, const double *q_dev, const dou
     CK(cudaMemsetAsync(b->w.status, 0xff, sizeof(int) * b->B, st));  // "valid so far"; stages clear it on failure
     {
         size_t smem = sizeof(double) * wpb * rbd_smem_doubles(b->w.nb);
+        CK(cudaFuncSetAttribute(rbd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // > 48 KB for the 40+ joint models
         KernelScope ks(b, DWBC_K_RBD, st);
         DWBC_LAUNCH(rbd_kernel, grid, wpb * 32, smem, st, b->d_model, q_dev, qdot_dev, b->w);
+        CK(cudaGetLastError());
     }
     {
         size_t smem = sizeof(double) * ainv_smem_doubles(n);
@@ -473,11 +475,12 @@ int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *
     if (stages & DWBC_SOLVE_TASK) {
         int tmax = 1;
         for (int l = 0; l < b->cfg.nlevels; l++) tmax = b->cfg.tasks[l].dof > tmax ? b->cfg.tasks[l].dof : tmax;
-        TaskSmem L(b->w.n, b->w.m, tmax);
+        TaskSmem L(b->w.n, b->w.m, b->cfg.tasks, b->cfg.nlevels);
         size_t smem = sizeof(double) * L.total;
+        if (smem > 227 * 1024) return fail(DWBC_ERR_LIMIT, "solve: the task hierarchy does not fit the shared memory of one SM");
         CK(cudaFuncSetAttribute(task_space_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelScope ks(b, DWBC_K_TASK, st);
-        DWBC_LAUNCH(task_space_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0, tmax, 0);
+        DWBC_LAUNCH(task_space_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0, 0);
     } else {
         CK(cudaMemsetAsync(b->w.tau_task, 0, sizeof(double) * B * m, st));
         CK(cudaMemsetAsync(b->w.tau_contact, 0, sizeof(double) * B * m, st));
@@ -930,11 +933,11 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
             DWBC_LAUNCH(reduced_task_jacobian_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, b->wr, b->rx, b->rc, tmaxR);
         }
         {
-            TaskSmem L(rn, rm, tmaxR);
+            TaskSmem L(rn, rm, b->cfgR.tasks, b->cfgR.nlevels);
             size_t smem = sizeof(double) * L.total;
             CK(cudaFuncSetAttribute(task_space_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             KernelScope ks(b, DWBC_K_TASK, st);
-            DWBC_LAUNCH(task_space_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, b->wr, 0, tmaxR, k < c.nlevels ? 1 : 0);
+            DWBC_LAUNCH(task_space_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, b->wr, 0, k < c.nlevels ? 1 : 0);
         }
     }
     {

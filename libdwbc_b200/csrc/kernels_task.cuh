@@ -19,22 +19,31 @@
 
 namespace dwbc {
 
+// Shared-memory arena of one state.  The level-independent quantities of ALL hierarchy levels are stacked (rows of level l
+// start at row r_l = sum of the dofs above it), so that every phase between two CTA barriers works on the whole hierarchy.
 struct TaskSmem {
-    int ldt, ldm, X1, X2, T, Nul, S1, S2, S3, vec, total;
-    // tmax: largest task dof of the configured hierarchy (the arena is sized for it at launch time)
-    __host__ __device__ TaskSmem(int n, int m, int tmax) {
-        ldt = tmax | 1;
-        ldm = m | 1;
-        int x1 = ldt * n > ldm * tmax ? ldt * n : ldm * tmax;
+    int tsum, ldt, ldm, X1, X2, T, S1, S2, vec, total;
+    __host__ __device__ static int sblock(const TaskCfg *tasks, int nl) {
         int o = 0;
-        X1 = o; o += x1;            // J_task -> Q -> J_kt -> Ntorque
-        X2 = o; o += ldm * tmax;    // W^+ Q^T -> J_kt Lambda_t
-        T = o; o += ldt * n;        // J (A^{-1} N_c)
-        Nul = o; o += ldm * m;      // Null_{l-1}
-        S1 = o; o += ldt * tmax;    // Lambda_t
-        S2 = o; o += ldt * tmax;    // (Q W^+ Q^T)^{-1}
-        S3 = -1;                    // scratch of the SPD inverses: X2 for Lambda_t (W^+ Q^T not formed yet), X1 for (Q W^+ Q^T)^{-1} (Q dead)
-        vec = o; o += 3 * (n + 1);
+        for (int l = 0; l < nl; l++) o += (tasks[l].dof | 1) * tasks[l].dof;
+        return o;
+    }
+    __host__ __device__ TaskSmem(int n, int m, const TaskCfg *tasks, int nl) {
+        tsum = 0;
+        for (int l = 0; l < nl; l++) tsum += tasks[l].dof;
+        ldt = tsum | 1;
+        ldm = m | 1;
+        const int sb = sblock(tasks, nl);
+        int x1 = ldt * n > ldm * tsum ? ldt * n : ldm * tsum;
+        int x2 = ldm * tsum > sb ? ldm * tsum : sb;
+        x1 = x1 > sb ? x1 : sb;
+        int o = 0;
+        X1 = o; o += x1;   // J_task (all levels) -> Q -> scratch of the second inverses -> J_kt
+        X2 = o; o += x2;   // scratch of the first inverses -> W^+ Q^T -> J_kt Lambda_t -> Ntorque
+        T = o; o += ldt * n;   // J (A^{-1} N_c), all levels
+        S1 = o; o += sb;   // Lambda_t blocks
+        S2 = o; o += sb;   // (Q W^+ Q^T)^{-1} blocks
+        vec = o; o += 2 * (tsum + 1) + (m + 1) + MAX_TASK_DOF + 4;  // f*, condition numbers, closed-form torque, 1/diag of a team Cholesky
         total = o;
     }
 };
@@ -91,8 +100,8 @@ __device__ __forceinline__ void build_task_jacobian(const DevModel *__restrict__
     }
 }
 
-// SPD inverse of the t x t matrix in S (ld), in place; Scr is scratch of the same size.  Returns min pivot / max diagonal.
-// Synchronises on entry and exit.
+// SPD inverse of the t x t matrix in S (ld), in place, by the whole team; Scr is scratch of the same size.  Returns min pivot /
+// max diagonal.  Synchronises on entry and exit.  (Used by the reduced-dimension kernels.)
 __device__ __forceinline__ double spd_inverse_small(int t, double *S, int ld, double *Scr, double *rd) {
     tsync();
     double dmax = 0.0;
@@ -104,17 +113,25 @@ __device__ __forceinline__ double spd_inverse_small(int t, double *S, int ld, do
     return dmax > 0.0 ? piv / dmax : 0.0;
 }
 
-__global__ void __launch_bounds__(TEAM, 6) task_space_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int tmax,
-                                                             int null_last) {
+constexpr int WARP_INV_MAX = 8;  // largest t x t inverse given to a single warp
+
+// One CTA (team) per state.  Phases (one CTA barrier each) work on the whole hierarchy at once; only the null-space recursion
+// (Ntorque_l = Null_{l-1} J_kt Lambda_t, Null_l = Null_{l-1} - Ntorque_l T_l[:,6:]) is sequential over the levels, and Null itself
+// lives in HBM/L2 (it is a public RobotData field that is written there anyway).  The t x t inverses of different levels run on
+// different warps at the same time (warp_spd_inverse).  The per-level version of this kernel went through ~126 CTA barriers
+// per state (2 (t + 5) of them inside the SPD inverses) and ncu attributed most of its warp time to waiting at them
+// (profiles/r01_ncu_dmma.md).
+__global__ void __launch_bounds__(TEAM, 6) task_space_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int null_last) {
     DWBC_DYN_SMEM(smem);
-    const int tid = t_id(), nt = t_n();
+    const int tid = t_id(), nt = t_n(), warp = tid >> 5, nw = nt >> 5;
     const long long s = blockIdx.x;
     const int n = w.n, m = w.m;
-    const TaskSmem L(n, m, tmax);
+    const int nl = cfg->nlevels;
+    const TaskSmem L(n, m, cfg->tasks, nl);
     double *sm = (double *)smem;
-    double *X1 = sm + L.X1, *X2 = sm + L.X2, *T = sm + L.T, *Nul = sm + L.Nul, *S1 = sm + L.S1, *S2 = sm + L.S2;
-    double *rd = sm + L.vec, *fs = rd + n + 1, *tt = fs + n + 1;
-    const int ldm = L.ldm;
+    double *X1 = sm + L.X1, *X2 = sm + L.X2, *T = sm + L.T, *S1 = sm + L.S1, *S2 = sm + L.S2;
+    double *fs = sm + L.vec, *cnd = fs + L.tsum + 1, *tt = cnd + L.tsum + 1, *rdv = tt + m + 1;
+    const int ldm = L.ldm, ldt = L.ldt;
     double *tau_task = w.tau_task + s * m;
     for (int i = tid; i < m; i += nt) {
         tau_task[i] = 0.0;
@@ -122,70 +139,130 @@ __global__ void __launch_bounds__(TEAM, 6) task_space_kernel(const DevModel *__r
         tt[i] = 0.0;
     }
     if (!(w.status[s] & 1)) return;  // contact stage failed: leave zero torques, DWBC_ST_TASK_OK stays clear (uniform over the CTA)
-    const double *P = w.AinvNc + s * (long long)n * n;  // read through L1/L2, used once per level
+    const double *P = w.AinvNc + s * (long long)n * n;  // read through L1/L2
     const double *Winv = w.Winv + s * (long long)m * m;
-    int ok = 1;  // every thread computes the same value
-    const int nl = cfg->nlevels;
+    // per-level offsets: rows r0[l] in the stacked matrices, so[l] in the S1 / S2 block arenas
+    int r0[MAX_LEVELS], so[MAX_LEVELS], td[MAX_LEVELS];
+    {
+        int r = 0, o = 0;
+        for (int l = 0; l < nl; l++) {
+            td[l] = cfg->tasks[l].dof;
+            r0[l] = r;
+            so[l] = o;
+            r += td[l];
+            o += (td[l] | 1) * td[l];
+        }
+    }
+    // ---- phase 0: J_task of every level (stacked), f* ----
+    double *Js = X1;
     for (int l = 0; l < nl; l++) {
-        const int t = cfg->tasks[l].dof;
-        const int ldt = t | 1;
-        double *Js = X1;
-        tsync();  // X1 / X2 / T of the previous level are dead
-        build_task_jacobian(md, cfg, w, s, l, Js, ldt);
-        for (int i = tid; i < t; i += nt) fs[i] = w.fstar[l][s * t + i];
-        tsync();
-        tcopy(t, n, Js, ldt, w.Jt[l] + s * (long long)t * n, t);
-        // T = J (A^{-1} N_c)      (t x n)
-        tgemm_mma<2, false, false>(t, n, n, Js, ldt, P, n, [&](int i, int j, double v) { T[i + j * ldt] = v; });
-        tsync();
-        // Lambda_t = (T J^T)^{-1}  (t x t)
-        tgemm_mma<1, false, true>(t, t, n, T, ldt, Js, ldt, [&](int i, int j, double v) { S1[i + j * ldt] = v; });
-        const double cnd1 = spd_inverse_small(t, S1, ldt, X2, rd);  // S1 = Lambda_t
-        if (!(cnd1 > 1e-14)) ok = 0;
-        tcopy(t, t, S1, ldt, w.Lamt[l] + s * (long long)t * t, t);
-        // Q = Lambda_t T[:, 6:]    (t x m) -> X1 (J_task is dead)
-        double *Qm = X1;
-        tgemm_mma<2, false, false>(t, m, t, S1, ldt, T + 6 * ldt, ldt, [&](int i, int j, double v) { Qm[i + j * ldt] = v; });
-        tsync();
-        // WQ = W^+ Q^T             (m x t)
-        double *WQ = X2;
-        tgemm_mma<2, false, true>(m, t, m, Winv, m, Qm, ldt, [&](int i, int j, double v) { WQ[i + j * ldm] = v; });
-        tsync();
-        // (Q W^+ Q^T)^{-1}         (t x t)
-        tgemm_mma<1, false, false>(t, t, m, Qm, ldt, WQ, ldm, [&](int i, int j, double v) { S2[i + j * ldt] = v; });
-        const double cnd2 = spd_inverse_small(t, S2, ldt, X1, rd);
-        if (!(cnd2 > 1e-14)) ok = 0;
-        // J_kt = WQ (Q W^+ Q^T)^{-1}   (m x t) -> X1 (Q is dead)
-        double *Jkt = X1;
-        tgemm_mma<2, false, false>(m, t, t, WQ, ldm, S2, ldt, [&](int i, int j, double v) { Jkt[i + j * ldm] = v; });
-        tsync();
-        tcopy(m, t, Jkt, ldm, w.Jkt[l] + s * (long long)m * t, m);
-        // JL = J_kt Lambda_t       (m x t) -> X2 (WQ is dead)
-        double *JL = X2;
-        tgemm_mma<2, false, false>(m, t, t, Jkt, ldm, S1, ldt, [&](int i, int j, double v) { JL[i + j * ldm] = v; });
-        tsync();
-        // torque_h = JL f*  (closed-form branch; the HQP kernel overwrites it with f* + f*_qp)
-        tgemv<false>(m, t, JL, ldm, fs, [&](int i, double v) { w.torque_h[l][s * m + i] = v; });
-        // Ntorque = Null_{l-1} JL  (m x t) -> X1 (J_kt already stored)
-        double *Nt = JL;
+        build_task_jacobian(md, cfg, w, s, l, Js + r0[l], ldt);
+        for (int i = tid; i < td[l]; i += nt) fs[r0[l] + i] = w.fstar[l][s * td[l] + i];
+    }
+    tsync();
+    for (int l = 0; l < nl; l++) tcopy(td[l], n, Js + r0[l], ldt, w.Jt[l] + s * (long long)td[l] * n, td[l]);
+    // ---- phase 1: T = J (A^{-1} N_c)   (tsum x n) ----
+    tgemm_mma<2, false, false>(L.tsum, n, n, Js, ldt, P, n, [&](int i, int j, double v) { T[i + j * ldt] = v; });
+    tsync();
+    // ---- phase 2: Lambda_t^{-1} = T_l J_l^T   (t x t per level) ----
+    for (int l = 0; l < nl; l++) {
+        const int t = td[l], lds = t | 1;
+        double *S = S1 + so[l];
+        tgemm_mma<1, false, true>(t, t, n, T + r0[l], ldt, Js + r0[l], ldt, [&](int i, int j, double v) { S[i + j * lds] = v; }, l);
+    }
+    tsync();
+    // ---- phase 3: Lambda_t, one level per warp ----
+    // small levels: one per warp, concurrently (only __syncwarp inside); large levels: the whole team, one after another
+    for (int l = warp; l < nl; l += nw) {
+        const int t = td[l], lds = t | 1;
+        if (t > WARP_INV_MAX) continue;
+        const double c1 = warp_spd_inverse(t, S1 + so[l], lds, X2 + so[l], lds);
+        if (lane_id() == 0) cnd[l] = c1;
+    }
+    for (int l = 0; l < nl; l++) {
+        const int t = td[l], lds = t | 1;
+        if (t <= WARP_INV_MAX) continue;
+        const double c1 = spd_inverse_small(t, S1 + so[l], lds, X2 + so[l], rdv);
+        if (tid == 0) cnd[l] = c1;
+    }
+    tsync();
+    // ---- phase 4: Q_l = Lambda_t T_l[:, 6:]   (stacked tsum x m) -> X1 (J_task is dead) ----
+    double *Qm = X1;
+    for (int l = 0; l < nl; l++) {
+        const int t = td[l], lds = t | 1;
+        tcopy(t, t, S1 + so[l], lds, w.Lamt[l] + s * (long long)t * t, t);
+        tgemm_mma<2, false, false>(t, m, t, S1 + so[l], lds, T + r0[l] + 6 * ldt, ldt, [&](int i, int j, double v) { Qm[r0[l] + i + j * ldt] = v; }, l);
+    }
+    tsync();
+    // ---- phase 5: WQ = W^+ Q^T   (m x tsum) ----
+    double *WQ = X2;
+    tgemm_mma<2, false, true>(m, L.tsum, m, Winv, m, Qm, ldt, [&](int i, int j, double v) { WQ[i + j * ldm] = v; });
+    tsync();
+    // ---- phase 6: Q_l W^+ Q_l^T   (t x t per level) ----
+    for (int l = 0; l < nl; l++) {
+        const int t = td[l], lds = t | 1;
+        double *S = S2 + so[l];
+        tgemm_mma<1, false, false>(t, t, m, Qm + r0[l], ldt, WQ + r0[l] * ldm, ldm, [&](int i, int j, double v) { S[i + j * lds] = v; }, l);
+    }
+    tsync();
+    // ---- phase 7: (Q W^+ Q^T)^{-1}, one level per warp (scratch: X1, Q is dead) ----
+    for (int l = warp; l < nl; l += nw) {
+        const int t = td[l], lds = t | 1;
+        if (t > WARP_INV_MAX) continue;
+        const double c2 = warp_spd_inverse(t, S2 + so[l], lds, X1 + so[l], lds);
+        if (lane_id() == 0) cnd[l] = fmin(cnd[l], c2);
+    }
+    for (int l = 0; l < nl; l++) {
+        const int t = td[l], lds = t | 1;
+        if (t <= WARP_INV_MAX) continue;
+        const double c2 = spd_inverse_small(t, S2 + so[l], lds, X1 + so[l], rdv);
+        if (tid == 0) cnd[l] = fmin(cnd[l], c2);
+    }
+    tsync();
+    int ok = 1;  // every thread computes the same value
+    for (int l = 0; l < nl; l++)
+        if (!(cnd[l] > 1e-14)) ok = 0;
+    // ---- phase 8: J_kt = WQ_l (Q W^+ Q^T)^{-1}   (m x t per level, stacked m x tsum) -> X1 ----
+    double *Jkt = X1;
+    for (int l = 0; l < nl; l++) {
+        const int t = td[l], lds = t | 1;
+        tgemm_mma<2, false, false>(m, t, t, WQ + r0[l] * ldm, ldm, S2 + so[l], lds, [&](int i, int j, double v) { Jkt[i + (r0[l] + j) * ldm] = v; }, l);
+    }
+    tsync();
+    // ---- phase 9: JL = J_kt Lambda_t   (m x t per level) -> X2 (WQ is dead) ----
+    double *JL = X2;
+    for (int l = 0; l < nl; l++) {
+        const int t = td[l], lds = t | 1;
+        tcopy(m, t, Jkt + r0[l] * ldm, ldm, w.Jkt[l] + s * (long long)m * t, m);
+        tgemm_mma<2, false, false>(m, t, t, Jkt + r0[l] * ldm, ldm, S1 + so[l], lds, [&](int i, int j, double v) { JL[i + (r0[l] + j) * ldm] = v; }, l);
+    }
+    tsync();
+    // torque_h = JL f*  (closed-form branch; the HQP kernel overwrites it with f* + f*_qp)
+    for (int l = 0; l < nl; l++)
+        tgemv<false>(m, td[l], JL + r0[l] * ldm, ldm, fs + r0[l], [&](int i, double v) { w.torque_h[l][s * m + i] = v; });
+    // ---- sequential part: Ntorque_l = Null_{l-1} JL_l;  Null_l = Null_{l-1} - Ntorque_l T_l[:, 6:] ----
+    double *Ntm = X1;  // J_kt is stored
+    for (int l = 0; l < nl; l++) {
+        const int t = td[l];
+        const double *Nt = JL + r0[l] * ldm;
         if (l > 0) {
-            Nt = X1;
-            tgemm_mma<2, false, false>(m, t, m, Nul, ldm, JL, ldm, [&](int i, int j, double v) { Nt[i + j * ldm] = v; });
+            const double *Nprev = w.Null[l - 1] + s * (long long)m * m;
+            tsync();  // X1 of the previous level is dead, Null_{l-1} is visible (written by this CTA before the barrier)
+            tgemm_mma<2, false, false>(m, t, m, Nprev, m, JL + r0[l] * ldm, ldm, [&](int i, int j, double v) { Ntm[i + j * ldm] = v; });
             tsync();
+            Nt = Ntm;
         }
         tcopy(m, t, Nt, ldm, w.Ntq[l] + s * (long long)m * t, m);
         // closed-form torque: torque_task += Null_{l-1} torque_h = Ntorque f*
-        tgemv<false>(m, t, Nt, ldm, fs, [&](int i, double v) { tt[i] += v; });
-        // Null_l = Null_{l-1} - Ntorque T[:, 6:]     (not needed for the last level)
+        tgemv<false>(m, t, Nt, ldm, fs + r0[l], [&](int i, double v) { tt[i] += v; });
         if (l + 1 < nl || null_last) {  // null_last: the reduced variant needs Null of its last contact-chain level
+            double *Nout = w.Null[l] + s * (long long)m * m;
             if (l == 0) {
-                tgemm_mma<2, false, false>(m, m, t, Nt, ldm, T + 6 * ldt, ldt,
-                                          [&](int i, int j, double v) { Nul[i + j * ldm] = (i == j ? 1.0 : 0.0) - v; });
+                tgemm_mma<2, false, false>(m, m, t, Nt, ldm, T + r0[l] + 6 * ldt, ldt, [&](int i, int j, double v) { Nout[i + j * m] = (i == j ? 1.0 : 0.0) - v; });
             } else {
-                tgemm_mma<2, false, false>(m, m, t, Nt, ldm, T + 6 * ldt, ldt, [&](int i, int j, double v) { Nul[i + j * ldm] -= v; });
+                const double *Nprev = w.Null[l - 1] + s * (long long)m * m;
+                tgemm_mma<2, false, false>(m, m, t, Nt, ldm, T + r0[l] + 6 * ldt, ldt, [&](int i, int j, double v) { Nout[i + j * m] = Nprev[i + j * m] - v; });
             }
-            tsync();
-            tcopy(m, m, Nul, ldm, w.Null[l] + s * (long long)m * m, m);
         }
     }
     tsync();

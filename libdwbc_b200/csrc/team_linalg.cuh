@@ -125,39 +125,55 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 // loads.  Requires blockDim.x to be a multiple of 32; every warp runs the same item count modulo one.
 // KTRI: opA(i,k) = 0 for k < i and opB(k,j) = 0 for k < j (the X^T X product of a lower-triangular X): the k loop of an
 // item starts at its first row / column.
+// woff rotates the item -> warp assignment, so that several small products issued in one phase do not all land on warp 0.
 template <int NT, bool TA, bool TB, bool KTRI = false, class Epi>
-__device__ __forceinline__ void tgemm_mma(int M, int N, int K, const double *__restrict__ A, int lda, const double *__restrict__ B, int ldb,
-                                          Epi epi) {
-    const int lane = lane_id(), warp = t_id() >> 5, nw = t_n() >> 5;
+__device__ __forceinline__ void tgemm_mma(int M, int N, int K, const double *A, int lda, const double *B, int ldb, Epi epi, int woff = 0) {
+    // (A and B are deliberately not __restrict__: an operand may have been written to global memory earlier in the same kernel
+    // -- Null_{l-1} in task_space_kernel -- and must not be fetched through the non-coherent read-only path.)
+    const int lane = lane_id(), nw = t_n() >> 5, warp = ((t_id() >> 5) + nw - (woff % nw)) % nw;
     const int g = lane >> 2, t = lane & 3;
     const int tr = (M + 7) >> 3, tc = (N + 7) >> 3, gc = (tc + NT - 1) / NT;
+    const int sa = TA ? 1 : lda, sb = TB ? ldb : 1;
+    const int Kfull = K & ~3;
     for (int item = warp; item < tr * gc; item += nw) {
         const int gj = item / tr, bi = item - gj * tr;
         const int i = bi * 8 + g;
         const bool iv = i < M;
-        const double *ap = A + (iv ? i : 0) * (TA ? lda : 1);
-        const double *bp[NT];
-        bool jv[NT];
+        // Rows / columns beyond the edge read row / column 0 instead of being zero-filled: row i of the product only depends on
+        // row i of opA and column j only on column j of opB, so the garbage stays in outputs that are never stored.  Only the
+        // k tail (K not a multiple of 4) has to be zeroed.
+        const int kbeg = KTRI ? 8 * (bi > gj * NT ? bi : gj * NT) : 0;
+        const double *pa = A + (iv ? i : 0) * (TA ? lda : 1) + (kbeg + t) * sa;
+        const double *pb[NT];
         double c[NT][2];
         DWBC_UNROLL(NT)
         for (int jj = 0; jj < NT; jj++) {
             const int j = (gj * NT + jj) * 8 + g;
-            jv[jj] = j < N;
-            bp[jj] = B + (jv[jj] ? j : 0) * (TB ? 1 : ldb);
+            pb[jj] = B + (j < N ? j : 0) * (TB ? 1 : ldb) + (kbeg + t) * sb;
             c[jj][0] = 0.0;
             c[jj][1] = 0.0;
         }
-        const int sa = TA ? 1 : lda, sb = TB ? ldb : 1;
-        const int kbeg = KTRI ? 8 * (bi > gj * NT ? bi : gj * NT) : 0;
+        const int ntile = tc - gj * NT < NT ? tc - gj * NT : NT;  // tiles of this item that exist (warp-uniform)
         DWBC_UNROLL(2)
-        for (int k0 = kbeg; k0 < K; k0 += 4) {
-            const int k = k0 + t;
-            const bool kv = k < K;
-            const double a = (iv && kv) ? ap[k * sa] : 0.0;
+        for (int k0 = kbeg; k0 < Kfull; k0 += 4) {
+            const double a = *pa;
+            pa += 4 * sa;
             DWBC_UNROLL(NT)
             for (int jj = 0; jj < NT; jj++) {
-                if ((gj * NT + jj) * 8 < N) {  // warp-uniform: skip tiles beyond the last column
-                    const double b = (jv[jj] && kv) ? bp[jj][k * sb] : 0.0;
+                if (jj < ntile) {
+                    const double b = *pb[jj];
+                    dmma884(c[jj][0], c[jj][1], a, b);
+                }
+                pb[jj] += 4 * sb;
+            }
+        }
+        if (Kfull < K && Kfull >= kbeg) {
+            const bool kv = Kfull + t < K;
+            const double a = kv ? *pa : 0.0;
+            DWBC_UNROLL(NT)
+            for (int jj = 0; jj < NT; jj++) {
+                if (jj < ntile) {
+                    const double b = kv ? *pb[jj] : 0.0;
                     dmma884(c[jj][0], c[jj][1], a, b);
                 }
             }
@@ -298,6 +314,54 @@ __device__ __noinline__ void ttri_inverse(int n, const double *L, int ld, const 
             if (valid && ((i - j) & 3) == part) Xi[i + j * ldx] = (i == j) ? rdiag[j] : -s0 * rdiag[i];
         }
     }
+}
+
+// SPD inverse by ONE warp, n <= 32, in place (full symmetric result in S); X (n x n, ldx) is scratch.  Only __syncwarp inside:
+// different warps of a team can invert different matrices at the same time (task_space_kernel: one hierarchy level per warp)
+// instead of the whole team going through n + 5 CTA barriers per matrix.  Returns min pivot / max diagonal (<= 0: not SPD).
+__device__ __noinline__ double warp_spd_inverse(int n, double *S, int ld, double *X, int ldx) {
+    const int lane = lane_id();
+    double dmax = 0.0, minpiv = 1e300;
+    for (int i = 0; i < n; i++) dmax = fmax(dmax, S[i + i * ld]);
+    double lik = 0.0;
+    for (int k = 0; k < n; k++) {
+        __syncwarp();
+        double akk = S[k + k * ld];
+        minpiv = akk < minpiv ? akk : minpiv;
+        if (!(akk > 1e-300)) akk = 1e-300;
+        const double r = rsqrt(akk);
+        __syncwarp();
+        if (lane > k && lane < n) {
+            lik = S[lane + k * ld] * r;
+            S[lane + k * ld] = lik;
+        }
+        if (lane == k) S[k + k * ld] = akk * r;
+        __syncwarp();
+        if (lane > k && lane < n)
+            for (int j = k + 1; j <= lane; j++) S[lane + j * ld] = fma(-lik, S[j + k * ld], S[lane + j * ld]);
+    }
+    __syncwarp();
+    if (lane < n) {  // X[:, lane] = L^{-1} e_lane
+        double *xj = X + lane * ldx;
+        for (int i = 0; i < lane; i++) xj[i] = 0.0;
+        xj[lane] = 1.0 / S[lane + lane * ld];
+        for (int i = lane + 1; i < n; i++) {
+            double a0 = 0.0;
+            for (int k = lane; k < i; k++) a0 = fma(-S[i + k * ld], xj[k], a0);
+            xj[i] = a0 / S[i + i * ld];
+        }
+    }
+    __syncwarp();
+    for (int e = lane; e < n * n; e += 32) {  // S = X^T X, lower triangle mirrored
+        const int j = e / n, i = e - j * n;
+        if (i < j) continue;
+        double a0 = 0.0;
+        for (int k = i; k < n; k++) a0 = fma(X[k + i * ldx], X[k + j * ldx], a0);
+        S[i + j * ld] = a0;
+        S[j + i * ld] = a0;
+    }
+    __syncwarp();
+    return dmax > 0.0 ? minpiv / dmax : 0.0;
 }
 
 // Out(i,j) <- epi(i, j, (A^{-1})(i,j)) with A^{-1} = Xi^T Xi for the lower-triangular Xi = L^{-1} (full storage, zeros above
