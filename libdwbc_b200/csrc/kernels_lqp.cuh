@@ -37,6 +37,7 @@ constexpr double LQP_SIGMA = 1.0e-6;
 constexpr double LQP_TORQUE_LIMIT = 200.0, LQP_ACC_LIMIT = 5.0;  // reference src/dwbc.cpp:4357-4371, 4395-4403
 constexpr int LQP_MAX_LEVELS = MAX_LEVELS + 2;
 constexpr int LQP_CHOL_OWN = 9;  // 45*46/2 entries of the lower triangle over 128 threads
+constexpr int LQP_NU_TILES = (LQP_WCAP + 7) / 8;  // column tiles of a level's row matrix (nu <= LQP_WCAP)
 
 struct LqpOut {
     double *y;      // [B][LQP_MAX_LEVELS][n + CMAX]   answer after every level
@@ -536,19 +537,19 @@ __global__ void __launch_bounds__(TEAM, 2) lqp_kernel(const DevModel *__restrict
                 ee[r] = (d + bb) * rn;
             }
             tsync();
-            tgemm<2, 2, false, false>(neq, nu, n, Bm, ldb, Zw, ldz, [&](int i, int j, double v) { E[i + j * lde] = v * htau[i]; });
+            tgemm_mma<2, false, false>(neq, nu, n, Bm, ldb, Zw, ldz, [&](int i, int j, double v) { E[i + j * lde] = v * htau[i]; });
         }
         tsync();
         if (lev > 0) {
             // ---- T = A Z_a (n x nu, in the R arena), ta = A y_a ----
             double *T = R;
-            tgemm<2, 2, false, false>(n, nu, n, A, n, Zw, ldz, [&](int i, int j, double v) { T[i + j * ldt] = v; });
+            tgemm_mma<2, false, false>(n, nu, n, A, n, Zw, ldz, [&](int i, int j, double v) { T[i + j * ldt] = v; });
             tgemv<false>(n, n, A, n, y, [&](int i, double v) { ta[i] = v; });
             tsync();
             // ---- Hu = E^T E + hs Z_a^T T + sigma I,  g = E^T e + hs Z_a^T ta ----
-            tgemm<2, 2, true, false>(nu, nu, neq, E, lde, E, lde, [&](int i, int j, double v) { H[i + j * ldh] = v; });
+            tgemm_mma<2, true, false>(nu, nu, neq, E, lde, E, lde, [&](int i, int j, double v) { H[i + j * ldh] = v; });
             tsync();
-            tgemm<2, 2, true, false>(nu, nu, n, Zw, ldz, T, ldt, [&](int i, int j, double v) { H[i + j * ldh] += hs * v + (i == j ? LQP_SIGMA : 0.0); });
+            tgemm_mma<2, true, false>(nu, nu, n, Zw, ldz, T, ldt, [&](int i, int j, double v) { H[i + j * ldh] += hs * v + (i == j ? LQP_SIGMA : 0.0); });
             tgemv<true>(nu, neq, E, lde, ee, [&](int i, double v) { gg[i] = v; });
             tsync();
             tgemv<true>(nu, n, Zw, ldz, ta, [&](int i, double v) { gg[i] += hs * v; });
@@ -576,23 +577,16 @@ __global__ void __launch_bounds__(TEAM, 2) lqp_kernel(const DevModel *__restrict
                 ub[2 * m + k] = -d * cm[k * 7 + 6] + vfro[2 * m + k];
             }
             tsync();
-            for (int e = tid; e < (2 * m + 10 * kc) * nu; e += nt) {
-                const int ur = e % (2 * m + 10 * kc), j = e / (2 * m + 10 * kc);
-                double v;
-                if (ur < m) {
-                    v = T[6 + ur + j * ldt];
-                    for (int a = 0; a < c; a++) v = fma(Jc[a + (6 + ur) * CMAX], Zw[n + a + j * ldz], v);
-                    v *= u[ur];
-                } else if (ur < m + 10 * kc) {
-                    const int k = ur - m, kk = k / 10;
-                    v = 0.0;
-                    for (int a = 0; a < 6; a++) v = fma(cm[k * 7 + a], Zw[n + 6 * kk + a + j * ldz], v);
-                    v *= cm[k * 7 + 6];
-                } else {
-                    v = Zw[6 + (ur - m - 10 * kc) + j * ldz];
-                }
-                G[ur + j * ldg] = v;
+            // torque rows: (T[6+r,:] + Jc^T[6+r,:] Z_f) / |row|;  friction / ZMP rows: C_k Z_f[6k:6k+6,:] / |row|;  accel rows: Z[6+r,:]
+            tgemm_mma<2, true, false>(m, nu, c, Jc + 6 * CMAX, CMAX, Zw + n, ldz, [&](int i, int j, double v) { G[i + j * ldg] = (v + T[6 + i + j * ldt]) * u[i]; });
+            for (int k = 0; k < kc; k++)
+                tgemm_mma<2, true, false>(10, nu, 6, cm + 70 * k, 7, Zw + n + 6 * k, ldz,
+                                          [&](int i, int j, double v) { G[m + 10 * k + i + j * ldg] = v * cm[(10 * k + i) * 7 + 6]; }, k + 1);
+            for (int e = tid; e < m * nu; e += nt) {
+                const int j = e / m, r = e - j * m;
+                G[m + 10 * kc + r + j * ldg] = Zw[6 + r + j * ldz];
             }
+            tsync();  // T (in the R arena) is dead from here on
             // ---- Lc Lc^T = Hu;  gh = Lc^{-1} g;  G <- G Lc^{-T};  ub += G gh ----
             double *rdiag = u;  // 1 / Lc(i,i)   (the torque-row norms are no longer needed after the barrier inside tchol_lower)
             const double piv = tchol_lower<LQP_CHOL_OWN>(nu, H, ldh, rdiag);
@@ -600,30 +594,14 @@ __global__ void __launch_bounds__(TEAM, 2) lqp_kernel(const DevModel *__restrict
                 solved = 0;
                 break;
             }
-            if (warp == 0) {
-                for (int k = 0; k < nu; k++) {
-                    __syncwarp();
-                    const double hk = gg[k] * rdiag[k];
-                    __syncwarp();
-                    if (lane == 0) gg[k] = hk;
-                    for (int j = k + 1 + lane; j < nu; j += 32) gg[j] = fma(-H[j + k * ldh], hk, gg[j]);
-                }
-                __syncwarp();
-                for (int j = lane; j < nu; j += 32) gh[j] = gg[j];
-            }
-            for (int ur = tid; ur < 2 * m + 10 * kc; ur += nt) {
-                double *g = G + ur;
-                for (int j = 0; j < nu; j++) {
-                    double a0 = g[j * ldg], a1 = 0.0;
-                    int k = 0;
-                    for (; k + 1 < j; k += 2) {
-                        a0 = fma(-H[j + k * ldh], g[k * ldg], a0);
-                        a1 = fma(-H[j + (k + 1) * ldh], g[(k + 1) * ldg], a1);
-                    }
-                    if (k < j) a0 = fma(-H[j + k * ldh], g[k * ldg], a0);
-                    g[j * ldg] = (a0 + a1) * rdiag[j];
-                }
-            }
+            // Xi = Lc^{-1} (R arena, free until the solve);  gh = Xi g;  G <- G Xi^T in place on the tensor cores: an item is an
+            // 8-row band times ALL column tiles, so it only reads the rows it later overwrites
+            double *Xi = R;
+            const int ldx = L.ldh;
+            ttri_inverse(nu, H, ldh, rdiag, Xi, ldx);
+            tsync();
+            tgemv<false>(nu, nu, Xi, ldx, gg, [&](int i, double v) { gh[i] = v; });
+            tgemm_mma<LQP_NU_TILES, false, true>(2 * m + 10 * kc, nu, nu, G, ldg, Xi, ldx, [&](int i, int j, double v) { G[i + j * ldg] = v; });
             tsync();
             for (int i = tid; i < rows; i += nt) {
                 int ur;

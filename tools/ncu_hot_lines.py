@@ -14,6 +14,7 @@ import tempfile
 
 rep, kern, so = sys.argv[1], sys.argv[2], os.path.abspath(sys.argv[3])
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+by_inst = len(sys.argv) > 5 and sys.argv[5] == "inst"  # sort by executed instructions instead of stall samples
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
@@ -51,5 +52,5 @@ ts, ti = sum(samp.values()), sum(inst.values())
 print(f"{kern}: {len(sass)} SASS instructions, {ts} stall samples, {ti:.3e} warp instructions executed")
 print("| source line | samples % | warp inst % |")
 print("|---|---|---|")
-for ln, s in samp.most_common(top):
-    print(f"| {ln[0]}:{ln[1]} | {100.0 * s / ts:.1f} | {100.0 * inst[ln] / ti:.1f} |")
+for ln, _ in (inst if by_inst else samp).most_common(top):
+    print(f"| {ln[0]}:{ln[1]} | {100.0 * samp[ln] / ts:.1f} | {100.0 * inst[ln] / ti:.1f} |")
