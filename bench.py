@@ -334,8 +334,21 @@ def run_b200(args):
     dom_s = kern[dom]["ms_per_launch"] * 1e-3
     achieved = B * flk[dom] / dom_s / 1e12
     step_flops = sum(flk.values())
+    for k in kern:  # every kernel's own fraction, so that a change of the dominant kernel between runs stays readable
+        if k in flk and kern[k]["ms_per_launch"] > 0:
+            kern[k]["achieved_tflops"] = B * flk[k] / (kern[k]["ms_per_launch"] * 1e-3) / 1e12
+            kern[k]["frac"] = kern[k]["achieved_tflops"] / fp64_peak
+    # DRAM traffic of the dominant kernel per launch from the committed `ncu --set full` capture (same B), else null
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tj.get("states_per_launch") == B and dom in tj["kernels"]:
+            traffic = tj["kernels"][dom]["dram_read_bytes"] + tj["kernels"][dom]["dram_write_bytes"]
+            traffic_src = "profiles/r01_traffic.json: " + tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                "traffic": None,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "DFMA-chain probe in this run (dwbc_probe_fp64); MEASURED_PEAKS.json has no FP64 figure" if tf else "nominal",
                 "algorithmic_flops_per_solve": step_flops, "kernel_flops_per_solve": flk[dom],
                 "whole_step": {"achieved": world * B * step_flops / (ms_total / args.steps * 1e-3) / 1e12 / world, "frac": B * step_flops / (ms_total / args.steps * 1e-3) / 1e12 / fp64_peak},
