@@ -184,12 +184,18 @@ int dwbc_batch_get_zmp(dwbc_batch_t *b, const double *cf_dev, double *zmp_dev, v
 int dwbc_batch_reduced_dynamics(dwbc_batch_t *b, const uint8_t *pattern_host, void *stream);
 /* ReducedCalcContactConstraint()   reference src/dwbc.cpp:3077-3142 */
 int dwbc_batch_reduced_calc_contact_constraint(dwbc_batch_t *b, void *stream);
-/* ReducedCalcGravCompensation (DWBC_SOLVE_GRAV) + ReducedCalcTaskSpace + ReducedCalcTaskControlTorque(hqp=false)
- * (DWBC_SOLVE_TASK)   reference src/dwbc.cpp:3144-3446.  Outputs as dwbc_batch_solve (full 33-joint torques).
- * DWBC_SOLVE_HQP / DWBC_SOLVE_REDIST (CalcSingleTaskTorqueWithQP_R[_NC], CalcContactRedistributeR) are not built yet
- * and return DWBC_ERR_ARG. */
+/* ReducedCalcGravCompensation (DWBC_SOLVE_GRAV) + ReducedCalcTaskSpace + ReducedCalcTaskControlTorque (DWBC_SOLVE_TASK: hqp=false;
+ * DWBC_SOLVE_HQP: hqp=true, CalcSingleTaskTorqueWithQP_R) + ReducedCalcContactRedistribute(hqp=true) (DWBC_SOLVE_REDIST,
+ * CalcContactRedistributeR)   reference src/dwbc.cpp:3144-3599, 3758-3770, 4777-4925.  Outputs as dwbc_batch_solve (full
+ * 33-joint torques; torque_contact_[0:contact_dof_] = torque_contact_R_[0:contact_dof_]).
+ * The QP branches are available for hierarchies of COM / contact-chain levels; with a non-contact level they need
+ * CalcSingleTaskTorqueWithQP_R_NC, which is not built (DWBC_ERR_ARG), as is the analytic branch of CalcContactRedistributeR. */
 int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *tau_task_dev, double *tau_contact_dev,
                              int32_t *status_dev, void *stream);
+/* Torque limit of the reduced QPs: reduced_model_dof_ entries (contact-chain joints, then the 6 coordinates of the condensed
+ * non-contact body), as CalcSingleTaskTorqueWithQP_R compares torque_limit_.size() with reduced_model_dof_ (reference
+ * src/dwbc.cpp:3462-3468).  The full-model limit of dwbc_batch_set_torque_limit is not used by the reduced QPs.  count = 0 clears it. */
+int dwbc_batch_set_reduced_torque_limit(dwbc_batch_t *b, const double *tlim_host, int count);
 /* co_dof, nc_dof, vc_dof, reduced_system_dof_, reduced_model_dof_ of the current pattern (reference src/dwbc.cpp:2818-2823) */
 int dwbc_batch_reduced_dims(const dwbc_batch_t *b, int *co_dof, int *nc_dof, int *vc_dof, int *reduced_system_dof, int *reduced_model_dof);
 /* public RobotData fields of the reduced variant */

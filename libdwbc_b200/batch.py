@@ -232,12 +232,20 @@ class RobotDataBatch:
         self._ck(self.L.dwbc_batch_reduced_dims(self._h, *[C.byref(x) for x in d]))
         self.co_dof, self.nc_dof, self.vc_dof, self.reduced_system_dof_, self.reduced_model_dof_ = [x.value for x in d]
 
+    def set_reduced_torque_limit(self, tlim):
+        """torque limit of the reduced QPs (reduced_model_dof_ entries, reference src/dwbc.cpp:3462-3468); None clears it"""
+        if tlim is None:
+            self._ck(self.L.dwbc_batch_set_reduced_torque_limit(self._h, None, 0))
+            return
+        a = np.ascontiguousarray(np.asarray(tlim, dtype=np.float64).reshape(-1))
+        self._ck(self.L.dwbc_batch_set_reduced_torque_limit(self._h, a.ctypes.data_as(_dp), len(a)))
+
     def reduced_calc_contact_constraint(self):
         self._ck(self.L.dwbc_batch_reduced_calc_contact_constraint(self._h, self.be.stream()))
 
     def reduced_solve(self, stages=SOLVE_GRAV | SOLVE_TASK, out=None):
-        """ReducedCalcGravCompensation + ReducedCalcTaskSpace + ReducedCalcTaskControlTorque(hqp=false);
-        returns (torque_grav, torque_task, torque_contact, status) like solve()."""
+        """ReducedCalcGravCompensation + ReducedCalcTaskSpace + ReducedCalcTaskControlTorque (SOLVE_HQP: hqp=true) +
+        ReducedCalcContactRedistribute (SOLVE_REDIST); returns (torque_grav, torque_task, torque_contact, status) like solve()."""
         be = self.be
         B, m = self.batch, self.model_dof_
         if out is None:

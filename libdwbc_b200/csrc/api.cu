@@ -67,6 +67,8 @@ struct dwbc_batch {
     int red_rn = 0;
     std::string red_task_sig;
     bool have_red_dyn = false, have_red_cc = false;
+    bool red_tlim_set = false;
+    std::vector<double> red_tlim;
     // section 8(f): f* generation and the MuJoCo / float32 wire format
     struct TrajHost {
         double gains[18] = {0};
@@ -715,6 +717,8 @@ void free_reduced_tasks(dwbc_batch *b) {
     b->red_task_sig.clear();
     for (int l = 0; l < MAX_LEVELS; l++) {
         b->wr.Jt[l] = b->wr.Lamt[l] = b->wr.Jkt[l] = b->wr.Null[l] = b->wr.Ntq[l] = b->wr.torque_h[l] = nullptr;
+        b->wr.fstar_qp[l] = b->wr.contact_qp[l] = nullptr;
+        b->wr.active[l] = nullptr;
         b->rx.JtR[l] = b->rx.LamNC[l] = nullptr;
     }
 }
@@ -744,7 +748,8 @@ int alloc_reduced(dwbc_batch *b, int rn, int rm) {
               dev_alloc(b, &r.tau_task, B * m, L) && dev_alloc(b, &r.tau_contact, B * m, L) && dev_alloc(b, &r.status, B, L) &&
               dev_alloc(b, &x.JI, B * 6 * NCMAX, L) && dev_alloc(b, &x.JIinvT, B * 6 * NCMAX, L) && dev_alloc(b, &x.SInc, B * 16, L) &&
               dev_alloc(b, &x.AR, B * n * n, L) && dev_alloc(b, &x.Jbkt, B * m * 6, L) && dev_alloc(b, &x.tauR, B * m, L) &&
-              dev_alloc(b, &x.tauNC, B * NCMAX, L) && dev_alloc(b, &b->d_cfgR, 1, L);
+              dev_alloc(b, &x.tauNC, B * NCMAX, L) && dev_alloc(b, &b->d_cfgR, 1, L) && dev_alloc(b, &r.active[MAX_LEVELS], B * ACTIVE_WORDS, L) &&
+              dev_alloc(b, &r.cf_redis, B * RMAX, L) && dev_alloc(b, &r.qp_iters, B, L);
     if (!ok) {
         free_reduced(b);
         return DWBC_ERR_CUDA;
@@ -821,6 +826,19 @@ int dwbc_batch_reduced_calc_contact_constraint(dwbc_batch_t *b, void *stream) {
     return DWBC_OK;
 }
 
+int dwbc_batch_set_reduced_torque_limit(dwbc_batch_t *b, const double *tlim_host, int count) {
+    if (!b) return fail(DWBC_ERR_ARG, "set_reduced_torque_limit: null handle");
+    if (!tlim_host || count <= 0) {
+        b->red_tlim_set = false;
+        b->red_tlim.clear();
+        return DWBC_OK;
+    }
+    if (count > MAXB) return fail(DWBC_ERR_LIMIT, "set_reduced_torque_limit: too many entries");
+    b->red_tlim.assign(tlim_host, tlim_host + count);
+    b->red_tlim_set = true;
+    return DWBC_OK;
+}
+
 int dwbc_batch_reduced_dims(const dwbc_batch_t *b, int *co_dof, int *nc_dof, int *vc_dof, int *rsys, int *rmod) {
     if (!b || !b->have_red_dyn) return fail(DWBC_ERR_ORDER, "reduced_dims: call reduced_dynamics first");
     if (co_dof) *co_dof = b->rc.co_dof;
@@ -835,8 +853,13 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
                              void *stream) {
     if (!b) return fail(DWBC_ERR_ARG, "reduced_solve: null handle");
     if (!b->have_red_cc) return fail(DWBC_ERR_ORDER, "reduced_solve: call reduced_calc_contact_constraint first");
-    if (stages & (DWBC_SOLVE_HQP | DWBC_SOLVE_REDIST | DWBC_SOLVE_REDIST_ANALYTIC))
-        return fail(DWBC_ERR_ARG, "reduced_solve: the QP branches of the reduced variant (CalcSingleTaskTorqueWithQP_R, CalcContactRedistributeR) are not built yet");
+    if (stages & DWBC_SOLVE_REDIST_ANALYTIC)
+        return fail(DWBC_ERR_ARG, "reduced_solve: the analytic branch of CalcContactRedistributeR is not built");
+    if (stages & DWBC_SOLVE_HQP) stages |= DWBC_SOLVE_TASK;
+    if ((stages & DWBC_SOLVE_REDIST) && !(stages & DWBC_SOLVE_TASK)) return fail(DWBC_ERR_ARG, "reduced_solve: DWBC_SOLVE_REDIST needs DWBC_SOLVE_TASK");
+    const bool use_qp = (stages & (DWBC_SOLVE_HQP | DWBC_SOLVE_REDIST)) != 0;
+    if (use_qp && b->red_tlim_set && (int)b->red_tlim.size() != b->rc.rm)
+        return fail(DWBC_ERR_ARG, "reduced_solve: task qp torque limit size is not matched with model size (reduced_model_dof_)");
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
     int rcode = upload_cfg(b, st);
@@ -897,6 +920,8 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
             if (rc.cls[l] != 2) return fail(DWBC_ERR_ARG, "reduced_solve: COM / contact-chain levels must precede the non-contact levels");
         if (k == 0) return fail(DWBC_ERR_ARG, "reduced_solve: the first level cannot be a non-contact task (the reference reads ts_[-1])");
         rc.k_contact = k;
+        if (use_qp && k != c.nlevels)
+            return fail(DWBC_ERR_ARG, "reduced_solve: non-contact tasks under hqp need CalcSingleTaskTorqueWithQP_R_NC, which is not built");
         if (sig != b->red_task_sig) {
             free_reduced_tasks(b);
             std::vector<void *> *L = &b->red_task_allocs;
@@ -906,7 +931,8 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
                 if (l < k)
                     ok = dev_alloc(b, &wr.Jt[l], B * t * rn, L) && dev_alloc(b, &wr.Lamt[l], B * t * t, L) && dev_alloc(b, &wr.Jkt[l], B * rm * t, L) &&
                          dev_alloc(b, &wr.Null[l], B * rm * rm, L) && dev_alloc(b, &wr.Ntq[l], B * rm * t, L) && dev_alloc(b, &wr.torque_h[l], B * rm, L) &&
-                         dev_alloc(b, &b->rx.JtR[l], B * t * rn, L);
+                         dev_alloc(b, &b->rx.JtR[l], B * t * rn, L) && dev_alloc(b, &wr.fstar_qp[l], B * t, L) && dev_alloc(b, &wr.contact_qp[l], B * RMAX, L) &&
+                         dev_alloc(b, &wr.active[l], B * ACTIVE_WORDS, L);
                 else
                     ok = dev_alloc(b, &b->rx.LamNC[l], B * t * t, L);
                 if (!ok) return DWBC_ERR_CUDA;
@@ -916,6 +942,8 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
         // reduced hierarchy = the first k levels with per-state custom Jacobians
         b->cfgR = b->cfg;
         b->cfgR.nlevels = k;
+        b->cfgR.tlim_set = b->red_tlim_set ? 1 : 0;  // the full-model limit has the wrong size for the reduced QP (src/dwbc.cpp:3462-3468)
+        for (int i = 0; i < (int)b->red_tlim.size() && i < MAXB; i++) b->cfgR.tlim[i] = b->red_tlim[i];
         for (int l = 0; l < k; l++) {
             b->cfgR.tasks[l].custom = 1;
             b->cfgR.tasks[l].link_count = 0;
@@ -937,7 +965,18 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
             size_t smem = sizeof(double) * L.total;
             CK(cudaFuncSetAttribute(task_space_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             KernelScope ks(b, DWBC_K_TASK, st);
-            DWBC_LAUNCH(task_space_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, b->wr, 0, k < c.nlevels ? 1 : 0);
+            DWBC_LAUNCH(task_space_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, b->wr, (stages & DWBC_SOLVE_HQP) ? 1 : 0, k < c.nlevels ? 1 : 0);
+        }
+        if (use_qp) {
+            // CalcSingleTaskTorqueWithQP_R / CalcContactRedistributeR: the same QPs on the reduced matrices (src/dwbc.cpp:3448-3599, 4777-4925)
+            int nvmax = RMAX > 0 ? RMAX : 1;
+            for (int l = 0; l < k; l++) nvmax = c.tasks[l].dof + RMAX > nvmax ? c.tasks[l].dof + RMAX : nvmax;
+            HqpSmem L(rn, rm, nvmax);
+            size_t smem = sizeof(double) * L.total;
+            CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            KernelScope ks(b, DWBC_K_HQP, st);
+            DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, b->wr, (stages & DWBC_SOLVE_HQP) ? 1 : 0,
+                        (stages & DWBC_SOLVE_REDIST) ? 2 : 0, nvmax);
         }
     }
     {
@@ -945,7 +984,8 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
         size_t smem = sizeof(double) * L.total;
         CK(cudaFuncSetAttribute(reduced_nc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelScope ks(b, DWBC_K_REDUCED, st);
-        DWBC_LAUNCH(reduced_nc_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, b->wr, b->rx, b->rc, tmax);
+        DWBC_LAUNCH(reduced_nc_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, b->wr, b->rx, b->rc, tmax,
+                    ((stages & DWBC_SOLVE_HQP) ? 1 : 0) | ((stages & DWBC_SOLVE_REDIST) ? 2 : 0));
     }
     CK(cudaGetLastError());
     if (tau_grav_dev) CK(cudaMemcpyAsync(tau_grav_dev, b->w.tau_grav, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));

@@ -943,7 +943,12 @@ __global__ void __launch_bounds__(TEAM, 6) hqp_kernel(const DevModel *__restrict
             for (int i = tid; i < m; i += nt) tau_contact[i] = 0.0;  // reference src/dwbc.cpp:1562-1566
             st |= 4;
         } else {
-            for (int i = tid; i < m; i += nt) base[i] = w.tau_grav[s * m + i] + tau_task[i] + tau_contact[i];  // tau_in
+            // tau_in: torque_grav_ + torque_task_ + torque_contact_ (reference src/dwbc.cpp:1372-1380); the reduced variant passes
+            // torque_grav_R_ + torque_task_R_ and ASSIGNS torque_contact_R_ = NwJw_R x (redist == 2, src/dwbc.cpp:3763, 4915)
+            for (int i = tid; i < m; i += nt) {
+                if (redist == 2) tau_contact[i] = 0.0;
+                base[i] = w.tau_grav[s * m + i] + tau_task[i] + tau_contact[i];
+            }
             tsync();
             const bool quick = quick_feasible();
             if (quick) st |= 4;  // x = 0: torque_contact is left as it is, cf_redis_qp_ = 0

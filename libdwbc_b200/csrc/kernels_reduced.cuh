@@ -229,8 +229,10 @@ struct ReducedNcSmem {
     }
 };
 
+// qp_mode bit 0: the COM / contact-chain levels went through hqp_kernel (CalcSingleTaskTorqueWithQP_R); bit 1: so did the
+// contact redistribution (CalcContactRedistributeR): torque_contact_[0:contact_dof_] = torque_contact_R_[0:contact_dof_].
 __global__ void __launch_bounds__(TEAM, 4) reduced_nc_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, Work wr, ReducedX rx,
-                                                             ReducedCfg rc, int tmax) {
+                                                             ReducedCfg rc, int tmax, int qp_mode) {
     DWBC_DYN_SMEM(smem);
     const int tid = t_id(), nt = t_n();
     const long long s = blockIdx.x;
@@ -405,7 +407,9 @@ __global__ void __launch_bounds__(TEAM, 4) reduced_nc_kernel(const DevModel *__r
         for (int k = 0; k < 6; k++) v = fma(JI[k + i * 6], z[k], v);
         tau_task[co + i] = v;
     }
-    if (tid == 0) w.status[s] = 1 | (ok ? 2 : 0);
+    if (qp_mode & 2)  // reference src/dwbc.cpp:3765-3766
+        for (int i = tid; i < c && i < rm; i += nt) w.tau_contact[s * m + i] = wr.tau_contact[s * rm + i];
+    if (tid == 0) w.status[s] = 1 | (ok ? 2 : 0) | (((qp_mode & 2) && c > 6) ? (st & 4) : 0);  // reference: ret stays 0 for contact_dof_ <= 6
 }
 
 }  // namespace dwbc

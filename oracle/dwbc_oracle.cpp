@@ -237,6 +237,13 @@ struct Robot {
     void calc_task_space();
     int calc_task_torque(bool hqp);
     int single_task_qp(Task &t, const Mat &null_prev, const Mat &torque_prev);
+    int single_task_qp_on(Task &t, const Mat &Jkt, int m, const Mat &null_prev, const Mat &torque_prev, const Mat &NwJw, const Mat &J_C_INV_T,
+                          const Mat &P_C, bool tlim_set, const Mat &tlim);
+    // reduced torque limit (reduced_model_dof_ entries): the reference compares torque_limit_.size() with reduced_model_dof_
+    // in CalcSingleTaskTorqueWithQP_R (src/dwbc.cpp:3462-3468), i.e. the caller sets a reduced-size limit before the reduced HQP
+    bool tlimR_set = false;
+    Mat tlimR, torque_contact_R, cf_redis_qp_R;
+    int reduced_redistribute();
     int calc_redistribute(bool hqp);
     Mat get_contact_force(const Mat &command_torque) const;
     V3 get_zmp(const Mat &contact_force, std::vector<V3> *per_contact = nullptr) const;
@@ -572,6 +579,13 @@ void Robot::contact_const(Mat &A_const, Mat &A_rot, int &csize) const {
 
 // reference src/dwbc.cpp:941-1127
 int Robot::single_task_qp(Task &t, const Mat &null_prev, const Mat &torque_prev) {
+    return single_task_qp_on(t, t.Jkt, m, null_prev, torque_prev, NwJw, J_C_INV_T, P_C, tlim_set, tlim);
+}
+
+// The QP of CalcSingleTaskTorqueWithQP (src/dwbc.cpp:941-1127) and of its reduced twin CalcSingleTaskTorqueWithQP_R
+// (src/dwbc.cpp:3448-3599): the two differ only in the matrices they are handed (model size m / reduced_model_dof_).
+int Robot::single_task_qp_on(Task &t, const Mat &Jkt, int m, const Mat &null_prev, const Mat &torque_prev, const Mat &NwJw, const Mat &J_C_INV_T,
+                             const Mat &P_C, bool tlim_set, const Mat &tlim) {
     int td = t.dof, r = std::max(contact_dof - 6, 0);
     int nv = td + r;
     int tl_rows = tlim_set ? 2 * m : 0;
@@ -580,7 +594,7 @@ int Robot::single_task_qp(Task &t, const Mat &null_prev, const Mat &torque_prev)
     contact_const(A_const, A_rot, csize);
     int rows = csize + tl_rows;
     Mat Aq(rows, nv), ub(rows, 1);
-    Mat Nt = null_prev * t.Jkt * t.Lambda;
+    Mat Nt = null_prev * Jkt * t.Lambda;
     Mat base = torque_prev + Nt * t.fstar;
     if (tlim_set) {
         Aq.set_block(0, 0, Nt);
@@ -1068,7 +1082,9 @@ int Robot::reduced_task_space() {
 
 // ReducedCalcTaskControlTorque(hqp=false), reference src/dwbc.cpp:3255-3446 (else-branch :3374-3417, expansion :3442-3443)
 int Robot::reduced_task_torque(bool hqp) {
-    if (hqp) return 0;  // CalcSingleTaskTorqueWithQP_R / _R_NC: not restated yet
+    if (hqp)  // CalcSingleTaskTorqueWithQP_R_NC (non-contact tasks under hqp, src/dwbc.cpp:3601-3756) is not restated
+        for (auto &t : ts)
+            if (t.noncont) return 0;
     torque_task_R.set_zero(rmod, 1);
     torque_task.set_zero(m, 1);
     torque_task_NC.set_zero(nc_dof, 1);
@@ -1103,6 +1119,15 @@ int Robot::reduced_task_torque(bool hqp) {
                 null_torque_h_r.set_block(co_dof, 0, J_I_nc_inv_T * (t.torque_nc - p.J_NC.t() * null_force));
                 t.torque_null_h_R = p.Null_R * null_torque_h_r;
             }
+        } else if (hqp) {
+            // reference src/dwbc.cpp:3336-3362
+            t.fstar_qp.set_zero(t.dof, 1);
+            t.contact_qp.set_zero(std::max(contact_dof - 6, 0), 1);
+            Mat prev_null = (i == 0) ? Mat::identity(rmod) : ts[i - 1].Null_R;
+            Mat tprev = (i == 0) ? torque_grav_R : torque_grav_R + torque_task_R;
+            if (!single_task_qp_on(t, t.Jkt_R, rmod, prev_null, tprev, NwJw_R, J_CR_INV_T, P_CR, tlimR_set, tlimR)) return 0;
+            t.torque_h_R = t.Jkt_R * t.Lambda * (t.fstar + t.fstar_qp);
+            t.torque_null_h_R = (i == 0) ? t.torque_h_R : ts[i - 1].Null_R * t.torque_h_R;
         } else {
             t.torque_h_R = t.Jkt_R * t.Lambda * t.fstar;
             t.torque_null_h_R = (i == 0) ? t.torque_h_R : ts[i - 1].Null_R * t.torque_h_R;
@@ -1112,6 +1137,42 @@ int Robot::reduced_task_torque(bool hqp) {
     }
     torque_task.set_block(0, 0, torque_task_R.block(0, 0, co_dof, 1));
     torque_task.set_block(co_dof, 0, J_I_nc.t() * torque_task_R.block(co_dof, 0, 6, 1) + N_I_nc * torque_task_NC);
+    return 1;
+}
+
+// ReducedCalcContactRedistribute(hqp = true) -> CalcContactRedistributeR, reference src/dwbc.cpp:3758-3770, 4762-4960: the QP of
+// CalcContactRedistribute on the reduced matrices with torque_input = torque_grav_R_ + torque_task_R_; then
+// torque_contact_[0:contact_dof_] = torque_contact_R_[0:contact_dof_].
+int Robot::reduced_redistribute() {
+    torque_contact.set_zero(m, 1);
+    torque_contact_R.set_zero(rmod, 1);
+    const int r = contact_dof - 6;
+    if (r <= 0) return 0;  // reference: ret stays 0 when contact_dof_ <= 6
+    Mat tin = torque_grav_R + torque_task_R;
+    Mat A_const, A_rot;
+    int csize;
+    contact_const(A_const, A_rot, csize);
+    const int tl_rows = tlimR_set ? 2 * rmod : 0;
+    Mat Aq(tl_rows + csize, r), ub(tl_rows + csize, 1);
+    if (tlimR_set) {
+        Aq.set_block(0, 0, NwJw_R);
+        Aq.set_block(rmod, 0, -NwJw_R);
+        for (int i = 0; i < rmod; i++) {
+            ub[i] = tlimR[i] - tin[i];
+            ub[rmod + i] = tlimR[i] + tin[i];
+        }
+    }
+    Mat CM = -(A_const * A_rot);
+    Mat CJ = CM * J_CR_INV_T.right_cols(rmod);
+    Aq.set_block(tl_rows, 0, CJ * NwJw_R);
+    Mat rhs = CM * P_CR - CJ * tin;
+    for (int i = 0; i < csize; i++) ub[tl_rows + i] = rhs[i];
+    QpResult res = qp_min_norm(Aq, ub.d);
+    if (!res.status) return 0;
+    cf_redis_qp_R.set_zero(r, 1);
+    for (int i = 0; i < r; i++) cf_redis_qp_R[i] = res.x[i];
+    torque_contact_R = NwJw_R * cf_redis_qp_R;
+    for (int i = 0; i < contact_dof; i++) torque_contact[i] = torque_contact_R[i];
     return 1;
 }
 
@@ -1481,6 +1542,13 @@ int orc_reduced_contact_constraint(void *h) { return ((Robot *)h)->reduced_conta
 void orc_reduced_grav(void *h) { ((Robot *)h)->reduced_grav(); }
 int orc_reduced_task_space(void *h) { return ((Robot *)h)->reduced_task_space(); }
 int orc_reduced_task_torque(void *h, int hqp) { return ((Robot *)h)->reduced_task_torque(hqp != 0); }
+int orc_reduced_redistribute(void *h) { return ((Robot *)h)->reduced_redistribute(); }
+void orc_set_reduced_torque_limit(void *h, const double *tlim, int count) {
+    Robot *R = (Robot *)h;
+    R->tlimR_set = true;
+    R->tlimR.set_zero(count, 1);
+    for (int i = 0; i < count; i++) R->tlimR[i] = tlim[i];
+}
 void orc_configure_lqp(void *h) { ((Robot *)h)->configure_lqp(); }
 int orc_calc_lqp(void *h) { return ((Robot *)h)->calc_lqp(); }
 int orc_lqp_levels(void *h) { return (int)((Robot *)h)->lqp.size(); }
@@ -1541,7 +1609,8 @@ static const Mat *find_mat(Robot *R, const std::string &name, Mat &tmp) {
             {"A_R_inv", &R->A_R_inv}, {"A_R", &R->A_R}, {"J_I_nc_inv_T", &R->J_I_nc_inv_T}, {"N_I_nc", &R->N_I_nc}, {"G_R", &R->G_R}, {"J_CR", &R->J_CR},
             {"Lambda_CR", &R->Lambda_CR}, {"J_CR_INV_T", &R->J_CR_INV_T}, {"N_CR", &R->N_CR}, {"A_R_inv_N_CR", &R->A_R_inv_N_CR}, {"W_R", &R->W_R},
             {"W_R_inv", &R->W_R_inv}, {"V2_R", &R->V2_R}, {"NwJw_R", &R->NwJw_R}, {"P_CR", &R->P_CR}, {"torque_grav_R", &R->torque_grav_R},
-            {"J_base_R_kt", &R->J_base_R_kt}, {"torque_task_R", &R->torque_task_R}, {"torque_task_NC", &R->torque_task_NC}};
+            {"J_base_R_kt", &R->J_base_R_kt}, {"torque_task_R", &R->torque_task_R}, {"torque_task_NC", &R->torque_task_NC},
+            {"torque_contact_R", &R->torque_contact_R}, {"cf_redis_qp_R", &R->cf_redis_qp_R}};
         for (auto &e : red)
             if (name == e.first) return e.second;
     }

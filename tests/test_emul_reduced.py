@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from libdwbc_b200 import CONTACT_6D, SOLVE_GRAV, SOLVE_TASK, TASK_LINK_6D, TASK_LINK_POSITION, TASK_LINK_ROTATION, DwbcError, RobotDataBatch
+from oracle import oracle as orc
 from tests.common import *
 from tests.emul.emul_backend import EmulBackend
 from tests.test_oracle_reduced import full_and_reduced
@@ -103,3 +104,64 @@ def test_emul_reduced_rejections():
         rd2.set_task_space(l, np.zeros((1, t)), np.ascontiguousarray(posture_selector()) if l == 2 else None)
     with pytest.raises(DwbcError, match="UNDEFINED TASK TYPE"):
         rd2.reduced_solve(SOLVE_TASK)
+
+
+def run_reduced_hqp(make_rd, D, H, B=4, tlimR=None):
+    """Reduced HQP + reduced contact redistribution (CalcSingleTaskTorqueWithQP_R, CalcContactRedistributeR) on a COM /
+    contact-chain hierarchy vs the oracle; every other state saturates the friction rows."""
+    from libdwbc_b200 import CONTACT_6D, SOLVE_GRAV, SOLVE_HQP, SOLVE_REDIST, TASK_LINK_POSITION, TASK_LINK_ROTATION
+
+    q, qd, rng = synth_states(B, 20246)
+    fs = [0.5 * rng.standard_normal((B, 3)), rng.standard_normal((B, 3))]
+    fs[0][::2, 1] = 4.0
+    rd = make_rd(B)
+    rd.add_contact_constraint(LEFT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+    rd.add_contact_constraint(RIGHT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+    rd.add_task_space(0, TASK_LINK_POSITION, "COM")
+    rd.add_task_space(1, TASK_LINK_ROTATION, "pelvis_link")
+    rd.set_torque_limit(300.0)  # full-model limit: must be ignored by the reduced QPs
+    if tlimR is not None:
+        rd.set_reduced_torque_limit(tlimR)
+    rd.update_kinematics(D(q), D(qd))
+    rd.set_contact(D(np.ones((B, 2), dtype=np.uint8)))
+    rd.reduced_dynamics_calculate((1, 1))
+    rd.reduced_calc_contact_constraint()
+    for l, f in enumerate(fs):
+        rd.set_task_space(l, D(f))
+    tg, tt, tc, st = [H(x) for x in rd.reduced_solve(SOLVE_GRAV | SOLVE_HQP | SOLVE_REDIST)]
+    n_active = 0
+    for b in range(B):
+        ref = orc.OracleRobot(URDF)
+        ref.add_contact(LEFT_FOOT, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+        ref.add_contact(RIGHT_FOOT, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+        ref.add_task(0, orc.TASK_LINK_POSITION, "COM")
+        ref.add_task(1, orc.TASK_LINK_ROTATION, "pelvis_link")
+        if tlimR is not None:
+            ref.set_reduced_torque_limit(tlimR)
+        ref.update_kinematics(q[b], qd[b])
+        ref.set_contact(1, 1)
+        for l, f in enumerate(fs):
+            ref.set_task(l, f[b])
+        ref.reduced_dynamics()
+        assert ref.reduced_contact_constraint() == 1
+        ref.reduced_grav()
+        assert ref.reduced_task_space() == 1
+        ok = ref.reduced_task_torque(hqp=True)
+        ok2 = ref.reduced_redistribute()
+        assert (st[b] & 7) == (1 | (2 if ok else 0) | (4 if ok2 else 0)), (b, st[b], ok, ok2)
+        n_active += int(np.linalg.norm(ref.get("f_star_qp0")) > 1e-6)
+        assert relerr(tg[b], ref.get("torque_grav")[:, 0]) < 1e-9
+        assert relerr(tt[b], ref.get("torque_task")[:, 0]) < 1e-6, b
+        tcr = ref.get("torque_contact")[:, 0]
+        assert np.abs(tc[b] - tcr).max() < 1e-6 * max(1.0, np.abs(tcr).max()), b
+    assert n_active >= B // 2 - 1
+
+
+# reduced limit: 300 on the 12 contact-chain joints; the 6 coordinates of the condensed non-contact body carry its weight
+# (42.6 kg) and are not motor torques, so they get a wide bound
+TLIM_R = np.concatenate([np.full(12, 300.0), np.full(6, 2000.0)])
+
+
+@pytest.mark.parametrize("limited", [False, True])
+def test_emul_reduced_hqp_vs_oracle(limited):
+    run_reduced_hqp(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, lambda a: a, tlimR=TLIM_R if limited else None)

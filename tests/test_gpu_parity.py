@@ -479,3 +479,53 @@ def test_gpu_generic_dof(dof):
         return T(a, torch.uint8 if a.dtype == np.uint8 else torch.float64)
 
     run_generic(dof, lambda urdf, B: RobotDataBatch(urdf, B, 0), D, lambda x: x.cpu().numpy(), B=8)
+
+
+@pytest.mark.parametrize("limited", [False, True])
+def test_gpu_reduced_hqp_vs_oracle(limited):
+    """a9 QP branches (CalcSingleTaskTorqueWithQP_R, CalcContactRedistributeR; reference src/dwbc.cpp:3448-3599, 4777-4925) on the
+    device vs the oracle, whose restatement is pinned by "reduced HQP == full-model HQP" (tests/test_oracle_reduced.py)."""
+    from libdwbc_b200 import RobotDataBatch
+    from tests.test_emul_reduced import TLIM_R, run_reduced_hqp
+
+    def D(a):
+        a = np.ascontiguousarray(a)
+        return T(a, torch.uint8 if a.dtype == np.uint8 else torch.float64)
+
+    run_reduced_hqp(lambda B: RobotDataBatch(URDF, B, 0), D, lambda x: x.cpu().numpy(), B=16, tlimR=TLIM_R if limited else None)
+
+
+def test_gpu_reduced_hqp_full_size_equals_full_model():
+    """B = 65536: without a torque limit the reduced HQP + redistribution reproduces the full-model HQP of every state
+    (COM position / pelvis rotation hierarchy; 5 % of the states saturate the friction rows)."""
+    from libdwbc_b200 import (CONTACT_6D, SOLVE_GRAV, SOLVE_HQP, SOLVE_REDIST, TASK_LINK_POSITION, TASK_LINK_ROTATION, RobotDataBatch)
+
+    B = 65536
+    q, qd, rng = synth_states(B, 20247)
+    fs = [0.5 * rng.standard_normal((B, 3)), rng.standard_normal((B, 3))]
+    fs[0][rng.choice(B, B // 20, replace=False), 1] = 4.0
+    qt, qdt, fst, flags = T(q), T(qd), [T(f) for f in fs], T(np.ones((B, 2), dtype=np.uint8), torch.uint8)
+    res = []
+    for reduced in (False, True):
+        rd = RobotDataBatch(URDF, B, 0)
+        rd.add_contact_constraint(LEFT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+        rd.add_contact_constraint(RIGHT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+        rd.add_task_space(0, TASK_LINK_POSITION, "COM")
+        rd.add_task_space(1, TASK_LINK_ROTATION, "pelvis_link")
+        rd.update_kinematics(qt, qdt)
+        rd.set_contact(flags)
+        if reduced:
+            rd.reduced_dynamics_calculate((1, 1))
+            rd.reduced_calc_contact_constraint()
+        else:
+            rd.calc_contact_constraint()
+        for l, f in enumerate(fst):
+            rd.set_task_space(l, f)
+        res.append((rd.reduced_solve if reduced else rd.solve)(SOLVE_GRAV | SOLVE_HQP | SOLVE_REDIST))
+    torch.cuda.synchronize()
+    (tg, tt, tc, st), (rg, rt, rc_, rs) = res
+    both = ((st & 7) == 7) & ((rs & 7) == 7)
+    assert both.float().mean().item() > 0.98
+    et = ((rt - tt).norm(dim=1) / tt.norm(dim=1).clamp_min(1.0))[both].max().item()
+    ec = ((rc_[:, :12] - tc[:, :12]).norm(dim=1) / tc.norm(dim=1).clamp_min(1.0))[both].max().item()
+    assert et < 1e-6 and ec < 1e-5, (et, ec)

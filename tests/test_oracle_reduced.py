@@ -84,3 +84,65 @@ def test_undefined_task_type_is_rejected():
     ref.reduced_dynamics()
     ref.reduced_contact_constraint()
     assert ref.reduced_task_space() == 0
+
+
+def _hqp_pair(q, qd, flags, fstars, tlimR=None):
+    """full-model HQP and reduced HQP (CalcSingleTaskTorqueWithQP_R, src/dwbc.cpp:3448-3599) on a COM / contact-chain hierarchy"""
+    out = []
+    for reduced in (False, True):
+        ref = orc.OracleRobot(URDF)
+        ref.add_contact(LEFT_FOOT, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+        ref.add_contact(RIGHT_FOOT, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+        ref.add_task(0, orc.TASK_LINK_POSITION, "COM")
+        ref.add_task(1, orc.TASK_LINK_ROTATION, "pelvis_link")
+        ref.update_kinematics(q, qd)
+        ref.set_contact(*flags)
+        for l, f in enumerate(fstars):
+            ref.set_task(l, f)
+        if not reduced:
+            assert ref.calc_contact_constraint() == 1
+            ref.calc_grav()
+            ok = ref.calc_task_torque(hqp=True)
+            ok2 = ref.calc_redistribute(hqp=True)
+        else:
+            if tlimR is not None:
+                ref.set_reduced_torque_limit(tlimR)
+            ref.reduced_dynamics()
+            assert ref.reduced_contact_constraint() == 1
+            ref.reduced_grav()
+            assert ref.reduced_task_space() == 1
+            ok = ref.reduced_task_torque(hqp=True)
+            ok2 = ref.reduced_redistribute()
+        out.append((ref, ok, ok2))
+    return out
+
+
+def test_reduced_hqp_equals_full_hqp_without_torque_limit():
+    """No golden exists for the reduced QP branch.  Property: for COM / contact-chain tasks the reduced model is exact, so without
+    a torque limit (the two models' limits are different objects) the reduced HQP reproduces the full-model HQP -- including a
+    state whose lateral COM acceleration saturates the friction rows (f* = 4, reference tests/dwbc_test.cpp:56)."""
+    B = 5
+    q, qd, rng = synth_states(B, 20244)
+    n_active = 0
+    for b in range(B):
+        fs = [0.5 * rng.standard_normal(3), rng.standard_normal(3)]
+        if b % 2 == 0:
+            fs[0][1] = 4.0
+        (full, ok, ok2), (red, rok, rok2) = _hqp_pair(q[b], qd[b], (1, 1), fs)
+        assert ok == 1 and rok == 1 and ok2 == 1 and rok2 == 1
+        n_active += int(np.linalg.norm(full.get("f_star_qp0")) > 1e-6)
+        assert relerr(red.get("f_star_qp0")[:, 0], full.get("f_star_qp0")[:, 0]) < 1e-6 or np.linalg.norm(full.get("f_star_qp0")) < 1e-9
+        assert relerr(red.get("torque_task")[:, 0], full.get("torque_task")[:, 0]) < 1e-6
+        # contact redistribution: the leg part of the full-model contact torque (upper-body entries of NwJw are ~0)
+        tc_full = full.get("torque_contact")[:, 0]
+        assert np.abs(red.get("torque_contact")[:12, 0] - tc_full[:12]).max() < 1e-6 * max(1.0, np.abs(tc_full).max())
+    assert n_active >= 2
+
+
+def test_reduced_hqp_with_reduced_torque_limit_respects_it():
+    q, qd, rng = synth_states(2, 20245)
+    fs = [np.array([0.3, 4.0, 0.2]), np.array([0.1, -0.1, 0.1])]
+    (full, ok, ok2), (red, rok, rok2) = _hqp_pair(q[0], qd[0], (1, 1), fs, tlimR=np.full(18, 300.0))
+    assert rok == 1
+    tr = red.get("torque_grav_R")[:, 0] + red.get("torque_task_R")[:, 0]
+    assert np.abs(tr).max() <= 300.0 + 1e-6
