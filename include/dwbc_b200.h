@@ -236,6 +236,13 @@ int dwbc_batch_get_reduced_matrix(dwbc_batch_t *b, int which, int level, double 
  * -(levels solved) when a level failed (the answer of the last solved level is returned, as HQP::solveSequential leaves it),
  * 0 when the contact constraint of the state is invalid.  Any output pointer may be NULL. */
 int dwbc_batch_calc_control_torque_lqp(dwbc_batch_t *b, double *y_dev, double *tau_dev, int32_t *status_dev, void *stream);
+/* ConfigureLQP_R + CalcControlTorqueLQP_R (reference src/dwbc.cpp:4504-4632, 4456-4478): the same hierarchy on the reduced model
+ * (A_R, A_R_inv, G_R, J_CR, J_task J_R_INV_T^T; torque bound 200 with 600 on row m-4; cost A_R / |A_|), task levels = the COM /
+ * contact-chain levels.  Call after reduced_dynamics, reduced_calc_contact_constraint and reduced_solve(DWBC_SOLVE_TASK) (which
+ * classifies the levels and forms the reduced task Jacobians).  y_dev [B x (reduced_system_dof + cmax)], tau_dev
+ * [B x reduced_model_dof].  ConfigureLQP_R_NC (the non-contact part) is not built. */
+int dwbc_batch_calc_control_torque_lqp_r(dwbc_batch_t *b, double *y_dev, double *tau_dev, int32_t *status_dev, void *stream);
+enum { DWBC_LQP_REDUCED = 256 }; /* OR into `which` of dwbc_batch_get_lqp for the results of the reduced variant */
 enum {
     DWBC_LQP_Y = 0,      /* hqp_hs_[level].y_ans_   (n + cmax) x 1, level in [0, 2 + task levels) */
     DWBC_LQP_V1,         /* hqp_hs_[1].v_ans_       (2m + 10*max_active_contacts) x 1: friction/ZMP rows, then +accel, -accel */

@@ -314,9 +314,20 @@ class RobotDataBatch:
         self._ck(self.L.dwbc_batch_calc_control_torque_lqp(self._h, be.ptr(y), be.ptr(tau), be.ptr(st), be.stream()))
         return y, tau, st
 
-    def get_lqp(self, name, level=0):
-        """"y" (answer after `level`), "v1" (slack of the level-1 inequality rows), "torque"."""
-        return self._get(self.L.dwbc_batch_get_lqp, {"y": 0, "v1": 1, "torque": 2}[name], level)
+    def calc_control_torque_lqp_r(self, out=None):
+        """ConfigureLQP_R + CalcControlTorqueLQP_R (after reduced_dynamics_calculate, reduced_calc_contact_constraint and
+        reduced_solve(SOLVE_TASK)): returns (y [B, reduced_system_dof + cmax], torque [B, reduced_model_dof], status [B])."""
+        be = self.be
+        B = self.batch
+        if out is None:
+            out = (be.empty((B, self.reduced_system_dof_ + self.cmax)), be.empty((B, self.reduced_model_dof_)), be.empty((B,), "i4"))
+        y, tau, st = out
+        self._ck(self.L.dwbc_batch_calc_control_torque_lqp_r(self._h, be.ptr(y), be.ptr(tau), be.ptr(st), be.stream()))
+        return y, tau, st
+
+    def get_lqp(self, name, level=0, reduced=False):
+        """"y" (answer after `level`), "v1" (slack of the level-1 inequality rows), "torque"; reduced=True: ConfigureLQP_R results."""
+        return self._get(self.L.dwbc_batch_get_lqp, {"y": 0, "v1": 1, "torque": 2}[name] | (256 if reduced else 0), level)
 
     def lqp_iterations(self):
         buf = self.be.empty((self.batch,), "i4")

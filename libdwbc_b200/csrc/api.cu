@@ -78,8 +78,8 @@ struct dwbc_batch {
     const double *last_qd = nullptr;  // qdot of the last update_kinematics (caller-owned or mj_qd)
     double *mj_q = nullptr, *mj_qd = nullptr;
     // a10 LQP variant
-    LqpOut lq{};
-    bool lqp_allocated = false, have_lqp = false;
+    LqpOut lq{}, lqr{};
+    bool lqp_allocated = false, have_lqp = false, lqr_allocated = false, have_lqp_r = false;
 };
 
 namespace {
@@ -726,6 +726,8 @@ void free_reduced(dwbc_batch *b) {
     free_reduced_tasks(b);
     for (void *p : b->red_allocs) cudaFree(p);
     b->red_allocs.clear();
+    b->lqr = LqpOut{};
+    b->lqr_allocated = b->have_lqp_r = false;
     b->red_rn = 0;
     b->d_cfgR = nullptr;
 }
@@ -1048,6 +1050,52 @@ int dwbc_batch_get_reduced_matrix(dwbc_batch_t *b, int which, int level, double 
 
 
 // ---- a10: LQP variant ----
+namespace {
+// shared by ConfigureLQP + CalcControlTorqueLQP (full model) and ConfigureLQP_R + CalcControlTorqueLQP_R (reduced model)
+int launch_lqp(dwbc_batch *b, bool reduced, double *y_dev, double *tau_dev, int32_t *status_dev, cudaStream_t st) {
+    const BatchCfg &cfg = reduced ? b->cfgR : b->cfg;
+    Work w = reduced ? b->wr : b->w;
+    LqpOut &lq = reduced ? b->lqr : b->lq;
+    bool &allocated = reduced ? b->lqr_allocated : b->lqp_allocated;
+    if (reduced) {
+        w.A = b->rx.AR;   // A_R (the reduced workspace shares the full A_ for the contact stage)
+        w.Bnl = b->wr.G;  // ConfigureLQP_R uses the gravity vector G_R only (reference src/dwbc.cpp:4526, 4538-4539, 4546)
+    }
+    const size_t B = b->B, n = w.n, m = w.m;
+    if (n + CMAX - 6 > LQP_WCAP || (n + CMAX - 6) * (n + CMAX - 5) / 2 > (size_t)LQP_CHOL_OWN * TEAM)
+        return fail(DWBC_ERR_ARG, "calc_control_torque_lqp: model too large for the LQP kernel (n + cmax - 6 <= 48)");
+    if (!allocated) {
+        std::vector<void *> *L = reduced ? &b->red_allocs : nullptr;
+        if (!dev_alloc(b, &lq.y, B * LQP_MAX_LEVELS * (n + CMAX), L) || !dev_alloc(b, &lq.v1, B * (2 * m + 10 * MAX_ACTIVE_CONTACTS), L) ||
+            !dev_alloc(b, &lq.tau, B * m, L) || !dev_alloc(b, &lq.status, B, L) || !dev_alloc(b, &lq.iters, B, L))
+            return DWBC_ERR_CUDA;
+        allocated = true;
+    }
+    int tmax = 1;
+    for (int l = 0; l < cfg.nlevels; l++) tmax = cfg.tasks[l].dof > tmax ? cfg.tasks[l].dof : tmax;
+    LqpParams prm{};
+    prm.anorm_src = b->w.A;
+    prm.anorm_n = b->w.n;
+    for (size_t i = 0; i < m && i < (size_t)MAXB; i++) prm.tlim[i] = LQP_TORQUE_LIMIT;
+    if (reduced && m >= 4) prm.tlim[m - 4] = 600.0;  // reference src/dwbc.cpp:4529-4531
+    const LqpSmem L((int)n, (int)m, tmax);
+    const size_t smem = sizeof(double) * L.total;
+    CK(cudaFuncSetAttribute(lqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        KernelScope ks(b, DWBC_K_LQP, st);
+        DWBC_LAUNCH(lqp_kernel, b->B, TEAM, smem, st, b->d_model, reduced ? b->d_cfgR : b->d_cfg, w, lq, tmax, prm);
+    }
+    CK(cudaGetLastError());
+    const int nlev = 2 + cfg.nlevels;
+    if (y_dev)
+        CK(cudaMemcpy2DAsync(y_dev, sizeof(double) * (n + CMAX), lq.y + (size_t)(nlev - 1) * (n + CMAX), sizeof(double) * LQP_MAX_LEVELS * (n + CMAX),
+                             sizeof(double) * (n + CMAX), B, cudaMemcpyDeviceToDevice, st));
+    if (tau_dev) CK(cudaMemcpyAsync(tau_dev, lq.tau, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));
+    if (status_dev) CK(cudaMemcpyAsync(status_dev, lq.status, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+    return DWBC_OK;
+}
+}  // namespace
+
 int dwbc_batch_calc_control_torque_lqp(dwbc_batch_t *b, double *y_dev, double *tau_dev, int32_t *status_dev, void *stream) {
     if (!b) return fail(DWBC_ERR_ARG, "calc_control_torque_lqp: null handle");
     if (!b->have_cc) return fail(DWBC_ERR_ORDER, "calc_control_torque_lqp: call calc_contact_constraint first");
@@ -1057,42 +1105,35 @@ int dwbc_batch_calc_control_torque_lqp(dwbc_batch_t *b, double *y_dev, double *t
     if (rc) return rc;
     for (int l = 0; l < b->cfg.nlevels; l++)
         if (!b->w.fstar[l]) return fail(DWBC_ERR_ORDER, "calc_control_torque_lqp: set_task has not been called for every level");
-    const size_t B = b->B, n = b->w.n, m = b->w.m;
-    if (n + CMAX - 6 > LQP_WCAP || (n + CMAX - 6) * (n + CMAX - 5) / 2 > LQP_CHOL_OWN * TEAM)
-        return fail(DWBC_ERR_ARG, "calc_control_torque_lqp: model too large for the LQP kernel (n + cmax - 6 <= 48)");
-    if (!b->lqp_allocated) {
-        if (!dev_alloc(b, &b->lq.y, B * LQP_MAX_LEVELS * (n + CMAX)) || !dev_alloc(b, &b->lq.v1, B * (2 * m + 10 * MAX_ACTIVE_CONTACTS)) ||
-            !dev_alloc(b, &b->lq.tau, B * m) || !dev_alloc(b, &b->lq.status, B) || !dev_alloc(b, &b->lq.iters, B))
-            return DWBC_ERR_CUDA;
-        b->lqp_allocated = true;
-    }
-    int tmax = 1;
-    for (int l = 0; l < b->cfg.nlevels; l++) tmax = b->cfg.tasks[l].dof > tmax ? b->cfg.tasks[l].dof : tmax;
-    const LqpSmem L((int)n, (int)m, tmax);
-    const size_t smem = sizeof(double) * L.total;
-    CK(cudaFuncSetAttribute(lqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-        KernelScope ks(b, DWBC_K_LQP, st);
-        DWBC_LAUNCH(lqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, b->lq, tmax);
-    }
-    CK(cudaGetLastError());
+    rc = launch_lqp(b, false, y_dev, tau_dev, status_dev, st);
+    if (rc) return rc;
     b->have_lqp = true;
-    const int nlev = 2 + b->cfg.nlevels;
-    if (y_dev)
-        CK(cudaMemcpy2DAsync(y_dev, sizeof(double) * (n + CMAX), b->lq.y + (size_t)(nlev - 1) * (n + CMAX), sizeof(double) * LQP_MAX_LEVELS * (n + CMAX),
-                             sizeof(double) * (n + CMAX), B, cudaMemcpyDeviceToDevice, st));
-    if (tau_dev) CK(cudaMemcpyAsync(tau_dev, b->lq.tau, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));
-    if (status_dev) CK(cudaMemcpyAsync(status_dev, b->lq.status, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+    return DWBC_OK;
+}
+
+int dwbc_batch_calc_control_torque_lqp_r(dwbc_batch_t *b, double *y_dev, double *tau_dev, int32_t *status_dev, void *stream) {
+    if (!b) return fail(DWBC_ERR_ARG, "calc_control_torque_lqp_r: null handle");
+    if (!b->have_red_cc || b->rc.k_contact <= 0)
+        return fail(DWBC_ERR_ORDER, "calc_control_torque_lqp_r: call reduced_dynamics, reduced_calc_contact_constraint and reduced_solve(DWBC_SOLVE_TASK) first");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_lqp(b, true, y_dev, tau_dev, status_dev, st);
+    if (rc) return rc;
+    b->have_lqp_r = true;
     return DWBC_OK;
 }
 
 int dwbc_batch_get_lqp(dwbc_batch_t *b, int which, int level, double *out_dev, int *rows, int *cols, void *stream) {
     if (!b) return fail(DWBC_ERR_ARG, "get_lqp: null handle");
-    if (!b->have_lqp) return fail(DWBC_ERR_ORDER, "get_lqp: call calc_control_torque_lqp first");
+    const bool reduced = (which & DWBC_LQP_REDUCED) != 0;
+    which &= ~DWBC_LQP_REDUCED;
+    if (!(reduced ? b->have_lqp_r : b->have_lqp)) return fail(DWBC_ERR_ORDER, "get_lqp: call calc_control_torque_lqp[_r] first");
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t B = b->B, n = b->w.n, m = b->w.m, nvs = n + CMAX;
-    const int nlev = 2 + b->cfg.nlevels;
+    const Work &w = reduced ? b->wr : b->w;
+    const LqpOut &lq = reduced ? b->lqr : b->lq;
+    const size_t B = b->B, n = w.n, m = w.m, nvs = n + CMAX;
+    const int nlev = 2 + (reduced ? b->cfgR.nlevels : b->cfg.nlevels);
     int rr = 0;
     switch (which) {
     case DWBC_LQP_Y:
@@ -1107,10 +1148,10 @@ int dwbc_batch_get_lqp(dwbc_batch_t *b, int which, int level, double *out_dev, i
     if (cols) *cols = 1;
     if (!out_dev) return DWBC_OK;
     if (which == DWBC_LQP_Y)
-        CK(cudaMemcpy2DAsync(out_dev, sizeof(double) * nvs, b->lq.y + (size_t)level * nvs, sizeof(double) * LQP_MAX_LEVELS * nvs, sizeof(double) * nvs, B,
+        CK(cudaMemcpy2DAsync(out_dev, sizeof(double) * nvs, lq.y + (size_t)level * nvs, sizeof(double) * LQP_MAX_LEVELS * nvs, sizeof(double) * nvs, B,
                              cudaMemcpyDeviceToDevice, st));
     else
-        CK(cudaMemcpyAsync(out_dev, which == DWBC_LQP_V1 ? b->lq.v1 : b->lq.tau, sizeof(double) * B * rr, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(out_dev, which == DWBC_LQP_V1 ? lq.v1 : lq.tau, sizeof(double) * B * rr, cudaMemcpyDeviceToDevice, st));
     return DWBC_OK;
 }
 

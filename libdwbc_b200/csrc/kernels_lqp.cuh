@@ -47,6 +47,14 @@ struct LqpOut {
     int *iters;     // [B]  active-set iterations
 };
 
+// What differs between ConfigureLQP and ConfigureLQP_R besides the matrices in `Work` (reference src/dwbc.cpp:4341, 4357-4371 vs
+// :4519, 4529-4531): the torque bound of every joint row and the matrix whose Frobenius norm scales the cost.
+struct LqpParams {
+    const double *anorm_src;  // [B][anorm_n * anorm_n]  |A_|_F is always the FULL mass matrix
+    int anorm_n;
+    double tlim[MAXB];        // torque bound of row i (200; ConfigureLQP_R: 600 on row m-4)
+};
+
 struct LqpSmem {
     int nvmax, numax, urmax, rtmax, ldz, ldg, ldh, lde, ldr, ldt;
     int Z, G, H, E, R, vec, total;
@@ -431,7 +439,8 @@ __device__ __noinline__ int lqp_ldp_solve(double *sm, int n, int m, int tmax, in
     return status == 1 ? q : -1;
 }
 
-__global__ void __launch_bounds__(TEAM, 2) lqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, LqpOut out, int tmax) {
+__global__ void __launch_bounds__(TEAM, 2) lqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, LqpOut out, int tmax,
+                                                      LqpParams prm) {
     DWBC_DYN_SMEM(smem);
     const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
     const long long s = blockIdx.x;
@@ -468,7 +477,10 @@ __global__ void __launch_bounds__(TEAM, 2) lqp_kernel(const DevModel *__restrict
     for (int i = tid; i < c; i += nt) y[n + i] = 0.0;
     for (int i = tid; i < L.rtmax; i += nt) vfro[i] = 0.0;
     double an = 0.0;
-    for (int e = tid; e < n * n; e += nt) an = fma(A[e], A[e], an);
+    {
+        const double *An = prm.anorm_src + s * (long long)prm.anorm_n * prm.anorm_n;
+        for (int e = tid; e < prm.anorm_n * prm.anorm_n; e += nt) an = fma(An[e], An[e], an);
+    }
     an = sqrt(lq_team_sum(an, red));
     const double hs = 5.0 / an;  // reference src/dwbc.cpp:4341
     for (int e = tid; e < kc * 6; e += nt) {
@@ -564,8 +576,8 @@ __global__ void __launch_bounds__(TEAM, 2) lqp_kernel(const DevModel *__restrict
                 }
                 const double rn = s2 > 0.0 ? rsqrt(s2) : 0.0;
                 u[r] = rn;  // scratch: 1 / row norm of the torque rows
-                ub[r] = (LQP_TORQUE_LIMIT - tq) * rn;
-                ub[m + r] = (LQP_TORQUE_LIMIT + tq) * rn;
+                ub[r] = (prm.tlim[r] - tq) * rn;
+                ub[m + r] = (prm.tlim[r] + tq) * rn;
                 const int ia = 3 * m + 10 * kc;
                 ub[2 * m + 10 * kc + r] = LQP_ACC_LIMIT - y[6 + r] + vfro[2 * m + 10 * kc + r];
                 ub[ia + r] = LQP_ACC_LIMIT + y[6 + r] + vfro[ia + r];

@@ -275,7 +275,8 @@ struct Robot {
     std::vector<LqpLevel> lqp;
     Mat lqp_H, lqp_torque;  // cost Hessian shared by the levels; torque of the final y
     int lqp_acc = 0, lqp_con = 0;
-    void configure_lqp();
+    void configure_lqp(bool reduced = false);
+    bool lqp_reduced = false;
     void lqp_prepare();
     int lqp_solve_level(int i);
     int calc_lqp();
@@ -1214,14 +1215,22 @@ static void lqp_normalize(Mat &A, Mat &a) {  // HQP_Hierarch::normalizeConstrain
     }
 }
 
-// reference src/dwbc.cpp:4304-4430 (ConfigureLQP)
-void Robot::configure_lqp() {
+// reference src/dwbc.cpp:4304-4430 (ConfigureLQP) and, with reduced = true, :4504-4632 (ConfigureLQP_R): the same hierarchy on
+// A_R, A_R_inv, G_R (gravity only), J_CR, J_task J_R_INV_T^T, torque limit 200 except 600 on entry size-4 (:4529-4531), cost
+// A_R / |A_| (the norm of the FULL mass matrix, :4519); only the COM / contact-chain task levels are added (:4609-4627).
+void Robot::configure_lqp(bool reduced) {
+    lqp_reduced = reduced;
+    const Mat &A = reduced ? this->A_R : this->A;
+    const Mat &A_inv = reduced ? this->A_R_inv : this->A_inv;
+    const Mat &B = reduced ? this->G_R : this->B;
+    const Mat &J_C = reduced ? this->J_CR : this->J_C;
+    const int n = reduced ? rsys : this->n, m = reduced ? rmod : this->m;
     const int acc = n, tq = m, con = contact_dof, nvar = acc + con;
     lqp_acc = acc;
     lqp_con = con;
     lqp.clear();
     lqp_H.set_zero(nvar, nvar);
-    const double an = A.norm();
+    const double an = this->A.norm();
     for (int j = 0; j < acc; j++)
         for (int i = 0; i < acc; i++) lqp_H(i, j) = A(i, j) / an * 5.0;  // :4341
     Mat JcT = J_C.t();
@@ -1242,8 +1251,9 @@ void Robot::configure_lqp() {
         for (int i = 0; i < tq; i++) {
             for (int j = 0; j < acc; j++) L.A(i, j) = A(6 + i, j), L.A(tq + i, j) = -A(6 + i, j);
             for (int j = 0; j < con; j++) L.A(i, acc + j) = JcT(6 + i, j), L.A(tq + i, acc + j) = -JcT(6 + i, j);
-            L.a[i] = -200.0 + B[6 + i];
-            L.a[tq + i] = -200.0 - B[6 + i];
+            const double tl = (reduced && i == tq - 4) ? 600.0 : 200.0;
+            L.a[i] = -tl + B[6 + i];
+            L.a[tq + i] = -tl - B[6 + i];
         }
         lqp_normalize(L.A, L.a);
         lqp_normalize(L.B, L.b);
@@ -1286,13 +1296,15 @@ void Robot::configure_lqp() {
     }
     // Priority 3..: one level per task space, J_task qdd = f*  :4409-4425
     for (auto &t : ts) {
+        if (reduced && t.noncont) continue;
+        const Mat &TJ = reduced ? t.J_R : t.J;
         LqpLevel L;
         L.nineq = 0;
         L.neq = t.dof;
         L.B.set_zero(t.dof, nvar);
         L.b.set_zero(t.dof, 1);
         for (int j = 0; j < acc; j++)
-            for (int i = 0; i < t.dof; i++) L.B(i, j) = t.J(i, j);
+            for (int i = 0; i < t.dof; i++) L.B(i, j) = TJ(i, j);
         for (int i = 0; i < t.dof; i++) L.b[i] = -t.fstar[i];
         L.cost = true;
         lqp_normalize(L.B, L.b);
@@ -1433,6 +1445,10 @@ int Robot::calc_lqp() {
         }
     }
     const Mat &y = lqp.back().y;
+    const Mat &A = lqp_reduced ? this->A_R : this->A;
+    const Mat &B = lqp_reduced ? this->G_R : this->B;
+    const Mat &J_C = lqp_reduced ? this->J_CR : this->J_C;
+    const int n = lqp_reduced ? rsys : this->n, m = lqp_reduced ? rmod : this->m;
     lqp_torque.set_zero(m, 1);
     for (int i = 0; i < m; i++) {
         double s = B[6 + i];
@@ -1549,7 +1565,8 @@ void orc_set_reduced_torque_limit(void *h, const double *tlim, int count) {
     R->tlimR.set_zero(count, 1);
     for (int i = 0; i < count; i++) R->tlimR[i] = tlim[i];
 }
-void orc_configure_lqp(void *h) { ((Robot *)h)->configure_lqp(); }
+void orc_configure_lqp(void *h) { ((Robot *)h)->configure_lqp(false); }
+void orc_configure_lqp_r(void *h) { ((Robot *)h)->configure_lqp(true); }
 int orc_calc_lqp(void *h) { return ((Robot *)h)->calc_lqp(); }
 int orc_lqp_levels(void *h) { return (int)((Robot *)h)->lqp.size(); }
 void orc_reduced_dims(void *h, int *out) {

@@ -74,7 +74,7 @@ def lib():
         L.orc_reduced_redistribute.argtypes = [C.c_void_p]
         L.orc_set_reduced_torque_limit.argtypes = [C.c_void_p, _dp, C.c_int]
         L.orc_reduced_dims.argtypes = [C.c_void_p, _ip]
-        for f in ("orc_configure_lqp", "orc_calc_lqp", "orc_lqp_levels", "orc_update_task_space"):
+        for f in ("orc_configure_lqp", "orc_configure_lqp_r", "orc_calc_lqp", "orc_lqp_levels", "orc_update_task_space"):
             getattr(L, f).argtypes = [C.c_void_p]
         _lib = L
     return _lib
@@ -209,8 +209,10 @@ class OracleRobot:
     def update_task_space(self):
         lib().orc_update_task_space(self.h)
 
-    def configure_lqp(self):
-        lib().orc_configure_lqp(self.h)
+    def configure_lqp(self, reduced=False):
+        """ConfigureLQP (reference src/dwbc.cpp:4304-4430) or, reduced=True, ConfigureLQP_R (:4504-4632; needs reduced_dynamics,
+        reduced_contact_constraint and reduced_task_space first)"""
+        (lib().orc_configure_lqp_r if reduced else lib().orc_configure_lqp)(self.h)
         return lib().orc_lqp_levels(self.h)
 
     def calc_lqp(self):

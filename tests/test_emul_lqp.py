@@ -62,3 +62,54 @@ def test_emul_lqp_vs_oracle(hard):
     out = rd.calc_control_torque_lqp()
     refs = lqp_oracle_states(q, qd, flags, fs)
     check_lqp(rd, out, refs, flags)
+
+
+def run_reduced_lqp(make_rd, D, H, B=3):
+    """ConfigureLQP_R + CalcControlTorqueLQP_R (reference src/dwbc.cpp:4504-4632) vs the oracle: hierarchy = COM position +
+    pelvis rotation (contact-chain level) followed by a non-contact level that the reduced LQP leaves out."""
+    from libdwbc_b200 import CONTACT_6D, SOLVE_GRAV, SOLVE_TASK, TASK_LINK_6D, TASK_LINK_POSITION, TASK_LINK_ROTATION
+
+    q, qd, rng = synth_states(B, 20249)
+    fs = lqp_fstars(rng, B, False)
+    fs[0][0, 1] = 12.0  # one state far beyond the friction cone
+    rd = make_rd(B)
+    rd.add_contact_constraint(LEFT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.13, 0.06)
+    rd.add_contact_constraint(RIGHT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.13, 0.06)
+    rd.add_task_space(0, TASK_LINK_POSITION, "COM")
+    rd.add_task_space(0, TASK_LINK_ROTATION, "pelvis_link")
+    rd.add_task_space(1, TASK_LINK_6D, "L_Wrist2_Link")
+    rd.update_kinematics(D(q), D(qd))
+    rd.set_contact(D(np.ones((B, 2), dtype=np.uint8)))
+    rd.reduced_dynamics_calculate((1, 1))
+    rd.reduced_calc_contact_constraint()
+    for l, f in enumerate(fs):
+        rd.set_task_space(l, D(f))
+    rd.reduced_solve(SOLVE_GRAV | SOLVE_TASK)
+    y, tau, st = [H(x) for x in rd.calc_control_torque_lqp_r()]
+    n = 24
+    for b in range(B):
+        r = orc.OracleRobot(URDF)
+        r.add_contact(LEFT_FOOT, FOOT_POINT, (0, 0, 1), 0.13, 0.06)
+        r.add_contact(RIGHT_FOOT, FOOT_POINT, (0, 0, 1), 0.13, 0.06)
+        r.add_task(0, orc.TASK_LINK_POSITION, "COM")
+        r.add_task(0, orc.TASK_LINK_ROTATION, "pelvis_link")
+        r.add_task(1, orc.TASK_LINK_6D, "L_Wrist2_Link")
+        r.update_kinematics(q[b], qd[b])
+        r.set_contact(1, 1)
+        for l, f in enumerate(fs):
+            r.set_task(l, f[b])
+        r.reduced_dynamics()
+        assert r.reduced_contact_constraint() == 1
+        assert r.reduced_task_space() == 1
+        nl = r.configure_lqp(reduced=True)
+        ok = r.calc_lqp()
+        assert nl == 3 and ok == 1 and int(st[b]) == 3, (b, nl, ok, st[b])
+        for l in range(nl):
+            yl = H(rd.get_lqp("y", l, reduced=True))[b]
+            assert relerr(yl[:n + 12], r.get(f"lqp_y{l}")[:, 0]) < 1e-6, (b, l)
+        assert relerr(tau[b], r.get("lqp_torque")[:, 0]) < 1e-6, b
+        assert relerr(y[b][:n + 12], r.get(f"lqp_y{nl - 1}")[:, 0]) < 1e-6
+
+
+def test_emul_reduced_lqp_vs_oracle():
+    run_reduced_lqp(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, lambda a: a)

@@ -529,3 +529,15 @@ def test_gpu_reduced_hqp_full_size_equals_full_model():
     et = ((rt - tt).norm(dim=1) / tt.norm(dim=1).clamp_min(1.0))[both].max().item()
     ec = ((rc_[:, :12] - tc[:, :12]).norm(dim=1) / tc.norm(dim=1).clamp_min(1.0))[both].max().item()
     assert et < 1e-6 and ec < 1e-5, (et, ec)
+
+
+def test_gpu_reduced_lqp_vs_oracle():
+    """a10 on the reduced model (ConfigureLQP_R + CalcControlTorqueLQP_R, reference src/dwbc.cpp:4504-4632) vs the oracle."""
+    from libdwbc_b200 import RobotDataBatch
+    from tests.test_emul_lqp import run_reduced_lqp
+
+    def D(a):
+        a = np.ascontiguousarray(a)
+        return T(a, torch.uint8 if a.dtype == np.uint8 else torch.float64)
+
+    run_reduced_lqp(lambda B: RobotDataBatch(URDF, B, 0), D, lambda x: x.cpu().numpy(), B=12)

@@ -108,3 +108,48 @@ def test_lqp_oracle_kkt_and_hierarchy(flags, hard):
             if sum(flags) == 2:  # single support: the ZMP rows of a random posture can be physically unattainable
                 assert np.linalg.norm(r.get("lqp_v1")) < 1e-3  # sigma-regularisation bias only
             assert np.linalg.norm(Jc @ y[:n]) < 0.1 * np.linalg.norm(Jc @ ys[0][:n])
+
+
+def test_reduced_lqp_oracle_kkt_and_physics():
+    """ConfigureLQP_R (reference src/dwbc.cpp:4504-4632): the same hierarchy on the reduced model.  KKT of every level, the
+    reduced floating-base equation of motion (the reduced variant uses gravity G_R only) and the null-space hierarchy."""
+    q, _, rng = synth_states(3, 20248)
+    for b in range(3):
+        f0 = np.concatenate([0.5 * rng.standard_normal(3), 1.0 * rng.standard_normal(3)])
+        res = []
+        for reduced in (False, True):
+            r = orc.OracleRobot(URDF)
+            r.add_contact(LEFT_FOOT, FOOT_POINT, (0, 0, 1), 0.13, 0.06)
+            r.add_contact(RIGHT_FOOT, FOOT_POINT, (0, 0, 1), 0.13, 0.06)
+            r.add_task(0, orc.TASK_LINK_POSITION, "COM")
+            r.add_task(0, orc.TASK_LINK_ROTATION, "pelvis_link")
+            r.update_kinematics(q[b], np.zeros(39))
+            r.set_contact(1, 1)
+            r.set_task(0, f0)
+            if reduced:
+                r.reduced_dynamics()
+                assert r.reduced_contact_constraint() == 1
+                assert r.reduced_task_space() == 1
+            else:
+                assert r.calc_contact_constraint() == 1
+                r.update_task_space()
+            nl = r.configure_lqp(reduced)
+            assert nl == 3 and r.calc_lqp() == 1
+            res.append(r)
+        full, red = res
+        n = 24
+        for l in range(1, 3):
+            H, g = red.get(f"lqp_qpH{l}"), red.get(f"lqp_qpg{l}")[:, 0]
+            QA, ub = red.get(f"lqp_qpA{l}"), red.get(f"lqp_qpub{l}")[:, 0]
+            u, v = red.get(f"lqp_u{l}")[:, 0], red.get(f"lqp_v{l}")[:, 0]
+            resid, act = kkt_residual(H, g, QA, ub, np.concatenate([u, v]), len(u))
+            assert resid < 1e-8 * max(1.0, np.linalg.norm(g)), (l, resid)
+        y = red.get("lqp_y2")[:, 0]
+        AR, GR, JCR = red.get("A_R"), red.get("G_R")[:, 0], red.get("J_CR")
+        eom = AR @ y[:n] + JCR.T @ y[n:] + GR
+        assert np.linalg.norm(eom[:6]) < 1e-8 * np.linalg.norm(GR)
+        assert relerr(red.get("lqp_torque")[:, 0], eom[6:]) < 1e-12
+        # hierarchy: the task level works in the null space of the contact level (its equality residual is unchanged)
+        B1, y1 = red.get("lqp_B1"), red.get("lqp_y1")[:, 0]
+        assert np.linalg.norm(B1 @ (y - y1)) < 1e-8
+        assert full.get("lqp_y2").shape[0] == 51 and len(y) == 36
