@@ -58,7 +58,8 @@ struct dwbc_batch {
     double k_ms[DWBC_K_COUNT] = {0};
     long long k_launches[DWBC_K_COUNT] = {0};
     // a9 reduced-dimension variant: second workspace (n = rn, m = rm) + extras
-    Work wr;
+    Work wr, wq;  // wq: scratch outputs of the base-wrench QP (CalcSingleTaskTorqueWithQP_R_NC)
+    BatchCfg *d_cfgNC = nullptr;
     ReducedX rx;
     ReducedCfg rc;
     BatchCfg cfgR;
@@ -721,6 +722,9 @@ void free_reduced_tasks(dwbc_batch *b) {
         b->wr.active[l] = nullptr;
         b->rx.JtR[l] = b->rx.LamNC[l] = nullptr;
     }
+    b->rx.fonR = b->rx.tprevNC = b->rx.NtqNC = b->rx.fqpNC = nullptr;
+    b->rx.stNC = nullptr;
+    b->d_cfgNC = nullptr;
 }
 void free_reduced(dwbc_batch *b) {
     free_reduced_tasks(b);
@@ -922,8 +926,8 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
             if (rc.cls[l] != 2) return fail(DWBC_ERR_ARG, "reduced_solve: COM / contact-chain levels must precede the non-contact levels");
         if (k == 0) return fail(DWBC_ERR_ARG, "reduced_solve: the first level cannot be a non-contact task (the reference reads ts_[-1])");
         rc.k_contact = k;
-        if (use_qp && k != c.nlevels)
-            return fail(DWBC_ERR_ARG, "reduced_solve: non-contact tasks under hqp need CalcSingleTaskTorqueWithQP_R_NC, which is not built");
+        if ((stages & DWBC_SOLVE_REDIST) && k != c.nlevels)
+            return fail(DWBC_ERR_ARG, "reduced_solve: CalcContactRedistributeR is only built for hierarchies without non-contact levels");
         if (sig != b->red_task_sig) {
             free_reduced_tasks(b);
             std::vector<void *> *L = &b->red_task_allocs;
@@ -937,6 +941,19 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
                          dev_alloc(b, &wr.active[l], B * ACTIVE_WORDS, L);
                 else
                     ok = dev_alloc(b, &b->rx.LamNC[l], B * t * t, L);
+                if (!ok) return DWBC_ERR_CUDA;
+            }
+            if (k < c.nlevels) {  // workspace of CalcSingleTaskTorqueWithQP_R_NC (one 6-dof pseudo level for hqp_kernel)
+                ReducedX &x = b->rx;
+                Work &q = b->wq;
+                q = Work();
+                std::memset(&q, 0, sizeof(q));
+                bool ok = dev_alloc(b, &x.fonR, B * 6, L) && dev_alloc(b, &x.tprevNC, B * rm, L) && dev_alloc(b, &x.NtqNC, B * rm * 6, L) &&
+                          dev_alloc(b, &x.stNC, B, L) && dev_alloc(b, &x.fqpNC, B * 6, L) && dev_alloc(b, &q.tau_task, B * rm, L) &&
+                          dev_alloc(b, &q.tau_contact, B * rm, L) && dev_alloc(b, &q.contact_qp[0], B * RMAX, L) &&
+                          dev_alloc(b, &q.active[0], B * ACTIVE_WORDS, L) && dev_alloc(b, &q.torque_h[0], B * rm, L) &&
+                          dev_alloc(b, &q.Lamt[0], B * 36, L) && dev_alloc(b, &q.Jkt[0], B * rm * 6, L) && dev_alloc(b, &q.qp_iters, B, L) &&
+                          dev_alloc(b, &b->d_cfgNC, 1, L);
                 if (!ok) return DWBC_ERR_CUDA;
             }
             b->red_task_sig = sig;
@@ -988,6 +1005,38 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
         KernelScope ks(b, DWBC_K_REDUCED, st);
         DWBC_LAUNCH(reduced_nc_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, b->wr, b->rx, b->rc, tmax,
                     ((stages & DWBC_SOLVE_HQP) ? 1 : 0) | ((stages & DWBC_SOLVE_REDIST) ? 2 : 0));
+    }
+    if ((stages & DWBC_SOLVE_HQP) && rc.k_contact < rc.nlevels) {
+        // CalcSingleTaskTorqueWithQP_R_NC: the level QP once more, on a 6-dof pseudo level whose f*, Ntorque and torque_prev were
+        // prepared by reduced_nc_kernel (zero Lambda / J_kt: the pseudo level has no torque_h of its own)
+        Work q = b->wq;
+        const Work &r = b->wr;
+        q.B = r.B; q.n = r.n; q.m = r.m; q.nb = r.nb;
+        q.pose = r.pose; q.cdof = r.cdof; q.cidx = r.cidx; q.Jbar = r.Jbar; q.PC = r.PC; q.NwJw = r.NwJw;
+        q.tau_grav = b->rx.tprevNC;
+        q.status = b->rx.stNC;
+        q.Ntq[0] = b->rx.NtqNC;
+        q.fstar[0] = b->rx.fonR;
+        q.fstar_qp[0] = b->rx.fqpNC;
+        BatchCfg cn = b->cfgR;
+        cn.nlevels = 1;
+        cn.tasks[0].custom = 1;
+        cn.tasks[0].dof = 6;
+        cn.tasks[0].link_count = 0;
+        CK(cudaMemcpyAsync(b->d_cfgNC, &cn, sizeof(BatchCfg), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        const int nvmax = 6 + RMAX;
+        HqpSmem L(rn, rm, nvmax);
+        size_t smem = sizeof(double) * L.total;
+        CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            KernelScope ks(b, DWBC_K_HQP, st);
+            DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgNC, q, 1, 0, nvmax);
+        }
+        {
+            KernelScope ks(b, DWBC_K_REDUCED, st);
+            DWBC_LAUNCH(reduced_ncqp_apply_kernel, b->B, 64, 0, st, b->w, b->rx, b->rc);
+        }
     }
     CK(cudaGetLastError());
     if (tau_grav_dev) CK(cudaMemcpyAsync(tau_grav_dev, b->w.tau_grav, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));

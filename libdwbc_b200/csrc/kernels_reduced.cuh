@@ -53,6 +53,12 @@ struct ReducedX {
     double *LamNC[MAX_LEVELS];  // [B][t*t]   Lambda_task_ of the non-contact levels
     double *tauR;     // [B][rm]  torque_task_R_
     double *tauNC;    // [B][NCMAX] torque_task_NC_
+    // CalcSingleTaskTorqueWithQP_R_NC (reference src/dwbc.cpp:3601-3756): inputs prepared by reduced_nc_kernel for hqp_kernel
+    double *fonR;     // [B][6]     force_on_nc_r_   (plays f*)
+    double *tprevNC;  // [B][rm]    torque_grav_R_ + torque_task_R_ of the COM / contact-chain levels  (plays torque_grav_)
+    double *NtqNC;    // [B][rm*6]  Null_{first_nc-1} J_base_R_kt_   (plays Ntorque)
+    int *stNC;        // [B]        status word of the base-wrench QP
+    double *fqpNC;    // [B][6]     force_on_nc_R_qp_
 };
 
 __host__ __device__ inline int reduced_dyn_smem_doubles(int rn, int nc) {
@@ -246,6 +252,8 @@ __global__ void __launch_bounds__(TEAM, 4) reduced_nc_kernel(const DevModel *__r
     double *rd = sm + Ls.vec, *tmp = rd + VL, *y1 = tmp + VL, *uu = y1 + VL, *tmp2 = uu + VL, *tauR = tmp2 + VL, *tauNC = tauR + VL;
     double *thR = tauNC + VL, *ntr = thR + VL, *z = ntr + VL, *z2 = z + VL, *lf = z2 + VL, *fsv = lf + VL, *nf = fsv + VL, *fon = nf + VL;
     const int ldr = rm | 1;
+    double *fonr = fon + 8;  // force_on_nc_r_ (6 entries in the tail of fon's slot)
+    if (tid < 6) fonr[tid] = 0.0;
     double *tau_task = w.tau_task + s * m, *tau_grav = w.tau_grav + s * m;
     for (int i = tid; i < m; i += nt) tau_task[i] = 0.0, w.tau_contact[s * m + i] = 0.0;
     const int st = wr.status[s];
@@ -336,6 +344,7 @@ __global__ void __launch_bounds__(TEAM, 4) reduced_nc_kernel(const DevModel *__r
                 if (tid < 3) v = tmp[tid];
                 else v = pose[(tid - 3) * 3] * tmp[3] + pose[(tid - 3) * 3 + 1] * tmp[4] + pose[(tid - 3) * 3 + 2] * tmp[5];
                 fon[tid] = v;
+                fonr[tid] += v;  // force_on_nc_r_ += force_on_nc_   (reference :3302; only used under hqp)
             }
             tsync();
             tgemv<false>(co, 6, Jbkt, ldr, fon, [&](int i, double v) { thR[i] = v; });
@@ -375,6 +384,7 @@ __global__ void __launch_bounds__(TEAM, 4) reduced_nc_kernel(const DevModel *__r
                     if (tid < 3) v = tmp2[tid];
                     else v = pose[(tid - 3) * 3] * tmp2[3] + pose[(tid - 3) * 3 + 1] * tmp2[4] + pose[(tid - 3) * 3 + 2] * tmp2[5];
                     fon[tid] = v;
+                    fonr[tid] -= v;  // force_on_nc_r_ -= temp_torque_[0:6]   (reference :3325)
                 }
                 tsync();
                 tgemv<false>(co, 6, Jbkt, ldr, fon, [&](int i, double v) { ntr[i] = thR[i] - v; });
@@ -395,6 +405,16 @@ __global__ void __launch_bounds__(TEAM, 4) reduced_nc_kernel(const DevModel *__r
         }
     }
     tsync();
+    if ((qp_mode & 1) && k0 < nl && k0 > 0) {
+        // inputs of CalcSingleTaskTorqueWithQP_R_NC for hqp_kernel: f* := force_on_nc_r_, Ntorque := Null_{k0-1} J_base_R_kt_,
+        // torque_prev := torque_grav_R_ + torque_task_R_ of the contact-chain levels (their sum is still in wr.tau_task)
+        const double *NulR = wr.Null[k0 - 1] + s * (long long)rm * rm;
+        double *g = rx.NtqNC + s * (long long)rm * 6;
+        tgemm<1, 1, false, false>(rm, 6, rm, NulR, rm, Jbkt, ldr, [&](int i, int j, double v) { g[i + j * rm] = v; });
+        for (int i = tid; i < rm; i += nt) rx.tprevNC[s * rm + i] = wr.tau_grav[s * rm + i] + wr.tau_task[s * rm + i];
+        if (tid < 6) rx.fonR[s * 6 + tid] = fonr[tid];
+        if (tid == 0) rx.stNC[s] = ok ? (1 | 8) : 0;
+    }
     // ---- expansion (reference :3442-3443): tau[0:co] = tau_R[0:co];  tau[co:] = J_I_nc^T tau_R[co:co+6] + N_I_nc tau_NC,
     //      N_I_nc tau_NC = tau_NC - J_I_nc^T (J_I_nc_inv_T tau_NC)
     tgemv<false>(6, nc, JT, 6, tauNC, [&](int i, double v) { z[i] = tauR[co + i] - v; });
@@ -410,6 +430,27 @@ __global__ void __launch_bounds__(TEAM, 4) reduced_nc_kernel(const DevModel *__r
     if (qp_mode & 2)  // reference src/dwbc.cpp:3765-3766
         for (int i = tid; i < c && i < rm; i += nt) w.tau_contact[s * m + i] = wr.tau_contact[s * rm + i];
     if (tid == 0) w.status[s] = 1 | (ok ? 2 : 0) | (((qp_mode & 2) && c > 6) ? (st & 4) : 0);  // reference: ret stays 0 for contact_dof_ <= 6
+}
+
+// After the base-wrench QP: torque_task_[0:co] += (J_base_R_kt_ force_on_nc_R_qp_)[0:co]  (reference src/dwbc.cpp:3420-3424); a failed
+// QP makes ReducedCalcTaskControlTorque return 0 before torque_task_ is assembled (:3399-3403): zero torque, task bit cleared.
+__global__ void reduced_ncqp_apply_kernel(Work w, ReducedX rx, ReducedCfg rc) {
+    const long long s = blockIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x, m = w.m, rm = rc.rm, co = rc.co_dof;
+    const int st = w.status[s];
+    if (!(st & 2)) return;  // already failed (or the state does not show the pattern)
+    const bool okq = (rx.stNC[s] & 2) != 0;
+    const double *Jb = rx.Jbkt + s * (long long)rm * 6, *x = rx.fqpNC + s * 6;
+    for (int i = tid; i < m; i += nt) {
+        if (!okq) {
+            w.tau_task[s * m + i] = 0.0;
+        } else if (i < co) {
+            double v = 0.0;
+            for (int k = 0; k < 6; k++) v = fma(Jb[i + k * rm], x[k], v);
+            w.tau_task[s * m + i] += v;
+        }
+    }
+    if (tid == 0 && !okq) w.status[s] = st & ~2;
 }
 
 }  // namespace dwbc

@@ -242,7 +242,8 @@ struct Robot {
     // reduced torque limit (reduced_model_dof_ entries): the reference compares torque_limit_.size() with reduced_model_dof_
     // in CalcSingleTaskTorqueWithQP_R (src/dwbc.cpp:3462-3468), i.e. the caller sets a reduced-size limit before the reduced HQP
     bool tlimR_set = false;
-    Mat tlimR, torque_contact_R, cf_redis_qp_R;
+    Mat tlimR, torque_contact_R, cf_redis_qp_R, force_on_nc_r, force_on_nc_R_qp, nc_qp_contact, nc_qpA, nc_qpub;
+    std::vector<int> nc_qp_active;
     int reduced_redistribute();
     int calc_redistribute(bool hqp);
     Mat get_contact_force(const Mat &command_torque) const;
@@ -1083,9 +1084,9 @@ int Robot::reduced_task_space() {
 
 // ReducedCalcTaskControlTorque(hqp=false), reference src/dwbc.cpp:3255-3446 (else-branch :3374-3417, expansion :3442-3443)
 int Robot::reduced_task_torque(bool hqp) {
-    if (hqp)  // CalcSingleTaskTorqueWithQP_R_NC (non-contact tasks under hqp, src/dwbc.cpp:3601-3756) is not restated
-        for (auto &t : ts)
-            if (t.noncont) return 0;
+    int first_nc = -1;
+    force_on_nc_r.set_zero(6, 1);
+    force_on_nc_R_qp.set_zero(6, 1);
     torque_task_R.set_zero(rmod, 1);
     torque_task.set_zero(m, 1);
     torque_task_NC.set_zero(nc_dof, 1);
@@ -1104,9 +1105,11 @@ int Robot::reduced_task_torque(bool hqp) {
             t.torque_nc = temp.block(vc_dof, 0, nc_dof, 1);
             t.force_on_nc.set_block(0, 0, temp.block(0, 0, 3, 1));
             t.force_on_nc.set_block(3, 0, R0 * temp.block(3, 0, 3, 1));
+            if (hqp) force_on_nc_r = force_on_nc_r + t.force_on_nc;  // reference src/dwbc.cpp:3302
             t.torque_h_R.set_block(0, 0, J_base_R_kt.top_rows(co_dof) * t.force_on_nc);
             t.torque_h_R.set_block(co_dof, 0, J_I_nc_inv_T * t.torque_nc);
             if (t.nc_h == 0) {
+                first_nc = (int)i;
                 t.torque_null_h_R = ts[i - 1].Null_R * t.torque_h_R;
                 t.torque_null_h_nc = t.torque_nc;
             } else {
@@ -1119,7 +1122,9 @@ int Robot::reduced_task_torque(bool hqp) {
                 null_torque_h_r.set_block(0, 0, t.torque_h_R.block(0, 0, co_dof, 1) - J_base_R_kt.top_rows(co_dof) * temp.block(0, 0, 6, 1));
                 null_torque_h_r.set_block(co_dof, 0, J_I_nc_inv_T * (t.torque_nc - p.J_NC.t() * null_force));
                 t.torque_null_h_R = p.Null_R * null_torque_h_r;
+                if (hqp) force_on_nc_r = force_on_nc_r - temp.block(0, 0, 6, 1);  // :3325
             }
+            if (hqp) continue;  // under hqp the non-contact levels are summed after the base-wrench QP (:3405-3418)
         } else if (hqp) {
             // reference src/dwbc.cpp:3336-3362
             t.fstar_qp.set_zero(t.dof, 1);
@@ -1136,7 +1141,30 @@ int Robot::reduced_task_torque(bool hqp) {
         torque_task_R = torque_task_R + t.torque_null_h_R;
         torque_task_NC = torque_task_NC + t.torque_null_h_nc;
     }
-    torque_task.set_block(0, 0, torque_task_R.block(0, 0, co_dof, 1));
+    Mat torque_task_R_qp(rmod, 1);
+    if (hqp && first_nc >= 0) {
+        // CalcSingleTaskTorqueWithQP_R_NC (reference src/dwbc.cpp:3601-3756): the QP of CalcSingleTaskTorqueWithQP_R with the "task"
+        // Ntorque = Null_{first_nc-1} J_base_R_kt (6 variables: a correction of the wrench the non-contact levels put on the
+        // condensed body) and f* replaced by force_on_nc_r_
+        Task ncq;
+        ncq.dof = 6;
+        ncq.Lambda = Mat::identity(6);
+        ncq.fstar = force_on_nc_r;
+        const int okq = single_task_qp_on(ncq, J_base_R_kt, rmod, ts[first_nc - 1].Null_R, torque_grav_R + torque_task_R, NwJw_R, J_CR_INV_T, P_CR, tlimR_set, tlimR);
+        nc_qpA = ncq.qpA;
+        nc_qpub = ncq.qpub;
+        if (!okq) return 0;
+        force_on_nc_R_qp = ncq.fstar_qp;
+        nc_qp_contact = ncq.contact_qp;
+        nc_qp_active = ncq.active;
+        for (size_t i = first_nc; i < ts.size(); i++)
+            if (ts[i].noncont) {
+                torque_task_R = torque_task_R + ts[i].torque_null_h_R;
+                torque_task_NC = torque_task_NC + ts[i].torque_null_h_nc;
+            }
+        torque_task_R_qp = J_base_R_kt * force_on_nc_R_qp;  // only rows 0..co_dof-1 are used (:3420)
+    }
+    torque_task.set_block(0, 0, torque_task_R.block(0, 0, co_dof, 1) + torque_task_R_qp.block(0, 0, co_dof, 1));
     torque_task.set_block(co_dof, 0, J_I_nc.t() * torque_task_R.block(co_dof, 0, 6, 1) + N_I_nc * torque_task_NC);
     return 1;
 }
@@ -1627,7 +1655,8 @@ static const Mat *find_mat(Robot *R, const std::string &name, Mat &tmp) {
             {"Lambda_CR", &R->Lambda_CR}, {"J_CR_INV_T", &R->J_CR_INV_T}, {"N_CR", &R->N_CR}, {"A_R_inv_N_CR", &R->A_R_inv_N_CR}, {"W_R", &R->W_R},
             {"W_R_inv", &R->W_R_inv}, {"V2_R", &R->V2_R}, {"NwJw_R", &R->NwJw_R}, {"P_CR", &R->P_CR}, {"torque_grav_R", &R->torque_grav_R},
             {"J_base_R_kt", &R->J_base_R_kt}, {"torque_task_R", &R->torque_task_R}, {"torque_task_NC", &R->torque_task_NC},
-            {"torque_contact_R", &R->torque_contact_R}, {"cf_redis_qp_R", &R->cf_redis_qp_R}};
+            {"torque_contact_R", &R->torque_contact_R}, {"cf_redis_qp_R", &R->cf_redis_qp_R}, {"force_on_nc_r", &R->force_on_nc_r},
+            {"force_on_nc_R_qp", &R->force_on_nc_R_qp}, {"nc_qp_contact", &R->nc_qp_contact}, {"nc_qpA", &R->nc_qpA}, {"nc_qpub", &R->nc_qpub}};
         for (auto &e : red)
             if (name == e.first) return e.second;
     }

@@ -165,3 +165,63 @@ TLIM_R = np.concatenate([np.full(12, 300.0), np.full(6, 2000.0)])
 @pytest.mark.parametrize("limited", [False, True])
 def test_emul_reduced_hqp_vs_oracle(limited):
     run_reduced_hqp(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, lambda a: a, tlimR=TLIM_R if limited else None)
+
+
+def run_reduced_hqp_nc(make_rd, D, H, scales=(0.0, 6.5, 7.0, 7.5)):
+    """Reduced HQP with non-contact levels (CalcSingleTaskTorqueWithQP_R + _R_NC, reference src/dwbc.cpp:3255-3446, 3601-3756) vs the
+    oracle on the hierarchy of reference tests/sp_test/redu_dyn_test.cpp:97-101; scales around 7 make the base-wrench QP active."""
+    from libdwbc_b200 import CONTACT_6D, SOLVE_GRAV, SOLVE_HQP, TASK_LINK_6D, TASK_LINK_POSITION, TASK_LINK_ROTATION
+
+    B = len(scales)
+    q, qd, rng = synth_states(B, 20249)
+    fs = [0.3 * rng.standard_normal((B, 3)), 0.3 * rng.standard_normal((B, 3)), 0.3 * rng.standard_normal((B, 3)), 0.3 * rng.standard_normal((B, 6))]
+    for b, sc in enumerate(scales):
+        if sc > 0:
+            fs[0][b], fs[1][b] = 0.3, 0.3
+            fs[2][b] = [25.0 * sc, 0.0, 0.0]
+            fs[3][b] = [0.0, 150.0 * sc, 0.0, 0.0, 0.0, 0.0]
+    rd = make_rd(B)
+    rd.add_contact_constraint(LEFT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+    rd.add_contact_constraint(RIGHT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+    rd.add_task_space(0, TASK_LINK_POSITION, "COM")
+    rd.add_task_space(1, TASK_LINK_ROTATION, "pelvis_link")
+    rd.add_task_space(2, TASK_LINK_ROTATION, "upperbody_link")
+    rd.add_task_space(3, TASK_LINK_6D, "L_Wrist2_Link")
+    rd.update_kinematics(D(q), D(qd))
+    rd.set_contact(D(np.ones((B, 2), dtype=np.uint8)))
+    rd.reduced_dynamics_calculate((1, 1))
+    rd.reduced_calc_contact_constraint()
+    for l, f in enumerate(fs):
+        rd.set_task_space(l, D(f))
+    tg, tt, tc, st = [H(x) for x in rd.reduced_solve(SOLVE_GRAV | SOLVE_HQP)]
+    n_active = 0
+    for b in range(B):
+        ref = orc.OracleRobot(URDF)
+        ref.add_contact(LEFT_FOOT, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+        ref.add_contact(RIGHT_FOOT, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+        ref.add_task(0, orc.TASK_LINK_POSITION, "COM")
+        ref.add_task(1, orc.TASK_LINK_ROTATION, "pelvis_link")
+        ref.add_task(2, orc.TASK_LINK_ROTATION, "upperbody_link")
+        ref.add_task(3, orc.TASK_LINK_6D, "L_Wrist2_Link")
+        ref.update_kinematics(q[b], qd[b])
+        ref.set_contact(1, 1)
+        for l, f in enumerate(fs):
+            ref.set_task(l, f[b])
+        ref.reduced_dynamics()
+        assert ref.reduced_contact_constraint() == 1
+        ref.reduced_grav()
+        assert ref.reduced_task_space() == 1
+        ok = ref.reduced_task_torque(hqp=True)
+        assert bool(st[b] & 2) == bool(ok), (b, st[b], ok)
+        if not ok:
+            assert np.all(tt[b] == 0.0)
+            continue
+        n_active += int(np.linalg.norm(ref.get("force_on_nc_R_qp")) > 1e-6)
+        want = ref.get("torque_task")[:, 0]
+        assert np.abs(tt[b] - want).max() < 1e-6 * max(1.0, np.abs(want).max()), (b, np.abs(tt[b] - want).max())
+    return n_active
+
+
+def test_emul_reduced_hqp_with_non_contact_levels():
+    n_active = run_reduced_hqp_nc(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, lambda a: a)
+    assert n_active >= 1

@@ -541,3 +541,17 @@ def test_gpu_reduced_lqp_vs_oracle():
         return T(a, torch.uint8 if a.dtype == np.uint8 else torch.float64)
 
     run_reduced_lqp(lambda B: RobotDataBatch(URDF, B, 0), D, lambda x: x.cpu().numpy(), B=12)
+
+
+def test_gpu_reduced_hqp_with_non_contact_levels():
+    """a9: reduced HQP on the full hierarchy of reference tests/sp_test/redu_dyn_test.cpp:97-101 incl. the base-wrench QP of the
+    non-contact levels (CalcSingleTaskTorqueWithQP_R_NC, src/dwbc.cpp:3601-3756) vs the oracle; at least one state has it active."""
+    from libdwbc_b200 import RobotDataBatch
+    from tests.test_emul_reduced import run_reduced_hqp_nc
+
+    def D(a):
+        a = np.ascontiguousarray(a)
+        return T(a, torch.uint8 if a.dtype == np.uint8 else torch.float64)
+
+    n_active = run_reduced_hqp_nc(lambda B: RobotDataBatch(URDF, B, 0), D, lambda x: x.cpu().numpy(), scales=(0.0, 0.0, 6.5, 6.8, 7.0, 7.2, 7.5, 1.0))
+    assert n_active >= 1

@@ -146,3 +146,51 @@ def test_reduced_hqp_with_reduced_torque_limit_respects_it():
     assert rok == 1
     tr = red.get("torque_grav_R")[:, 0] + red.get("torque_task_R")[:, 0]
     assert np.abs(tr).max() <= 300.0 + 1e-6
+
+
+def test_reduced_hqp_with_non_contact_levels():
+    """CalcSingleTaskTorqueWithQP_R_NC (reference src/dwbc.cpp:3601-3756), no golden: (1) when no row is active every QP returns
+    zero and the hqp result equals the closed-form reduced result (which equals the full model, see above); (2) on a
+    friction-saturating state the base-wrench QP is active, its answer moves only the contact-chain torques through
+    J_base_R_kt, and it satisfies every row of the assembled QP with at least one of them active."""
+    q, qd, rng = synth_states(4, 20249)
+    n_active = 0
+    for b in range(4):
+        fs = [0.3 * rng.standard_normal(3), 0.3 * rng.standard_normal(3), 0.3 * rng.standard_normal(3), 0.3 * rng.standard_normal(6)]
+        if b >= 1:
+            # violent upper-body roll / lateral hand accelerations: the reaction of the non-contact chain on the base breaks the
+            # ZMP / friction rows for scales around 7 (the COM-level null space hides most of it; above ~8 the QP is infeasible)
+            sc = (0.0, 6.5, 7.0, 7.5)[b]
+            fs = [0.3 * np.ones(3), 0.3 * np.ones(3), np.array([25.0 * sc, 0.0, 0.0]), np.array([0.0, 150.0 * sc, 0.0, 0.0, 0.0, 0.0])]
+        res = []
+        for hqp in (False, True):
+            ref = orc.OracleRobot(URDF)
+            ref.add_contact(LEFT_FOOT, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+            ref.add_contact(RIGHT_FOOT, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+            reduced_tasks(ref)
+            ref.update_kinematics(q[b], qd[b])
+            ref.set_contact(1, 1)
+            for l, f in enumerate(fs):
+                ref.set_task(l, f)
+            ref.reduced_dynamics()
+            assert ref.reduced_contact_constraint() == 1
+            ref.reduced_grav()
+            assert ref.reduced_task_space() == 1
+            ok = ref.reduced_task_torque(hqp=hqp)
+            assert ok == 1 or (hqp and b >= 1)
+            res.append((ref, ok))
+        if not res[1][1]:
+            continue  # infeasible base-wrench QP: the reference returns 0 as well
+        closed, hq = res[0][0], res[1][0]
+        x6 = hq.get("force_on_nc_R_qp")[:, 0]
+        dt = hq.get("torque_task")[:, 0] - closed.get("torque_task")[:, 0]
+        if np.linalg.norm(x6) < 1e-9 and all(np.linalg.norm(hq.get(f"f_star_qp{l}")) < 1e-9 for l in range(2)):
+            assert np.abs(dt).max() < 1e-8 * max(1.0, np.abs(closed.get("torque_task")).max())
+        else:
+            n_active += 1
+            assert np.abs(dt[12:]).max() < 1e-9  # non-contact joints are untouched by the QPs
+            # the answer satisfies every row of the QP the reference assembles, with at least one row active
+            x = np.concatenate([x6, hq.get("nc_qp_contact")[:, 0]])
+            slack = hq.get("nc_qpub")[:, 0] - hq.get("nc_qpA") @ x
+            assert slack.min() > -1e-7 * max(1.0, np.abs(hq.get("nc_qpub")).max()) and (slack < 1e-6).sum() >= 1
+    assert n_active >= 1
