@@ -926,8 +926,6 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
             if (rc.cls[l] != 2) return fail(DWBC_ERR_ARG, "reduced_solve: COM / contact-chain levels must precede the non-contact levels");
         if (k == 0) return fail(DWBC_ERR_ARG, "reduced_solve: the first level cannot be a non-contact task (the reference reads ts_[-1])");
         rc.k_contact = k;
-        if ((stages & DWBC_SOLVE_REDIST) && k != c.nlevels)
-            return fail(DWBC_ERR_ARG, "reduced_solve: CalcContactRedistributeR is only built for hierarchies without non-contact levels");
         if (sig != b->red_task_sig) {
             free_reduced_tasks(b);
             std::vector<void *> *L = &b->red_task_allocs;
@@ -993,9 +991,12 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
             HqpSmem L(rn, rm, nvmax);
             size_t smem = sizeof(double) * L.total;
             CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            KernelScope ks(b, DWBC_K_HQP, st);
-            DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, b->wr, (stages & DWBC_SOLVE_HQP) ? 1 : 0,
-                        (stages & DWBC_SOLVE_REDIST) ? 2 : 0, nvmax);
+            // with non-contact levels the redistribution needs torque_task_R_ after their sums: it runs after reduced_nc_kernel
+            const int redist_now = ((stages & DWBC_SOLVE_REDIST) && k == c.nlevels) ? 2 : 0;
+            if ((stages & DWBC_SOLVE_HQP) || redist_now) {
+                KernelScope ks(b, DWBC_K_HQP, st);
+                DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, b->wr, (stages & DWBC_SOLVE_HQP) ? 1 : 0, redist_now, nvmax);
+            }
         }
     }
     {
@@ -1004,7 +1005,7 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
         CK(cudaFuncSetAttribute(reduced_nc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelScope ks(b, DWBC_K_REDUCED, st);
         DWBC_LAUNCH(reduced_nc_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, b->wr, b->rx, b->rc, tmax,
-                    ((stages & DWBC_SOLVE_HQP) ? 1 : 0) | ((stages & DWBC_SOLVE_REDIST) ? 2 : 0));
+                    ((stages & DWBC_SOLVE_HQP) ? 1 : 0) | (((stages & DWBC_SOLVE_REDIST) && rc.k_contact == rc.nlevels) ? 2 : 0));
     }
     if ((stages & DWBC_SOLVE_HQP) && rc.k_contact < rc.nlevels) {
         // CalcSingleTaskTorqueWithQP_R_NC: the level QP once more, on a 6-dof pseudo level whose f*, Ntorque and torque_prev were
@@ -1036,6 +1037,23 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
         {
             KernelScope ks(b, DWBC_K_REDUCED, st);
             DWBC_LAUNCH(reduced_ncqp_apply_kernel, b->B, 64, 0, st, b->w, b->rx, b->rc);
+        }
+    }
+    if ((stages & DWBC_SOLVE_REDIST) && rc.k_contact < rc.nlevels) {
+        // CalcContactRedistributeR(torque_grav_R_ + torque_task_R_) with the final torque_task_R_ (reference src/dwbc.cpp:3758-3770)
+        Work d = b->wr;
+        d.tau_task = b->rx.tauR;
+        const int nvmax = RMAX > 0 ? RMAX : 1;
+        HqpSmem L(rn, rm, nvmax);
+        size_t smem = sizeof(double) * L.total;
+        CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            KernelScope ks(b, DWBC_K_HQP, st);
+            DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, d, 0, 2, nvmax);
+        }
+        {
+            KernelScope ks(b, DWBC_K_REDUCED, st);
+            DWBC_LAUNCH(reduced_redist_apply_kernel, b->B, 64, 0, st, b->w, b->wr, b->rc);
         }
     }
     CK(cudaGetLastError());

@@ -453,4 +453,16 @@ __global__ void reduced_ncqp_apply_kernel(Work w, ReducedX rx, ReducedCfg rc) {
     if (tid == 0 && !okq) w.status[s] = st & ~2;
 }
 
+// ReducedCalcContactRedistribute after a hierarchy with non-contact levels: torque_contact_[0:contact_dof_] = torque_contact_R_[0:contact_dof_]
+// (reference src/dwbc.cpp:3765-3766) and the redistribution bit of the status word.
+__global__ void reduced_redist_apply_kernel(Work w, Work wr, ReducedCfg rc) {
+    const long long s = blockIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x, m = w.m, rm = rc.rm;
+    const int st = w.status[s];
+    if (!(st & 1)) return;
+    const int c = w.cdof[s];
+    for (int i = tid; i < m; i += nt) w.tau_contact[s * m + i] = (i < c && i < rm) ? wr.tau_contact[s * rm + i] : 0.0;
+    if (tid == 0 && c > 6) w.status[s] = st | (wr.status[s] & 4);
+}
+
 }  // namespace dwbc

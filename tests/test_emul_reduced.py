@@ -170,7 +170,7 @@ def test_emul_reduced_hqp_vs_oracle(limited):
 def run_reduced_hqp_nc(make_rd, D, H, scales=(0.0, 6.5, 7.0, 7.5)):
     """Reduced HQP with non-contact levels (CalcSingleTaskTorqueWithQP_R + _R_NC, reference src/dwbc.cpp:3255-3446, 3601-3756) vs the
     oracle on the hierarchy of reference tests/sp_test/redu_dyn_test.cpp:97-101; scales around 7 make the base-wrench QP active."""
-    from libdwbc_b200 import CONTACT_6D, SOLVE_GRAV, SOLVE_HQP, TASK_LINK_6D, TASK_LINK_POSITION, TASK_LINK_ROTATION
+    from libdwbc_b200 import CONTACT_6D, SOLVE_GRAV, SOLVE_HQP, SOLVE_REDIST, TASK_LINK_6D, TASK_LINK_POSITION, TASK_LINK_ROTATION
 
     B = len(scales)
     q, qd, rng = synth_states(B, 20249)
@@ -193,7 +193,7 @@ def run_reduced_hqp_nc(make_rd, D, H, scales=(0.0, 6.5, 7.0, 7.5)):
     rd.reduced_calc_contact_constraint()
     for l, f in enumerate(fs):
         rd.set_task_space(l, D(f))
-    tg, tt, tc, st = [H(x) for x in rd.reduced_solve(SOLVE_GRAV | SOLVE_HQP)]
+    tg, tt, tc, st = [H(x) for x in rd.reduced_solve(SOLVE_GRAV | SOLVE_HQP | SOLVE_REDIST)]
     n_active = 0
     for b in range(B):
         ref = orc.OracleRobot(URDF)
@@ -219,6 +219,12 @@ def run_reduced_hqp_nc(make_rd, D, H, scales=(0.0, 6.5, 7.0, 7.5)):
         n_active += int(np.linalg.norm(ref.get("force_on_nc_R_qp")) > 1e-6)
         want = ref.get("torque_task")[:, 0]
         assert np.abs(tt[b] - want).max() < 1e-6 * max(1.0, np.abs(want).max()), (b, np.abs(tt[b] - want).max())
+        # ReducedCalcContactRedistribute on torque_grav_R_ + the final torque_task_R_ (reference src/dwbc.cpp:3758-3770)
+        ok2 = ref.reduced_redistribute()
+        assert bool(st[b] & 4) == bool(ok2), (b, st[b], ok2)
+        if ok2:
+            tcr = ref.get("torque_contact")[:, 0]
+            assert np.abs(tc[b] - tcr).max() < 1e-6 * max(1.0, np.abs(tcr).max()), b
     return n_active
 
 
