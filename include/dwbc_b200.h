@@ -189,8 +189,8 @@ int dwbc_batch_reduced_calc_contact_constraint(dwbc_batch_t *b, void *stream);
  * CalcContactRedistributeR)   reference src/dwbc.cpp:3144-3599, 3758-3770, 4777-4925.  Outputs as dwbc_batch_solve (full
  * 33-joint torques; torque_contact_[0:contact_dof_] = torque_contact_R_[0:contact_dof_]).
  * DWBC_SOLVE_HQP / DWBC_SOLVE_REDIST cover every hierarchy the closed form covers (non-contact levels go through
- * CalcSingleTaskTorqueWithQP_R_NC, src/dwbc.cpp:3601-3756); the analytic branch of CalcContactRedistributeR
- * (DWBC_SOLVE_REDIST_ANALYTIC) is not built (DWBC_ERR_ARG). */
+ * CalcSingleTaskTorqueWithQP_R_NC, src/dwbc.cpp:3601-3756); DWBC_SOLVE_REDIST_ANALYTIC is the analytic branch of
+ * CalcContactRedistributeR (:4938-4990). */
 int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *tau_task_dev, double *tau_contact_dev,
                              int32_t *status_dev, void *stream);
 /* Torque limit of the reduced QPs: reduced_model_dof_ entries (contact-chain joints, then the 6 coordinates of the condensed

@@ -859,10 +859,10 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
                              void *stream) {
     if (!b) return fail(DWBC_ERR_ARG, "reduced_solve: null handle");
     if (!b->have_red_cc) return fail(DWBC_ERR_ORDER, "reduced_solve: call reduced_calc_contact_constraint first");
-    if (stages & DWBC_SOLVE_REDIST_ANALYTIC)
-        return fail(DWBC_ERR_ARG, "reduced_solve: the analytic branch of CalcContactRedistributeR is not built");
+    if ((stages & DWBC_SOLVE_REDIST_ANALYTIC) && (stages & DWBC_SOLVE_REDIST)) stages &= ~DWBC_SOLVE_REDIST_ANALYTIC;  // as dwbc_batch_solve
     if (stages & DWBC_SOLVE_HQP) stages |= DWBC_SOLVE_TASK;
-    if ((stages & DWBC_SOLVE_REDIST) && !(stages & DWBC_SOLVE_TASK)) return fail(DWBC_ERR_ARG, "reduced_solve: DWBC_SOLVE_REDIST needs DWBC_SOLVE_TASK");
+    if ((stages & (DWBC_SOLVE_REDIST | DWBC_SOLVE_REDIST_ANALYTIC)) && !(stages & DWBC_SOLVE_TASK))
+        return fail(DWBC_ERR_ARG, "reduced_solve: the contact redistribution needs DWBC_SOLVE_TASK");
     const bool use_qp = (stages & (DWBC_SOLVE_HQP | DWBC_SOLVE_REDIST)) != 0;
     if (use_qp && b->red_tlim_set && (int)b->red_tlim.size() != b->rc.rm)
         return fail(DWBC_ERR_ARG, "reduced_solve: task qp torque limit size is not matched with model size (reduced_model_dof_)");
@@ -1037,6 +1037,23 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
         {
             KernelScope ks(b, DWBC_K_REDUCED, st);
             DWBC_LAUNCH(reduced_ncqp_apply_kernel, b->B, 64, 0, st, b->w, b->rx, b->rc);
+        }
+    }
+    if (stages & DWBC_SOLVE_REDIST_ANALYTIC) {
+        // analytic branch of CalcContactRedistributeR (reference src/dwbc.cpp:4938-4990): the closed form of
+        // CalcContactRedistribute(hqp = false) on J_CR_INV_T, P_CR, V2_R with torque_input = torque_grav_R_ + torque_task_R_
+        Work d = b->wr;
+        d.tau_task = b->rx.tauR;
+        CK(cudaMemsetAsync(d.tau_contact, 0, sizeof(double) * B * rm, st));
+        const int wpb = WARPS_PER_BLOCK, grid = grid_for(b->B, wpb);
+        const size_t smem = sizeof(double) * wpb * (MAXB + CMAX + 6 * 7 + 8);
+        {
+            KernelScope ks(b, DWBC_K_POST, st);
+            DWBC_LAUNCH(redistribute_analytic_kernel, grid, wpb * 32, smem, st, b->d_model, b->d_cfgR, d);
+        }
+        {
+            KernelScope ks(b, DWBC_K_REDUCED, st);
+            DWBC_LAUNCH(reduced_redist_apply_kernel, b->B, 64, 0, st, b->w, b->wr, b->rc);
         }
     }
     if ((stages & DWBC_SOLVE_REDIST) && rc.k_contact < rc.nlevels) {

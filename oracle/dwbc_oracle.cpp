@@ -244,7 +244,8 @@ struct Robot {
     bool tlimR_set = false;
     Mat tlimR, torque_contact_R, cf_redis_qp_R, force_on_nc_r, force_on_nc_R_qp, nc_qp_contact, nc_qpA, nc_qpub;
     std::vector<int> nc_qp_active;
-    int reduced_redistribute();
+    int reduced_redistribute(bool hqp = true);
+    Mat redistribute_analytic(const Mat &JCINVT, const Mat &PC, const Mat &V2m, const Mat &tin, int msize);
     int calc_redistribute(bool hqp);
     Mat get_contact_force(const Mat &command_torque) const;
     V3 get_zmp(const Mat &contact_force, std::vector<V3> *per_contact = nullptr) const;
@@ -744,6 +745,34 @@ V3 Robot::get_zmp(const Mat &cf, std::vector<V3> *per_contact) const {
 // reference src/dwbc.cpp:1377-1568 (QP branch).  The reference sizes the QP with
 // contact_link_num_*contact_constraint_size rows (quirk 5): the extra rows are 0*x in [0,0]
 // and are dropped here.
+// The closed form shared by CalcContactRedistribute(hqp = false) (reference src/dwbc.cpp:1570-1619) and the analytic branch of
+// CalcContactRedistributeR (:4940-4985): ContactRedistributetwomod on the yaw-aligned contact forces, then the torque that
+// realises the change of the second foot's wrench through the internal-force space V2.
+Mat Robot::redistribute_analytic(const Mat &JCINVT, const Mat &PC, const Mat &V2m, const Mat &tin, int msize) {
+    Mat cf = JCINVT.right_cols(msize) * tin - PC;  // ContactForce_
+    const double ang = -eigen_euler_zyx(Rw[0])[2];  // -link_[0].rpy(2), rpy = rotm.eulerAngles(2, 1, 0) (src/link.cpp:81)
+    M3 Rz = eye3();  // rotateWithZ, reference src/math.cpp:55-74
+    Rz.m[0][0] = std::cos(ang); Rz.m[0][1] = -std::sin(ang);
+    Rz.m[1][0] = std::sin(ang); Rz.m[1][1] = std::cos(ang);
+    V3 P1 = mul(Rz, cc[0].xc - com_pos), P2 = mul(Rz, cc[1].xc - com_pos);
+    double F12[12], FR[12], res6[6], eta = 0.95;
+    for (int k = 0; k < 4; k++) {
+        V3 f = mul(Rz, V3{cf[3 * k], cf[3 * k + 1], cf[3 * k + 2]});
+        F12[3 * k] = f.x; F12[3 * k + 1] = f.y; F12[3 * k + 2] = f.z;
+    }
+    contact_redistribute_two(0.99, 0.26, 0.1, 1.0, 0.9, 0.9, P1, P2, F12, res6, FR, eta);
+    Mat des(6, 1);
+    M3 Rzt = tr(Rz);
+    for (int k = 2; k < 4; k++) {
+        V3 f = mul(Rzt, V3{FR[3 * k], FR[3 * k + 1], FR[3 * k + 2]});
+        des[3 * (k - 2)] = -cf[3 * k] + f.x;
+        des[3 * (k - 2) + 1] = -cf[3 * k + 1] + f.y;
+        des[3 * (k - 2) + 2] = -cf[3 * k + 2] + f.z;
+    }
+    redis_eta = eta;
+    return V2m.t() * lu_inverse(JCINVT.right_cols(msize).bottom_rows(6) * V2m.t()) * des;
+}
+
 int Robot::calc_redistribute(bool hqp) {
     redis_status = 0;
     redis_active.clear();
@@ -755,28 +784,7 @@ int Robot::calc_redistribute(bool hqp) {
             torque_contact.set_zero(m, 1);
             return 0;
         }
-        Mat cf = J_C_INV_T.right_cols(m) * tin - P_C;  // ContactForce_
-        const double ang = -eigen_euler_zyx(Rw[0])[2];  // -link_[0].rpy(2), rpy = rotm.eulerAngles(2, 1, 0) (src/link.cpp:81)
-        M3 Rz = eye3();  // rotateWithZ, reference src/math.cpp:55-74
-        Rz.m[0][0] = std::cos(ang); Rz.m[0][1] = -std::sin(ang);
-        Rz.m[1][0] = std::sin(ang); Rz.m[1][1] = std::cos(ang);
-        V3 P1 = mul(Rz, cc[0].xc - com_pos), P2 = mul(Rz, cc[1].xc - com_pos);
-        double F12[12], FR[12], res6[6], eta = 0.95;
-        for (int k = 0; k < 4; k++) {
-            V3 f = mul(Rz, V3{cf[3 * k], cf[3 * k + 1], cf[3 * k + 2]});
-            F12[3 * k] = f.x; F12[3 * k + 1] = f.y; F12[3 * k + 2] = f.z;
-        }
-        contact_redistribute_two(0.99, 0.26, 0.1, 1.0, 0.9, 0.9, P1, P2, F12, res6, FR, eta);
-        Mat des(6, 1);
-        M3 Rzt = tr(Rz);
-        for (int k = 2; k < 4; k++) {
-            V3 f = mul(Rzt, V3{FR[3 * k], FR[3 * k + 1], FR[3 * k + 2]});
-            des[3 * (k - 2)] = -cf[3 * k] + f.x;
-            des[3 * (k - 2) + 1] = -cf[3 * k + 1] + f.y;
-            des[3 * (k - 2) + 2] = -cf[3 * k + 2] + f.z;
-        }
-        redis_eta = eta;
-        torque_contact = V2.t() * lu_inverse(J_C_INV_T.right_cols(m).bottom_rows(6) * V2.t()) * des;
+        torque_contact = redistribute_analytic(J_C_INV_T, P_C, V2, tin, m);
         redis_status = 1;
         return 1;
     }
@@ -1172,12 +1180,18 @@ int Robot::reduced_task_torque(bool hqp) {
 // ReducedCalcContactRedistribute(hqp = true) -> CalcContactRedistributeR, reference src/dwbc.cpp:3758-3770, 4762-4960: the QP of
 // CalcContactRedistribute on the reduced matrices with torque_input = torque_grav_R_ + torque_task_R_; then
 // torque_contact_[0:contact_dof_] = torque_contact_R_[0:contact_dof_].
-int Robot::reduced_redistribute() {
+int Robot::reduced_redistribute(bool hqp) {
     torque_contact.set_zero(m, 1);
     torque_contact_R.set_zero(rmod, 1);
     const int r = contact_dof - 6;
     if (r <= 0) return 0;  // reference: ret stays 0 when contact_dof_ <= 6
     Mat tin = torque_grav_R + torque_task_R;
+    if (!hqp) {  // analytic branch, reference src/dwbc.cpp:4938-4990
+        if (co_dof != 12) return 0;
+        torque_contact_R = redistribute_analytic(J_CR_INV_T, P_CR, V2_R, tin, rmod);
+        for (int i = 0; i < contact_dof; i++) torque_contact[i] = torque_contact_R[i];
+        return 1;
+    }
     Mat A_const, A_rot;
     int csize;
     contact_const(A_const, A_rot, csize);
@@ -1586,7 +1600,7 @@ int orc_reduced_contact_constraint(void *h) { return ((Robot *)h)->reduced_conta
 void orc_reduced_grav(void *h) { ((Robot *)h)->reduced_grav(); }
 int orc_reduced_task_space(void *h) { return ((Robot *)h)->reduced_task_space(); }
 int orc_reduced_task_torque(void *h, int hqp) { return ((Robot *)h)->reduced_task_torque(hqp != 0); }
-int orc_reduced_redistribute(void *h) { return ((Robot *)h)->reduced_redistribute(); }
+int orc_reduced_redistribute(void *h, int hqp) { return ((Robot *)h)->reduced_redistribute(hqp != 0); }
 void orc_set_reduced_torque_limit(void *h, const double *tlim, int count) {
     Robot *R = (Robot *)h;
     R->tlimR_set = true;

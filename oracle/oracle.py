@@ -71,7 +71,7 @@ def lib():
         for f in ("orc_reduced_dynamics", "orc_reduced_contact_constraint", "orc_reduced_grav", "orc_reduced_task_space"):
             getattr(L, f).argtypes = [C.c_void_p]
         L.orc_reduced_task_torque.argtypes = [C.c_void_p, C.c_int]
-        L.orc_reduced_redistribute.argtypes = [C.c_void_p]
+        L.orc_reduced_redistribute.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_reduced_torque_limit.argtypes = [C.c_void_p, _dp, C.c_int]
         L.orc_reduced_dims.argtypes = [C.c_void_p, _ip]
         for f in ("orc_configure_lqp", "orc_configure_lqp_r", "orc_calc_lqp", "orc_lqp_levels", "orc_update_task_space"):
@@ -191,9 +191,9 @@ class OracleRobot:
     def reduced_task_torque(self, hqp=False):
         return lib().orc_reduced_task_torque(self.h, 1 if hqp else 0)
 
-    def reduced_redistribute(self):
-        """ReducedCalcContactRedistribute(hqp=true), reference src/dwbc.cpp:3758-3770"""
-        return lib().orc_reduced_redistribute(self.h)
+    def reduced_redistribute(self, hqp=True):
+        """ReducedCalcContactRedistribute(hqp), reference src/dwbc.cpp:3758-3770 (hqp=False: the analytic two-foot branch)"""
+        return lib().orc_reduced_redistribute(self.h, 1 if hqp else 0)
 
     def set_reduced_torque_limit(self, tlim):
         """torque limit of reduced_model_dof_ entries, as CalcSingleTaskTorqueWithQP_R expects (reference src/dwbc.cpp:3462-3468)"""

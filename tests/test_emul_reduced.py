@@ -231,3 +231,25 @@ def run_reduced_hqp_nc(make_rd, D, H, scales=(0.0, 6.5, 7.0, 7.5)):
 def test_emul_reduced_hqp_with_non_contact_levels():
     n_active = run_reduced_hqp_nc(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, lambda a: a)
     assert n_active >= 1
+
+
+def test_emul_reduced_analytic_redistribution():
+    """analytic branch of CalcContactRedistributeR (reference src/dwbc.cpp:4938-4990) on the reduced workspace vs the oracle"""
+    from libdwbc_b200 import SOLVE_REDIST_ANALYTIC
+
+    B = 3
+    q, qd, rng = synth_states(B, 20250)
+    fs = [0.5 * rng.standard_normal((B, 3)), rng.standard_normal((B, 3)), rng.standard_normal((B, 3)), rng.standard_normal((B, 6))]
+    rd = reduced_product(EmulBackend(), q, qd, (1, 1), fs, B)
+    rd.update_kinematics(np.ascontiguousarray(q), np.ascontiguousarray(qd))
+    rd.set_contact(np.ones((B, 2), dtype=np.uint8))
+    rd.reduced_dynamics_calculate((1, 1))
+    rd.reduced_calc_contact_constraint()
+    for l, f in enumerate(fs):
+        rd.set_task_space(l, np.ascontiguousarray(f))
+    tg, tt, tc, st = rd.reduced_solve(SOLVE_GRAV | SOLVE_TASK | SOLVE_REDIST_ANALYTIC)
+    for b in range(B):
+        full, red = full_and_reduced(q[b], qd[b], (1, 1), [f[b] for f in fs])
+        assert red.reduced_redistribute(hqp=False) == 1 and (st[b] & 7) == 7
+        tcr = red.get("torque_contact")[:, 0]
+        assert np.abs(tc[b] - tcr).max() < 1e-8 * max(1.0, np.abs(tcr).max()), b

@@ -194,3 +194,16 @@ def test_reduced_hqp_with_non_contact_levels():
             slack = hq.get("nc_qpub")[:, 0] - hq.get("nc_qpA") @ x
             assert slack.min() > -1e-7 * max(1.0, np.abs(hq.get("nc_qpub")).max()) and (slack < 1e-6).sum() >= 1
     assert n_active >= 1
+
+
+def test_reduced_analytic_redistribution_equals_full():
+    """Analytic branch of CalcContactRedistributeR (reference src/dwbc.cpp:4938-4990), no golden: the reduced model is exact for
+    the contact wrench, so the leg part of the redistribution torque equals the full-model CalcContactRedistribute(hqp=false)."""
+    q, qd, rng = synth_states(3, 20250)
+    for b in range(3):
+        fs = [0.5 * rng.standard_normal(3), rng.standard_normal(3), rng.standard_normal(3), rng.standard_normal(6)]
+        full, red = full_and_reduced(q[b], qd[b], (1, 1), fs)
+        assert full.calc_redistribute(hqp=False) == 1 and red.reduced_redistribute(hqp=False) == 1
+        tcf, tcr = full.get("torque_contact")[:, 0], red.get("torque_contact")[:, 0]
+        assert np.abs(tcr[:12] - tcf[:12]).max() < 1e-7 * max(1.0, np.abs(tcf).max())
+        assert np.all(tcr[12:] == 0.0)
