@@ -51,6 +51,7 @@ __device__ __forceinline__ double team_spd_inverse(int n, double *L, int ld, dou
     const int nt = t_n();
     const int slots = ((n + 1) >> 1) * (n + 1);  // ownership slots of tchol_lower
     if (slots <= 2 * nt) return team_spd_inverse_t<2>(n, L, ld, Xi, ldx, rd);
+    if (slots <= 5 * nt) return team_spd_inverse_t<5>(n, L, ld, Xi, ldx, rd);  // n <= 33 with 128 threads
     if (slots <= 7 * nt) return team_spd_inverse_t<7>(n, L, ld, Xi, ldx, rd);
     if constexpr (TEAM >= 128) {
         return team_spd_inverse_t<12>(n, L, ld, Xi, ldx, rd);  // n <= 54

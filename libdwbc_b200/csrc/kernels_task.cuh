@@ -22,7 +22,7 @@ namespace dwbc {
 // Shared-memory arena of one state.  The level-independent quantities of ALL hierarchy levels are stacked (rows of level l
 // start at row r_l = sum of the dofs above it), so that every phase between two CTA barriers works on the whole hierarchy.
 struct TaskSmem {
-    int tsum, ldt, ldm, X1, X2, T, S1, S2, vec, total;
+    int tsum, ldt, ldm, X1, X2, T, S1, S2, vec, total, pstage;
     __host__ __device__ static int sblock(const TaskCfg *tasks, int nl) {
         int o = 0;
         for (int l = 0; l < nl; l++) o += (tasks[l].dof | 1) * tasks[l].dof;
@@ -39,10 +39,11 @@ struct TaskSmem {
         x1 = x1 > sb ? x1 : sb;
         int o = 0;
         X1 = o; o += x1;   // J_task (all levels) -> Q -> scratch of the second inverses -> J_kt
-        X2 = o; o += x2;   // scratch of the first inverses -> W^+ Q^T -> J_kt Lambda_t -> Ntorque
         T = o; o += ldt * n;   // J (A^{-1} N_c), all levels
+        X2 = o; o += x2;   // scratch of the first inverses -> W^+ Q^T -> J_kt Lambda_t -> Ntorque
         S1 = o; o += sb;   // Lambda_t blocks
         S2 = o; o += sb;   // (Q W^+ Q^T)^{-1} blocks
+        pstage = (x2 + 2 * sb >= n * n) ? X2 : -1;  // X2..S2 are free until T exists: room to stage A^{-1}N_c for the first product
         vec = o; o += 2 * (tsum + 1) + (m + 1) + MAX_TASK_DOF + 4;  // f*, condition numbers, closed-form torque, 1/diag of a team Cholesky
         total = o;
     }
@@ -159,10 +160,18 @@ __global__ void __launch_bounds__(TEAM, 6) task_space_kernel(const DevModel *__r
         build_task_jacobian(md, cfg, w, s, l, Js + r0[l], ldt);
         for (int i = tid; i < td[l]; i += nt) fs[r0[l] + i] = w.fstar[l][s * td[l] + i];
     }
+    // A^{-1}N_c is read by every warp of the first product: one coalesced copy into shared memory instead of 8-byte fragment
+    // loads from L2 in the k loop (long_scoreboard was this kernel's top stall)
+    const double *Pop = P;
+    if (L.pstage >= 0) {
+        double *Ps = sm + L.pstage;
+        for (int e = tid; e < n * n; e += nt) Ps[e] = P[e];
+        Pop = Ps;
+    }
     tsync();
     for (int l = 0; l < nl; l++) tcopy(td[l], n, Js + r0[l], ldt, w.Jt[l] + s * (long long)td[l] * n, td[l]);
     // ---- phase 1: T = J (A^{-1} N_c)   (tsum x n) ----
-    tgemm_mma<2, false, false>(L.tsum, n, n, Js, ldt, P, n, [&](int i, int j, double v) { T[i + j * ldt] = v; });
+    tgemm_mma<2, false, false>(L.tsum, n, n, Js, ldt, Pop, n, [&](int i, int j, double v) { T[i + j * ldt] = v; });
     tsync();
     // ---- phase 2: Lambda_t^{-1} = T_l J_l^T   (t x t per level) ----
     for (int l = 0; l < nl; l++) {
