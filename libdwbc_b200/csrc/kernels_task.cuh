@@ -42,8 +42,13 @@ struct TaskSmem {
         T = o; o += ldt * n;   // J (A^{-1} N_c), all levels
         X2 = o; o += x2;   // scratch of the first inverses -> W^+ Q^T -> J_kt Lambda_t -> Ntorque
         S1 = o; o += sb;   // Lambda_t blocks
-        S2 = o; o += sb;   // (Q W^+ Q^T)^{-1} blocks
-        pstage = (x2 + 2 * sb >= n * n) ? X2 : -1;  // X2..S2 are free until T exists: room to stage A^{-1}N_c for the first product
+        int cs = 0, rr = 0;  // the null-space recursion keeps T[0:r_l, 6:] JL_l ((r_l | 1) x t_l) where the S2 blocks were
+        for (int l = 0; l < nl; l++) {
+            cs = (rr | 1) * tasks[l].dof > cs ? (rr | 1) * tasks[l].dof : cs;
+            rr += tasks[l].dof;
+        }
+        S2 = o; o += sb > cs ? sb : cs;   // (Q W^+ Q^T)^{-1} blocks
+        pstage = (S2 + sb - X2 >= n * n) ? X2 : -1;  // X2..S2 are free until T exists: room to stage A^{-1}N_c for the first product
         vec = o; o += 2 * (tsum + 1) + (m + 1) + MAX_TASK_DOF + 4;  // f*, condition numbers, closed-form torque, 1/diag of a team Cholesky
         total = o;
     }
@@ -249,29 +254,32 @@ __global__ void __launch_bounds__(TEAM, 6) task_space_kernel(const DevModel *__r
     // torque_h = JL f*  (closed-form branch; the HQP kernel overwrites it with f* + f*_qp)
     for (int l = 0; l < nl; l++)
         tgemv<false>(m, td[l], JL + r0[l] * ldm, ldm, fs + r0[l], [&](int i, double v) { w.torque_h[l][s * m + i] = v; });
-    // ---- sequential part: Ntorque_l = Null_{l-1} JL_l;  Null_l = Null_{l-1} - Ntorque_l T_l[:, 6:] ----
-    double *Ntm = X1;  // J_kt is stored
+    // ---- sequential part, without ever reading Null back: with Null_{l-1} = I - sum_{k<l} Ntorque_k T_k[:,6:],
+    //   Ntorque_l = Null_{l-1} JL_l = JL_l - Nta[:, 0:r_l] (T[0:r_l, 6:] JL_l)      (Nta: Ntorque of the levels above, stacked)
+    //   Null_l    = I - Nta[:, 0:r_{l+1}] T[0:r_{l+1}, 6:]
+    // Every operand is in shared memory and the inner dimensions are the (small) task dofs instead of m. ----
+    double *Nta = X1;  // J_kt is stored
+    double *Cs = S2;   // (Q W^+ Q^T)^{-1} is dead
     for (int l = 0; l < nl; l++) {
-        const int t = td[l];
-        const double *Nt = JL + r0[l] * ldm;
-        if (l > 0) {
-            const double *Nprev = w.Null[l - 1] + s * (long long)m * m;
-            tsync();  // X1 of the previous level is dead, Null_{l-1} is visible (written by this CTA before the barrier)
-            tgemm_mma<2, false, false>(m, t, m, Nprev, m, JL + r0[l] * ldm, ldm, [&](int i, int j, double v) { Ntm[i + j * ldm] = v; });
+        const int t = td[l], rl = r0[l];
+        const double *Nt = JL + rl * ldm;
+        if (l == 0) {
+            tcopy(m, t, JL, ldm, Nta, ldm);
+        } else {
+            const int ldc = rl | 1;
+            tgemm_mma<1, false, false>(rl, t, m, T + 6 * ldt, ldt, JL + rl * ldm, ldm, [&](int i, int j, double v) { Cs[i + j * ldc] = v; });
             tsync();
-            Nt = Ntm;
+            tgemm_mma<2, false, false>(m, t, rl, Nta, ldm, Cs, ldc, [&](int i, int j, double v) { Nta[i + (rl + j) * ldm] = JL[i + (rl + j) * ldm] - v; });
+            tsync();
+            Nt = Nta + rl * ldm;
         }
         tcopy(m, t, Nt, ldm, w.Ntq[l] + s * (long long)m * t, m);
         // closed-form torque: torque_task += Null_{l-1} torque_h = Ntorque f*
-        tgemv<false>(m, t, Nt, ldm, fs + r0[l], [&](int i, double v) { tt[i] += v; });
+        tgemv<false>(m, t, Nt, ldm, fs + rl, [&](int i, double v) { tt[i] += v; });
         if (l + 1 < nl || null_last) {  // null_last: the reduced variant needs Null of its last contact-chain level
             double *Nout = w.Null[l] + s * (long long)m * m;
-            if (l == 0) {
-                tgemm_mma<2, false, false>(m, m, t, Nt, ldm, T + r0[l] + 6 * ldt, ldt, [&](int i, int j, double v) { Nout[i + j * m] = (i == j ? 1.0 : 0.0) - v; });
-            } else {
-                const double *Nprev = w.Null[l - 1] + s * (long long)m * m;
-                tgemm_mma<2, false, false>(m, m, t, Nt, ldm, T + r0[l] + 6 * ldt, ldt, [&](int i, int j, double v) { Nout[i + j * m] = Nprev[i + j * m] - v; });
-            }
+            tgemm_mma<2, false, false>(m, m, rl + t, l == 0 ? JL : Nta, ldm, T + 6 * ldt, ldt,
+                                       [&](int i, int j, double v) { Nout[i + j * m] = (i == j ? 1.0 : 0.0) - v; });
         }
     }
     tsync();
