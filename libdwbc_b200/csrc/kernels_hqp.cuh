@@ -849,8 +849,11 @@ __global__ void __launch_bounds__(TEAM, 6) hqp_kernel(const DevModel *__restrict
     for (int i = tid; i < m; i += nt) tprev[i] = w.tau_grav[s * m + i];
     tsync();
     const double *NwJw = w.NwJw + s * (long long)m * RMAX;
+    // The hierarchy levels and the contact redistribution are the same QP (the redistribution has no task variables and its
+    // own tau_in), so they share ONE copy of the assembly / solve / update code: index q < nl is a level, q == nl the
+    // redistribution.  (Two inlined copies made this kernel 9.7 k SASS instructions and instruction fetch its top stall.)
+    const int nl = hqp ? cfg->nlevels : 0;
     if (hqp) {
-        const int nl = cfg->nlevels;
         for (int i = tid; i < m; i += nt) tau_task[i] = 0.0, tau_contact[i] = 0.0;
         for (int l = 0; l < nl; l++) {
             const int t = cfg->tasks[l].dof;
@@ -858,90 +861,30 @@ __global__ void __launch_bounds__(TEAM, 6) hqp_kernel(const DevModel *__restrict
             for (int i = tid; i < RMAX; i += nt) w.contact_qp[l][s * RMAX + i] = 0.0;
             if (tid < ACTIVE_WORDS) w.active[l][s * ACTIVE_WORDS + tid] = 0u;
         }
-        bool all_ok = task_ok;
-        for (int l = 0; l < nl && all_ok; l++) {
-            const int t = cfg->tasks[l].dof;
-            const int nv = t + r;
-            tsync();  // the previous level is done with U / AU / b / fs
-            {
-                const double *Ntq = w.Ntq[l] + s * (long long)m * t;
-                for (int i = tid; i < t; i += nt) fs[i] = w.fstar[l][s * t + i];
-                tsync();
-                tgemv<false>(m, t, Ntq, m, fs, [&](int i, double v) { base[i] = tprev[i] + v; });
-                tsync();
-                if (quick_feasible()) {
-                    // x = 0: torque_task += Ntorque f* (= base - tau_prev), tau_prev = base, torque_h = J_kt Lambda_t f*, contact_qp = 0
-                    for (int i = tid; i < m; i += nt) {
-                        tau_task[i] += base[i] - tprev[i];
-                        tprev[i] = base[i];
-                        if (r > 0) tau_contact[i] = 0.0;
-                    }
-                    const double *Lt = w.Lamt[l] + s * (long long)t * t, *Jk = w.Jkt[l] + s * (long long)m * t;
-                    tgemv<false>(t, t, Lt, t, fs, [&](int i, double v) { lf[i] = v; });
-                    tsync();
-                    tgemv<false>(m, t, Jk, m, lf, [&](int i, double v) { w.torque_h[l][s * m + i] = v; });
-                    continue;
-                }
-            }
-            // U = [Ntorque | NwJw]
-            tcopy(m, t, w.Ntq[l] + s * (long long)m * t, m, U, ldm);
-            tcopy(m, r, NwJw, m, U + t * ldm, ldm);
-            for (int i = tid; i < t; i += nt) fs[i] = w.fstar[l][s * t + i];
-            build_At();
-            tsync();
-            // base = tau_prev + Ntorque f*
-            tgemv<false>(m, t, U, ldm, fs, [&](int i, double v) { base[i] = tprev[i] + v; });
-            // AU = Atemp U
-            tgemm_mma<2, false, false>(nc, nv, m, At, ldc, U, ldm, [&](int i, int j, double v) { AU[i + j * ldc] = v; });
-            tsync();
-            if (mt)
-                for (int i = tid; i < m; i += nt) {
-                    b[i] = cfg->tlim[i] - base[i];
-                    b[m + i] = cfg->tlim[i] + base[i];
-                }
-            tgemv<false>(nc, m, At, ldc, base, [&](int i, double v) { b[mt + i] = -(bA0[i] - v); });
-            tsync();
-            const LevelOut lo = solve_level(sm, n, m, nvmax, t, r, mt, nc, w.active[l] + s * ACTIVE_WORDS);
-            total_iters += lo.iters;
-            if (!lo.status) {
-                all_ok = false;  // reference: f_star_qp_ = contact_qp_ = 0 and return 0 (src/dwbc.cpp:1117-1125, 836-837)
-                break;
-            }
-            if (tid < t) {
-                const double xj = S.xj[tid];
-                w.fstar_qp[l][s * t + tid] = xj;
-                fs[tid] += xj;
-            } else if (tid < nv) {
-                const double xj = S.xj[tid];
-                w.contact_qp[l][s * RMAX + tid - t] = xj;
-                xs[tid - t] = xj;
-            }
-            tsync();
-            // torque_task += Null_{l-1} J_kt Lambda (f* + f*_qp) = Ntorque (f* + x_t);  tau_prev = tau_grav + torque_task
-            tgemv<false>(m, t, U, ldm, fs, [&](int i, double v) {
-                const double tt = tau_task[i] + v;
-                tau_task[i] = tt;
-                tprev[i] = w.tau_grav[s * m + i] + tt;
-            });
-            // torque_h = J_kt Lambda_t (f* + f*_qp)
-            {
-                const double *Lt = w.Lamt[l] + s * (long long)t * t, *Jk = w.Jkt[l] + s * (long long)m * t;
-                tgemv<false>(t, t, Lt, t, fs, [&](int i, double v) { lf[i] = v; });
-                tsync();
-                tgemv<false>(m, t, Jk, m, lf, [&](int i, double v) { w.torque_h[l][s * m + i] = v; });
-            }
-            // torque_contact = NwJw contact_qp  (zero without an internal-force space: quirk 1 of SURVEY Appendix A)
-            if (r > 0) tgemv<false>(m, r, NwJw, m, xs, [&](int i, double v) { tau_contact[i] = v; });
-        }
-        if (all_ok) st |= 2;
     }
     if (redist) {
         if (tid < ACTIVE_WORDS) w.active[MAX_LEVELS][s * ACTIVE_WORDS + tid] = 0u;
         for (int i = tid; i < RMAX; i += nt) w.cf_redis[s * RMAX + i] = 0.0;
-        tsync();  // tau_task / tau_contact of the level loop are visible to every thread
-        if (r <= 0) {
+    }
+    bool all_ok = task_ok;
+    DWBC_UNROLL(1)
+    for (int q = 0; q < nl + (redist ? 1 : 0); q++) {
+        const bool lev = q < nl;
+        if (lev && !all_ok) continue;  // a failed level ends CalcTaskControlTorque (reference src/dwbc.cpp:836-837); the redistribution still runs
+        const int t = lev ? cfg->tasks[q].dof : 0;
+        const int nv = t + r;
+        tsync();  // the previous QP is done with U / AU / b / fs; tau_task / tau_contact are visible to every thread
+        if (!lev && r <= 0) {
             for (int i = tid; i < m; i += nt) tau_contact[i] = 0.0;  // reference src/dwbc.cpp:1562-1566
             st |= 4;
+            continue;
+        }
+        const double *Ntq = lev ? w.Ntq[q] + s * (long long)m * t : NwJw;
+        if (lev) {
+            // base = tau_prev + Ntorque f*
+            for (int i = tid; i < t; i += nt) fs[i] = w.fstar[q][s * t + i];
+            tsync();
+            tgemv<false>(m, t, Ntq, m, fs, [&](int i, double v) { base[i] = tprev[i] + v; });
         } else {
             // tau_in: torque_grav_ + torque_task_ + torque_contact_ (reference src/dwbc.cpp:1372-1380); the reduced variant passes
             // torque_grav_R_ + torque_task_R_ and ASSIGNS torque_contact_R_ = NwJw_R x (redist == 2, src/dwbc.cpp:3763, 4915)
@@ -949,38 +892,67 @@ __global__ void __launch_bounds__(TEAM, 6) hqp_kernel(const DevModel *__restrict
                 if (redist == 2) tau_contact[i] = 0.0;
                 base[i] = w.tau_grav[s * m + i] + tau_task[i] + tau_contact[i];
             }
+        }
+        tsync();
+        bool solved = true, have_x = false;
+        if (!quick_feasible()) {
+            // U = [Ntorque | NwJw],  AU = Atemp U,  right-hand sides
+            if (lev) tcopy(m, t, Ntq, m, U, ldm);
+            tcopy(m, r, NwJw, m, U + t * ldm, ldm);
+            build_At();
             tsync();
-            const bool quick = quick_feasible();
-            if (quick) st |= 4;  // x = 0: torque_contact is left as it is, cf_redis_qp_ = 0
-            if (!quick) {
-                tcopy(m, r, NwJw, m, U, ldm);
-                build_At();
-                tsync();
-                tgemm_mma<1, false, false>(nc, r, m, At, ldc, U, ldm, [&](int i, int j, double v) { AU[i + j * ldc] = v; });
-                if (mt)
-                    for (int i = tid; i < m; i += nt) {
-                        b[i] = cfg->tlim[i] - base[i];
-                        b[m + i] = cfg->tlim[i] + base[i];
-                    }
-                tgemv<false>(nc, m, At, ldc, base, [&](int i, double v) { b[mt + i] = -(bA0[i] - v); });
-                tsync();
-                const LevelOut lo = solve_level(sm, n, m, nvmax, 0, r, mt, nc, w.active[MAX_LEVELS] + s * ACTIVE_WORDS);
-                total_iters += lo.iters;
-                if (lo.status) {
-                    if (tid < r) {
-                        const double xj = S.xj[tid];
-                        w.cf_redis[s * RMAX + tid] = xj;
-                        xs[tid] = xj;
-                    }
-                    tsync();
-                    tgemv<false>(m, r, NwJw, m, xs, [&](int i, double v) { tau_contact[i] += v; });
-                    st |= 4;
-                } else {
-                    for (int i = tid; i < m; i += nt) tau_contact[i] = 0.0;  // reference src/dwbc.cpp:1553-1559
+            tgemm_mma<2, false, false>(nc, nv, m, At, ldc, U, ldm, [&](int i, int j, double v) { AU[i + j * ldc] = v; });
+            if (mt)
+                for (int i = tid; i < m; i += nt) {
+                    b[i] = cfg->tlim[i] - base[i];
+                    b[m + i] = cfg->tlim[i] + base[i];
                 }
+            tgemv<false>(nc, m, At, ldc, base, [&](int i, double v) { b[mt + i] = -(bA0[i] - v); });
+            tsync();
+            const LevelOut lo = solve_level(sm, n, m, nvmax, t, r, mt, nc, w.active[lev ? q : MAX_LEVELS] + s * ACTIVE_WORDS);
+            total_iters += lo.iters;
+            solved = lo.status != 0;
+            have_x = solved;
+        }
+        if (!solved) {
+            if (lev) {
+                all_ok = false;  // reference: f_star_qp_ = contact_qp_ = 0 and return 0 (src/dwbc.cpp:1117-1125, 836-837)
+            } else {
+                for (int i = tid; i < m; i += nt) tau_contact[i] = 0.0;  // reference src/dwbc.cpp:1553-1559
+            }
+            continue;
+        }
+        // x = [x_t; x_c]  (zero on the fast path: the outputs were cleared above)
+        if (tid < nv) {
+            const double xj = have_x ? S.xj[tid] : 0.0;
+            if (tid < t) {
+                if (have_x) w.fstar_qp[q][s * t + tid] = xj;
+                fs[tid] += xj;
+            } else {
+                xs[tid - t] = xj;
+                if (have_x) (lev ? w.contact_qp[q] : w.cf_redis)[s * RMAX + tid - t] = xj;
             }
         }
+        tsync();
+        if (lev) {
+            // torque_task += Null_{l-1} J_kt Lambda (f* + f*_qp) = Ntorque (f* + x_t);  tau_prev = tau_grav + torque_task
+            tgemv<false>(m, t, Ntq, m, fs, [&](int i, double v) {
+                const double tt = tau_task[i] + v;
+                tau_task[i] = tt;
+                tprev[i] = w.tau_grav[s * m + i] + tt;
+            });
+            // torque_h = J_kt Lambda_t (f* + f*_qp)
+            const double *Lt = w.Lamt[q] + s * (long long)t * t, *Jk = w.Jkt[q] + s * (long long)m * t;
+            tgemv<false>(t, t, Lt, t, fs, [&](int i, double v) { lf[i] = v; });
+            tsync();
+            tgemv<false>(m, t, Jk, m, lf, [&](int i, double v) { w.torque_h[q][s * m + i] = v; });
+        }
+        // level: torque_contact = NwJw contact_qp (zero without an internal-force space: quirk 1 of SURVEY Appendix A);
+        // redistribution: torque_contact += NwJw x
+        if (r > 0) tgemv<false>(m, r, NwJw, m, xs, [&](int i, double v) { tau_contact[i] = (lev ? 0.0 : tau_contact[i]) + v; });
+        if (!lev) st |= 4;
     }
+    if (hqp && all_ok) st |= 2;
     if (tid == 0) {
         w.status[s] = st;
         w.qp_iters[s] = total_iters;
