@@ -6,6 +6,8 @@
                                  model reader consumes (<link><inertial>, <joint> origin/axis/parent/child/limit);
                                  visuals, collisions and MuJoCo tags are dropped.  Numbers are kept as
                                  the literal strings of the source file.
+* tests/golden/dof/tocabi_dof{18,25,45}.urdf : the same reduction of three models of the reference's DoF study
+                                 (reference tests/dof_test/dyros_tocabi_dof{18,25,45}.urdf, tests/sp_test/dof_comparison.cpp:41-146)
 """
 import os
 import shutil
@@ -21,21 +23,30 @@ for case in ("1", "2"):
     for f in sorted(os.listdir(os.path.join(REF, "tests", "cases", case))):
         shutil.copyfile(os.path.join(REF, "tests", "cases", case, f), os.path.join(dst, f))
 
-root = ET.parse(os.path.join(REF, "tests", "dyros_tocabi.urdf")).getroot()
-out = ET.Element("robot", {"name": "tocabi"})
-for el in root:
-    if el.tag == "link":
-        ln = ET.SubElement(out, "link", {"name": el.get("name")})
-        inert = el.find("inertial")
-        if inert is not None:
-            i2 = ET.SubElement(ln, "inertial")
-            for ch in inert:
-                ET.SubElement(i2, ch.tag, dict(ch.attrib))
-    elif el.tag == "joint":
-        jn = ET.SubElement(out, "joint", {"name": el.get("name"), "type": el.get("type")})
-        for ch in el:
-            if ch.tag in ("origin", "parent", "child", "axis", "limit"):
-                ET.SubElement(jn, ch.tag, dict(ch.attrib))
-ET.indent(out, space=" ")
-ET.ElementTree(out).write(os.path.join(HERE, "tocabi_model.urdf"), xml_declaration=True, encoding="utf-8")
+
+
+def reduce_urdf(src, dst, name):
+    root = ET.parse(src).getroot()
+    out = ET.Element("robot", {"name": name})
+    for el in root:
+        if el.tag == "link":
+            ln = ET.SubElement(out, "link", {"name": el.get("name")})
+            inert = el.find("inertial")
+            if inert is not None:
+                i2 = ET.SubElement(ln, "inertial")
+                for ch in inert:
+                    ET.SubElement(i2, ch.tag, dict(ch.attrib))
+        elif el.tag == "joint":
+            jn = ET.SubElement(out, "joint", {"name": el.get("name"), "type": el.get("type")})
+            for ch in el:
+                if ch.tag in ("origin", "parent", "child", "axis", "limit"):
+                    ET.SubElement(jn, ch.tag, dict(ch.attrib))
+    ET.indent(out, space=" ")
+    ET.ElementTree(out).write(dst, xml_declaration=True, encoding="utf-8")
+
+
+reduce_urdf(os.path.join(REF, "tests", "dyros_tocabi.urdf"), os.path.join(HERE, "tocabi_model.urdf"), "tocabi")
+os.makedirs(os.path.join(HERE, "dof"), exist_ok=True)
+for dof in (18, 25, 45):
+    reduce_urdf(os.path.join(REF, "tests", "dof_test", f"dyros_tocabi_dof{dof}.urdf"), os.path.join(HERE, "dof", f"tocabi_dof{dof}.urdf"), f"tocabi_dof{dof}")
 print("fixtures written under", HERE)

@@ -1,5 +1,5 @@
 """generic-DoF models -- the reference's own scaling-study family (reference tests/dof_test/
-dyros_tocabi_dof{18..45}.urdf, tests/sp_test/dof_comparison.cpp:41-146; three of them copied as fixtures under
+dyros_tocabi_dof{18..45}.urdf, tests/sp_test/dof_comparison.cpp:41-146; three of them reduced to their dynamics data under
 tests/golden/dof/).  Kernel logic (emulation build) vs the oracle on 18-, 25- and 45-joint models: gravity compensation,
 contact-consistent dynamics, closed-form task torque and the 2-level HQP + redistribution with torque limit 200."""
 import os
@@ -13,7 +13,7 @@ from tests.common import *
 
 
 def dof_urdf(dof):
-    return os.path.join(GOLDEN, "dof", f"dyros_tocabi_dof{dof}.urdf")
+    return os.path.join(GOLDEN, "dof", f"tocabi_dof{dof}.urdf")
 
 
 def dof_states(dof, B, seed):
