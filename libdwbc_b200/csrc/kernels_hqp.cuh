@@ -163,6 +163,21 @@ __device__ __forceinline__ double team_max(double v, const GiScratch &S) {
     tsync();
     return r;
 }
+// two maxima with one pair of barriers (red has GI_WARPS_MAX slots: first half for a, second half for b)
+__device__ __forceinline__ void team_max2(double &a, double &b, const GiScratch &S) {
+    static_assert(2 * (TEAM / 32) <= GI_WARPS_MAX, "team_max2 needs two slots per warp");
+    a = warp_max(a);
+    b = warp_max(b);
+    const int nw = t_n() >> 5;
+    if (lane_id() == 0) S.red[t_id() >> 5] = a, S.red[nw + (t_id() >> 5)] = b;
+    tsync();
+    a = S.red[0], b = S.red[nw];
+    for (int w = 1; w < nw; w++) {
+        a = S.red[w] > a ? S.red[w] : a;
+        b = S.red[nw + w] > b ? S.red[nw + w] : b;
+    }
+    tsync();
+}
 __device__ __forceinline__ double team_sum(double v, const GiScratch &S) {
     v = warp_sum(v);
     if (lane_id() == 0) S.red[t_id() >> 5] = v;
@@ -181,7 +196,7 @@ __device__ __forceinline__ double team_sum(double v, const GiScratch &S) {
 // dropped.  On return S.dxs holds dx, S.act / S.u the active rows and their multipliers (logical positions < q).
 // Deliberately NOT inlined (instruction-cache footprint, profiles/r01_ncu_summary.md).  Synchronises on entry and exit.
 __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, int mt, int nc, int col0, int nv, int use_bt, double isd_t,
-                                          double isd_c, int tsplit, int use_pin, int max_iter) {
+                                          double isd_c, int tsplit, int use_pin, int max_iter, double ztol) {
     // Everything is re-derived from the arena base and a few integers: structs passed by reference to a non-inlined function
     // live in local memory, and with most of L1 carved out as shared memory those loads went to L2 (ncu: 20 % L1 hit rate,
     // long-scoreboard the second largest stall of the first team version).
@@ -227,15 +242,32 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
         smax = s > smax ? s : smax;
     }
     smax = team_max(smax, S);
+    // A row whose normal is numerically zero IN THIS COLUMN WINDOW cannot be moved by the sub-problem's variables: if it is
+    // violated the sub-problem is infeasible (e.g. stage A of solve_level, x_t = 0: a torque-limit row that only the task
+    // variables can relieve).  ztol: solve_level's margin for rows that are zero in every column, 1e-9 (1 + max|b|).
+    bool zero_row_violated = false;
     DWBC_UNROLL(1)
     for (int i = tid; i < mc; i += nt) {
         const double s = rin[i];
-        rin[i] = (s > 0.0 && s > 1e-20 * smax) ? 1.0 / sqrt(s) : 0.0;
+        const bool live = s > 0.0 && s > 1e-20 * smax;
+        rin[i] = live ? 1.0 / sqrt(s) : 0.0;
+        if (!live && !(pin && bit_test(pin, i)) && bt[i] < -fmax(tolv[i], ztol)) zero_row_violated = true;
+    }
+    {
+        const bool wz = __any_sync(DWBC_FULL, zero_row_violated);
+        if (lane == 0) ired[warp] = wz ? 1 : 0;
     }
     tsync();
+    GiResult res{0, 0, 0};
+    {
+        bool anyz = false;
+        DWBC_UNROLL(1)
+        for (int wI = 0; wI < nw; wI++) anyz = anyz || ired[wI];
+        tsync();
+        if (anyz) return res;  // status 0: infeasible
+    }
     int q = 0, neq = 0;
     uint32_t used = 0;  // physical R columns in use
-    GiResult res{0, 0, 0};
     int p = -1;  // row being added
     double sp = 0.0, sigma = 1.0, up = 0.0;
     int pin_scan = 0;
@@ -577,7 +609,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
     tsync();
     if (tid < QP_NV_MAX) xj[tid] = 0.0;
     // row tolerances in the units of the rows, the quick exit, and the active rows of the quick exit.  Numerically zero
-    // rows (norm <= 1e-10 of the largest) cannot be influenced by x: they only decide feasibility (b >= -1e-9).
+    // rows (norm <= 1e-10 of the largest) cannot be influenced by x: they only decide feasibility (b >= -1e-9 (1 + max|b|)).
     double smax = 0.0;
     DWBC_UNROLL(1)
     for (int i = tid; i < mc; i += nt) {
@@ -590,7 +622,13 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
         rin[i] = s;
         smax = s > smax ? s : smax;
     }
-    smax = team_max(smax, S);
+    // magnitude of the right-hand sides: a numerically zero row is "violated" only beyond 1e-9 of it (its b is a difference of
+    // quantities of that size, e.g. tlim - tau where an earlier level left the torque limit active to ~1e-10 relative)
+    double babs = 0.0;
+    DWBC_UNROLL(1)
+    for (int i = tid; i < mc; i += nt) babs = fmax(babs, fabs(b[i]));
+    team_max2(smax, babs, S);
+    const double zero_row_tol = 1e-9 * (1.0 + babs);
     double bmin = 1e300;
     bool infeasible = false;
     DWBC_UNROLL(1)
@@ -603,7 +641,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
             tolv[i] = 1e-10 * sc;
             if (s > 1e-20 * smax && s >= 1e-28)
                 bmin = fmin(bmin, b[i] + 1e-10 * sc);
-            else if (b[i] < -1e-9)
+            else if (b[i] < -zero_row_tol)
                 infeasible = true;
             on = s > 0.0 && b[i] < 1e-9 * (1.0 + fabs(b[i]));
         }
@@ -635,7 +673,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
     const int max_iter = 20 * (nv + 8);
     bool done = false;
     if (t == 0 || r == 0) {
-        GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, 0, nv, 0, 1.0, 1.0, nv, 0, max_iter);
+        GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, 0, nv, 0, 1.0, 1.0, nv, 0, max_iter, zero_row_tol);
         out.iters += g.iters;
         out.status = g.status;
         if (tid < nv) xj[tid] = S.dxs[tid];
@@ -645,7 +683,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
         // ---- A: is x_t = 0 attainable?  (looser tolerances: the set may be a thin face inherited from the levels above)
         DWBC_UNROLL(1)
         for (int i = tid; i < mc; i += nt) tolv[i] *= 100.0;
-        GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, t, r, 0, 1.0, 1.0, r, 0, max_iter);
+        GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, t, r, 0, 1.0, 1.0, r, 0, max_iter, zero_row_tol);
         out.iters += g.iters;
         if (g.status) {
             if (tid < r) xj[t + tid] = S.dxs[tid];
@@ -687,7 +725,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
             if (k > 0 && gi_warm(sm, n, m, nvmax, mt, nc, 0, nv, g.q)) {
                 out.iters += 1;
             } else {
-                g = gi_solve(sm, n, m, nvmax, mt, nc, 0, nv, 1, 1.0, isd_c, t, 0, max_iter);
+                g = gi_solve(sm, n, m, nvmax, mt, nc, 0, nv, 1, 1.0, isd_c, t, 0, max_iter, zero_row_tol);
                 out.iters += g.iters;
             }
             if (!g.status) {
@@ -730,7 +768,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
                 bt[i] = s;
                 tolv[i] *= 100.0;
             }
-            GiResult gc = gi_solve(sm, n, m, nvmax, mt, nc, t, r, 1, 1.0, 1.0, r, 1, max_iter);
+            GiResult gc = gi_solve(sm, n, m, nvmax, mt, nc, t, r, 1, 1.0, 1.0, r, 1, max_iter, zero_row_tol);
             out.iters += gc.iters;
             if (!gc.status) out.status = 0;
             if (tid < r) xj[t + tid] = S.dxs[tid];

@@ -204,6 +204,14 @@ __device__ __noinline__ int lqp_ldp_solve(double *sm, int n, int m, int tmax, in
     smax = red[0];
     for (int w = 1; w < nw; w++) smax = red[w] > smax ? red[w] : smax;
     tsync();
+    double uabs = 0.0;  // magnitude of the right-hand sides (margin of the numerically zero rows, as in kernels_hqp.cuh)
+    for (int i = tid; i < rows; i += nt) uabs = fmax(uabs, fabs(ub[i]));
+    uabs = warp_max(uabs);
+    if (lane == 0) red[warp] = uabs;
+    tsync();
+    uabs = red[0];
+    for (int w = 1; w < nw; w++) uabs = red[w] > uabs ? red[w] : uabs;
+    tsync();
     bool bad = false;
     for (int i = tid; i < rows; i += nt) {
         const double s = rin[i];
@@ -215,7 +223,7 @@ __device__ __noinline__ int lqp_ldp_solve(double *sm, int n, int m, int tmax, in
             rin[i] = rsqrt(s);
         else {
             rin[i] = 0.0;
-            if (ub[i] < -1e-9) bad = true;
+            if (ub[i] < -1e-9 * (1.0 + uabs)) bad = true;
         }
     }
     if (lane == 0) ired[warp] = 0;

@@ -186,12 +186,14 @@ inline bool ldp(const Mat &G, const std::vector<double> &h, std::vector<double> 
         for (int j = 0; j < n; j++) s += G(i, j) * G(i, j);
         smax = std::max(smax, std::sqrt(s));
     }
+    double habs = 0;  // magnitude of the right-hand sides: the feasibility margin of a numerically zero row is relative to it
+    for (int i = 0; i < m; i++) habs = std::max(habs, std::fabs(h[i]));
     for (int i = 0; i < m; i++) {
         double s = 0;
         for (int j = 0; j < n; j++) s += G(i, j) * G(i, j);
         s = std::sqrt(s);
         if (s < 1e-14 || s <= 1e-10 * smax) {
-            if (h[i] > 1e-9) return false;
+            if (h[i] > 1e-9 * (1.0 + habs)) return false;
             continue;
         }
         rows.push_back(i);
