@@ -122,3 +122,45 @@ def test_emul_analytic_redistribution_contact_force_zmp():
     cf2 = rd.get_contact_force(tau)
     ref.update_kinematics(q[0], qd[0]); ref.set_contact(1, 1); ref.calc_contact_constraint(); ref.calc_grav()
     assert relerr(cf2[0], ref.contact_force(tau[0])) < 1e-9
+
+
+def run_tight_torque_limit(make_rd, D, H, B, tl=45.0):
+    """Config-2 hierarchy with a torque limit low enough that the limit rows are active in most states (the goldens and the
+    workload rarely activate them): product vs oracle, and the limit holds for the summed torque."""
+    from libdwbc_b200 import CONTACT_6D, TASK_LINK_POSITION, TASK_LINK_ROTATION
+
+    q, qd, rng = synth_states(B, 20255)
+    fs = synth_fstar(rng, B)
+    flags = np.ones((B, 2), dtype=np.uint8)
+    rd = make_rd(B)
+    rd.add_contact_constraint(LEFT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+    rd.add_contact_constraint(RIGHT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
+    rd.add_task_space(0, TASK_LINK_POSITION, "COM")
+    rd.add_task_space(1, TASK_LINK_ROTATION, "pelvis_link")
+    rd.add_task_space(1, TASK_LINK_ROTATION, "upperbody_link")
+    rd.add_custom_task_space(2, 21)
+    rd.set_torque_limit(tl)
+    rd.update_kinematics(D(q), D(qd))
+    rd.set_contact(D(flags))
+    rd.calc_contact_constraint()
+    for l, f in enumerate(fs):
+        rd.set_task_space(l, D(f), D(posture_selector()) if l == 2 else None)
+    tg, tt, tc, st = [H(x) for x in rd.solve(SOLVE_GRAV | SOLVE_HQP | SOLVE_REDIST)]
+    ref = configure_oracle(orc.OracleRobot(URDF), 2)
+    ref.set_torque_limit(tl)
+    o = ref.run_batch(q, qd, fs, flags)
+    assert np.array_equal(st & 7, o["status"] & 7)
+    ok = (o["status"] & 7) == 7
+    assert ok.sum() >= B // 2
+    n_at_limit = 0
+    for b in np.where(ok)[0]:
+        for a, k in ((tt, "torque_task"), (tc, "torque_contact")):
+            assert np.abs(a[b] - o[k][b]).max() < 1e-6 * max(1.0, np.abs(o[k][b]).max()), (b, k)
+        tot = np.abs(tg[b] + tt[b] + tc[b]).max()
+        assert tot <= tl + 1e-6
+        n_at_limit += int(tot > tl - 1e-6)
+    assert n_at_limit >= ok.sum() // 3
+
+
+def test_emul_tight_torque_limit():
+    run_tight_torque_limit(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, lambda a: a, 6)

@@ -555,3 +555,15 @@ def test_gpu_reduced_hqp_with_non_contact_levels():
 
     n_active = run_reduced_hqp_nc(lambda B: RobotDataBatch(URDF, B, 0), D, lambda x: x.cpu().numpy(), scales=(0.0, 0.0, 6.5, 6.8, 7.0, 7.2, 7.5, 1.0))
     assert n_active >= 1
+
+
+def test_gpu_tight_torque_limit():
+    """torque-limit rows active in most states (limit 45 Nm): GPU HQP + redistribution vs the oracle"""
+    from libdwbc_b200 import RobotDataBatch
+    from tests.test_emul_parity import run_tight_torque_limit
+
+    def D(a):
+        a = np.ascontiguousarray(a)
+        return T(a, torch.uint8 if a.dtype == np.uint8 else torch.float64)
+
+    run_tight_torque_limit(lambda B: RobotDataBatch(URDF, B, 0), D, lambda x: x.cpu().numpy(), 96)
