@@ -567,3 +567,35 @@ def test_gpu_tight_torque_limit():
         return T(a, torch.uint8 if a.dtype == np.uint8 else torch.float64)
 
     run_tight_torque_limit(lambda B: RobotDataBatch(URDF, B, 0), D, lambda x: x.cpu().numpy(), 96)
+
+
+def test_gpu_rl_bridge_batch():
+    """RlWBCBridgeBatch / RlWBCBridge on the device (reference src/pybind/rl_wbc_bridge.cpp call sequence): MuJoCo-ordered input,
+    float32 torque command, per-environment contact flags; checked against the oracle running the calls the reference bridge makes."""
+    from libdwbc_b200 import RlWBCBridge, RlWBCBridgeBatch
+    from tests.test_bridge import _oracle_cmd
+
+    B = 16
+    q, qd, rng = synth_states(B, 20252)
+    qpos = np.concatenate([q[:, 0:3], q[:, 39:40], q[:, 3:6], q[:, 6:39]], axis=1)
+    f0, f1 = 0.3 * rng.standard_normal((B, 6)), 0.3 * rng.standard_normal((B, 3))
+    br = RlWBCBridgeBatch(B, device=0, urdf_path=URDF)
+    br.UpdateKinematics(T(qpos), T(qd), None)
+    br.SetContact(True, True)
+    br.SetTaskSpace(0, T(f0))
+    br.SetTaskSpace(1, T(f1))
+    br.CalcTorque()
+    cmd = br.getTorqueCommand()
+    assert cmd.dtype == torch.float32 and tuple(cmd.shape) == (B, 33) and cmd.is_cuda
+    cmd = cmd.cpu().numpy()
+    for b in range(0, B, 3):
+        want = _oracle_cmd(q[b], qd[b], (1, 1), f0[b], f1[b])
+        assert np.abs(cmd[b] - want).max() <= 1e-5 * max(1.0, np.abs(want).max()), b
+    one = RlWBCBridge(0, device=0, urdf_path=URDF)
+    one.UpdateKinematics(qpos[1], qd[1], np.zeros(39))
+    one.SetContact(True, True)
+    one.SetTaskSpace(0, f0[1])
+    one.SetTaskSpace(1, f1[1])
+    one.CalcTorque()
+    out = one.getTorqueCommand()
+    assert len(out) == 33 and np.array_equal(np.float32(out), cmd[1])
