@@ -807,17 +807,17 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
 __global__ void __launch_bounds__(TEAM, 6) hqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int redist,
                                                       int nvmax) {
     DWBC_DYN_SMEM(smem);
-    const int tid = t_id(), nt = t_n(), warp = tid >> 5, lane = lane_id();
+    const int tid = t_id(), nt = t_n();
     const long long s = blockIdx.x;
     const int n = w.n, m = w.m, nb = w.nb;
     const HqpSmem L(n, m, nvmax);
     double *sm = (double *)smem;
-    double *U = sm + L.U, *AU = sm + L.AU, *At = sm + L.At, *Q = sm + L.Q, *R = sm + L.R, *b = sm + L.b, *tolv = sm + L.tol, *rin = sm + L.rin;
+    double *U = sm + L.U, *AU = sm + L.AU, *At = sm + L.At, *b = sm + L.b;
     const GiScratch S(sm + L.gi, sm + L.bt);
     double *vec = sm + L.vec;
     const int vs = n + 2;
     double *tprev = vec, *base = vec + vs, *fs = vec + 2 * vs, *bA0 = vec + 3 * vs, *xs = vec + 4 * vs, *lf = vec + 5 * vs;
-    const int ldm = L.ldm, ldc = L.ldc, ldq = L.ldq;
+    const int ldm = L.ldm, ldc = L.ldc;
     int st = w.status[s];
     const bool contact_ok = st & 1;
     const bool task_ok = (st & 8) != 0;  // set by task_space_kernel when hqp = 1

@@ -478,9 +478,12 @@ int Robot::calc_contact_constraint() {
     if (c > 6) {
         int rank = f.rank;
         V2 = f.Q.t().block(rank, 0, m - rank, m);
+        if (c - 6 != V2.r) {  // "Contact Space Factorization Error" (src/wbd.cpp:130-135): the reference inverts a non-square matrix here
+            contact_ok = 0;
+            return contact_ok;
+        }
         Mat tmp = lu_inverse(J_C_INV_T.block(0, 6, c - 6, m) * V2.t());  // topRightCorner(rows-6, cols-6)
         NwJw = V2.t() * tmp;
-        if (c - 6 != V2.r) contact_ok = 0;
     }
     return contact_ok;
 }

@@ -8,6 +8,9 @@
                                  the literal strings of the source file.
 * tests/golden/dof/tocabi_dof{18,25,45}.urdf : the same reduction of three models of the reference's DoF study
                                  (reference tests/dof_test/dyros_tocabi_dof{18,25,45}.urdf, tests/sp_test/dof_comparison.cpp:41-146)
+* tests/golden/variants/tocabi_{ub,wo_head,fixed_head}.urdf : the same reduction of the reference's model variants
+                                 (reference tests/dyros_tocabi_{ub,wo_head,fixed_head}.urdf; users: tests/sp_test/rot_test.cpp:19,
+                                 tests/sp_test/test_mod.cpp:525)
 """
 import os
 import shutil
@@ -49,4 +52,7 @@ reduce_urdf(os.path.join(REF, "tests", "dyros_tocabi.urdf"), os.path.join(HERE, 
 os.makedirs(os.path.join(HERE, "dof"), exist_ok=True)
 for dof in (18, 25, 45):
     reduce_urdf(os.path.join(REF, "tests", "dof_test", f"dyros_tocabi_dof{dof}.urdf"), os.path.join(HERE, "dof", f"tocabi_dof{dof}.urdf"), f"tocabi_dof{dof}")
+os.makedirs(os.path.join(HERE, "variants"), exist_ok=True)
+for v in ("ub", "wo_head", "fixed_head"):
+    reduce_urdf(os.path.join(REF, "tests", f"dyros_tocabi_{v}.urdf"), os.path.join(HERE, "variants", f"tocabi_{v}.urdf"), f"tocabi_{v}")
 print("fixtures written under", HERE)

@@ -481,6 +481,25 @@ def test_gpu_generic_dof(dof):
     run_generic(dof, lambda urdf, B: RobotDataBatch(urdf, B, 0), D, lambda x: x.cpu().numpy(), B=8)
 
 
+@pytest.mark.parametrize("name", ["wo_head", "fixed_head", "ub"])
+def test_gpu_model_variant(name):
+    """the reference's model variants (tests/dyros_tocabi_{wo_head,fixed_head,ub}.urdf) on the device
+    vs the oracle: the whole path on the 32-joint models, UpdateKinematics on the leg-less upper-body model."""
+    from libdwbc_b200 import RobotDataBatch
+    from tests.test_generic_dof import run_upper_body, run_variant
+
+    def D(a):
+        a = np.ascontiguousarray(a)
+        return T(a, torch.uint8 if a.dtype == np.uint8 else torch.float64)
+
+    make = lambda urdf, B: RobotDataBatch(urdf, B, 0)
+    H = lambda x: x.cpu().numpy()
+    if name == "ub":
+        run_upper_body(make, D, H, B=8)
+    else:
+        run_variant(name, make, D, H, B=8)
+
+
 @pytest.mark.parametrize("limited", [False, True])
 def test_gpu_reduced_hqp_vs_oracle(limited):
     """a9 QP branches (CalcSingleTaskTorqueWithQP_R, CalcContactRedistributeR; reference src/dwbc.cpp:3448-3599, 4777-4925) on the
