@@ -277,11 +277,17 @@ int dwbc_batch_update_kinematics_mujoco(dwbc_batch_t *b, const double *qpos_dev,
 int dwbc_batch_get_torque_command_f32(dwbc_batch_t *b, float *out_dev, void *stream);
 
 /* ---- whole cycle with HOST buffers (pinned or pageable): H2D, all stages, D2H, synchronised on return.
- * This is what the RobotData shim, the pybind bridge and bench.py's end-to-end timing call.
- * fstar_host: concatenation over levels of [B x t_l] blocks. flags_host [B x ncontact]. */
+ * This is what the RobotData shim, the pybind bridge and bench.py's end-to-end timing call
+ * (one call = UpdateKinematics ... CalcContactRedistribute of reference tests/dwbc_test.cpp:61-130 for every state).
+ * fstar_host: concatenation over levels of [B x t_l] blocks. flags_host [B x ncontact].
+ * Large batches are cut into slices of consecutive states that alternate between two internal streams ordered after `stream`,
+ * so the copies of one slice run under the kernels of another (pinned host buffers needed for that overlap); results are
+ * identical to the unsliced call because states are independent. */
 int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, const double *qdot_host, const double *fstar_host,
                           const uint8_t *flags_host, double *tau_grav_host, double *tau_task_host, double *tau_contact_host,
                           int32_t *status_host, void *stream);
+/* Number of slices dwbc_batch_cycle_host cuts the batch into: 0 = automatic (one per 4096 states, at most 8), 1 = no slicing. */
+int dwbc_batch_set_host_slices(dwbc_batch_t *b, int slices);
 
 /* ---- diagnostics ---- */
 /* Best DFMA-chain throughput (TFLOP/s, 2 flop per FMA) observed over ~`seconds` of back-to-back launches on

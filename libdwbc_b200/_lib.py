@@ -53,6 +53,7 @@ def declare(L):
     L.dwbc_batch_get_contact_force.argtypes = [vp, vp, vp, vp]
     L.dwbc_batch_get_zmp.argtypes = [vp, vp, vp, vp]
     L.dwbc_batch_cycle_host.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.dwbc_batch_set_host_slices.argtypes = [vp, C.c_int]
     L.dwbc_probe_fp64.argtypes = [C.c_int, C.c_double, _dp]
     L.dwbc_batch_get_qp_iterations.argtypes = [vp, vp, vp]
     L.dwbc_batch_set_profiling.argtypes = [vp, C.c_int]
@@ -88,7 +89,7 @@ EXPORTS = [
     "dwbc_batch_reduced_dynamics", "dwbc_batch_reduced_calc_contact_constraint", "dwbc_batch_reduced_solve", "dwbc_batch_reduced_dims", "dwbc_batch_set_reduced_torque_limit",
     "dwbc_batch_get_reduced_matrix", "dwbc_batch_calc_control_torque_lqp", "dwbc_batch_calc_control_torque_lqp_r", "dwbc_batch_get_lqp", "dwbc_batch_get_lqp_iterations",
     "dwbc_batch_set_task_gain", "dwbc_batch_set_trajectory_quintic", "dwbc_batch_set_trajectory_rotation", "dwbc_batch_calc_fstar",
-    "dwbc_batch_update_kinematics_mujoco", "dwbc_batch_get_torque_command_f32",
+    "dwbc_batch_update_kinematics_mujoco", "dwbc_batch_get_torque_command_f32", "dwbc_batch_set_host_slices",
 ]
 
 _lib = None

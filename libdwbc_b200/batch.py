@@ -403,6 +403,10 @@ class RobotDataBatch:
         return {self.L.dwbc_kernel_name(k).decode(): (ms[k], cnt[k]) for k in range(K)}
 
     # ---- whole cycle from host buffers (pinned numpy / torch CPU tensors) ----
+    def set_host_slices(self, slices):
+        """dwbc_batch_set_host_slices: slices cycle_host pipelines the batch in (0 = automatic, 1 = no slicing)"""
+        self._ck(self.L.dwbc_batch_set_host_slices(self._h, int(slices)))
+
     def cycle_host(self, stages, q, qdot, fstars, flags, out=None):
         """H2D + all stages + D2H through dwbc_batch_cycle_host.  All arguments are host arrays (numpy)."""
         B, m = self.batch, self.model_dof_

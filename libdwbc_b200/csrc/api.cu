@@ -2,6 +2,7 @@
 // checking, workspace ownership, kernel launches.  There is deliberately no CPU code path for the math.
 #include "../../include/dwbc_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -44,6 +45,11 @@ struct dwbc_batch {
     uint8_t *d_flags = nullptr;
     int32_t *d_status = nullptr;
     size_t d_fstar_cap = 0;
+    // dwbc_batch_cycle_host pipelines slices of the batch over these streams (copies of one slice under the kernels of another)
+    int host_slices = 0;  // 0 = automatic
+    bool pipe_ready = false;
+    cudaStream_t pipe_stream[2] = {};
+    cudaEvent_t pipe_fork = {}, pipe_join[2] = {};
     int sm_count = 148;
     // call-order tracking
     bool have_kin = false, have_contact = false, have_cc = false;
@@ -153,6 +159,31 @@ int upload_cfg(dwbc_batch *b, cudaStream_t st) {
     CK(cudaStreamSynchronize(st));  // cfg lives on the host stack of the handle: keep it simple and safe
     b->cfg_dirty = false;
     return DWBC_OK;
+}
+
+// The records of states [s0, s0 + cnt) as a batch of their own: every per-state array is state-major (batch.h), so a slice is the
+// same Work with each pointer advanced by s0 records.
+Work slice_work(const Work &f, const BatchCfg &cfg, size_t s0, int cnt) {
+    Work v = f;
+    const size_t n = f.n, m = f.m, nb = f.nb;
+    v.B = cnt;
+    auto adv = [&](auto *&p, size_t rec) {
+        if (p) p += s0 * rec;
+    };
+    adv(v.A, n * n), adv(v.Ainv, n * n), adv(v.G, n), adv(v.Bnl, n), adv(v.pose, nb * POSE_STRIDE), adv(v.com, 16), adv(v.linkvel, nb * 6);
+    adv(v.Jc, CMAX * n), adv(v.cdof, 1), adv(v.cidx, MAX_ACTIVE_CONTACTS);
+    adv(v.Lam, CMAX * CMAX), adv(v.Jbar, CMAX * n), adv(v.AinvNc, n * n), adv(v.W, m * m), adv(v.Winv, m * m), adv(v.V2, RMAX * m);
+    adv(v.NwJw, m * RMAX), adv(v.PC, CMAX), adv(v.tau_grav, m), adv(v.status, 1);
+    for (int l = 0; l < MAX_LEVELS; l++) {
+        const size_t t = l < cfg.nlevels ? cfg.tasks[l].dof : 0;
+        adv(v.fstar[l], t);
+        if (v.jcustom_per_state[l]) adv(v.jcustom[l], t * n);
+        adv(v.Jt[l], t * n), adv(v.Lamt[l], t * t), adv(v.Jkt[l], m * t), adv(v.Null[l], m * m), adv(v.Ntq[l], m * t);
+        adv(v.fstar_qp[l], t), adv(v.contact_qp[l], RMAX), adv(v.torque_h[l], m), adv(v.active[l], ACTIVE_WORDS);
+    }
+    adv(v.active[MAX_LEVELS], ACTIVE_WORDS);
+    adv(v.tau_task, m), adv(v.tau_contact, m), adv(v.cf_redis, RMAX), adv(v.qp_iters, 1);
+    return v;
 }
 
 int alloc_tasks(dwbc_batch *b) {
@@ -268,6 +299,13 @@ void dwbc_batch_destroy(dwbc_batch_t *b) {
     for (void *p : b->red_allocs) cudaFree(p);
     for (void *p : b->red_task_allocs) cudaFree(p);
     if (b->d_fstar) cudaFree(b->d_fstar);
+    if (b->pipe_ready) {
+        for (int i = 0; i < 2; i++) {
+            cudaStreamDestroy(b->pipe_stream[i]);
+            cudaEventDestroy(b->pipe_join[i]);
+        }
+        cudaEventDestroy(b->pipe_fork);
+    }
     for (auto &p : b->pending) {
         cudaEventDestroy(p.e0);
         cudaEventDestroy(p.e1);
@@ -660,13 +698,19 @@ const char *dwbc_kernel_name(int k) {
     return (k >= 0 && k < DWBC_K_COUNT) ? names[k] : nullptr;
 }
 
+int dwbc_batch_set_host_slices(dwbc_batch_t *b, int slices) {
+    if (!b || slices < 0) return fail(DWBC_ERR_ARG, "set_host_slices: bad argument");
+    b->host_slices = slices;
+    return DWBC_OK;
+}
+
 int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, const double *qdot_host, const double *fstar_host,
                           const uint8_t *flags_host, double *tau_grav_host, double *tau_task_host, double *tau_contact_host,
                           int32_t *status_host, void *stream) {
     if (!b || !q_host || !qdot_host || !flags_host) return fail(DWBC_ERR_ARG, "cycle_host: null argument");
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t B = b->B, n = b->w.n, m = b->w.m;
+    const size_t B = b->B, n = b->w.n, m = b->w.m, nc = b->cfg.ncontact;
     const bool need_tasks = (stages & (DWBC_SOLVE_TASK | DWBC_SOLVE_HQP)) != 0;
     size_t ftot = 0;
     for (int l = 0; l < b->cfg.nlevels; l++) ftot += (size_t)b->cfg.tasks[l].dof * B;
@@ -679,33 +723,94 @@ int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, con
             b->d_fstar = (double *)raw;
             b->d_fstar_cap = ftot;
         }
-        CK(cudaMemcpyAsync(b->d_fstar, fstar_host, ftot * sizeof(double), cudaMemcpyHostToDevice, st));
     }
-    CK(cudaMemcpyAsync(b->d_q, q_host, sizeof(double) * B * (n + 1), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(b->d_qd, qdot_host, sizeof(double) * B * n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(b->d_flags, flags_host, B * b->cfg.ncontact, cudaMemcpyHostToDevice, st));
-    int rc = dwbc_batch_update_kinematics(b, b->d_q, b->d_qd, stream);
+    // everything that allocates or uploads the configuration happens before the batch is sliced
+    int rc = upload_cfg(b, st);
     if (rc) return rc;
-    rc = dwbc_batch_set_contact(b, b->d_flags, stream);
-    if (rc) return rc;
-    rc = dwbc_batch_calc_contact_constraint(b, stream);
-    if (rc) return rc;
+    if (stages & (DWBC_SOLVE_TASK | DWBC_SOLVE_HQP | DWBC_SOLVE_REDIST | DWBC_SOLVE_REDIST_ANALYTIC)) {
+        rc = alloc_tasks(b);
+        if (rc) return rc;
+    }
+    // slices of >= 4096 states, at most 8: the H2D of slice k+1 and the D2H of slice k-1 run under the kernels of slice k
+    int K = b->host_slices > 0 ? b->host_slices : (int)std::min<size_t>(8, B / 4096);
+    K = std::max(1, std::min<int>(K, (int)B));
+    if (K > 1 && !b->pipe_ready) {
+        for (int i = 0; i < 2; i++) {
+            CK(cudaStreamCreateWithFlags(&b->pipe_stream[i], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&b->pipe_join[i], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&b->pipe_fork, cudaEventDisableTiming));
+        b->pipe_ready = true;
+    }
+    if (K > 1) {
+        CK(cudaEventRecord(b->pipe_fork, st));
+        for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(b->pipe_stream[i], b->pipe_fork, 0));
+    }
+    const Work full = b->w;
+    const size_t per = (B + K - 1) / K;
+    rc = DWBC_OK;
+    for (int k = 0; k < K && rc == DWBC_OK; k++) {
+        const size_t s0 = (size_t)k * per, cnt = std::min(per, B - std::min(B, s0));
+        if (cnt == 0) break;
+        cudaStream_t sk = K > 1 ? b->pipe_stream[k & 1] : st;
+        b->w = slice_work(full, b->cfg, s0, (int)cnt);
+        b->B = (int)cnt;
+        rc = [&]() -> int {
+            if (need_tasks) {
+                size_t off = 0;
+                for (int l = 0; l < b->cfg.nlevels; l++) {
+                    const size_t t = b->cfg.tasks[l].dof;
+                    CK(cudaMemcpyAsync(b->d_fstar + off + s0 * t, fstar_host + off + s0 * t, cnt * t * sizeof(double), cudaMemcpyHostToDevice, sk));
+                    off += t * B;
+                }
+            }
+            CK(cudaMemcpyAsync(b->d_q + s0 * (n + 1), q_host + s0 * (n + 1), sizeof(double) * cnt * (n + 1), cudaMemcpyHostToDevice, sk));
+            CK(cudaMemcpyAsync(b->d_qd + s0 * n, qdot_host + s0 * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, sk));
+            CK(cudaMemcpyAsync(b->d_flags + s0 * nc, flags_host + s0 * nc, cnt * nc, cudaMemcpyHostToDevice, sk));
+            int r = dwbc_batch_update_kinematics(b, b->d_q + s0 * (n + 1), b->d_qd + s0 * n, sk);
+            if (r) return r;
+            r = dwbc_batch_set_contact(b, b->d_flags + s0 * nc, sk);
+            if (r) return r;
+            r = dwbc_batch_calc_contact_constraint(b, sk);
+            if (r) return r;
+            if (need_tasks) {
+                size_t off = 0;
+                for (int l = 0; l < b->cfg.nlevels; l++) {
+                    const size_t t = b->cfg.tasks[l].dof;
+                    r = dwbc_batch_set_task(b, l, b->d_fstar + off + s0 * t, nullptr, 0, sk);
+                    if (r) return r;
+                    off += t * B;
+                }
+            }
+            r = dwbc_batch_solve(b, stages, nullptr, nullptr, nullptr, nullptr, sk);
+            if (r) return r;
+            // results go to the host straight from the workspace records of the slice
+            if (tau_grav_host) CK(cudaMemcpyAsync(tau_grav_host + s0 * m, b->w.tau_grav, sizeof(double) * cnt * m, cudaMemcpyDeviceToHost, sk));
+            if (tau_task_host) CK(cudaMemcpyAsync(tau_task_host + s0 * m, b->w.tau_task, sizeof(double) * cnt * m, cudaMemcpyDeviceToHost, sk));
+            if (tau_contact_host) CK(cudaMemcpyAsync(tau_contact_host + s0 * m, b->w.tau_contact, sizeof(double) * cnt * m, cudaMemcpyDeviceToHost, sk));
+            if (status_host) CK(cudaMemcpyAsync(status_host + s0, b->w.status, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, sk));
+            return DWBC_OK;
+        }();
+    }
+    // back to the whole batch: the handle keeps describing all B states (get_matrix, diagnostics, later device-pointer calls)
+    b->w = full;
+    b->B = (int)B;
+    b->last_qd = b->d_qd;
     if (need_tasks) {
         size_t off = 0;
         for (int l = 0; l < b->cfg.nlevels; l++) {
-            rc = dwbc_batch_set_task(b, l, b->d_fstar + off, nullptr, 0, stream);
-            if (rc) return rc;
+            b->w.fstar[l] = b->d_fstar + off;
             off += (size_t)b->cfg.tasks[l].dof * B;
         }
     }
-    rc = dwbc_batch_solve(b, stages, b->d_tg, b->d_tt, b->d_tc, b->d_status, stream);
-    if (rc) return rc;
-    if (tau_grav_host) CK(cudaMemcpyAsync(tau_grav_host, b->d_tg, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st));
-    if (tau_task_host) CK(cudaMemcpyAsync(tau_task_host, b->d_tt, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st));
-    if (tau_contact_host) CK(cudaMemcpyAsync(tau_contact_host, b->d_tc, sizeof(double) * B * m, cudaMemcpyDeviceToHost, st));
-    if (status_host) CK(cudaMemcpyAsync(status_host, b->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    if (K > 1) {
+        for (int i = 0; i < 2; i++) {
+            cudaEventRecord(b->pipe_join[i], b->pipe_stream[i]);
+            cudaStreamWaitEvent(st, b->pipe_join[i], 0);
+        }
+    }
     CK(cudaStreamSynchronize(st));
-    return DWBC_OK;
+    return rc;
 }
 
 }  // extern "C"

@@ -164,3 +164,32 @@ def run_tight_torque_limit(make_rd, D, H, B, tl=45.0):
 
 def test_emul_tight_torque_limit():
     run_tight_torque_limit(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, lambda a: a, 6)
+
+
+def run_sliced_cycle_host(make_rd, D, B, variants):
+    """dwbc_batch_cycle_host cut into slices (copies of one slice under the kernels of another) returns bit for bit what the
+    unsliced call returns: ragged slice sizes, mixed support, shared and per-state custom Jacobian."""
+    q, qd, rng = synth_states(B, 11)
+    fs = synth_fstar(rng, B)
+    flags = np.ones((B, 2), dtype=np.uint8)
+    flags[::3, 1] = 0
+    flags[1::6, 0] = 0
+    Jp = posture_selector()
+    Jps = np.ascontiguousarray(np.broadcast_to(Jp, (B,) + Jp.shape))  # the same selector handed over per state
+    ALL = SOLVE_GRAV | SOLVE_HQP | SOLVE_REDIST
+    outs = []
+    for slices, per_state in variants:
+        rd = configure_product(make_rd(B), 2)
+        rd.set_task_space(2, D(np.zeros((B, 21))), D(Jps if per_state else Jp))
+        rd.set_host_slices(slices)
+        outs.append([np.array(a) for a in rd.cycle_host(ALL, q, qd, fs, flags)])
+        assert rd.batch == B and rd.get("A").shape[0] == B  # the handle describes the whole batch again afterwards
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
+    assert ((outs[0][3] & 1) == 1).all()
+    return (q, qd, fs, flags), outs[0]
+
+
+def test_emul_sliced_cycle_host():
+    run_sliced_cycle_host(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, 7, ((1, False), (3, True)))

@@ -258,6 +258,34 @@ def test_cycle_host_matches_device_calls():
     assert np.array_equal(tg, tg2) and np.array_equal(tt, tt2) and np.array_equal(tc, tc2) and np.array_equal(st, st2)
 
 
+def test_gpu_sliced_cycle_host():
+    """The pipelined (sliced, two-stream) dwbc_batch_cycle_host == the unsliced call == the staged device-pointer calls, bit for bit,
+    for ragged slices, mixed support and pinned host buffers; automatic slicing at a batch large enough to trigger it."""
+    from libdwbc_b200 import RobotDataBatch
+    from tests.test_emul_parity import run_sliced_cycle_host
+
+    make = lambda B: RobotDataBatch(URDF, B, 0)
+    (q, qd, fs, flags), out = run_sliced_cycle_host(make, T, 1031, ((1, False), (2, False), (7, True), (64, False)))
+    rd, staged = run_product(2, q, qd, fs, flags, ALL)
+    for a, b in zip(out, staged):
+        assert np.array_equal(a, b)
+    # automatic slicing (B >= 8192 -> 2 slices) with pinned buffers, against the unsliced call
+    B = 8192 + 40
+    q, qd, rng = synth_states(B, 12)
+    fs = synth_fstar(rng, B)
+    flags = np.ones((B, 2), dtype=np.uint8)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    args = (pin(q), pin(qd), pin(np.concatenate([f.reshape(-1) for f in fs])), pin(flags))
+    res = []
+    for slices in (0, 1):
+        rd = configure_product(make(B), 2)
+        rd.set_task_space(2, T(np.zeros((B, 21))), T(posture_selector()))
+        rd.set_host_slices(slices)
+        res.append([np.array(a) for a in rd.cycle_host(ALL, *args)])
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+
+
 def test_error_behaviour():
     """Call-order and argument errors are reported, not silently ignored (reference prints and returns:
     src/dwbc.cpp:282-296, 407-411, 664-671)."""
