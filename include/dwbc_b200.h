@@ -286,7 +286,7 @@ int dwbc_batch_get_torque_command_f32(dwbc_batch_t *b, float *out_dev, void *str
 int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, const double *qdot_host, const double *fstar_host,
                           const uint8_t *flags_host, double *tau_grav_host, double *tau_task_host, double *tau_contact_host,
                           int32_t *status_host, void *stream);
-/* Number of slices dwbc_batch_cycle_host cuts the batch into: 0 = automatic (one per 4096 states, at most 8), 1 = no slicing. */
+/* Number of slices dwbc_batch_cycle_host cuts the batch into: 0 = automatic (one per 4096 states, at most 16), 1 = no slicing. */
 int dwbc_batch_set_host_slices(dwbc_batch_t *b, int slices);
 
 /* ---- diagnostics ---- */

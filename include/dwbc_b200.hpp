@@ -117,6 +117,7 @@ public:
                    double *torque_contact, int32_t *status) {
         ck(dwbc_batch_cycle_host(batch_, stages, q, qdot, fstar, flags, torque_grav, torque_task, torque_contact, status, stream_), "CycleHost");
     }
+    void SetHostSlices(int slices) { ck(dwbc_batch_set_host_slices(batch_, slices), "SetHostSlices"); }  // 0 = automatic, 1 = unsliced
     dwbc_batch_t *handle() { return batch_; }
 
 private:

@@ -731,8 +731,8 @@ int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, con
         rc = alloc_tasks(b);
         if (rc) return rc;
     }
-    // slices of >= 4096 states, at most 8: the H2D of slice k+1 and the D2H of slice k-1 run under the kernels of slice k
-    int K = b->host_slices > 0 ? b->host_slices : (int)std::min<size_t>(8, B / 4096);
+    // slices of >= 4096 states, at most 16 (measured: profiles/r01_host_slices.json): the H2D of slice k+1 and the D2H of slice k-1 run under the kernels of slice k
+    int K = b->host_slices > 0 ? b->host_slices : (int)std::min<size_t>(16, B / 4096);
     K = std::max(1, std::min<int>(K, (int)B));
     if (K > 1 && !b->pipe_ready) {
         for (int i = 0; i < 2; i++) {

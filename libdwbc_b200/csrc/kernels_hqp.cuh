@@ -804,7 +804,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
 
 // One CTA (team) per state: QP assembly (U, Atemp U, right-hand sides), the active-set iterations (gi_solve) and the torque
 // updates all use every thread of the team.
-__global__ void __launch_bounds__(TEAM, 6) hqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int redist,
+__global__ void __launch_bounds__(TEAM, 7) hqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int redist,
                                                       int nvmax) {
     DWBC_DYN_SMEM(smem);
     const int tid = t_id(), nt = t_n();
