@@ -126,6 +126,34 @@ struct ContactSmem {
     }
 };
 
+// Upper Cholesky factor G = R^T R of an r x r SPD matrix (r <= 7) by ONE warp: lane e owns entry (i, j), i <= j, e = j(j+1)/2 + i,
+// in a register; step k scales row k by 1/sqrt(g_kk) and applies g_ij -= R_ki R_kj (i > k) with two shuffles.  Per entry this is the
+// sequence  sacc = fma(-R_ki, R_kj, sacc), k ascending, then sqrt or the division  of the scalar loop it replaces.
+// Returns false if a pivot is not positive (that pivot is replaced by 1, like the scalar loop).  All 32 lanes must call it.
+__device__ __forceinline__ bool wchol_upper_packed(int r, double *G, int ldg, int lane) {
+    int j = 0;
+    while ((j + 1) * (j + 2) / 2 <= lane) j++;
+    const int i = lane - j * (j + 1) / 2;
+    const bool own = lane < r * (r + 1) / 2;
+    double g = own ? G[i + j * ldg] : 0.0;
+    bool ok = true;
+    for (int k = 0; k < r; k++) {
+        double d2 = __shfl_sync(DWBC_FULL, g, k * (k + 1) / 2 + k);
+        if (!(d2 > 1e-280)) {
+            d2 = 1.0;
+            ok = false;
+        }
+        const double d = sqrt(d2);
+        if (own && i == k) g = (j == k) ? d : g / d;
+        const bool below = own && i > k;
+        const double rki = __shfl_sync(DWBC_FULL, g, below ? i * (i + 1) / 2 + k : 0);
+        const double rkj = __shfl_sync(DWBC_FULL, g, below ? j * (j + 1) / 2 + k : 0);
+        if (below) g = fma(-rki, rkj, g);
+    }
+    if (own) G[i + j * ldg] = g;
+    return ok;
+}
+
 __global__ void __launch_bounds__(TEAM, 6) contact_dynamics_kernel(const DevModel *__restrict__ md, Work w) {
     DWBC_DYN_SMEM(smem);
     const int tid = t_id(), nt = t_n(), warp = tid >> 5, lane = lane_id();
@@ -215,7 +243,11 @@ __global__ void __launch_bounds__(TEAM, 6) contact_dynamics_kernel(const DevMode
                 }
             }
             tsync();
-            if (tid == 0) {
+            if (r <= 7) {
+                // r(r+1)/2 <= 28 entries: one lane per entry, factor in registers (the one-thread loop below held three warps at
+                // the barrier for ~12 % of the kernel); same fma order per entry, so the factor is bit-identical
+                if (warp == 0 && !wchol_upper_packed(r, Aug, lda, lane) && lane == 0) s_ok = 0;
+            } else if (tid == 0) {
                 for (int j = 0; j < r; j++)
                     for (int i = 0; i <= j; i++) {
                         double sacc = Aug[i + j * lda];
