@@ -205,9 +205,15 @@ __global__ void __launch_bounds__(TEAM, 6) contact_dynamics_kernel(const DevMode
         tcopy(m, m, P + 6 + 6 * ldn, ldn, w.W + s * m * m, m);
     }
     // u = (A^{-1}N_c)[6:, :] G   and   P_C = Jbar^T G
-    tgemv<false>(m, n, P + 6, ldn, Gs, [&](int i, double v) { u[i] = v; });
-    tgemv<false>(c, n, Jbar, ldc, Gs, [&](int i, double v) { w.PC[s * CMAX + i] = v; });
-    for (int i = c + tid; i < CMAX; i += nt) w.PC[s * CMAX + i] = 0.0;
+    // With a null space to build (r > 0) warp 0 runs the one-warp Gauss-Jordan steps below while the other warps do the
+    // independent products / copies of the same phase; without one the whole team does them.
+    const bool split = r > 0 && nt >= 64;
+    const int stid = split ? tid - 32 : tid, snt = split ? nt - 32 : nt;
+    if (!(split && warp == 0)) {
+        tgemv<false>(m, n, P + 6, ldn, Gs, [&](int i, double v) { u[i] = v; }, stid, snt);
+        tgemv<false>(c, n, Jbar, ldc, Gs, [&](int i, double v) { w.PC[s * CMAX + i] = v; }, stid, snt);
+        for (int i = c + stid; i < CMAX; i += snt) w.PC[s * CMAX + i] = 0.0;
+    }
     double *Wblk = P + 6 + 6 * ldn;  // view of W inside P, leading dimension ldn
     const int lda = 13;
     if (r > 0) {
@@ -302,6 +308,10 @@ __global__ void __launch_bounds__(TEAM, 6) contact_dynamics_kernel(const DevMode
             const double cond2 = wgauss_jordan(r, r, Aug, lda);
             if (!(cond2 > 1e-14) && lane == 0) s_ok = 0;
         }
+        if (!(split && warp == 0)) {  // W^+ is final: its copy and tau_g = W^+ u do not wait for Mx^{-1}
+            tcopy(m, m, Wblk, ldn, w.Winv + s * m * m, m, stid, snt);
+            tgemv<false>(m, m, Wblk, ldn, u, [&](int i, double v) { w.tau_grav[s * m + i] = v; }, stid, snt);
+        }
         tsync();
         double *g = w.NwJw + s * m * RMAX;
         tgemm<1, 2, false, false>(m, r, r, V, ldm, Aug + r * lda, lda, [&](int i, int j, double v) { g[i + j * m] = v; });
@@ -310,10 +320,10 @@ __global__ void __launch_bounds__(TEAM, 6) contact_dynamics_kernel(const DevMode
         double *g = w.NwJw + s * m * RMAX;
         for (int e = tid; e < m * RMAX; e += nt) g[e] = 0.0;
         tsync();
+        tcopy(m, m, Wblk, ldn, w.Winv + s * m * m, m);
+        // tau_g = W^+ u
+        tgemv<false>(m, m, Wblk, ldn, u, [&](int i, double v) { w.tau_grav[s * m + i] = v; });
     }
-    tcopy(m, m, Wblk, ldn, w.Winv + s * m * m, m);
-    // tau_g = W^+ u
-    tgemv<false>(m, m, Wblk, ldn, u, [&](int i, double v) { w.tau_grav[s * m + i] = v; });
     tsync();
     if (tid == 0) w.status[s] = s_ok ? 1 : 0;
 }

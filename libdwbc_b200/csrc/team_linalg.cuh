@@ -21,8 +21,9 @@ __device__ __forceinline__ int t_n() { return (int)blockDim.x; }
 __device__ __forceinline__ void tsync() { __syncthreads(); }
 
 // Cooperative copy of a column-major rows x cols block (global or shared on either side).
-__device__ __forceinline__ void tcopy(int rows, int cols, const double *__restrict__ src, int lds, double *__restrict__ dst, int ldd) {
-    const int tid = t_id(), nt = t_n();
+// (tid, nt): the threads taking part, numbered 0..nt-1 -- the whole team by default, or a sub-team of whole warps.
+__device__ __forceinline__ void tcopy(int rows, int cols, const double *__restrict__ src, int lds, double *__restrict__ dst, int ldd, int tid = t_id(),
+                                      int nt = t_n()) {
     if (lds == rows && ldd == rows) {
         for (int e = tid; e < rows * cols; e += nt) dst[e] = src[e];
     } else {
@@ -189,9 +190,11 @@ __device__ __forceinline__ void tgemm_mma(int M, int N, int K, const double *A, 
 
 // y(i) <- epi(i, sum_k opA(i,k) x(k)).  Four adjacent lanes share one row (each takes every 4th k) and combine with
 // two shuffles, so a 33..39-row product keeps the whole team busy.  Requires blockDim.x to be a multiple of 32.
+// (tid, nt) as in tcopy: a sub-team of whole warps gives the same sums (the split of k over the four lanes does not change).
 template <bool TA, class Epi>
-__device__ __forceinline__ void tgemv(int M, int K, const double *__restrict__ A, int lda, const double *__restrict__ x, Epi epi) {
-    const int tid = t_id(), rows_per_pass = t_n() >> 2, part = tid & 3;
+__device__ __forceinline__ void tgemv(int M, int K, const double *__restrict__ A, int lda, const double *__restrict__ x, Epi epi, int tid = t_id(),
+                                      int nt = t_n()) {
+    const int rows_per_pass = nt >> 2, part = tid & 3;
     for (int r0 = 0; r0 < M; r0 += rows_per_pass) {
         const int i = r0 + (tid >> 2);
         const bool act = i < M;
