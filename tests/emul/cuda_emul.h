@@ -13,7 +13,7 @@
 #ifndef DWBC_CPU_EMUL
 #error "cuda_emul.h is only for the emulation build"
 #endif
-#include <barrier>
+#include <pthread.h>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -46,13 +46,23 @@ enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpy
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
 
 namespace emul {
+// Blocking barrier (futex wait, no spinning): a block is 128 host threads on a handful of cores, and std::barrier's
+// spin-then-yield phase turned every __syncthreads into a scheduler storm (sys time 3x the user time, run time at the mercy of
+// whatever else the host was doing).
+struct Barrier {
+    pthread_barrier_t b;
+    explicit Barrier(int n) { pthread_barrier_init(&b, nullptr, (unsigned)n); }
+    ~Barrier() { pthread_barrier_destroy(&b); }
+    Barrier(const Barrier &) = delete;
+    void arrive_and_wait() { pthread_barrier_wait(&b); }
+};
 struct WarpCtx {
-    std::barrier<> bar;
+    Barrier bar;
     unsigned long long slot[32];
     explicit WarpCtx(int n) : bar(n) {}
 };
 struct BlockCtx {
-    std::barrier<> bar;
+    Barrier bar;
     std::vector<std::unique_ptr<WarpCtx>> warps;
     std::vector<char> smem;
     BlockCtx(int nthreads, size_t smem_bytes) : bar(nthreads), smem(smem_bytes + 64) {
