@@ -192,4 +192,4 @@ def run_sliced_cycle_host(make_rd, D, B, variants):
 
 
 def test_emul_sliced_cycle_host():
-    run_sliced_cycle_host(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, 7, ((1, False), (3, True)))
+    run_sliced_cycle_host(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, 4, ((1, False), (3, True)))
