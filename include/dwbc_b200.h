@@ -71,7 +71,8 @@ enum {
 enum {
     DWBC_ST_CONTACT_OK = 1,   /* CalcContactConstraint */
     DWBC_ST_TASK_OK = 2,      /* CalcTaskControlTorque */
-    DWBC_ST_REDIST_OK = 4     /* CalcContactRedistribute */
+    DWBC_ST_REDIST_OK = 4,    /* CalcContactRedistribute */
+    DWBC_ST_QP_SLOW = 16      /* diagnostic: a QP's proximal-point loop stopped at its iteration cap (the feasible iterate was kept) */
 };
 
 /* matrices retrievable with dwbc_batch_get_matrix (public RobotData fields of the reference) */

@@ -168,6 +168,9 @@ class RobotDataBatch:
     def clear_task_space(self):
         self._ck(self.L.dwbc_batch_clear_tasks(self._h))
         self.task_dofs = []
+        # the C side drops the gains / trajectory pointers of the removed task links: drop the buffers kept alive for them
+        for k in [k for k in self._keep if isinstance(k, tuple) and k[0] in ("trajp", "trajr", "f", "J")]:
+            del self._keep[k]
 
     def set_torque_limit(self, tlim):
         a = np.ascontiguousarray(np.broadcast_to(np.asarray(tlim, dtype=np.float64), (self.model_dof_,)))
@@ -408,16 +411,49 @@ class RobotDataBatch:
         self._ck(self.L.dwbc_batch_set_host_slices(self._h, int(slices)))
 
     def cycle_host(self, stages, q, qdot, fstars, flags, out=None):
-        """H2D + all stages + D2H through dwbc_batch_cycle_host.  All arguments are host arrays (numpy)."""
-        B, m = self.batch, self.model_dof_
+        """H2D + all stages + D2H through dwbc_batch_cycle_host.  All arguments are host arrays (numpy or torch CPU tensors):
+        q [B, n+1] float64, qdot [B, n] float64, fstars one [B, t_l] float64 array per level (or their concatenation), flags
+        [B, ncontact] uint8.  Wrong dtypes are converted, wrong shapes raise: the C side reads raw pointers."""
+        B, m, n = self.batch, self.model_dof_, self.system_dof_
 
-        def hp(a):
-            return C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
+        def host(a, dtype, shape, what):
+            if not isinstance(a, np.ndarray):
+                a = a.numpy() if hasattr(a, "numpy") else np.asarray(a)
+            if a.dtype != dtype and dtype == np.uint8 and a.dtype not in (np.bool_, np.int8, np.int32, np.int64):
+                raise DwbcError(f"cycle_host: {what} must be an integer / bool array")
+            a = np.ascontiguousarray(a, dtype=dtype)
+            if a.size != int(np.prod(shape)):
+                raise DwbcError(f"cycle_host: {what} has {a.size} entries, expected {shape}")
+            return a
 
+        q = host(q, np.float64, (B, n + 1), "q")
+        qdot = host(qdot, np.float64, (B, n), "qdot")
+        flags = host(flags, np.uint8, (B, self.ncontact), "flags")
+        fcat = None
+        if fstars is not None and not (isinstance(fstars, (list, tuple)) and len(fstars) == 0):
+            dofs = list(self.task_dofs)
+            if isinstance(fstars, (list, tuple)):
+                if len(fstars) != len(dofs):
+                    raise DwbcError(f"cycle_host: {len(fstars)} f* arrays for {len(dofs)} hierarchy levels")
+                fcat = np.concatenate([host(f, np.float64, (B, dofs[l]), f"fstar[{l}]").reshape(-1) for l, f in enumerate(fstars)])
+            else:
+                fcat = host(fstars, np.float64, (B * sum(dofs),), "fstar")
         if out is None:
             out = (np.empty((B, m)), np.empty((B, m)), np.empty((B, m)), np.empty((B,), dtype=np.int32))
         tg, tt, tc, st = out
-        fcat = fstars if not isinstance(fstars, (list, tuple)) else (np.concatenate([np.ascontiguousarray(f).reshape(-1) for f in fstars]) if fstars else None)
-        self._ck(self.L.dwbc_batch_cycle_host(self._h, int(stages), hp(q), hp(qdot), hp(fcat) if fcat is not None else None, hp(flags),
+        for a, dt, sh, what in ((tg, np.float64, B * m, "tau_grav out"), (tt, np.float64, B * m, "tau_task out"),
+                                (tc, np.float64, B * m, "tau_contact out"), (st, np.int32, B, "status out")):
+            if a is None:
+                continue
+            an = a if isinstance(a, np.ndarray) else a.numpy()
+            if an.dtype != dt or an.size != sh or not an.flags["C_CONTIGUOUS"]:
+                raise DwbcError(f"cycle_host: {what} must be a contiguous {np.dtype(dt).name} array with {sh} entries")
+
+        def hp(a):
+            if a is None:
+                return None
+            return C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
+
+        self._ck(self.L.dwbc_batch_cycle_host(self._h, int(stages), hp(q), hp(qdot), hp(fcat), hp(flags),
                                              hp(tg), hp(tt), hp(tc), hp(st), self.be.stream()))
         return tg, tt, tc, st

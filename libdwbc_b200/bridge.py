@@ -56,12 +56,24 @@ class RlWBCBridgeBatch:
         self.rd_.update_kinematics_mujoco(qpos, qvel)
 
     def SetContact(self, left, right):
-        """left / right: bool (all environments) or per-environment arrays / tensors [B]."""
+        """left / right: bool (all environments) or per-environment arrays / tensors [B].  Device tensors stay on the device: the
+        [B, 2] uint8 flag array is assembled there (no D2H + H2D round trip on the RL step path)."""
         rd, be = self.rd_, self.rd_.be
-        fl = np.empty((self.num_envs, 2), dtype=np.uint8)
-        for k, v in enumerate((left, right)):
-            fl[:, k] = be.to_numpy(v).astype(np.uint8) if hasattr(v, "shape") and not isinstance(v, np.ndarray) else np.asarray(v, dtype=np.uint8)
-        self._flags = be.from_numpy(fl) if not isinstance(self._flags, np.ndarray) else fl
+        torch = getattr(be, "torch", None)
+        on_dev = torch is not None and any(isinstance(v, torch.Tensor) and v.is_cuda for v in (left, right))
+        if on_dev:
+            cols = []
+            for v in (left, right):
+                if isinstance(v, torch.Tensor):
+                    cols.append(v.to(device=be.device).reshape(self.num_envs).ne(0).to(torch.uint8))
+                else:
+                    cols.append(torch.full((self.num_envs,), 1 if v else 0, dtype=torch.uint8, device=be.device))
+            self._flags = torch.stack(cols, dim=1).contiguous()
+        else:
+            fl = np.empty((self.num_envs, 2), dtype=np.uint8)
+            for k, v in enumerate((left, right)):
+                fl[:, k] = np.asarray(be.to_numpy(v) if hasattr(v, "shape") and not isinstance(v, np.ndarray) else v).astype(np.uint8).reshape(-1)
+            self._flags = be.from_numpy(fl)
         rd.set_contact(self._flags)
         rd.calc_contact_constraint()  # + CalcTaskSpace: done inside solve()
 

@@ -3,6 +3,7 @@
 #include "../../include/dwbc_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -91,7 +92,7 @@ struct dwbc_batch {
 
 namespace {
 thread_local std::string g_err;
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -218,7 +219,7 @@ void free_tasks(dwbc_batch *b) {
 extern "C" {
 
 const char *dwbc_last_error(void) { return g_err.c_str(); }
-long long dwbc_launch_count(void) { return g_launches; }
+long long dwbc_launch_count(void) { return g_launches.load(); }
 
 dwbc_model_t *dwbc_model_load_urdf(const char *urdf_path, int floating) {
     if (!urdf_path) {
@@ -375,6 +376,7 @@ int dwbc_batch_add_task(dwbc_batch_t *b, int level, int task_mode, int link, con
     TaskCfg &t = c.tasks[level];
     if (t.custom) return fail(DWBC_ERR_ARG, "add_task: level holds a custom task");
     if (t.dof + dof > MAX_TASK_DOF) return fail(DWBC_ERR_LIMIT, "add_task: task dof exceeds MAX_TASK_DOF");
+    b->traj[t.link_start + t.link_count] = dwbc_batch::TrajHost();  // a (re)assigned slot starts without gains / trajectories
     TaskLinkCfg &tl = c.tlinks[t.link_start + t.link_count++];
     tl.mode = task_mode;
     tl.link = link;
@@ -405,6 +407,7 @@ int dwbc_batch_add_custom_task(dwbc_batch_t *b, int level, int task_dof) {
 int dwbc_batch_clear_tasks(dwbc_batch_t *b) {
     if (!b) return fail(DWBC_ERR_ARG, "clear_tasks: null handle");
     b->cfg.nlevels = 0;
+    for (auto &t : b->traj) t = dwbc_batch::TrajHost();  // gains / trajectory pointers belong to the task links that are gone
     b->cfg_dirty = true;
     free_tasks(b);
     return DWBC_OK;
@@ -522,10 +525,10 @@ int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *
         CK(cudaFuncSetAttribute(task_space_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelScope ks(b, DWBC_K_TASK, st);
         DWBC_LAUNCH(task_space_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0, 0);
-    } else {
-        CK(cudaMemsetAsync(b->w.tau_task, 0, sizeof(double) * B * m, st));
-        CK(cudaMemsetAsync(b->w.tau_contact, 0, sizeof(double) * B * m, st));
     }
+    // Without DWBC_SOLVE_TASK torque_task_ / torque_contact_ keep the values of the previous call: the reference's split order
+    // CalcTaskControlTorque(true) then CalcContactRedistribute(true) feeds torque_grav_ + torque_task_ + torque_contact_ into the
+    // redistribution (reference src/dwbc.cpp:1372-1375).  The workspace is zero-initialised, task_space_kernel clears both.
     if (stages & (DWBC_SOLVE_HQP | DWBC_SOLVE_REDIST)) {
         int nvmax = RMAX > 0 ? RMAX : 1;
         if (stages & DWBC_SOLVE_HQP)
@@ -655,6 +658,7 @@ int dwbc_batch_get_active_set(dwbc_batch_t *b, int level, uint32_t *out_dev, voi
     if (!b || !out_dev) return fail(DWBC_ERR_ARG, "get_active_set: null argument");
     if (level >= b->cfg.nlevels || level < -1) return fail(DWBC_ERR_ARG, "get_active_set: level out of range");
     if (level >= 0 && !b->tasks_allocated) return fail(DWBC_ERR_ORDER, "get_active_set: no QP has been solved yet");
+    CK(cudaSetDevice(b->device));
     const uint32_t *src = level < 0 ? b->w.active[MAX_LEVELS] : b->w.active[level];
     CK(cudaMemcpyAsync(out_dev, src, sizeof(uint32_t) * (size_t)b->B * ACTIVE_WORDS, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return DWBC_OK;
@@ -662,6 +666,7 @@ int dwbc_batch_get_active_set(dwbc_batch_t *b, int level, uint32_t *out_dev, voi
 
 int dwbc_batch_get_qp_iterations(dwbc_batch_t *b, int32_t *out_dev, void *stream) {
     if (!b || !out_dev) return fail(DWBC_ERR_ARG, "get_qp_iterations: null argument");
+    CK(cudaSetDevice(b->device));
     CK(cudaMemcpyAsync(out_dev, b->w.qp_iters, sizeof(int32_t) * (size_t)b->B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return DWBC_OK;
 }

@@ -591,6 +591,7 @@ __device__ __noinline__ bool gi_warm(double *sm, int n, int m, int nvmax, int mt
 struct LevelOut {
     int status;
     int iters;
+    int slow;  // 1: the proximal-point loop stopped at its iteration cap; the last (primal-feasible) iterate was kept
 };
 
 // Solves one QP (t task variables first, then r contact variables) with the whole team.  U (m x nv), AU (nc x nv) and b (rows)
@@ -603,7 +604,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
     double *tolv = sm + L.tol, *rin = sm + L.rin;
     const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
     const int nv = t + r, mc = mt + nc;
-    LevelOut out{1, 0};
+    LevelOut out{1, 0, 0};
     const QpView V{sm + L.U, sm + L.AU, L.ldm, L.ldc, m, mt, nc, 0, nv};
     double *xj = S.xj, *xs = S.xs, *xp = S.xp;
     tsync();
@@ -748,7 +749,10 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
                 break;
             }
         }
-        if (out.status && !conv) out.status = 0;
+        // Every proximal iterate is primal feasible and the sequence decreases |x_t| monotonically: a state that has not met the
+        // 1e-12 step test within the cap keeps its last iterate (qpOASES, with nWSR = 1000, would also return a point for a
+        // feasible problem; reference src/dwbc.cpp:1080) and is flagged DWBC_ST_QP_SLOW instead of being reported as failed.
+        if (out.status && !conv) out.slow = 1;
         if (out.status) {
             // ---- C: min |x_c|^2 on the optimal face; rows with a positive multiplier are pinned ----
             const double umax = warp_max(lane < g.q ? S.u[lane] : 0.0);  // identical in every warp
@@ -949,6 +953,7 @@ __global__ void __launch_bounds__(TEAM, 7) hqp_kernel(const DevModel *__restrict
             tsync();
             const LevelOut lo = solve_level(sm, n, m, nvmax, t, r, mt, nc, w.active[lev ? q : MAX_LEVELS] + s * ACTIVE_WORDS);
             total_iters += lo.iters;
+            if (lo.slow) st |= 16;
             solved = lo.status != 0;
             have_x = solved;
         }

@@ -193,3 +193,27 @@ def run_sliced_cycle_host(make_rd, D, B, variants):
 
 def test_emul_sliced_cycle_host():
     run_sliced_cycle_host(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, 4, ((1, False), (3, True)))
+
+
+def test_emul_split_call_order_equals_fused():
+    """The reference's split order -- CalcGravCompensation, CalcTaskControlTorque(true), CalcContactRedistribute(true) as three
+    calls (tests/dwbc_test.cpp:100-130) -- must give the torques of the fused solve: the redistribution reads
+    torque_grav_ + torque_task_ + torque_contact_ left by the earlier calls (reference src/dwbc.cpp:1372-1375)."""
+    B = 3
+    q, qd, rng = synth_states(B, 20242)
+    fs = synth_fstar(rng, B)
+    fs[0][0, 1] = 4.0
+    flags = np.ones((B, 2), dtype=np.uint8)
+    rd, (tg, tt, tc, st) = run_product(2, q, qd, fs, flags, SOLVE_GRAV | SOLVE_HQP | SOLVE_REDIST)
+    tg, tt, tc, st = tg.copy(), tt.copy(), tc.copy(), st.copy()
+    rd2, _ = run_product(2, q, qd, fs, flags, SOLVE_GRAV)
+    _, tt2, tc_mid, _ = rd2.solve(SOLVE_GRAV | SOLVE_TASK | SOLVE_HQP)
+    tt2, tc_mid = tt2.copy(), tc_mid.copy()
+    tg3, tt3, tc3, st3 = rd2.solve(SOLVE_REDIST)
+    assert np.array_equal(st3 & 7, st & 7)
+    assert np.array_equal(tg3, tg) and np.array_equal(tt3, tt) and np.array_equal(tt2, tt)
+    assert np.array_equal(tc3, tc)
+    assert np.abs(tt).max() > 0 and np.abs(tc).max() > 0  # non-trivial torques: a wiped torque_task_ / torque_contact_ would show
+    # a lone gravity call afterwards leaves the task / contact torques in place
+    tg4, tt4, tc4, _ = rd2.solve(SOLVE_GRAV)
+    assert np.array_equal(tt4, tt) and np.array_equal(tc4, tc)
