@@ -290,6 +290,23 @@ int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, con
 /* Number of slices dwbc_batch_cycle_host cuts the batch into: 0 = automatic (one per 4096 states, at most 16), 1 = no slicing. */
 int dwbc_batch_set_host_slices(dwbc_batch_t *b, int slices);
 
+/* ---- output groups: which RobotData fields a cycle materialises in HBM ----
+ * DWBC_OUT_ALL      every public field of the reference's RobotData (A_, A_inv_, J_C, Lambda_contact, J_C_INV_T, A_inv_N_C, W, W_inv,
+ *                   V2, NwJw, per level J_task_, Lambda_task_, J_kt_, Null_task_, torque_h_ ...) is written for every state and can be
+ *                   read with dwbc_batch_get_matrix: ~110 KB of workspace and ~190 KB of HBM traffic per state and cycle.
+ * DWBC_OUT_TORQUES  torque_grav_ / torque_task_ / torque_contact_, status, f_star_qp_ / contact_qp_ / cf_redis_qp_ and the active sets
+ *                   only.  The staged calls (update_kinematics, set_contact, calc_contact_constraint, set_task) then only RECORD
+ *                   their arguments (the buffers must stay valid until dwbc_batch_solve returns) and dwbc_batch_solve runs the whole
+ *                   cycle of a state in one kernel with every intermediate matrix in shared memory, followed by the active-set QP
+ *                   kernel over the states whose QPs are active.  ~19 KB of workspace per state.  dwbc_batch_get_matrix of any other
+ *                   field returns DWBC_ERR_ORDER.  Models / hierarchies without a compiled specialisation of that kernel fall back to
+ *                   the generic kernels transparently (dwbc_batch_last_path tells which ran).
+ * DWBC_OUT_AUTO     (default) DWBC_OUT_ALL for the staged calls, DWBC_OUT_TORQUES inside dwbc_batch_cycle_host. */
+enum { DWBC_OUT_AUTO = -1, DWBC_OUT_TORQUES = 0, DWBC_OUT_ALL = 1 };
+int dwbc_batch_set_outputs(dwbc_batch_t *b, int outputs);
+/* 1 if the last dwbc_batch_solve / dwbc_batch_cycle_host ran the one-kernel cycle, 0 if it ran the generic kernels */
+int dwbc_batch_last_path(const dwbc_batch_t *b);
+
 /* ---- diagnostics ---- */
 /* Best DFMA-chain throughput (TFLOP/s, 2 flop per FMA) observed over ~`seconds` of back-to-back launches on
  * `device`: the FP64-pipe roofline denominator used by bench.py. */
@@ -298,7 +315,7 @@ int dwbc_probe_fp64(int device, double seconds, double *tflops);
  * recorded on the launch stream (no host synchronisation is added to the hot path).  dwbc_batch_get_kernel_times
  * synchronises the pending events and returns, per DWBC_K_* kernel, the summed duration in ms (only launches made while
  * profiling was on) and the launch count since the last reset.  bench.py's roofline numbers come from here. */
-enum { DWBC_K_RBD = 0, DWBC_K_AINV, DWBC_K_CONTACT_JAC, DWBC_K_CONTACT_DYN, DWBC_K_TASK, DWBC_K_HQP, DWBC_K_EXPORT, DWBC_K_POST, DWBC_K_REDUCED, DWBC_K_LQP, DWBC_K_COUNT };
+enum { DWBC_K_RBD = 0, DWBC_K_AINV, DWBC_K_CONTACT_JAC, DWBC_K_CONTACT_DYN, DWBC_K_TASK, DWBC_K_HQP, DWBC_K_EXPORT, DWBC_K_POST, DWBC_K_REDUCED, DWBC_K_LQP, DWBC_K_LEAN, DWBC_K_COUNT };
 int dwbc_batch_set_profiling(dwbc_batch_t *b, int enable);
 int dwbc_batch_get_kernel_times(dwbc_batch_t *b, double *ms_sum, long long *launches, int reset);
 const char *dwbc_kernel_name(int k);

@@ -9,12 +9,16 @@ compute call needs the CUDA library and a GPU and raises otherwise.
 from ._lib import DwbcError, library_path, load_library  # noqa: F401
 from .batch import (  # noqa: F401
     CONTACT_6D,
+    OUT_ALL,
+    OUT_AUTO,
+    OUT_TORQUES,
     SOLVE_GRAV,
     SOLVE_HQP,
     SOLVE_REDIST,
     SOLVE_REDIST_ANALYTIC,
     SOLVE_TASK,
     ST_CONTACT_OK,
+    ST_QP_SLOW,
     ST_REDIST_OK,
     ST_TASK_OK,
     TASK_LINK_6D,

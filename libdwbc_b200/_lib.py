@@ -76,6 +76,8 @@ def declare(L):
     L.dwbc_batch_calc_fstar.argtypes = [vp, C.c_int, vp, vp, vp]
     L.dwbc_batch_update_kinematics_mujoco.argtypes = [vp, vp, vp, vp]
     L.dwbc_batch_get_torque_command_f32.argtypes = [vp, vp, vp]
+    L.dwbc_batch_set_outputs.argtypes = [vp, C.c_int]
+    L.dwbc_batch_last_path.argtypes = [vp]
     return L
 
 
@@ -90,6 +92,7 @@ EXPORTS = [
     "dwbc_batch_get_reduced_matrix", "dwbc_batch_calc_control_torque_lqp", "dwbc_batch_calc_control_torque_lqp_r", "dwbc_batch_get_lqp", "dwbc_batch_get_lqp_iterations",
     "dwbc_batch_set_task_gain", "dwbc_batch_set_trajectory_quintic", "dwbc_batch_set_trajectory_rotation", "dwbc_batch_calc_fstar",
     "dwbc_batch_update_kinematics_mujoco", "dwbc_batch_get_torque_command_f32", "dwbc_batch_set_host_slices",
+    "dwbc_batch_set_outputs", "dwbc_batch_last_path",
 ]
 
 _lib = None

@@ -21,7 +21,8 @@ CONTACT_6D = 0
 (TASK_LINK_6D, TASK_LINK_6D_COM_FRAME, TASK_LINK_6D_CUSTOM_FRAME, TASK_LINK_POSITION, TASK_LINK_POSITION_COM_FRAME,
  TASK_LINK_POSITION_CUSTOM_FRAME, TASK_LINK_ROTATION, TASK_LINK_ROTATION_CUSTOM_FRAME) = range(8)
 SOLVE_GRAV, SOLVE_TASK, SOLVE_HQP, SOLVE_REDIST, SOLVE_REDIST_ANALYTIC = 1, 2, 4, 8, 16
-ST_CONTACT_OK, ST_TASK_OK, ST_REDIST_OK = 1, 2, 4
+ST_CONTACT_OK, ST_TASK_OK, ST_REDIST_OK, ST_QP_SLOW = 1, 2, 4, 16
+OUT_AUTO, OUT_TORQUES, OUT_ALL = -1, 0, 1
 
 # name -> (matrix id, per-level?)
 _MATS = {
@@ -393,13 +394,25 @@ class RobotDataBatch:
         self._ck(self.L.dwbc_batch_get_qp_iterations(self._h, self.be.ptr(buf), self.be.stream()))
         return buf
 
+    # ---- output groups ----
+    def set_outputs(self, outputs):
+        """dwbc_batch_set_outputs: OUT_ALL (every public RobotData field, generic kernels), OUT_TORQUES (torques + status only, the
+        one-kernel cycle; the staged calls then only record their arguments until solve()), OUT_AUTO (default)."""
+        self._ck(self.L.dwbc_batch_set_outputs(self._h, int(outputs)))
+
+    def last_path(self):
+        """1 if the last solve / cycle_host ran the one-kernel cycle (lean_cycle_kernel), 0 for the generic kernels"""
+        return self.L.dwbc_batch_last_path(self._h)
+
     # ---- per-kernel device timing (CUDA events recorded by the library around each of its launches) ----
     def set_profiling(self, enable=True):
         self._ck(self.L.dwbc_batch_set_profiling(self._h, 1 if enable else 0))
 
     def kernel_times(self, reset=True):
         """{kernel name: (summed ms while profiling was on, launches since the last reset)}"""
-        K = 10
+        K = 0
+        while self.L.dwbc_kernel_name(K):
+            K += 1
         ms = (C.c_double * K)()
         cnt = (C.c_longlong * K)()
         self._ck(self.L.dwbc_batch_get_kernel_times(self._h, ms, cnt, 1 if reset else 0))

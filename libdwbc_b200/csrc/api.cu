@@ -17,6 +17,7 @@
 #include "kernels_contact.cuh"
 #include "kernels_hqp.cuh"
 #include "kernels_io.cuh"
+#include "kernels_lean.cuh"
 #include "kernels_lqp.cuh"
 #include "kernels_post.cuh"
 #include "kernels_reduced.cuh"
@@ -39,13 +40,25 @@ struct dwbc_batch {
     Work w;
     std::vector<void *> allocs;
     std::vector<void *> task_allocs;
-    bool tasks_allocated = false;
-    double *d_scratch = nullptr;  // B*n*n doubles (N_C on request, staging)
+    bool tasks_allocated = false;  // tasks_level > 0
     // staging for the *_host entry point
-    double *d_q = nullptr, *d_qd = nullptr, *d_fstar = nullptr, *d_tg = nullptr, *d_tt = nullptr, *d_tc = nullptr;
+    double *d_q = nullptr, *d_qd = nullptr, *d_fstar = nullptr;
     uint8_t *d_flags = nullptr;
-    int32_t *d_status = nullptr;
     size_t d_fstar_cap = 0;
+    // Output groups (dwbc_batch_set_outputs).  -1 = automatic: the staged calls materialise every public RobotData field
+    // (DWBC_OUT_ALL), dwbc_batch_cycle_host produces torques + status only (DWBC_OUT_TORQUES).
+    int outputs = -1;
+    bool in_cycle_host = false;
+    bool full_allocated = false;  // the per-state matrices of DWBC_OUT_ALL (A_, A_inv_, J_C, Lambda_contact, A_inv_N_C, W, W_inv, V2, ...)
+    // DWBC_OUT_TORQUES: the staged calls only record their arguments; dwbc_batch_solve runs the whole cycle (kernels_lean.cuh)
+    const double *lean_q = nullptr, *lean_qd = nullptr;
+    const uint8_t *lean_flags = nullptr;
+    bool lean_kin_pending = false, lean_contact_pending = false;
+    int *d_list = nullptr, *d_count = nullptr;
+    size_t list_off = 0;  // dwbc_batch_cycle_host: the slice's part of d_list and its stream's counter
+    int count_slot = 0;
+    int last_path = 0;  // 1: the last solve ran lean_cycle_kernel, 0: the generic kernels
+    int tasks_level = 0;  // 0: no per-level buffers, 1: those of DWBC_OUT_TORQUES, 2: all
     // dwbc_batch_cycle_host pipelines slices of the batch over these streams (copies of one slice under the kernels of another)
     int host_slices = 0;  // 0 = automatic
     bool pipe_ready = false;
@@ -187,25 +200,46 @@ Work slice_work(const Work &f, const BatchCfg &cfg, size_t s0, int cnt) {
     return v;
 }
 
-int alloc_tasks(dwbc_batch *b) {
-    if (b->tasks_allocated) return DWBC_OK;
+// Per-level buffers.  full = false: what the torque path needs (Ntorque, f_star_qp_, contact_qp_, active sets);
+// full = true: every public per-level field (J_task_, Lambda_task_, J_kt_, Null_task_, torque_h_) as well.
+int alloc_tasks(dwbc_batch *b, bool full = true) {
+    const int want = full ? 2 : 1;
+    if (b->tasks_level >= want) return DWBC_OK;
     const size_t B = b->B, n = b->w.n, m = b->w.m;
     for (int l = 0; l < b->cfg.nlevels; l++) {
         const size_t t = b->cfg.tasks[l].dof;
-        if (!dev_alloc(b, &b->w.Jt[l], B * t * n, &b->task_allocs) || !dev_alloc(b, &b->w.Lamt[l], B * t * t, &b->task_allocs) ||
-            !dev_alloc(b, &b->w.Jkt[l], B * m * t, &b->task_allocs) || !dev_alloc(b, &b->w.Null[l], B * m * m, &b->task_allocs) ||
-            !dev_alloc(b, &b->w.Ntq[l], B * m * t, &b->task_allocs) || !dev_alloc(b, &b->w.fstar_qp[l], B * t, &b->task_allocs) ||
-            !dev_alloc(b, &b->w.contact_qp[l], B * RMAX, &b->task_allocs) || !dev_alloc(b, &b->w.torque_h[l], B * m, &b->task_allocs) ||
-            !dev_alloc(b, &b->w.active[l], B * ACTIVE_WORDS, &b->task_allocs))
+        if (b->tasks_level < 1 &&
+            (!dev_alloc(b, &b->w.Ntq[l], B * m * t, &b->task_allocs) || !dev_alloc(b, &b->w.fstar_qp[l], B * t, &b->task_allocs) ||
+             !dev_alloc(b, &b->w.contact_qp[l], B * RMAX, &b->task_allocs) || !dev_alloc(b, &b->w.active[l], B * ACTIVE_WORDS, &b->task_allocs)))
+            return DWBC_ERR_CUDA;
+        if (full && (!dev_alloc(b, &b->w.Jt[l], B * t * n, &b->task_allocs) || !dev_alloc(b, &b->w.Lamt[l], B * t * t, &b->task_allocs) ||
+                     !dev_alloc(b, &b->w.Jkt[l], B * m * t, &b->task_allocs) || !dev_alloc(b, &b->w.Null[l], B * m * m, &b->task_allocs) ||
+                     !dev_alloc(b, &b->w.torque_h[l], B * m, &b->task_allocs)))
             return DWBC_ERR_CUDA;
     }
+    b->tasks_level = want;
     b->tasks_allocated = true;
+    return DWBC_OK;
+}
+// The per-state matrices of DWBC_OUT_ALL, allocated when the generic kernels first run (a handle that only ever produces torques
+// keeps ~19 KB per state instead of ~110 KB).
+int ensure_full(dwbc_batch *b) {
+    if (b->full_allocated) return DWBC_OK;
+    Work &w = b->w;
+    const size_t B = w.B, n = w.n, mm = w.m, nb = w.nb;
+    const bool ok = dev_alloc(b, &w.A, B * n * n) && dev_alloc(b, &w.Ainv, B * n * n) && dev_alloc(b, &w.G, B * n) && dev_alloc(b, &w.Bnl, B * n) &&
+                    dev_alloc(b, &w.com, B * 16) && dev_alloc(b, &w.linkvel, B * nb * 6) && dev_alloc(b, &w.Jc, B * CMAX * n) &&
+                    dev_alloc(b, &w.Lam, B * CMAX * CMAX) && dev_alloc(b, &w.AinvNc, B * n * n) && dev_alloc(b, &w.W, B * mm * mm) &&
+                    dev_alloc(b, &w.Winv, B * mm * mm) && dev_alloc(b, &w.V2, B * RMAX * mm);
+    if (!ok) return DWBC_ERR_CUDA;
+    b->full_allocated = true;
     return DWBC_OK;
 }
 void free_tasks(dwbc_batch *b) {
     for (void *p : b->task_allocs) cudaFree(p);
     b->task_allocs.clear();
     b->tasks_allocated = false;
+    b->tasks_level = 0;
     for (int l = 0; l < MAX_LEVELS; l++) {
         b->w.Jt[l] = b->w.Lamt[l] = b->w.Jkt[l] = b->w.Null[l] = b->w.Ntq[l] = nullptr;
         b->w.fstar_qp[l] = b->w.contact_qp[l] = b->w.torque_h[l] = nullptr;
@@ -213,6 +247,92 @@ void free_tasks(dwbc_batch *b) {
         b->w.fstar[l] = b->w.jcustom[l] = nullptr;
         b->w.jcustom_per_state[l] = 0;
     }
+}
+
+// ---- DWBC_OUT_TORQUES: the one-kernel cycle (kernels_lean.cuh) ----
+inline bool lean_staged(const dwbc_batch *b) { return b->outputs == DWBC_OUT_TORQUES || (b->outputs < 0 && b->in_cycle_host); }
+
+#ifndef DWBC_LEAN_LDN
+#define DWBC_LEAN_LDN 44
+#endif
+
+template <class S>
+int launch_lean(dwbc_batch *b, int stages, cudaStream_t st) {
+    using L = LeanSmem<S>;
+    const size_t smem = sizeof(double) * L::total;
+    CK(cudaFuncSetAttribute(lean_cycle_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LeanArgs a{};
+    a.q = b->lean_q;
+    a.qd = b->lean_qd;
+    a.flags = b->lean_flags;
+    a.hqp = (stages & DWBC_SOLVE_HQP) ? 1 : 0;
+    a.redist = (stages & DWBC_SOLVE_REDIST) ? 1 : 0;
+    a.list = b->d_list + b->list_off;
+    a.count = b->d_count + b->count_slot;
+    CK(cudaMemsetAsync(a.count, 0, sizeof(int), st));
+    {
+        KernelScope ks(b, DWBC_K_LEAN, st);
+        DWBC_LAUNCH(lean_cycle_kernel<S>, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, a);
+    }
+    CK(cudaGetLastError());
+    if (stages & (DWBC_SOLVE_HQP | DWBC_SOLVE_REDIST)) {
+        // the states whose QPs are active (compact list written by the kernel above): one CTA each, CTAs beyond the count exit
+        int nvmax = RMAX > 0 ? RMAX : 1;
+        if (stages & DWBC_SOLVE_HQP)
+            for (int l = 0; l < b->cfg.nlevels; l++) nvmax = b->cfg.tasks[l].dof + RMAX > nvmax ? b->cfg.tasks[l].dof + RMAX : nvmax;
+        HqpSmem H(b->w.n, b->w.m, nvmax);
+        const size_t hs = sizeof(double) * H.total;
+        CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+        KernelScope ks(b, DWBC_K_HQP, st);
+        DWBC_LAUNCH(hqp_kernel, b->B, TEAM, hs, st, b->d_model, b->d_cfg, b->w, a.hqp, a.redist, nvmax, (const int *)a.list, (const int *)a.count);
+    }
+    CK(cudaGetLastError());
+    return DWBC_OK;
+}
+
+// Runs the whole cycle in lean_cycle_kernel when a specialisation exists for the handle's model and hierarchy and the stage set;
+// *done = false (and nothing launched) otherwise.
+int lean_which(const dwbc_batch *b, int stages) {
+    if (stages & DWBC_SOLVE_HQP) stages |= DWBC_SOLVE_TASK;
+    if (TEAM != 128) return -1;
+    if (stages & DWBC_SOLVE_REDIST_ANALYTIC) return -1;
+    if (b->w.nb != 34) return -1;  // TOCABI (33 joints); other models run the generic kernels
+    const bool tasks = (stages & DWBC_SOLVE_TASK) != 0;
+    const BatchCfg &c = b->cfg;
+    if ((stages & DWBC_SOLVE_REDIST) && !tasks && c.nlevels > 0) return -1;  // a lone redistribution reads torque_task_ of an earlier call
+    if (c.ncontact <= 0) return -1;
+    int d[MAX_LEVELS] = {0, 0, 0, 0};
+    const int nl = tasks ? c.nlevels : 0;
+    for (int l = 0; l < nl; l++) d[l] = c.tasks[l].dof;
+    auto is = [&](int n, int a0, int a1, int a2) { return nl == n && d[0] == a0 && d[1] == a1 && d[2] == a2; };
+    int which = -1;
+    if (is(0, 0, 0, 0)) which = 0;
+    else if (is(3, 3, 6, 21)) which = 1;
+    else if (is(2, 3, 3, 0)) which = 2;
+    else if (is(2, 6, 3, 0)) which = 3;
+    return which;
+}
+int try_lean_cycle(dwbc_batch *b, int stages, cudaStream_t st, bool *done) {
+    *done = false;
+    const int which = lean_which(b, stages);
+    if (which < 0) return DWBC_OK;
+    const bool tasks = (stages & DWBC_SOLVE_TASK) != 0;
+    int rc = upload_cfg(b, st);
+    if (rc) return rc;
+    if (tasks || (stages & DWBC_SOLVE_REDIST)) {
+        rc = alloc_tasks(b, false);
+        if (rc) return rc;
+    }
+    constexpr int LDN = DWBC_LEAN_LDN;
+    switch (which) {
+    case 0: rc = launch_lean<LeanSpec<34, LevelPack<>, LDN>>(b, stages, st); break;
+    case 1: rc = launch_lean<LeanSpec<34, LevelPack<3, 6, 21>, LDN>>(b, stages, st); break;
+    case 2: rc = launch_lean<LeanSpec<34, LevelPack<3, 3>, LDN>>(b, stages, st); break;
+    case 3: rc = launch_lean<LeanSpec<34, LevelPack<6, 3>, LDN>>(b, stages, st); break;
+    }
+    if (rc) return rc;
+    *done = true;
+    return DWBC_OK;
 }
 }  // namespace
 
@@ -274,17 +394,14 @@ dwbc_batch_t *dwbc_batch_create(const dwbc_model_t *m, int batch, int device) {
     w.m = b->hm.dev.m;
     w.nb = b->hm.dev.nb;
     const size_t B = batch, n = w.n, mm = w.m, nb = w.nb;
-    bool ok = dev_alloc(b, &b->d_model, 1) && dev_alloc(b, &b->d_cfg, 1) && dev_alloc(b, &w.A, B * n * n) && dev_alloc(b, &w.Ainv, B * n * n) &&
-              dev_alloc(b, &w.G, B * n) && dev_alloc(b, &w.Bnl, B * n) && dev_alloc(b, &w.pose, B * nb * POSE_STRIDE) &&
-              dev_alloc(b, &w.com, B * 16) && dev_alloc(b, &w.linkvel, B * nb * 6) && dev_alloc(b, &w.Jc, B * CMAX * n) &&
-              dev_alloc(b, &w.cdof, B) && dev_alloc(b, &w.cidx, B * MAX_ACTIVE_CONTACTS) && dev_alloc(b, &w.Lam, B * CMAX * CMAX) &&
-              dev_alloc(b, &w.Jbar, B * CMAX * n) && dev_alloc(b, &w.AinvNc, B * n * n) && dev_alloc(b, &w.W, B * mm * mm) &&
-              dev_alloc(b, &w.Winv, B * mm * mm) && dev_alloc(b, &w.V2, B * RMAX * mm) && dev_alloc(b, &w.NwJw, B * mm * RMAX) &&
-              dev_alloc(b, &w.PC, B * CMAX) && dev_alloc(b, &w.tau_grav, B * mm) && dev_alloc(b, &w.status, B) &&
-              dev_alloc(b, &w.tau_task, B * mm) && dev_alloc(b, &w.tau_contact, B * mm) && dev_alloc(b, &w.cf_redis, B * RMAX) &&
-              dev_alloc(b, &w.active[MAX_LEVELS], B * ACTIVE_WORDS) && dev_alloc(b, &w.qp_iters, B) && dev_alloc(b, &b->d_scratch, B * n * n) &&
+    (void)n;
+    bool ok = dev_alloc(b, &b->d_model, 1) && dev_alloc(b, &b->d_cfg, 1) && dev_alloc(b, &w.pose, B * nb * POSE_STRIDE) &&
+              dev_alloc(b, &w.cdof, B) && dev_alloc(b, &w.cidx, B * MAX_ACTIVE_CONTACTS) && dev_alloc(b, &w.Jbar, B * CMAX * n) &&
+              dev_alloc(b, &w.NwJw, B * mm * RMAX) && dev_alloc(b, &w.PC, B * CMAX) && dev_alloc(b, &w.tau_grav, B * mm) &&
+              dev_alloc(b, &w.status, B) && dev_alloc(b, &w.tau_task, B * mm) && dev_alloc(b, &w.tau_contact, B * mm) &&
+              dev_alloc(b, &w.cf_redis, B * RMAX) && dev_alloc(b, &w.active[MAX_LEVELS], B * ACTIVE_WORDS) && dev_alloc(b, &w.qp_iters, B) &&
               dev_alloc(b, &b->d_q, B * (n + 1)) && dev_alloc(b, &b->d_qd, B * n) && dev_alloc(b, &b->d_flags, B * MAX_CONTACTS) &&
-              dev_alloc(b, &b->d_tg, B * mm) && dev_alloc(b, &b->d_tt, B * mm) && dev_alloc(b, &b->d_tc, B * mm) && dev_alloc(b, &b->d_status, B);
+              dev_alloc(b, &b->d_list, B) && dev_alloc(b, &b->d_count, 4);
     if (ok) ok = cuda_ok(cudaMemcpy(b->d_model, &b->hm.dev, sizeof(DevModel), cudaMemcpyHostToDevice), "cudaMemcpy(model)");
     if (!ok) {
         dwbc_batch_destroy(b);
@@ -424,6 +541,23 @@ int dwbc_batch_update_kinematics(dwbc_batch_t *b, const double *q_dev, const dou
     if (!b || !q_dev || !qdot_dev) return fail(DWBC_ERR_ARG, "update_kinematics: null argument");
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (lean_staged(b)) {
+        // DWBC_OUT_TORQUES: nothing is computed before dwbc_batch_solve knows the whole cycle; q / qdot must stay valid until then
+        b->lean_q = q_dev;
+        b->lean_qd = qdot_dev;
+        b->lean_kin_pending = true;
+        b->lean_contact_pending = false;
+        b->have_kin = true;
+        b->last_qd = qdot_dev;
+        b->have_contact = b->have_cc = false;
+        b->have_red_dyn = b->have_red_cc = false;
+        return DWBC_OK;
+    }
+    {
+        const int rc = ensure_full(b);
+        if (rc) return rc;
+    }
+    b->lean_kin_pending = false;
     const int wpb = WARPS_PER_BLOCK, grid = grid_for(b->B, wpb);
     const int n = b->w.n;
     CK(cudaMemsetAsync(b->w.status, 0xff, sizeof(int) * b->B, st));  // "valid so far"; stages clear it on failure
@@ -454,6 +588,13 @@ int dwbc_batch_set_contact(dwbc_batch_t *b, const uint8_t *flags_dev, void *stre
     if (b->cfg.ncontact == 0) return fail(DWBC_ERR_ORDER, "set_contact: no contact registered");
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (b->lean_kin_pending) {  // DWBC_OUT_TORQUES: recorded, evaluated by dwbc_batch_solve
+        b->lean_flags = flags_dev;
+        b->lean_contact_pending = true;
+        b->have_contact = true;
+        b->have_cc = false;
+        return DWBC_OK;
+    }
     int rc = upload_cfg(b, st);
     if (rc) return rc;
     const int wpb = WARPS_PER_BLOCK, grid = grid_for(b->B, wpb);
@@ -473,6 +614,10 @@ int dwbc_batch_calc_contact_constraint(dwbc_batch_t *b, void *stream) {
     if (!b->have_contact) return fail(DWBC_ERR_ORDER, "calc_contact_constraint: call set_contact first");
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (b->lean_kin_pending) {
+        b->have_cc = true;
+        return DWBC_OK;
+    }
     ContactSmem L(b->w.n, b->w.m);
     size_t smem = sizeof(double) * L.total;
     CK(cudaFuncSetAttribute(contact_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -507,18 +652,40 @@ int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *
     if (rc) return rc;
     const size_t B = b->B, m = b->w.m;
     if (stages & DWBC_SOLVE_HQP) stages |= DWBC_SOLVE_TASK;
-    if (stages & (DWBC_SOLVE_TASK | DWBC_SOLVE_REDIST | DWBC_SOLVE_REDIST_ANALYTIC)) {
-        if (stages & DWBC_SOLVE_TASK) {
-            if (b->cfg.nlevels == 0) return fail(DWBC_ERR_ORDER, "solve: no task registered");
-            for (int l = 0; l < b->cfg.nlevels; l++)
-                if (!b->w.fstar[l]) return fail(DWBC_ERR_ORDER, "solve: set_task has not been called for every level");
+    if (stages & DWBC_SOLVE_TASK) {
+        if (b->cfg.nlevels == 0) return fail(DWBC_ERR_ORDER, "solve: no task registered");
+        for (int l = 0; l < b->cfg.nlevels; l++)
+            if (!b->w.fstar[l]) return fail(DWBC_ERR_ORDER, "solve: set_task has not been called for every level");
+    }
+    bool lean_done = false;
+    if (b->lean_kin_pending) {
+        if (!b->lean_contact_pending) return fail(DWBC_ERR_ORDER, "solve: call set_contact first");
+        rc = try_lean_cycle(b, stages, st, &lean_done);
+        if (rc) return rc;
+        if (!lean_done) {
+            // no specialisation of the one-kernel cycle for this model / hierarchy / stage set: run the generic kernels on the recorded inputs
+            b->lean_kin_pending = false;
+            const double *q = b->lean_q, *qd = b->lean_qd;
+            const uint8_t *fl = b->lean_flags;
+            const int keep = b->outputs;
+            const bool keep_host = b->in_cycle_host;
+            b->outputs = DWBC_OUT_ALL;
+            b->in_cycle_host = false;
+            rc = dwbc_batch_update_kinematics(b, q, qd, stream);
+            if (!rc) rc = dwbc_batch_set_contact(b, fl, stream);
+            if (!rc) rc = dwbc_batch_calc_contact_constraint(b, stream);
+            b->outputs = keep;
+            b->in_cycle_host = keep_host;
+            if (rc) return rc;
         }
+    }
+    b->last_path = lean_done ? 1 : 0;
+    if (!lean_done && (stages & (DWBC_SOLVE_TASK | DWBC_SOLVE_REDIST | DWBC_SOLVE_REDIST_ANALYTIC))) {
         rc = alloc_tasks(b);
         if (rc) return rc;
     }
+    if (lean_done) stages = 0;  // everything ran above; only the copies of the results are left
     if (stages & DWBC_SOLVE_TASK) {
-        int tmax = 1;
-        for (int l = 0; l < b->cfg.nlevels; l++) tmax = b->cfg.tasks[l].dof > tmax ? b->cfg.tasks[l].dof : tmax;
         TaskSmem L(b->w.n, b->w.m, b->cfg.tasks, b->cfg.nlevels);
         size_t smem = sizeof(double) * L.total;
         if (smem > 227 * 1024) return fail(DWBC_ERR_LIMIT, "solve: the task hierarchy does not fit the shared memory of one SM");
@@ -538,7 +705,7 @@ int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *
         CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelScope ks(b, DWBC_K_HQP, st);
         DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0,
-                    (stages & DWBC_SOLVE_REDIST) ? 1 : 0, nvmax);
+                    (stages & DWBC_SOLVE_REDIST) ? 1 : 0, nvmax, (const int *)nullptr, (const int *)nullptr);
     }
     if ((stages & DWBC_SOLVE_REDIST_ANALYTIC) && !(stages & DWBC_SOLVE_REDIST)) {
         const int wpb = WARPS_PER_BLOCK, grid = grid_for(b->B, wpb);
@@ -604,6 +771,13 @@ int dwbc_batch_get_matrix(dwbc_batch_t *b, int which, int level, double *out_dev
     if (cols) *cols = c;
     if (!out_dev) return DWBC_OK;
     const size_t bytes = sizeof(double) * (size_t)b->B * r * c;
+    const bool computed_on_request = which == DWBC_MAT_N_C || which == DWBC_MAT_COM || which == DWBC_MAT_LINK_POS || which == DWBC_MAT_LINK_ROT;
+    const bool torque_group = which == DWBC_MAT_TORQUE_GRAV || which == DWBC_MAT_TORQUE_TASK || which == DWBC_MAT_TORQUE_CONTACT ||
+                              which == DWBC_MAT_CF_REDIS || which == DWBC_MAT_FSTAR_QP || which == DWBC_MAT_CONTACT_QP;
+    if ((b->last_path == 1 || b->lean_kin_pending) && !torque_group)
+        return fail(DWBC_ERR_ORDER, "get_matrix: this field is not materialised with DWBC_OUT_TORQUES; call dwbc_batch_set_outputs(b, DWBC_OUT_ALL) before the cycle");
+    if (!computed_on_request && !src) return fail(DWBC_ERR_ORDER, "get_matrix: the field has not been computed yet");
+    if (computed_on_request && !b->full_allocated) return fail(DWBC_ERR_ORDER, "get_matrix: call update_kinematics first");
     if (src) {
         CK(cudaMemcpyAsync(out_dev, src, bytes, cudaMemcpyDeviceToDevice, st));
         return DWBC_OK;
@@ -621,8 +795,15 @@ int dwbc_batch_get_matrix(dwbc_batch_t *b, int which, int level, double *out_dev
     return DWBC_OK;
 }
 
+#define NEED_ALL(b, who)                                                                                                          \
+    do {                                                                                                                          \
+        if ((b)->lean_kin_pending || (b)->last_path == 1)                                                                         \
+            return fail(DWBC_ERR_ORDER, who ": needs the fields of DWBC_OUT_ALL (call dwbc_batch_set_outputs(b, DWBC_OUT_ALL) before the cycle)"); \
+    } while (0)
+
 int dwbc_batch_get_contact_force(dwbc_batch_t *b, const double *torque_dev, double *cf_dev, void *stream) {
     if (!b || !cf_dev) return fail(DWBC_ERR_ARG, "get_contact_force: null argument");
+    NEED_ALL(b, "get_contact_force");
     if (!b->have_cc) return fail(DWBC_ERR_ORDER, "get_contact_force: call calc_contact_constraint first");
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -639,6 +820,7 @@ int dwbc_batch_get_contact_force(dwbc_batch_t *b, const double *torque_dev, doub
 }
 int dwbc_batch_get_zmp(dwbc_batch_t *b, const double *cf_dev, double *zmp_dev, void *stream) {
     if (!b || !cf_dev || !zmp_dev) return fail(DWBC_ERR_ARG, "get_zmp: null argument");
+    NEED_ALL(b, "get_zmp");
     if (!b->have_cc) return fail(DWBC_ERR_ORDER, "get_zmp: call calc_contact_constraint first");
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -671,6 +853,16 @@ int dwbc_batch_get_qp_iterations(dwbc_batch_t *b, int32_t *out_dev, void *stream
     return DWBC_OK;
 }
 
+int dwbc_batch_set_outputs(dwbc_batch_t *b, int outputs) {
+    if (!b) return fail(DWBC_ERR_ARG, "set_outputs: null handle");
+    if (outputs != DWBC_OUT_AUTO && outputs != DWBC_OUT_TORQUES && outputs != DWBC_OUT_ALL) return fail(DWBC_ERR_ARG, "set_outputs: unknown output group");
+    b->outputs = outputs;
+    b->lean_kin_pending = b->lean_contact_pending = false;
+    b->have_kin = b->have_contact = b->have_cc = false;  // the next cycle starts from update_kinematics
+    return DWBC_OK;
+}
+int dwbc_batch_last_path(const dwbc_batch_t *b) { return b ? b->last_path : -1; }
+
 int dwbc_batch_set_profiling(dwbc_batch_t *b, int enable) {
     if (!b) return fail(DWBC_ERR_ARG, "set_profiling: null handle");
     b->profiling = enable != 0;
@@ -699,7 +891,7 @@ int dwbc_batch_get_kernel_times(dwbc_batch_t *b, double *ms_sum, long long *laun
 
 const char *dwbc_kernel_name(int k) {
     static const char *names[DWBC_K_COUNT] = {"rbd_kernel", "ainv_kernel", "contact_jacobian_kernel", "contact_dynamics_kernel",
-                                              "task_space_kernel", "hqp_kernel", "export_kernels", "post_kernels", "reduced_kernels", "lqp_kernel"};
+                                              "task_space_kernel", "hqp_kernel", "export_kernels", "post_kernels", "reduced_kernels", "lqp_kernel", "lean_cycle_kernel"};
     return (k >= 0 && k < DWBC_K_COUNT) ? names[k] : nullptr;
 }
 
@@ -732,8 +924,27 @@ int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, con
     // everything that allocates or uploads the configuration happens before the batch is sliced
     int rc = upload_cfg(b, st);
     if (rc) return rc;
+    b->in_cycle_host = true;
+    struct HostFlag {
+        dwbc_batch *b;
+        ~HostFlag() { b->in_cycle_host = false; }
+    } host_flag{b};
+    // The path is chosen once, before the batch is sliced (allocations must see the whole batch): the one-kernel cycle when the
+    // output group allows it and a specialisation exists, the generic kernels otherwise.
+    const bool lean = lean_staged(b) && lean_which(b, stages) >= 0;
+    const int keep_outputs = b->outputs;
+    struct OutputsGuard {
+        dwbc_batch *b;
+        int keep;
+        ~OutputsGuard() { b->outputs = keep; b->list_off = 0; b->count_slot = 0; }
+    } outputs_guard{b, keep_outputs};
+    b->outputs = lean ? DWBC_OUT_TORQUES : DWBC_OUT_ALL;
+    if (!lean) {
+        rc = ensure_full(b);
+        if (rc) return rc;
+    }
     if (stages & (DWBC_SOLVE_TASK | DWBC_SOLVE_HQP | DWBC_SOLVE_REDIST | DWBC_SOLVE_REDIST_ANALYTIC)) {
-        rc = alloc_tasks(b);
+        rc = alloc_tasks(b, !lean);
         if (rc) return rc;
     }
     // slices of >= 4096 states, at most 16 (measured: profiles/r01_host_slices.json): the H2D of slice k+1 and the D2H of slice k-1 run under the kernels of slice k
@@ -760,6 +971,8 @@ int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, con
         cudaStream_t sk = K > 1 ? b->pipe_stream[k & 1] : st;
         b->w = slice_work(full, b->cfg, s0, (int)cnt);
         b->B = (int)cnt;
+        b->list_off = s0;
+        b->count_slot = k & 1;
         rc = [&]() -> int {
             if (need_tasks) {
                 size_t off = 0;
@@ -880,6 +1093,7 @@ extern "C" {
 int dwbc_batch_reduced_dynamics(dwbc_batch_t *b, const uint8_t *pattern_host, void *stream) {
     if (!b || !pattern_host) return fail(DWBC_ERR_ARG, "reduced_dynamics: null argument");
     if (!b->have_contact) return fail(DWBC_ERR_ORDER, "reduced_dynamics: call update_kinematics and set_contact first");
+    NEED_ALL(b, "reduced_dynamics");
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
     const DevModel &md = b->hm.dev;
@@ -1105,7 +1319,7 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
             const int redist_now = ((stages & DWBC_SOLVE_REDIST) && k == c.nlevels) ? 2 : 0;
             if ((stages & DWBC_SOLVE_HQP) || redist_now) {
                 KernelScope ks(b, DWBC_K_HQP, st);
-                DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, b->wr, (stages & DWBC_SOLVE_HQP) ? 1 : 0, redist_now, nvmax);
+                DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, b->wr, (stages & DWBC_SOLVE_HQP) ? 1 : 0, redist_now, nvmax, (const int *)nullptr, (const int *)nullptr);
             }
         }
     }
@@ -1142,7 +1356,7 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
         CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
             KernelScope ks(b, DWBC_K_HQP, st);
-            DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgNC, q, 1, 0, nvmax);
+            DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgNC, q, 1, 0, nvmax, (const int *)nullptr, (const int *)nullptr);
         }
         {
             KernelScope ks(b, DWBC_K_REDUCED, st);
@@ -1176,7 +1390,7 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
         CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
             KernelScope ks(b, DWBC_K_HQP, st);
-            DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, d, 0, 2, nvmax);
+            DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, d, 0, 2, nvmax, (const int *)nullptr, (const int *)nullptr);
         }
         {
             KernelScope ks(b, DWBC_K_REDUCED, st);
@@ -1293,6 +1507,7 @@ int launch_lqp(dwbc_batch *b, bool reduced, double *y_dev, double *tau_dev, int3
 int dwbc_batch_calc_control_torque_lqp(dwbc_batch_t *b, double *y_dev, double *tau_dev, int32_t *status_dev, void *stream) {
     if (!b) return fail(DWBC_ERR_ARG, "calc_control_torque_lqp: null handle");
     if (!b->have_cc) return fail(DWBC_ERR_ORDER, "calc_control_torque_lqp: call calc_contact_constraint first");
+    NEED_ALL(b, "calc_control_torque_lqp");
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc = upload_cfg(b, st);
@@ -1399,6 +1614,7 @@ int dwbc_batch_set_trajectory_rotation(dwbc_batch_t *b, int level, int link_inde
 int dwbc_batch_calc_fstar(dwbc_batch_t *b, int level, const double *control_time_dev, double *fstar_dev, void *stream) {
     if (!b || !control_time_dev || !fstar_dev) return fail(DWBC_ERR_ARG, "calc_fstar: null argument");
     if (!b->have_kin) return fail(DWBC_ERR_ORDER, "calc_fstar: call update_kinematics first");
+    NEED_ALL(b, "calc_fstar");
     if (level < 0 || level >= b->cfg.nlevels || b->cfg.tasks[level].custom) return fail(DWBC_ERR_ARG, "calc_fstar: level out of range or TASK_CUSTOM");
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;

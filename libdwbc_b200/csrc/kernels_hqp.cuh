@@ -808,11 +808,14 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
 
 // One CTA (team) per state: QP assembly (U, Atemp U, right-hand sides), the active-set iterations (gi_solve) and the torque
 // updates all use every thread of the team.
+// list / count (may be null): the compact list of states left QP-active by lean_cycle_kernel (kernels_lean.cuh); CTA i finishes state
+// list[i] and CTAs beyond *count exit at once.  Without a list CTA i owns state i.
 __global__ void __launch_bounds__(TEAM, 7) hqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int redist,
-                                                      int nvmax) {
+                                                      int nvmax, const int *__restrict__ list, const int *__restrict__ count) {
     DWBC_DYN_SMEM(smem);
     const int tid = t_id(), nt = t_n();
-    const long long s = blockIdx.x;
+    if (list && (int)blockIdx.x >= *count) return;
+    const long long s = list ? list[blockIdx.x] : blockIdx.x;
     const int n = w.n, m = w.m, nb = w.nb;
     const HqpSmem L(n, m, nvmax);
     double *sm = (double *)smem;
@@ -984,11 +987,13 @@ __global__ void __launch_bounds__(TEAM, 7) hqp_kernel(const DevModel *__restrict
                 tau_task[i] = tt;
                 tprev[i] = w.tau_grav[s * m + i] + tt;
             });
-            // torque_h = J_kt Lambda_t (f* + f*_qp)
-            const double *Lt = w.Lamt[q] + s * (long long)t * t, *Jk = w.Jkt[q] + s * (long long)m * t;
-            tgemv<false>(t, t, Lt, t, fs, [&](int i, double v) { lf[i] = v; });
-            tsync();
-            tgemv<false>(m, t, Jk, m, lf, [&](int i, double v) { w.torque_h[q][s * m + i] = v; });
+            // torque_h = J_kt Lambda_t (f* + f*_qp)   (a public field: not produced when only the torques were asked for)
+            if (w.torque_h[q]) {
+                const double *Lt = w.Lamt[q] + s * (long long)t * t, *Jk = w.Jkt[q] + s * (long long)m * t;
+                tgemv<false>(t, t, Lt, t, fs, [&](int i, double v) { lf[i] = v; });
+                tsync();
+                tgemv<false>(m, t, Jk, m, lf, [&](int i, double v) { w.torque_h[q][s * m + i] = v; });
+            }
         }
         // level: torque_contact = NwJw contact_qp (zero without an internal-force space: quirk 1 of SURVEY Appendix A);
         // redistribution: torque_contact += NwJw x

@@ -92,8 +92,9 @@ struct RbdOut {
 // shared-memory doubles needed per warp
 __host__ __device__ inline int rbd_smem_doubles(int nb) { return nb * RB_STRIDE + 16; }
 
-__device__ __forceinline__ void rbd_state(const DevModel *__restrict__ md, const double *__restrict__ q, const double *__restrict__ qd,
-                                          double *rb, const RbdOut &out, long long s) {
+// Forward / backward sweeps of one state by ONE warp: pose, world axis, velocity, bias acceleration, common-frame inertia,
+// composite inertia and subtree bias force of every body, left in the per-body records rb (RB_*).  Only __syncwarp inside.
+__device__ __forceinline__ void rbd_sweeps(const DevModel *__restrict__ md, const double *__restrict__ q, const double *__restrict__ qd, double *rb) {
     const int lane = lane_id();
     const int nb = md->nb, n = md->n;
     // ---- base pose ----
@@ -194,6 +195,13 @@ __device__ __forceinline__ void rbd_state(const DevModel *__restrict__ md, const
         }
         __syncwarp();
     }
+}
+
+__device__ __forceinline__ void rbd_state(const DevModel *__restrict__ md, const double *__restrict__ q, const double *__restrict__ qd,
+                                          double *rb, const RbdOut &out, long long s) {
+    const int lane = lane_id();
+    const int nb = md->nb, n = md->n;
+    rbd_sweeps(md, q, qd, rb);
     // ---- mass matrix: row i per lane, all columns; A(i,j) = s_j . (Ic_deeper s_deeper) ----
     double *A = out.A + s * (long long)n * n;
     for (int i = lane; i < n; i += 32) {

@@ -194,7 +194,7 @@ struct Task {
     std::vector<TaskLink> links;
     Mat J, Lambda, Jkt, Null, fstar, fstar_qp, contact_qp, torque_h;
     Mat qpA, qpub;  // last assembled QP (parity with the golden A*mat / ubA*mat)
-    std::vector<int> active;
+    std::vector<int> active, gray;
     int qp_status = 0, prox_iters = 0;
     // a9 reduced-dimension variant (reference include/dwbc_task.h: noncont_task, reduced_task_, cmm_task, ..._R_ members)
     bool noncont = false, reduced = false, cmm = false;
@@ -226,7 +226,7 @@ struct Robot {
     V3 com_pos;
     int contact_dof = 0, contact_links = 0, contact_ok = 0, redis_status = 0;
     double redis_eta = 0;
-    std::vector<int> redis_active;
+    std::vector<int> redis_active, redis_gray;
 
     void update_kinematics(const double *q_, const double *qd_);
     Mat point_jac(int body, V3 pl) const;
@@ -627,6 +627,7 @@ int Robot::single_task_qp_on(Task &t, const Mat &Jkt, int m, const Mat &null_pre
     t.qp_status = res.status;
     t.prox_iters = res.prox_iters;
     t.active = res.active;
+    t.gray = res.gray;
     t.fstar_qp.set_zero(td, 1);
     t.contact_qp.set_zero(r, 1);
     if (!res.status) return 0;
@@ -640,7 +641,7 @@ int Robot::calc_task_torque(bool hqp) {
     calc_task_space();
     torque_task.set_zero(m, 1);
     torque_contact.set_zero(m, 1);
-    for (auto &t : ts) t.qp_status = 0, t.active.clear(), t.fstar_qp.set_zero(t.dof, 1), t.contact_qp.set_zero(std::max(contact_dof - 6, 0), 1);
+    for (auto &t : ts) t.qp_status = 0, t.active.clear(), t.gray.clear(), t.fstar_qp.set_zero(t.dof, 1), t.contact_qp.set_zero(std::max(contact_dof - 6, 0), 1);
     for (size_t i = 0; i < ts.size(); i++) {
         Task &t = ts[i];
         if (hqp) {
@@ -779,6 +780,7 @@ Mat Robot::redistribute_analytic(const Mat &JCINVT, const Mat &PC, const Mat &V2
 int Robot::calc_redistribute(bool hqp) {
     redis_status = 0;
     redis_active.clear();
+    redis_gray.clear();
     Mat tin = torque_grav + torque_task + torque_contact;
     int r = contact_dof - 6;
     if (!hqp) {
@@ -823,6 +825,7 @@ int Robot::calc_redistribute(bool hqp) {
     }
     fill_active(Aq, ub.d, res);
     redis_active = res.active;
+    redis_gray = res.gray;
     cf_redis_qp.set_zero(r, 1);
     for (int i = 0; i < r; i++) cf_redis_qp[i] = res.x[i];
     torque_contact = torque_contact + NwJw * cf_redis_qp;
@@ -1798,9 +1801,10 @@ void orc_cod_pinv(int rows, int cols, const double *A, double thr, double *pinv,
 // Outputs [B x m] row-major torques, status [B] (bit0 contact ok, bit1 task ok, bit2 redistribute ok).
 // bit4: CalcContactRedistribute(hqp=false) (analytic two-foot branch) instead of the QP.  Optional outputs: contact_force
 // [B x 6*ncontact] = getContactForce(tau_grav + tau_task + tau_contact) (zero padded), zmp [B x 3] = getZMP(contact_force).
-int orc_run_batch(void *h, int B, const double *q, const double *qd, const double *fstar, const unsigned char *flags,
-                  int stages, double *tau_grav, double *tau_task, double *tau_contact, int *status, int nthreads,
-                  double *contact_force, double *zmp) {
+// active / gray (may be null): [B][levels + 1][4] bit masks of the rows each QP reports active / weakly active (last = redistribution)
+static int run_batch_impl(void *h, int B, const double *q, const double *qd, const double *fstar, const unsigned char *flags,
+                          int stages, double *tau_grav, double *tau_task, double *tau_contact, int *status, int nthreads,
+                          double *contact_force, double *zmp, unsigned *active, unsigned *gray) {
     Robot *R0 = (Robot *)h;
     int n = R0->n, m = R0->m, nc = (int)R0->cc.size();
     std::vector<size_t> foff;
@@ -1848,6 +1852,25 @@ int orc_run_batch(void *h, int B, const double *q, const double *qd, const doubl
                     tau_contact[(size_t)b * m + i] = R.torque_contact[i];
                 }
                 status[b] = st;
+                if (active || gray) {
+                    const size_t nq = R.ts.size() + 1;
+                    for (size_t l = 0; l < nq; l++) {
+                        const std::vector<int> &a = l < R.ts.size() ? R.ts[l].active : R.redis_active;
+                        const std::vector<int> &g = l < R.ts.size() ? R.ts[l].gray : R.redis_gray;
+                        unsigned wa[4] = {0, 0, 0, 0}, wg[4] = {0, 0, 0, 0};
+                        const bool ran = l < R.ts.size() ? ((stages & 4) != 0) : ((stages & 8) != 0);
+                        if (ran) {
+                            for (int i : a)
+                                if (i < 128) wa[i >> 5] |= 1u << (i & 31);
+                            for (int i : g)
+                                if (i < 128) wg[i >> 5] |= 1u << (i & 31);
+                        }
+                        for (int k = 0; k < 4; k++) {
+                            if (active) active[((size_t)b * nq + l) * 4 + k] = wa[k];
+                            if (gray) gray[((size_t)b * nq + l) * 4 + k] = wg[k];
+                        }
+                    }
+                }
             }
         }
     };
@@ -1859,6 +1882,16 @@ int orc_run_batch(void *h, int B, const double *q, const double *qd, const doubl
         for (auto &t : th) t.join();
     }
     return 0;
+}
+int orc_run_batch(void *h, int B, const double *q, const double *qd, const double *fstar, const unsigned char *flags,
+                  int stages, double *tau_grav, double *tau_task, double *tau_contact, int *status, int nthreads,
+                  double *contact_force, double *zmp) {
+    return run_batch_impl(h, B, q, qd, fstar, flags, stages, tau_grav, tau_task, tau_contact, status, nthreads, contact_force, zmp, nullptr, nullptr);
+}
+int orc_run_batch_sets(void *h, int B, const double *q, const double *qd, const double *fstar, const unsigned char *flags,
+                       int stages, double *tau_grav, double *tau_task, double *tau_contact, int *status, int nthreads,
+                       unsigned *active, unsigned *gray) {
+    return run_batch_impl(h, B, q, qd, fstar, flags, stages, tau_grav, tau_task, tau_contact, status, nthreads, nullptr, nullptr, active, gray);
 }
 
 int orc_num_threads() {

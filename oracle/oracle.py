@@ -35,13 +35,30 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_NATIVE = os.path.join(os.path.dirname(_LIB), "liboracle_native.so")
+_use_native = False
+flavour = "portable (-march=x86-64-v3)"
+
+
+def use_native():
+    """bench.py's CPU arms: build the oracle with -march=native ON THIS MACHINE and time that one (falls back to the portable
+    library if the compiler is missing).  Must be called before the first use of the library."""
+    global _use_native, flavour
+    try:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "native"])
+        C.CDLL(_NATIVE)
+        _use_native = True
+        flavour = "built on this host with -O3 -march=native"
+    except Exception:
+        _use_native = False
+    return _use_native
 
 
 def lib():
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(_LIB)
+        L = C.CDLL(_NATIVE if _use_native else _LIB)
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp]
         L.orc_destroy.argtypes = [C.c_void_p]
@@ -63,6 +80,7 @@ def lib():
         L.orc_lexqp.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _ip]
         L.orc_cod_pinv.argtypes = [C.c_int, C.c_int, _dp, C.c_double, _dp, _ip]
         L.orc_run_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_char_p, C.c_int, _dp, _dp, _dp, _ip, C.c_int, _dp, _dp]
+        L.orc_run_batch_sets.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_char_p, C.c_int, _dp, _dp, _dp, _ip, C.c_int, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
         L.orc_contact_force.argtypes = [C.c_void_p, _dp, _dp]
         L.orc_zmp.argtypes = [C.c_void_p, _dp, _dp]
         L.orc_redis_eta.argtypes = [C.c_void_p]
@@ -253,8 +271,10 @@ class OracleRobot:
         lib().orc_get_qp_info(self.h, int(level), C.byref(s), C.byref(p))
         return s.value, p.value
 
-    def run_batch(self, q, qd, fstars, flags, stages=0xF, nthreads=0):
-        """Whole cycle over B states. fstars: list over levels of [B, t_l]. Returns dict."""
+    def run_batch(self, q, qd, fstars, flags, stages=0xF, nthreads=0, sets=False):
+        """Whole cycle over B states. fstars: list over levels of [B, t_l]. Returns dict.  sets=True: also the active-set bit masks
+        `active` / `gray` [B, levels + 1, 4] uint32 (last = redistribution QP; gray = rows whose relative slack lies within a decade
+        of the 1e-9 reporting threshold), instead of contact_force / zmp."""
         q = np.ascontiguousarray(q, dtype=np.float64)
         qd = np.ascontiguousarray(qd, dtype=np.float64)
         B = q.shape[0]
@@ -263,6 +283,14 @@ class OracleRobot:
         assert fl.shape == (B, self.ncontact)
         tg = np.zeros((B, self.m)); tt = np.zeros((B, self.m)); tc = np.zeros((B, self.m))
         st = np.zeros(B, dtype=np.int32)
+        if sets:
+            nq = len(fstars) + 1
+            act = np.zeros((B, nq, 4), dtype=np.uint32); gray = np.zeros((B, nq, 4), dtype=np.uint32)
+            up = C.POINTER(C.c_uint)
+            lib().orc_run_batch_sets(self.h, B, q.ctypes.data_as(_dp), qd.ctypes.data_as(_dp), fs.ctypes.data_as(_dp),
+                                     fl.ctypes.data_as(C.c_char_p), int(stages), tg.ctypes.data_as(_dp), tt.ctypes.data_as(_dp),
+                                     tc.ctypes.data_as(_dp), st.ctypes.data_as(_ip), int(nthreads), act.ctypes.data_as(up), gray.ctypes.data_as(up))
+            return dict(torque_grav=tg, torque_task=tt, torque_contact=tc, status=st, active=act, gray=gray)
         cf = np.zeros((B, 6 * self.ncontact)); zmp = np.zeros((B, 3))
         lib().orc_run_batch(self.h, B, q.ctypes.data_as(_dp), qd.ctypes.data_as(_dp), fs.ctypes.data_as(_dp),
                             fl.ctypes.data_as(C.c_char_p), int(stages), tg.ctypes.data_as(_dp), tt.ctypes.data_as(_dp),

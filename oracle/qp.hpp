@@ -239,6 +239,7 @@ struct QpResult {
     int status = 0;  // 1 solved, 0 infeasible / failed
     std::vector<double> x;
     std::vector<int> active;  // rows with A x = ub at the solution (|slack| <= tol)
+    std::vector<int> gray;    // rows whose relative slack lies within a decade of that threshold, (-1e-8, -1e-10): weakly active, may be reported either way
     int prox_iters = 0;
 };
 
@@ -255,11 +256,14 @@ inline QpResult qp_min_norm(const Mat &A, const std::vector<double> &ub, const s
 
 inline void fill_active(const Mat &A, const std::vector<double> &ub, QpResult &res) {
     res.active.clear();
+    res.gray.clear();
     for (int i = 0; i < A.r; i++) {
         double s = -ub[i], nn = 0;
         for (int j = 0; j < A.c; j++) s += A(i, j) * res.x[j], nn += A(i, j) * A(i, j);
         if (nn == 0) continue;
         if (s > -1e-9 * (1.0 + std::fabs(ub[i]))) res.active.push_back(i);
+        const double rel = s / (1.0 + std::fabs(ub[i]));
+        if (rel > -1e-8 && rel < -1e-10) res.gray.push_back(i);
     }
 }
 

@@ -646,3 +646,151 @@ def test_gpu_rl_bridge_batch():
     one.CalcTorque()
     out = one.getTorqueCommand()
     assert len(out) == 33 and np.array_equal(np.float32(out), cmd[1])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# DWBC_OUT_TORQUES: the one-kernel cycle (lean_cycle_kernel) + the active-set kernel over the compacted QP-active states
+# ---------------------------------------------------------------------------------------------------------------------
+def run_lean(config, q, qd, fstars, flags, stages, ncontacts=2, outputs=None):
+    from libdwbc_b200 import OUT_TORQUES, RobotDataBatch
+
+    B = q.shape[0]
+    rd = configure_product(RobotDataBatch(URDF, B, 0), config, ncontacts)
+    rd.set_outputs(OUT_TORQUES if outputs is None else outputs)
+    rd.update_kinematics(T(q), T(qd))
+    rd.set_contact(T(flags, torch.uint8))
+    rd.calc_contact_constraint()
+    for l, f in enumerate(fstars):
+        rd.set_task_space(l, T(f), T(posture_selector()) if (config == 2 and l == 2) else None)
+    out = rd.solve(stages)
+    torch.cuda.synchronize()
+    return rd, tuple(o.cpu().numpy() for o in out)
+
+
+def active_masks(rd, nlevels):
+    """[B, nlevels + 1, 4] uint32 bit masks of the product's reported active rows (last = redistribution)"""
+    B = rd.batch
+    out = np.zeros((B, nlevels + 1, 4), dtype=np.uint32)
+    for k, l in enumerate(list(range(nlevels)) + [-1]):
+        buf = torch.zeros((B, 4), dtype=torch.int32, device=_dev())
+        rd._ck(rd.L.dwbc_batch_get_active_set(rd._h, l, rd.be.ptr(buf), rd.be.stream()))
+        torch.cuda.synchronize()
+        out[:, k, :] = buf.cpu().numpy().view(np.uint32)
+    return out
+
+
+@pytest.mark.parametrize("case", [1, 2])
+def test_lean_golden(case):
+    from oracle.urdf_model import read_golden
+
+    q = np.array([Q_CASE[case]], dtype=np.float64)
+    flags = np.array([[1, 1, 0, 0]], dtype=np.uint8)
+    fs = [np.array([FSTAR_CASE[case][0]]), np.array([FSTAR_CASE[case][1]])]
+    rd, (tg, tt, tc, st) = run_lean("golden", q, np.zeros((1, 39)), fs, flags, ALL, 4)
+    assert rd.last_path() == 1 and st[0] == 7
+    g = lambda n: read_golden(os.path.join(GOLDEN, "cases", str(case), n))
+    assert relerr(tg[0], g("torque_grav_")[:, 0]) < 1e-9
+    assert relerr(tt[0], g("torque_task_")[:, 0]) < 1e-9
+    assert relerr(tc[0], g("torque_contact_")[:, 0]) < (1e-9 if case == 1 else 1e-4)
+    if case == 1:
+        assert rd.active_set(0)[0] == [66, 67, 68, 69, 70, 71, 72, 73, 74, 75, 78]
+        assert rd.active_set(1)[0] == [67, 68, 71, 72, 75, 78]
+
+
+def _full_parity(B, seed, mixed, outputs):
+    """Every state of a full-size batch against the oracle: status identical, torque_grav_ 1e-9, torque_task_ / torque_contact_ 1e-6,
+    active sets of all four QPs identical outside the oracle's weakly-active (gray) rows; the gray exemptions are counted."""
+    from oracle import oracle as orc
+
+    q, qd, rng = synth_states(B, seed)
+    fs = synth_fstar(rng, B)
+    flags = _mixed_flags(B, rng) if mixed else np.ones((B, 2), dtype=np.uint8)
+    rd, (tg, tt, tc, st) = run_lean(2, q, qd, fs, flags, ALL, outputs=outputs)
+    o = configure_oracle(orc.OracleRobot(URDF), 2).run_batch(q, qd, fs, flags, sets=True)
+    assert np.array_equal(st & 7, o["status"] & 7)
+    good = (o["status"] & 7) == 7
+    assert good.mean() > 0.99
+    scale = lambda a: np.maximum(1.0, np.abs(a).max(axis=1))
+    eg = (np.abs(tg - o["torque_grav"]).max(axis=1) / scale(o["torque_grav"]))[good].max()
+    et = (np.abs(tt - o["torque_task"]).max(axis=1) / scale(o["torque_task"]))[good].max()
+    ec = (np.abs(tc - o["torque_contact"]).max(axis=1) / scale(o["torque_contact"]))[good].max()
+    assert eg < 1e-9 and et < 1e-6 and ec < 1e-6, (eg, et, ec)
+    act = active_masks(rd, 3)
+    diff = (act ^ o["active"])[good]
+    exempt = diff & o["gray"][good]
+    hard = diff & ~o["gray"][good]
+    n_hard = int((hard != 0).any(axis=(1, 2)).sum())
+    n_exempt = int((exempt != 0).any(axis=(1, 2)).sum())
+    n_active = int((o["active"][good] != 0).any(axis=(1, 2)).sum())
+    print(f"B={B} mixed={mixed}: {int(good.sum())} solved, {n_active} with an active QP row, torque errors {eg:.1e} {et:.1e} {ec:.1e}, "
+          f"{n_exempt} states used a gray-row exemption, {n_hard} differ outside gray rows, slow flag on {int(((st & 16) != 0).sum())}")
+    assert n_hard == 0
+    assert n_exempt < 1e-3 * B
+    assert n_active > 0.2 * B  # the batch does exercise the active-set logic
+    return rd
+
+
+def test_lean_full_size_every_state_ds():
+    """BASELINE.json configs[2] at its full size (65 536 states, double support), every state against the oracle."""
+    from libdwbc_b200 import OUT_TORQUES
+
+    rd = _full_parity(65536, 20242, False, OUT_TORQUES)
+    assert rd.last_path() == 1
+
+
+def test_lean_full_size_every_state_mixed():
+    """One GPU's slice of BASELINE.json configs[4] (131 072 states, DS / left-SS / right-SS 0.5 / 0.25 / 0.25), every state."""
+    from libdwbc_b200 import OUT_TORQUES
+
+    rd = _full_parity(131072, 20244, True, OUT_TORQUES)
+    assert rd.last_path() == 1
+
+
+def test_generic_full_size_every_state_ds():
+    """The same check for the generic kernels (DWBC_OUT_ALL), 65 536 states."""
+    from libdwbc_b200 import OUT_ALL
+
+    rd = _full_parity(65536, 20242, False, OUT_ALL)
+    assert rd.last_path() == 0
+
+
+def test_lean_equals_generic_bitwise_status_and_close_torques():
+    """Output groups both ways on the same batch: identical status and active sets, torques to 1e-9."""
+    from libdwbc_b200 import OUT_ALL
+
+    B = 4096
+    q, qd, rng = synth_states(B, 20247)
+    fs = synth_fstar(rng, B)
+    flags = _mixed_flags(B, rng)
+    rl, (tg, tt, tc, st) = run_lean(2, q, qd, fs, flags, ALL)
+    rg, (tg0, tt0, tc0, st0) = run_lean(2, q, qd, fs, flags, ALL, outputs=OUT_ALL)
+    assert rl.last_path() == 1 and rg.last_path() == 0
+    assert np.array_equal(st & 7, st0 & 7)
+    for a, b in ((tg, tg0), (tt, tt0), (tc, tc0)):
+        assert (np.abs(a - b).max(axis=1) / np.maximum(1.0, np.abs(b).max(axis=1))).max() < 1e-8
+    assert (active_masks(rl, 3) != active_masks(rg, 3)).any(axis=(1, 2)).mean() < 1e-3
+    with pytest.raises(Exception):
+        rl.get("A_inv")
+
+
+def test_lean_cycle_host_and_config1():
+    from libdwbc_b200 import RobotDataBatch
+
+    B = 1000
+    q, qd, rng = synth_states(B, 20248)
+    fs = synth_fstar(rng, B)
+    flags = _mixed_flags(B, rng)
+    _, ref = run_lean(2, q, qd, fs, flags, ALL)
+    rd = configure_product(RobotDataBatch(URDF, B, 0), 2)
+    rd.set_task_space(2, T(np.zeros((B, 21))), T(posture_selector()))
+    rd.set_host_slices(3)
+    out = rd.cycle_host(ALL, q, qd, fs, flags)
+    assert rd.last_path() == 1
+    for a, b in zip(out, ref):
+        assert np.array_equal(a, b)
+    # closed-form hierarchy of config 1 (hqp = false)
+    fs1 = synth_fstar(rng, B, dofs=(3, 3), scales=(0.5, 1.0), hard_frac=0)
+    rl, (tg, tt, tc, st) = run_lean(1, q, qd, fs1, flags, 3)
+    rg, (tg0, tt0, tc0, st0) = run_product(1, q, qd, fs1, flags, 3)
+    assert rl.last_path() == 1 and np.array_equal(st & 7, st0 & 7)
+    assert relerr(tg, tg0) < 1e-10 and relerr(tt, tt0) < 1e-9

@@ -1,0 +1,94 @@
+"""Unit tests of the compile-time-specialised team linear algebra (libdwbc_b200/csrc/lean_linalg.cuh) through the CUDA
+emulation (test infrastructure, tests/emul): blocked Cholesky / triangular inverse / SYRK on the emulated DMMA, the
+one-warp small inverse, the DMMA products and the matrix-vector product, against numpy."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(ROOT, "libdwbc_b200", "csrc")
+EMUL = os.path.join(HERE, "emul")
+OUT = os.path.join(EMUL, "build", "liblean_unit.so")
+_dp = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    srcs = [os.path.join(EMUL, "lean_unit.cpp"), os.path.join(EMUL, "cuda_emul.h"), os.path.join(CSRC, "lean_linalg.cuh"),
+            os.path.join(CSRC, "team_linalg.cuh"), os.path.join(CSRC, "warp_linalg.cuh")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(s) > os.path.getmtime(OUT) for s in srcs):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++20", "-fPIC", "-shared", "-DDWBC_CPU_EMUL", "-I", EMUL, "-I", CSRC,
+                               srcs[0], "-o", OUT, "-lpthread", "-Wno-unused-variable", "-Wno-unused-but-set-variable"])
+    return C.CDLL(OUT)
+
+
+def p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def spd(n, rng, cond=1e4):
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    return (q * np.geomspace(1.0, cond, n)) @ q.T
+
+
+@pytest.mark.parametrize("n", [39, 40, 33, 21, 12, 24, 18, 6, 9])
+def test_spd_inverse(lib, n):
+    rng = np.random.default_rng(n)
+    A = spd(n, rng)
+    A = 0.5 * (A + A.T)
+    out = np.zeros((n, n))
+    piv = np.zeros(1)
+    assert lib.lean_spd_inverse(n, p(np.asfortranarray(A).T.copy()), p(out), p(piv)) == 0
+    ref = np.linalg.inv(A)
+    assert np.abs(out.T - ref).max() / np.abs(ref).max() < 1e-11
+    assert np.array_equal(out, out.T)
+    assert piv[0] > 0
+
+
+@pytest.mark.parametrize("n", [1, 3, 6, 8])
+def test_small_inverse(lib, n):
+    rng = np.random.default_rng(100 + n)
+    A = spd(n, rng, 1e3)
+    A = 0.5 * (A + A.T)
+    out = np.zeros((n, n))
+    cond = np.zeros(1)
+    assert lib.lean_small_inverse(n, p(A.T.copy()), p(out), p(cond)) == 0
+    ref = np.linalg.inv(A)
+    assert np.abs(out.T - ref).max() / np.abs(ref).max() < 1e-11
+    assert cond[0] > 0
+
+
+GEMMS = {0: (30, 39, 39), 1: (39, 12, 39), 2: (12, 39, 12), 3: (33, 30, 33), 4: (3, 6, 33), 5: (33, 21, 9), 6: (20, 27, 33)}
+
+
+@pytest.mark.parametrize("which", sorted(GEMMS))
+def test_gemm(lib, which):
+    M, N, K = GEMMS[which]
+    rng = np.random.default_rng(which)
+    a, b = rng.standard_normal((M, K)), rng.standard_normal((K, N))
+    c = np.zeros((N, M))
+    assert lib.lean_gemm(which, p(a.T.copy()), p(b.T.copy()), p(c)) == 0
+    assert np.abs(c.T - a @ b).max() < 1e-12
+
+
+@pytest.mark.parametrize("which,shape", [(0, (33, 6)), (1, (39, 12)), (2, (21, 33))])
+def test_gemm_sym(lib, which, shape):
+    rng = np.random.default_rng(which)
+    a = rng.standard_normal(shape)
+    c = np.zeros((shape[0], shape[0]))
+    assert lib.lean_gemm_sym(which, p(a.T.copy()), p(c)) == 0
+    assert np.abs(c.T - a @ a.T).max() < 1e-12
+
+
+@pytest.mark.parametrize("which,shape", [(0, (33, 39)), (1, (12, 39)), (2, (33, 21)), (3, (70, 7))])
+def test_gemv(lib, which, shape):
+    rng = np.random.default_rng(which)
+    a, x = rng.standard_normal(shape), rng.standard_normal(shape[1])
+    y = np.zeros(shape[0])
+    assert lib.lean_gemv(which, p(a.T.copy()), p(x), p(y)) == 0
+    assert np.abs(y - a @ x).max() < 1e-12
