@@ -24,6 +24,7 @@
 #ifndef DWBC_B200_H
 #define DWBC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -287,8 +288,38 @@ int dwbc_batch_get_torque_command_f32(dwbc_batch_t *b, float *out_dev, void *str
 int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, const double *qdot_host, const double *fstar_host,
                           const uint8_t *flags_host, double *tau_grav_host, double *tau_task_host, double *tau_contact_host,
                           int32_t *status_host, void *stream);
+/* The same with one f* pointer per hierarchy level (fstar_levels_host[l] -> [B x t_l]): what a caller uses whose level blocks are not
+ * one concatenation, e.g. a slice of a larger batch (dwbc_multi_cycle_host). */
+int dwbc_batch_cycle_host_levels(dwbc_batch_t *b, int stages, const double *q_host, const double *qdot_host, const double *const *fstar_levels_host,
+                                 const uint8_t *flags_host, double *tau_grav_host, double *tau_task_host, double *tau_contact_host,
+                                 int32_t *status_host, void *stream);
 /* Number of slices dwbc_batch_cycle_host cuts the batch into: 0 = automatic (one per 4096 states, at most 16), 1 = no slicing. */
 int dwbc_batch_set_host_slices(dwbc_batch_t *b, int slices);
+
+/* ---- one host batch over several GPUs of one box: contiguous slices of the batch, one host thread + one
+ * stream + one dwbc_batch_t per GPU, no collective on the data path; every GPU reads and writes its own slice of the caller's host
+ * buffers and the call returns when every slice is done.  `devices` = NULL means GPUs 0 .. ngpus-1.  The setup calls mirror the
+ * dwbc_batch_* ones and are applied to every shard (a custom task takes its [t x n] column-major Jacobian, shared by all states, from
+ * the host).  Host buffers should come from dwbc_host_alloc (pinned, visible to every GPU) for the copies to overlap the kernels. */
+typedef struct dwbc_multi dwbc_multi_t;
+dwbc_multi_t *dwbc_multi_create(const dwbc_model_t *m, int batch, int ngpus, const int *devices);
+void dwbc_multi_destroy(dwbc_multi_t *mh);
+int dwbc_multi_gpus(const dwbc_multi_t *mh);
+/* shard g: its handle (for per-GPU queries), device, first state and state count */
+int dwbc_multi_shard(dwbc_multi_t *mh, int g, dwbc_batch_t **batch, int *device, int *first_state, int *count);
+int dwbc_multi_add_contact(dwbc_multi_t *mh, int link, int contact_type, const double point[3], const double normal[3], double lx, double ly);
+int dwbc_multi_add_task(dwbc_multi_t *mh, int level, int task_mode, int link, const double point[3]);
+int dwbc_multi_add_custom_task(dwbc_multi_t *mh, int level, int task_dof, const double *jtask_host);
+int dwbc_multi_set_torque_limit(dwbc_multi_t *mh, const double *tlim_host);
+int dwbc_multi_set_outputs(dwbc_multi_t *mh, int outputs);
+/* dwbc_batch_cycle_host for the whole batch: same argument layout ([B x ...] host arrays, f* = concatenation over levels of [B x t_l]) */
+int dwbc_multi_cycle_host(dwbc_multi_t *mh, int stages, const double *q_host, const double *qdot_host, const double *fstar_host,
+                          const uint8_t *flags_host, double *tau_grav_host, double *tau_task_host, double *tau_contact_host,
+                          int32_t *status_host);
+/* host wall time (ms) of every shard's thread in the last dwbc_multi_cycle_host: out[g], g < dwbc_multi_gpus */
+int dwbc_multi_last_shard_ms(const dwbc_multi_t *mh, double *out);
+void *dwbc_host_alloc(size_t bytes);
+void dwbc_host_free(void *p);
 
 /* ---- output groups: which RobotData fields a cycle materialises in HBM ----
  * DWBC_OUT_ALL      every public field of the reference's RobotData (A_, A_inv_, J_C, Lambda_contact, J_C_INV_T, A_inv_N_C, W, W_inv,
@@ -306,6 +337,9 @@ enum { DWBC_OUT_AUTO = -1, DWBC_OUT_TORQUES = 0, DWBC_OUT_ALL = 1 };
 int dwbc_batch_set_outputs(dwbc_batch_t *b, int outputs);
 /* 1 if the last dwbc_batch_solve / dwbc_batch_cycle_host ran the one-kernel cycle, 0 if it ran the generic kernels */
 int dwbc_batch_last_path(const dwbc_batch_t *b);
+/* Diagnostics of the one-kernel cycle: stamps_dev [B x 32] int64 (device) receives the SM clock (clock64) at the end of every phase of
+ * every state (phase list next to LEAN_STAMP in csrc/kernels_lean.cuh); NULL switches it off.  tools/lean_phases.py prints the table. */
+int dwbc_batch_set_lean_timing(dwbc_batch_t *b, long long *stamps_dev);
 
 /* ---- diagnostics ---- */
 /* Best DFMA-chain throughput (TFLOP/s, 2 flop per FMA) observed over ~`seconds` of back-to-back launches on

@@ -6,7 +6,10 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
+#include <functional>
+#include <memory>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -57,6 +60,7 @@ struct dwbc_batch {
     int *d_list = nullptr, *d_count = nullptr;
     size_t list_off = 0;  // dwbc_batch_cycle_host: the slice's part of d_list and its stream's counter
     int count_slot = 0;
+    long long *lean_timing = nullptr;  // diagnostics: device buffer [B][32] of phase stamps (dwbc_batch_set_lean_timing)
     int last_path = 0;  // 1: the last solve ran lean_cycle_kernel, 0: the generic kernels
     int tasks_level = 0;  // 0: no per-level buffers, 1: those of DWBC_OUT_TORQUES, 2: all
     // dwbc_batch_cycle_host pipelines slices of the batch over these streams (copies of one slice under the kernels of another)
@@ -267,6 +271,7 @@ int launch_lean(dwbc_batch *b, int stages, cudaStream_t st) {
     a.flags = b->lean_flags;
     a.hqp = (stages & DWBC_SOLVE_HQP) ? 1 : 0;
     a.redist = (stages & DWBC_SOLVE_REDIST) ? 1 : 0;
+    a.timing = b->lean_timing ? b->lean_timing + 32 * b->list_off : nullptr;
     a.list = b->d_list + b->list_off;
     a.count = b->d_count + b->count_slot;
     CK(cudaMemsetAsync(a.count, 0, sizeof(int), st));
@@ -862,6 +867,11 @@ int dwbc_batch_set_outputs(dwbc_batch_t *b, int outputs) {
     return DWBC_OK;
 }
 int dwbc_batch_last_path(const dwbc_batch_t *b) { return b ? b->last_path : -1; }
+int dwbc_batch_set_lean_timing(dwbc_batch_t *b, long long *stamps_dev) {
+    if (!b) return fail(DWBC_ERR_ARG, "set_lean_timing: null handle");
+    b->lean_timing = stamps_dev;
+    return DWBC_OK;
+}
 
 int dwbc_batch_set_profiling(dwbc_batch_t *b, int enable) {
     if (!b) return fail(DWBC_ERR_ARG, "set_profiling: null handle");
@@ -904,6 +914,22 @@ int dwbc_batch_set_host_slices(dwbc_batch_t *b, int slices) {
 int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, const double *qdot_host, const double *fstar_host,
                           const uint8_t *flags_host, double *tau_grav_host, double *tau_task_host, double *tau_contact_host,
                           int32_t *status_host, void *stream) {
+    if (!b) return fail(DWBC_ERR_ARG, "cycle_host: null argument");
+    const double *lv[MAX_LEVELS] = {nullptr, nullptr, nullptr, nullptr};
+    if (fstar_host) {
+        size_t off = 0;
+        for (int l = 0; l < b->cfg.nlevels; l++) {
+            lv[l] = fstar_host + off;
+            off += (size_t)b->cfg.tasks[l].dof * b->B;
+        }
+    }
+    return dwbc_batch_cycle_host_levels(b, stages, q_host, qdot_host, fstar_host ? lv : nullptr, flags_host, tau_grav_host, tau_task_host,
+                                        tau_contact_host, status_host, stream);
+}
+
+int dwbc_batch_cycle_host_levels(dwbc_batch_t *b, int stages, const double *q_host, const double *qdot_host, const double *const *fstar_levels_host,
+                                 const uint8_t *flags_host, double *tau_grav_host, double *tau_task_host, double *tau_contact_host,
+                                 int32_t *status_host, void *stream) {
     if (!b || !q_host || !qdot_host || !flags_host) return fail(DWBC_ERR_ARG, "cycle_host: null argument");
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -912,7 +938,9 @@ int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, con
     size_t ftot = 0;
     for (int l = 0; l < b->cfg.nlevels; l++) ftot += (size_t)b->cfg.tasks[l].dof * B;
     if (need_tasks) {
-        if (!fstar_host) return fail(DWBC_ERR_ARG, "cycle_host: fstar_host is null");
+        if (!fstar_levels_host) return fail(DWBC_ERR_ARG, "cycle_host: fstar_host is null");
+        for (int l = 0; l < b->cfg.nlevels; l++)
+            if (!fstar_levels_host[l]) return fail(DWBC_ERR_ARG, "cycle_host: f* of a hierarchy level is null");
         if (ftot > b->d_fstar_cap) {
             if (b->d_fstar) cudaFree(b->d_fstar);
             void *raw = nullptr;
@@ -978,7 +1006,7 @@ int dwbc_batch_cycle_host(dwbc_batch_t *b, int stages, const double *q_host, con
                 size_t off = 0;
                 for (int l = 0; l < b->cfg.nlevels; l++) {
                     const size_t t = b->cfg.tasks[l].dof;
-                    CK(cudaMemcpyAsync(b->d_fstar + off + s0 * t, fstar_host + off + s0 * t, cnt * t * sizeof(double), cudaMemcpyHostToDevice, sk));
+                    CK(cudaMemcpyAsync(b->d_fstar + off + s0 * t, fstar_levels_host[l] + s0 * t, cnt * t * sizeof(double), cudaMemcpyHostToDevice, sk));
                     off += t * B;
                 }
             }
@@ -1671,6 +1699,242 @@ int dwbc_batch_get_torque_command_f32(dwbc_batch_t *b, float *out_dev, void *str
     }
     CK(cudaGetLastError());
     return DWBC_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ multi-GPU host path
+// the batch shards embarrassingly -- contiguous slices [g B/G, (g+1) B/G) of every batch array, one host
+// thread + one stream + one dwbc_batch_t per GPU, no collective; every GPU reads and writes its own slice of the caller's (pinned)
+// host buffers and the host call returns when all slices are done ("the host gathers the results": the slices land in place).
+#ifndef DWBC_CPU_EMUL
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#else
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#endif
+
+struct dwbc_multi {
+    struct Shard {
+        dwbc_batch *b = nullptr;
+        int device = 0;
+        size_t first = 0, count = 0;
+        cudaStream_t stream = nullptr;
+        std::vector<void *> dev_allocs;  // custom-task Jacobians uploaded to this GPU
+        // worker
+        std::thread th;
+        std::mutex mu;
+        std::condition_variable cv;
+        bool has_job = false, done = false, quit = false;
+        int rc = 0;
+        std::string err;
+        std::function<int(Shard &)> job;
+        double last_ms = 0.0;
+    };
+    std::vector<std::unique_ptr<Shard>> shards;
+    int B = 0, nlevels = 0;
+    int tdof[MAX_LEVELS] = {0, 0, 0, 0};
+    int n = 0, m = 0, ncontact = 0;
+};
+
+namespace {
+void multi_worker(dwbc_multi::Shard *s) {
+    cudaSetDevice(s->device);
+    std::unique_lock<std::mutex> lk(s->mu);
+    while (true) {
+        s->cv.wait(lk, [&] { return s->has_job || s->quit; });
+        if (s->quit) return;
+        s->has_job = false;
+        lk.unlock();
+        const auto t0 = std::chrono::steady_clock::now();
+        int rc = s->job(*s);
+        const auto t1 = std::chrono::steady_clock::now();
+        lk.lock();
+        s->rc = rc;
+        s->last_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        if (rc) s->err = g_err;  // g_err is thread_local: carry the message to the calling thread
+        s->done = true;
+        s->cv.notify_all();
+    }
+}
+// runs job on every shard's own host thread and waits for all of them; returns the first error
+int multi_run(dwbc_multi *mh, const std::function<int(dwbc_multi::Shard &)> &job) {
+    for (auto &sp : mh->shards) {
+        std::lock_guard<std::mutex> lk(sp->mu);
+        sp->job = job;
+        sp->done = false;
+        sp->has_job = true;
+        sp->cv.notify_all();
+    }
+    int rc = 0;
+    for (auto &sp : mh->shards) {
+        std::unique_lock<std::mutex> lk(sp->mu);
+        sp->cv.wait(lk, [&] { return sp->done; });
+        if (sp->rc && !rc) {
+            rc = sp->rc;
+            g_err = "gpu " + std::to_string(sp->device) + ": " + sp->err;
+        }
+    }
+    return rc;
+}
+template <class F>
+int multi_each(dwbc_multi *mh, F f) {  // configuration calls: cheap, run on the calling thread
+    for (auto &sp : mh->shards) {
+        const int rc = f(*sp);
+        if (rc < 0) return rc;
+    }
+    return DWBC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+dwbc_multi_t *dwbc_multi_create(const dwbc_model_t *m, int batch, int ngpus, const int *devices) {
+    if (!m || batch <= 0 || ngpus <= 0 || ngpus > batch) {
+        g_err = "dwbc_multi_create: bad arguments";
+        return nullptr;
+    }
+    dwbc_multi *mh = new (std::nothrow) dwbc_multi();
+    if (!mh) return nullptr;
+    mh->B = batch;
+    mh->n = m->hm.dev.n;
+    mh->m = m->hm.dev.m;
+    const size_t per = ((size_t)batch + ngpus - 1) / ngpus;
+    for (int g = 0; g < ngpus; g++) {
+        const size_t first = std::min<size_t>(batch, g * per), count = std::min<size_t>(per, batch - first);
+        if (count == 0) break;
+        auto sp = std::make_unique<dwbc_multi::Shard>();
+        sp->device = devices ? devices[g] : g;
+        sp->first = first;
+        sp->count = count;
+        sp->b = dwbc_batch_create(m, (int)count, sp->device);
+        if (!sp->b || !cuda_ok(cudaStreamCreateWithFlags(&sp->stream, cudaStreamNonBlocking), "cudaStreamCreateWithFlags")) {
+            if (sp->b) dwbc_batch_destroy(sp->b);
+            for (auto &o : mh->shards) {
+                dwbc_batch_destroy(o->b);
+            }
+            delete mh;
+            return nullptr;
+        }
+        mh->shards.push_back(std::move(sp));
+    }
+    for (auto &sp : mh->shards) sp->th = std::thread(multi_worker, sp.get());
+    return mh;
+}
+void dwbc_multi_destroy(dwbc_multi_t *mh) {
+    if (!mh) return;
+    for (auto &sp : mh->shards) {
+        {
+            std::lock_guard<std::mutex> lk(sp->mu);
+            sp->quit = true;
+            sp->cv.notify_all();
+        }
+        if (sp->th.joinable()) sp->th.join();
+        cudaSetDevice(sp->device);
+        for (void *p : sp->dev_allocs) cudaFree(p);
+        if (sp->stream) cudaStreamDestroy(sp->stream);
+        dwbc_batch_destroy(sp->b);
+    }
+    delete mh;
+}
+int dwbc_multi_gpus(const dwbc_multi_t *mh) { return mh ? (int)mh->shards.size() : 0; }
+int dwbc_multi_shard(dwbc_multi_t *mh, int g, dwbc_batch_t **batch, int *device, int *first_state, int *count) {
+    if (!mh || g < 0 || g >= (int)mh->shards.size()) return fail(DWBC_ERR_ARG, "multi_shard: bad index");
+    auto &s = *mh->shards[g];
+    if (batch) *batch = s.b;
+    if (device) *device = s.device;
+    if (first_state) *first_state = (int)s.first;
+    if (count) *count = (int)s.count;
+    return DWBC_OK;
+}
+int dwbc_multi_add_contact(dwbc_multi_t *mh, int link, int contact_type, const double point[3], const double normal[3], double lx, double ly) {
+    if (!mh) return fail(DWBC_ERR_ARG, "multi_add_contact: null handle");
+    int idx = 0;
+    const int rc = multi_each(mh, [&](dwbc_multi::Shard &s) { return idx = dwbc_batch_add_contact(s.b, link, contact_type, point, normal, lx, ly); });
+    if (rc < 0) return rc;
+    mh->ncontact = idx + 1;
+    return idx;
+}
+int dwbc_multi_add_task(dwbc_multi_t *mh, int level, int task_mode, int link, const double point[3]) {
+    if (!mh) return fail(DWBC_ERR_ARG, "multi_add_task: null handle");
+    const int rc = multi_each(mh, [&](dwbc_multi::Shard &s) { return dwbc_batch_add_task(s.b, level, task_mode, link, point); });
+    if (rc < 0) return rc;
+    const BatchCfg &c = mh->shards[0]->b->cfg;
+    mh->nlevels = c.nlevels;
+    for (int l = 0; l < c.nlevels; l++) mh->tdof[l] = c.tasks[l].dof;
+    return DWBC_OK;
+}
+int dwbc_multi_add_custom_task(dwbc_multi_t *mh, int level, int task_dof, const double *jtask_host) {
+    if (!mh || !jtask_host) return fail(DWBC_ERR_ARG, "multi_add_custom_task: null argument");
+    const int rc = multi_each(mh, [&](dwbc_multi::Shard &s) -> int {
+        int r = dwbc_batch_add_custom_task(s.b, level, task_dof);
+        if (r) return r;
+        CK(cudaSetDevice(s.device));
+        void *raw = nullptr;
+        const size_t bytes = sizeof(double) * (size_t)task_dof * s.b->w.n;
+        CK(cudaMalloc(&raw, bytes));
+        s.dev_allocs.push_back(raw);
+        CK(cudaMemcpy(raw, jtask_host, bytes, cudaMemcpyHostToDevice));
+        s.b->w.jcustom[level] = (const double *)raw;  // shared by all states of the shard
+        s.b->w.jcustom_per_state[level] = 0;
+        return DWBC_OK;
+    });
+    if (rc < 0) return rc;
+    const BatchCfg &c = mh->shards[0]->b->cfg;
+    mh->nlevels = c.nlevels;
+    for (int l = 0; l < c.nlevels; l++) mh->tdof[l] = c.tasks[l].dof;
+    return DWBC_OK;
+}
+int dwbc_multi_set_torque_limit(dwbc_multi_t *mh, const double *tlim_host) {
+    if (!mh) return fail(DWBC_ERR_ARG, "multi_set_torque_limit: null handle");
+    return multi_each(mh, [&](dwbc_multi::Shard &s) { return dwbc_batch_set_torque_limit(s.b, tlim_host); });
+}
+int dwbc_multi_set_outputs(dwbc_multi_t *mh, int outputs) {
+    if (!mh) return fail(DWBC_ERR_ARG, "multi_set_outputs: null handle");
+    return multi_each(mh, [&](dwbc_multi::Shard &s) { return dwbc_batch_set_outputs(s.b, outputs); });
+}
+
+int dwbc_multi_cycle_host(dwbc_multi_t *mh, int stages, const double *q_host, const double *qdot_host, const double *fstar_host,
+                          const uint8_t *flags_host, double *tau_grav_host, double *tau_task_host, double *tau_contact_host,
+                          int32_t *status_host) {
+    if (!mh || !q_host || !qdot_host || !flags_host) return fail(DWBC_ERR_ARG, "multi_cycle_host: null argument");
+    const size_t n = mh->n, m = mh->m, nc = mh->ncontact, B = mh->B;
+    return multi_run(mh, [=](dwbc_multi::Shard &s) -> int {
+        const double *lv[MAX_LEVELS] = {nullptr, nullptr, nullptr, nullptr};
+        if (fstar_host) {
+            size_t off = 0;
+            for (int l = 0; l < mh->nlevels; l++) {
+                lv[l] = fstar_host + off + s.first * mh->tdof[l];
+                off += (size_t)mh->tdof[l] * B;
+            }
+        }
+        auto adv = [&](double *p, size_t rec) { return p ? p + s.first * rec : nullptr; };
+        return dwbc_batch_cycle_host_levels(s.b, stages, q_host + s.first * (n + 1), qdot_host + s.first * n, fstar_host ? lv : nullptr,
+                                            flags_host + s.first * nc, adv(tau_grav_host, m), adv(tau_task_host, m), adv(tau_contact_host, m),
+                                            status_host ? status_host + s.first : nullptr, s.stream);
+    });
+}
+// host wall time (ms) each shard's thread spent in the last dwbc_multi_cycle_host: out[g], g < dwbc_multi_gpus
+int dwbc_multi_last_shard_ms(const dwbc_multi_t *mh, double *out) {
+    if (!mh || !out) return fail(DWBC_ERR_ARG, "multi_last_shard_ms: null argument");
+    for (size_t g = 0; g < mh->shards.size(); g++) out[g] = mh->shards[g]->last_ms;
+    return DWBC_OK;
+}
+// pinned host memory visible to every GPU (the copies of dwbc_multi_cycle_host overlap with kernels only from pinned memory)
+void *dwbc_host_alloc(size_t bytes) {
+    void *p = nullptr;
+#ifdef DWBC_CPU_EMUL
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+#else
+    if (!cuda_ok(cudaHostAlloc(&p, bytes, cudaHostAllocPortable), "cudaHostAlloc")) return nullptr;
+#endif
+    return p;
+}
+void dwbc_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 }  // extern "C"

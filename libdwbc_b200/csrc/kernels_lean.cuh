@@ -69,7 +69,14 @@ struct LeanArgs {
     int redist;  // 1: CalcContactRedistribute(hqp = true) follows
     int *list;   // [B] compact list of the states hqp_kernel still has to finish
     int *count;  // number of entries of list
+    long long *timing;  // diagnostics (may be null): [B][32] clock64() stamps of the phases of every state, see LEAN_STAMP
 };
+// phase stamps (thread 0 of the CTA): 0 start, 1 sweeps, 2 A, 3 A^-1, 4 Jc, 5 X, 6 Lambda_c, 7 Jbar + P, 8 V, 9 J_task, 10 T, 11 W + VV^T,
+// 12 (W + VV^T)^-1, 13 W^+ / NwJw / tau_grav, 14 Y, 15 M_l, 16 M_l^-1, 17 JL, 18 Ntorque, 19 QP tests, 20 end
+#define LEAN_STAMP(tm, k)                            \
+    do {                                             \
+        if ((tm) && t_id() == 0) (tm)[k] = clock64(); \
+    } while (0)
 
 // shared-memory arena of one state (doubles)
 template <class S>
@@ -136,12 +143,101 @@ __device__ __forceinline__ void point_jacobian_rb(const DevModel *__restrict__ m
     }
 }
 
+
+// Forward kinematics, common-frame inertias and composite inertias of one state for the torque path (no velocities, bias
+// accelerations or forces: B_ is not an output of DWBC_OUT_TORQUES).  The trigonometry and the joint-local rotations E_T R(q) of ALL
+// joints are formed by the team in parallel; only the two dependent chains -- parent-to-child pose, child-to-parent composite
+// inertia -- run level by level on one warp (`serial_warp`), 27 + 9 FMAs per body.  Same records as rbd_sweeps (RB_R, RB_P, RB_AX,
+// RB_IC).  Synchronises the team.
+__device__ __forceinline__ void rbd_sweeps_lean(const DevModel *__restrict__ md, const double *__restrict__ q, double *rb, int serial_warp) {
+    const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = lean::warp_id();
+    const int nb = md->nb, n = md->n;
+    for (int b = tid; b < nb; b += nt) {
+        double *bb = rb + b * RB_STRIDE;
+        if (b == 0) {
+            const double x = q[3], y = q[4], z = q[5], w = q[n];
+            double *R = bb + RB_R;
+            R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
+            R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+            R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
+            bb[RB_P] = bb[RB_P + 1] = bb[RB_P + 2] = 0.0;  // positions are kept relative to the pelvis origin
+            bb[RB_AX] = bb[RB_AX + 1] = bb[RB_AX + 2] = 0.0;
+        } else {
+            const Vec3 a = ld3(md->axis[b]);
+            double sn, cs;
+            sincos(q[5 + b], &sn, &cs);
+            const double c1 = 1.0 - cs;
+            const double Rq[9] = {cs + c1 * a.x * a.x,       c1 * a.x * a.y - sn * a.z, c1 * a.x * a.z + sn * a.y,
+                                  c1 * a.x * a.y + sn * a.z, cs + c1 * a.y * a.y,       c1 * a.y * a.z - sn * a.x,
+                                  c1 * a.x * a.z - sn * a.y, c1 * a.y * a.z + sn * a.x, cs + c1 * a.z * a.z};
+            double Rj[9];
+            mm3(md->E_T[b], Rq, Rj);
+            DWBC_UNROLL(9)
+            for (int k = 0; k < 9; k++) bb[RB_R + k] = Rj[k];  // joint-local rotation; becomes the world rotation in the chain below
+        }
+    }
+    tsync();
+    if (warp == serial_warp) {
+        for (int d = 1; d <= md->max_depth; d++) {
+            const int e0 = md->level_start[d], e1 = md->level_start[d + 1];
+            for (int e = e0 + lane; e < e1; e += 32) {
+                const int b = md->order[e], l = md->parent[b];
+                const double *pb = rb + l * RB_STRIDE;
+                double *bb = rb + b * RB_STRIDE;
+                double Rw[9];
+                mm3(pb + RB_R, bb + RB_R, Rw);
+                DWBC_UNROLL(9)
+                for (int k = 0; k < 9; k++) bb[RB_R + k] = Rw[k];
+                st3(bb + RB_P, ld3(pb + RB_P) + mv(pb + RB_R, ld3(md->r_T[b])));
+                st3(bb + RB_AX, mv(Rw, ld3(md->axis[b])));
+            }
+            __syncwarp();
+        }
+    }
+    tsync();
+    for (int b = tid; b < nb; b += nt) {  // inertia of every body in the common frame (mass, first moment, inertia about the pelvis origin)
+        double *bb = rb + b * RB_STRIDE;
+        const double *R = bb + RB_R;
+        const double mass = md->mass[b];
+        const Vec3 c = ld3(bb + RB_P) + mv(R, ld3(md->com[b]));
+        double T[9], Iw[9], Rt[9] = {R[0], R[3], R[6], R[1], R[4], R[7], R[2], R[5], R[8]};
+        mm3(R, md->inertia[b], T);
+        mm3(T, Rt, Iw);
+        const double cc = dot(c, c);
+        double *ic = bb + RB_IC;
+        ic[0] = mass;
+        st3(ic + 1, mass * c);
+        ic[4] = Iw[0] + mass * (cc - c.x * c.x);
+        ic[5] = Iw[1] - mass * c.x * c.y;
+        ic[6] = Iw[2] - mass * c.x * c.z;
+        ic[7] = Iw[4] + mass * (cc - c.y * c.y);
+        ic[8] = Iw[5] - mass * c.y * c.z;
+        ic[9] = Iw[8] + mass * (cc - c.z * c.z);
+    }
+    tsync();
+    if (warp == serial_warp) {
+        for (int d = md->max_depth - 1; d >= 0; d--) {  // parents gather the composite inertia of their children
+            const int e0 = md->level_start[d], e1 = md->level_start[d + 1];
+            for (int e = e0 + lane; e < e1; e += 32) {
+                const int b = md->order[e];
+                double *bb = rb + b * RB_STRIDE;
+                for (int ci = md->child_start[b]; ci < md->child_start[b + 1]; ci++) {
+                    const double *cb = rb + md->child_list[ci] * RB_STRIDE;
+                    DWBC_UNROLL(10)
+                    for (int k = 0; k < 10; k++) bb[RB_IC + k] += cb[RB_IC + k];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // ---- contact-consistent dynamics for a compile-time contact dof C (6 or 12): everything from Jc to W^+, tau_grav, NwJw ----
 // On return: P (R1) holds A^{-1}N_c with W^+ in its [6:,6:] block, T (R3) = J P, and the small items of R4 are filled.
 // Returns false (uniformly) if a factorisation failed.
 template <class S, int C>
 __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, const Work &w, long long s,
-                                                    double *sm, const int *cix) {
+                                                    double *sm, const int *cix, long long *tm) {
     using L = LeanSmem<S>;
     constexpr int N = S::N, M = S::M, LDN = S::LDN, LDM = S::LDM, LDT = S::LDT, LDC = S::LDC, TS = S::TS, R = C - 6;
     const int tid = t_id(), nt = t_n(), warp = lean::warp_id(), lane = lane_id();
@@ -157,13 +253,16 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
         if (tid < 9) Rc[9 * k + tid] = rb[c.link * RB_STRIDE + RB_R + tid];
     }
     tsync();
+    LEAN_STAMP(tm, 4);
     // X = A^{-1} Jc^T  (N x C)
     lean::mma_gemm<N, C, N, LDN, LDC, false, true, (C + 7) / 8>(P, Jc, [&](int i, int j, double v) { X[i + j * LDN] = v; });
     tsync();
+    LEAN_STAMP(tm, 5);
     // Jc X (C x C, SPD) -> Lambda_c
     lean::mma_gemm<C, C, N, LDC, LDN, false, false, 1>(Jc, X, [&](int i, int j, double v) { Lam[i + j * LDC] = v; });
     lean::spd_inverse<C, LDC, LDC>(Lam, Lw, rd, misc, 1);
     if (!(misc[0] > 0.0)) return false;
+    LEAN_STAMP(tm, 6);
     // Jbar^T = Lambda_c X^T  (C x N)
     lean::mma_gemm<C, N, C, LDC, LDN, false, true, 3>(Lam, X, [&](int i, int j, double v) { Jbar[i + j * LDC] = v; });
     tsync();
@@ -178,6 +277,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
         Jb6[i + j * LDC] = Jbar[i + (6 + j) * LDC];
     }
     lean::gemv<C, N, LDC, false, 4>(Jbar, Gs, [&](int i, double v) { PC[i] = v; });
+    LEAN_STAMP(tm, 7);
     if constexpr (R > 0) {
         // ---- orthonormal basis V (M x R) of null(W): {S Jc^T f : (Jc^T f)[0:6] = 0} ----
         constexpr int lda = 13;
@@ -224,6 +324,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
     } else {
         tsync();
     }
+    LEAN_STAMP(tm, 8);
     // u = (A^{-1}N_c)[6:, :] G   (tgv is scratch here)
     lean::gemv<M, N, LDN, false, 2>(P + 6, Gs, [&](int i, double v) { u[i] = v; });
     // ---- J_task of all levels (stacked, R2: Jc / X / Lambda_c are dead) and T = J P (R3: the sweep records are dead after this) ----
@@ -275,9 +376,11 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
             }
         });
         tsync();
+        LEAN_STAMP(tm, 9);
         lean::mma_gemm<TS, N, N, LDT, LDN, false, false, (N + 7) / 8>(Js, P, [&](int i, int j, double v) { T[i + j * LDT] = v; });
     }
     tsync();
+    LEAN_STAMP(tm, 10);
     // ---- W^+ = (W + V V^T)^{-1} - V V^T in place in P[6:, 6:] ----
     double *Wb = P + 6 + 6 * LDN;
     if constexpr (R > 0) {
@@ -286,8 +389,10 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
             if (i != j) Wb[j + i * LDN] += v;
         });
     }
+    LEAN_STAMP(tm, 11);
     lean::spd_inverse<M, LDN, LDM>(Wb, R2, rd, misc, 2);
     if (!(misc[0] > 0.0)) return false;
+    LEAN_STAMP(tm, 12);
     if constexpr (R > 0) {
         lean::mma_gemm_sym<M, R, LDM, LDM, false, true>(V, V, [&](int i, int j, double v) {
             Wb[i + j * LDN] -= v;
@@ -322,12 +427,13 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
         lean::gemv<M, M, LDN, false, 2>(Wb, u, [&](int i, double v) { tgv[i] = v; });
     }
     tsync();
+    LEAN_STAMP(tm, 13);
     return true;
 }
 
 // ---- task levels: Y = W^+ Tm^T, M_l = Tm_l Y_l, JL_l = Y_l M_l^{-1}, null-space recursion -> Ntorque (stacked, M x TS, in R2) ----
 template <class S>
-__device__ __forceinline__ bool lean_task_levels(double *sm) {
+__device__ __forceinline__ bool lean_task_levels(double *sm, long long *tm) {
     using L = LeanSmem<S>;
     using LV = typename S::Lv;
     constexpr int M = S::M, LDN = S::LDN, LDM = S::LDM, LDT = S::LDT, TS = S::TS;
@@ -338,6 +444,7 @@ __device__ __forceinline__ bool lean_task_levels(double *sm) {
     // Y = W^+ Tm^T   (M x TS)
     lean::mma_gemm<M, TS, M, LDN, LDT, false, true, 2>(Wb, Tm, [&](int i, int j, double v) { Y[i + j * LDM] = v; });
     tsync();
+    LEAN_STAMP(tm, 14);
     // M_l = Tm_l Y_l (t x t, SPD) into the task blocks of R1 (W^+ is dead: tau_grav and Y are formed)
     lean::static_for<0, LV::NL>([&](auto l_) {
         constexpr int l = decltype(l_)::value, t = LV::dof(l), r0 = LV::r0(l), ldb = L::ldb(l);
@@ -345,6 +452,7 @@ __device__ __forceinline__ bool lean_task_levels(double *sm) {
         lean::mma_gemm<t, t, M, LDT, LDM, false, false, 1>(Tm + r0, Y + r0 * LDM, [&](int i, int j, double v) { Ml[i + j * ldb] = v; }, l);
     });
     tsync();
+    LEAN_STAMP(tm, 15);
     // inverses: levels with t <= 8 by one warp each, concurrently; larger ones by the team
     lean::static_for<0, LV::NL>([&](auto l_) {
         constexpr int l = decltype(l_)::value, t = LV::dof(l), ldb = L::ldb(l);
@@ -367,6 +475,7 @@ __device__ __forceinline__ bool lean_task_levels(double *sm) {
         }
     });
     tsync();
+    LEAN_STAMP(tm, 16);
     bool okl = true;
     for (int l = 0; l < LV::NL; l++) okl = okl && (cnd[l] > 1e-14);
     // JL_l = Y_l M_l^{-1} in place (each work item owns one 8-row band of Y_l)
@@ -376,6 +485,7 @@ __device__ __forceinline__ bool lean_task_levels(double *sm) {
         lean::mma_gemm<M, t, t, LDM, ldb, false, false, (t + 7) / 8>(Yl, P + L::mo(l), [&](int i, int j, double v) { Yl[i + j * LDM] = v; }, l);
     });
     tsync();
+    LEAN_STAMP(tm, 17);
     // Ntorque_l = JL_l - Nta[:, 0:r_l] (Tm[0:r_l, :] JL_l), in place, levels in order
     lean::static_for<1, LV::NL>([&](auto l_) {
         constexpr int l = decltype(l_)::value, t = LV::dof(l), rl = LV::r0(l), ldc = ld4(rl);
@@ -385,6 +495,7 @@ __device__ __forceinline__ bool lean_task_levels(double *sm) {
         lean::mma_gemm<M, t, rl, LDM, ldc, false, false, (t + 7) / 8>(Y, Cs, [&](int i, int j, double v) { Yl[i + j * LDM] -= v; });
         tsync();
     });
+    LEAN_STAMP(tm, 18);
     return okl;
 }
 
@@ -437,8 +548,11 @@ __global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__rest
     int &cdof = *(int *)(misc + 6);
     double *tau_grav = w.tau_grav + s * M, *tau_task = w.tau_task + s * M, *tau_contact = w.tau_contact + s * M;
     // ---- a1: sweeps by one warp (rotating with the block index: warp k of every CTA shares an SM sub-partition) ----
-    if (warp == (int)(blockIdx.x % lean::NW)) {
-        rbd_sweeps(md, a.q + s * (N + 1), a.qd + s * N, rb);
+    long long *tm = a.timing ? a.timing + s * 32 : nullptr;
+    LEAN_STAMP(tm, 0);
+    const int serial_warp = (int)(blockIdx.x % lean::NW);
+    rbd_sweeps_lean(md, a.q + s * (N + 1), rb, serial_warp);
+    if (warp == serial_warp) {
         if (lane == 0) {
             // COM quantities of the COM pseudo link (reference src/dwbc.cpp:320-346)
             const double Mtot = rb[RB_IC];
@@ -476,6 +590,7 @@ __global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__rest
         fs[i] = w.fstar[l][s * LV::dof(l) + r];
     }
     tsync();
+    LEAN_STAMP(tm, 1);
     // motion column s_j = [w; v] and force column F_j = Ic_body(j) s_j of every velocity coordinate (R2: 12 x N)
     double *Sc = R2, *Fc = R2 + 6 * N;
     for (int j = tid; j < N; j += nt) {
@@ -515,13 +630,15 @@ __global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__rest
         }
     }
     const int c = cdof;
+    LEAN_STAMP(tm, 2);
     // ---- a1: A^{-1} ----
     lean::spd_inverse<N, LDN, LDN>(P, R2, rd, misc, (int)(blockIdx.x % lean::NW));
+    LEAN_STAMP(tm, 3);
     bool good = misc[0] > 0.0 && (c == 6 || c == 12);
     // ---- a2-a5 ----
     if (good) {
-        if (c == 12) good = lean_contact_task_T<S, 12>(md, cfg, w, s, sm, cix);
-        else good = lean_contact_task_T<S, 6>(md, cfg, w, s, sm, cix);
+        if (c == 12) good = lean_contact_task_T<S, 12>(md, cfg, w, s, sm, cix, tm);
+        else good = lean_contact_task_T<S, 6>(md, cfg, w, s, sm, cix, tm);
         good = good && ok != 0;
     }
     if (!good) {  // uniform: no contact / too many contacts / a factorisation failed -> status 0, zero torques
@@ -532,7 +649,7 @@ __global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__rest
     for (int i = tid; i < M; i += nt) tau_grav[i] = tgv[i], tau_contact[i] = 0.0;
     int st = 1;
     bool task_ok = true;
-    if constexpr (TS > 0) task_ok = lean_task_levels<S>(sm);
+    if constexpr (TS > 0) task_ok = lean_task_levels<S>(sm, tm);
     const double *Nta = R2;  // Ntorque of all levels, M x TS (LDM)
     bool active = false;
     if constexpr (TS > 0) {
@@ -574,6 +691,7 @@ __global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__rest
             else active = true;
         }
     }
+    LEAN_STAMP(tm, 19);
     // torque_task_ so far: final for an inactive state; for an active one hqp_kernel recomputes it (hqp) or reads it (closed form + redistribution QP)
     for (int i = tid; i < M; i += nt) tau_task[i] = (TS > 0 && (!a.hqp || task_ok)) ? tt[i] : 0.0;
     if (TS > 0 && a.hqp) {  // f_star_qp_ / contact_qp_ / active sets of a state whose QPs all end at x = 0 (hqp_kernel rewrites them for the others)
@@ -590,6 +708,7 @@ __global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__rest
     }
     if (!active) {
         if (tid == 0) w.status[s] = st, w.cdof[s] = c, w.qp_iters[s] = 0;
+        LEAN_STAMP(tm, 20);
         return;
     }
     // ---- QP-active state: hand the operands of the QPs to hqp_kernel (generic workspace layout) and enlist the state ----
@@ -627,6 +746,7 @@ __global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__rest
             a.list[slot] = (int)s;
         }
     }
+    LEAN_STAMP(tm, 20);
 }
 
 }  // namespace dwbc

@@ -134,6 +134,7 @@ inline unsigned __ballot_sync(unsigned, int pred) {
 }
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, !pred) == 0; }
+inline long long clock64() { return 0; }
 inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

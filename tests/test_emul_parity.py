@@ -166,7 +166,7 @@ def test_emul_tight_torque_limit():
     run_tight_torque_limit(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, lambda a: a, 6)
 
 
-def run_sliced_cycle_host(make_rd, D, B, variants):
+def run_sliced_cycle_host(make_rd, D, B, variants, outputs=1):
     """dwbc_batch_cycle_host cut into slices (copies of one slice under the kernels of another) returns bit for bit what the
     unsliced call returns: ragged slice sizes, mixed support, shared and per-state custom Jacobian."""
     q, qd, rng = synth_states(B, 11)
@@ -180,10 +180,11 @@ def run_sliced_cycle_host(make_rd, D, B, variants):
     outs = []
     for slices, per_state in variants:
         rd = configure_product(make_rd(B), 2)
+        rd.set_outputs(outputs)  # 1 = OUT_ALL: the generic kernels, comparable bit for bit with the staged calls; 0 = the one-kernel cycle
         rd.set_task_space(2, D(np.zeros((B, 21))), D(Jps if per_state else Jp))
         rd.set_host_slices(slices)
         outs.append([np.array(a) for a in rd.cycle_host(ALL, q, qd, fs, flags)])
-        assert rd.batch == B and rd.get("A").shape[0] == B  # the handle describes the whole batch again afterwards
+        assert rd.batch == B and rd.get("A" if outputs == 1 else "torque_grav").shape[0] == B  # the handle describes the whole batch again afterwards
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
             assert np.array_equal(a, b)
@@ -193,6 +194,7 @@ def run_sliced_cycle_host(make_rd, D, B, variants):
 
 def test_emul_sliced_cycle_host():
     run_sliced_cycle_host(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, 4, ((1, False), (3, True)))
+    run_sliced_cycle_host(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, 4, ((1, False), (3, True)), outputs=0)
 
 
 def test_emul_split_call_order_equals_fused():

@@ -252,7 +252,9 @@ def test_cycle_host_matches_device_calls():
     fs = synth_fstar(rng, B)
     flags = np.ones((B, 2), dtype=np.uint8)
     rd, (tg, tt, tc, st) = run_product(2, q, qd, fs, flags, ALL)
+    from libdwbc_b200 import OUT_ALL
     rd2 = configure_product(RobotDataBatch(URDF, B, 0), 2)
+    rd2.set_outputs(OUT_ALL)  # same kernels as the staged calls above (the default of cycle_host is the one-kernel cycle, tested below)
     rd2.set_task_space(2, T(np.zeros((B, 21))), T(posture_selector()))
     tg2, tt2, tc2, st2 = rd2.cycle_host(ALL, q, qd, fs, flags)
     assert np.array_equal(tg, tg2) and np.array_equal(tt, tt2) and np.array_equal(tc, tc2) and np.array_equal(st, st2)

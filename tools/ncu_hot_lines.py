@@ -15,6 +15,7 @@ import tempfile
 rep, kern, so = sys.argv[1], sys.argv[2], os.path.abspath(sys.argv[3])
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
 by_inst = len(sys.argv) > 5 and sys.argv[5] == "inst"  # sort by executed instructions instead of stall samples
+mangled = os.environ.get("FUNC_FILTER", "")  # extra substring of the mangled name (template instantiations share the kernel name)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
@@ -38,7 +39,7 @@ for cubin in glob.glob(d + "/*.cubin"):
         m = re.match(r"\.text\.(\S+):", line)
         if m:
             func = m.group(1)
-        if func and kern in func and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
+        if func and kern in func and mangled in func and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
             acc.append(cur)
     if acc:
         lines = acc
