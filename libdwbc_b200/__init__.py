@@ -32,3 +32,4 @@ from .batch import (  # noqa: F401
     RobotDataBatch,
 )
 from .bridge import RlWBCBridge, RlWBCBridgeBatch  # noqa: F401,E402
+from .multi import RobotDataMultiBatch  # noqa: F401,E402

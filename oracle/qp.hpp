@@ -231,6 +231,20 @@ inline bool ldp(const Mat &G, const std::vector<double> &h, std::vector<double> 
     if (getenv("ORC_QP_DEBUG")) fprintf(stderr, "  ldp: n=%d mr=%d rn=%.3e r[n]=%.3e\n", n, mr, rn, r[n]);
     if (rn < 1e-11 || !(r[n] < 0)) return false;
     for (int j = 0; j < n; j++) x[j] = -r[j] / r[n];
+    // Guard against a false "feasible": for an infeasible problem the NNLS residual is zero up to rounding, and a residual that
+    // lands just above the threshold gives a meaningless x = -r / r[n] (seen once in 65 536 states: |r| = 3e-11, rows violated by
+    // 49).  The answer must satisfy every row to the accuracy of this solver.
+    {
+        double xn2 = 0;
+        for (int j = 0; j < n; j++) xn2 += x[j] * x[j];
+        const double xn = std::sqrt(xn2);
+        for (int k = 0; k < mr; k++) {
+            double gx = 0;
+            for (int j = 0; j < n; j++) gx += G(rows[k], j) * x[j];
+            const double viol = (h[rows[k]] - gx) * scale[k];  // > 0: violated, in units of the normalised row
+            if (viol > 1e-6 * (1.0 + xn + std::fabs(h[rows[k]]) * scale[k])) return false;
+        }
+    }
     for (int k = 0; k < mr; k++) lambda[rows[k]] = u[k] * scale[k] / (-r[n]);
     return true;
 }
@@ -309,13 +323,18 @@ inline QpResult lexqp(const Mat &A, const std::vector<double> &ub, int t, double
     double delta = delta0 * (nc / r) / std::max(nt / t, 1e-300);
     double sq = std::sqrt(delta);
     Mat G(m, n);
-    for (int i = 0; i < m; i++) {
-        for (int j = 0; j < t; j++) G(i, j) = -At(i, j);
-        for (int j = 0; j < r; j++) G(i, t + j) = -Ac(i, j) / sq;
-    }
+    auto scale_G = [&]() {
+        for (int i = 0; i < m; i++) {
+            for (int j = 0; j < t; j++) G(i, j) = -At(i, j);
+            for (int j = 0; j < r; j++) G(i, t + j) = -Ac(i, j) / sq;
+        }
+    };
+    scale_G();
     std::vector<double> c(r, 0.0), h(m), y, lam, xprev(n, 0.0), x(n, 0.0);
     bool conv = false;
-    for (int k = 0; k < 30; k++) {
+    double dn_prev = 0.0;
+    int reductions = 0;
+    for (int k = 0; k < 40; k++) {
         for (int i = 0; i < m; i++) {
             double s = ub[i];
             for (int j = 0; j < r; j++) s -= Ac(i, j) * c[j];
@@ -330,13 +349,22 @@ inline QpResult lexqp(const Mat &A, const std::vector<double> &ub, int t, double
         for (int j = 0; j < t; j++) dn += (x[j] - xprev[j]) * (x[j] - xprev[j]), xn += x[j] * x[j];
         xprev = x;
         for (int j = 0; j < r; j++) c[j] = x[t + j];
-        if (getenv("ORC_QP_DEBUG")) fprintf(stderr, "prox %d dx_t %.3e |x_t| %.3e\n", k, std::sqrt(dn), std::sqrt(xn));
+        if (getenv("ORC_QP_DEBUG")) fprintf(stderr, "prox %d dx_t %.3e |x_t| %.3e delta %.3e\n", k, std::sqrt(dn), std::sqrt(xn), delta);
         // converged; or stalled at the accuracy of the NNLS-based inner solve (seen at |x_t| ~ 1e3: steps of 1e-10 relative that
         // never reach 1e-12) -- the iterate is then as good as this oracle gets and far inside the 1e-6 parity tolerance
         if (k > 0 && (std::sqrt(dn) <= 1e-12 * (1.0 + std::sqrt(xn)) || (k >= 8 && std::sqrt(dn) <= 5e-10 * (1.0 + std::sqrt(xn))))) {
             conv = true;
             break;
         }
+        // contraction ratio delta / (delta + sigma): on a nearly degenerate optimal face (sigma tiny) the default delta crawls;
+        // a step that shrinks by less than half switches to a 100 times smaller delta.  The limit does not depend on delta.
+        if (k >= 2 && reductions < 3 && dn > 0.25 * dn_prev) {
+            delta *= 0.01;
+            sq = std::sqrt(delta);
+            scale_G();
+            reductions++;
+        }
+        dn_prev = dn;
     }
     if (!conv) return res;
     // Stage 2 on the optimal face: rows with a positive multiplier are equalities.

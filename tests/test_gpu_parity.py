@@ -709,7 +709,15 @@ def _full_parity(B, seed, mixed, outputs):
     flags = _mixed_flags(B, rng) if mixed else np.ones((B, 2), dtype=np.uint8)
     rd, (tg, tt, tc, st) = run_lean(2, q, qd, fs, flags, ALL, outputs=outputs)
     o = configure_oracle(orc.OracleRobot(URDF), 2).run_batch(q, qd, fs, flags, sets=True)
-    assert np.array_equal(st & 7, o["status"] & 7)
+    bad = np.where((st & 7) != (o["status"] & 7))[0]
+    if len(bad):  # leave the evidence where the builder can pick it up (gpurun_out/ travels back from the GPU box)
+        import json
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"status_mismatch_B{B}_{'mixed' if mixed else 'ds'}_out{outputs}.json"), "w") as f:
+            json.dump({"seed": seed, "B": B, "mixed": mixed, "index": bad.tolist(), "gpu": st[bad].tolist(), "oracle": o["status"][bad].tolist(),
+                       "iters": rd.qp_iterations().cpu().numpy()[bad].tolist(), "n_gpu_not7": int(((st & 7) != 7).sum()),
+                       "n_oracle_not7": int(((o["status"] & 7) != 7).sum())}, f)
+    assert np.array_equal(st & 7, o["status"] & 7), (len(bad), bad[:10], st[bad][:10], o["status"][bad][:10])
     good = (o["status"] & 7) == 7
     assert good.mean() > 0.99
     scale = lambda a: np.maximum(1.0, np.abs(a).max(axis=1))
