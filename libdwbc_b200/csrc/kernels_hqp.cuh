@@ -195,15 +195,16 @@ __device__ __forceinline__ double team_sum(double v, const GiScratch &S) {
 // isd_j = isd_t for j < tsplit, isd_c otherwise.  `pin` (may be null): rows to be pinned as equalities, added first and never
 // dropped.  On return S.dxs holds dx, S.act / S.u the active rows and their multipliers (logical positions < q).
 // Deliberately NOT inlined (instruction-cache footprint, profiles/r01_ncu_summary.md).  Synchronises on entry and exit.
+// boff: offset of this problem's first row in the right-hand-side array b (2m when the torque rows are left out, mt = 0)
 __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, int mt, int nc, int col0, int nv, int use_bt, double isd_t,
-                                          double isd_c, int tsplit, int use_pin, int max_iter, double ztol) {
+                                          double isd_c, int tsplit, int use_pin, int max_iter, double ztol, int boff) {
     // Everything is re-derived from the arena base and a few integers: structs passed by reference to a non-inlined function
     // live in local memory, and with most of L1 carved out as shared memory those loads went to L2 (ncu: 20 % L1 hit rate,
     // long-scoreboard the second largest stall of the first team version).
     const HqpSmem L(n, m, nvmax);
     const GiScratch S(sm + L.gi, sm + L.bt);
     const QpView V{sm + L.U, sm + L.AU, L.ldm, L.ldc, m, mt, nc, col0, nv};
-    const double *bt = use_bt ? sm + L.bt : sm + L.b, *tolv = sm + L.tol;
+    const double *bt = use_bt ? sm + L.bt : sm + L.b + boff, *tolv = sm + L.tol;
     double *rin = sm + L.rin, *Q = sm + L.Q, *R = sm + L.R;
     const int ldq = L.ldq;
     const uint32_t *pin = use_pin ? S.pinw : nullptr;
@@ -588,6 +589,16 @@ __device__ __noinline__ bool gi_warm(double *sm, int n, int m, int nvmax, int mt
     return !bad;
 }
 
+
+// active_out[k] = bits of mask (ACTIVE_WORDS words in shared memory) shifted up by `shift` rows
+__device__ __forceinline__ uint32_t shifted_word(const uint32_t *mask, int k, int shift) {
+    const int ws = shift >> 5, bs = shift & 31;
+    const int a = k - ws;
+    uint32_t lo = (a >= 0 && a < ACTIVE_WORDS) ? mask[a] : 0u;
+    uint32_t hi = (a - 1 >= 0 && a - 1 < ACTIVE_WORDS) ? mask[a - 1] : 0u;
+    return bs ? ((lo << bs) | (hi >> (32 - bs))) : lo;
+}
+
 struct LevelOut {
     int status;
     int iters;
@@ -597,10 +608,13 @@ struct LevelOut {
 // Solves one QP (t task variables first, then r contact variables) with the whole team.  U (m x nv), AU (nc x nv) and b (rows)
 // are in shared memory; the solution is left in S.xj.  active_out (global, ACTIVE_WORDS words): rows with zero slack at the
 // solution.  Synchronises on entry and exit.
-__device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax, int t, int r, int mt, int nc, uint32_t *active_out) {
+// boff / row_shift: the problem's rows start at b[boff] and are reported as rows row_shift.. (a solve without the torque rows: mt = 0,
+// boff = row_shift = 2m keeps the reference's row numbering in the active set).
+__device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax, int t, int r, int mt, int nc, uint32_t *active_out, int boff,
+                                             int row_shift) {
     const HqpSmem L(n, m, nvmax);
     const GiScratch S(sm + L.gi, sm + L.bt);
-    const double *b = sm + L.b;
+    const double *b = sm + L.b + boff;
     double *tolv = sm + L.tol, *rin = sm + L.rin;
     const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
     const int nv = t + r, mc = mt + nc;
@@ -668,13 +682,15 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
     }
     if (bmin >= 0.0) {
         // x = 0 satisfies every row: optimal for both stages, no factorisation needed
-        if (active_out && tid < ACTIVE_WORDS) active_out[tid] = tid < (mc + 31) / 32 ? S.pinw[tid] : 0u;
+        if (tid < ACTIVE_WORDS && tid >= (mc + 31) / 32) S.pinw[tid] = 0u;
+        tsync();
+        if (active_out && tid < ACTIVE_WORDS) active_out[tid] = shifted_word(S.pinw, tid, row_shift);
         return out;
     }
     const int max_iter = 20 * (nv + 8);
     bool done = false;
     if (t == 0 || r == 0) {
-        GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, 0, nv, 0, 1.0, 1.0, nv, 0, max_iter, zero_row_tol);
+        GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, 0, nv, 0, 1.0, 1.0, nv, 0, max_iter, zero_row_tol, boff);
         out.iters += g.iters;
         out.status = g.status;
         if (tid < nv) xj[tid] = S.dxs[tid];
@@ -684,7 +700,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
         // ---- A: is x_t = 0 attainable?  (looser tolerances: the set may be a thin face inherited from the levels above)
         DWBC_UNROLL(1)
         for (int i = tid; i < mc; i += nt) tolv[i] *= 100.0;
-        GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, t, r, 0, 1.0, 1.0, r, 0, max_iter, zero_row_tol);
+        GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, t, r, 0, 1.0, 1.0, r, 0, max_iter, zero_row_tol, boff);
         out.iters += g.iters;
         if (g.status) {
             if (tid < r) xj[t + tid] = S.dxs[tid];
@@ -728,7 +744,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
             if (k > 0 && !force_cold && gi_warm(sm, n, m, nvmax, mt, nc, 0, nv, g.q)) {
                 out.iters += 1;
             } else {
-                g = gi_solve(sm, n, m, nvmax, mt, nc, 0, nv, 1, 1.0, isd_c, t, 0, max_iter, zero_row_tol);
+                g = gi_solve(sm, n, m, nvmax, mt, nc, 0, nv, 1, 1.0, isd_c, t, 0, max_iter, zero_row_tol, boff);
                 out.iters += g.iters;
             }
             force_cold = false;
@@ -786,7 +802,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
                 bt[i] = s;
                 tolv[i] *= 100.0;
             }
-            GiResult gc = gi_solve(sm, n, m, nvmax, mt, nc, t, r, 1, 1.0, 1.0, r, 1, max_iter, zero_row_tol);
+            GiResult gc = gi_solve(sm, n, m, nvmax, mt, nc, t, r, 1, 1.0, 1.0, r, 1, max_iter, zero_row_tol, boff);
             out.iters += gc.iters;
             if (!gc.status) out.status = 0;
             if (tid < r) xj[t + tid] = S.dxs[tid];
@@ -814,8 +830,9 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
         const int word = (i0 >> 5) + warp;
         if (lane == 0 && word < ACTIVE_WORDS) S.pinw[word] = bal;
     }
+    if (tid < ACTIVE_WORDS && tid >= (mc + 31) / 32) S.pinw[tid] = 0u;
     tsync();
-    if (active_out && tid < ACTIVE_WORDS) active_out[tid] = tid < (mc + 31) / 32 ? S.pinw[tid] : 0u;
+    if (active_out && tid < ACTIVE_WORDS) active_out[tid] = shifted_word(S.pinw, tid, row_shift);
     tsync();
     return out;
 }
@@ -968,7 +985,34 @@ __global__ void __launch_bounds__(TEAM, 7) hqp_kernel(const DevModel *__restrict
                 }
             tgemv<false>(nc, m, At, ldc, base, [&](int i, double v) { b[mt + i] = -(bA0[i] - v); });
             tsync();
-            const LevelOut lo = solve_level(sm, n, m, nvmax, t, r, mt, nc, w.active[lev ? q : MAX_LEVELS] + s * ACTIVE_WORDS);
+            // The torque-limit rows (2m of the 2m + 10k rows) are almost never active (0 of 16 384 sampled states of the headline
+            // workload): solve on the contact rows alone and accept the answer when it satisfies every torque row strictly -- it is then
+            // the optimum of the full problem as well (both lexicographic stages: an optimum of a relaxation that is feasible for the
+            // full problem).  An infeasible relaxation means an infeasible problem.  Only a torque row at or over its limit sends the QP
+            // through the full row set.
+            uint32_t *aout = w.active[lev ? q : MAX_LEVELS] + s * ACTIVE_WORDS;
+            LevelOut lo = solve_level(sm, n, m, nvmax, t, r, 0, nc, aout, mt, mt);
+            if (mt && lo.status) {
+                if (tid == 0) S.ired[0] = 1;
+                tsync();
+                bool okr = true;
+                for (int i = tid; i < m; i += nt) {
+                    double ux = 0.0;
+                    DWBC_UNROLL(1)
+                    for (int j = 0; j < nv; j++) ux = fma(U[i + j * ldm], S.xj[j], ux);
+                    const double lo_s = b[i] - ux, hi_s = b[m + i] + ux;
+                    okr = okr && lo_s > 1e-8 * (1.0 + fabs(b[i])) && hi_s > 1e-8 * (1.0 + fabs(b[m + i]));
+                }
+                if (!okr) S.ired[0] = 0;
+                tsync();
+                const bool all_in = S.ired[0] != 0;
+                tsync();
+                if (!all_in) {
+                    const int it0 = lo.iters;
+                    lo = solve_level(sm, n, m, nvmax, t, r, mt, nc, aout, 0, 0);
+                    lo.iters += it0;
+                }
+            }
             total_iters += lo.iters;
             if (lo.slow) st |= 16;
             solved = lo.status != 0;

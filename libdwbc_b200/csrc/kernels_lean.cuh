@@ -299,28 +299,49 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
             V[a + b * LDM] = v;
         }
         tsync();
-        for (int pass = 0; pass < 2; pass++) {  // Cholesky-QR, twice: G = V^T V = R^T R, V <- V R^{-1}
-            for (int e = tid; e < R * R; e += nt) {
-                const int j = e / R, i = e - j * R;
-                if (i <= j) {
-                    double d = 0.0;
-                    for (int a = 0; a < M; a++) d = fma(V[a + i * LDM], V[a + j * LDM], d);
-                    Aug[i + j * lda] = d;
-                }
-            }
-            tsync();
-            if (warp == 3 && !wchol_upper_packed(R, Aug, lda, lane) && lane == 0) ok = 0;
-            tsync();
-            for (int a = tid; a < M; a += nt) {
-                DWBC_UNROLL(R)
-                for (int j = 0; j < R; j++) {
-                    double x = V[a + j * LDM];
-                    for (int k = 0; k < j; k++) x = fma(-V[a + k * LDM], Aug[k + j * lda], x);
-                    V[a + j * LDM] = x / Aug[j + j * lda];
-                }
-            }
-            tsync();
+        // V does not have to be orthonormal: for ANY basis V of null(W), with G = V^T V,
+        //     (W + V V^T)^{-1} = W^+ + V G^{-2} V^T          (W symmetric, range(W) orthogonal to span V)
+        // and NwJw = V (Jbar^T[0:r, 6:] V)^{-1} does not depend on the basis.  Only the columns are normalised (conditioning of
+        // W + V V^T); G^{-1} is a 6 x 6 SPD inverse on one warp.  VG = V G^{-2} is kept for the correction after the big inverse.
+        // (The orthonormal V2 of the reference is a public field of DWBC_OUT_ALL only.)
+        double *Gm = Aug, *G2 = Aug + 6 * lda;  // two 6 x 6 blocks inside the 13 x 13 scratch
+        if (tid < R) {
+            double d = 0.0;
+            for (int a = 0; a < M; a++) d = fma(V[a + tid * LDM], V[a + tid * LDM], d);
+            Gm[12 * lda + tid] = rsqrt(d);  // column scales (row 12 of the scratch is free)
         }
+        tsync();
+        for (int e = tid; e < M * R; e += nt) V[(e % M) + (e / M) * LDM] *= Gm[12 * lda + e / M];
+        tsync();
+        for (int e = tid; e < R * R; e += nt) {
+            const int j = e / R, i = e - j * R;
+            double d = 0.0;
+            for (int a = 0; a < M; a++) d = fma(V[a + i * LDM], V[a + j * LDM], d);
+            Gm[i + j * lda] = d;
+        }
+        tsync();
+        if (warp == 3) {
+            const double cg = lean::warp_spd_inverse_small<R, lda>(Gm, G2);
+            if (!(cg > 1e-13) && lane == 0) ok = 0;
+        }
+        tsync();
+        for (int e = tid; e < R * R; e += nt) {  // G2 = G^{-1} G^{-1}
+            const int j = e / R, i = e - j * R;
+            double d = 0.0;
+            DWBC_UNROLL(R)
+            for (int k = 0; k < R; k++) d = fma(Gm[i + k * lda], Gm[k + j * lda], d);
+            G2[i + j * lda] = d;
+        }
+        tsync();
+        double *VG = sm + L::NwJw;  // V G^{-2} (M x R); NwJw itself is formed last, in the same place
+        for (int e = tid; e < M * R; e += nt) {
+            const int j = e / M, i = e - j * M;
+            double d = 0.0;
+            DWBC_UNROLL(R)
+            for (int k = 0; k < R; k++) d = fma(V[i + k * LDM], G2[k + j * lda], d);
+            VG[i + j * LDM] = d;
+        }
+        tsync();
     } else {
         tsync();
     }
@@ -394,7 +415,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
     if (!(misc[0] > 0.0)) return false;
     LEAN_STAMP(tm, 12);
     if constexpr (R > 0) {
-        lean::mma_gemm_sym<M, R, LDM, LDM, false, true>(V, V, [&](int i, int j, double v) {
+        lean::mma_gemm_sym<M, R, LDM, LDM, false, true>(sm + L::NwJw, V, [&](int i, int j, double v) {  // W^+ = (W + V V^T)^{-1} - (V G^{-2}) V^T
             Wb[i + j * LDN] -= v;
             if (i != j) Wb[j + i * LDN] -= v;
         });
