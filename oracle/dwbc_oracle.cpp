@@ -282,6 +282,11 @@ struct Robot {
     void lqp_prepare();
     int lqp_solve_level(int i);
     int calc_lqp();
+    // ConfigureLQP_R_NC + CalcControlTorqueLQP_R_NC (reference src/dwbc.cpp:4634-4760, 4479-4502): the non-contact chain's own hierarchy
+    std::vector<LqpLevel> lqp_nc;
+    Mat lqp_nc_H, lqp_nc_torque, lqp_stitched;  // cost; A_NC[nc,nc] qdd_nc + G_NC; the 33-joint torque of jacc_compare.cpp:543-569
+    void configure_lqp_r_nc();
+    int calc_lqp_r_nc();
 };
 
 void Robot::update_kinematics(const double *q_, const double *qd_) {
@@ -1507,6 +1512,115 @@ int Robot::calc_lqp() {
     return ok;
 }
 
+// ConfigureLQP_R_NC, reference src/dwbc.cpp:4634-4760.  Decision vector: the nc_dof joint accelerations of the non-contact chain, no
+// contact force.  q_acc = the acceleration part of the reduced LQP's final answer (hqp_.hqp_hs_.back().y_ans_.head(acc), reference
+// tests/sp_test/jacc_compare.cpp:485-486): its first 6 entries are the base acceleration, its last 6 the centroidal acceleration of the
+// condensed body.  Level 0 (solved, through HQP::solvefirst): J_I_nc qdd = fstar_gnc, torque rows +-200 on A_NC[nc,nc] qdd + G_NC;
+// level 1: the 6D task of ts_[1] -- hard-coded in the reference (:4738-4745) -- in the pelvis-relative form Ja (f* - fstar_base),
+// |qdd| <= 5.  Rows are NOT normalised here (updateConstraintMatrix is called on the raw matrices, :4677, 4755).
+void Robot::configure_lqp_r_nc() {
+    const int nc = nc_dof, acc = rsys;
+    Mat q_acc(acc, 1);
+    for (int i = 0; i < acc; i++) q_acc[i] = lqp.back().y[i];
+    lqp_nc.clear();
+    Mat Ann = A_NC.block(6, 6, nc, nc);
+    lqp_nc_H = Ann;  // :4647
+    {
+        const double sc = 5.0 / Ann.norm();
+        for (int i = 0; i < nc * nc; i++) lqp_nc_H[i] *= sc;
+    }
+    {   // virtual predecessor of level 0: the whole space, y = 0 (HQP::solvefirst works on the raw variables, src/dwbc_hqp.cpp:222-289)
+        LqpLevel L;
+        L.Z = Mat::identity(nc);
+        L.nu = nc;
+        L.y.set_zero(nc, 1);
+        L.v.set_zero(0, 1);
+        L.status = 1;
+        lqp_nc.push_back(L);
+    }
+    {   // level 0  :4649-4678
+        LqpLevel L;
+        L.nineq = 2 * nc;
+        L.neq = 6;
+        L.A.set_zero(2 * nc, nc);
+        L.a.set_zero(2 * nc, 1);
+        L.B = J_I_nc;
+        L.b.set_zero(6, 1);
+        for (int i = 0; i < 6; i++) L.b[i] = -q_acc[acc - 6 + i];
+        for (int i = 0; i < nc; i++) {
+            for (int j = 0; j < nc; j++) L.A(i, j) = Ann(i, j), L.A(nc + i, j) = -Ann(i, j);
+            L.a[i] = -200.0 + G[nc_joint[i]];
+            L.a[nc + i] = -200.0 - G[nc_joint[i]];
+        }
+        L.cost = true;
+        lqp_nc.push_back(L);
+    }
+    {   // level 1  :4735-4757
+        LqpLevel L;
+        const Task &t = ts[1];
+        L.nineq = 2 * nc;
+        L.neq = 6;
+        M3 sk = skew3(pw[t.links[0].link] - pw[0]);
+        Mat Ja = Mat::identity(6);
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) Ja(a, 3 + b) = sk.m[a][b];
+        Mat df(6, 1);
+        for (int i = 0; i < 6; i++) df[i] = t.fstar[i] - q_acc[i];
+        Mat fl = Ja * df;
+        L.B.set_zero(6, nc);
+        L.b.set_zero(6, 1);
+        for (int j = 0; j < nc; j++)
+            for (int i = 0; i < 6; i++) L.B(i, j) = t.J(i, n - nc + j);  // J_task_.rightCols(nc_dof)
+        for (int i = 0; i < 6; i++) L.b[i] = -fl[i];
+        L.A.set_zero(2 * nc, nc);
+        L.a.set_zero(2 * nc, 1);
+        for (int i = 0; i < nc; i++) {
+            L.A(i, i) = 1.0;
+            L.A(nc + i, i) = -1.0;
+            L.a[i] = -5.0;
+            L.a[nc + i] = -5.0;
+        }
+        L.cost = true;
+        lqp_nc.push_back(L);
+    }
+    // HQP::prepare: null spaces of the stacked equalities
+    for (size_t i = 1; i < lqp_nc.size(); i++) {
+        Mat Bn = lqp_nc[i].B * lqp_nc[i - 1].Z;
+        lqp_nc[i].Z = lqp_nc[i - 1].Z * lqp_null_space(Bn);
+        lqp_nc[i].nu = lqp_nc[i].Z.c;
+    }
+}
+
+// CalcControlTorqueLQP_R_NC (reference src/dwbc.cpp:4479-4502): solvefirst + solveSequential, then the torque stitching of the only
+// caller (reference tests/sp_test/jacc_compare.cpp:543-569): joints of the contact chain from the reduced LQP, the others from
+// A_NC[nc,nc] qdd_nc + G_NC.
+int Robot::calc_lqp_r_nc() {
+    std::swap(lqp, lqp_nc);
+    std::swap(lqp_H, lqp_nc_H);
+    int ok = 1;
+    for (size_t i = 1; i < lqp.size(); i++) {
+        if (!lqp_solve_level((int)i)) {
+            ok = 0;
+            for (size_t k = i; k < lqp.size(); k++) lqp[k].y = lqp[i - 1].y, lqp[k].status = 0;
+            break;
+        }
+    }
+    std::swap(lqp, lqp_nc);
+    std::swap(lqp_H, lqp_nc_H);
+    const int nc = nc_dof;
+    const Mat &y = lqp_nc.back().y;
+    lqp_nc_torque.set_zero(nc, 1);
+    for (int i = 0; i < nc; i++) {
+        double s_ = G[nc_joint[i]];
+        for (int j = 0; j < nc; j++) s_ += A_NC(6 + i, 6 + j) * y[j];
+        lqp_nc_torque[i] = s_;
+    }
+    lqp_stitched.set_zero(m, 1);
+    for (int i = 0; i < co_dof; i++) lqp_stitched[i] = lqp_torque[i];
+    for (int i = 0; i < nc; i++) lqp_stitched[m - nc + i] = lqp_nc_torque[i];
+    return ok;
+}
+
 extern "C" {
 
 void *orc_create(int nb, const int *parent, const double *E_T, const double *r_T, const double *axis, const double *mass,
@@ -1617,6 +1731,8 @@ void orc_configure_lqp(void *h) { ((Robot *)h)->configure_lqp(false); }
 void orc_configure_lqp_r(void *h) { ((Robot *)h)->configure_lqp(true); }
 int orc_calc_lqp(void *h) { return ((Robot *)h)->calc_lqp(); }
 int orc_lqp_levels(void *h) { return (int)((Robot *)h)->lqp.size(); }
+void orc_configure_lqp_r_nc(void *h) { ((Robot *)h)->configure_lqp_r_nc(); }
+int orc_calc_lqp_r_nc(void *h) { return ((Robot *)h)->calc_lqp_r_nc(); }
 void orc_reduced_dims(void *h, int *out) {
     Robot *R = (Robot *)h;
     out[0] = R->co_dof; out[1] = R->nc_dof; out[2] = R->vc_dof; out[3] = R->rsys; out[4] = R->rmod;
@@ -1709,6 +1825,24 @@ static const Mat *find_mat(Robot *R, const std::string &name, Mat &tmp) {
     int l;
     if (name == "lqp_H") return &R->lqp_H;
     if (name == "lqp_torque") return &R->lqp_torque;
+    if (name == "lqp_nc_H") return &R->lqp_nc_H;
+    if (name == "lqp_nc_torque") return &R->lqp_nc_torque;
+    if (name == "lqp_stitched_torque") return &R->lqp_stitched;
+    {
+        const int nl = (int)R->lqp_nc.size();
+        if ((l = lvl("lqpnc_y")) >= 0 && l < nl) return &R->lqp_nc[l].y;
+        if ((l = lvl("lqpnc_v")) >= 0 && l < nl) return &R->lqp_nc[l].v;
+        if ((l = lvl("lqpnc_w")) >= 0 && l < nl) return &R->lqp_nc[l].w;
+        if ((l = lvl("lqpnc_Z")) >= 0 && l < nl) return &R->lqp_nc[l].Z;
+        if ((l = lvl("lqpnc_A")) >= 0 && l < nl) return &R->lqp_nc[l].A;
+        if ((l = lvl("lqpnc_a")) >= 0 && l < nl) return &R->lqp_nc[l].a;
+        if ((l = lvl("lqpnc_B")) >= 0 && l < nl) return &R->lqp_nc[l].B;
+        if ((l = lvl("lqpnc_b")) >= 0 && l < nl) return &R->lqp_nc[l].b;
+        if ((l = lvl("lqpnc_qpH")) >= 0 && l < nl) return &R->lqp_nc[l].qpH;
+        if ((l = lvl("lqpnc_qpg")) >= 0 && l < nl) return &R->lqp_nc[l].qpg;
+        if ((l = lvl("lqpnc_qpA")) >= 0 && l < nl) return &R->lqp_nc[l].qpA;
+        if ((l = lvl("lqpnc_qpub")) >= 0 && l < nl) return &R->lqp_nc[l].qpub;
+    }
     {
         const int nl = (int)R->lqp.size();
         if ((l = lvl("lqp_y")) >= 0 && l < nl) return &R->lqp[l].y;

@@ -236,6 +236,15 @@ class OracleRobot:
     def calc_lqp(self):
         return lib().orc_calc_lqp(self.h)
 
+    def configure_lqp_r_nc(self):
+        """ConfigureLQP_R_NC (reference src/dwbc.cpp:4634-4760) from the final answer of the reduced LQP (call configure_lqp(True) and
+        calc_lqp() first); levels: 0 = whole space (virtual), 1 = centroidal equality + torque rows, 2 = the 6D task of ts_[1]"""
+        lib().orc_configure_lqp_r_nc(self.h)
+
+    def calc_lqp_r_nc(self):
+        """CalcControlTorqueLQP_R_NC (:4479-4502) + the torque stitching of tests/sp_test/jacc_compare.cpp:543-569"""
+        return lib().orc_calc_lqp_r_nc(self.h)
+
     def contact_force(self, torque):
         """getContactForce(command_torque), reference src/dwbc.cpp:891-896"""
         _, tp = _d(torque)

@@ -15,6 +15,7 @@
 #endif
 #include <pthread.h>
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>

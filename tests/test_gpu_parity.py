@@ -734,6 +734,16 @@ def _full_parity(B, seed, mixed, outputs):
     n_active = int((o["active"][good] != 0).any(axis=(1, 2)).sum())
     print(f"B={B} mixed={mixed}: {int(good.sum())} solved, {n_active} with an active QP row, torque errors {eg:.1e} {et:.1e} {ec:.1e}, "
           f"{n_exempt} states used a gray-row exemption, {n_hard} differ outside gray rows, slow flag on {int(((st & 16) != 0).sum())}")
+    if n_hard or n_exempt >= 1e-3 * B:
+        import json
+        gi = np.where(good)[0]
+        hs = gi[np.where((hard != 0).any(axis=(1, 2)))[0]][:64]
+        es = gi[np.where((exempt != 0).any(axis=(1, 2)))[0]][:64]
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"active_mismatch_B{B}_{'mixed' if mixed else 'ds'}_out{outputs}.json"), "w") as f:
+            json.dump({"seed": seed, "B": B, "mixed": mixed, "n_hard": n_hard, "n_exempt": n_exempt,
+                       "hard": [{"i": int(i), "gpu": act[i].tolist(), "oracle": o["active"][i].tolist(), "gray": o["gray"][i].tolist()} for i in hs],
+                       "exempt": [{"i": int(i), "gpu": act[i].tolist(), "oracle": o["active"][i].tolist(), "gray": o["gray"][i].tolist()} for i in es]}, f)
     assert n_hard == 0
     assert n_exempt < 1e-3 * B
     assert n_active > 0.2 * B  # the batch does exercise the active-set logic

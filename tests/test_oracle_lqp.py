@@ -153,3 +153,84 @@ def test_reduced_lqp_oracle_kkt_and_physics():
         B1, y1 = red.get("lqp_B1"), red.get("lqp_y1")[:, 0]
         assert np.linalg.norm(B1 @ (y - y1)) < 1e-8
         assert full.get("lqp_y2").shape[0] == 51 and len(y) == 36
+
+
+def reduced_lqp_nc_oracle(q, f0, f1):
+    """Reduced LQP + its non-contact half as reference tests/sp_test/jacc_compare.cpp:367-384, 485-487: L0 = COM position + pelvis
+    rotation (contact chain), L1 = left hand 6D (non-contact chain; ts_[1] is what ConfigureLQP_R_NC hard-codes)."""
+    r = orc.OracleRobot(URDF)
+    r.add_contact(LEFT_FOOT, FOOT_POINT, (0, 0, 1), 0.13, 0.06)
+    r.add_contact(RIGHT_FOOT, FOOT_POINT, (0, 0, 1), 0.13, 0.06)
+    r.add_task(0, orc.TASK_LINK_POSITION, "COM")
+    r.add_task(0, orc.TASK_LINK_ROTATION, "pelvis_link")
+    r.add_task(1, orc.TASK_LINK_6D, "L_Wrist2_Link")
+    r.update_kinematics(q, np.zeros(39))
+    r.set_contact(1, 1)
+    r.set_task(0, f0)
+    r.set_task(1, f1)
+    r.reduced_dynamics()
+    assert r.reduced_contact_constraint() == 1
+    assert r.reduced_task_space() == 1
+    assert r.configure_lqp(True) == 3 and r.calc_lqp() == 1
+    r.configure_lqp_r_nc()
+    ok = r.calc_lqp_r_nc()
+    return r, ok
+
+
+@pytest.mark.parametrize("hard", [False, True])
+def test_reduced_lqp_nc_oracle(hard):
+    """ConfigureLQP_R_NC + CalcControlTorqueLQP_R_NC (reference src/dwbc.cpp:4634-4760, 4479-4502): 21 joint accelerations of the
+    non-contact chain; level 0 (solvefirst) = centroidal equality J_I_nc qdd = fstar_gnc + torque rows, level 1 = hand task in the
+    pelvis-relative form + |qdd| <= 5.  KKT of both QPs, the hierarchy, the data of the levels and the stitched torque."""
+    q, _, rng = synth_states(3, 20249)
+    for b in range(3):
+        f0 = np.concatenate([0.5 * rng.standard_normal(3), 1.0 * rng.standard_normal(3)])
+        f1 = 1.0 * rng.standard_normal(6)
+        if hard:
+            f1[:3] *= 40.0  # the acceleration bound |qdd| <= 5 saturates
+        r, ok = reduced_lqp_nc_oracle(q[b], f0, f1)
+        assert ok == 1
+        nc, acc = 21, 24
+        yR = r.get("lqp_y2")[:, 0]
+        JI, ANC, G = r.get("J_I_nc"), r.get("A_NC"), r.get("G")[:, 0]
+        Ann, Gnc = ANC[6:, 6:], G[39 - nc:]
+        # level data as the reference writes them
+        B0, b0, A0, a0 = (r.get(f"lqpnc_{k}1") for k in ("B", "b", "A", "a"))
+        assert relerr(B0, JI) < 1e-14 and relerr(b0[:, 0], -yR[acc - 6:acc]) < 1e-14
+        assert relerr(A0, np.vstack([Ann, -Ann])) < 1e-14 and relerr(a0[:, 0], np.concatenate([-200 + Gnc, -200 - Gnc])) < 1e-14
+        assert relerr(r.get("lqp_nc_H"), 5 * Ann / np.linalg.norm(Ann)) < 1e-14
+        Jt = r.get("J_task1")
+        p = r.get("link_pos")
+        hand = 23
+        d = p[:, hand] - p[:, 0]
+        Ja = np.eye(6)
+        Ja[:3, 3:] = np.array([[0, -d[2], d[1]], [d[2], 0, -d[0]], [-d[1], d[0], 0]])
+        assert relerr(r.get("lqpnc_B2"), Jt[:, 39 - nc:]) < 1e-14
+        assert relerr(r.get("lqpnc_b2")[:, 0], -Ja @ (f1 - yR[:6])) < 1e-12
+        ys = [r.get(f"lqpnc_y{l}")[:, 0] for l in range(3)]
+        assert not ys[0].any()
+        for l in (1, 2):
+            H, g = r.get(f"lqpnc_qpH{l}"), r.get(f"lqpnc_qpg{l}")[:, 0]
+            QA, ub = r.get(f"lqpnc_qpA{l}"), r.get(f"lqpnc_qpub{l}")[:, 0]
+            Zp = r.get(f"lqpnc_Z{l - 1}")
+            nu = Zp.shape[1]
+            assert nu == (21 if l == 1 else 15)
+            z = np.concatenate([np.linalg.lstsq(Zp, ys[l] - ys[l - 1], rcond=None)[0], r.get(f"lqpnc_v{l}")[:, 0]])
+            res, act = kkt_residual(H, g, QA, ub, z, nu)
+            assert res < 1e-8 * max(1.0, np.linalg.norm(g)), (l, res)
+        # hierarchy: level 1 works in the null space of the centroidal equality and respects the frozen torque-row slack
+        assert np.linalg.norm(B0 @ (ys[2] - ys[1])) < 1e-9
+        v0 = r.get("lqpnc_v1")[:, 0]
+        assert (A0 @ ys[2] + a0[:, 0] - v0).max() < 1e-7
+        if not hard:
+            # (the cost 5 A_NC / |A_NC| shares level 0 with its equality rows -- HQP::solvefirst adds H_ to the Hessian, src/dwbc_hqp.cpp:264 --
+            # so the centroidal equality is met in the least-squares sense only)
+            assert np.abs(ys[2]).max() <= 5 + 1e-6
+        else:
+            # the bound is a soft row (slack with unit cost against the task residual): it bends, and the slack says by how much
+            v2 = r.get("lqpnc_v2")[:, 0]
+            assert v2.max() > 1e-3 and abs((np.abs(ys[2]).max() - 5.0) - v2.max()) < 1e-6
+        # stitched torque: contact-chain joints from the reduced LQP, the rest from the non-contact dynamics
+        tau = r.get("lqp_stitched_torque")[:, 0]
+        assert relerr(tau[:12], r.get("lqp_torque")[:12, 0]) < 1e-14
+        assert relerr(tau[12:], Ann @ ys[2] + Gnc) < 1e-12
