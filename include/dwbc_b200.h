@@ -243,8 +243,15 @@ int dwbc_batch_calc_control_torque_lqp(dwbc_batch_t *b, double *y_dev, double *t
  * (A_R, A_R_inv, G_R, J_CR, J_task J_R_INV_T^T; torque bound 200 with 600 on row m-4; cost A_R / |A_|), task levels = the COM /
  * contact-chain levels.  Call after reduced_dynamics, reduced_calc_contact_constraint and reduced_solve(DWBC_SOLVE_TASK) (which
  * classifies the levels and forms the reduced task Jacobians).  y_dev [B x (reduced_system_dof + cmax)], tau_dev
- * [B x reduced_model_dof].  ConfigureLQP_R_NC (the non-contact part) is not built. */
+ * [B x reduced_model_dof]. */
 int dwbc_batch_calc_control_torque_lqp_r(dwbc_batch_t *b, double *y_dev, double *tau_dev, int32_t *status_dev, void *stream);
+/* ConfigureLQP_R_NC + CalcControlTorqueLQP_R_NC (reference src/dwbc.cpp:4634-4760, 4479-4502): the non-contact chain's own two-level
+ * hierarchy over its nc_dof joint accelerations, fed by the answer of dwbc_batch_calc_control_torque_lqp_r (call that first):
+ * level 0 centroidal equality J_I_nc qdd = fstar_gnc + torque rows |A[nc,nc] qdd + G[nc]| <= 200; level 1 the 6D task of hierarchy
+ * level 1 (the reference hard-codes ts_[1]) in the pelvis-relative form + |qdd| <= 5.  qdd_nc_dev [B x nc_dof] final answer;
+ * tau_dev [B x m] the stitched joint torque of the only caller (reference tests/sp_test/jacc_compare.cpp:543-569): contact-chain joints
+ * from the reduced LQP, the others A[nc,nc] qdd + G[nc]; status_dev [B]: 2 both levels solved, -k level k failed, 0 no input. */
+int dwbc_batch_calc_control_torque_lqp_r_nc(dwbc_batch_t *b, double *qdd_nc_dev, double *tau_dev, int32_t *status_dev, void *stream);
 enum { DWBC_LQP_REDUCED = 256 }; /* OR into `which` of dwbc_batch_get_lqp for the results of the reduced variant */
 enum {
     DWBC_LQP_Y = 0,      /* hqp_hs_[level].y_ans_   (n + cmax) x 1, level in [0, 2 + task levels) */

@@ -68,6 +68,7 @@ def declare(L):
     L.dwbc_batch_get_reduced_matrix.argtypes = [vp, C.c_int, C.c_int, vp, _ip, _ip, vp]
     L.dwbc_batch_calc_control_torque_lqp.argtypes = [vp, vp, vp, vp, vp]
     L.dwbc_batch_calc_control_torque_lqp_r.argtypes = [vp, vp, vp, vp, vp]
+    L.dwbc_batch_calc_control_torque_lqp_r_nc.argtypes = [vp, vp, vp, vp, vp]
     L.dwbc_batch_get_lqp.argtypes = [vp, C.c_int, C.c_int, vp, _ip, _ip, vp]
     L.dwbc_batch_get_lqp_iterations.argtypes = [vp, vp, vp]
     L.dwbc_batch_set_task_gain.argtypes = [vp, C.c_int, C.c_int, _dp]
@@ -90,7 +91,7 @@ EXPORTS = [
     "dwbc_batch_get_matrix", "dwbc_batch_get_active_set", "dwbc_batch_cycle_host", "dwbc_probe_fp64", "dwbc_batch_get_qp_iterations",
     "dwbc_batch_set_profiling", "dwbc_batch_get_kernel_times", "dwbc_kernel_name", "dwbc_batch_get_contact_force", "dwbc_batch_get_zmp",
     "dwbc_batch_reduced_dynamics", "dwbc_batch_reduced_calc_contact_constraint", "dwbc_batch_reduced_solve", "dwbc_batch_reduced_dims", "dwbc_batch_set_reduced_torque_limit",
-    "dwbc_batch_get_reduced_matrix", "dwbc_batch_calc_control_torque_lqp", "dwbc_batch_calc_control_torque_lqp_r", "dwbc_batch_get_lqp", "dwbc_batch_get_lqp_iterations",
+    "dwbc_batch_get_reduced_matrix", "dwbc_batch_calc_control_torque_lqp", "dwbc_batch_calc_control_torque_lqp_r", "dwbc_batch_calc_control_torque_lqp_r_nc", "dwbc_batch_get_lqp", "dwbc_batch_get_lqp_iterations",
     "dwbc_batch_set_task_gain", "dwbc_batch_set_trajectory_quintic", "dwbc_batch_set_trajectory_rotation", "dwbc_batch_calc_fstar",
     "dwbc_batch_update_kinematics_mujoco", "dwbc_batch_get_torque_command_f32", "dwbc_batch_set_host_slices",
     "dwbc_batch_set_outputs", "dwbc_batch_last_path", "dwbc_batch_set_lean_timing", "dwbc_batch_cycle_host_levels",

@@ -329,6 +329,18 @@ class RobotDataBatch:
         self._ck(self.L.dwbc_batch_calc_control_torque_lqp_r(self._h, be.ptr(y), be.ptr(tau), be.ptr(st), be.stream()))
         return y, tau, st
 
+    def calc_control_torque_lqp_r_nc(self, out=None):
+        """ConfigureLQP_R_NC + CalcControlTorqueLQP_R_NC (reference src/dwbc.cpp:4634-4760, 4479-4502) after
+        calc_control_torque_lqp_r: returns (qdd_nc [B, nc_dof], stitched joint torque [B, m] as reference
+        tests/sp_test/jacc_compare.cpp:543-569, status [B])."""
+        be = self.be
+        B = self.batch
+        if out is None:
+            out = (be.empty((B, self.nc_dof)), be.empty((B, self.model_dof_)), be.empty((B,), "i4"))
+        y, tau, st = out
+        self._ck(self.L.dwbc_batch_calc_control_torque_lqp_r_nc(self._h, be.ptr(y), be.ptr(tau), be.ptr(st), be.stream()))
+        return y, tau, st
+
     def get_lqp(self, name, level=0, reduced=False):
         """"y" (answer after `level`), "v1" (slack of the level-1 inequality rows), "torque"; reduced=True: ConfigureLQP_R results."""
         return self._get(self.L.dwbc_batch_get_lqp, {"y": 0, "v1": 1, "torque": 2}[name] | (256 if reduced else 0), level)

@@ -104,6 +104,9 @@ struct dwbc_batch {
     double *mj_q = nullptr, *mj_qd = nullptr;
     // a10 LQP variant
     LqpOut lq{}, lqr{};
+    double *lqnc_y = nullptr, *lqnc_tau_nc = nullptr, *lqnc_tau = nullptr;  // ConfigureLQP_R_NC + CalcControlTorqueLQP_R_NC
+    int *lqnc_status = nullptr, *lqnc_iters = nullptr;
+    bool have_lqp_r_nc = false;
     bool lqp_allocated = false, have_lqp = false, lqr_allocated = false, have_lqp_r = false;
 };
 
@@ -1083,6 +1086,9 @@ void free_reduced(dwbc_batch *b) {
     b->red_allocs.clear();
     b->lqr = LqpOut{};
     b->lqr_allocated = b->have_lqp_r = false;
+    b->lqnc_y = b->lqnc_tau_nc = b->lqnc_tau = nullptr;
+    b->lqnc_status = b->lqnc_iters = nullptr;
+    b->have_lqp_r_nc = false;
     b->red_rn = 0;
     b->d_cfgR = nullptr;
 }
@@ -1557,6 +1563,56 @@ int dwbc_batch_calc_control_torque_lqp_r(dwbc_batch_t *b, double *y_dev, double 
     int rc = launch_lqp(b, true, y_dev, tau_dev, status_dev, st);
     if (rc) return rc;
     b->have_lqp_r = true;
+    return DWBC_OK;
+}
+
+int dwbc_batch_calc_control_torque_lqp_r_nc(dwbc_batch_t *b, double *qdd_nc_dev, double *tau_dev, int32_t *status_dev, void *stream) {
+    if (!b) return fail(DWBC_ERR_ARG, "calc_control_torque_lqp_r_nc: null handle");
+    if (!b->have_lqp_r) return fail(DWBC_ERR_ORDER, "calc_control_torque_lqp_r_nc: call calc_control_torque_lqp_r first (its answer is the input)");
+    const BatchCfg &c = b->cfg;
+    // ConfigureLQP_R_NC reads ts_[1] as THE non-contact task (reference src/dwbc.cpp:4738-4745): a 6D link task on the non-contact chain
+    if (c.nlevels < 2 || c.tasks[1].custom || c.tasks[1].dof != 6 || c.tasks[1].link_count != 1 || c.tlinks[c.tasks[1].link_start].dof != 6 ||
+        b->rc.cls[1] != 2)
+        return fail(DWBC_ERR_ARG, "calc_control_torque_lqp_r_nc: hierarchy level 1 must be one 6D link task on the non-contact chain (the reference hard-codes ts_[1])");
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = b->B, m = b->w.m, nc = b->rc.nc_dof;
+    if (nc + 6 > (size_t)LQP_WCAP || nc * (nc + 1) / 2 > (size_t)LQP_CHOL_OWN * TEAM) return fail(DWBC_ERR_LIMIT, "calc_control_torque_lqp_r_nc: non-contact chain too long");
+    if (!b->lqnc_y) {
+        std::vector<void *> *L = &b->red_allocs;
+        if (!dev_alloc(b, &b->lqnc_y, B * 2 * nc, L) || !dev_alloc(b, &b->lqnc_tau_nc, B * nc, L) || !dev_alloc(b, &b->lqnc_tau, B * m, L) ||
+            !dev_alloc(b, &b->lqnc_status, B, L) || !dev_alloc(b, &b->lqnc_iters, B, L))
+            return DWBC_ERR_CUDA;
+    }
+    const int rn = b->rc.rn, nlevR = 2 + b->cfgR.nlevels;
+    LqpNcArgs a{};
+    a.stride_yR = LQP_MAX_LEVELS * (rn + CMAX);
+    a.yR = b->lqr.y + (size_t)(nlevR - 1) * (rn + CMAX);
+    a.rn = rn;
+    a.tauR = b->lqr.tau;
+    a.rm = b->rc.rm;
+    a.co_dof = b->rc.co_dof;
+    a.vc_dof = b->rc.vc_dof;
+    a.nc = (int)nc;
+    a.statusR = b->lqr.status;
+    a.levelsR = nlevR;
+    a.ync = b->lqnc_y;
+    a.tau_nc = b->lqnc_tau_nc;
+    a.tau = b->lqnc_tau;
+    a.status = b->lqnc_status;
+    a.iters = b->lqnc_iters;
+    const LqpSmem L((int)nc, (int)nc, 6);
+    const size_t smem = sizeof(double) * L.total;
+    CK(cudaFuncSetAttribute(lqp_nc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        KernelScope ks(b, DWBC_K_LQP, st);
+        DWBC_LAUNCH(lqp_nc_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (const double *)b->rx.JI, a);
+    }
+    CK(cudaGetLastError());
+    if (qdd_nc_dev) CK(cudaMemcpy2DAsync(qdd_nc_dev, sizeof(double) * nc, b->lqnc_y + nc, sizeof(double) * 2 * nc, sizeof(double) * nc, B, cudaMemcpyDeviceToDevice, st));
+    if (tau_dev) CK(cudaMemcpyAsync(tau_dev, b->lqnc_tau, sizeof(double) * B * m, cudaMemcpyDeviceToDevice, st));
+    if (status_dev) CK(cudaMemcpyAsync(status_dev, b->lqnc_status, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+    b->have_lqp_r_nc = true;
     return DWBC_OK;
 }
 

@@ -716,4 +716,226 @@ __global__ void __launch_bounds__(TEAM, 2) lqp_kernel(const DevModel *__restrict
     if (tid == 0) out.status[s] = solved == nlev ? nlev : (solved > 0 ? -solved : 0), out.iters[s] = iters;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// ConfigureLQP_R_NC + CalcControlTorqueLQP_R_NC (reference src/dwbc.cpp:4634-4760, 4479-4502): the non-contact chain's own
+// two-level hierarchy over its nc joint accelerations (no contact force), fed by the answer of the reduced LQP:
+//   level 0 (HQP::solvefirst, src/dwbc_hqp.cpp:222-289)   eq  J_I_nc qdd = fstar_gnc (last 6 entries of the reduced qdd)
+//                                                         ineq |A[nc,nc] qdd + G[nc]| <= 200, own slack; cost 5 A[nc,nc] / |A[nc,nc]|_F
+//   level 1 (solveSequentialSingle)                       eq  J_task(ts_[1])[:, nc] qdd = Ja (f*_1 - fstar_base), Ja = [1 skew(p_link - p_pelvis); 0 1]
+//                                                         ineq |qdd| <= 5, own slack; the torque rows of level 0 frozen; same cost
+// ts_[1] is hard-coded by the reference (:4738-4745) and the rows are NOT normalised here (:4677, 4755).  A_NC[nc,nc] = A[nc,nc]
+// (the subtree of a non-contact joint is entirely non-contact, kernels_reduced.cuh).  Same exact level solve as lqp_kernel (the
+// stored-row layout of LqpRows with kc = 0, "m" = nc: torque rows, then acceleration rows), on an arena LqpSmem(nc, nc, 6).
+// Outputs: ync [B][2][nc] (answer after each level), tau_nc [B][nc] = A[nc,nc] qdd + G[nc], and the stitched joint torque of the
+// only caller (reference tests/sp_test/jacc_compare.cpp:543-569): tau [B][m] = [tau_reduced_lqp[0:co_dof]; tau_nc].
+struct LqpNcArgs {
+    const double *yR;      // [B][stride_yR] final answer of the reduced LQP (qdd_R first)
+    int stride_yR, rn;
+    const double *tauR;    // [B][rm] torque of the reduced LQP
+    int rm, co_dof, vc_dof, nc;
+    const int *statusR;    // [B] status of the reduced LQP (> 0: every level solved)
+    int levelsR;
+    double *ync, *tau_nc, *tau;  // outputs
+    int *status, *iters;         // [B] 2 = both levels solved, -k = level k failed, 0 = no valid input
+};
+
+__global__ void __launch_bounds__(TEAM, 3) lqp_nc_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, const double *JI_all,
+                                                         LqpNcArgs a) {
+    DWBC_DYN_SMEM(smem);
+    const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
+    const long long s = blockIdx.x;
+    const int n = w.n, m = w.m, nb = w.nb, nc = a.nc, vc = a.vc_dof;
+    const LqpSmem L(nc, nc, 6);
+    double *sm = (double *)smem;
+    double *Z = sm + L.Z, *G = sm + L.G, *H = sm + L.H, *E = sm + L.E, *R = sm + L.R;
+    double *y = sm + L.y, *u = sm + L.u, *xh = sm + L.xh, *gh = sm + L.gh, *gg = sm + L.gg, *ee = sm + L.ee, *htau = sm + L.hv_tau, *ta = sm + L.ta;
+    double *ub = sm + L.ub, *vfro = sm + L.vfro, *lam = sm + L.lam, *red = sm + L.red, *cm = sm + L.cm;
+    int *act = (int *)(sm + L.ints);
+    const int ldz = L.ldz, ldg = L.ldg, ldh = L.ldh, lde = L.lde, ldt = L.ldt;
+    double *yout = a.ync + s * 2 * (long long)nc;
+    for (int e = tid; e < 2 * nc; e += nt) yout[e] = 0.0;
+    for (int i = tid; i < nc; i += nt) a.tau_nc[s * nc + i] = 0.0;
+    for (int i = tid; i < m; i += nt) a.tau[s * m + i] = 0.0;
+    if (!(a.statusR[s] == a.levelsR)) {  // uniform over the CTA: the reduced LQP did not produce an answer
+        if (tid == 0) a.status[s] = 0, a.iters[s] = 0;
+        return;
+    }
+    const LqpRows RW{nc, 0};
+    const int rows = RW.total();  // 4 nc: torque +, torque -, accel +, accel -
+    const double *A = w.A + s * (long long)n * n + vc + (long long)vc * n;  // A[nc, nc], leading dimension n
+    const double *Gnc = w.G + s * n + vc;
+    const double *JI = JI_all + s * 6 * (MAXB - 1);  // 6 x nc, ld 6 (records of NCMAX = MAXB - 1 columns, kernels_reduced.cuh)
+    const double *qR = a.yR + s * (long long)a.stride_yR;
+    const double *pose = w.pose + s * (long long)nb * POSE_STRIDE;
+    int iters = 0;
+    // cost scale 5 / |A[nc,nc]|_F
+    double an = 0.0;
+    for (int e = tid; e < nc * nc; e += nt) {
+        const int j = e / nc, i = e - j * nc;
+        an = fma(A[i + (long long)j * n], A[i + (long long)j * n], an);
+    }
+    an = sqrt(lq_team_sum(an, red));
+    const double hs = 5.0 / an;
+    for (int e = tid; e < nc * nc; e += nt) {
+        const int j = e / nc, i = e - j * nc;
+        Z[i + j * ldz] = i == j ? 1.0 : 0.0;
+    }
+    for (int i = tid; i < nc; i += nt) y[i] = 0.0;
+    for (int i = tid; i < L.rtmax; i += nt) vfro[i] = 0.0;
+    // fstar_local = Ja (f*_1 - fstar_base)   (cm is free scratch here: no friction rows)
+    if (tid < 6) {
+        const TaskCfg &tc = cfg->tasks[1];
+        const int link = cfg->tlinks[tc.link_start].link;
+        const double *pl = pose + link * POSE_STRIDE + 9, *p0 = pose + 9;
+        const double d[3] = {pl[0] - p0[0], pl[1] - p0[1], pl[2] - p0[2]};
+        double df[6];
+        for (int k = 0; k < 6; k++) df[k] = w.fstar[1][s * 6 + k] - qR[k];
+        double v = df[tid];
+        if (tid == 0) v += -d[2] * df[4] + d[1] * df[5];
+        if (tid == 1) v += d[2] * df[3] - d[0] * df[5];
+        if (tid == 2) v += -d[1] * df[3] + d[0] * df[4];
+        cm[tid] = v;
+    }
+    int win = 0, solved = 0;
+    for (int lev = 0; lev < 2; lev++) {
+        const int nu = nc - win, neq = 6;
+        double *Zw = Z + win * ldz;
+        tsync();
+        // ---- E = B_lev Z (6 x nu), ee = B_lev y + b_lev ----
+        const double *Bm;
+        int ldb;
+        if (lev == 0) {
+            Bm = JI;
+            ldb = 6;
+        } else {
+            build_task_jacobian(md, cfg, w, s, 1, R, lde);  // 6 x n; its last nc columns are J_task_.rightCols(nc_dof)
+            Bm = R + vc * lde;
+            ldb = lde;
+            tsync();
+        }
+        for (int r = tid; r < neq; r += nt) {
+            double d = 0.0;
+            for (int j = 0; j < nc; j++) d = fma(Bm[r + j * ldb], y[j], d);
+            ee[r] = d + (lev == 0 ? -qR[a.rn - 6 + r] : -cm[r]);
+            htau[r] = 1.0;
+        }
+        tgemm<1, 2, false, false>(neq, nu, nc, Bm, ldb, Zw, ldz, [&](int i, int j, double v) { E[i + j * lde] = v; });
+        tsync();
+        // ---- T = A[nc,nc] Z_a (nc x nu), ta = A[nc,nc] y ----
+        double *T = R;
+        tgemm_mma<2, false, false>(nc, nu, nc, A, n, Zw, ldz, [&](int i, int j, double v) { T[i + j * ldt] = v; });
+        tgemv<false>(nc, nc, A, n, y, [&](int i, double v) { ta[i] = v; });
+        tsync();
+        // ---- Hu = E^T E + hs Z_a^T T + sigma I,  g = E^T e + hs Z_a^T ta ----
+        tgemm_mma<2, true, false>(nu, nu, neq, E, lde, E, lde, [&](int i, int j, double v) { H[i + j * ldh] = v; });
+        tsync();
+        tgemm_mma<2, true, false>(nu, nu, nc, Zw, ldz, T, ldt, [&](int i, int j, double v) { H[i + j * ldh] += hs * v + (i == j ? LQP_SIGMA : 0.0); });
+        tgemv<true>(nu, neq, E, lde, ee, [&](int i, double v) { gg[i] = v; });
+        tsync();
+        tgemv<true>(nu, nc, Zw, ldz, ta, [&](int i, double v) { gg[i] += hs * v; });
+        // ---- stored rows: torque rows T (raw), acceleration rows Z (absent at level 0: zero rows with a positive right-hand side) ----
+        for (int r = tid; r < nc; r += nt) {
+            const double tq = ta[r] + Gnc[r];
+            ub[r] = (LQP_TORQUE_LIMIT - tq) + vfro[r];
+            ub[nc + r] = (LQP_TORQUE_LIMIT + tq) + vfro[nc + r];
+            ub[2 * nc + r] = lev == 0 ? 1.0 : LQP_ACC_LIMIT - y[r];
+            ub[3 * nc + r] = lev == 0 ? 1.0 : LQP_ACC_LIMIT + y[r];
+        }
+        for (int e = tid; e < nc * nu; e += nt) {
+            const int j = e / nc, r = e - j * nc;
+            G[r + j * ldg] = T[r + j * ldt];
+            G[nc + r + j * ldg] = lev == 0 ? 0.0 : Zw[r + j * ldz];
+        }
+        tsync();  // T (in the R arena) is dead from here on
+        double *rdiag = u;
+        const double piv = tchol_lower<LQP_CHOL_OWN>(nu, H, ldh, rdiag);
+        if (!(piv > 0.0)) break;
+        double *Xi = R;
+        const int ldx = L.ldh;
+        ttri_inverse(nu, H, ldh, rdiag, Xi, ldx);
+        tsync();
+        tgemv<false>(nu, nu, Xi, ldx, gg, [&](int i, double v) { gh[i] = v; });
+        tgemm_mma<LQP_NU_TILES, false, true>(2 * nc, nu, nu, G, ldg, Xi, ldx, [&](int i, int j, double v) { G[i + j * ldg] = v; });
+        tsync();
+        for (int i = tid; i < rows; i += nt) {
+            int ur;
+            double sg;
+            RW.map(i, ur, sg);
+            ub[i] += sg * lq_rowdot(G, ldg, ur, nu, gh);
+        }
+        tsync();
+        const int q = lqp_ldp_solve(sm, nc, nc, 6, 0, nu, lev == 0 ? 0 : RW.level1_start(), &iters);
+        if (q < 0) break;
+        if (warp == 0) {
+            for (int j = lane; j < nu; j += 32) gg[j] = xh[j] - gh[j];
+            for (int k = nu - 1; k >= 0; k--) {
+                __syncwarp();
+                const double rk = gg[k] * rdiag[k];
+                __syncwarp();
+                if (lane == 0) gg[k] = rk;
+                for (int j = lane; j < k; j += 32) gg[j] = fma(-H[k + j * ldh], rk, gg[j]);
+            }
+            __syncwarp();
+        }
+        if (lev == 0)  // freeze the slack of the torque rows (the acceleration rows are not part of level 0)
+            for (int k = tid; k < q; k += nt)
+                if (act[k] < 2 * nc) vfro[act[k]] = lam[k];
+        tsync();
+        tgemv<false>(nc, nu, Zw, ldz, gg, [&](int i, double v) {
+            const double yn = y[i] + v;
+            y[i] = yn;
+            yout[lev * nc + i] = yn;
+        });
+        solved = lev + 1;
+        if (lev == 1) break;
+        // ---- Z <- Z H_0 ... H_5 (Householder reflections of (B Z)^T) ----
+        tsync();
+        bool rank_ok = true;
+        for (int k = 0; k < neq; k++) {
+            double s2 = 0.0;
+            for (int j = k + lane; j < nu; j += 32) s2 = fma(E[k + j * lde], E[k + j * lde], s2);
+            s2 = warp_sum(s2);
+            const double x0 = E[k + k * lde];
+            if (!(s2 > 1e-20)) {
+                rank_ok = false;
+                break;
+            }
+            const double alpha = x0 > 0.0 ? -sqrt(s2) : sqrt(s2);
+            const double tau = 1.0 / (s2 - alpha * x0);
+            tsync();
+            if (tid == 0) E[k + k * lde] = x0 - alpha, htau[k] = tau;
+            tsync();
+            for (int r = k + 1 + warp; r < neq; r += nw) {
+                double d = 0.0;
+                for (int j = k + lane; j < nu; j += 32) d = fma(E[r + j * lde], E[k + j * lde], d);
+                d = warp_sum(d) * tau;
+                for (int j = k + lane; j < nu; j += 32) E[r + j * lde] = fma(-d, E[k + j * lde], E[r + j * lde]);
+            }
+            tsync();
+        }
+        if (!rank_ok) break;
+        for (int i = tid; i < nc; i += nt) {
+            double *zr = Zw + i;
+            for (int k = 0; k < neq; k++) {
+                double d = 0.0;
+                for (int j = k; j < nu; j++) d = fma(zr[j * ldz], E[k + j * lde], d);
+                d *= htau[k];
+                for (int j = k; j < nu; j++) zr[j * ldz] = fma(-d, E[k + j * lde], zr[j * ldz]);
+            }
+        }
+        win += neq;
+    }
+    tsync();
+    if (solved == 1)
+        for (int i = tid; i < nc; i += nt) yout[nc + i] = y[i];  // a failed level keeps the previous answer
+    // tau_nc = A[nc,nc] qdd + G[nc]; stitched joint torque
+    tgemv<false>(nc, nc, A, n, y, [&](int i, double v) {
+        const double t = v + Gnc[i];
+        a.tau_nc[s * nc + i] = t;
+        a.tau[s * m + (m - nc) + i] = t;
+    });
+    for (int i = tid; i < a.co_dof; i += nt) a.tau[s * m + i] = a.tauR[s * a.rm + i];
+    if (tid == 0) a.status[s] = solved == 2 ? 2 : -solved, a.iters[s] = iters;
+}
+
 }  // namespace dwbc

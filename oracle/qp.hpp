@@ -265,6 +265,40 @@ inline QpResult qp_min_norm(const Mat &A, const std::vector<double> &ub, const s
     for (size_t i = 0; i < ub.size(); i++) h[i] = -ub[i];
     if (!ldp(G, h, res.x, lam, row_tol)) return res;
     res.status = 1;
+    // Polish: the NNLS-based LDP lets a row in only while it is violated by more than its tolerance, so the rows of the optimal
+    // face are met to that tolerance (1e-8 of the row scale in the loose stages) rather than exactly.  A lower level of the hierarchy
+    // then sees those rows with a right-hand side of +-1e-8 instead of 0 and "is this row active" becomes a coin flip.  With the
+    // multipliers identifying the face W, the answer is re-computed as the least-norm point of A_W x = ub_W (the same point, to
+    // rounding) and kept when every other row still holds.
+    {
+        double lmax = 0;
+        for (double v : lam) lmax = std::max(lmax, v);
+        std::vector<int> W;
+        for (int i = 0; i < A.r; i++)
+            if (lam[i] > 1e-9 * lmax && lmax > 0) W.push_back(i);
+        const int n = A.c, q = (int)W.size();
+        if (q > 0 && q <= n) {
+            Mat AW(q, n);
+            for (int k = 0; k < q; k++)
+                for (int j = 0; j < n; j++) AW(k, j) = A(W[k], j);
+            Cod f = cod_compute(AW, 1e-11);
+            if (f.rank == q) {
+                std::vector<double> xp(n, 0.0);
+                for (int j = 0; j < n; j++)
+                    for (int k = 0; k < q; k++) xp[j] += f.pinv(j, k) * ub[W[k]];
+                double dn = 0, xn = 0;
+                for (int j = 0; j < n; j++) dn += (xp[j] - res.x[j]) * (xp[j] - res.x[j]), xn += xp[j] * xp[j];
+                bool ok = std::sqrt(dn) <= 1e-6 * (1.0 + std::sqrt(xn));
+                for (int i = 0; i < A.r && ok; i++) {
+                    double s = -ub[i], nn = 0;
+                    for (int j = 0; j < n; j++) s += A(i, j) * xp[j], nn += A(i, j) * A(i, j);
+                    const double tol = row_tol ? (*row_tol)[i] : LDP_VIOL_TOL * std::max(std::sqrt(nn), std::fabs(ub[i]));
+                    if (s > tol) ok = false;
+                }
+                if (ok) res.x = xp;
+            }
+        }
+    }
     return res;
 }
 

@@ -86,6 +86,7 @@ def run_reduced_lqp(make_rd, D, H, B=3):
         rd.set_task_space(l, D(f))
     rd.reduced_solve(SOLVE_GRAV | SOLVE_TASK)
     y, tau, st = [H(x) for x in rd.calc_control_torque_lqp_r()]
+    ync, tau33, stnc = [H(x) for x in rd.calc_control_torque_lqp_r_nc()]
     n = 24
     for b in range(B):
         r = orc.OracleRobot(URDF)
@@ -109,6 +110,11 @@ def run_reduced_lqp(make_rd, D, H, B=3):
             assert relerr(yl[:n + 12], r.get(f"lqp_y{l}")[:, 0]) < 1e-6, (b, l)
         assert relerr(tau[b], r.get("lqp_torque")[:, 0]) < 1e-6, b
         assert relerr(y[b][:n + 12], r.get(f"lqp_y{nl - 1}")[:, 0]) < 1e-6
+        # ConfigureLQP_R_NC + CalcControlTorqueLQP_R_NC (reference src/dwbc.cpp:4634-4760, 4479-4502) and the stitched torque
+        r.configure_lqp_r_nc()
+        assert r.calc_lqp_r_nc() == 1 and int(stnc[b]) == 2, (b, stnc[b])
+        assert relerr(ync[b], r.get("lqpnc_y2")[:, 0]) < 1e-6, b
+        assert relerr(tau33[b], r.get("lqp_stitched_torque")[:, 0]) < 1e-6, b
 
 
 def test_emul_reduced_lqp_vs_oracle():
