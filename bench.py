@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="states per GPU (weak scaling)")
-    ap.add_argument("--contact-mix", default="ds", choices=["ds", "mixed"], help="ds: all double support (config 2); mixed: DS/left/right 0.5/0.25/0.25 (config 4)")
+    ap.add_argument("--contact-mix", default="ds", choices=["ds", "mixed", "ss", "sorted"],
+                    help="ds: all double support (config 2); mixed: DS/left/right 0.5/0.25/0.25 (config 4); ss: all left single support; sorted: the mixed batch grouped by contact pattern (diagnostics)")
     ap.add_argument("--outputs", default="torques", choices=["torques", "all"],
                     help="torques: DWBC_OUT_TORQUES, the one-kernel cycle (what a controller consumes); all: DWBC_OUT_ALL, every public RobotData field materialised (generic kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -50,7 +51,8 @@ def parse():
 
 
 def workload_name(args):
-    mix = "double support" if args.contact_mix == "ds" else "DS/left-SS/right-SS 0.5/0.25/0.25"
+    mix = {"ds": "double support", "mixed": "DS/left-SS/right-SS 0.5/0.25/0.25", "ss": "left single support",
+           "sorted": "DS/left-SS/right-SS 0.5/0.25/0.25 grouped by pattern"}[args.contact_mix]
     return f"TOCABI 33-DoF, batch {args.batch} states per GPU, 3-level HQP (COM / pelvis+upper-body rotation / 21-joint posture), torque limit 300 + friction/ZMP rows, contact redistribution QP, {mix}"
 
 
@@ -60,10 +62,14 @@ def make_inputs(B, seed, mix):
     q, qd, rng = synth_states(B, seed)
     fs = synth_fstar(rng, B, dofs=TASK_DOFS)
     flags = np.ones((B, 2), dtype=np.uint8)
-    if mix == "mixed":
+    if mix in ("mixed", "sorted"):
         u = rng.uniform(size=B)
+        if mix == "sorted":
+            u = np.sort(u)
         flags[(u >= 0.5) & (u < 0.75)] = [1, 0]
         flags[u >= 0.75] = [0, 1]
+    elif mix == "ss":
+        flags[:] = [1, 0]
     return q, qd, fs, flags
 
 
@@ -313,7 +319,7 @@ def run_b200(args):
     c_mean = 12.0 if args.contact_mix == "ds" else 9.0
     fl_ds = per_kernel_flops(TASK_DOFS, c=12, qp_iters_total=iters_mean)
     fl_ss = per_kernel_flops(TASK_DOFS, c=6, qp_iters_total=iters_mean)
-    wds = 1.0 if args.contact_mix == "ds" else 0.5
+    wds = {"ds": 1.0, "ss": 0.0}.get(args.contact_mix, 0.5)
     flk = {k: wds * fl_ds[k] + (1 - wds) * fl_ss[k] for k in fl_ds}
     # the one-kernel cycle does the work of the five dense kernels
     flk["lean_cycle_kernel"] = sum(flk[k] for k in ("rbd_kernel", "ainv_kernel", "contact_jacobian_kernel", "contact_dynamics_kernel", "task_space_kernel"))

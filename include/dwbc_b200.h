@@ -348,6 +348,13 @@ int dwbc_batch_last_path(const dwbc_batch_t *b);
  * every state (phase list next to LEAN_STAMP in csrc/kernels_lean.cuh); NULL switches it off.  tools/lean_phases.py prints the table. */
 int dwbc_batch_set_lean_timing(dwbc_batch_t *b, long long *stamps_dev);
 
+/* ---- staging for hosts that do not link the CUDA runtime (include/dwbc_compat/dwbc.h, the pybind module `dwbc`): plumbing only ---- */
+void *dwbc_device_alloc(int device, size_t bytes);            /* zero-initialised device buffer, NULL on failure */
+void dwbc_device_free(int device, void *p);
+int dwbc_memcpy_h2d(int device, void *dst_dev, const void *src_host, size_t bytes, void *stream);  /* synchronous on return */
+int dwbc_memcpy_d2h(int device, void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int dwbc_device_count(void);
+
 /* ---- diagnostics ---- */
 /* Best DFMA-chain throughput (TFLOP/s, 2 flop per FMA) observed over ~`seconds` of back-to-back launches on
  * `device`: the FP64-pipe roofline denominator used by bench.py. */

@@ -13,7 +13,8 @@ class DwbcError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, _LIBNAME)
+    # DWBC_LIB: another build of the same library (kernel experiments of tools/, e.g. a different unrolling); default: the in-tree one
+    return os.environ.get("DWBC_LIB") or os.path.join(_HERE, _LIBNAME)
 
 
 _dp = C.POINTER(C.c_double)
@@ -97,7 +98,7 @@ EXPORTS = [
     "dwbc_batch_set_outputs", "dwbc_batch_last_path", "dwbc_batch_set_lean_timing", "dwbc_batch_cycle_host_levels",
     "dwbc_multi_create", "dwbc_multi_destroy", "dwbc_multi_gpus", "dwbc_multi_shard", "dwbc_multi_add_contact", "dwbc_multi_add_task",
     "dwbc_multi_add_custom_task", "dwbc_multi_set_torque_limit", "dwbc_multi_set_outputs", "dwbc_multi_cycle_host", "dwbc_multi_last_shard_ms",
-    "dwbc_host_alloc", "dwbc_host_free",
+    "dwbc_host_alloc", "dwbc_host_free", "dwbc_device_alloc", "dwbc_device_free", "dwbc_memcpy_h2d", "dwbc_memcpy_d2h", "dwbc_device_count",
 ]
 
 _lib = None

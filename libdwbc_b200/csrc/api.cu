@@ -58,6 +58,7 @@ struct dwbc_batch {
     const uint8_t *lean_flags = nullptr;
     bool lean_kin_pending = false, lean_contact_pending = false;
     int *d_list = nullptr, *d_count = nullptr;
+    int *d_plist = nullptr, *d_pcount = nullptr;  // contact-pattern classes of the one-kernel cycle: lists [2][B], counts [2 streams][2]
     size_t list_off = 0;  // dwbc_batch_cycle_host: the slice's part of d_list and its stream's counter
     int count_slot = 0;
     long long *lean_timing = nullptr;  // diagnostics: device buffer [B][32] of phase stamps (dwbc_batch_set_lean_timing)
@@ -267,7 +268,8 @@ template <class S>
 int launch_lean(dwbc_batch *b, int stages, cudaStream_t st) {
     using L = LeanSmem<S>;
     const size_t smem = sizeof(double) * L::total;
-    CK(cudaFuncSetAttribute(lean_cycle_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(lean_cycle_kernel<S, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(lean_cycle_kernel<S, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LeanArgs a{};
     a.q = b->lean_q;
     a.qd = b->lean_qd;
@@ -277,10 +279,25 @@ int launch_lean(dwbc_batch *b, int stages, cudaStream_t st) {
     a.timing = b->lean_timing ? b->lean_timing + 32 * b->list_off : nullptr;
     a.list = b->d_list + b->list_off;
     a.count = b->d_count + b->count_slot;
+    // the slice's own region of the class lists: [2][slice size] starting at 2 * (first state of the slice)
+    int *plist0 = b->d_plist + 2 * b->list_off, *pcount = b->d_pcount + 2 * b->count_slot;
     CK(cudaMemsetAsync(a.count, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(pcount, 0, 2 * sizeof(int), st));
     {
         KernelScope ks(b, DWBC_K_LEAN, st);
-        DWBC_LAUNCH(lean_cycle_kernel<S>, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, a);
+        DWBC_LAUNCH(lean_classify_kernel, (b->B + 255) / 256, 256, 0, st, b->d_cfg, a.flags, b->B, plist0, pcount);
+    }
+    {
+        KernelScope ks(b, DWBC_K_LEAN, st);
+        a.plist = plist0;
+        a.pcount = pcount;
+        DWBC_LAUNCH((lean_cycle_kernel<S, 12>), b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, a);
+    }
+    {
+        KernelScope ks(b, DWBC_K_LEAN, st);
+        a.plist = plist0 + b->B;
+        a.pcount = pcount + 1;
+        DWBC_LAUNCH((lean_cycle_kernel<S, 6>), b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, a);
     }
     CK(cudaGetLastError());
     if (stages & (DWBC_SOLVE_HQP | DWBC_SOLVE_REDIST)) {
@@ -409,7 +426,7 @@ dwbc_batch_t *dwbc_batch_create(const dwbc_model_t *m, int batch, int device) {
               dev_alloc(b, &w.status, B) && dev_alloc(b, &w.tau_task, B * mm) && dev_alloc(b, &w.tau_contact, B * mm) &&
               dev_alloc(b, &w.cf_redis, B * RMAX) && dev_alloc(b, &w.active[MAX_LEVELS], B * ACTIVE_WORDS) && dev_alloc(b, &w.qp_iters, B) &&
               dev_alloc(b, &b->d_q, B * (n + 1)) && dev_alloc(b, &b->d_qd, B * n) && dev_alloc(b, &b->d_flags, B * MAX_CONTACTS) &&
-              dev_alloc(b, &b->d_list, B) && dev_alloc(b, &b->d_count, 4);
+              dev_alloc(b, &b->d_list, B) && dev_alloc(b, &b->d_count, 4) && dev_alloc(b, &b->d_plist, 2 * B) && dev_alloc(b, &b->d_pcount, 8);
     if (ok) ok = cuda_ok(cudaMemcpy(b->d_model, &b->hm.dev, sizeof(DevModel), cudaMemcpyHostToDevice), "cudaMemcpy(model)");
     if (!ok) {
         dwbc_batch_destroy(b);
@@ -1993,4 +2010,43 @@ void dwbc_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ host-side staging helpers
+// For hosts that do not link the CUDA runtime themselves (the RobotData shim include/dwbc_compat/dwbc.h, the pybind module): device
+// buffers and copies through the C ABI.  Plumbing only.
+extern "C" {
+void *dwbc_device_alloc(int device, size_t bytes) {
+    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return nullptr;
+    void *p = nullptr;
+    if (!cuda_ok(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc")) return nullptr;
+    cudaMemset(p, 0, bytes ? bytes : 1);
+    return p;
+}
+void dwbc_device_free(int device, void *p) {
+    if (!p) return;
+    cudaSetDevice(device);
+    cudaFree(p);
+}
+int dwbc_memcpy_h2d(int device, void *dst_dev, const void *src_host, size_t bytes, void *stream) {
+    CK(cudaSetDevice(device));
+    CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return DWBC_OK;
+}
+int dwbc_memcpy_d2h(int device, void *dst_host, const void *src_dev, size_t bytes, void *stream) {
+    CK(cudaSetDevice(device));
+    CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return DWBC_OK;
+}
+int dwbc_device_count(void) {
+#ifdef DWBC_CPU_EMUL
+    return 1;
+#else
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+#endif
+}
 }  // extern "C"

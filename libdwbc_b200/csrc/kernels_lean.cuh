@@ -70,7 +70,24 @@ struct LeanArgs {
     int *list;   // [B] compact list of the states hqp_kernel still has to finish
     int *count;  // number of entries of list
     long long *timing;  // diagnostics (may be null): [B][32] clock64() stamps of the phases of every state, see LEAN_STAMP
+    const int *plist;   // [<= B] the states this launch owns (those of one contact pattern class), CTA i runs state plist[i]
+    const int *pcount;  // number of entries of plist; CTAs beyond it exit
 };
+
+// Contact-pattern classes: the kernel is compiled once per contact dof (the two variants are ~20 k SASS instructions each and share
+// nothing from the contact stage on).  A batch that mixes double and single support used to run both variants side by side on every
+// SM and the instruction fetch collapsed (ncu: no_instruction 1.0 -> 7.6 warps per issue, 10 -> 25 ms per 65 536 states); now the
+// states are binned by class first and each class gets its own launch, so an SM streams one variant at a time.
+// class 0: exactly two active 6D contacts (c = 12); class 1: everything else (c = 6, or no / too many contacts -> status 0).
+__global__ void lean_classify_kernel(const BatchCfg *__restrict__ cfg, const uint8_t *__restrict__ flags, int B, int *lists, int *counts) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= B) return;
+    int k = 0;
+    for (int i = 0; i < cfg->ncontact; i++) k += flags[(long long)s * cfg->ncontact + i] ? 1 : 0;
+    const int cls = k == 2 ? 0 : 1;
+    const int slot = atomicAdd(counts + cls, 1);
+    lists[(long long)cls * B + slot] = s;
+}
 // phase stamps (thread 0 of the CTA): 0 start, 1 sweeps, 2 A, 3 A^-1, 4 Jc, 5 X, 6 Lambda_c, 7 Jbar + P, 8 V, 9 J_task, 10 T, 11 W + VV^T,
 // 12 (W + VV^T)^-1, 13 W^+ / NwJw / tau_grav, 14 Y, 15 M_l, 16 M_l^-1, 17 JL, 18 Ntorque, 19 QP tests, 20 end
 #define LEAN_STAMP(tm, k)                            \
@@ -523,7 +540,7 @@ __device__ __forceinline__ bool lean_task_levels(double *sm, long long *tm) {
 // The x = 0 test of one QP (reference quick exit, same margins as hqp_kernel's quick_feasible): torque rows tlim -/+ base > 0 and
 // contact rows -(A_const A_rot (P_C - Jbar^T[:,6:] base)) > 0, strictly.  Uniform result.  Synchronises.
 template <class S>
-__device__ __forceinline__ bool lean_quick_feasible(const BatchCfg *__restrict__ cfg, double *sm, int c, const int *cix, const double *base) {
+__device__ __noinline__ bool lean_quick_feasible(const BatchCfg *__restrict__ cfg, double *sm, int c, const int *cix, const double *base) {
     using L = LeanSmem<S>;
     constexpr int M = S::M, LDC = S::LDC;
     const int tid = t_id(), nt = t_n();
@@ -531,7 +548,7 @@ __device__ __forceinline__ bool lean_quick_feasible(const BatchCfg *__restrict__
     int &flag = *(int *)(misc + 7);
     if (tid == 0) flag = 1;
     if (c == 12) lean::gemv<12, M, LDC, false, 4>(Jb6, base, [&](int i, double v) { lf[i] = PC[i] - v; });
-    else lean::gemv<6, M, LDC, false, 4>(Jb6, base, [&](int i, double v) { lf[i] = PC[i] - v; });
+    else lean::gemv<6, M, LDC, false, 4>(Jb6, base, [&](int i, double v) { lf[i] = PC[i] - v; });  // (one out-of-line copy serves both classes)
     tsync();
     bool okq = true;
     if (cfg->tlim_set)
@@ -552,15 +569,17 @@ __device__ __forceinline__ bool lean_quick_feasible(const BatchCfg *__restrict__
     return res;
 }
 
-template <class S>
+template <class S, int CSEL>
 __global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, LeanArgs a) {
+    static_assert(CSEL == 12 || CSEL == 6, "contact dof of the class");
+    if ((int)blockIdx.x >= *a.pcount) return;
     using L = LeanSmem<S>;
     using LV = typename S::Lv;
     constexpr int N = S::N, M = S::M, NB = S::NB, LDN = S::LDN, LDM = S::LDM, TS = S::TS;
     DWBC_DYN_SMEM(smem);
     double *sm = (double *)smem;
     const int tid = t_id(), nt = t_n(), warp = lean::warp_id(), lane = lane_id();
-    const long long s = blockIdx.x;
+    const long long s = a.plist[blockIdx.x];
     double *P = sm + L::R1, *R2 = sm + L::R2, *rb = sm + L::R3;
     double *Gs = sm + L::Gs, *fs = sm + L::fs, *tgv = sm + L::tg, *tt = sm + L::tt, *base = sm + L::base, *com = sm + L::com, *misc = sm + L::misc;
     double *A06 = sm + L::A06, *rd = sm + L::rd;
@@ -655,11 +674,10 @@ __global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__rest
     // ---- a1: A^{-1} ----
     lean::spd_inverse<N, LDN, LDN>(P, R2, rd, misc, (int)(blockIdx.x % lean::NW));
     LEAN_STAMP(tm, 3);
-    bool good = misc[0] > 0.0 && (c == 6 || c == 12);
+    bool good = misc[0] > 0.0 && c == CSEL;
     // ---- a2-a5 ----
     if (good) {
-        if (c == 12) good = lean_contact_task_T<S, 12>(md, cfg, w, s, sm, cix, tm);
-        else good = lean_contact_task_T<S, 6>(md, cfg, w, s, sm, cix, tm);
+        good = lean_contact_task_T<S, CSEL>(md, cfg, w, s, sm, cix, tm);
         good = good && ok != 0;
     }
     if (!good) {  // uniform: no contact / too many contacts / a factorisation failed -> status 0, zero torques

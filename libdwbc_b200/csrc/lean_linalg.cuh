@@ -65,6 +65,31 @@ __device__ __forceinline__ void mma_gemm(const double *A, const double *B, Epi e
             c[jj][0] = 0.0;
             c[jj][1] = 0.0;
         }
+#ifdef DWBC_LEAN_ROLLK
+        // experiment: rolled k loop (smaller code, run-time addresses) -- see tools/gpu_variants.sh
+        DWBC_UNROLL(1)
+        for (int ks = 0; ks < KS - (KR != 0 ? 1 : 0); ks++) {
+            const double a = pa[ks * 4 * SA];
+            DWBC_UNROLL(NT)
+            for (int jj = 0; jj < NT; jj++) {
+                if ((TC % NT == 0) || gj * NT + jj < TC) {
+                    const double b = pb[jj][ks * 4 * SB];
+                    dmma884(c[jj][0], c[jj][1], a, b);
+                }
+            }
+        }
+        if constexpr (KR != 0) {
+            constexpr int ks = KS - 1;
+            const double a = t < KR ? pa[ks * 4 * SA] : 0.0;
+            DWBC_UNROLL(NT)
+            for (int jj = 0; jj < NT; jj++) {
+                if ((TC % NT == 0) || gj * NT + jj < TC) {
+                    const double b = t < KR ? pb[jj][ks * 4 * SB] : 0.0;
+                    dmma884(c[jj][0], c[jj][1], a, b);
+                }
+            }
+        }
+#else
         static_for<0, KS>([&](auto ks_) {
             constexpr int ks = decltype(ks_)::value;
             constexpr bool tail = (ks == KS - 1) && KR != 0;
@@ -81,6 +106,7 @@ __device__ __forceinline__ void mma_gemm(const double *A, const double *B, Epi e
                 }
             }
         });
+#endif
         DWBC_UNROLL(NT)
         for (int jj = 0; jj < NT; jj++) {
             const int j = (gj * NT + jj) * 8 + 2 * t;
@@ -141,16 +167,17 @@ __device__ __forceinline__ void gemv(const double *A, const double *x, Epi epi, 
         const int ii = act ? i : M - 1;
         const double *pa = TA ? A + ii * LDA : A + ii;
         double a0 = 0.0, a1 = 0.0;
-        constexpr int STEPS = (K + LPR - 1) / LPR;
-        static_for<0, STEPS>([&](auto s_) {
-            constexpr int s = decltype(s_)::value;
-            const int k = s * LPR + part;
-            if ((s + 1) * LPR <= K || k < K) {
-                const double av = TA ? pa[k] : pa[k * LDA];
-                if constexpr (s & 1) a1 = fma(av, x[k], a1);
-                else a0 = fma(av, x[k], a0);
-            }
-        });
+        // rolled (unroll 4): the matrix-vector products are latency-bound anyway and a fully unrolled copy per call site made up a fifth
+        // of the one-kernel cycle's code (8 k of 40 k SASS instructions)
+        constexpr int FULL = K / (2 * LPR);  // pairs of steps every lane takes
+        DWBC_UNROLL(4)
+        for (int s2 = 0; s2 < FULL; s2++) {
+            const int k0 = (2 * s2) * LPR + part, k1 = k0 + LPR;
+            a0 = fma(TA ? pa[k0] : pa[k0 * LDA], x[k0], a0);
+            a1 = fma(TA ? pa[k1] : pa[k1 * LDA], x[k1], a1);
+        }
+        DWBC_UNROLL(2 * LPR)
+        for (int k = FULL * 2 * LPR + part; k < K; k += LPR) a0 = fma(TA ? pa[k] : pa[k * LDA], x[k], a0);
         a0 += a1;
         if constexpr (LPR >= 2) a0 += __shfl_xor_sync(DWBC_FULL, a0, 1);
         if constexpr (LPR >= 4) a0 += __shfl_xor_sync(DWBC_FULL, a0, 2);
