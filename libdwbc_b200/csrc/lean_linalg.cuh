@@ -453,5 +453,335 @@ __device__ __forceinline__ double warp_spd_inverse_small(double *S, double *Xs) 
     return dmax > 0.0 ? minp / dmax : 0.0;
 }
 
+
+// ===========================================================================================================================
+// Run-time-dimension twins of the routines above, each compiled ONCE (__noinline__) and called from every site.
+//
+// Why (profiles/r02_ncu_lean_first.md): with one fully unrolled copy per call site the one-kernel cycle was 29 k SASS instructions
+// (468 KB) of straight-line code that every CTA streams once per state; the SM's instruction cache (L1.5: 32 KB) hit only 69 % of the
+// fetches (sm__icc_request_hit_rate) and the one warp working on a serial section spent its time waiting for instructions.  The
+// blocked algorithms and the DMMA inner loops are the same; only the dimensions, leading dimensions and transposes are arguments, so
+// ~2 k instructions of library code serve all ~40 call sites of a state and stay resident across the CTAs of an SM.
+namespace rt {
+
+constexpr int NTMAX = 5;  // column tiles per work item (N <= 40)
+
+// C(i,j) <- alpha * sum_k opA(i,k) opB(k,j) + (beta ? C(i,j) : 0).  Element (i,k) of opA is A[i*ra + k*sa], (k,j) of opB is B[k*sb + j*rb]
+// (any transpose / leading dimension); C is column-major with ldc.  A work item is one 8-row band times nt (<= NTMAX) adjacent column
+// tiles; nt = all column tiles makes the product safe IN PLACE on A (an item only reads the band it later writes).  No synchronisation.
+__device__ __noinline__ void gemm(int M, int N, int K, const double *A, int ra, int sa, const double *B, int sb, int rb, double *C, int ldc, double alpha,
+                                  int beta, int nt, int wrot) {
+    const int lane = lane_id(), g = lane >> 2, t = lane & 3;
+    const int w = (warp_id() + NW - (wrot % NW)) % NW;
+    const int TR = (M + 7) >> 3, TC = (N + 7) >> 3, GC = (TC + nt - 1) / nt, KF = K >> 2, KR = K & 3;
+    DWBC_UNROLL(1)
+    for (int item = w; item < TR * GC; item += NW) {
+        const int gj = item / TR, bi = item - gj * TR;
+        const int i = bi * 8 + g, ic = i < M ? i : M - 1;
+        const double *pa = A + ic * ra + t * sa;
+        const double *pb[NTMAX];
+        double c[NTMAX][2];
+        DWBC_UNROLL(NTMAX)
+        for (int jj = 0; jj < NTMAX; jj++) {
+            const int j = (gj * nt + jj) * 8 + g, jc = j < N ? j : N - 1;
+            pb[jj] = B + jc * rb + t * sb;
+            c[jj][0] = 0.0;
+            c[jj][1] = 0.0;
+        }
+        const int ntile = TC - gj * nt < nt ? TC - gj * nt : nt;  // tiles of this item (warp-uniform)
+        DWBC_UNROLL(2)
+        for (int ks = 0; ks < KF; ks++) {
+            const double a = *pa;
+            pa += 4 * sa;
+            DWBC_UNROLL(NTMAX)
+            for (int jj = 0; jj < NTMAX; jj++) {
+                if (jj < ntile) {
+                    const double b = *pb[jj];
+                    pb[jj] += 4 * sb;
+                    dmma884(c[jj][0], c[jj][1], a, b);
+                }
+            }
+        }
+        if (KR) {
+            const bool kv = t < KR;
+            const double a = kv ? *pa : 0.0;
+            DWBC_UNROLL(NTMAX)
+            for (int jj = 0; jj < NTMAX; jj++) {
+                if (jj < ntile) {
+                    const double b = kv ? *pb[jj] : 0.0;
+                    dmma884(c[jj][0], c[jj][1], a, b);
+                }
+            }
+        }
+        DWBC_UNROLL(NTMAX)
+        for (int jj = 0; jj < NTMAX; jj++) {
+            if (jj < ntile && i < M) {
+                const int j = (gj * nt + jj) * 8 + 2 * t;
+                double *pc = C + i + j * ldc;
+                if (j < N) pc[0] = beta ? fma(alpha, c[jj][0], pc[0]) : alpha * c[jj][0];
+                if (j + 1 < N) pc[ldc] = beta ? fma(alpha, c[jj][1], pc[ldc]) : alpha * c[jj][1];
+            }
+        }
+    }
+}
+
+// y(i) <- alpha * sum_k opA(i,k) x(k) + (z ? z(i) : 0); two lanes per row.  (tid, nt): the participating threads (whole warps).
+__device__ __noinline__ void gemv(int M, int K, const double *A, int ra, int sa, const double *x, double *y, double alpha, const double *z, int tid, int nt) {
+    const int rpp = nt >> 1, part = tid & 1;
+    DWBC_UNROLL(1)
+    for (int r0 = 0; r0 < M; r0 += rpp) {
+        const int i = r0 + (tid >> 1);
+        const bool act = i < M;
+        const double *pa = A + (act ? i : M - 1) * ra;
+        double a0 = 0.0, a1 = 0.0;
+        int k = part;
+        DWBC_UNROLL(2)
+        for (; k + 2 < K; k += 4) {
+            a0 = fma(pa[k * sa], x[k], a0);
+            a1 = fma(pa[(k + 2) * sa], x[k + 2], a1);
+        }
+        if (k < K) a0 = fma(pa[k * sa], x[k], a0);
+        a0 += a1;
+        a0 += __shfl_xor_sync(DWBC_FULL, a0, 1);
+        if (act && part == 0) y[i] = fma(alpha, a0, z ? z[i] : 0.0);
+    }
+}
+
+// Panel of the blocked Cholesky: columns c0 .. c0 + w - 1 (w <= 8), rows c0 .. n - 1 (at most 64), executed by one warp (see chol_panel).
+__device__ __forceinline__ void chol_panel(double *A, int ld, int n, int c0, int w, double *rdiag, double *pivslot) {
+    const int lane = lane_id();
+    double a[2][8];
+    DWBC_UNROLL(2)
+    for (int s = 0; s < 2; s++) {
+        const int r = c0 + 32 * s + lane;
+        DWBC_UNROLL(8)
+        for (int k = 0; k < 8; k++) a[s][k] = (r < n && k < w) ? A[r + (c0 + k) * ld] : 0.0;
+    }
+    double minp = 1e300;
+    DWBC_UNROLL(8)
+    for (int k = 0; k < 8; k++) {
+        if (k < w) {  // warp-uniform
+            double d = __shfl_sync(DWBC_FULL, a[0][k], k);
+            minp = d < minp ? d : minp;
+            if (!(d > 1e-300)) d = 1e-300;
+            const double rs = rsqrt(d);
+            a[0][k] *= rs;
+            a[1][k] *= rs;
+            if (lane == k) a[0][k] = d * rs;
+            if (lane == 0) rdiag[c0 + k] = rs;
+            DWBC_UNROLL(8)
+            for (int j = k + 1; j < 8; j++) {
+                const double ljk = __shfl_sync(DWBC_FULL, a[0][k], j);
+                a[0][j] = fma(-a[0][k], ljk, a[0][j]);
+                a[1][j] = fma(-a[1][k], ljk, a[1][j]);
+            }
+        }
+    }
+    DWBC_UNROLL(2)
+    for (int s = 0; s < 2; s++) {
+        const int r = c0 + 32 * s + lane;
+        DWBC_UNROLL(8)
+        for (int k = 0; k < 8; k++)
+            if (r < n && k < w) A[r + (c0 + k) * ld] = (s == 0 && lane < k) ? 0.0 : a[s][k];
+    }
+    if (lane == 0) *pivslot = minp < *pivslot ? minp : *pivslot;
+}
+
+// SPD inverse in place (see spd_inverse): A n x n (ld) -> full symmetric inverse; X (n x n, ldx) scratch; rdiag n doubles; *pivslot the
+// smallest pivot.  Synchronises on entry and exit.
+__device__ __noinline__ void spd_inverse(double *A, int ld, double *X, int ldx, int n, double *rdiag, double *pivslot, int wrot) {
+    const int NB = (n + 7) >> 3;
+    const int lane = lane_id(), g = lane >> 2, t = lane & 3, wid = warp_id();
+    const int warp = (wid + NW - (wrot % NW)) % NW;
+    tsync();
+    if (t_id() == 0) *pivslot = 1e300;
+    // ---- blocked Cholesky ----
+    DWBC_UNROLL(1)
+    for (int kb = 0; kb < NB; kb++) {
+        const int c0 = 8 * kb, w = n - c0 < 8 ? n - c0 : 8;
+        if (kb > 0) tsync();
+        if (wid == (kb + wrot) % NW) chol_panel(A, ld, n, c0, w, rdiag, pivslot);
+        if (kb < NB - 1) {
+            tsync();
+            const int NR = NB - 1 - kb, ntiles = NR * (NR + 1) / 2;
+            DWBC_UNROLL(1)
+            for (int p = wid; p < ntiles; p += NW) {
+                int bj = 0, rem = p;
+                while (rem >= NR - bj) {
+                    rem -= NR - bj;
+                    bj++;
+                }
+                const int bi = bj + rem + kb + 1;
+                bj += kb + 1;
+                const int i = 8 * bi + g, jg = 8 * bj + g;
+                const int ic = i < n ? i : n - 1, jc = jg < n ? jg : n - 1;
+                const double *pa = A + ic + (c0 + t) * ld, *pb = A + jc + (c0 + t) * ld;
+                const int cj = 8 * bj + 2 * t;
+                const bool v0 = i < n && cj < n, v1 = i < n && cj + 1 < n;
+                double c0v = v0 ? A[i + cj * ld] : 0.0, c1v = v1 ? A[i + (cj + 1) * ld] : 0.0;
+                const double a0 = -pa[0], a1 = -pa[4 * ld], b0 = pb[0], b1 = pb[4 * ld];
+                dmma884(c0v, c1v, a0, b0);
+                dmma884(c0v, c1v, a1, b1);
+                if (v0) A[i + cj * ld] = c0v;
+                if (v1) A[i + (cj + 1) * ld] = c1v;
+            }
+        }
+    }
+    tsync();
+    // ---- X = L^{-1}: diagonal blocks (one warp each), then one warp per block column ----
+    DWBC_UNROLL(1)
+    for (int kb = warp; kb < NB; kb += NW) {
+        const int c0 = 8 * kb, wd = n - c0 < 8 ? n - c0 : 8;
+        double x[8];
+        DWBC_UNROLL(8)
+        for (int i = 0; i < 8; i++) {
+            double s = 0.0;
+            x[i] = 0.0;
+            if (i < wd) {
+                DWBC_UNROLL(8)
+                for (int k = 0; k < i; k++) s = fma(A[c0 + i + (c0 + k) * ld], x[k], s);
+                const double rd = rdiag[c0 + i];
+                x[i] = (i == lane) ? rd : -s * rd;
+            }
+        }
+        if (lane < wd) {
+            DWBC_UNROLL(8)
+            for (int i = 0; i < 8; i++)
+                if (i < wd) X[c0 + i + (c0 + lane) * ldx] = x[i];
+        }
+    }
+    tsync();
+    DWBC_UNROLL(1)
+    for (int jb = warp; jb < NB - 1; jb += NW) {
+        DWBC_UNROLL(1)
+        for (int ib = jb + 1; ib < NB; ib++) {
+            const int i = 8 * ib + g, ic = i < n ? i : n - 1;
+            double c0 = 0.0, c1 = 0.0;
+            DWBC_UNROLL(1)
+            for (int kb = jb; kb < ib; kb++) {
+                const double *pa = A + ic + (8 * kb + t) * ld;
+                const double *pb = X + (8 * kb + t) + (8 * jb + g) * ldx;
+                dmma884(c0, c1, pa[0], pb[0]);
+                dmma884(c0, c1, pa[4 * ld], pb[4]);
+            }
+            double *dst = X + i + (8 * jb + 2 * t) * ldx;
+            if (i < n) {
+                dst[0] = c0;
+                dst[ldx] = c1;
+            }
+            __syncwarp();
+            const bool k0v = 8 * ib + t < n, k1v = 8 * ib + t + 4 < n;
+            const double *xa = X + ic + (8 * ib + t) * ldx;
+            const double *sb = X + (8 * ib + t) + (8 * jb + g) * ldx;
+            const double a0 = k0v ? xa[0] : 0.0, a1 = k1v ? xa[4 * ldx] : 0.0;
+            const double b0 = k0v ? sb[0] : 0.0, b1 = k1v ? sb[4] : 0.0;
+            double d0 = 0.0, d1 = 0.0;
+            dmma884(d0, d1, a0, b0);
+            dmma884(d0, d1, a1, b1);
+            __syncwarp();
+            if (i < n) {
+                dst[0] = -d0;
+                dst[ldx] = -d1;
+            }
+            __syncwarp();
+        }
+    }
+    tsync();
+    // ---- A^{-1} = X^T X on the lower tiles, mirrored ----
+    {
+        const int ntiles = NB * (NB + 1) / 2;
+        DWBC_UNROLL(1)
+        for (int p = warp; p < ntiles; p += NW) {
+            int bi = 0, rem = p;  // row-major over the lower triangle: tile (bi, bj), bj <= bi
+            while (rem > bi) {
+                rem -= bi + 1;
+                bi++;
+            }
+            const int bj = rem;
+            const int i = 8 * bi + g, jg = 8 * bj + g, k0 = 8 * bi;
+            const int ic = i < n ? i : n - 1, jc = jg < n ? jg : n - 1;
+            const double *pa = X + (k0 + t) + ic * ldx, *pb = X + (k0 + t) + jc * ldx;
+            double c0 = 0.0, c1 = 0.0;
+            const int KF = (n - k0) >> 2, KR = (n - k0) & 3;
+            DWBC_UNROLL(2)
+            for (int ks = 0; ks < KF; ks++) {
+                dmma884(c0, c1, pa[0], pb[0]);
+                pa += 4;
+                pb += 4;
+            }
+            if (KR) {
+                const bool kv = t < KR;
+                dmma884(c0, c1, kv ? pa[0] : 0.0, kv ? pb[0] : 0.0);
+            }
+            const int j = 8 * bj + 2 * t;
+            if (i < n && j < n && (bi > bj || i >= j)) A[i + j * ld] = c0, A[j + i * ld] = c0;
+            if (i < n && j + 1 < n && (bi > bj || i >= j + 1)) A[i + (j + 1) * ld] = c1, A[j + 1 + i * ld] = c1;
+        }
+    }
+    tsync();
+}
+
+// SPD inverse of an n x n matrix, n <= 8, by ONE warp (see warp_spd_inverse_small); Xs: n*n doubles private to the warp.
+__device__ __noinline__ double warp_spd_inverse_small(double *S, int ld, int n, double *Xs) {
+    const int lane = lane_id();
+    double a[8], rs[8], x[8];
+    DWBC_UNROLL(8)
+    for (int k = 0; k < 8; k++) a[k] = (lane < n && k < n) ? S[lane + k * ld] : 0.0, rs[k] = 0.0;
+    double dk = 0.0;
+    DWBC_UNROLL(8)
+    for (int k = 0; k < 8; k++)
+        if (lane == k) dk = a[k];
+    const double dmax = warp_max(dk);
+    double minp = 1e300;
+    DWBC_UNROLL(8)
+    for (int k = 0; k < 8; k++) {
+        if (k < n) {
+            double d = __shfl_sync(DWBC_FULL, a[k], k);
+            minp = d < minp ? d : minp;
+            if (!(d > 1e-300)) d = 1e-300;
+            rs[k] = rsqrt(d);
+            a[k] *= rs[k];
+            if (lane == k) a[k] = d * rs[k];
+            DWBC_UNROLL(8)
+            for (int j = k + 1; j < 8; j++) {
+                const double ljk = __shfl_sync(DWBC_FULL, a[k], j);
+                a[j] = fma(-a[k], ljk, a[j]);
+            }
+        }
+    }
+    DWBC_UNROLL(8)
+    for (int i = 0; i < 8; i++) {
+        double s = 0.0;
+        x[i] = 0.0;
+        if (i < n) {
+            DWBC_UNROLL(8)
+            for (int k = 0; k < i; k++) {
+                const double lik = __shfl_sync(DWBC_FULL, a[k], i);
+                s = fma(lik, x[k], s);
+            }
+            x[i] = (i == lane) ? rs[i] : -s * rs[i];
+            if (i < lane) x[i] = 0.0;
+        }
+    }
+    if (lane < n) {
+        DWBC_UNROLL(8)
+        for (int i = 0; i < 8; i++)
+            if (i < n) Xs[i + lane * n] = x[i];
+    }
+    __syncwarp();
+    for (int e = lane; e < n * n; e += 32) {
+        const int j = e / n, i = e - j * n;
+        if (i < j) continue;
+        double s = 0.0;
+        for (int k = i; k < n; k++) s = fma(Xs[k + i * n], Xs[k + j * n], s);
+        S[i + j * ld] = s;
+        S[j + i * ld] = s;
+    }
+    __syncwarp();
+    return dmax > 0.0 ? minp / dmax : 0.0;
+}
+
+}  // namespace rt
+
 }  // namespace lean
 }  // namespace dwbc

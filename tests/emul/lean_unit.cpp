@@ -79,7 +79,79 @@ __global__ void k_gemv(const double *a, const double *x, double *y) {
     lean::gemv<M, K, LDA, TA, LPR>(A, xs, [&](int i, double v) { y[i] = v; });
 }
 
+// ---- run-time-dimension twins (lean::rt) ----
+__global__ void k_rt_spd_inverse(int n, int ld, int ldx, const double *in, double *out, double *piv) {
+    DWBC_DYN_SMEM(smem);
+    double *A = (double *)smem, *X = A + ld * n + 8, *rd = X + ldx * n + 8, *ps = rd + n + 2;
+    for (int e = t_id(); e < n * n; e += t_n()) A[(e % n) + (e / n) * ld] = in[e];
+    lean::rt::spd_inverse(A, ld, X, ldx, n, rd, ps, 1);
+    for (int e = t_id(); e < n * n; e += t_n()) out[e] = A[(e % n) + (e / n) * ld];
+    if (t_id() == 0) *piv = *ps;
+}
+__global__ void k_rt_small_inverse(int n, int ld, const double *in, double *out, double *cond) {
+    DWBC_DYN_SMEM(smem);
+    double *S = (double *)smem, *Xs = S + ld * n + 8;
+    for (int e = t_id(); e < n * n; e += t_n()) S[(e % n) + (e / n) * ld] = in[e];
+    tsync();
+    if (lean::warp_id() == 2) {
+        const double c = lean::rt::warp_spd_inverse_small(S, ld, n, Xs);
+        if (lane_id() == 0) *cond = c;
+    }
+    tsync();
+    for (int e = t_id(); e < n * n; e += t_n()) out[e] = S[(e % n) + (e / n) * ld];
+}
+// C = alpha op(A) op(B) + beta C0, operands stored with transposes ta / tb
+__global__ void k_rt_gemm(int M, int N, int K, int ta, int tb, int nt, double alpha, int beta, const double *a, const double *b, double *c) {
+    DWBC_DYN_SMEM(smem);
+    const int lda = (ta ? K : M) + 3, ldb = (tb ? N : K) + 5, ldc = M + 1;
+    double *A = (double *)smem, *B = A + lda * (ta ? M : K) + 4, *Cm = B + ldb * (tb ? K : N) + 4;
+    for (int e = t_id(); e < M * K; e += t_n()) {
+        const int i = e % M, k = e / M;
+        A[ta ? k + i * lda : i + k * lda] = a[e];
+    }
+    for (int e = t_id(); e < K * N; e += t_n()) {
+        const int k = e % K, j = e / K;
+        B[tb ? j + k * ldb : k + j * ldb] = b[e];
+    }
+    for (int e = t_id(); e < M * N; e += t_n()) Cm[(e % M) + (e / M) * ldc] = c[e];
+    tsync();
+    lean::rt::gemm(M, N, K, A, ta ? lda : 1, ta ? 1 : lda, B, tb ? ldb : 1, tb ? 1 : ldb, Cm, ldc, alpha, beta, nt, 3);
+    tsync();
+    for (int e = t_id(); e < M * N; e += t_n()) c[e] = Cm[(e % M) + (e / M) * ldc];
+}
+__global__ void k_rt_gemv(int M, int K, int ta, double alpha, int usez, const double *a, const double *x, double *y) {
+    DWBC_DYN_SMEM(smem);
+    const int lda = (ta ? K : M) + 1;
+    double *A = (double *)smem, *xs = A + lda * (ta ? M : K) + 2, *zs = xs + K + 2, *ys = zs + M + 2;
+    for (int e = t_id(); e < M * K; e += t_n()) {
+        const int i = e % M, k = e / M;
+        A[ta ? k + i * lda : i + k * lda] = a[e];
+    }
+    for (int e = t_id(); e < K; e += t_n()) xs[e] = x[e];
+    for (int e = t_id(); e < M; e += t_n()) zs[e] = y[e];
+    tsync();
+    lean::rt::gemv(M, K, A, ta ? lda : 1, ta ? 1 : lda, xs, ys, alpha, usez ? zs : nullptr, t_id(), t_n());
+    tsync();
+    for (int e = t_id(); e < M; e += t_n()) y[e] = ys[e];
+}
+
 extern "C" {
+int lean_rt_spd_inverse(int n, int ld, int ldx, const double *in, double *out, double *piv) {
+    DWBC_LAUNCH(k_rt_spd_inverse, 1, TEAM, sizeof(double) * (ld * n + ldx * n + n + 64), nullptr, n, ld, ldx, in, out, piv);
+    return 0;
+}
+int lean_rt_small_inverse(int n, int ld, const double *in, double *out, double *cond) {
+    DWBC_LAUNCH(k_rt_small_inverse, 1, TEAM, 8192, nullptr, n, ld, in, out, cond);
+    return 0;
+}
+int lean_rt_gemm(int M, int N, int K, int ta, int tb, int nt, double alpha, int beta, const double *a, const double *b, double *c) {
+    DWBC_LAUNCH(k_rt_gemm, 1, TEAM, sizeof(double) * 3 * (M + K + N + 16) * (M + K + N + 16), nullptr, M, N, K, ta, tb, nt, alpha, beta, a, b, c);
+    return 0;
+}
+int lean_rt_gemv(int M, int K, int ta, double alpha, int usez, const double *a, const double *x, double *y) {
+    DWBC_LAUNCH(k_rt_gemv, 1, TEAM, sizeof(double) * ((M + 4) * (K + 4) + 2 * M + K + 32), nullptr, M, K, ta, alpha, usez, a, x, y);
+    return 0;
+}
 int lean_spd_inverse(int n, const double *in, double *out, double *piv) {
     switch (n) {
     case 39: run_spd<39, 44, 44>(in, out, piv); return 0;
