@@ -87,7 +87,7 @@ public:
     static VectorXd Zero(Index n) { return VectorXd(n); }
     static VectorXd Constant(Index n, double v) {
         VectorXd x(n);
-        x.setConstant(v);
+        x.MatrixXd::setConstant(v);
         return x;
     }
     void resize(Index n) { MatrixXd::resize(n, 1); }

@@ -272,25 +272,28 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
     tsync();
     LEAN_STAMP(tm, 4);
     // X = A^{-1} Jc^T  (N x C)
-    lean::rt::gemm(N, C, N, P, 1, LDN, Jc, LDC, 1, X, LDN, 1.0, 0, (C + 7) / 8, 0);
+    lean::mma_gemm<N, C, N, LDN, LDC, false, true, (C + 7) / 8>(P, Jc, [&](int i, int j, double v) { X[i + j * LDN] = v; });
     tsync();
     LEAN_STAMP(tm, 5);
     // Jc X (C x C, SPD) -> Lambda_c
-    lean::rt::gemm(C, C, N, Jc, 1, LDC, X, 1, LDN, Lam, LDC, 1.0, 0, 1, 0);
-    lean::rt::spd_inverse(Lam, LDC, Lw, LDC, C, rd, misc, 1);
+    lean::mma_gemm<C, C, N, LDC, LDN, false, false, 1>(Jc, X, [&](int i, int j, double v) { Lam[i + j * LDC] = v; });
+    lean::spd_inverse<C, LDC, LDC>(Lam, Lw, rd, misc, 1);
     if (!(misc[0] > 0.0)) return false;
     LEAN_STAMP(tm, 6);
     // Jbar^T = Lambda_c X^T  (C x N)
-    lean::rt::gemm(C, N, C, Lam, 1, LDC, X, LDN, 1, Jbar, LDC, 1.0, 0, 3, 0);
+    lean::mma_gemm<C, N, C, LDC, LDN, false, true, 3>(Lam, X, [&](int i, int j, double v) { Jbar[i + j * LDC] = v; });
     tsync();
     // P = A^{-1} N_c = A^{-1} - X Jbar^T  (symmetric rank-C update)
-    lean::rt::gemm(N, N, C, X, 1, LDN, Jbar, 1, LDC, P, LDN, -1.0, 1, 2, 0);
+    lean::mma_gemm_sym<N, C, LDN, LDC, false, false>(X, Jbar, [&](int i, int j, double v) {
+        P[i + j * LDN] -= v;
+        if (i != j) P[j + i * LDN] -= v;
+    });
     // Jbar^T[:, 6:] and P_C = Jbar^T G are what the QPs need later
     for (int e = tid; e < C * M; e += nt) {
         const int j = e / C, i = e - j * C;
         Jb6[i + j * LDC] = Jbar[i + (6 + j) * LDC];
     }
-    lean::rt::gemv(C, N, Jbar, 1, LDC, Gs, PC, 1.0, nullptr, tid, nt);
+    lean::gemv<C, N, LDC, false, 4>(Jbar, Gs, [&](int i, double v) { PC[i] = v; });
     LEAN_STAMP(tm, 7);
     if constexpr (R > 0) {
         // ---- orthonormal basis V (M x R) of null(W): {S Jc^T f : (Jc^T f)[0:6] = 0} ----
@@ -335,7 +338,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
         }
         tsync();
         if (warp == 3) {
-            const double cg = lean::rt::warp_spd_inverse_small(Gm, lda, R, G2);
+            const double cg = lean::warp_spd_inverse_small<R, lda>(Gm, G2);
             if (!(cg > 1e-13) && lane == 0) ok = 0;
         }
         tsync();
@@ -361,7 +364,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
     }
     LEAN_STAMP(tm, 8);
     // u = (A^{-1}N_c)[6:, :] G   (tgv is scratch here)
-    lean::rt::gemv(M, N, P + 6, 1, LDN, Gs, u, 1.0, nullptr, tid, nt);
+    lean::gemv<M, N, LDN, false, 2>(P + 6, Gs, [&](int i, double v) { u[i] = v; });
     // ---- J_task of all levels (stacked, R2: Jc / X / Lambda_c are dead) and T = J P (R3: the sweep records are dead after this) ----
     if constexpr (TS > 0) {
         double *Js = R2;
@@ -412,21 +415,27 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
         });
         tsync();
         LEAN_STAMP(tm, 9);
-        lean::rt::gemm(TS, N, N, Js, 1, LDT, P, 1, LDN, T, LDT, 1.0, 0, (N + 7) / 8, 0);
+        lean::mma_gemm<TS, N, N, LDT, LDN, false, false, (N + 7) / 8>(Js, P, [&](int i, int j, double v) { T[i + j * LDT] = v; });
     }
     tsync();
     LEAN_STAMP(tm, 10);
     // ---- W^+ = (W + V V^T)^{-1} - V V^T in place in P[6:, 6:] ----
     double *Wb = P + 6 + 6 * LDN;
     if constexpr (R > 0) {
-        lean::rt::gemm(M, M, R, V, 1, LDM, V, LDM, 1, Wb, LDN, 1.0, 1, 2, 0);
+        lean::mma_gemm_sym<M, R, LDM, LDM, false, true>(V, V, [&](int i, int j, double v) {
+            Wb[i + j * LDN] += v;
+            if (i != j) Wb[j + i * LDN] += v;
+        });
     }
     LEAN_STAMP(tm, 11);
-    lean::rt::spd_inverse(Wb, LDN, R2, LDM, M, rd, misc, 2);
+    lean::spd_inverse<M, LDN, LDM>(Wb, R2, rd, misc, 2);
     if (!(misc[0] > 0.0)) return false;
     LEAN_STAMP(tm, 12);
     if constexpr (R > 0) {
-        lean::rt::gemm(M, M, R, sm + L::NwJw, 1, LDM, V, LDM, 1, Wb, LDN, -1.0, 1, 2, 0);  // W^+ = (W + V V^T)^{-1} - (V G^{-2}) V^T
+        lean::mma_gemm_sym<M, R, LDM, LDM, false, true>(sm + L::NwJw, V, [&](int i, int j, double v) {  // W^+ = (W + V V^T)^{-1} - (V G^{-2}) V^T
+            Wb[i + j * LDN] -= v;
+            if (i != j) Wb[j + i * LDN] -= v;
+        });
         // Mx = Jbar^T[0:R, 6:] V (R x R) and the identity beside it; NwJw = V Mx^{-1}
         constexpr int lda = 13;
         for (int e = tid; e < R * R; e += nt) {
@@ -442,7 +451,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
             if (!(cond2 > 1e-14) && lane == 0) ok = 0;
         }
         // tau_grav = W^+ u does not wait for Mx^{-1}
-        if (warp != 1) lean::rt::gemv(M, M, Wb, 1, LDN, u, tgv, 1.0, nullptr, tid < 32 ? tid : tid - 32, nt - 32);
+        if (warp != 1) lean::gemv<M, M, LDN, false, 2>(Wb, u, [&](int i, double v) { tgv[i] = v; }, tid < 32 ? tid : tid - 32, nt - 32);
         tsync();
         for (int e = tid; e < M * R; e += nt) {
             const int j = e / M, i = e - j * M;
@@ -453,7 +462,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
         }
     } else {
         tsync();
-        lean::rt::gemv(M, M, Wb, 1, LDN, u, tgv, 1.0, nullptr, tid, nt);
+        lean::gemv<M, M, LDN, false, 2>(Wb, u, [&](int i, double v) { tgv[i] = v; });
     }
     tsync();
     LEAN_STAMP(tm, 13);
@@ -471,14 +480,14 @@ __device__ __forceinline__ bool lean_task_levels(double *sm, long long *tm) {
     double *Wb = P + 6 + 6 * LDN, *Tm = T + 6 * LDT;
     double *cnd = misc + 2;  // per level: relative pivot of M_l
     // Y = W^+ Tm^T   (M x TS)
-    lean::rt::gemm(M, TS, M, Wb, 1, LDN, Tm, LDT, 1, Y, LDM, 1.0, 0, 2, 0);
+    lean::mma_gemm<M, TS, M, LDN, LDT, false, true, 2>(Wb, Tm, [&](int i, int j, double v) { Y[i + j * LDM] = v; });
     tsync();
     LEAN_STAMP(tm, 14);
     // M_l = Tm_l Y_l (t x t, SPD) into the task blocks of R1 (W^+ is dead: tau_grav and Y are formed)
     lean::static_for<0, LV::NL>([&](auto l_) {
         constexpr int l = decltype(l_)::value, t = LV::dof(l), r0 = LV::r0(l), ldb = L::ldb(l);
         double *Ml = P + L::mo(l);
-        lean::rt::gemm(t, t, M, Tm + r0, 1, LDT, Y + r0 * LDM, 1, LDM, Ml, ldb, 1.0, 0, 1, l);
+        lean::mma_gemm<t, t, M, LDT, LDM, false, false, 1>(Tm + r0, Y + r0 * LDM, [&](int i, int j, double v) { Ml[i + j * ldb] = v; }, l);
     });
     tsync();
     LEAN_STAMP(tm, 15);
@@ -487,7 +496,7 @@ __device__ __forceinline__ bool lean_task_levels(double *sm, long long *tm) {
         constexpr int l = decltype(l_)::value, t = LV::dof(l), ldb = L::ldb(l);
         if constexpr (t <= 8) {
             if (warp == (l + 1) % lean::NW) {
-                const double c = lean::rt::warp_spd_inverse_small(P + L::mo(l), ldb, t, P + L::mo(l) + ldb * t);
+                const double c = lean::warp_spd_inverse_small<t, ldb>(P + L::mo(l), P + L::mo(l) + ldb * t);
                 if (lane == 0) cnd[l] = c;
             }
         }
@@ -499,7 +508,7 @@ __device__ __forceinline__ bool lean_task_levels(double *sm, long long *tm) {
             tsync();
             double dmax = 0.0;
             for (int i = 0; i < t; i++) dmax = fmax(dmax, Ml[i + i * ldb]);
-            lean::rt::spd_inverse(Ml, ldb, Ml + ldb * t, ldb, t, rd, misc, l);
+            lean::spd_inverse<t, ldb, ldb>(Ml, Ml + ldb * t, rd, misc, l);
             if (tid == 0) cnd[l] = dmax > 0.0 ? misc[0] / dmax : 0.0;
         }
     });
@@ -511,7 +520,7 @@ __device__ __forceinline__ bool lean_task_levels(double *sm, long long *tm) {
     lean::static_for<0, LV::NL>([&](auto l_) {
         constexpr int l = decltype(l_)::value, t = LV::dof(l), r0 = LV::r0(l), ldb = L::ldb(l);
         double *Yl = Y + r0 * LDM;
-        lean::rt::gemm(M, t, t, Yl, 1, LDM, P + L::mo(l), 1, ldb, Yl, LDM, 1.0, 0, (t + 7) / 8, l);
+        lean::mma_gemm<M, t, t, LDM, ldb, false, false, (t + 7) / 8>(Yl, P + L::mo(l), [&](int i, int j, double v) { Yl[i + j * LDM] = v; }, l);
     });
     tsync();
     LEAN_STAMP(tm, 17);
@@ -519,9 +528,9 @@ __device__ __forceinline__ bool lean_task_levels(double *sm, long long *tm) {
     lean::static_for<1, LV::NL>([&](auto l_) {
         constexpr int l = decltype(l_)::value, t = LV::dof(l), rl = LV::r0(l), ldc = ld4(rl);
         double *Cs = P + L::Cs, *Yl = Y + rl * LDM;
-        lean::rt::gemm(rl, t, M, Tm, 1, LDT, Yl, 1, LDM, Cs, ldc, 1.0, 0, 1, 0);
+        lean::mma_gemm<rl, t, M, LDT, LDM, false, false, 1>(Tm, Yl, [&](int i, int j, double v) { Cs[i + j * ldc] = v; });
         tsync();
-        lean::rt::gemm(M, t, rl, Y, 1, LDM, Cs, 1, ldc, Yl, LDM, -1.0, 1, (t + 7) / 8, 0);
+        lean::mma_gemm<M, t, rl, LDM, ldc, false, false, (t + 7) / 8>(Y, Cs, [&](int i, int j, double v) { Yl[i + j * LDM] -= v; });
         tsync();
     });
     LEAN_STAMP(tm, 18);
@@ -538,7 +547,8 @@ __device__ __noinline__ bool lean_quick_feasible(const BatchCfg *__restrict__ cf
     double *Jb6 = sm + L::Jb6, *PC = sm + L::PC, *lf = sm + L::lf, *Rc = sm + L::Rc, *misc = sm + L::misc;
     int &flag = *(int *)(misc + 7);
     if (tid == 0) flag = 1;
-    lean::rt::gemv(c, M, Jb6, 1, LDC, base, lf, -1.0, PC, tid, nt);
+    if (c == 12) lean::gemv<12, M, LDC, false, 4>(Jb6, base, [&](int i, double v) { lf[i] = PC[i] - v; });
+    else lean::gemv<6, M, LDC, false, 4>(Jb6, base, [&](int i, double v) { lf[i] = PC[i] - v; });  // (one out-of-line copy serves both classes)
     tsync();
     bool okq = true;
     if (cfg->tlim_set)
@@ -662,7 +672,7 @@ __global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__rest
     const int c = cdof;
     LEAN_STAMP(tm, 2);
     // ---- a1: A^{-1} ----
-    lean::rt::spd_inverse(P, LDN, R2, LDN, N, rd, misc, (int)(blockIdx.x % lean::NW));
+    lean::spd_inverse<N, LDN, LDN>(P, R2, rd, misc, (int)(blockIdx.x % lean::NW));
     LEAN_STAMP(tm, 3);
     bool good = misc[0] > 0.0 && c == CSEL;
     // ---- a2-a5 ----
@@ -684,7 +694,7 @@ __global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__rest
     if constexpr (TS > 0) {
         if (!a.hqp) {
             // closed form (reference src/dwbc.cpp:856-871): torque_task = sum_l Ntorque_l f*_l; always returns 1, a singular task space is reported
-            lean::rt::gemv(M, TS, Nta, 1, LDM, fs, tt, 1.0, nullptr, tid, nt);
+            lean::gemv<M, TS, LDM, false, 2>(Nta, fs, [&](int i, double v) { tt[i] = v; });
             tsync();
             if (task_ok) st |= 2;
         } else if (task_ok) {
@@ -694,9 +704,7 @@ __global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__rest
                 constexpr int l = decltype(l_)::value, t = LV::dof(l), r0 = LV::r0(l);
                 if (!active) {
                     // base = tau_prev + Ntorque_l f*_l with tau_prev = tau_grav + torque_task so far
-                    for (int i = tid; i < M; i += nt) base[i] = tgv[i] + tt[i];
-                    tsync();
-                    lean::rt::gemv(M, t, Nta + r0 * LDM, 1, LDM, fs + r0, base, 1.0, base, tid, nt);
+                    lean::gemv<M, t, LDM, false, 2>(Nta + r0 * LDM, fs + r0, [&](int i, double v) { base[i] = tgv[i] + tt[i] + v; });
                     tsync();
                     if (lean_quick_feasible<S>(cfg, sm, c, cix, base)) {
                         for (int i = tid; i < M; i += nt) tt[i] = base[i] - tgv[i];

@@ -462,6 +462,11 @@ __device__ __forceinline__ double warp_spd_inverse_small(double *S, double *Xs) 
 // fetches (sm__icc_request_hit_rate) and the one warp working on a serial section spent its time waiting for instructions.  The
 // blocked algorithms and the DMMA inner loops are the same; only the dimensions, leading dimensions and transposes are arguments, so
 // ~2 k instructions of library code serve all ~40 call sites of a state and stay resident across the CTAs of an SM.
+//
+// MEASURED AND NOT USED by lean_cycle_kernel (profiles/r02_*_rt_primitives_dropped.*): the instruction-cache hit rate rose from 69 % to
+// 84 % and the kernel shrank from 29 k to 13 k SASS instructions, but the one-kernel cycle took 21.9 ms instead of 10.1 ms per 65 536
+// states -- every phase about twice as long (run-time strides, call overhead and the panel's worst-case register tiles cost more issue
+// slots and dependent latency than the instruction fetch they save).  Kept, with their unit tests, as the documented alternative.
 namespace rt {
 
 constexpr int NTMAX = 5;  // column tiles per work item (N <= 40)

@@ -87,3 +87,27 @@ def test_cpp_shim_runs_reference_cycle():
     assert relerr(vals[:, 1], g("torque_task_")) < 1e-9
     assert relerr(vals[:, 2], g("torque_contact_")) < 1e-9
     assert out[33] == "status 7" and out[34].startswith("error ok: Link Name is Wrong")
+
+
+def build_and_run_cpp(lib, src_name, include_dirs, args):
+    """g++ a host program against `lib` (the emulation build here, libdwbc_b200.so in the gpu-marked twins) and run it."""
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(lib), src_name.replace(".cpp", "_" + os.path.basename(lib).split(".")[0]))
+    cmd = ["g++", "-std=c++17", "-O1"]
+    for d in include_dirs:
+        cmd += ["-I", os.path.join(ROOT, d)]
+    cmd += [os.path.join(ROOT, "tests", src_name), lib, "-Wl,-rpath," + os.path.dirname(lib), "-lpthread", "-o", exe]
+    subprocess.check_call(cmd)
+    return subprocess.run([exe] + args, capture_output=True, text=True)
+
+
+def test_robotdata_compat_header_reference_sequence():
+    """include/dwbc_compat/dwbc.h: the reference's CASE 1 / CASE 2 verification sequence (reference tests/dwbc_test.cpp:29-235) written
+    against the single-state DWBC::RobotData -- same calls, same public members, golden binaries checked like check_binary -- through the
+    emulation build of the C ABI.  (Eigen is absent from the image: the header's own MatrixXd / VectorXd stand-in is used.)"""
+    from tests.common import GOLDEN
+    from tests.emul.build_emul import build
+
+    r = build_and_run_cpp(build(), "robotdata_check.cpp", ["include/dwbc_compat"], [URDF, os.path.join(GOLDEN, "cases")])
+    assert r.returncode == 0 and r.stdout.strip().endswith("ALL OK"), r.stdout + r.stderr

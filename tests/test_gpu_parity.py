@@ -819,3 +819,33 @@ def test_lean_cycle_host_and_config1():
     rg, (tg0, tt0, tc0, st0) = run_product(1, q, qd, fs1, flags, 3)
     assert rl.last_path() == 1 and np.array_equal(st & 7, st0 & 7)
     assert relerr(tg, tg0) < 1e-10 and relerr(tt, tt0) < 1e-9
+
+
+def test_cpp_hosts_on_the_gpu():
+    """The two C++ hosts of the C ABI against the REAL library on the GPU: include/dwbc_b200.hpp (DWBC::RobotDataBatch, tests/shim_check.cpp)
+    and include/dwbc_compat/dwbc.h (the header-compatible single-state DWBC::RobotData running the reference's own CASE 1 / CASE 2 sequence
+    against the golden binaries, tests/robotdata_check.cpp)."""
+    from libdwbc_b200._lib import library_path
+    from oracle.urdf_model import read_golden
+    from tests.test_abi import build_and_run_cpp
+
+    _dev()
+    lib = library_path()
+    r = build_and_run_cpp(lib, "robotdata_check.cpp", ["include/dwbc_compat"], [URDF, os.path.join(GOLDEN, "cases")])
+    assert r.returncode == 0 and r.stdout.strip().endswith("ALL OK"), r.stdout + r.stderr
+    r = build_and_run_cpp(lib, "shim_check.cpp", ["include"], [URDF])
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = r.stdout.splitlines()
+    vals = np.array([[float(x) for x in l.split()] for l in out[:33]])
+    g = lambda n: read_golden(os.path.join(GOLDEN, "cases", "1", n))[:, 0]
+    assert relerr(vals[:, 0], g("torque_grav_")) < 1e-9 and relerr(vals[:, 1], g("torque_task_")) < 1e-9 and relerr(vals[:, 2], g("torque_contact_")) < 1e-9
+    assert out[33] == "status 7" and out[34].startswith("error ok: Link Name is Wrong")
+
+
+def test_pybind_module_on_the_gpu():
+    """`import dwbc` (the compiled pybind11 module with the reference's RlWBCBridge signature) against libdwbc_b200.so on the GPU."""
+    from libdwbc_b200._lib import library_path
+    from tests.test_bridge import run_pybind_module
+
+    _dev()
+    run_pybind_module(library_path(), os.path.dirname(library_path()))
