@@ -511,6 +511,9 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
         }
     }
     res.q = q;
+#ifdef DWBC_CPU_EMUL
+    if (tid == 0 && getenv("DWBC_QP_TRACE")) fprintf(stderr, "gi_solve nv %d col0 %d pin %d iters %d status %d q %d\n", nv, col0, use_pin, res.iters, res.status, q);
+#endif
     tsync();
     return res;
 }

@@ -101,6 +101,44 @@ def flops_per_solve(task_dofs, **kw):
     return sum(per_kernel_flops(task_dofs, **kw).values())
 
 
+# ---- variants (BASELINE.json configs[3]); same as-written convention, coarser because the reference code is longer ----
+def reduced_flops(task_dofs, c=12, hqp=True, redist=True, qp_iters_total=None, n=N_SYS, m=M_DOF):
+    """Reduced-dimension pipeline (reference src/dwbc.cpp:2752-3446): full-model rbd + A^-1, the nc-chain CRBA / lumped body,
+    J_R A^-1 J_R^T and its LLT inverse, then the contact / task / QP pipeline at n_R = 6 + c + 6, m_R = c + 6."""
+    nr, mr, nc = 6 + c + 6, c + 6, m - c
+    assemble = 8.0e3 + 2 * 6 * 6 * nc + 2 * nr * n * n + 2 * nr * nr * n + nr ** 3 / 3.0 + 2.0 * nr ** 3 + 2 * nr * n + 4 * nc * nc * 6
+    pk = per_kernel_flops(task_dofs, c=c, hqp=hqp, redist=redist, tlim=True, qp_iters_total=qp_iters_total, n=nr, m=mr)
+    red = assemble + pk["contact_dynamics_kernel"] + pk["task_space_kernel"] + pk["hqp_kernel"] + 2 * m * nr
+    return {"rbd_kernel": rbd_flops(n), "ainv_kernel": ainv_flops(n), "contact_jacobian_kernel": contact_jacobian_flops(c), "reduced_kernels": red}
+
+
+def lqp_level_flops(nv, k_prev, eq_rows, ineq_rows, carried_rows, iters=8.0):
+    """One level of the null-space hierarchy (reference src/dwbc_hqp.cpp:23-58, 291-395): B Z, COD null space, Z update,
+    H = (BZ)^T BZ, A Z for this level's and the carried inequality rows, then the QP in [u; v]."""
+    k = max(k_prev - eq_rows, 0)
+    f = 2 * eq_rows * nv * k_prev + (4.0 / 3) * k_prev ** 3 + 2 * nv * k_prev * k
+    f += 2 * eq_rows * k_prev * k_prev + 2 * (ineq_rows + carried_rows) * nv * k_prev
+    f += qp_solve_flops(ineq_rows + carried_rows, k_prev + ineq_rows, iters)
+    return f, k
+
+
+def lqp_flops(task_dofs, c=12, n=N_SYS, m=M_DOF, iters=8.0):
+    """ConfigureLQP + CalcControlTorqueLQP (reference src/dwbc.cpp:4304-4454): y = [qdd; Fc], level 0 dynamics (6 eq, 2m torque
+    rows carried), level 1 contact (c eq, 10 c/6 + 2m rows), then one level per task."""
+    nv = n + c
+    f = 2 * n * n  # y0 = -A^-1 B
+    l0, k = lqp_level_flops(nv, nv, 6, 0, 2 * m, 0.0)
+    f += l0
+    carried = 2 * m
+    l1, k = lqp_level_flops(nv, k, c, 10 * (c // 6) + 2 * m, carried, iters)
+    f += l1
+    carried += 10 * (c // 6) + 2 * m
+    for t in task_dofs:
+        lt, k = lqp_level_flops(nv, k, t, 0, carried, iters)
+        f += lt
+    return f + 2 * m * nv  # torque from y
+
+
 # Compulsory HBM traffic of one solve (SURVEY 8(d)): q, qdot, f*, flags in; three torque vectors + status out.
 def io_bytes_per_solve(task_dofs, ncontact=2, n=N_SYS, m=M_DOF):
     return 8 * (n + 1) + 8 * n + 8 * sum(task_dofs) + ncontact, 3 * 8 * m + 4
