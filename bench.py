@@ -98,7 +98,7 @@ def make_inputs(B, seed, args):
     elif args.config == "3i":
         fs = [0.5 * rng.standard_normal((B, 3)), rng.standard_normal((B, 3)), rng.standard_normal((B, 3)), rng.standard_normal((B, 6))]
     elif dofs:
-        fs = synth_fstar(rng, B, dofs=dofs, scales=(0.5, 1.0, 2.0)[:len(dofs)], hard_frac=0.05 if args.cfg["kind"] == 2 else 0.0)
+        fs = synth_fstar(rng, B, dofs=dofs, scales=(0.5, 1.0, 2.0)[:len(dofs)], hard_frac=float(os.environ.get("DWBC_BENCH_HARD_FRAC", "0.05")) if args.cfg["kind"] == 2 else 0.0)  # env: diagnostics only
     else:
         fs = []
     flags = np.ones((B, 2), dtype=np.uint8)

@@ -267,7 +267,8 @@ inline bool lean_staged(const dwbc_batch *b) { return b->outputs == DWBC_OUT_TOR
 template <class S>
 int launch_lean(dwbc_batch *b, int stages, cudaStream_t st) {
     using L = LeanSmem<S>;
-    const size_t smem = sizeof(double) * L::total;
+    const size_t smem = sizeof(double) * L::total * LEAN_GANG;
+    const int lean_grid = (b->B + LEAN_GANG - 1) / LEAN_GANG;
     CK(cudaFuncSetAttribute(lean_cycle_kernel<S, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(lean_cycle_kernel<S, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LeanArgs a{};
@@ -291,13 +292,13 @@ int launch_lean(dwbc_batch *b, int stages, cudaStream_t st) {
         KernelScope ks(b, DWBC_K_LEAN, st);
         a.plist = plist0;
         a.pcount = pcount;
-        DWBC_LAUNCH((lean_cycle_kernel<S, 12>), b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, a);
+        DWBC_LAUNCH((lean_cycle_kernel<S, 12>), lean_grid, TEAM * LEAN_GANG, smem, st, b->d_model, b->d_cfg, b->w, a);
     }
     {
         KernelScope ks(b, DWBC_K_LEAN, st);
         a.plist = plist0 + b->B;
         a.pcount = pcount + 1;
-        DWBC_LAUNCH((lean_cycle_kernel<S, 6>), b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, a);
+        DWBC_LAUNCH((lean_cycle_kernel<S, 6>), lean_grid, TEAM * LEAN_GANG, smem, st, b->d_model, b->d_cfg, b->w, a);
     }
     CK(cudaGetLastError());
     if (stages & (DWBC_SOLVE_HQP | DWBC_SOLVE_REDIST)) {
@@ -309,7 +310,9 @@ int launch_lean(dwbc_batch *b, int stages, cudaStream_t st) {
         const size_t hs = sizeof(double) * H.total;
         CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
         KernelScope ks(b, DWBC_K_HQP, st);
-        DWBC_LAUNCH(hqp_kernel, b->B, TEAM, hs, st, b->d_model, b->d_cfg, b->w, a.hqp, a.redist, nvmax, (const int *)a.list, (const int *)a.count);
+        Work wq = b->w;
+        wq.hqp_timing = a.timing;
+        DWBC_LAUNCH(hqp_kernel, b->B, TEAM, hs, st, b->d_model, b->d_cfg, wq, a.hqp, a.redist, nvmax, (const int *)a.list, (const int *)a.count);
     }
     CK(cudaGetLastError());
     return DWBC_OK;

@@ -85,6 +85,7 @@ struct Work {
     uint32_t *active[MAX_LEVELS + 1];  // [B][ACTIVE_WORDS], last = redistribution
     double *tau_task, *tau_contact, *cf_redis;  // [B][m], [B][m], [B][RMAX]
     int *qp_iters;  // [B] total active-set iterations (diagnostics)
+    long long *hqp_timing;  // diagnostics (null unless dwbc_batch_set_lean_timing): [B][32], hqp_kernel accumulates cycles per phase in slots 21..29
 };
 
 }  // namespace dwbc

@@ -523,11 +523,11 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
 // rows and  lambda = R^{-1} w  its multipliers.  If lambda >= 0 and every other row is satisfied this is the (unique) optimum
 // of the new sub-problem -- at the cost of about one active-set iteration; otherwise nothing is modified and the caller falls
 // back to a cold gi_solve.  Same team conventions as gi_solve; synchronises on entry and exit.
-__device__ __noinline__ bool gi_warm(double *sm, int n, int m, int nvmax, int mt, int nc, int col0, int nv, int q) {
+__device__ __noinline__ bool gi_warm(double *sm, int n, int m, int nvmax, int mt, int nc, int col0, int nv, int q, int use_bt) {
     const HqpSmem L(n, m, nvmax);
     const GiScratch S(sm + L.gi, sm + L.bt);
     const QpView V{sm + L.U, sm + L.AU, L.ldm, L.ldc, m, mt, nc, col0, nv};
-    const double *bt = sm + L.bt, *tolv = sm + L.tol, *rin = sm + L.rin, *Q = sm + L.Q, *R = sm + L.R;
+    const double *bt = use_bt ? sm + L.bt : sm + L.b, *tolv = sm + L.tol, *rin = sm + L.rin, *Q = sm + L.Q, *R = sm + L.R;
     const int ldq = L.ldq;
     const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
     const int mc = V.rows();
@@ -622,7 +622,7 @@ struct LevelOut {
 // boff / row_shift: the problem's rows start at b[boff] and are reported as rows row_shift.. (a solve without the torque rows: mt = 0,
 // boff = row_shift = 2m keeps the reference's row numbering in the active set).
 __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax, int t, int r, int mt, int nc, uint32_t *active_out, int boff,
-                                             int row_shift) {
+                                             int row_shift, int c0, int skip_a) {
     const HqpSmem L(n, m, nvmax);
     const GiScratch S(sm + L.gi, sm + L.bt);
     const double *b = sm + L.b + boff;
@@ -630,7 +630,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
     const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
     const int nv = t + r, mc = mt + nc;
     LevelOut out{1, 0, 0};
-    const QpView V{sm + L.U, sm + L.AU, L.ldm, L.ldc, m, mt, nc, 0, nv};
+    const QpView V{sm + L.U, sm + L.AU, L.ldm, L.ldc, m, mt, nc, c0, nv};
     double *xj = S.xj, *xs = S.xs, *xp = S.xp;
     tsync();
     if (tid < QP_NV_MAX) xj[tid] = 0.0;
@@ -701,17 +701,17 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
     const int max_iter = 20 * (nv + 8);
     bool done = false;
     if (t == 0 || r == 0) {
-        GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, 0, nv, 0, 1.0, 1.0, nv, 0, max_iter, zero_row_tol, boff);
+        GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, c0, nv, 0, 1.0, 1.0, nv, 0, max_iter, zero_row_tol, boff);
         out.iters += g.iters;
         out.status = g.status;
         if (tid < nv) xj[tid] = S.dxs[tid];
         done = true;
     }
-    if (!done) {
+    if (!done && !skip_a) {
         // ---- A: is x_t = 0 attainable?  (looser tolerances: the set may be a thin face inherited from the levels above)
         DWBC_UNROLL(1)
         for (int i = tid; i < mc; i += nt) tolv[i] *= 100.0;
-        GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, t, r, 0, 1.0, 1.0, r, 0, max_iter, zero_row_tol, boff);
+        GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, c0 + t, r, 0, 1.0, 1.0, r, 0, max_iter, zero_row_tol, boff);
         out.iters += g.iters;
         if (g.status) {
             if (tid < r) xj[t + tid] = S.dxs[tid];
@@ -752,10 +752,10 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
                 for (int j = t; j < nv; j++) s = fma(-V.a(i, j), xs[j], s);
                 bt[i] = s;
             }
-            if (k > 0 && !force_cold && gi_warm(sm, n, m, nvmax, mt, nc, 0, nv, g.q)) {
+            if (k > 0 && !force_cold && gi_warm(sm, n, m, nvmax, mt, nc, c0, nv, g.q, 1)) {
                 out.iters += 1;
             } else {
-                g = gi_solve(sm, n, m, nvmax, mt, nc, 0, nv, 1, 1.0, isd_c, t, 0, max_iter, zero_row_tol, boff);
+                g = gi_solve(sm, n, m, nvmax, mt, nc, c0, nv, 1, 1.0, isd_c, t, 0, max_iter, zero_row_tol, boff);
                 out.iters += g.iters;
             }
             force_cold = false;
@@ -794,6 +794,9 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
         // 1e-12 step test within the cap keeps its last iterate (qpOASES, with nWSR = 1000, would also return a point for a
         // feasible problem; reference src/dwbc.cpp:1080) and is flagged DWBC_ST_QP_SLOW instead of being reported as failed.
         if (out.status && !conv) out.slow = 1;
+#ifdef DWBC_CPU_EMUL
+        if (tid == 0 && getenv("DWBC_QP_TRACE")) fprintf(stderr, "prox t %d r %d iters_so_far %d conv %d reductions %d\n", t, r, out.iters, (int)conv, reductions);
+#endif
         if (out.status) {
             // ---- C: min |x_c|^2 on the optimal face; rows with a positive multiplier are pinned ----
             const double umax = warp_max(lane < g.q ? S.u[lane] : 0.0);  // identical in every warp
@@ -813,7 +816,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
                 bt[i] = s;
                 tolv[i] *= 100.0;
             }
-            GiResult gc = gi_solve(sm, n, m, nvmax, mt, nc, t, r, 1, 1.0, 1.0, r, 1, max_iter, zero_row_tol, boff);
+            GiResult gc = gi_solve(sm, n, m, nvmax, mt, nc, c0 + t, r, 1, 1.0, 1.0, r, 1, max_iter, zero_row_tol, boff);
             out.iters += gc.iters;
             if (!gc.status) out.status = 0;
             if (tid < r) xj[t + tid] = S.dxs[tid];
@@ -848,6 +851,115 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
     return out;
 }
 
+// The contact-variable sub-problem  min |x_c|^2  s.t. every row holds with x_t = 0  (stage A of solve_level; for the redistribution
+// QP, which has no task variables, the whole problem).  Its matrix -- the columns [NwJw] of U and Atemp NwJw of AU, at columns
+// [cc, cc + r) -- is the SAME for every level of the hierarchy and for the redistribution of one state; only the right-hand side b
+// moves with the torque of the levels above.  So the caller assembles those r columns once per state and this function keeps the
+// factorisation of the last solve (aq = number of active rows it left, -1: none) and first tries gi_warm on it: about one active-set
+// iteration when the active rows stay the same from level to level, which is the common case (a friction / ZMP row that the first
+// level leaves active stays active below).  Falls back to a cold gi_solve.  The window norms are kept in the bt array (unused here:
+// the right-hand side is b itself).  t = task dof of this level (only to place the answer in S.xj = [0_t; x_c] and, for the few
+// torque rows that end with zero slack, to evaluate the task part of their normal from Ntq in global memory); loose: the 100 times
+// wider row tolerances of stage A.  status 0: x_t = 0 is not attainable (nothing usable is left in S.xj).
+__device__ __noinline__ LevelOut solve_contact_only(double *sm, int n, int m, int nvmax, int t, int r, int mt, int nc, uint32_t *active_out, int cc,
+                                                    int *aq_io, int loose, const double *__restrict__ Ntq) {
+    const HqpSmem L(n, m, nvmax);
+    const GiScratch S(sm + L.gi, sm + L.bt);
+    const double *b = sm + L.b;
+    double *tolv = sm + L.tol, *nrm = sm + L.bt;
+    const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
+    const int mc = mt + nc;
+    const QpView V{sm + L.U, sm + L.AU, L.ldm, L.ldc, m, mt, nc, cc, r};
+    LevelOut out{1, 0, 0};
+    int aq = *aq_io;
+    tsync();
+    if (aq < 0) {  // (re)build the window norms: a full solve of an earlier level used bt
+        DWBC_UNROLL(1)
+        for (int i = tid; i < mc; i += nt) {
+            double s = 0.0;
+            DWBC_UNROLL(1)
+            for (int j = 0; j < r; j++) {
+                const double v = V.a(i, j);
+                s = fma(v, v, s);
+            }
+            nrm[i] = s;
+        }
+    }
+    double smax = 0.0, babs = 0.0;
+    tsync();
+    DWBC_UNROLL(1)
+    for (int i = tid; i < mc; i += nt) smax = fmax(smax, nrm[i]), babs = fmax(babs, fabs(b[i]));
+    team_max2(smax, babs, S);
+    const double ztol = 1e-9 * (1.0 + babs);
+    const double rel = loose ? 1e-8 : 1e-10;
+    bool infeasible = false;
+    DWBC_UNROLL(1)
+    for (int i = tid; i < mc; i += nt) {
+        const double s = nrm[i];
+        const double tl = rel * fmax(sqrt(s), fabs(b[i]));
+        tolv[i] = tl;
+        // a row the contact variables cannot move (e.g. the torque limit of an upper-body joint) must already hold
+        if (!(s > 1e-20 * smax && s >= 1e-28) && b[i] < -fmax(tl, ztol)) infeasible = true;
+    }
+    const bool winf = __any_sync(DWBC_FULL, infeasible);
+    if (lane == 0) S.ired[warp] = winf ? 1 : 0;
+    tsync();
+    bool any_inf = false;
+    DWBC_UNROLL(1)
+    for (int w = 0; w < nw; w++) any_inf = any_inf || S.ired[w];
+    tsync();
+    if (any_inf) {
+        out.status = 0;
+        return out;
+    }
+    if (aq >= 0 && gi_warm(sm, n, m, nvmax, mt, nc, cc, r, aq, 0)) {
+        out.iters = 1;
+#ifdef DWBC_CPU_EMUL
+        if (tid == 0 && getenv("DWBC_QP_TRACE")) fprintf(stderr, "contact_only warm t %d q %d\n", t, aq);
+#endif
+    } else {
+#ifdef DWBC_CPU_EMUL
+        if (tid == 0 && getenv("DWBC_QP_TRACE")) fprintf(stderr, "contact_only cold t %d (kept q %d)\n", t, aq);
+#endif
+        const GiResult g = gi_solve(sm, n, m, nvmax, mt, nc, cc, r, 0, 1.0, 1.0, r, 0, 20 * (r + 8), ztol, 0);
+        out.iters = g.iters;
+        out.status = g.status;
+        aq = g.status ? g.q : -1;
+        *aq_io = aq;
+        if (!g.status) return out;
+    }
+    if (tid < QP_NV_MAX) S.xj[tid] = (tid >= t && tid < t + r) ? S.dxs[tid - t] : 0.0;
+    tsync();
+    // active rows at the solution (rule of solve_level: slack within 1e-9 (1 + |b|), rows with a zero normal excluded)
+    DWBC_UNROLL(1)
+    for (int i0 = 0; i0 < mc; i0 += nt) {
+        const int i = i0 + tid;
+        bool on = false;
+        if (i < mc) {
+            double sl = -b[i];
+            DWBC_UNROLL(1)
+            for (int j = 0; j < r; j++) sl = fma(V.a(i, j), S.xj[t + j], sl);
+            if (sl > -1e-9 * (1.0 + fabs(b[i]))) {
+                double nn2 = nrm[i];
+                if (!(nn2 > 0.0) && i < mt && Ntq) {
+                    const int row = i < m ? i : i - m;
+                    DWBC_UNROLL(1)
+                    for (int j = 0; j < t; j++) nn2 = fma(Ntq[row + j * m], Ntq[row + j * m], nn2);
+                }
+                on = nn2 > 0.0;
+            }
+        }
+        const unsigned bal = __ballot_sync(DWBC_FULL, on);
+        const int word = (i0 >> 5) + warp;
+        if (lane == 0 && word < ACTIVE_WORDS) S.pinw[word] = bal;
+    }
+    if (tid < ACTIVE_WORDS && tid >= (mc + 31) / 32) S.pinw[tid] = 0u;
+    tsync();
+    if (active_out && tid < ACTIVE_WORDS) active_out[tid] = S.pinw[tid];
+    tsync();
+    return out;
+}
+
 // One CTA (team) per state: QP assembly (U, Atemp U, right-hand sides), the active-set iterations (gi_solve) and the torque
 // updates all use every thread of the team.
 // list / count (may be null): the compact list of states left QP-active by lean_cycle_kernel (kernels_lean.cuh); CTA i finishes state
@@ -865,7 +977,7 @@ __global__ void __launch_bounds__(TEAM, 7) hqp_kernel(const DevModel *__restrict
     const GiScratch S(sm + L.gi, sm + L.bt);
     double *vec = sm + L.vec;
     const int vs = n + 2;
-    double *tprev = vec, *base = vec + vs, *fs = vec + 2 * vs, *bA0 = vec + 3 * vs, *xs = vec + 4 * vs, *lf = vec + 5 * vs;
+    double *tprev = vec, *base = vec + vs, *fs = vec + 2 * vs, *xs = vec + 4 * vs, *lf = vec + 5 * vs;
     const int ldm = L.ldm, ldc = L.ldc;
     int st = w.status[s];
     const bool contact_ok = st & 1;
@@ -877,30 +989,40 @@ __global__ void __launch_bounds__(TEAM, 7) hqp_kernel(const DevModel *__restrict
     const int nc = 10 * kc;
     const int mt = cfg->tlim_set ? 2 * m : 0;
     int total_iters = 0;
+    // diagnostics (builds with -DDWBC_HQP_TIMING only: the bookkeeping costs registers of a kernel compiled for seven states per SM):
+    // cycles per phase accumulated in slots 21.. of the state's stamp record (tools/lean_phases.py)
+#ifdef DWBC_HQP_TIMING
+    long long *tm = w.hqp_timing ? w.hqp_timing + s * 32 : nullptr;
+    long long tlast = tm ? clock64() : 0;
+    auto lap = [&](int k) {
+        if (tm && tid == 0) {
+            const long long now = clock64();
+            tm[k] += now - tlast;
+            tlast = now;
+        }
+    };
+    if (tm && tid < 11) tm[21 + tid] = 0;
+#else
+    constexpr long long *tm = nullptr;
+    auto lap = [](int) {};
+#endif
     double *tau_task = w.tau_task + s * m, *tau_contact = w.tau_contact + s * m;
     if (!contact_ok) {  // uniform over the CTA
         if (tid == 0) w.status[s] = st, w.qp_iters[s] = 0;
         return;
     }
-    // ---- Atemp = A_const A_rot Jbar^T[:, 6:]  (nc x m)  and  bA0 = A_const A_rot P_C.  Rebuilt for every QP: the solver's Q / R
-    // overwrite its storage (a few hundred flops from L2-resident operands against 4-5 KB of shared memory per state) ----
+    // ---- Atemp = A_const A_rot Jbar^T[:, 6:]  (nc x m).  Rebuilt when a QP needs it again: the solver's Q / R overwrite its storage
+    // (a few hundred flops from L2-resident operands against 4-5 KB of shared memory per state) ----
     auto build_At = [&]() {
         const double *Jb = w.Jbar + s * (long long)CMAX * n;
         const double *pose = w.pose + s * (long long)nb * POSE_STRIDE;
-        for (int e = tid; e < kc * (m + 1); e += nt) {
-            const int k = e / (m + 1), j = e - k * (m + 1);
+        for (int e = tid; e < kc * m; e += nt) {
+            const int k = e / m, j = e - k * m;
             const ContactCfg &cc = cfg->contacts[w.cidx[s * MAX_ACTIVE_CONTACTS + k]];
-            const double *Rl = pose + cc.link * POSE_STRIDE;
+            const double *col = Jb + 6 * k + (long long)(6 + j) * CMAX;
             double o[10];
-            if (j < m) {
-                const double *col = Jb + 6 * k + (long long)(6 + j) * CMAX;
-                contact_rows(cc, Rl, ld3(col), ld3(col + 3), o);
-                for (int a = 0; a < 10; a++) At[10 * k + a + j * ldc] = o[a];
-            } else {
-                const double *pc = w.PC + s * CMAX + 6 * k;
-                contact_rows(cc, Rl, ld3(pc), ld3(pc + 3), o);
-                for (int a = 0; a < 10; a++) bA0[10 * k + a] = o[a];
-            }
+            contact_rows(cc, pose + cc.link * POSE_STRIDE, ld3(col), ld3(col + 3), o);
+            for (int a = 0; a < 10; a++) At[10 * k + a + j * ldc] = o[a];
         }
     };
     // ---- fast path test: with x = 0, is every row of the QP strictly satisfied for the torque `base` (shared memory, visible)?
@@ -908,6 +1030,7 @@ __global__ void __launch_bounds__(TEAM, 7) hqp_kernel(const DevModel *__restrict
     // is the optimum of both lexicographic stages with an empty active set and none of U, Atemp, Atemp U, the row norms or the
     // factorisation is needed: most QPs of the workload end here (profiles: with f* = 0 the assembly alone cost 7.4 of 9.6 ms).
     // Stricter than solve_level's own quick exit (margin 1e-8 (1 + |b|)), so the results are the same.  Uniform over the CTA.
+    // It also leaves the right-hand sides b of the QP (what the rows evaluate to at x = 0) for the solver.
     auto quick_feasible = [&]() -> bool {
         const double *Jb6 = w.Jbar + s * (long long)CMAX * n + 6 * CMAX;
         const double *pc = w.PC + s * CMAX;
@@ -919,13 +1042,18 @@ __global__ void __launch_bounds__(TEAM, 7) hqp_kernel(const DevModel *__restrict
         if (mt)
             for (int i = tid; i < m; i += nt) {
                 const double lo = cfg->tlim[i] - base[i], hi = cfg->tlim[i] + base[i];
+                b[i] = lo;
+                b[m + i] = hi;
                 okq = okq && lo > 1e-8 * (1.0 + fabs(lo)) && hi > 1e-8 * (1.0 + fabs(hi));
             }
         for (int k = tid; k < kc; k += nt) {
             const ContactCfg &cc = cfg->contacts[w.cidx[s * MAX_ACTIVE_CONTACTS + k]];
             double o[10];
             contact_rows(cc, pose + cc.link * POSE_STRIDE, ld3(lf + 6 * k), ld3(lf + 6 * k + 3), o);
-            for (int a = 0; a < 10; a++) okq = okq && (-o[a] > 1e-8 * (1.0 + fabs(o[a])));
+            for (int a = 0; a < 10; a++) {
+                b[mt + 10 * k + a] = -o[a];
+                okq = okq && (-o[a] > 1e-8 * (1.0 + fabs(o[a])));
+            }
         }
         if (!okq) S.ired[0] = 0;
         tsync();
@@ -954,6 +1082,9 @@ __global__ void __launch_bounds__(TEAM, 7) hqp_kernel(const DevModel *__restrict
         for (int i = tid; i < RMAX; i += nt) w.cf_redis[s * RMAX + i] = 0.0;
     }
     bool all_ok = task_ok;
+    const int TC = nvmax - r;  // first contact column of U / AU
+    bool cols_ready = false;   // the contact columns are assembled
+    int aq = -1;               // active rows of the kept factorisation of the contact sub-problem (-1: none)
     DWBC_UNROLL(1)
     for (int q = 0; q < nl + (redist ? 1 : 0); q++) {
         const bool lev = q < nl;
@@ -981,27 +1112,47 @@ __global__ void __launch_bounds__(TEAM, 7) hqp_kernel(const DevModel *__restrict
             }
         }
         tsync();
-        bool solved = true, have_x = false;
-        if (!quick_feasible()) {
-            // U = [Ntorque | NwJw],  AU = Atemp U,  right-hand sides
-            if (lev) tcopy(m, t, Ntq, m, U, ldm);
-            tcopy(m, r, NwJw, m, U + t * ldm, ldm);
-            build_At();
-            tsync();
-            tgemm_mma<2, false, false>(nc, nv, m, At, ldc, U, ldm, [&](int i, int j, double v) { AU[i + j * ldc] = v; });
-            if (mt)
-                for (int i = tid; i < m; i += nt) {
-                    b[i] = cfg->tlim[i] - base[i];
-                    b[m + i] = cfg->tlim[i] + base[i];
-                }
-            tgemv<false>(nc, m, At, ldc, base, [&](int i, double v) { b[mt + i] = -(bA0[i] - v); });
-            tsync();
-            // (Solving on the contact rows alone first and verifying the torque rows afterwards -- they are never active in the headline
-            // workload -- was measured slower: 7.75 vs 7.11 ms per 65 536 states; the row scan is not what bounds this kernel.)
+        bool solved = true, have_x = false, xt_zero = true;
+        lap(21);
+        const bool qf = quick_feasible();
+        lap(22);
+        if (!qf) {
+            if (tm && tid == 0) tm[29] += 1;
             uint32_t *aout = w.active[lev ? q : MAX_LEVELS] + s * ACTIVE_WORDS;
-            const LevelOut lo = solve_level(sm, n, m, nvmax, t, r, mt, nc, aout, 0, 0);
-            total_iters += lo.iters;
-            if (lo.slow) st |= 16;
+            LevelOut lo{0, 0, 0};
+            if (r > 0) {
+                // the contact columns [NwJw] / Atemp NwJw sit at the fixed columns [TC, TC + r) and are assembled once per state
+                if (!cols_ready) {
+                    tcopy(m, r, NwJw, m, U + TC * ldm, ldm);
+                    build_At();
+                    tsync();
+                    tgemm_mma<2, false, false>(nc, r, m, At, ldc, U + TC * ldm, ldm, [&](int i, int j, double v) { AU[i + (TC + j) * ldc] = v; });
+                    tsync();
+                    cols_ready = true;
+                    aq = -1;
+                    lap(23);
+                }
+                lo = solve_contact_only(sm, n, m, nvmax, t, r, mt, nc, aout, TC, &aq, lev ? 1 : 0, lev ? Ntq : nullptr);
+                total_iters += lo.iters;
+                lap(24);
+            }
+            if (!lo.status && lev) {
+                // x_t = 0 is not attainable (or there is no internal-force space): the whole problem, task columns [TC - t, TC)
+                tcopy(m, t, Ntq, m, U + (TC - t) * ldm, ldm);
+                build_At();
+                tsync();
+                tgemm_mma<2, false, false>(nc, t, m, At, ldc, U + (TC - t) * ldm, ldm, [&](int i, int j, double v) { AU[i + (TC - t + j) * ldc] = v; });
+                tsync();
+                lap(25);
+                xt_zero = false;
+                aq = -1;  // the solver reuses the storage of the kept factorisation
+                // (Solving on the contact rows alone first and verifying the torque rows afterwards -- they are never active in the headline
+                // workload -- was measured slower: 7.75 vs 7.11 ms per 65 536 states; the row scan is not what bounds this kernel.)
+                lo = solve_level(sm, n, m, nvmax, t, r, mt, nc, aout, 0, 0, TC - t, r > 0 ? 1 : 0);
+                total_iters += lo.iters;
+                if (lo.slow) st |= 16;
+                lap(26);
+            }
             solved = lo.status != 0;
             have_x = solved;
         }
@@ -1026,12 +1177,25 @@ __global__ void __launch_bounds__(TEAM, 7) hqp_kernel(const DevModel *__restrict
         }
         tsync();
         if (lev) {
-            // torque_task += Null_{l-1} J_kt Lambda (f* + f*_qp) = Ntorque (f* + x_t);  tau_prev = tau_grav + torque_task
-            tgemv<false>(m, t, Ntq, m, fs, [&](int i, double v) {
-                const double tt = tau_task[i] + v;
-                tau_task[i] = tt;
-                tprev[i] = w.tau_grav[s * m + i] + tt;
-            });
+            // torque_task += Null_{l-1} J_kt Lambda (f* + f*_qp) = Ntorque (f* + x_t);  tau_prev = tau_grav + torque_task.
+            // With x_t = 0 (the x = 0 test or the contact-only solve decided the level) Ntorque f* is base - tau_prev: no second pass
+            // over Ntorque in global memory.
+#ifdef DWBC_HQP_NO_XTZERO
+            xt_zero = false;
+#endif
+            if (xt_zero) {
+                for (int i = tid; i < m; i += nt) {
+                    const double tt = tau_task[i] + (base[i] - tprev[i]);
+                    tau_task[i] = tt;
+                    tprev[i] = w.tau_grav[s * m + i] + tt;
+                }
+            } else {
+                tgemv<false>(m, t, Ntq, m, fs, [&](int i, double v) {
+                    const double tt = tau_task[i] + v;
+                    tau_task[i] = tt;
+                    tprev[i] = w.tau_grav[s * m + i] + tt;
+                });
+            }
             // torque_h = J_kt Lambda_t (f* + f*_qp)   (a public field: not produced when only the torques were asked for)
             if (w.torque_h[q]) {
                 const double *Lt = w.Lamt[q] + s * (long long)t * t, *Jk = w.Jkt[q] + s * (long long)m * t;
@@ -1042,10 +1206,15 @@ __global__ void __launch_bounds__(TEAM, 7) hqp_kernel(const DevModel *__restrict
         }
         // level: torque_contact = NwJw contact_qp (zero without an internal-force space: quirk 1 of SURVEY Appendix A);
         // redistribution: torque_contact += NwJw x
-        if (r > 0) tgemv<false>(m, r, NwJw, m, xs, [&](int i, double v) { tau_contact[i] = (lev ? 0.0 : tau_contact[i]) + v; });
+        if (r > 0) {
+            if (have_x) tgemv<false>(m, r, NwJw, m, xs, [&](int i, double v) { tau_contact[i] = (lev ? 0.0 : tau_contact[i]) + v; });
+            else if (lev)
+                for (int i = tid; i < m; i += nt) tau_contact[i] = 0.0;
+        }
         if (!lev) st |= 4;
     }
     if (hqp && all_ok) st |= 2;
+    lap(21);
     if (tid == 0) {
         w.status[s] = st;
         w.qp_iters[s] = total_iters;

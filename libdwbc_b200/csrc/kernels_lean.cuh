@@ -95,6 +95,15 @@ __global__ void lean_classify_kernel(const BatchCfg *__restrict__ cfg, const uin
         if ((tm) && t_id() == 0) (tm)[k] = clock64(); \
     } while (0)
 
+// states per CTA of lean_cycle_kernel (see the kernel)
+#ifndef LEAN_GANG
+#ifdef DWBC_CPU_EMUL
+#define LEAN_GANG 1
+#else
+#define LEAN_GANG 1
+#endif
+#endif
+
 // shared-memory arena of one state (doubles)
 template <class S>
 struct LeanSmem {
@@ -570,16 +579,22 @@ __device__ __noinline__ bool lean_quick_feasible(const BatchCfg *__restrict__ cf
 }
 
 template <class S, int CSEL>
-__global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, LeanArgs a) {
+__global__ void __launch_bounds__(TEAM * LEAN_GANG, 1) lean_cycle_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, LeanArgs a) {
     static_assert(CSEL == 12 || CSEL == 6, "contact dof of the class");
-    if ((int)blockIdx.x >= *a.pcount) return;
+    // LEAN_GANG teams per CTA, one state each, on private slices of the shared-memory arena.  tsync() is the CTA-wide barrier, so
+    // the teams of an SM walk through the phases of the cycle together and fetch each stretch of this (large, mostly straight-line)
+    // kernel once per LEAN_GANG states: the instruction cache holds 32 KB, and independent one-state CTAs drifting apart had it
+    // thrashing (profiles/r02_*: icc hit rate 66 %).  A team whose slot lies beyond the list leaves at once; exited warps are not
+    // waited for by the barrier.
+    const int slot = (int)blockIdx.x * LEAN_GANG + (int)(threadIdx.x / TEAM);
+    if (slot >= *a.pcount) return;
     using L = LeanSmem<S>;
     using LV = typename S::Lv;
     constexpr int N = S::N, M = S::M, NB = S::NB, LDN = S::LDN, LDM = S::LDM, TS = S::TS;
     DWBC_DYN_SMEM(smem);
-    double *sm = (double *)smem;
+    double *sm = (double *)smem + (threadIdx.x / TEAM) * L::total;
     const int tid = t_id(), nt = t_n(), warp = lean::warp_id(), lane = lane_id();
-    const long long s = a.plist[blockIdx.x];
+    const long long s = a.plist[slot];
     double *P = sm + L::R1, *R2 = sm + L::R2, *rb = sm + L::R3;
     double *Gs = sm + L::Gs, *fs = sm + L::fs, *tgv = sm + L::tg, *tt = sm + L::tt, *base = sm + L::base, *com = sm + L::com, *misc = sm + L::misc;
     double *A06 = sm + L::A06, *rd = sm + L::rd;
@@ -590,7 +605,7 @@ __global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__rest
     // ---- a1: sweeps by one warp (rotating with the block index: warp k of every CTA shares an SM sub-partition) ----
     long long *tm = a.timing ? a.timing + s * 32 : nullptr;
     LEAN_STAMP(tm, 0);
-    const int serial_warp = (int)(blockIdx.x % lean::NW);
+    const int serial_warp = slot % lean::NW;
     rbd_sweeps_lean(md, a.q + s * (N + 1), rb, serial_warp);
     if (warp == serial_warp) {
         if (lane == 0) {
@@ -672,7 +687,7 @@ __global__ void __launch_bounds__(TEAM) lean_cycle_kernel(const DevModel *__rest
     const int c = cdof;
     LEAN_STAMP(tm, 2);
     // ---- a1: A^{-1} ----
-    lean::spd_inverse<N, LDN, LDN>(P, R2, rd, misc, (int)(blockIdx.x % lean::NW));
+    lean::spd_inverse<N, LDN, LDN>(P, R2, rd, misc, slot % lean::NW);
     LEAN_STAMP(tm, 3);
     bool good = misc[0] > 0.0 && c == CSEL;
     // ---- a2-a5 ----

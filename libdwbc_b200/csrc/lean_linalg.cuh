@@ -28,7 +28,7 @@ namespace lean {
 
 constexpr int NW = TEAM / 32;
 
-__device__ __forceinline__ int warp_id() { return (int)(threadIdx.x >> 5); }
+__device__ __forceinline__ int warp_id() { return (int)((threadIdx.x >> 5) & (NW - 1)); }  // warp within the team
 
 template <int I, int N, class F>
 __device__ __forceinline__ void static_for(F &&f) {

@@ -16,8 +16,16 @@
 
 namespace dwbc {
 
+// A CTA may hold several teams (lean_cycle_kernel: LEAN_GANG states per CTA, kernels_lean.cuh): thread index within the team and team
+// size.  For the one-team kernels (blockDim.x <= TEAM) these are threadIdx.x and blockDim.x.
+#ifdef DWBC_CPU_EMUL
 __device__ __forceinline__ int t_id() { return (int)threadIdx.x; }
 __device__ __forceinline__ int t_n() { return (int)blockDim.x; }
+#else
+static_assert((TEAM & (TEAM - 1)) == 0, "TEAM must be a power of two");
+__device__ __forceinline__ int t_id() { return (int)(threadIdx.x & (TEAM - 1)); }
+__device__ __forceinline__ int t_n() { return (int)blockDim.x < TEAM ? (int)blockDim.x : TEAM; }
+#endif
 __device__ __forceinline__ void tsync() { __syncthreads(); }
 
 // Cooperative copy of a column-major rows x cols block (global or shared on either side).

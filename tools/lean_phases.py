@@ -45,4 +45,13 @@ d = np.diff(st[:, :21], axis=1).astype(np.float64)
 d[st[:, 1:21] == 0] = np.nan  # phases a state did not go through
 out = {"B": B, "mixed": "--mixed" in sys.argv, "total_cycles_mean": float(np.nanmean(st[:, 20] - st[:, 0])),
        "phases": {NAMES[k]: float(np.nanmean(d[:, k])) for k in range(20) if not np.all(np.isnan(d[:, k]))}}
+# hqp_kernel: cycles accumulated per phase (slots 21..26), slot 29 = QPs that were not decided by the x = 0 test
+H = st[:, 21:30].astype(np.float64)
+act = H.sum(axis=1) > 0
+if act.any():
+    HN = {0: "other (base, torque updates, clears)", 1: "x = 0 feasibility tests", 2: "contact columns (once per state)", 3: "contact-only solve", 4: "full assembly", 5: "solve_level (stages B, C)"}
+    tot = H[act][:, :6].sum(axis=1)
+    out["hqp"] = {"active_states": int(act.sum()), "total_cycles_mean": float(tot.mean()), "total_cycles_p50": float(np.median(tot)), "total_cycles_p99": float(np.percentile(tot, 99)),
+                  "phases_mean": {HN[k]: float(H[act][:, k].mean()) for k in range(6)}, "qps_not_quick_mean": float(H[act][:, 8].mean()),
+                  "states_with_full_solve": int((H[:, 5] > 0).sum()), "full_solve_states_total_cycles_mean": float(tot[H[act][:, 5] > 0].mean()) if (H[:, 5] > 0).any() else None}
 print(json.dumps(out, indent=1))
