@@ -998,8 +998,11 @@ int dwbc_batch_cycle_host_levels(dwbc_batch_t *b, int stages, const double *q_ho
         rc = alloc_tasks(b, !lean);
         if (rc) return rc;
     }
-    // slices of >= 4096 states, at most 16 (measured: profiles/r01_host_slices.json): the H2D of slice k+1 and the D2H of slice k-1 run under the kernels of slice k
-    int K = b->host_slices > 0 ? b->host_slices : (int)std::min<size_t>(16, B / 4096);
+    // The H2D of slice k+1 and the D2H of slice k-1 run under the kernels of slice k.  Slice size: the generic kernels (DWBC_OUT_ALL) liked
+    // slices of 4096 states, at most 16 (profiles/r01_host_slices.json); the torque path wants few, large slices -- hqp_kernel only sees the
+    // QP-active ~44 % of a slice, and 4096 states leave it less than two waves of CTAs (profiles/r02_host_slices.json: 65 536 states in
+    // 19.2 / 18.0 / 18.2 / 18.3 / 20.2 / 23.3 ms with 1 / 2 / 4 / 8 / 16 / 32 slices) -- so slices of 32 768 states, at most 4.
+    int K = b->host_slices > 0 ? b->host_slices : (lean ? (int)std::min<size_t>(4, B / 32768) : (int)std::min<size_t>(16, B / 4096));
     K = std::max(1, std::min<int>(K, (int)B));
     if (K > 1 && !b->pipe_ready) {
         for (int i = 0; i < 2; i++) {
@@ -1878,10 +1881,10 @@ dwbc_multi_t *dwbc_multi_create(const dwbc_model_t *m, int batch, int ngpus, con
     mh->B = batch;
     mh->n = m->hm.dev.n;
     mh->m = m->hm.dev.m;
-    const size_t per = ((size_t)batch + ngpus - 1) / ngpus;
     for (int g = 0; g < ngpus; g++) {
-        const size_t first = std::min<size_t>(batch, g * per), count = std::min<size_t>(per, batch - first);
-        if (count == 0) break;
+        // balanced contiguous slices: every GPU gets floor or ceil of batch / ngpus states (none is left empty while ngpus <= batch)
+        const size_t first = (size_t)batch * g / ngpus, count = (size_t)batch * (g + 1) / ngpus - first;
+        if (count == 0) continue;
         auto sp = std::make_unique<dwbc_multi::Shard>();
         sp->device = devices ? devices[g] : g;
         sp->first = first;

@@ -964,7 +964,11 @@ __device__ __noinline__ LevelOut solve_contact_only(double *sm, int n, int m, in
 // updates all use every thread of the team.
 // list / count (may be null): the compact list of states left QP-active by lean_cycle_kernel (kernels_lean.cuh); CTA i finishes state
 // list[i] and CTAs beyond *count exit at once.  Without a list CTA i owns state i.
-__global__ void __launch_bounds__(TEAM, 7) hqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int redist,
+#ifndef DWBC_HQP_CTAS
+#define DWBC_HQP_CTAS 7  // states per SM (72 registers); 6 (80 registers) measured slower in both rounds (round 2: 7.18 vs 6.89 ms)
+#endif
+// (Out-of-line warp / team reductions shrink this kernel from 9.7 k to 8.8 k SASS instructions but run slower: 7.33 vs 7.02 ms.)
+__global__ void __launch_bounds__(TEAM, DWBC_HQP_CTAS) hqp_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int redist,
                                                       int nvmax, const int *__restrict__ list, const int *__restrict__ count) {
     DWBC_DYN_SMEM(smem);
     const int tid = t_id(), nt = t_n();

@@ -17,6 +17,14 @@ Q_CASE = {
 }
 # reference tests/dwbc_test.cpp:56-57 and :160-161
 FSTAR_CASE = {1: ([0.1, 4.0, 0.1, 0.1, -0.1, 0.1], [0.1, -0.1, 0.1]), 2: ([0.4, 2.0, 0.1, 0.3, -0.1, 0.1], [0.1, 0.1, 0.1])}
+# reference tests/sp_test/data_confirmation.cpp:41-57: a state and f* captured from a walking controller (four registered contacts, feet
+# active; COM / pelvis rotation / upper-body rotation / both hands 6D; no torque limit)
+Q_WALKING = [-0.0325, -0.0579, 0.7273, 0.0194, -0.0118, -0.0008, -0.0006, 0.0698, -0.7835, 1.6487, -0.8420, -0.0911,
+             -0.0007, 0.0767, -0.7963, 1.6742, -0.8549, -0.1150, -0.0001, -0.0003, 0.0204,
+             0.2998, 0.3001, 1.5000, -1.2701, -1.0507, 0.0000, -1.0000, 0.0000,
+             -0.0000, 0.0003, -0.2998, -0.3060, -1.5001, 1.2700, 1.0848, 0.0000, 1.0000, 0.0000, 0.9997]
+FSTAR_WALKING = ([0.3142, -1.8202, -1.7750], [-17.8677, 8.4977, 1.0850], [-8.5340, 8.5992, 1.2655],
+                 [4.0251, 3.9975, 7.5672, -8.2841, 30.3652, 0.8954, 2.7585, 3.7898, 9.3234, -9.5724, 43.8036, 2.5202])
 FOOT_POINT = (0.03, 0.0, -0.1585)  # reference tests/dwbc_test.cpp:66-67
 LEFT_FOOT, RIGHT_FOOT, PELVIS, UPPERBODY = 6, 12, 0, 15
 
@@ -71,6 +79,15 @@ def posture_selector(n=39, first_joint=12, count=21):
 # ---------------------------------------------------------------------------------------------
 def configure_product(rd, config, ncontacts=2):
     from libdwbc_b200 import CONTACT_6D, TASK_LINK_6D, TASK_LINK_POSITION, TASK_LINK_ROTATION
+    if config == "walking":  # reference tests/sp_test/data_confirmation.cpp:59-72
+        for link, lx, ly in ((LEFT_FOOT, 0.12, 0.06), (RIGHT_FOOT, 0.12, 0.06), (23, 0.04, 0.04), (31, 0.04, 0.04)):
+            rd.add_contact_constraint(link, CONTACT_6D, FOOT_POINT, (0, 0, 1), lx, ly)
+        rd.add_task_space(0, TASK_LINK_POSITION, "COM")
+        rd.add_task_space(1, TASK_LINK_ROTATION, "pelvis_link")
+        rd.add_task_space(2, TASK_LINK_ROTATION, "upperbody_link")
+        rd.add_task_space(3, TASK_LINK_6D, "L_Wrist2_Link")
+        rd.add_task_space(3, TASK_LINK_6D, "R_Wrist2_Link")
+        return rd
     rd.add_contact_constraint(LEFT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
     rd.add_contact_constraint(RIGHT_FOOT, CONTACT_6D, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
     if ncontacts == 4:
@@ -98,6 +115,15 @@ def configure_product(rd, config, ncontacts=2):
 
 def configure_oracle(ref, config, ncontacts=2):
     from oracle import oracle as orc
+    if config == "walking":
+        for link, lx, ly in ((LEFT_FOOT, 0.12, 0.06), (RIGHT_FOOT, 0.12, 0.06), (23, 0.04, 0.04), (31, 0.04, 0.04)):
+            ref.add_contact(link, FOOT_POINT, (0, 0, 1), lx, ly)
+        ref.add_task(0, orc.TASK_LINK_POSITION, "COM")
+        ref.add_task(1, orc.TASK_LINK_ROTATION, "pelvis_link")
+        ref.add_task(2, orc.TASK_LINK_ROTATION, "upperbody_link")
+        ref.add_task(3, orc.TASK_LINK_6D, "L_Wrist2_Link")
+        ref.add_task(3, orc.TASK_LINK_6D, "R_Wrist2_Link")
+        return ref
     ref.add_contact(LEFT_FOOT, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
     ref.add_contact(RIGHT_FOOT, FOOT_POINT, (0, 0, 1), 0.15, 0.075)
     if ncontacts == 4:
@@ -124,8 +150,38 @@ def configure_oracle(ref, config, ncontacts=2):
     return ref
 
 
+def walking_inputs(B=1):
+    """The captured walking state of reference tests/sp_test/data_confirmation.cpp:41-57 (B copies): q with the base quaternion
+    normalised (the capture is rounded to four decimals; RBDL expects a unit quaternion, and with a non-unit one the rotation matrix
+    is not orthogonal -- the oracle, which follows RBDL's body-frame recursions, and the kernels, which work in one common frame, then
+    differ by O(1 - |quat|) = 3e-7), zero velocity, the four f* vectors, contact flags feet on / hands off."""
+    q = np.array([Q_WALKING] * B, dtype=np.float64)
+    q[:, [3, 4, 5, 39]] /= np.linalg.norm(q[0, [3, 4, 5, 39]])
+    fs = [np.array([f] * B, dtype=np.float64) for f in FSTAR_WALKING]
+    flags = np.array([[1, 1, 0, 0]] * B, dtype=np.uint8)
+    return q, np.zeros((B, 39)), fs, flags
+
+
+def check_walking_state(rd, out, to_np):
+    """Product results for walking_inputs() against the oracle: torques 1e-9 (the QPs are active: the right foot is unloaded to zero
+    wrench, a vertex where all ten rows of that contact and one row of the left foot hold with equality), identical active sets."""
+    from oracle import oracle as orc
+
+    q, qd, fs, flags = walking_inputs(1)
+    o = configure_oracle(orc.OracleRobot(URDF), "walking").run_batch(q, qd, fs, flags, sets=True)
+    tg, tt, tc, st = [to_np(x) for x in out]
+    assert int(st[0]) & 7 == 7 and int(o["status"][0]) & 7 == 7
+    assert relerr(tg[0], o["torque_grav"][0]) < 1e-9
+    assert relerr(tt[0], o["torque_task"][0]) < 1e-9 and relerr(tc[0], o["torque_contact"][0]) < 1e-9
+    assert np.abs(tt[0]).max() > 10 and np.abs(tc[0]).max() > 10
+    for l in range(4):
+        rows = [i for i in range(128) if (int(o["active"][0, l, i // 32]) >> (i % 32)) & 1]
+        got = list(rd.active_set(l)[0])
+        assert got == rows and len(rows) >= 10, (l, got, rows)
+
+
 def config_dofs(config):
-    return {"golden": (6, 3), 1: (3, 3), 2: (3, 6, 21), "lqp": (6, 6)}[config]
+    return {"golden": (6, 3), 1: (3, 3), 2: (3, 6, 21), "lqp": (6, 6), "walking": (3, 3, 3, 12)}[config]
 
 
 def lqp_fstars(rng, B, hard=False):

@@ -47,12 +47,12 @@ def check_lqp(rd, out, refs, flags, tol=1e-6):
 
 @pytest.mark.parametrize("hard", [False, True])
 def test_emul_lqp_vs_oracle(hard):
-    B = 4
+    B = 3
     q, qd, rng = synth_states(B, 20243)
     fs = lqp_fstars(rng, B, hard)
     flags = np.ones((B, 2), dtype=np.uint8)
-    flags[2] = [1, 0]
-    flags[3] = [0, 1]
+    flags[1] = [1, 0]
+    flags[2] = [0, 1]
     rd = configure_product(RobotDataBatch(URDF, B, _backend=EmulBackend()), "lqp")
     rd.update_kinematics(np.ascontiguousarray(q), np.ascontiguousarray(qd))
     rd.set_contact(flags)

@@ -163,7 +163,7 @@ def run_tight_torque_limit(make_rd, D, H, B, tl=45.0):
 
 
 def test_emul_tight_torque_limit():
-    run_tight_torque_limit(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, lambda a: a, 6)
+    run_tight_torque_limit(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, lambda a: a, 3)
 
 
 def run_sliced_cycle_host(make_rd, D, B, variants, outputs=1):
@@ -192,16 +192,26 @@ def run_sliced_cycle_host(make_rd, D, B, variants, outputs=1):
     return (q, qd, fs, flags), outs[0]
 
 
+def test_emul_walking_state_of_data_confirmation():
+    """reference tests/sp_test/data_confirmation.cpp:41-84: a captured walking state, four registered contacts (feet active), four
+    hierarchy levels (3 / 3 / 3 / 12), HQP + redistribution, no torque limit."""
+    from tests.common import check_walking_state, walking_inputs
+
+    q, qd, fs, flags = walking_inputs(1)
+    rd, out = run_product("walking", q, qd, fs, flags, SOLVE_GRAV | SOLVE_HQP | SOLVE_REDIST)
+    check_walking_state(rd, out, np.asarray)
+
+
 def test_emul_sliced_cycle_host():
-    run_sliced_cycle_host(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, 4, ((1, False), (3, True)))
-    run_sliced_cycle_host(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, 4, ((1, False), (3, True)), outputs=0)
+    run_sliced_cycle_host(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, 3, ((1, False), (3, True)))
+    run_sliced_cycle_host(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, 3, ((1, False), (2, True)), outputs=0)
 
 
 def test_emul_split_call_order_equals_fused():
     """The reference's split order -- CalcGravCompensation, CalcTaskControlTorque(true), CalcContactRedistribute(true) as three
     calls (tests/dwbc_test.cpp:100-130) -- must give the torques of the fused solve: the redistribution reads
     torque_grav_ + torque_task_ + torque_contact_ left by the earlier calls (reference src/dwbc.cpp:1372-1375)."""
-    B = 3
+    B = 2
     q, qd, rng = synth_states(B, 20242)
     fs = synth_fstar(rng, B)
     fs[0][0, 1] = 4.0

@@ -167,7 +167,7 @@ def test_emul_reduced_hqp_vs_oracle(limited):
     """limited = 2: a uniform 300 limit, which the level QPs leave ACTIVE on a condensed-body coordinate; the redistribution QP then
     sees that row with a zero normal and b ~ -1e-8 -- feasible under the relative zero-row rule."""
     tl = (None, TLIM_R, np.full(18, 300.0))[limited]
-    run_reduced_hqp(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, lambda a: a, tlimR=tl)
+    run_reduced_hqp(lambda B: RobotDataBatch(URDF, B, _backend=EmulBackend()), np.ascontiguousarray, lambda a: a, B=2, tlimR=tl)  # GPU twin: B = 4
 
 
 def run_reduced_hqp_nc(make_rd, D, H, scales=(0.0, 6.5, 7.0, 7.5)):

@@ -145,6 +145,45 @@ def test_config1_closed_form_vs_oracle():
         assert relerr(nul[b], ref.get("Null_task0")) < 1e-9
 
 
+def test_gpu_walking_state_of_data_confirmation():
+    """reference tests/sp_test/data_confirmation.cpp:41-84 (captured walking state, hierarchy 3 / 3 / 3 / 12, four registered contacts)"""
+    from tests.common import check_walking_state, walking_inputs
+
+    q, qd, fs, flags = walking_inputs(1)
+    rd, out = run_product("walking", q, qd, fs, flags, ALL)
+    check_walking_state(rd, out, np.asarray)
+
+
+def test_gpu_perturbed_golden_set():
+    """The reference's repeat test (tests/test.cpp:156-162): the golden configuration perturbed by 0.01 U per coordinate, base
+    rotation reset to identity, through the golden hierarchy (pelvis 6D / upper-body rotation, torque limit 300, HQP +
+    redistribution) -- every state of a 4096-state set against the oracle."""
+    from oracle import oracle as orc
+
+    B = 4096
+    rng = np.random.default_rng(156162)
+    q = np.array([Q_CASE[1]] * B, dtype=np.float64) + 0.01 * rng.uniform(-1, 1, (B, 40))
+    q[:, 3:6] = 0.0
+    q[:, 39] = 1.0
+    qd = np.zeros((B, 39))
+    fs = [np.array([FSTAR_CASE[1][0]] * B), np.array([FSTAR_CASE[1][1]] * B)]
+    flags = np.array([[1, 1, 0, 0]] * B, dtype=np.uint8)
+    rd, (tg, tt, tc, st) = run_product("golden", q, qd, fs, flags, ALL, 4)
+    o = configure_oracle(orc.OracleRobot(URDF), "golden", 4).run_batch(q, qd, fs, flags, sets=True)
+    assert np.array_equal(st & 7, o["status"] & 7) and ((st & 7) == 7).mean() > 0.99
+    good = (st & 7) == 7
+    scale = lambda a: np.maximum(1.0, np.abs(a).max(axis=1))
+    eg = (np.abs(tg - o["torque_grav"]).max(axis=1) / scale(o["torque_grav"]))[good].max()
+    et = (np.abs(tt - o["torque_task"]).max(axis=1) / scale(o["torque_task"]))[good].max()
+    ec = (np.abs(tc - o["torque_contact"]).max(axis=1) / scale(o["torque_contact"]))[good].max()
+    print(f"perturbed golden set: {int(good.sum())} of {B} solved, errors {eg:.1e} {et:.1e} {ec:.1e}")
+    assert eg < 1e-9 and et < 1e-6 and ec < 1e-6, (eg, et, ec)
+    act = active_masks(rd, 2)[:, :2]
+    diff = (act ^ o["active"][:, :2])[good]
+    n_hard = int(((diff & ~o["gray"][:, :2][good]) != 0).any(axis=(1, 2)).sum())
+    assert n_hard <= 2, n_hard
+
+
 def _mixed_flags(B, rng):
     """DS : left-SS : right-SS = 0.5 : 0.25 : 0.25."""
     u = rng.uniform(size=B)

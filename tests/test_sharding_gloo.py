@@ -70,7 +70,7 @@ def test_two_rank_slices_match_single_process(tmp_path):
     from tests.emul.emul_backend import EmulBackend
 
     build()  # compile once, before the ranks race for it
-    total, world = 5, 2  # ragged: 3 + 2 states
+    total, world = 3, 2  # ragged: 2 + 1 states (a state costs seconds in the emulation)
     mp.spawn(_worker, args=(world, _free_port(), total, str(tmp_path)), nprocs=world, join=True)
     got = np.load(tmp_path / "gathered.npy")
 

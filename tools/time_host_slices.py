@@ -9,13 +9,13 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import ALL_STAGES, make_inputs  # noqa: E402
+from bench import ALL_STAGES, make_inputs, parse  # noqa: E402
 from libdwbc_b200 import RobotDataBatch  # noqa: E402
 from tests.common import URDF, configure_product, posture_selector  # noqa: E402
 
 B = 65536
 dev = torch.device("cuda", 0)
-sets = [make_inputs(B, 20242 + j, 0.0) for j in range(2)]
+sets = [make_inputs(B, 20242 + j, parse([])) for j in range(2)]
 pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
 hsets = [(pin(q), pin(qd), pin(np.concatenate([f.reshape(-1) for f in fs])), pin(fl)) for q, qd, fs, fl in sets]
 hout = tuple(torch.empty((B, 33), dtype=torch.float64).pin_memory() for _ in range(3)) + (torch.empty((B,), dtype=torch.int32).pin_memory(),)
