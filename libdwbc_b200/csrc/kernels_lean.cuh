@@ -129,7 +129,8 @@ struct LeanSmem {
     static constexpr int rd = vec, Gs = rd + N + 1, u = Gs + N + 1, fs = u + M + 1, tg = fs + (TS | 1) + 1, tt = tg + M + 1, base = tt + M + 1,
                          PC = base + M + 1, lf = PC + CMAX, com = lf + CMAX, misc = com + 16;
     // misc: [0] pivot slot, [1] validity flag (int), [2..5] relative pivots of the task levels, [6] contact dof (int), [7] scratch flag (int), [8] active contact indices (2 int)
-    static constexpr int total = misc + 16;
+    static constexpr int anc = misc + 16;  // ancestor bit masks of the bodies (uint64 each): read in inner loops, fetched from the model once
+    static constexpr int total = anc + S::NB + 2;
     // task-level blocks inside R1 (W^+ is dead by then)
     __host__ __device__ static constexpr int ldb(int l) { return ld4(LV::dof(l)); }
     __host__ __device__ static constexpr int mo(int l) {  // offset of M_l; each level keeps 2 blocks (matrix + inverse scratch)
@@ -144,12 +145,12 @@ struct LeanSmem {
 
 // 6 x n point Jacobian (rows [linear; angular]) of a point fixed in `body` from the sweep records rb (positions relative to the
 // pelvis origin), written to dst (leading dimension ldd) starting at row row0; one column per thread.
-__device__ __forceinline__ void point_jacobian_rb(const DevModel *__restrict__ md, const double *rb, int n, int body, Vec3 pl, double *dst, int ldd,
+__device__ __forceinline__ void point_jacobian_rb(const uint64_t *anc_s, const double *rb, int n, int body, Vec3 pl, double *dst, int ldd,
                                                   int row0, int rows_first, int rows_count, int tid, int nt) {
     const double *pb = rb + body * RB_STRIDE;
     const Vec3 pw = ld3(pb + RB_P) + mv(pb + RB_R, pl);
     const double *R0 = rb + RB_R;
-    const uint64_t anc = md->anc_mask[body];
+    const uint64_t anc = anc_s[body];
     for (int j = tid; j < n; j += nt) {
         Vec3 lin = v3(0, 0, 0), ang = v3(0, 0, 0);
         if (j < 3) {
@@ -175,11 +176,12 @@ __device__ __forceinline__ void point_jacobian_rb(const DevModel *__restrict__ m
 // joints are formed by the team in parallel; only the two dependent chains -- parent-to-child pose, child-to-parent composite
 // inertia -- run level by level on one warp (`serial_warp`), 27 + 9 FMAs per body.  Same records as rbd_sweeps (RB_R, RB_P, RB_AX,
 // RB_IC).  Synchronises the team.
-__device__ __forceinline__ void rbd_sweeps_lean(const DevModel *__restrict__ md, const double *__restrict__ q, double *rb, int serial_warp) {
+__device__ __forceinline__ void rbd_sweeps_lean(const DevModel *__restrict__ md, const double *__restrict__ q, double *rb, int serial_warp, uint64_t *anc_s) {
     const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = lean::warp_id();
     const int nb = md->nb, n = md->n;
     for (int b = tid; b < nb; b += nt) {
         double *bb = rb + b * RB_STRIDE;
+        anc_s[b] = md->anc_mask[b];
         if (b == 0) {
             const double x = q[3], y = q[4], z = q[5], w = q[n];
             double *R = bb + RB_R;
@@ -202,20 +204,46 @@ __device__ __forceinline__ void rbd_sweeps_lean(const DevModel *__restrict__ md,
             for (int k = 0; k < 9; k++) bb[RB_R + k] = Rj[k];  // joint-local rotation; becomes the world rotation in the chain below
         }
     }
+    // The two dependent chains run on one warp, lane k owning entries k and k + 32 of the level order.  Everything the chains need from
+    // the model (parent, depth, joint offset and axis, children) is fetched into registers BEFORE the chains start, so that their
+    // steps only touch shared memory: with the loads inside the loops every level paid two or three dependent global-memory latencies.
+    int cb_[2] = {-1, -1}, cp_[2] = {0, 0}, cd_[2] = {-1, -1}, cch_[2][4] = {{-1, -1, -1, -1}, {-1, -1, -1, -1}}, cnch_[2] = {0, 0};
+    Vec3 crt_[2] = {v3(0, 0, 0), v3(0, 0, 0)}, cax_[2] = {v3(0, 0, 0), v3(0, 0, 0)};
+    const int max_depth = md->max_depth;
+    if (warp == serial_warp) {
+        DWBC_UNROLL(2)
+        for (int k = 0; k < 2; k++) {
+            const int e = lane + 32 * k;
+            if (e < nb) {
+                const int b = md->order[e];
+                cb_[k] = b;
+                int d = 0;
+                for (int dd = 1; dd <= max_depth; dd++) d = e >= md->level_start[dd] ? dd : d;
+                cd_[k] = d;
+                cp_[k] = b > 0 ? md->parent[b] : 0;
+                crt_[k] = ld3(md->r_T[b]);
+                cax_[k] = ld3(md->axis[b]);
+                const int c0 = md->child_start[b], c1 = md->child_start[b + 1];
+                cnch_[k] = c1 - c0;
+                DWBC_UNROLL(4)
+                for (int j = 0; j < 4; j++) cch_[k][j] = c0 + j < c1 ? md->child_list[c0 + j] : -1;
+            }
+        }
+    }
     tsync();
     if (warp == serial_warp) {
-        for (int d = 1; d <= md->max_depth; d++) {
-            const int e0 = md->level_start[d], e1 = md->level_start[d + 1];
-            for (int e = e0 + lane; e < e1; e += 32) {
-                const int b = md->order[e], l = md->parent[b];
-                const double *pb = rb + l * RB_STRIDE;
-                double *bb = rb + b * RB_STRIDE;
+        for (int d = 1; d <= max_depth; d++) {
+            DWBC_UNROLL(2)
+            for (int k = 0; k < 2; k++) {
+                if (cd_[k] != d) continue;
+                const double *pb = rb + cp_[k] * RB_STRIDE;
+                double *bb = rb + cb_[k] * RB_STRIDE;
                 double Rw[9];
                 mm3(pb + RB_R, bb + RB_R, Rw);
                 DWBC_UNROLL(9)
-                for (int k = 0; k < 9; k++) bb[RB_R + k] = Rw[k];
-                st3(bb + RB_P, ld3(pb + RB_P) + mv(pb + RB_R, ld3(md->r_T[b])));
-                st3(bb + RB_AX, mv(Rw, ld3(md->axis[b])));
+                for (int j = 0; j < 9; j++) bb[RB_R + j] = Rw[j];
+                st3(bb + RB_P, ld3(pb + RB_P) + mv(pb + RB_R, crt_[k]));
+                st3(bb + RB_AX, mv(Rw, cax_[k]));
             }
             __syncwarp();
         }
@@ -242,15 +270,26 @@ __device__ __forceinline__ void rbd_sweeps_lean(const DevModel *__restrict__ md,
     }
     tsync();
     if (warp == serial_warp) {
-        for (int d = md->max_depth - 1; d >= 0; d--) {  // parents gather the composite inertia of their children
-            const int e0 = md->level_start[d], e1 = md->level_start[d + 1];
-            for (int e = e0 + lane; e < e1; e += 32) {
-                const int b = md->order[e];
-                double *bb = rb + b * RB_STRIDE;
-                for (int ci = md->child_start[b]; ci < md->child_start[b + 1]; ci++) {
-                    const double *cb = rb + md->child_list[ci] * RB_STRIDE;
-                    DWBC_UNROLL(10)
-                    for (int k = 0; k < 10; k++) bb[RB_IC + k] += cb[RB_IC + k];
+        for (int d = max_depth - 1; d >= 0; d--) {  // parents gather the composite inertia of their children
+            DWBC_UNROLL(2)
+            for (int k = 0; k < 2; k++) {
+                if (cd_[k] != d || cnch_[k] == 0) continue;
+                double *bb = rb + cb_[k] * RB_STRIDE;
+                if (cnch_[k] <= 4) {
+                    DWBC_UNROLL(4)
+                    for (int j = 0; j < 4; j++) {
+                        if (cch_[k][j] < 0) continue;
+                        const double *cb = rb + cch_[k][j] * RB_STRIDE;
+                        DWBC_UNROLL(10)
+                        for (int i = 0; i < 10; i++) bb[RB_IC + i] += cb[RB_IC + i];
+                    }
+                } else {  // more than four children: read the list from the model
+                    const int b = cb_[k];
+                    for (int ci = md->child_start[b]; ci < md->child_start[b + 1]; ci++) {
+                        const double *cb = rb + md->child_list[ci] * RB_STRIDE;
+                        DWBC_UNROLL(10)
+                        for (int i = 0; i < 10; i++) bb[RB_IC + i] += cb[RB_IC + i];
+                    }
                 }
             }
             __syncwarp();
@@ -275,7 +314,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
     // Jc (C x N): stacked 6D point Jacobians of the active contacts; rotation of their links for the wrench-cone rows
     for (int k = 0; k < C / 6; k++) {
         const ContactCfg &c = cfg->contacts[cix[k]];
-        point_jacobian_rb(md, rb, N, c.link, v3(c.point[0], c.point[1], c.point[2]), Jc, LDC, 6 * k, 0, 6, tid, nt);
+        point_jacobian_rb((const uint64_t *)(sm + L::anc), rb, N, c.link, v3(c.point[0], c.point[1], c.point[2]), Jc, LDC, 6 * k, 0, 6, tid, nt);
         if (tid < 9) Rc[9 * k + tid] = rb[c.link * RB_STRIDE + RB_R + tid];
     }
     tsync();
@@ -416,7 +455,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
                             pl = ld3(md->com[tl.link]);
                         else if (tl.mode == DWBC_TASK_LINK_6D_CUSTOM_FRAME || tl.mode == DWBC_TASK_LINK_POSITION_CUSTOM_FRAME)
                             pl = v3(tl.point[0], tl.point[1], tl.point[2]);
-                        point_jacobian_rb(md, rb, N, tl.link, pl, Js, LDT, row, first, tl.dof, tid, nt);
+                        point_jacobian_rb((const uint64_t *)(sm + L::anc), rb, N, tl.link, pl, Js, LDT, row, first, tl.dof, tid, nt);
                     }
                     row += tl.dof;
                 }
@@ -556,19 +595,24 @@ __device__ __noinline__ bool lean_quick_feasible(const BatchCfg *__restrict__ cf
     double *Jb6 = sm + L::Jb6, *PC = sm + L::PC, *lf = sm + L::lf, *Rc = sm + L::Rc, *misc = sm + L::misc;
     int &flag = *(int *)(misc + 7);
     if (tid == 0) flag = 1;
+    // the limit of this thread's joint and the parameters of this thread's contact are fetched before the product: their global-memory
+    // latency then hides behind it instead of following the barrier
+    static_assert(M <= TEAM, "one torque row pair per thread");
+    const bool has_tl = cfg->tlim_set && tid < M;
+    const double tl = has_tl ? cfg->tlim[tid] : 0.0;
+    ContactCfg cc{};
+    if (tid < c / 6) cc = cfg->contacts[cix[tid]];
     if (c == 12) lean::gemv<12, M, LDC, false, 4>(Jb6, base, [&](int i, double v) { lf[i] = PC[i] - v; });
     else lean::gemv<6, M, LDC, false, 4>(Jb6, base, [&](int i, double v) { lf[i] = PC[i] - v; });  // (one out-of-line copy serves both classes)
     tsync();
     bool okq = true;
-    if (cfg->tlim_set)
-        for (int i = tid; i < M; i += nt) {
-            const double lo = cfg->tlim[i] - base[i], hi = cfg->tlim[i] + base[i];
-            okq = okq && lo > 1e-8 * (1.0 + fabs(lo)) && hi > 1e-8 * (1.0 + fabs(hi));
-        }
-    for (int k = tid; k < c / 6; k += nt) {
-        const ContactCfg &cc = cfg->contacts[cix[k]];
+    if (has_tl) {
+        const double lo = tl - base[tid], hi = tl + base[tid];
+        okq = okq && lo > 1e-8 * (1.0 + fabs(lo)) && hi > 1e-8 * (1.0 + fabs(hi));
+    }
+    if (tid < c / 6) {
         double o[10];
-        contact_rows(cc, Rc + 9 * k, ld3(lf + 6 * k), ld3(lf + 6 * k + 3), o);
+        contact_rows(cc, Rc + 9 * tid, ld3(lf + 6 * tid), ld3(lf + 6 * tid + 3), o);
         for (int a = 0; a < 10; a++) okq = okq && (-o[a] > 1e-8 * (1.0 + fabs(o[a])));
     }
     if (!okq) flag = 0;
@@ -606,7 +650,8 @@ __global__ void __launch_bounds__(TEAM * LEAN_GANG, 1) lean_cycle_kernel(const D
     long long *tm = a.timing ? a.timing + s * 32 : nullptr;
     LEAN_STAMP(tm, 0);
     const int serial_warp = slot % lean::NW;
-    rbd_sweeps_lean(md, a.q + s * (N + 1), rb, serial_warp);
+    uint64_t *anc_s = (uint64_t *)(sm + L::anc);
+    rbd_sweeps_lean(md, a.q + s * (N + 1), rb, serial_warp, anc_s);
     if (warp == serial_warp) {
         if (lane == 0) {
             // COM quantities of the COM pseudo link (reference src/dwbc.cpp:320-346)
@@ -676,7 +721,7 @@ __global__ void __launch_bounds__(TEAM * LEAN_GANG, 1) lean_cycle_kernel(const D
             }
             const int bi = i < 6 ? 0 : i - 5, bj = j < 6 ? 0 : j - 5;
             double val = 0.0;
-            if (bj == 0 || bj == bi || ((md->anc_mask[bi] >> bj) & 1ull))
+            if (bj == 0 || bj == bi || ((anc_s[bi] >> bj) & 1ull))
                 val = dot(ld3(Sc + 6 * j), ld3(Fc + 6 * i)) + dot(ld3(Sc + 6 * j + 3), ld3(Fc + 6 * i + 3));
             P[i + j * LDN] = val;
             P[j + i * LDN] = val;
