@@ -292,13 +292,13 @@ int launch_lean(dwbc_batch *b, int stages, cudaStream_t st) {
         KernelScope ks(b, DWBC_K_LEAN, st);
         a.plist = plist0;
         a.pcount = pcount;
-        DWBC_LAUNCH((lean_cycle_kernel<S, 12>), lean_grid, TEAM * LEAN_GANG, smem, st, b->d_model, b->d_cfg, b->w, a);
+        DWBC_LAUNCH((lean_cycle_kernel<S, 12>), lean_grid, TEAM * LEAN_GANG, smem, st, b->d_model, b->d_cfg, b->cfg, b->w, a);
     }
     {
         KernelScope ks(b, DWBC_K_LEAN, st);
         a.plist = plist0 + b->B;
         a.pcount = pcount + 1;
-        DWBC_LAUNCH((lean_cycle_kernel<S, 6>), lean_grid, TEAM * LEAN_GANG, smem, st, b->d_model, b->d_cfg, b->w, a);
+        DWBC_LAUNCH((lean_cycle_kernel<S, 6>), lean_grid, TEAM * LEAN_GANG, smem, st, b->d_model, b->d_cfg, b->cfg, b->w, a);
     }
     CK(cudaGetLastError());
     if (stages & (DWBC_SOLVE_HQP | DWBC_SOLVE_REDIST)) {

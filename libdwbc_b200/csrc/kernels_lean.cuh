@@ -301,7 +301,7 @@ __device__ __forceinline__ void rbd_sweeps_lean(const DevModel *__restrict__ md,
 // On return: P (R1) holds A^{-1}N_c with W^+ in its [6:,6:] block, T (R3) = J P, and the small items of R4 are filled.
 // Returns false (uniformly) if a factorisation failed.
 template <class S, int C>
-__device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, const Work &w, long long s,
+__device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__ md, const BatchCfg &cfg, const Work &w, long long s,
                                                     double *sm, const int *cix, long long *tm) {
     using L = LeanSmem<S>;
     constexpr int N = S::N, M = S::M, LDN = S::LDN, LDM = S::LDM, LDT = S::LDT, LDC = S::LDC, TS = S::TS, R = C - 6;
@@ -313,7 +313,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
     int &ok = *(int *)(misc + 1);
     // Jc (C x N): stacked 6D point Jacobians of the active contacts; rotation of their links for the wrench-cone rows
     for (int k = 0; k < C / 6; k++) {
-        const ContactCfg &c = cfg->contacts[cix[k]];
+        const ContactCfg &c = cfg.contacts[cix[k]];
         point_jacobian_rb((const uint64_t *)(sm + L::anc), rb, N, c.link, v3(c.point[0], c.point[1], c.point[2]), Jc, LDC, 6 * k, 0, 6, tid, nt);
         if (tid < 9) Rc[9 * k + tid] = rb[c.link * RB_STRIDE + RB_R + tid];
     }
@@ -420,7 +420,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
         const double *A06 = sm + L::A06, *co = sm + L::com;
         lean::static_for<0, LV::NL>([&](auto l_) {
             constexpr int l = decltype(l_)::value, t = LV::dof(l), r0 = LV::r0(l);
-            const TaskCfg &tc = cfg->tasks[l];
+            const TaskCfg &tc = cfg.tasks[l];
             if (tc.custom) {
                 const double *src = w.jcustom[l] + (w.jcustom_per_state[l] ? s * (long long)t * N : 0);
                 for (int e = tid; e < t * N; e += nt) {
@@ -430,7 +430,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
             } else {
                 int row = r0;
                 for (int k = 0; k < tc.link_count; k++) {
-                    const TaskLinkCfg &tl = cfg->tlinks[tc.link_start + k];
+                    const TaskLinkCfg &tl = cfg.tlinks[tc.link_start + k];
                     const int first = (tl.mode == DWBC_TASK_LINK_ROTATION || tl.mode == DWBC_TASK_LINK_ROTATION_CUSTOM_FRAME) ? 3 : 0;
                     if (tl.link == S::NB) {
                         // COM pseudo link: jac_ = SI_body^{-1} CMM_ (reference src/dwbc.cpp:331-356), see build_task_jacobian
@@ -518,6 +518,24 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
 }
 
 // ---- task levels: Y = W^+ Tm^T, M_l = Tm_l Y_l, JL_l = Y_l M_l^{-1}, null-space recursion -> Ntorque (stacked, M x TS, in R2) ----
+template <class LV>
+__host__ __device__ constexpr int lean_count_big() {
+    int c = 0;
+    for (int l = 0; l < LV::NL; l++) c += LV::dof(l) > 8 ? 1 : 0;
+    return c;
+}
+template <class LV>
+__host__ __device__ constexpr int lean_small_index(int l) {  // number of small levels before level l
+    int c = 0;
+    for (int k = 0; k < l; k++) c += LV::dof(k) <= 8 ? 1 : 0;
+    return c;
+}
+template <class LV>
+__host__ __device__ constexpr int lean_first_big() {
+    for (int l = 0; l < LV::NL; l++)
+        if (LV::dof(l) > 8) return l;
+    return -1;
+}
 template <class S>
 __device__ __forceinline__ bool lean_task_levels(double *sm, long long *tm) {
     using L = LeanSmem<S>;
@@ -539,24 +557,31 @@ __device__ __forceinline__ bool lean_task_levels(double *sm, long long *tm) {
     });
     tsync();
     LEAN_STAMP(tm, 15);
-    // inverses: levels with t <= 8 by one warp each, concurrently; larger ones by the team
-    lean::static_for<0, LV::NL>([&](auto l_) {
-        constexpr int l = decltype(l_)::value, t = LV::dof(l), ldb = L::ldb(l);
-        if constexpr (t <= 8) {
-            if (warp == (l + 1) % lean::NW) {
-                const double c = lean::warp_spd_inverse_small<t, ldb>(P + L::mo(l), P + L::mo(l) + ldb * t);
-                if (lane == 0) cnd[l] = c;
+    // inverses: levels with t <= 8 by one warp each; a larger one by the team, and while its first Cholesky panel occupies one warp the
+    // small levels are inverted by the other warps (they used to run before it, with the team waiting at a barrier)
+    constexpr int NBIG = lean_count_big<LV>(), LBIG = lean_first_big<LV>();
+    auto small_levels = [&](int busy_warp) {
+        lean::static_for<0, LV::NL>([&](auto l_) {
+            constexpr int l = decltype(l_)::value, t = LV::dof(l), ldb = L::ldb(l);
+            if constexpr (t <= 8) {
+                constexpr int idx = lean_small_index<LV>(l);  // k-th small level -> k-th warp that is not the panel warp
+                const int wl = (idx + ((busy_warp >= 0 && idx >= busy_warp) ? 1 : 0)) % lean::NW;
+                if (warp == wl) {
+                    const double c = lean::warp_spd_inverse_small<t, ldb>(P + L::mo(l), P + L::mo(l) + ldb * t);
+                    if (lane == 0) cnd[l] = c;
+                }
             }
-        }
-    });
+        });
+    };
+    if constexpr (NBIG == 0) small_levels(-1);
     lean::static_for<0, LV::NL>([&](auto l_) {
         constexpr int l = decltype(l_)::value, t = LV::dof(l), ldb = L::ldb(l);
         if constexpr (t > 8) {
             double *Ml = P + L::mo(l);
-            tsync();
             double dmax = 0.0;
             for (int i = 0; i < t; i++) dmax = fmax(dmax, Ml[i + i * ldb]);
-            lean::spd_inverse<t, ldb, ldb>(Ml, Ml + ldb * t, rd, misc, l);
+            if constexpr (l == LBIG) lean::spd_inverse<t, ldb, ldb>(Ml, Ml + ldb * t, rd, misc, l, small_levels);
+            else lean::spd_inverse<t, ldb, ldb>(Ml, Ml + ldb * t, rd, misc, l);
             if (tid == 0) cnd[l] = dmax > 0.0 ? misc[0] / dmax : 0.0;
         }
     });
@@ -623,13 +648,15 @@ __device__ __noinline__ bool lean_quick_feasible(const BatchCfg *__restrict__ cf
 }
 
 template <class S, int CSEL>
-__global__ void __launch_bounds__(TEAM * LEAN_GANG, 1) lean_cycle_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, LeanArgs a) {
+__global__ void __launch_bounds__(TEAM * LEAN_GANG, 1) lean_cycle_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, const BatchCfg cv, Work w, LeanArgs a) {
     static_assert(CSEL == 12 || CSEL == 6, "contact dof of the class");
     // LEAN_GANG teams per CTA, one state each, on private slices of the shared-memory arena.  tsync() is the CTA-wide barrier, so
     // the teams of an SM walk through the phases of the cycle together and fetch each stretch of this (large, mostly straight-line)
     // kernel once per LEAN_GANG states: the instruction cache holds 32 KB, and independent one-state CTAs drifting apart had it
     // thrashing (profiles/r02_*: icc hit rate 66 %).  A team whose slot lies beyond the list leaves at once; exited warps are not
     // waited for by the barrier.
+    // cv: the configuration BY VALUE (kernel-parameter constant bank): the contact / task-link descriptions steer the Jacobian phases
+    // with uniform reads, and from global memory (cfg) every one of them was a dependent L2 latency.  cfg stays for the per-thread reads.
     const int slot = (int)blockIdx.x * LEAN_GANG + (int)(threadIdx.x / TEAM);
     if (slot >= *a.pcount) return;
     using L = LeanSmem<S>;
@@ -669,8 +696,8 @@ __global__ void __launch_bounds__(TEAM * LEAN_GANG, 1) lean_cycle_kernel(const D
             com[15] = Mtot;
             // active contacts of this state
             int k = 0, over = 0;
-            for (int i = 0; i < cfg->ncontact; i++) {
-                if (!a.flags[s * cfg->ncontact + i]) continue;
+            for (int i = 0; i < cv.ncontact; i++) {
+                if (!a.flags[s * cv.ncontact + i]) continue;
                 if (k >= MAX_ACTIVE_CONTACTS) {
                     over = 1;
                     break;
@@ -737,7 +764,7 @@ __global__ void __launch_bounds__(TEAM * LEAN_GANG, 1) lean_cycle_kernel(const D
     bool good = misc[0] > 0.0 && c == CSEL;
     // ---- a2-a5 ----
     if (good) {
-        good = lean_contact_task_T<S, CSEL>(md, cfg, w, s, sm, cix, tm);
+        good = lean_contact_task_T<S, CSEL>(md, cv, w, s, sm, cix, tm);
         good = good && ok != 0;
     }
     if (!good) {  // uniform: no contact / too many contacts / a factorisation failed -> status 0, zero torques
@@ -824,7 +851,7 @@ __global__ void __launch_bounds__(TEAM * LEAN_GANG, 1) lean_cycle_kernel(const D
         }
         if (tid < CMAX) gP[tid] = tid < c ? PC[tid] : 0.0;
         for (int k = 0; k < c / 6; k++) {
-            const int link = cfg->contacts[cix[k]].link;
+            const int link = cv.contacts[cix[k]].link;
             if (tid < 9) w.pose[(s * NB + link) * POSE_STRIDE + tid] = Rc[9 * k + tid];
         }
         if (tid < MAX_ACTIVE_CONTACTS) w.cidx[s * MAX_ACTIVE_CONTACTS + tid] = tid < c / 6 ? cix[tid] : -1;

@@ -258,8 +258,13 @@ __device__ __forceinline__ void chol_trailing(double *A) {
 // In-place lower Cholesky of the SPD matrix in A (N x N, LD; the full symmetric matrix must be finite).  On return the lower
 // triangle holds L with exact zeros above the diagonal inside the 8x8 diagonal blocks, rdiag[i] = 1/L(i,i), *pivslot = smallest
 // pivot (<= 0: not SPD; the factorisation continues with a clamped pivot).  Synchronises on entry and exit.
-template <int N, int LD>
-__device__ __forceinline__ void chol_blocked(double *A, double *rdiag, double *pivslot, int wrot = 0) {
+// `side`: work of the OTHER warps while the first panel is factored by its one warp (it must not touch A, rdiag or *pivslot, is called
+// by every warp with the index of the panel warp, and is complete at the barrier that follows the panel).
+struct NoSideWork {
+    __device__ __forceinline__ void operator()(int) const {}
+};
+template <int N, int LD, class Side = NoSideWork>
+__device__ __forceinline__ void chol_blocked(double *A, double *rdiag, double *pivslot, int wrot = 0, Side side = Side()) {
     constexpr int NB = (N + 7) / 8;
     tsync();
     if (t_id() == 0) *pivslot = 1e300;
@@ -267,6 +272,7 @@ __device__ __forceinline__ void chol_blocked(double *A, double *rdiag, double *p
         constexpr int KB = decltype(kb_)::value;
         if constexpr (KB > 0) tsync();
         if (warp_id() == (KB + wrot) % NW) chol_panel<N, LD, KB>(A, rdiag, pivslot);
+        if constexpr (KB == 0) side(wrot % NW);
         if constexpr (KB < NB - 1) {
             tsync();
             chol_trailing<N, LD, KB>(A);
@@ -379,9 +385,9 @@ __device__ __forceinline__ void syrk_inverse(const double *X, Epi epi, int wrot 
 
 // SPD inverse in place: on return A holds the full symmetric inverse; X (N x N, LDX) is scratch, rdiag N doubles, *pivslot the
 // smallest Cholesky pivot.  Synchronises on entry and exit.
-template <int N, int LD, int LDX>
-__device__ __forceinline__ void spd_inverse(double *A, double *X, double *rdiag, double *pivslot, int wrot = 0) {
-    chol_blocked<N, LD>(A, rdiag, pivslot, wrot);
+template <int N, int LD, int LDX, class Side = NoSideWork>
+__device__ __forceinline__ void spd_inverse(double *A, double *X, double *rdiag, double *pivslot, int wrot = 0, Side side = Side()) {
+    chol_blocked<N, LD, Side>(A, rdiag, pivslot, wrot, side);
     trinv_blocked<N, LD, LDX>(A, rdiag, X, wrot);
     tsync();
     syrk_inverse<N, LDX>(X, [&](int i, int j, double v) {
