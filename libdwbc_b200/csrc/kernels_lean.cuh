@@ -325,7 +325,23 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
     LEAN_STAMP(tm, 5);
     // Jc X (C x C, SPD) -> Lambda_c
     lean::mma_gemm<C, C, N, LDC, LDN, false, false, 1>(Jc, X, [&](int i, int j, double v) { Lam[i + j * LDC] = v; });
-    lean::spd_inverse<C, LDC, LDC>(Lam, Lw, rd, misc, 1);
+    // While one warp factors the first panel of Jc X, another prepares the null-space basis of W (below): T = B_1^{-T} [B_2^T ...],
+    // B_i = Jc[6i:6i+6, 0:6], by Gauss-Jordan on [B_1^T | B_2^T ...].  It only needs Jc and its own scratch.
+    constexpr int lda = 13;
+    auto null_basis_prep = [&](int busy_warp) {
+        if constexpr (R > 0) {
+            if (warp == (busy_warp + 1) % lean::NW) {
+                for (int e = lane; e < 6 * (6 + R); e += 32) {
+                    const int col = e / 6, row = e - col * 6;
+                    Aug[row + col * lda] = Jc[col + row * LDC];
+                }
+                __syncwarp();
+                const double cond1 = wgauss_jordan(6, R, Aug, lda);
+                if (!(cond1 > 1e-14) && lane == 0) ok = 0;
+            }
+        }
+    };
+    lean::spd_inverse<C, LDC, LDC>(Lam, Lw, rd, misc, 1, null_basis_prep);
     if (!(misc[0] > 0.0)) return false;
     LEAN_STAMP(tm, 6);
     // Jbar^T = Lambda_c X^T  (C x N)
@@ -344,18 +360,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
     lean::gemv<C, N, LDC, false, 4>(Jbar, Gs, [&](int i, double v) { PC[i] = v; });
     LEAN_STAMP(tm, 7);
     if constexpr (R > 0) {
-        // ---- orthonormal basis V (M x R) of null(W): {S Jc^T f : (Jc^T f)[0:6] = 0} ----
-        constexpr int lda = 13;
-        if (warp == 2) {  // T = B_1^{-T} [B_2^T ...], B_i = Jc[6i:6i+6, 0:6]: Gauss-Jordan on [B_1^T | B_2^T ...]
-            for (int e = lane; e < 6 * (6 + R); e += 32) {
-                const int col = e / 6, row = e - col * 6;
-                Aug[row + col * lda] = Jc[col + row * LDC];
-            }
-            __syncwarp();
-            const double cond1 = wgauss_jordan(6, R, Aug, lda);
-            if (!(cond1 > 1e-14) && lane == 0) ok = 0;
-        }
-        tsync();
+        // ---- basis V (M x R) of null(W): {S Jc^T f : (Jc^T f)[0:6] = 0}, from the T prepared during the inverse of Jc X above ----
         for (int e = tid; e < M * R; e += nt) {  // V_raw(a, b) = Jc[6+b][6+a] - sum_e Jc[e][6+a] T(e, b)
             const int b = e / M, a = e - b * M;
             double v = Jc[(6 + b) + (6 + a) * LDC];
@@ -363,57 +368,65 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
             for (int k = 0; k < 6; k++) v = fma(-Jc[k + (6 + a) * LDC], Aug[k + (6 + b) * lda], v);
             V[a + b * LDM] = v;
         }
-        tsync();
+    }
+    tsync();
+    // Two independent strands from here to the next barrier.  Warp 3 alone (warp-level synchronisation only) turns V_raw into the
+    // scaled basis V, G = V^T V, G^{-1} and V G^{-2}; the other three warps form u and the task Jacobians of all levels.  The strand of
+    // warp 3 is a chain of seven short dependent steps that used to keep the whole team at seven barriers.
+    const bool vwarp = R > 0 && warp == 3;
+    const int jtid = tid, jnt = R > 0 ? nt - 32 : nt;  // thread index / count of the Jacobian strand
+    if constexpr (R > 0) {
+        if (vwarp) {
         // V does not have to be orthonormal: for ANY basis V of null(W), with G = V^T V,
         //     (W + V V^T)^{-1} = W^+ + V G^{-2} V^T          (W symmetric, range(W) orthogonal to span V)
         // and NwJw = V (Jbar^T[0:r, 6:] V)^{-1} does not depend on the basis.  Only the columns are normalised (conditioning of
         // W + V V^T); G^{-1} is a 6 x 6 SPD inverse on one warp.  VG = V G^{-2} is kept for the correction after the big inverse.
         // (The orthonormal V2 of the reference is a public field of DWBC_OUT_ALL only.)
         double *Gm = Aug, *G2 = Aug + 6 * lda;  // two 6 x 6 blocks inside the 13 x 13 scratch
-        if (tid < R) {
+        if (lane < R) {
             double d = 0.0;
-            for (int a = 0; a < M; a++) d = fma(V[a + tid * LDM], V[a + tid * LDM], d);
-            Gm[12 * lda + tid] = rsqrt(d);  // column scales (row 12 of the scratch is free)
+            for (int a = 0; a < M; a++) d = fma(V[a + lane * LDM], V[a + lane * LDM], d);
+            Gm[12 * lda + lane] = rsqrt(d);  // column scales (row 12 of the scratch is free)
         }
-        tsync();
-        for (int e = tid; e < M * R; e += nt) V[(e % M) + (e / M) * LDM] *= Gm[12 * lda + e / M];
-        tsync();
-        for (int e = tid; e < R * R; e += nt) {
+        __syncwarp();
+        for (int e = lane; e < M * R; e += 32) V[(e % M) + (e / M) * LDM] *= Gm[12 * lda + e / M];
+        __syncwarp();
+        for (int e = lane; e < R * R; e += 32) {
             const int j = e / R, i = e - j * R;
             double d = 0.0;
             for (int a = 0; a < M; a++) d = fma(V[a + i * LDM], V[a + j * LDM], d);
             Gm[i + j * lda] = d;
         }
-        tsync();
-        if (warp == 3) {
+        __syncwarp();
+        {
             const double cg = lean::warp_spd_inverse_small<R, lda>(Gm, G2);
             if (!(cg > 1e-13) && lane == 0) ok = 0;
         }
-        tsync();
-        for (int e = tid; e < R * R; e += nt) {  // G2 = G^{-1} G^{-1}
+        __syncwarp();
+        for (int e = lane; e < R * R; e += 32) {  // G2 = G^{-1} G^{-1}
             const int j = e / R, i = e - j * R;
             double d = 0.0;
             DWBC_UNROLL(R)
             for (int k = 0; k < R; k++) d = fma(Gm[i + k * lda], Gm[k + j * lda], d);
             G2[i + j * lda] = d;
         }
-        tsync();
+        __syncwarp();
         double *VG = sm + L::NwJw;  // V G^{-2} (M x R); NwJw itself is formed last, in the same place
-        for (int e = tid; e < M * R; e += nt) {
+        for (int e = lane; e < M * R; e += 32) {
             const int j = e / M, i = e - j * M;
             double d = 0.0;
             DWBC_UNROLL(R)
             for (int k = 0; k < R; k++) d = fma(V[i + k * LDM], G2[k + j * lda], d);
             VG[i + j * LDM] = d;
         }
-        tsync();
-    } else {
-        tsync();
+        __syncwarp();
+        }
     }
     LEAN_STAMP(tm, 8);
-    // u = (A^{-1}N_c)[6:, :] G   (tgv is scratch here)
-    lean::gemv<M, N, LDN, false, 2>(P + 6, Gs, [&](int i, double v) { u[i] = v; });
-    // ---- J_task of all levels (stacked, R2: Jc / X / Lambda_c are dead) and T = J P (R3: the sweep records are dead after this) ----
+    if (!vwarp) {
+    // u = (A^{-1}N_c)[6:, :] G
+    lean::gemv<M, N, LDN, false, 2>(P + 6, Gs, [&](int i, double v) { u[i] = v; }, jtid, jnt);
+    // ---- J_task of all levels (stacked, R2: Jc / X / Lambda_c are dead) ----
     if constexpr (TS > 0) {
         double *Js = R2;
         using LV = typename S::Lv;
@@ -423,7 +436,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
             const TaskCfg &tc = cfg.tasks[l];
             if (tc.custom) {
                 const double *src = w.jcustom[l] + (w.jcustom_per_state[l] ? s * (long long)t * N : 0);
-                for (int e = tid; e < t * N; e += nt) {
+                for (int e = jtid; e < t * N; e += jnt) {
                     const int j = e / t, i = e - j * t;
                     Js[r0 + i + j * LDT] = src[e];
                 }
@@ -441,7 +454,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
                         const double det = I[0] * c00 + I[1] * c01 + I[2] * c02, rdet = 1.0 / det;
                         const double c11 = I[0] * I[8] - I[2] * I[6], c12 = I[1] * I[6] - I[0] * I[7], c22 = I[0] * I[4] - I[1] * I[3];
                         const double inv[9] = {c00 * rdet, c01 * rdet, c02 * rdet, c01 * rdet, c11 * rdet, c12 * rdet, c02 * rdet, c12 * rdet, c22 * rdet};
-                        for (int j = tid; j < N; j += nt) {
+                        for (int j = jtid; j < N; j += jnt) {
                             const Vec3 al = v3(A06[0 + 6 * j], A06[1 + 6 * j], A06[2 + 6 * j]), aa = v3(A06[3 + 6 * j], A06[4 + 6 * j], A06[5 + 6 * j]);
                             const Vec3 lin = (1.0 / Mt) * al;
                             const Vec3 h = cross(al, c) + mv(rb + RB_R, aa);
@@ -455,12 +468,17 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
                             pl = ld3(md->com[tl.link]);
                         else if (tl.mode == DWBC_TASK_LINK_6D_CUSTOM_FRAME || tl.mode == DWBC_TASK_LINK_POSITION_CUSTOM_FRAME)
                             pl = v3(tl.point[0], tl.point[1], tl.point[2]);
-                        point_jacobian_rb((const uint64_t *)(sm + L::anc), rb, N, tl.link, pl, Js, LDT, row, first, tl.dof, tid, nt);
+                        point_jacobian_rb((const uint64_t *)(sm + L::anc), rb, N, tl.link, pl, Js, LDT, row, first, tl.dof, jtid, jnt);
                     }
                     row += tl.dof;
                 }
             }
         });
+    }
+    }
+    // ---- T = J P (R3: the sweep records are dead after this) ----
+    if constexpr (TS > 0) {
+        double *Js = R2;
         tsync();
         LEAN_STAMP(tm, 9);
         lean::mma_gemm<TS, N, N, LDT, LDN, false, false, (N + 7) / 8>(Js, P, [&](int i, int j, double v) { T[i + j * LDT] = v; });
