@@ -494,7 +494,25 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
         });
     }
     LEAN_STAMP(tm, 11);
-    lean::spd_inverse<M, LDN, LDM>(Wb, R2, rd, misc, 2);
+    // While one warp factors the first panel, another prepares NwJw = V Mx^{-1}: Mx = Jbar^T[0:R, 6:] V (R x R) with the identity beside it,
+    // inverted by Gauss-Jordan in the 13 x 13 scratch (free again: G and G^{-2} went into V G^{-2}).  Independent of the inverse.
+    auto mx_prep = [&](int busy_warp) {
+        if constexpr (R > 0) {
+            if (warp == (busy_warp + 1) % lean::NW) {
+                for (int e = lane; e < R * R; e += 32) {
+                    const int j = e / R, i = e - j * R;
+                    double d = 0.0;
+                    for (int a = 0; a < M; a++) d = fma(Jb6[i + a * LDC], V[a + j * LDM], d);
+                    Aug[i + j * lda] = d;
+                    Aug[i + (R + j) * lda] = (i == j) ? 1.0 : 0.0;
+                }
+                __syncwarp();
+                const double cond2 = wgauss_jordan(R, R, Aug, lda);
+                if (!(cond2 > 1e-14) && lane == 0) ok = 0;
+            }
+        }
+    };
+    lean::spd_inverse<M, LDN, LDM>(Wb, R2, rd, misc, 2, mx_prep);
     if (!(misc[0] > 0.0)) return false;
     LEAN_STAMP(tm, 12);
     if constexpr (R > 0) {
@@ -502,23 +520,8 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
             Wb[i + j * LDN] -= v;
             if (i != j) Wb[j + i * LDN] -= v;
         });
-        // Mx = Jbar^T[0:R, 6:] V (R x R) and the identity beside it; NwJw = V Mx^{-1}
-        constexpr int lda = 13;
-        for (int e = tid; e < R * R; e += nt) {
-            const int j = e / R, i = e - j * R;
-            double d = 0.0;
-            for (int a = 0; a < M; a++) d = fma(Jb6[i + a * LDC], V[a + j * LDM], d);
-            Aug[i + j * lda] = d;
-            Aug[i + (R + j) * lda] = (i == j) ? 1.0 : 0.0;
-        }
         tsync();
-        if (warp == 1) {
-            const double cond2 = wgauss_jordan(R, R, Aug, lda);
-            if (!(cond2 > 1e-14) && lane == 0) ok = 0;
-        }
-        // tau_grav = W^+ u does not wait for Mx^{-1}
-        if (warp != 1) lean::gemv<M, M, LDN, false, 2>(Wb, u, [&](int i, double v) { tgv[i] = v; }, tid < 32 ? tid : tid - 32, nt - 32);
-        tsync();
+        lean::gemv<M, M, LDN, false, 2>(Wb, u, [&](int i, double v) { tgv[i] = v; });  // tau_grav = W^+ u
         for (int e = tid; e < M * R; e += nt) {
             const int j = e / M, i = e - j * M;
             double d = 0.0;
