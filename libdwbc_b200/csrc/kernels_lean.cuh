@@ -671,6 +671,7 @@ __device__ __noinline__ bool lean_quick_feasible(const BatchCfg *__restrict__ cf
 template <class S, int CSEL>
 __global__ void __launch_bounds__(TEAM * LEAN_GANG, 1) lean_cycle_kernel(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, const BatchCfg cv, Work w, LeanArgs a) {
     static_assert(CSEL == 12 || CSEL == 6, "contact dof of the class");
+    static_assert(lean::NW == 4, "the warp roles of the strands and of the side work assume a team of four warps");
     // LEAN_GANG teams per CTA, one state each, on private slices of the shared-memory arena.  tsync() is the CTA-wide barrier, so
     // the teams of an SM walk through the phases of the cycle together and fetch each stretch of this (large, mostly straight-line)
     // kernel once per LEAN_GANG states: the instruction cache holds 32 KB, and independent one-state CTAs drifting apart had it
