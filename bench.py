@@ -625,7 +625,8 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, world),
-            "details": {"solved_fraction": ok_frac, "path": path if P.main_path else "variant kernels (reduced_kernels / lqp_kernel)"},
+            "details": {"solved_fraction": ok_frac, "path": path if P.main_path else "variant kernels (reduced_kernels / lqp_kernel)",
+                        "workspace_bytes_per_state": rd.workspace_bytes() / B},
             "latency_ms": {"p50": p50, "p99": p99, "note": "one batched cycle of states_per_gpu states per GPU, device-resident inputs, max over ranks"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * h2d_in, "d2h_bytes_per_step": B * d2h_out, "steps": e2e_steps,
                     "ms_per_step": e2e_ms / e2e_steps, "latency_ms": {"p50": float(np.percentile(e2e_lat, 50)), "max": float(np.max(e2e_lat))},

@@ -344,6 +344,9 @@ enum { DWBC_OUT_AUTO = -1, DWBC_OUT_TORQUES = 0, DWBC_OUT_ALL = 1 };
 int dwbc_batch_set_outputs(dwbc_batch_t *b, int outputs);
 /* 1 if the last dwbc_batch_solve / dwbc_batch_cycle_host ran the one-kernel cycle, 0 if it ran the generic kernels */
 int dwbc_batch_last_path(const dwbc_batch_t *b);
+/* device memory (bytes) the handle has allocated so far: inputs staging, outputs and the per-state workspace of the output group in use
+ * (allocation is lazy: the public-field workspace of DWBC_OUT_ALL only exists once that group has been used) */
+long long dwbc_batch_workspace_bytes(const dwbc_batch_t *b);
 /* Diagnostics of the one-kernel cycle: stamps_dev [B x 32] int64 (device) receives the SM clock (clock64) at the end of every phase of
  * every state (phase list next to LEAN_STAMP in csrc/kernels_lean.cuh); NULL switches it off.  tools/lean_phases.py prints the table. */
 int dwbc_batch_set_lean_timing(dwbc_batch_t *b, long long *stamps_dev);

@@ -80,6 +80,8 @@ def declare(L):
     L.dwbc_batch_get_torque_command_f32.argtypes = [vp, vp, vp]
     L.dwbc_batch_set_outputs.argtypes = [vp, C.c_int]
     L.dwbc_batch_last_path.argtypes = [vp]
+    L.dwbc_batch_workspace_bytes.argtypes = [vp]
+    L.dwbc_batch_workspace_bytes.restype = C.c_longlong
     L.dwbc_batch_set_lean_timing.argtypes = [vp, vp]
     return L
 
@@ -95,7 +97,7 @@ EXPORTS = [
     "dwbc_batch_get_reduced_matrix", "dwbc_batch_calc_control_torque_lqp", "dwbc_batch_calc_control_torque_lqp_r", "dwbc_batch_calc_control_torque_lqp_r_nc", "dwbc_batch_get_lqp", "dwbc_batch_get_lqp_iterations",
     "dwbc_batch_set_task_gain", "dwbc_batch_set_trajectory_quintic", "dwbc_batch_set_trajectory_rotation", "dwbc_batch_calc_fstar",
     "dwbc_batch_update_kinematics_mujoco", "dwbc_batch_get_torque_command_f32", "dwbc_batch_set_host_slices",
-    "dwbc_batch_set_outputs", "dwbc_batch_last_path", "dwbc_batch_set_lean_timing", "dwbc_batch_cycle_host_levels",
+    "dwbc_batch_set_outputs", "dwbc_batch_last_path", "dwbc_batch_workspace_bytes", "dwbc_batch_set_lean_timing", "dwbc_batch_cycle_host_levels",
     "dwbc_multi_create", "dwbc_multi_destroy", "dwbc_multi_gpus", "dwbc_multi_shard", "dwbc_multi_add_contact", "dwbc_multi_add_task",
     "dwbc_multi_add_custom_task", "dwbc_multi_set_torque_limit", "dwbc_multi_set_outputs", "dwbc_multi_cycle_host", "dwbc_multi_last_shard_ms",
     "dwbc_host_alloc", "dwbc_host_free", "dwbc_device_alloc", "dwbc_device_free", "dwbc_memcpy_h2d", "dwbc_memcpy_d2h", "dwbc_device_count",

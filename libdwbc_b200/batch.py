@@ -416,6 +416,10 @@ class RobotDataBatch:
         """1 if the last solve / cycle_host ran the one-kernel cycle (lean_cycle_kernel), 0 for the generic kernels"""
         return self.L.dwbc_batch_last_path(self._h)
 
+    def workspace_bytes(self):
+        """device memory the handle has allocated so far (lazy: grows when DWBC_OUT_ALL is first used)"""
+        return int(self.L.dwbc_batch_workspace_bytes(self._h))
+
     # ---- per-kernel device timing (CUDA events recorded by the library around each of its launches) ----
     def set_profiling(self, enable=True):
         self._ck(self.L.dwbc_batch_set_profiling(self._h, 1 if enable else 0))

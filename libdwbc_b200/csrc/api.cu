@@ -40,6 +40,7 @@ struct dwbc_batch {
     DevModel *d_model = nullptr;
     BatchCfg *d_cfg = nullptr;
     bool cfg_dirty = true;
+    size_t alloc_bytes = 0;  // device memory this handle has allocated so far (dwbc_batch_workspace_bytes)
     Work w;
     std::vector<void *> allocs;
     std::vector<void *> task_allocs;
@@ -134,6 +135,7 @@ bool dev_alloc(dwbc_batch *b, T **p, size_t count, std::vector<void *> *list = n
     void *raw = nullptr;
     if (!cuda_ok(cudaMalloc(&raw, count * sizeof(T) + 16), "cudaMalloc")) return false;
     cudaMemset(raw, 0, count * sizeof(T) + 16);
+    b->alloc_bytes += count * sizeof(T) + 16;
     (list ? *list : b->allocs).push_back(raw);
     *p = (T *)raw;
     return true;
@@ -890,6 +892,7 @@ int dwbc_batch_set_outputs(dwbc_batch_t *b, int outputs) {
     return DWBC_OK;
 }
 int dwbc_batch_last_path(const dwbc_batch_t *b) { return b ? b->last_path : -1; }
+long long dwbc_batch_workspace_bytes(const dwbc_batch_t *b) { return b ? (long long)b->alloc_bytes : -1; }
 int dwbc_batch_set_lean_timing(dwbc_batch_t *b, long long *stamps_dev) {
     if (!b) return fail(DWBC_ERR_ARG, "set_lean_timing: null handle");
     b->lean_timing = stamps_dev;
