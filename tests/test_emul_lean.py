@@ -89,6 +89,8 @@ def test_lean_config1_and_config0():
     rdg, (tg0, tt0, tc0, st0) = run(1, q, qd, fs, flags, SOLVE_GRAV | SOLVE_TASK, OUT_ALL)
     assert rdl.last_path() == 1 and np.array_equal(st & 7, st0 & 7)
     assert relerr(tg, tg0) < 1e-10 and relerr(tt, tt0) < 1e-9 and not tc.any()
+    # the torque path never allocates the public-field workspace (dwbc_batch_workspace_bytes: lazy allocation)
+    assert 0 < rdl.workspace_bytes() < 40 * 1024 * B and rdg.workspace_bytes() > 2 * rdl.workspace_bytes()
     rdl, (tg, tt, tc, st) = run(1, q, qd, fs, flags, SOLVE_GRAV, OUT_TORQUES)
     assert rdl.last_path() == 1 and np.array_equal(st & 7, np.ones(B, dtype=np.int32))
     assert relerr(tg, tg0) < 1e-10 and not tt.any()
