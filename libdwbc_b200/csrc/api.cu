@@ -310,11 +310,16 @@ int launch_lean(dwbc_batch *b, int stages, cudaStream_t st) {
             for (int l = 0; l < b->cfg.nlevels; l++) nvmax = b->cfg.tasks[l].dof + RMAX > nvmax ? b->cfg.tasks[l].dof + RMAX : nvmax;
         HqpSmem H(b->w.n, b->w.m, nvmax);
         const size_t hs = sizeof(double) * H.total;
-        CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+        CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
         KernelScope ks(b, DWBC_K_HQP, st);
         Work wq = b->w;
         wq.hqp_timing = a.timing;
-        DWBC_LAUNCH(hqp_kernel, b->B, TEAM, hs, st, b->d_model, b->d_cfg, wq, a.hqp, a.redist, nvmax, (const int *)a.list, (const int *)a.count);
+        if (b->w.n == 39 && b->w.m == 33 && nvmax == 27 && b->cfg.tlim_set) {  // the headline model and hierarchy: dimensions as compile-time constants
+            CK(cudaFuncSetAttribute(hqp_kernel_t<39, 33, 27, 66>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+            DWBC_LAUNCH((hqp_kernel_t<39, 33, 27, 66>), b->B, TEAM, hs, st, b->d_model, b->d_cfg, wq, a.hqp, a.redist, nvmax, (const int *)a.list, (const int *)a.count);
+        } else {
+            DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1>), b->B, TEAM, hs, st, b->d_model, b->d_cfg, wq, a.hqp, a.redist, nvmax, (const int *)a.list, (const int *)a.count);
+        }
     }
     CK(cudaGetLastError());
     return DWBC_OK;
@@ -732,9 +737,9 @@ int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *
             for (int l = 0; l < b->cfg.nlevels; l++) nvmax = b->cfg.tasks[l].dof + RMAX > nvmax ? b->cfg.tasks[l].dof + RMAX : nvmax;
         HqpSmem L(b->w.n, b->w.m, nvmax);
         size_t smem = sizeof(double) * L.total;
-        CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelScope ks(b, DWBC_K_HQP, st);
-        DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0,
+        DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1>), b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0,
                     (stages & DWBC_SOLVE_REDIST) ? 1 : 0, nvmax, (const int *)nullptr, (const int *)nullptr);
     }
     if ((stages & DWBC_SOLVE_REDIST_ANALYTIC) && !(stages & DWBC_SOLVE_REDIST)) {
@@ -1374,12 +1379,12 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
             for (int l = 0; l < k; l++) nvmax = c.tasks[l].dof + RMAX > nvmax ? c.tasks[l].dof + RMAX : nvmax;
             HqpSmem L(rn, rm, nvmax);
             size_t smem = sizeof(double) * L.total;
-            CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             // with non-contact levels the redistribution needs torque_task_R_ after their sums: it runs after reduced_nc_kernel
             const int redist_now = ((stages & DWBC_SOLVE_REDIST) && k == c.nlevels) ? 2 : 0;
             if ((stages & DWBC_SOLVE_HQP) || redist_now) {
                 KernelScope ks(b, DWBC_K_HQP, st);
-                DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, b->wr, (stages & DWBC_SOLVE_HQP) ? 1 : 0, redist_now, nvmax, (const int *)nullptr, (const int *)nullptr);
+                DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1>), b->B, TEAM, smem, st, b->d_model, b->d_cfgR, b->wr, (stages & DWBC_SOLVE_HQP) ? 1 : 0, redist_now, nvmax, (const int *)nullptr, (const int *)nullptr);
             }
         }
     }
@@ -1413,10 +1418,10 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
         const int nvmax = 6 + RMAX;
         HqpSmem L(rn, rm, nvmax);
         size_t smem = sizeof(double) * L.total;
-        CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
             KernelScope ks(b, DWBC_K_HQP, st);
-            DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgNC, q, 1, 0, nvmax, (const int *)nullptr, (const int *)nullptr);
+            DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1>), b->B, TEAM, smem, st, b->d_model, b->d_cfgNC, q, 1, 0, nvmax, (const int *)nullptr, (const int *)nullptr);
         }
         {
             KernelScope ks(b, DWBC_K_REDUCED, st);
@@ -1447,10 +1452,10 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
         const int nvmax = RMAX > 0 ? RMAX : 1;
         HqpSmem L(rn, rm, nvmax);
         size_t smem = sizeof(double) * L.total;
-        CK(cudaFuncSetAttribute(hqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
             KernelScope ks(b, DWBC_K_HQP, st);
-            DWBC_LAUNCH(hqp_kernel, b->B, TEAM, smem, st, b->d_model, b->d_cfgR, d, 0, 2, nvmax, (const int *)nullptr, (const int *)nullptr);
+            DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1>), b->B, TEAM, smem, st, b->d_model, b->d_cfgR, d, 0, 2, nvmax, (const int *)nullptr, (const int *)nullptr);
         }
         {
             KernelScope ks(b, DWBC_K_REDUCED, st);
