@@ -59,6 +59,7 @@ struct dwbc_batch {
     const uint8_t *lean_flags = nullptr;
     bool lean_kin_pending = false, lean_contact_pending = false;
     int *d_list = nullptr, *d_count = nullptr;
+    int *d_list2 = nullptr;  // QP-active states of the second contact class (d_count[2..3] are its counters)
     int *d_plist = nullptr, *d_pcount = nullptr;  // contact-pattern classes of the one-kernel cycle: lists [2][B], counts [2 streams][2]
     size_t list_off = 0;  // dwbc_batch_cycle_host: the slice's part of d_list and its stream's counter
     int count_slot = 0;
@@ -284,7 +285,10 @@ int launch_lean(dwbc_batch *b, int stages, cudaStream_t st) {
     a.count = b->d_count + b->count_slot;
     // the slice's own region of the class lists: [2][slice size] starting at 2 * (first state of the slice)
     int *plist0 = b->d_plist + 2 * b->list_off, *pcount = b->d_pcount + 2 * b->count_slot;
-    CK(cudaMemsetAsync(a.count, 0, sizeof(int), st));
+    // QP-active states: one list per contact class (hqp_kernel is launched per class, the two-contact class with its dimensions as constants)
+    int *const list1 = a.list, *const count1 = a.count, *const list2 = b->d_list2 + b->list_off, *const count2 = b->d_count + 2 + b->count_slot;
+    CK(cudaMemsetAsync(count1, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(count2, 0, sizeof(int), st));
     CK(cudaMemsetAsync(pcount, 0, 2 * sizeof(int), st));
     {
         KernelScope ks(b, DWBC_K_LEAN, st);
@@ -300,6 +304,8 @@ int launch_lean(dwbc_batch *b, int stages, cudaStream_t st) {
         KernelScope ks(b, DWBC_K_LEAN, st);
         a.plist = plist0 + b->B;
         a.pcount = pcount + 1;
+        a.list = list2;
+        a.count = count2;
         DWBC_LAUNCH((lean_cycle_kernel<S, 6>), lean_grid, TEAM * LEAN_GANG, smem, st, b->d_model, b->d_cfg, b->cfg, b->w, a);
     }
     CK(cudaGetLastError());
@@ -310,15 +316,27 @@ int launch_lean(dwbc_batch *b, int stages, cudaStream_t st) {
             for (int l = 0; l < b->cfg.nlevels; l++) nvmax = b->cfg.tasks[l].dof + RMAX > nvmax ? b->cfg.tasks[l].dof + RMAX : nvmax;
         HqpSmem H(b->w.n, b->w.m, nvmax);
         const size_t hs = sizeof(double) * H.total;
-        CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
-        KernelScope ks(b, DWBC_K_HQP, st);
+        CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
         Work wq = b->w;
         wq.hqp_timing = a.timing;
-        if (b->w.n == 39 && b->w.m == 33 && nvmax == 27 && b->cfg.tlim_set) {  // the headline model and hierarchy: dimensions as compile-time constants
-            CK(cudaFuncSetAttribute(hqp_kernel_t<39, 33, 27, 66>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
-            DWBC_LAUNCH((hqp_kernel_t<39, 33, 27, 66>), b->B, TEAM, hs, st, b->d_model, b->d_cfg, wq, a.hqp, a.redist, nvmax, (const int *)a.list, (const int *)a.count);
-        } else {
-            DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1>), b->B, TEAM, hs, st, b->d_model, b->d_cfg, wq, a.hqp, a.redist, nvmax, (const int *)a.list, (const int *)a.count);
+        const bool spec = b->w.n == 39 && b->w.m == 33 && nvmax == 27 && b->cfg.tlim_set;  // the headline model and hierarchy
+        {
+            KernelScope ks(b, DWBC_K_HQP, st);
+            if (spec) {  // dimensions, row counts and the contact window as compile-time constants
+                CK(cudaFuncSetAttribute(hqp_kernel_t<39, 33, 27, 66, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+                DWBC_LAUNCH((hqp_kernel_t<39, 33, 27, 66, 12>), b->B, TEAM, hs, st, b->d_model, b->d_cfg, wq, a.hqp, a.redist, nvmax, (const int *)list1, (const int *)count1);
+            } else {
+                DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1, -1>), b->B, TEAM, hs, st, b->d_model, b->d_cfg, wq, a.hqp, a.redist, nvmax, (const int *)list1, (const int *)count1);
+            }
+        }
+        {
+            KernelScope ks(b, DWBC_K_HQP, st);
+            if (spec) {
+                CK(cudaFuncSetAttribute(hqp_kernel_t<39, 33, 27, 66, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+                DWBC_LAUNCH((hqp_kernel_t<39, 33, 27, 66, -1>), b->B, TEAM, hs, st, b->d_model, b->d_cfg, wq, a.hqp, a.redist, nvmax, (const int *)list2, (const int *)count2);
+            } else {
+                DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1, -1>), b->B, TEAM, hs, st, b->d_model, b->d_cfg, wq, a.hqp, a.redist, nvmax, (const int *)list2, (const int *)count2);
+            }
         }
     }
     CK(cudaGetLastError());
@@ -436,7 +454,7 @@ dwbc_batch_t *dwbc_batch_create(const dwbc_model_t *m, int batch, int device) {
               dev_alloc(b, &w.status, B) && dev_alloc(b, &w.tau_task, B * mm) && dev_alloc(b, &w.tau_contact, B * mm) &&
               dev_alloc(b, &w.cf_redis, B * RMAX) && dev_alloc(b, &w.active[MAX_LEVELS], B * ACTIVE_WORDS) && dev_alloc(b, &w.qp_iters, B) &&
               dev_alloc(b, &b->d_q, B * (n + 1)) && dev_alloc(b, &b->d_qd, B * n) && dev_alloc(b, &b->d_flags, B * MAX_CONTACTS) &&
-              dev_alloc(b, &b->d_list, B) && dev_alloc(b, &b->d_count, 4) && dev_alloc(b, &b->d_plist, 2 * B) && dev_alloc(b, &b->d_pcount, 8);
+              dev_alloc(b, &b->d_list, B) && dev_alloc(b, &b->d_list2, B) && dev_alloc(b, &b->d_count, 4) && dev_alloc(b, &b->d_plist, 2 * B) && dev_alloc(b, &b->d_pcount, 8);
     if (ok) ok = cuda_ok(cudaMemcpy(b->d_model, &b->hm.dev, sizeof(DevModel), cudaMemcpyHostToDevice), "cudaMemcpy(model)");
     if (!ok) {
         dwbc_batch_destroy(b);
@@ -737,9 +755,9 @@ int dwbc_batch_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, double *
             for (int l = 0; l < b->cfg.nlevels; l++) nvmax = b->cfg.tasks[l].dof + RMAX > nvmax ? b->cfg.tasks[l].dof + RMAX : nvmax;
         HqpSmem L(b->w.n, b->w.m, nvmax);
         size_t smem = sizeof(double) * L.total;
-        CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelScope ks(b, DWBC_K_HQP, st);
-        DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1>), b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0,
+        DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1, -1>), b->B, TEAM, smem, st, b->d_model, b->d_cfg, b->w, (stages & DWBC_SOLVE_HQP) ? 1 : 0,
                     (stages & DWBC_SOLVE_REDIST) ? 1 : 0, nvmax, (const int *)nullptr, (const int *)nullptr);
     }
     if ((stages & DWBC_SOLVE_REDIST_ANALYTIC) && !(stages & DWBC_SOLVE_REDIST)) {
@@ -1379,12 +1397,12 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
             for (int l = 0; l < k; l++) nvmax = c.tasks[l].dof + RMAX > nvmax ? c.tasks[l].dof + RMAX : nvmax;
             HqpSmem L(rn, rm, nvmax);
             size_t smem = sizeof(double) * L.total;
-            CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             // with non-contact levels the redistribution needs torque_task_R_ after their sums: it runs after reduced_nc_kernel
             const int redist_now = ((stages & DWBC_SOLVE_REDIST) && k == c.nlevels) ? 2 : 0;
             if ((stages & DWBC_SOLVE_HQP) || redist_now) {
                 KernelScope ks(b, DWBC_K_HQP, st);
-                DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1>), b->B, TEAM, smem, st, b->d_model, b->d_cfgR, b->wr, (stages & DWBC_SOLVE_HQP) ? 1 : 0, redist_now, nvmax, (const int *)nullptr, (const int *)nullptr);
+                DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1, -1>), b->B, TEAM, smem, st, b->d_model, b->d_cfgR, b->wr, (stages & DWBC_SOLVE_HQP) ? 1 : 0, redist_now, nvmax, (const int *)nullptr, (const int *)nullptr);
             }
         }
     }
@@ -1418,10 +1436,10 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
         const int nvmax = 6 + RMAX;
         HqpSmem L(rn, rm, nvmax);
         size_t smem = sizeof(double) * L.total;
-        CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
             KernelScope ks(b, DWBC_K_HQP, st);
-            DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1>), b->B, TEAM, smem, st, b->d_model, b->d_cfgNC, q, 1, 0, nvmax, (const int *)nullptr, (const int *)nullptr);
+            DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1, -1>), b->B, TEAM, smem, st, b->d_model, b->d_cfgNC, q, 1, 0, nvmax, (const int *)nullptr, (const int *)nullptr);
         }
         {
             KernelScope ks(b, DWBC_K_REDUCED, st);
@@ -1452,10 +1470,10 @@ int dwbc_batch_reduced_solve(dwbc_batch_t *b, int stages, double *tau_grav_dev, 
         const int nvmax = RMAX > 0 ? RMAX : 1;
         HqpSmem L(rn, rm, nvmax);
         size_t smem = sizeof(double) * L.total;
-        CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(hqp_kernel_t<0, 0, 0, -1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
             KernelScope ks(b, DWBC_K_HQP, st);
-            DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1>), b->B, TEAM, smem, st, b->d_model, b->d_cfgR, d, 0, 2, nvmax, (const int *)nullptr, (const int *)nullptr);
+            DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1, -1>), b->B, TEAM, smem, st, b->d_model, b->d_cfgR, d, 0, 2, nvmax, (const int *)nullptr, (const int *)nullptr);
         }
         {
             KernelScope ks(b, DWBC_K_REDUCED, st);

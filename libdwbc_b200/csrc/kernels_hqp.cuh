@@ -196,11 +196,12 @@ __device__ __forceinline__ double team_sum(double v, const GiScratch &S) {
 // dropped.  On return S.dxs holds dx, S.act / S.u the active rows and their multipliers (logical positions < q).
 // Deliberately NOT inlined (instruction-cache footprint, profiles/r01_ncu_summary.md).  Synchronises on entry and exit.
 // boff: offset of this problem's first row in the right-hand-side array b (2m when the torque rows are left out, mt = 0)
-template <int CN, int CM, int CNV, int CMT>
+template <int CN, int CM, int CNV, int CMT, int CC>
 __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, int mt, int nc, int col0, int nv, int use_bt, double isd_t,
                                           double isd_c, int tsplit, int use_pin, int max_iter, double ztol, int boff) {
     if constexpr (CN > 0) n = CN, m = CM, nvmax = CNV;  // dimensions known at compile time: strides and offsets fold into the instructions
     if constexpr (CMT >= 0) mt = CMT;
+    if constexpr (CC > 0) nc = 10 * (CC / 6);  // contact class of the launch: row counts and the contact window are constants
     // Everything is re-derived from the arena base and a few integers: structs passed by reference to a non-inlined function
     // live in local memory, and with most of L1 carved out as shared memory those loads went to L2 (ncu: 20 % L1 hit rate,
     // long-scoreboard the second largest stall of the first team version).
@@ -526,10 +527,11 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
 // rows and  lambda = R^{-1} w  its multipliers.  If lambda >= 0 and every other row is satisfied this is the (unique) optimum
 // of the new sub-problem -- at the cost of about one active-set iteration; otherwise nothing is modified and the caller falls
 // back to a cold gi_solve.  Same team conventions as gi_solve; synchronises on entry and exit.
-template <int CN, int CM, int CNV, int CMT>
+template <int CN, int CM, int CNV, int CMT, int CC>
 __device__ __noinline__ bool gi_warm(double *sm, int n, int m, int nvmax, int mt, int nc, int col0, int nv, int q, int use_bt) {
     if constexpr (CN > 0) n = CN, m = CM, nvmax = CNV;  // dimensions known at compile time: strides and offsets fold into the instructions
     if constexpr (CMT >= 0) mt = CMT;
+    if constexpr (CC > 0) nc = 10 * (CC / 6);  // contact class of the launch: row counts and the contact window are constants
     const HqpSmem L(n, m, nvmax);
     const GiScratch S(sm + L.gi, sm + L.bt);
     const QpView V{sm + L.U, sm + L.AU, L.ldm, L.ldc, m, mt, nc, col0, nv};
@@ -627,11 +629,13 @@ struct LevelOut {
 // solution.  Synchronises on entry and exit.
 // boff / row_shift: the problem's rows start at b[boff] and are reported as rows row_shift.. (a solve without the torque rows: mt = 0,
 // boff = row_shift = 2m keeps the reference's row numbering in the active set).
-template <int CN, int CM, int CNV, int CMT>
+template <int CN, int CM, int CNV, int CMT, int CC>
 __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax, int t, int r, int mt, int nc, uint32_t *active_out, int boff,
                                              int row_shift, int c0, int skip_a) {
     if constexpr (CN > 0) n = CN, m = CM, nvmax = CNV;  // dimensions known at compile time: strides and offsets fold into the instructions
     if constexpr (CMT >= 0) mt = CMT;
+    if constexpr (CC > 0) nc = 10 * (CC / 6);  // contact class of the launch: row counts and the contact window are constants
+    if constexpr (CC > 0) r = CC - 6;
     const HqpSmem L(n, m, nvmax);
     const GiScratch S(sm + L.gi, sm + L.bt);
     const double *b = sm + L.b + boff;
@@ -710,7 +714,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
     const int max_iter = 20 * (nv + 8);
     bool done = false;
     if (t == 0 || r == 0) {
-        GiResult g = gi_solve<CN, CM, CNV, CMT>(sm, n, m, nvmax, mt, nc, c0, nv, 0, 1.0, 1.0, nv, 0, max_iter, zero_row_tol, boff);
+        GiResult g = gi_solve<CN, CM, CNV, CMT, CC>(sm, n, m, nvmax, mt, nc, c0, nv, 0, 1.0, 1.0, nv, 0, max_iter, zero_row_tol, boff);
         out.iters += g.iters;
         out.status = g.status;
         if (tid < nv) xj[tid] = S.dxs[tid];
@@ -720,7 +724,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
         // ---- A: is x_t = 0 attainable?  (looser tolerances: the set may be a thin face inherited from the levels above)
         DWBC_UNROLL(1)
         for (int i = tid; i < mc; i += nt) tolv[i] *= 100.0;
-        GiResult g = gi_solve<CN, CM, CNV, CMT>(sm, n, m, nvmax, mt, nc, c0 + t, r, 0, 1.0, 1.0, r, 0, max_iter, zero_row_tol, boff);
+        GiResult g = gi_solve<CN, CM, CNV, CMT, CC>(sm, n, m, nvmax, mt, nc, c0 + t, r, 0, 1.0, 1.0, r, 0, max_iter, zero_row_tol, boff);
         out.iters += g.iters;
         if (g.status) {
             if (tid < r) xj[t + tid] = S.dxs[tid];
@@ -761,10 +765,10 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
                 for (int j = t; j < nv; j++) s = fma(-V.a(i, j), xs[j], s);
                 bt[i] = s;
             }
-            if (k > 0 && !force_cold && gi_warm<CN, CM, CNV, CMT>(sm, n, m, nvmax, mt, nc, c0, nv, g.q, 1)) {
+            if (k > 0 && !force_cold && gi_warm<CN, CM, CNV, CMT, CC>(sm, n, m, nvmax, mt, nc, c0, nv, g.q, 1)) {
                 out.iters += 1;
             } else {
-                g = gi_solve<CN, CM, CNV, CMT>(sm, n, m, nvmax, mt, nc, c0, nv, 1, 1.0, isd_c, t, 0, max_iter, zero_row_tol, boff);
+                g = gi_solve<CN, CM, CNV, CMT, CC>(sm, n, m, nvmax, mt, nc, c0, nv, 1, 1.0, isd_c, t, 0, max_iter, zero_row_tol, boff);
                 out.iters += g.iters;
             }
             force_cold = false;
@@ -825,7 +829,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
                 bt[i] = s;
                 tolv[i] *= 100.0;
             }
-            GiResult gc = gi_solve<CN, CM, CNV, CMT>(sm, n, m, nvmax, mt, nc, c0 + t, r, 1, 1.0, 1.0, r, 1, max_iter, zero_row_tol, boff);
+            GiResult gc = gi_solve<CN, CM, CNV, CMT, CC>(sm, n, m, nvmax, mt, nc, c0 + t, r, 1, 1.0, 1.0, r, 1, max_iter, zero_row_tol, boff);
             out.iters += gc.iters;
             if (!gc.status) out.status = 0;
             if (tid < r) xj[t + tid] = S.dxs[tid];
@@ -870,11 +874,13 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
 // the right-hand side is b itself).  t = task dof of this level (only to place the answer in S.xj = [0_t; x_c] and, for the few
 // torque rows that end with zero slack, to evaluate the task part of their normal from Ntq in global memory); loose: the 100 times
 // wider row tolerances of stage A.  status 0: x_t = 0 is not attainable (nothing usable is left in S.xj).
-template <int CN, int CM, int CNV, int CMT>
+template <int CN, int CM, int CNV, int CMT, int CC>
 __device__ __noinline__ LevelOut solve_contact_only(double *sm, int n, int m, int nvmax, int t, int r, int mt, int nc, uint32_t *active_out, int cc,
                                                     int *aq_io, int loose, const double *__restrict__ Ntq) {
     if constexpr (CN > 0) n = CN, m = CM, nvmax = CNV;  // dimensions known at compile time: strides and offsets fold into the instructions
     if constexpr (CMT >= 0) mt = CMT;
+    if constexpr (CC > 0) nc = 10 * (CC / 6);  // contact class of the launch: row counts and the contact window are constants
+    if constexpr (CC > 0) r = CC - 6;
     const HqpSmem L(n, m, nvmax);
     const GiScratch S(sm + L.gi, sm + L.bt);
     const double *b = sm + L.b;
@@ -924,7 +930,7 @@ __device__ __noinline__ LevelOut solve_contact_only(double *sm, int n, int m, in
         out.status = 0;
         return out;
     }
-    if (aq >= 0 && gi_warm<CN, CM, CNV, CMT>(sm, n, m, nvmax, mt, nc, cc, r, aq, 0)) {
+    if (aq >= 0 && gi_warm<CN, CM, CNV, CMT, CC>(sm, n, m, nvmax, mt, nc, cc, r, aq, 0)) {
         out.iters = 1;
 #ifdef DWBC_CPU_EMUL
         if (tid == 0 && getenv("DWBC_QP_TRACE")) fprintf(stderr, "contact_only warm t %d q %d\n", t, aq);
@@ -933,7 +939,7 @@ __device__ __noinline__ LevelOut solve_contact_only(double *sm, int n, int m, in
 #ifdef DWBC_CPU_EMUL
         if (tid == 0 && getenv("DWBC_QP_TRACE")) fprintf(stderr, "contact_only cold t %d (kept q %d)\n", t, aq);
 #endif
-        const GiResult g = gi_solve<CN, CM, CNV, CMT>(sm, n, m, nvmax, mt, nc, cc, r, 0, 1.0, 1.0, r, 0, 20 * (r + 8), ztol, 0);
+        const GiResult g = gi_solve<CN, CM, CNV, CMT, CC>(sm, n, m, nvmax, mt, nc, cc, r, 0, 1.0, 1.0, r, 0, 20 * (r + 8), ztol, 0);
         out.iters = g.iters;
         out.status = g.status;
         aq = g.status ? g.q : -1;
@@ -980,7 +986,7 @@ __device__ __noinline__ LevelOut solve_contact_only(double *sm, int n, int m, in
 #define DWBC_HQP_CTAS 7  // states per SM (72 registers); 6 (80 registers) measured slower in both rounds (round 2: 7.18 vs 6.89 ms)
 #endif
 // (Out-of-line warp / team reductions shrink this kernel from 9.7 k to 8.8 k SASS instructions but run slower: 7.33 vs 7.02 ms.)
-template <int CN, int CM, int CNV, int CMT>
+template <int CN, int CM, int CNV, int CMT, int CC>
 __global__ void __launch_bounds__(TEAM, DWBC_HQP_CTAS) hqp_kernel_t(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int redist,
                                                         int nvmax, const int *__restrict__ list, const int *__restrict__ count) {
     DWBC_DYN_SMEM(smem);
@@ -1001,7 +1007,7 @@ __global__ void __launch_bounds__(TEAM, DWBC_HQP_CTAS) hqp_kernel_t(const DevMod
     const bool contact_ok = st & 1;
     const bool task_ok = (st & 8) != 0;  // set by task_space_kernel when hqp = 1
     st &= ~8;
-    const int c = contact_ok ? w.cdof[s] : 0;
+    const int c = CC > 0 ? CC : (contact_ok ? w.cdof[s] : 0);  // (a class launch only lists states with that many contact dof)
     const int r = c > 6 ? c - 6 : 0;
     const int kc = c / 6;
     const int nc = 10 * kc;
@@ -1150,7 +1156,7 @@ __global__ void __launch_bounds__(TEAM, DWBC_HQP_CTAS) hqp_kernel_t(const DevMod
                     aq = -1;
                     lap(23);
                 }
-                lo = solve_contact_only<CN, CM, CNV, CMT>(sm, n, m, nvmax, t, r, mt, nc, aout, TC, &aq, lev ? 1 : 0, lev ? Ntq : nullptr);
+                lo = solve_contact_only<CN, CM, CNV, CMT, CC>(sm, n, m, nvmax, t, r, mt, nc, aout, TC, &aq, lev ? 1 : 0, lev ? Ntq : nullptr);
                 total_iters += lo.iters;
                 lap(24);
             }
@@ -1166,7 +1172,7 @@ __global__ void __launch_bounds__(TEAM, DWBC_HQP_CTAS) hqp_kernel_t(const DevMod
                 aq = -1;  // the solver reuses the storage of the kept factorisation
                 // (Solving on the contact rows alone first and verifying the torque rows afterwards -- they are never active in the headline
                 // workload -- was measured slower: 7.75 vs 7.11 ms per 65 536 states; the row scan is not what bounds this kernel.)
-                lo = solve_level<CN, CM, CNV, CMT>(sm, n, m, nvmax, t, r, mt, nc, aout, 0, 0, TC - t, r > 0 ? 1 : 0);
+                lo = solve_level<CN, CM, CNV, CMT, CC>(sm, n, m, nvmax, t, r, mt, nc, aout, 0, 0, TC - t, r > 0 ? 1 : 0);
                 total_iters += lo.iters;
                 if (lo.slow) st |= 16;
                 lap(26);
