@@ -332,8 +332,8 @@ int launch_lean(dwbc_batch *b, int stages, cudaStream_t st) {
         {
             KernelScope ks(b, DWBC_K_HQP, st);
             if (spec) {
-                CK(cudaFuncSetAttribute(hqp_kernel_t<39, 33, 27, 66, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
-                DWBC_LAUNCH((hqp_kernel_t<39, 33, 27, 66, -1>), b->B, TEAM, hs, st, b->d_model, b->d_cfg, wq, a.hqp, a.redist, nvmax, (const int *)list2, (const int *)count2);
+                CK(cudaFuncSetAttribute(hqp_kernel_t<39, 33, 27, 66, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+                DWBC_LAUNCH((hqp_kernel_t<39, 33, 27, 66, 6>), b->B, TEAM, hs, st, b->d_model, b->d_cfg, wq, a.hqp, a.redist, nvmax, (const int *)list2, (const int *)count2);
             } else {
                 DWBC_LAUNCH((hqp_kernel_t<0, 0, 0, -1, -1>), b->B, TEAM, hs, st, b->d_model, b->d_cfg, wq, a.hqp, a.redist, nvmax, (const int *)list2, (const int *)count2);
             }
