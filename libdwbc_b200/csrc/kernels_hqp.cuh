@@ -212,7 +212,7 @@ __device__ __noinline__ GiResult gi_solve(double *sm, int n, int m, int nvmax, i
     double *rin = sm + L.rin, *Q = sm + L.Q, *R = sm + L.R;
     const int ldq = L.ldq;
     const uint32_t *pin = use_pin ? S.pinw : nullptr;
-    const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
+    const int tid = t_id(), nt = CN > 0 ? TEAM : t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;  // (the specialised launches use TEAM threads)
     const int mc = V.rows();
     double *y = S.y, *u = S.u, *dxs = S.dxs, *dv = S.dv, *zv = S.zv, *rkv = S.rkv, *isds = S.isds, *gcs = S.gcs, *scal = S.scal;
     int *act = S.act, *slot = S.slot, *ired = S.ired;
@@ -537,7 +537,7 @@ __device__ __noinline__ bool gi_warm(double *sm, int n, int m, int nvmax, int mt
     const QpView V{sm + L.U, sm + L.AU, L.ldm, L.ldc, m, mt, nc, col0, nv};
     const double *bt = use_bt ? sm + L.bt : sm + L.b, *tolv = sm + L.tol, *rin = sm + L.rin, *Q = sm + L.Q, *R = sm + L.R;
     const int ldq = L.ldq;
-    const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
+    const int tid = t_id(), nt = CN > 0 ? TEAM : t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;  // (the specialised launches use TEAM threads)
     const int mc = V.rows();
     double *wv = S.dv, *lam = S.rkv, *yn = S.zv;  // scratch vectors of gi_solve, free between calls
     tsync();
@@ -640,7 +640,7 @@ __device__ __noinline__ LevelOut solve_level(double *sm, int n, int m, int nvmax
     const GiScratch S(sm + L.gi, sm + L.bt);
     const double *b = sm + L.b + boff;
     double *tolv = sm + L.tol, *rin = sm + L.rin;
-    const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
+    const int tid = t_id(), nt = CN > 0 ? TEAM : t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;  // (the specialised launches use TEAM threads)
     const int nv = t + r, mc = mt + nc;
     LevelOut out{1, 0, 0};
     const QpView V{sm + L.U, sm + L.AU, L.ldm, L.ldc, m, mt, nc, c0, nv};
@@ -885,7 +885,7 @@ __device__ __noinline__ LevelOut solve_contact_only(double *sm, int n, int m, in
     const GiScratch S(sm + L.gi, sm + L.bt);
     const double *b = sm + L.b;
     double *tolv = sm + L.tol, *nrm = sm + L.bt;
-    const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;
+    const int tid = t_id(), nt = CN > 0 ? TEAM : t_n(), lane = lane_id(), warp = tid >> 5, nw = nt >> 5;  // (the specialised launches use TEAM threads)
     const int mc = mt + nc;
     const QpView V{sm + L.U, sm + L.AU, L.ldm, L.ldc, m, mt, nc, cc, r};
     LevelOut out{1, 0, 0};
@@ -990,7 +990,7 @@ template <int CN, int CM, int CNV, int CMT, int CC>
 __global__ void __launch_bounds__(TEAM, DWBC_HQP_CTAS) hqp_kernel_t(const DevModel *__restrict__ md, const BatchCfg *__restrict__ cfg, Work w, int hqp, int redist,
                                                         int nvmax, const int *__restrict__ list, const int *__restrict__ count) {
     DWBC_DYN_SMEM(smem);
-    const int tid = t_id(), nt = t_n();
+    const int tid = t_id(), nt = CN > 0 ? TEAM : t_n();
     if (list && (int)blockIdx.x >= *count) return;
     const long long s = list ? list[blockIdx.x] : blockIdx.x;
     const int n = CN > 0 ? CN : w.n, m = CN > 0 ? CM : w.m, nb = w.nb;
