@@ -177,7 +177,7 @@ __device__ __forceinline__ void point_jacobian_rb(const uint64_t *anc_s, const d
 // inertia -- run level by level on one warp (`serial_warp`), 27 + 9 FMAs per body.  Same records as rbd_sweeps (RB_R, RB_P, RB_AX,
 // RB_IC).  Synchronises the team.
 __device__ __forceinline__ void rbd_sweeps_lean(const DevModel *__restrict__ md, const double *__restrict__ q, double *rb, int serial_warp, uint64_t *anc_s) {
-    const int tid = t_id(), nt = t_n(), lane = lane_id(), warp = lean::warp_id();
+    const int tid = t_id(), nt = TEAM, lane = lane_id(), warp = lean::warp_id();
     const int nb = md->nb, n = md->n;
     for (int b = tid; b < nb; b += nt) {
         double *bb = rb + b * RB_STRIDE;
@@ -305,7 +305,7 @@ __device__ __forceinline__ bool lean_contact_task_T(const DevModel *__restrict__
                                                     double *sm, const int *cix, long long *tm) {
     using L = LeanSmem<S>;
     constexpr int N = S::N, M = S::M, LDN = S::LDN, LDM = S::LDM, LDT = S::LDT, LDC = S::LDC, TS = S::TS, R = C - 6;
-    const int tid = t_id(), nt = t_n(), warp = lean::warp_id(), lane = lane_id();
+    const int tid = t_id(), nt = TEAM, warp = lean::warp_id(), lane = lane_id();
     double *P = sm + L::R1, *R2 = sm + L::R2, *rb = sm + L::R3, *T = sm + L::R3;
     double *Jbar = R2 + L::oJbar, *Jc = R2 + L::oJc, *X = R2 + L::oX, *Lam = R2 + L::oLam, *Lw = R2 + L::oLw;
     double *V = sm + L::V, *Aug = sm + L::Aug, *Jb6 = sm + L::Jb6, *NwJw = sm + L::NwJw, *Rc = sm + L::Rc;
@@ -637,7 +637,7 @@ template <class S>
 __device__ __noinline__ bool lean_quick_feasible(const BatchCfg *__restrict__ cfg, double *sm, int c, const int *cix, const double *base) {
     using L = LeanSmem<S>;
     constexpr int M = S::M, LDC = S::LDC;
-    const int tid = t_id(), nt = t_n();
+    const int tid = t_id(), nt = TEAM;
     double *Jb6 = sm + L::Jb6, *PC = sm + L::PC, *lf = sm + L::lf, *Rc = sm + L::Rc, *misc = sm + L::misc;
     int &flag = *(int *)(misc + 7);
     if (tid == 0) flag = 1;
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(TEAM * LEAN_GANG, 1) lean_cycle_kernel(const D
     constexpr int N = S::N, M = S::M, NB = S::NB, LDN = S::LDN, LDM = S::LDM, TS = S::TS;
     DWBC_DYN_SMEM(smem);
     double *sm = (double *)smem + (threadIdx.x / TEAM) * L::total;
-    const int tid = t_id(), nt = t_n(), warp = lean::warp_id(), lane = lane_id();
+    const int tid = t_id(), nt = TEAM, warp = lean::warp_id(), lane = lane_id();
     const long long s = a.plist[slot];
     double *P = sm + L::R1, *R2 = sm + L::R2, *rb = sm + L::R3;
     double *Gs = sm + L::Gs, *fs = sm + L::fs, *tgv = sm + L::tg, *tt = sm + L::tt, *base = sm + L::base, *com = sm + L::com, *misc = sm + L::misc;
