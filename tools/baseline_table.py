@@ -39,7 +39,7 @@ for c, label in ROWS:
     cb = d.get("cpu_baseline") or {}
     multi = []
     for n in (2, 4, 8):
-        m = newest(f"r02_bench_n{n}_c4_*.json") if c == "4" else (newest(f"r02_bench_n{n}_*.json", rf"r02_bench_n{n}_[0-9a-f]{{7}}\.json") if c == "2" else None)
+        m = newest(f"r02_bench_n{n}_c4_*.json", rf"r02_bench_n{n}_c4_(final|[0-9a-f]{{7}})\.json") if c == "4" else (newest(f"r02_bench_n{n}_*.json", rf"r02_bench_n{n}_(final|[0-9a-f]{{7}})\.json") if c == "2" else None)
         multi.append(fmt(m["value"]) if m else "")
     r = d["roofline"]
     print(f"| {label} | {cb.get('single_thread_us_per_solve', 0):.0f} | {fmt(cb.get('value'))} ({cb.get('cores')}) | {fmt(d['value'])} ({fmt(d['e2e']['value'])}) | {multi[0]} | {multi[1]} | {multi[2]} | "
